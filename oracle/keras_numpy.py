@@ -1,0 +1,540 @@
+"""NumPy restatement of the Keras 2.2.x layer numerics used by the LongTerm360FoV
+hot path, and of the four canonical model graphs (SURVEY.md section 8a').
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Parity status of this
+file: **parity unpinned** for the Keras layer numerics (Keras/TF1 is not
+installable here and the reference holds no golden vectors); the featuriser
+functions are pinned against the reference's own code via
+``tests/golden/reference_numpy_golden.npz``.
+
+Every function cites the reference call site it follows (paths relative to
+``/root/reference``).  Weight layouts are Keras': LSTM ``kernel (in,4H)``,
+``recurrent_kernel (H,4H)``, ``bias (4H)`` with gate column blocks i,f,c,o;
+ConvLSTM2D ``kernel (kh,kw,Cin,4F)``, ``recurrent_kernel (kh,kw,F,4F)``; Dense
+``kernel (in,out)``; Conv2D ``(kh,kw,Cin,Cout)``; Conv1D ``(k,Cin,Cout)``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+FPS = 30
+
+# --------------------------------------------------------------------------- #
+# activations
+# --------------------------------------------------------------------------- #
+
+
+def hard_sigmoid(x):
+    """Keras backend ``hard_sigmoid``: clip(0.2*x + 0.5, 0, 1).  Default
+    ``recurrent_activation`` of LSTM / ConvLSTM2D in Keras 2.2.x (signature pasted
+    at mycode/FOV_trj_pred_LSTM_concatState.py:110)."""
+    return np.clip(0.2 * x + 0.5, 0.0, 1.0)
+
+
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def _rec_act(name):
+    return {"hard_sigmoid": hard_sigmoid, "sigmoid": sigmoid}[name]
+
+
+def _act(name):
+    if name in (None, "linear"):
+        return lambda v: v
+    if name == "tanh":
+        return np.tanh
+    if name == "relu":
+        return lambda v: np.maximum(v, 0.0)
+    if name == "softmax":
+        return lambda v: softmax(v, axis=-1)
+    raise ValueError(name)
+
+
+def softmax(x, axis=-1):
+    """keras.layers.Softmax(axis=-1) (mycode/convlstm_seq2seq.py:237)."""
+    m = np.max(x, axis=axis, keepdims=True)
+    e = np.exp(x - m)
+    return e / np.sum(e, axis=axis, keepdims=True)
+
+
+# --------------------------------------------------------------------------- #
+# Dense / LSTM
+# --------------------------------------------------------------------------- #
+
+
+def dense(x, kernel, bias, activation=None):
+    """keras.layers.Dense on the last axis (mycode/FoV_seq2seq.py:96-97)."""
+    return _act(activation)(x @ kernel + bias)
+
+
+def lstm_step(x, h, c, kernel, recurrent_kernel, bias, recurrent_activation="hard_sigmoid"):
+    """One Keras LSTMCell step (implementation=1 algebra): gate blocks i,f,c,o."""
+    H = recurrent_kernel.shape[0]
+    ra = _rec_act(recurrent_activation)
+    z = x @ kernel + bias + h @ recurrent_kernel
+    i = ra(z[:, 0 * H:1 * H])
+    f = ra(z[:, 1 * H:2 * H])
+    g = np.tanh(z[:, 2 * H:3 * H])
+    o = ra(z[:, 3 * H:4 * H])
+    c_new = f * c + i * g
+    h_new = o * np.tanh(c_new)
+    return h_new, c_new
+
+
+def lstm(x, kernel, recurrent_kernel, bias, h0=None, c0=None,
+         recurrent_activation="hard_sigmoid"):
+    """keras.layers.LSTM(H, return_sequences=True, return_state=True)
+    (mycode/FoV_seq2seq.py:83-84,93-95).  x: (B,T,in).  Returns (seq, h, c)."""
+    B, T, _ = x.shape
+    H = recurrent_kernel.shape[0]
+    h = np.zeros((B, H), x.dtype) if h0 is None else h0
+    c = np.zeros((B, H), x.dtype) if c0 is None else c0
+    seq = np.zeros((B, T, H), x.dtype)
+    for t in range(T):
+        h, c = lstm_step(x[:, t], h, c, kernel, recurrent_kernel, bias, recurrent_activation)
+        seq[:, t] = h
+    return seq, h, c
+
+
+# --------------------------------------------------------------------------- #
+# convolutions (channels-last, TF 'same' padding)
+# --------------------------------------------------------------------------- #
+
+
+def _same_pads(k, d):
+    total = (k - 1) * d
+    lo = total // 2
+    return lo, total - lo
+
+
+def conv2d_same(x, kernel, bias=None, dilation=(1, 1)):
+    """TF/Keras conv2d, stride 1, padding='same', NHWC, kernel (kh,kw,Cin,Cout).
+    It is a cross-correlation (no kernel flip), as in TF."""
+    kh, kw, cin, cout = kernel.shape
+    B, H, W, C = x.shape
+    assert C == cin
+    dh, dw = dilation
+    pt, pb = _same_pads(kh, dh)
+    pl, pr = _same_pads(kw, dw)
+    xp = np.pad(x, ((0, 0), (pt, pb), (pl, pr), (0, 0)))
+    out = np.zeros((B, H, W, cout), np.result_type(x, kernel))
+    for i in range(kh):
+        for j in range(kw):
+            patch = xp[:, i * dh:i * dh + H, j * dw:j * dw + W, :]
+            out += patch @ kernel[i, j]
+    if bias is not None:
+        out = out + bias
+    return out
+
+
+def conv2d(x, kernel, bias, activation=None, dilation=(1, 1)):
+    """keras.layers.Conv2D(padding='same') (mycode/convlstm_seq2seq.py:175-181)."""
+    return _act(activation)(conv2d_same(x, kernel, bias, dilation))
+
+
+def conv1d(x, kernel, bias, activation=None):
+    """keras.layers.Conv1D(padding='same') (mycode/convlstm_seq2seq.py:184-189).
+    x: (B,L,Cin), kernel (k,Cin,Cout)."""
+    y = conv2d_same(x[:, None], kernel[None], bias)[:, 0]
+    return _act(activation)(y)
+
+
+def convlstm2d_step(x, h, c, kernel, recurrent_kernel, bias, dilation=(1, 1),
+                    recurrent_activation="hard_sigmoid", dropout_masks=None):
+    """One Keras ConvLSTM2DCell step.  Input conv: user padding 'same', given
+    dilation, with bias; recurrent conv: always 'same', stride 1, no dilation, no
+    bias.  ``dropout_masks`` (4 arrays, one per gate, already scaled by 1/(1-p)) is
+    the training-time input dropout of mycode/others_LSTM_span_whole.py:89."""
+    F = recurrent_kernel.shape[-1] // 4
+    ra = _rec_act(recurrent_activation)
+    if dropout_masks is None:
+        zx = conv2d_same(x, kernel, bias, dilation)
+    else:
+        zx = np.concatenate([
+            conv2d_same(x * dropout_masks[g], kernel[..., g * F:(g + 1) * F],
+                        bias[g * F:(g + 1) * F], dilation) for g in range(4)], axis=-1)
+    z = zx + conv2d_same(h, recurrent_kernel, None)
+    i = ra(z[..., 0 * F:1 * F])
+    f = ra(z[..., 1 * F:2 * F])
+    g = np.tanh(z[..., 2 * F:3 * F])
+    o = ra(z[..., 3 * F:4 * F])
+    c_new = f * c + i * g
+    h_new = o * np.tanh(c_new)
+    return h_new, c_new
+
+
+def convlstm2d(x, kernel, recurrent_kernel, bias, h0=None, c0=None, dilation=(1, 1),
+               recurrent_activation="hard_sigmoid", dropout_masks=None):
+    """keras.layers.ConvLSTM2D(F, padding='same', return_sequences=True,
+    return_state=True) (mycode/others_LSTM_span_whole.py:88-100,
+    mycode/convlstm_seq2seq.py:100-126).  x: (B,T,H,W,Cin)."""
+    B, T, Hh, Ww, _ = x.shape
+    F = recurrent_kernel.shape[-1] // 4
+    h = np.zeros((B, Hh, Ww, F), x.dtype) if h0 is None else h0
+    c = np.zeros((B, Hh, Ww, F), x.dtype) if c0 is None else c0
+    seq = np.zeros((B, T, Hh, Ww, F), x.dtype)
+    for t in range(T):
+        h, c = convlstm2d_step(x[:, t], h, c, kernel, recurrent_kernel, bias, dilation,
+                               recurrent_activation, dropout_masks)
+        seq[:, t] = h
+    return seq, h, c
+
+
+# --------------------------------------------------------------------------- #
+# featuriser / re-sampler (pure NumPy in the reference)
+# --------------------------------------------------------------------------- #
+
+
+def get_gt_target_xyz(y):
+    """mycode/utility.py:483-500: per-second mean and population variance of
+    x,y,z.  (N,T,90) interleaved xyz or (N,T,30,3) -> (N,T,6)."""
+    if y.shape[-1] == 3:
+        assert y.ndim == 4
+        tx, ty, tz = y[..., 0], y[..., 1], y[..., 2]
+    else:
+        assert y.shape[-1] == 3 * FPS and y.ndim == 3
+        tx, ty, tz = y[:, :, 0::3], y[:, :, 1::3], y[:, :, 2::3]
+    parts = [np.mean(tx, -1), np.mean(ty, -1), np.mean(tz, -1),
+             np.var(tx, -1), np.var(ty, -1), np.var(tz, -1)]
+    return np.stack(parts, axis=-1)
+
+
+def get_gt_target_xyz_oth(y):
+    """mycode/utility.py:505-517: (N,T,U,30,3) -> (N,T,U,6)."""
+    tx, ty, tz = y[..., 0], y[..., 1], y[..., 2]
+    parts = [np.mean(tx, -1), np.mean(ty, -1), np.mean(tz, -1),
+             np.var(tx, -1), np.var(ty, -1), np.var(tz, -1)]
+    return np.stack(parts, axis=-1)
+
+
+def gaussian_resample(mu, var, noise, mode="sqrt_floor"):
+    """Gaussian sample-and-refeed with the standard-normal draw made explicit.
+    mu,var: (B,3); noise: (B,30,3) ~ N(0,1).  Returns (B,30,3) frames.
+    mode 'sqrt_floor': mycode/utility.py:73-80 (var<0 -> 1e-3, std=sqrt(var));
+    mode 'sqrt': mycode/others_LSTM_span_whole.py:64-69 (std = sqrt(var));
+    mode 'var_as_std': mycode/convlstm_seq2seq.py:51-58 (std = var, as written)."""
+    if mode == "sqrt_floor":
+        v = np.where(var < 0, 1e-3, var)
+        std = np.sqrt(v)
+    elif mode == "sqrt":
+        std = np.sqrt(var)
+    elif mode == "var_as_std":
+        std = var
+    else:
+        raise ValueError(mode)
+    return mu[:, None, :] + std[:, None, :] * noise
+
+
+def reshape2second_stacks(per_video_db, collapse_user=False, stride=10, running_length=10):
+    """mycode/utility.py:264-305 (purelly_testing=False): sliding windows of
+    ``running_length`` seconds with stride ``stride``; future = windows shifted by
+    running_length//stride; decoder input = [last past second, future[:-1]]."""
+    L = running_length
+    n_tok = per_video_db.shape[-1]
+    assert per_video_db.shape[1] >= 2 * L
+    shift = L // stride
+    nrows = (per_video_db.shape[1] - L) // stride + 1
+    idx = stride * np.arange(nrows)[:, None] + np.arange(L)
+    win = per_video_db[:, idx, :].transpose(1, 0, 2, 3)        # (nrows, users, L, tok)
+    fut = win[shift:]
+    past = win[:-shift]
+    last = past[:, :, -1:, :]
+    fut_in = np.concatenate((last, fut[:, :, :-1, :]), axis=2)
+    if collapse_user:
+        return (past.reshape(-1, L, n_tok), fut.reshape(-1, L, n_tok),
+                fut_in.reshape(-1, L, n_tok))
+    return (past.transpose(1, 0, 2, 3), fut.transpose(1, 0, 2, 3),
+            fut_in.transpose(1, 0, 2, 3))
+
+
+# --------------------------------------------------------------------------- #
+# losses
+# --------------------------------------------------------------------------- #
+
+
+def mse(y_true, y_pred):
+    """Keras 'mean_squared_error' reduced by fit(): mean over every element
+    (mycode/FoV_seq2seq.py:103; mycode/cost.py:20-29 with add_xyz_sum1=False)."""
+    return float(np.mean((y_pred - y_true) ** 2))
+
+
+def gauss_nll(y_true, y_pred, running_length=10, fps=FPS, eps=1e-7):
+    """mycode/cost.py:138-187 ``likelihood_loss``.  y_true (B,T,90) interleaved
+    xyz frames, y_pred (B,T,6)=[ux,uy,uz,varx,vary,varz]."""
+    total = 0.0
+    for a in range(3):
+        u = y_pred[:, :, a:a + 1]
+        v = np.clip(np.abs(y_pred[:, :, 3 + a:4 + a]), 1e-4, 2.0)
+        x = y_true[:, :, a::3]
+        l = np.log(v + eps) + (x - u) ** 2 / (v + eps)
+        l = np.clip(l, -2000.0, 2000.0)
+        total = total + l
+    loss = np.mean(np.sum(np.sum(total, axis=2), axis=1))
+    return float(loss / running_length / fps)
+
+
+def categorical_crossentropy(y_true, y_pred, eps=1e-7):
+    """Keras 'categorical_crossentropy' on probabilities, last axis = classes
+    (mycode/convlstm_heatmap.py:281): renormalise, clip to [eps,1-eps], -sum t*log p,
+    mean over the remaining axes."""
+    p = y_pred / np.sum(y_pred, axis=-1, keepdims=True)
+    p = np.clip(p, eps, 1.0 - eps)
+    return float(np.mean(-np.sum(y_true * np.log(p), axis=-1)))
+
+
+# --------------------------------------------------------------------------- #
+# optimisers (Keras forms)
+# --------------------------------------------------------------------------- #
+
+
+def adam_step(p, g, m, v, t, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7):
+    """Keras 2.2 Adam.get_updates: lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
+    p -= lr_t * m / (sqrt(v) + eps)  (eps OUTSIDE the bias correction).  t is the
+    1-based iteration.  ('Adam' string default, mycode/FoV_seq2seq.py:103)."""
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    lr_t = lr * np.sqrt(1 - beta2 ** t) / (1 - beta1 ** t)
+    p = p - lr_t * m / (np.sqrt(v) + eps)
+    return p, m, v
+
+
+def rmsprop_step(p, g, a, lr=1e-3, rho=0.9, eps=1e-7):
+    """Keras 2.2 RMSprop.get_updates ('RMSprop' string default,
+    mycode/convlstm_seq2seq.py:287)."""
+    a = rho * a + (1 - rho) * g * g
+    p = p - lr * g / (np.sqrt(a) + eps)
+    return p, a
+
+
+# --------------------------------------------------------------------------- #
+# initialisers (from-scratch loss curves only)
+# --------------------------------------------------------------------------- #
+
+
+def glorot_uniform(rng, shape, dtype=np.float32):
+    """Keras glorot_uniform: fan_in/fan_out use the receptive field for conv kernels."""
+    if len(shape) == 2:
+        fan_in, fan_out = shape
+    else:
+        rf = int(np.prod(shape[:-2]))
+        fan_in, fan_out = shape[-2] * rf, shape[-1] * rf
+    lim = np.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, size=shape).astype(dtype)
+
+
+def orthogonal(rng, shape, dtype=np.float32):
+    """Keras Orthogonal(gain=1): SVD of a normal matrix, flattened over leading dims."""
+    rows = int(np.prod(shape[:-1]))
+    cols = shape[-1]
+    a = rng.normal(0.0, 1.0, (rows, cols))
+    u, _, vt = np.linalg.svd(a, full_matrices=False)
+    q = u if u.shape == (rows, cols) else vt
+    return q.reshape(shape).astype(dtype)
+
+
+def lstm_bias(units, dtype=np.float32):
+    """zeros with the forget block = 1 (unit_forget_bias=True)."""
+    b = np.zeros(4 * units, dtype)
+    b[units:2 * units] = 1.0
+    return b
+
+
+def init_lstm(rng, in_dim, units, prefix, out):
+    out[prefix + "/kernel"] = glorot_uniform(rng, (in_dim, 4 * units))
+    out[prefix + "/recurrent_kernel"] = orthogonal(rng, (units, 4 * units))
+    out[prefix + "/bias"] = lstm_bias(units)
+
+
+def init_convlstm(rng, kh, kw, cin, filters, prefix, out):
+    out[prefix + "/kernel"] = glorot_uniform(rng, (kh, kw, cin, 4 * filters))
+    out[prefix + "/recurrent_kernel"] = orthogonal(rng, (kh, kw, filters, 4 * filters))
+    out[prefix + "/bias"] = lstm_bias(filters)
+
+
+def init_dense(rng, in_dim, out_dim, prefix, out):
+    out[prefix + "/kernel"] = glorot_uniform(rng, (in_dim, out_dim))
+    out[prefix + "/bias"] = np.zeros(out_dim, np.float32)
+
+
+def init_conv(rng, kshape, prefix, out):
+    out[prefix + "/kernel"] = glorot_uniform(rng, kshape)
+    out[prefix + "/bias"] = np.zeros(kshape[-1], np.float32)
+
+
+# --------------------------------------------------------------------------- #
+# canonical model graphs (SURVEY.md 8a')
+# --------------------------------------------------------------------------- #
+
+
+def init_fov_seq2seq(seed=1, num_encoder_tokens=90, num_decoder_tokens=6, latent_dim=64):
+    """Weights of M1 (num_encoder_tokens=90) / M2 (=6)."""
+    rng = np.random.default_rng(seed)
+    w = {}
+    init_lstm(rng, num_encoder_tokens, latent_dim, "encoder", w)
+    init_lstm(rng, num_decoder_tokens, latent_dim, "decoder", w)
+    init_dense(rng, latent_dim, num_decoder_tokens, "decoder_dense", w)
+    return w
+
+
+def fov_seq2seq_forward(w, enc_in, dec_in, teacher_forcing=True, decoder_no_init_state=False,
+                        recurrent_activation="hard_sigmoid", steps=None):
+    """M1/M2.  Teacher forcing: mycode/FoV_seq2seq.py:82-97 (dec_in (B,T,6)).
+    Autoregressive: mycode/FoV_seq2seq.py:154-178 and the in-graph form
+    mycode/FoV_seq2seq_no_teac_forc.py:88-129 (dec_in (B,1,6), output re-fed).
+    ``decoder_no_init_state`` is the ablation at FoV_seq2seq_no_teac_forc.py:29,98-101
+    (zero decoder state at step 0)."""
+    _, h, c = lstm(enc_in, w["encoder/kernel"], w["encoder/recurrent_kernel"], w["encoder/bias"],
+                   recurrent_activation=recurrent_activation)
+    if decoder_no_init_state:
+        h, c = np.zeros_like(h), np.zeros_like(c)
+    if teacher_forcing:
+        seq, _, _ = lstm(dec_in, w["decoder/kernel"], w["decoder/recurrent_kernel"],
+                         w["decoder/bias"], h, c, recurrent_activation)
+        return dense(seq, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+    T = steps if steps is not None else 10
+    x = dec_in[:, 0]
+    outs = []
+    for _ in range(T):
+        h, c = lstm_step(x, h, c, w["decoder/kernel"], w["decoder/recurrent_kernel"],
+                         w["decoder/bias"], recurrent_activation)
+        y = dense(h, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+        outs.append(y)
+        x = y
+    return np.stack(outs, axis=1)
+
+
+def init_others_lstm_span_whole(seed=1, num_user=34, kernel_size=5, latent_dim=64,
+                                oth_filters=(32, 16, 8), flat_dense=256):
+    """Weights of M3, the canonical concat-state model (SURVEY.md hazard 2)."""
+    rng = np.random.default_rng(seed)
+    w = {}
+    cin = 6
+    for l, f in enumerate(oth_filters):
+        init_convlstm(rng, 1, kernel_size, cin, f, "oth_convlstm%d" % l, w)
+        cin = f
+    flat = (num_user - 1) * sum(oth_filters)
+    init_dense(rng, flat, (num_user - 1) * 6, "oth_recon_dense", w)
+    init_dense(rng, flat, flat_dense, "oth_flat_dense", w)
+    init_lstm(rng, 6, latent_dim, "encoder", w)
+    init_lstm(rng, 6, latent_dim, "decoder", w)
+    init_dense(rng, latent_dim, 6, "encoder_dense", w)
+    init_dense(rng, latent_dim + flat_dense, 6, "decoder_dense", w)
+    return w
+
+
+def others_convlstm_stack(w, x, prefix="oth_convlstm", n_layers=3, h0c0=None, dilation=(1, 1),
+                          recurrent_activation="hard_sigmoid"):
+    """Three stacked ConvLSTM2D layers, channel-concat of their sequences
+    (mycode/others_LSTM_span_whole.py:88-102).  Returns (concat_seq, [(h,c)]*3)."""
+    seqs, states = [], []
+    cur = x
+    for l in range(n_layers):
+        p = "%s%d" % (prefix, l)
+        h0, c0 = (None, None) if h0c0 is None else h0c0[l]
+        cur, h, c = convlstm2d(cur, w[p + "/kernel"], w[p + "/recurrent_kernel"], w[p + "/bias"],
+                               h0, c0, dilation, recurrent_activation)
+        seqs.append(cur)
+        states.append((h, c))
+    return np.concatenate(seqs, axis=-1), states
+
+
+def others_lstm_span_whole_forward(w, enc_in, oth_in, dec_in, recurrent_activation="hard_sigmoid"):
+    """M3 forward.  enc_in (B,10,6), oth_in (B,20,1,33,6), dec_in (B,1,6) ->
+    [decoder_outputs (B,10,6), decoder_outputs_oth (B,20,198), encoder_reconstruct_tar (B,10,6)]
+    (mycode/others_LSTM_span_whole.py:80-132,226-349 with use_fclstm_tar=True and the
+    intended nesting of mycode/others_LSTM_span_whole_attention.py:233-263)."""
+    B, Tenc = enc_in.shape[:2]
+    Tall = oth_in.shape[1]
+    Tdec = Tall - Tenc
+    oth_seq, _ = others_convlstm_stack(w, oth_in, recurrent_activation=recurrent_activation)
+    flat = oth_seq.reshape(B, Tall, -1)
+    r_oth = dense(flat, w["oth_recon_dense/kernel"], w["oth_recon_dense/bias"])
+    enc_seq, h, c = lstm(enc_in, w["encoder/kernel"], w["encoder/recurrent_kernel"],
+                         w["encoder/bias"], recurrent_activation=recurrent_activation)
+    r_tar = dense(enc_seq, w["encoder_dense/kernel"], w["encoder_dense/bias"], "tanh")
+    x = dec_in[:, 0]
+    outs = []
+    for t in range(Tdec):
+        h, c = lstm_step(x, h, c, w["decoder/kernel"], w["decoder/recurrent_kernel"],
+                         w["decoder/bias"], recurrent_activation)
+        s = dense(flat[:, Tenc + t], w["oth_flat_dense/kernel"], w["oth_flat_dense/bias"])
+        y = dense(np.concatenate([h, s], axis=1), w["decoder_dense/kernel"],
+                  w["decoder_dense/bias"])
+        outs.append(y)
+        x = y
+    return [np.stack(outs, axis=1), r_oth, r_tar]
+
+
+def init_convlstm_seq2seq(seed=1, in_ch=30, filters=(32, 16, 8), kernel_size=5,
+                          head=(512, 1024, 30), head_kind="conv2d", head_kernel=None,
+                          flat_dim=None):
+    """Weights of M4 (heatmap form: head_kind='conv2d'; trajectory form: 'conv1d'
+    with kernel 7, or 'dense')."""
+    rng = np.random.default_rng(seed)
+    w = {}
+    for side in ("enc", "dec"):
+        cin = in_ch
+        for l, f in enumerate(filters):
+            init_convlstm(rng, kernel_size, kernel_size, cin, f, "%s_convlstm%d" % (side, l), w)
+            cin = f
+    cat = sum(filters)
+    if head_kind == "conv2d":
+        cin = cat
+        for l, f in enumerate(head):
+            init_conv(rng, (kernel_size, kernel_size, cin, f), "head_conv%d" % l, w)
+            cin = f
+    elif head_kind == "conv1d":
+        cin = cat
+        k = head_kernel or 7
+        for l, f in enumerate(head):
+            init_conv(rng, (k, cin, f), "head_conv%d" % l, w)
+            cin = f
+    else:
+        init_dense(rng, flat_dim, 6, "head_dense", w)
+    return w
+
+
+def convlstm_seq2seq_forward(w, enc_in, dec_in, head_kind="conv2d", steps=10, dilation=(1, 1),
+                             recurrent_activation="hard_sigmoid"):
+    """M4 forward (mycode/convlstm_seq2seq.py:100-126,146-165,209-281).
+    heatmap form: enc_in (B,10,36,18,30), dec_in (B,1,36,18,30) -> (B,10,36,18,30);
+    trajectory forms: enc_in (B,10,1,30,3), dec_in (B,1,1,30,3) ->
+    conv1d head (B,10,1,30,3) (last Conv1D has softmax, :188-189) or dense head
+    (B,10,6) with enc_in (B,10,1,1,6) (input_mean_var)."""
+    B = enc_in.shape[0]
+    _, states = others_convlstm_stack(w, enc_in, prefix="enc_convlstm", dilation=dilation,
+                                      recurrent_activation=recurrent_activation)
+    x = dec_in[:, 0]
+    outs = []
+    for _ in range(steps):
+        hs = []
+        cur = x
+        new_states = []
+        for l in range(3):
+            p = "dec_convlstm%d" % l
+            h, c = convlstm2d_step(cur, states[l][0], states[l][1], w[p + "/kernel"],
+                                   w[p + "/recurrent_kernel"], w[p + "/bias"], dilation,
+                                   recurrent_activation)
+            new_states.append((h, c))
+            hs.append(h)
+            cur = h
+        states = new_states
+        d = np.concatenate(hs, axis=-1)                     # (B,H,W,56)
+        if head_kind == "conv2d":
+            y = conv2d(d, w["head_conv0/kernel"], w["head_conv0/bias"], "relu")
+            y = conv2d(y, w["head_conv1/kernel"], w["head_conv1/bias"], "relu")
+            y = conv2d(y, w["head_conv2/kernel"], w["head_conv2/bias"], "relu")
+            y = softmax(y, -1)
+            x = y
+        elif head_kind == "conv1d":
+            y = conv1d(d[:, 0], w["head_conv0/kernel"], w["head_conv0/bias"], "relu")
+            y = conv1d(y, w["head_conv1/kernel"], w["head_conv1/bias"], "relu")
+            y = conv1d(y, w["head_conv2/kernel"], w["head_conv2/bias"], "softmax")
+            y = y[:, None]
+            x = y
+        else:
+            y = dense(d[:, 0].reshape(B, -1), w["head_dense/kernel"], w["head_dense/bias"])
+            x = y[:, None, None, :]
+        outs.append(y)
+    return np.stack(outs, axis=1)

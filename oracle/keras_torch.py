@@ -1,0 +1,293 @@
+"""torch-CPU restatement of the same Keras 2.2.x graphs as ``keras_numpy`` —
+the second, independent restatement (F.conv2d / F.linear / autograd instead of
+NumPy loops).  It supplies gradients (autograd) for the BPTT parity tests and is
+the timed CPU baseline of ``bench.py`` (a Keras-equivalent stand-in: Keras/TF1
+cannot be installed here).
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  **parity unpinned** for
+the Keras layer numerics; anchored by agreement with ``keras_numpy`` (1e-6),
+``torch.nn.LSTM`` (sigmoid mode), known-answer cases and finite differences.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+FPS = 30
+
+
+def hard_sigmoid(x):
+    return torch.clamp(0.2 * x + 0.5, 0.0, 1.0)
+
+
+def _rec_act(name):
+    return {"hard_sigmoid": hard_sigmoid, "sigmoid": torch.sigmoid}[name]
+
+
+def _act(name):
+    if name in (None, "linear"):
+        return lambda v: v
+    if name == "tanh":
+        return torch.tanh
+    if name == "relu":
+        return torch.relu
+    if name == "softmax":
+        return lambda v: torch.softmax(v, dim=-1)
+    raise ValueError(name)
+
+
+def to_torch(w, dtype=torch.float64, requires_grad=False):
+    out = {}
+    for k, v in w.items():
+        t = torch.tensor(np.asarray(v), dtype=dtype)
+        t.requires_grad_(requires_grad)
+        out[k] = t
+    return out
+
+
+def dense(x, kernel, bias, activation=None):
+    return _act(activation)(x @ kernel + bias)
+
+
+def lstm_step(x, h, c, kernel, rk, bias, ra="hard_sigmoid"):
+    H = rk.shape[0]
+    a = _rec_act(ra)
+    z = x @ kernel + bias + h @ rk
+    i, f, g, o = a(z[:, :H]), a(z[:, H:2 * H]), torch.tanh(z[:, 2 * H:3 * H]), a(z[:, 3 * H:])
+    c = f * c + i * g
+    return o * torch.tanh(c), c
+
+
+def lstm(x, kernel, rk, bias, h0=None, c0=None, ra="hard_sigmoid"):
+    B, T, _ = x.shape
+    H = rk.shape[0]
+    h = x.new_zeros(B, H) if h0 is None else h0
+    c = x.new_zeros(B, H) if c0 is None else c0
+    seq = []
+    for t in range(T):
+        h, c = lstm_step(x[:, t], h, c, kernel, rk, bias, ra)
+        seq.append(h)
+    return torch.stack(seq, 1), h, c
+
+
+def conv2d_same(x, kernel, bias=None, dilation=(1, 1)):
+    """NHWC in/out, kernel (kh,kw,Cin,Cout); TF 'same' (asymmetric for even k)."""
+    kh, kw = kernel.shape[:2]
+    dh, dw = dilation
+    th, tw = (kh - 1) * dh, (kw - 1) * dw
+    xp = F.pad(x.permute(0, 3, 1, 2), (tw // 2, tw - tw // 2, th // 2, th - th // 2))
+    y = F.conv2d(xp, kernel.permute(3, 2, 0, 1), bias, dilation=dilation)
+    return y.permute(0, 2, 3, 1)
+
+
+def conv2d(x, kernel, bias, activation=None, dilation=(1, 1)):
+    return _act(activation)(conv2d_same(x, kernel, bias, dilation))
+
+
+def conv1d(x, kernel, bias, activation=None):
+    return _act(activation)(conv2d_same(x[:, None], kernel[None], bias)[:, 0])
+
+
+def convlstm2d_step(x, h, c, kernel, rk, bias, dilation=(1, 1), ra="hard_sigmoid",
+                    dropout_masks=None):
+    Fh = rk.shape[-1] // 4
+    a = _rec_act(ra)
+    if dropout_masks is None:
+        zx = conv2d_same(x, kernel, bias, dilation)
+    else:
+        zx = torch.cat([conv2d_same(x * dropout_masks[g], kernel[..., g * Fh:(g + 1) * Fh],
+                                    bias[g * Fh:(g + 1) * Fh], dilation) for g in range(4)], -1)
+    z = zx + conv2d_same(h, rk)
+    i, f = a(z[..., :Fh]), a(z[..., Fh:2 * Fh])
+    g, o = torch.tanh(z[..., 2 * Fh:3 * Fh]), a(z[..., 3 * Fh:])
+    c = f * c + i * g
+    return o * torch.tanh(c), c
+
+
+def convlstm2d(x, kernel, rk, bias, h0=None, c0=None, dilation=(1, 1), ra="hard_sigmoid",
+               dropout_masks=None):
+    B, T, Hh, Ww, _ = x.shape
+    Fh = rk.shape[-1] // 4
+    h = x.new_zeros(B, Hh, Ww, Fh) if h0 is None else h0
+    c = x.new_zeros(B, Hh, Ww, Fh) if c0 is None else c0
+    seq = []
+    for t in range(T):
+        h, c = convlstm2d_step(x[:, t], h, c, kernel, rk, bias, dilation, ra, dropout_masks)
+        seq.append(h)
+    return torch.stack(seq, 1), h, c
+
+
+def convlstm_stack(w, x, prefix, h0c0=None, dilation=(1, 1), ra="hard_sigmoid", n_layers=3):
+    seqs, states = [], []
+    cur = x
+    for l in range(n_layers):
+        p = "%s%d" % (prefix, l)
+        h0, c0 = (None, None) if h0c0 is None else h0c0[l]
+        cur, h, c = convlstm2d(cur, w[p + "/kernel"], w[p + "/recurrent_kernel"], w[p + "/bias"],
+                               h0, c0, dilation, ra)
+        seqs.append(cur)
+        states.append((h, c))
+    return torch.cat(seqs, -1), states
+
+
+# ------------------------------- losses ----------------------------------- #
+
+
+def mse(y_true, y_pred):
+    return torch.mean((y_pred - y_true) ** 2)
+
+
+def gauss_nll(y_true, y_pred, running_length=10, fps=FPS, eps=1e-7):
+    total = 0.0
+    for a in range(3):
+        u = y_pred[:, :, a:a + 1]
+        v = torch.clamp(torch.abs(y_pred[:, :, 3 + a:4 + a]), 1e-4, 2.0)
+        x = y_true[:, :, a::3]
+        l = torch.log(v + eps) + (x - u) ** 2 / (v + eps)
+        total = total + torch.clamp(l, -2000.0, 2000.0)
+    return torch.mean(total.sum(2).sum(1)) / running_length / fps
+
+
+def categorical_crossentropy(y_true, y_pred, eps=1e-7):
+    p = y_pred / y_pred.sum(-1, keepdim=True)
+    p = torch.clamp(p, eps, 1.0 - eps)
+    return torch.mean(-(y_true * torch.log(p)).sum(-1))
+
+
+# ------------------------------- models ----------------------------------- #
+
+
+def fov_seq2seq_forward(w, enc_in, dec_in, teacher_forcing=True, decoder_no_init_state=False,
+                        ra="hard_sigmoid", steps=10):
+    _, h, c = lstm(enc_in, w["encoder/kernel"], w["encoder/recurrent_kernel"], w["encoder/bias"],
+                   ra=ra)
+    if decoder_no_init_state:
+        h, c = torch.zeros_like(h), torch.zeros_like(c)
+    if teacher_forcing:
+        seq, _, _ = lstm(dec_in, w["decoder/kernel"], w["decoder/recurrent_kernel"],
+                         w["decoder/bias"], h, c, ra)
+        return dense(seq, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+    x = dec_in[:, 0]
+    outs = []
+    for _ in range(steps):
+        h, c = lstm_step(x, h, c, w["decoder/kernel"], w["decoder/recurrent_kernel"],
+                         w["decoder/bias"], ra)
+        y = dense(h, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+        outs.append(y)
+        x = y
+    return torch.stack(outs, 1)
+
+
+def others_lstm_span_whole_forward(w, enc_in, oth_in, dec_in, ra="hard_sigmoid"):
+    B, Tenc = enc_in.shape[:2]
+    Tall = oth_in.shape[1]
+    oth_seq, _ = convlstm_stack(w, oth_in, "oth_convlstm", ra=ra)
+    flat = oth_seq.reshape(B, Tall, -1)
+    r_oth = dense(flat, w["oth_recon_dense/kernel"], w["oth_recon_dense/bias"])
+    enc_seq, h, c = lstm(enc_in, w["encoder/kernel"], w["encoder/recurrent_kernel"],
+                         w["encoder/bias"], ra=ra)
+    r_tar = dense(enc_seq, w["encoder_dense/kernel"], w["encoder_dense/bias"], "tanh")
+    s_all = dense(flat[:, Tenc:], w["oth_flat_dense/kernel"], w["oth_flat_dense/bias"])
+    x = dec_in[:, 0]
+    outs = []
+    for t in range(Tall - Tenc):
+        h, c = lstm_step(x, h, c, w["decoder/kernel"], w["decoder/recurrent_kernel"],
+                         w["decoder/bias"], ra)
+        y = dense(torch.cat([h, s_all[:, t]], 1), w["decoder_dense/kernel"],
+                  w["decoder_dense/bias"])
+        outs.append(y)
+        x = y
+    return [torch.stack(outs, 1), r_oth, r_tar]
+
+
+def convlstm_seq2seq_forward(w, enc_in, dec_in, head_kind="conv2d", steps=10, dilation=(1, 1),
+                             ra="hard_sigmoid"):
+    B = enc_in.shape[0]
+    _, states = convlstm_stack(w, enc_in, "enc_convlstm", dilation=dilation, ra=ra)
+    x = dec_in[:, 0]
+    outs = []
+    for _ in range(steps):
+        hs, new_states, cur = [], [], x
+        for l in range(3):
+            p = "dec_convlstm%d" % l
+            h, c = convlstm2d_step(cur, states[l][0], states[l][1], w[p + "/kernel"],
+                                   w[p + "/recurrent_kernel"], w[p + "/bias"], dilation, ra)
+            new_states.append((h, c))
+            hs.append(h)
+            cur = h
+        states = new_states
+        d = torch.cat(hs, -1)
+        if head_kind == "conv2d":
+            y = conv2d(d, w["head_conv0/kernel"], w["head_conv0/bias"], "relu")
+            y = conv2d(y, w["head_conv1/kernel"], w["head_conv1/bias"], "relu")
+            y = conv2d(y, w["head_conv2/kernel"], w["head_conv2/bias"], "relu")
+            y = torch.softmax(y, -1)
+            x = y
+        elif head_kind == "conv1d":
+            y = conv1d(d[:, 0], w["head_conv0/kernel"], w["head_conv0/bias"], "relu")
+            y = conv1d(y, w["head_conv1/kernel"], w["head_conv1/bias"], "relu")
+            y = conv1d(y, w["head_conv2/kernel"], w["head_conv2/bias"], "softmax")
+            y = y[:, None]
+            x = y
+        else:
+            y = dense(d[:, 0].reshape(B, -1), w["head_dense/kernel"], w["head_dense/bias"])
+            x = y[:, None, None, :]
+        outs.append(y)
+    return torch.stack(outs, 1)
+
+
+# ------------------------- loss + gradient helpers ------------------------- #
+
+
+def loss_and_grads(forward, w, inputs, targets, loss_fns, loss_weights=None):
+    """Run ``forward(w, *inputs)``, total loss = sum_i weight_i * loss_i(target_i, out_i)
+    (Keras multi-output compile, mycode/others_LSTM_span_whole.py:352-353); return
+    (loss, outputs, {name: grad})."""
+    for t in w.values():
+        t.requires_grad_(True)
+        t.grad = None
+    outs = forward(w, *inputs)
+    if not isinstance(outs, (list, tuple)):
+        outs = [outs]
+    if loss_weights is None:
+        loss_weights = [1.0] * len(outs)
+    total = 0.0
+    for o, y, fn, lw in zip(outs, targets, loss_fns, loss_weights):
+        total = total + lw * fn(y, o)
+    total.backward()
+    grads = {k: v.grad.detach().clone() for k, v in w.items()}
+    return total.detach(), [o.detach() for o in outs], grads
+
+
+class KerasAdam:
+    """Keras-form Adam over a dict of tensors (eps outside the bias correction)."""
+
+    def __init__(self, w, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7):
+        self.w, self.lr, self.b1, self.b2, self.eps = w, lr, beta1, beta2, eps
+        self.m = {k: torch.zeros_like(v) for k, v in w.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in w.items()}
+        self.t = 0
+
+    def step(self, grads):
+        self.t += 1
+        lr_t = self.lr * np.sqrt(1 - self.b2 ** self.t) / (1 - self.b1 ** self.t)
+        with torch.no_grad():
+            for k, p in self.w.items():
+                g = grads[k]
+                self.m[k].mul_(self.b1).add_(g, alpha=1 - self.b1)
+                self.v[k].mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+                p.sub_(lr_t * self.m[k] / (self.v[k].sqrt() + self.eps))
+
+
+class KerasRMSprop:
+    def __init__(self, w, lr=1e-3, rho=0.9, eps=1e-7):
+        self.w, self.lr, self.rho, self.eps = w, lr, rho, eps
+        self.a = {k: torch.zeros_like(v) for k, v in w.items()}
+
+    def step(self, grads):
+        with torch.no_grad():
+            for k, p in self.w.items():
+                g = grads[k]
+                self.a[k].mul_(self.rho).addcmul_(g, g, value=1 - self.rho)
+                p.sub_(self.lr * g / (self.a[k].sqrt() + self.eps))

@@ -1,0 +1,214 @@
+"""CPU tests of the oracle itself: pinned against the reference's own NumPy
+functions (golden vectors), the two restatements against each other, torch.nn.LSTM
+as an independent gate-algebra check, known-answer cases and finite differences."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import keras_numpy as kn
+from oracle import keras_torch as kt
+
+
+# ---------------- pinned: reference's own functions ------------------------ #
+
+def test_featuriser_matches_reference_golden(golden):
+    np.testing.assert_allclose(kn.get_gt_target_xyz(golden["xyz90_in"]), golden["xyz90_out"],
+                               rtol=0, atol=1e-15)
+    np.testing.assert_allclose(kn.get_gt_target_xyz(golden["xyz4_in"]), golden["xyz4_out"],
+                               rtol=0, atol=1e-15)
+    np.testing.assert_allclose(kn.get_gt_target_xyz_oth(golden["oth_in"]), golden["oth_out"],
+                               rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("stride", [10, 1, 2])
+@pytest.mark.parametrize("collapse", [True, False])
+def test_windowing_matches_reference_golden(golden, stride, collapse):
+    a, b, c = kn.reshape2second_stacks(golden["stack_in"], collapse_user=collapse, stride=stride)
+    tag = "stack_s%d_c%d" % (stride, int(collapse))
+    assert np.array_equal(a, golden[tag + "_past"])
+    assert np.array_equal(b, golden[tag + "_fut"])
+    assert np.array_equal(c, golden[tag + "_futin"])
+
+
+def test_resampler_matches_reference_golden(golden):
+    mu, var, noise = golden["fake_mu"], golden["fake_var"], golden["fake_noise"]
+    got = kn.gaussian_resample(mu[:, None], var[:, None], noise[:, :, None], "sqrt_floor")[..., 0]
+    np.testing.assert_allclose(got, golden["fake_out"], rtol=0, atol=1e-14)
+
+
+# ---------------- known-answer cases --------------------------------------- #
+
+def test_hard_sigmoid_saturation():
+    x = np.array([-3.0, -2.5, 0.0, 2.5, 3.0, 1.0])
+    np.testing.assert_allclose(kn.hard_sigmoid(x), [0, 0, 0.5, 1, 1, 0.7])
+
+
+def test_lstm_zero_weights_and_forget_bias():
+    B, T, I, H = 2, 3, 4, 5
+    x = np.ones((B, T, I))
+    W, U = np.zeros((I, 4 * H)), np.zeros((H, 4 * H))
+    seq, h, c = kn.lstm(x, W, U, np.zeros(4 * H))
+    assert np.all(seq == 0) and np.all(c == 0)            # g = tanh(0) = 0
+    b = np.zeros(4 * H)
+    b[2 * H:3 * H] = 10.0                                   # g ~ 1, i=f=o=0.5
+    seq, h, c = kn.lstm(x, W, U, b)
+    g = np.tanh(10.0)
+    c1 = 0.5 * g
+    c2 = 0.5 * c1 + 0.5 * g
+    np.testing.assert_allclose(seq[:, 1], 0.5 * np.tanh(c2), atol=1e-15)
+
+
+def test_conv_same_delta_image():
+    # 'same' padding on a delta image reproduces the (un-flipped) kernel, centred.
+    k = np.arange(15, dtype=np.float64).reshape(3, 5, 1, 1)
+    x = np.zeros((1, 7, 9, 1))
+    x[0, 3, 4, 0] = 1.0
+    y = kn.conv2d_same(x, k)[0, :, :, 0]
+    # cross-correlation: y[p] = sum_d x[p+d-c] k[d] -> kernel appears flipped around the delta
+    np.testing.assert_allclose(y[2:5, 2:7], k[::-1, ::-1, 0, 0])
+    # even kernel: TF puts the extra pad at the end (low = 0 for k=2)
+    k2 = np.array([1.0, 2.0]).reshape(1, 2, 1, 1)
+    x2 = np.zeros((1, 1, 4, 1)); x2[0, 0, 0, 0] = 1.0
+    np.testing.assert_allclose(kn.conv2d_same(x2, k2)[0, 0, :, 0], [1, 0, 0, 0])
+    x2 = np.zeros((1, 1, 4, 1)); x2[0, 0, 3, 0] = 1.0
+    np.testing.assert_allclose(kn.conv2d_same(x2, k2)[0, 0, :, 0], [0, 0, 2, 1])
+
+
+def test_adam_first_step_known_answer():
+    p, m, v = kn.adam_step(np.array([1.0]), np.array([0.5]), np.zeros(1), np.zeros(1), 1)
+    # m=0.05, v=2.5e-4, lr_t = 1e-3*sqrt(1e-3)/0.1 ; step = lr_t*m/(sqrt(v)+1e-7)
+    lr_t = 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    np.testing.assert_allclose(p, 1.0 - lr_t * 0.05 / (np.sqrt(2.5e-4) + 1e-7), rtol=1e-14)
+
+
+def test_gauss_nll_hand_case():
+    y_true = np.zeros((1, 10, 90))
+    y_pred = np.zeros((1, 10, 6)); y_pred[..., 3:] = 1.0
+    # var=1, x=u=0 -> log(1+1e-7) per frame per coord; sum over 30*10*3, /10/30
+    np.testing.assert_allclose(kn.gauss_nll(y_true, y_pred), 3 * np.log(1 + 1e-7), rtol=1e-9)
+    y_pred[..., 3:] = -5.0                                   # |var| clipped to 2
+    np.testing.assert_allclose(kn.gauss_nll(y_true, y_pred), 3 * np.log(2 + 1e-7), rtol=1e-9)
+
+
+# ---------------- independent restatements agree --------------------------- #
+
+def test_lstm_matches_torch_nn_lstm_in_sigmoid_mode():
+    rng = np.random.default_rng(0)
+    B, T, I, H = 3, 6, 5, 8
+    x = rng.normal(size=(B, T, I))
+    W, U, b = rng.normal(size=(I, 4 * H)) * .3, rng.normal(size=(H, 4 * H)) * .3, rng.normal(size=4 * H) * .1
+    seq, h, c = kn.lstm(x, W, U, b, recurrent_activation="sigmoid")
+    ref = torch.nn.LSTM(I, H, batch_first=True).double()
+    with torch.no_grad():
+        ref.weight_ih_l0.copy_(torch.tensor(W.T)); ref.weight_hh_l0.copy_(torch.tensor(U.T))
+        ref.bias_ih_l0.copy_(torch.tensor(b)); ref.bias_hh_l0.zero_()
+        out, (hn, cn) = ref(torch.tensor(x))
+    np.testing.assert_allclose(seq, out.numpy(), atol=1e-12)
+    np.testing.assert_allclose(c, cn[0].numpy(), atol=1e-12)
+
+
+def _rand_weights(init, seed=3, scale=1.0, **kw):
+    w = init(seed=seed, **kw)
+    rng = np.random.default_rng(seed + 100)
+    return {k: (v.astype(np.float64) * scale + rng.normal(size=v.shape) * 0.05) for k, v in w.items()}
+
+
+@pytest.mark.parametrize("tf", [True, False])
+def test_m1_numpy_vs_torch(tf):
+    rng = np.random.default_rng(1)
+    w = _rand_weights(kn.init_fov_seq2seq)
+    enc = rng.uniform(-1, 1, (4, 10, 90)); dec = rng.uniform(-1, 1, (4, 10 if tf else 1, 6))
+    a = kn.fov_seq2seq_forward(w, enc, dec, teacher_forcing=tf)
+    b = kt.fov_seq2seq_forward(kt.to_torch(w), torch.tensor(enc), torch.tensor(dec), teacher_forcing=tf)
+    np.testing.assert_allclose(a, b.numpy(), atol=1e-10)
+
+
+def test_m3_numpy_vs_torch():
+    rng = np.random.default_rng(2)
+    w = _rand_weights(kn.init_others_lstm_span_whole, num_user=6)
+    enc = rng.uniform(-1, 1, (3, 10, 6)); oth = rng.uniform(-1, 1, (3, 20, 1, 5, 6)); dec = rng.uniform(-1, 1, (3, 1, 6))
+    a = kn.others_lstm_span_whole_forward(w, enc, oth, dec)
+    b = kt.others_lstm_span_whole_forward(kt.to_torch(w), torch.tensor(enc), torch.tensor(oth), torch.tensor(dec))
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(x, y.numpy(), atol=1e-10)
+    assert a[0].shape == (3, 10, 6) and a[1].shape == (3, 20, 30) and a[2].shape == (3, 10, 6)
+
+
+@pytest.mark.parametrize("kind", ["conv2d", "conv1d", "dense"])
+def test_m4_numpy_vs_torch(kind):
+    rng = np.random.default_rng(4)
+    if kind == "conv2d":
+        w = _rand_weights(kn.init_convlstm_seq2seq, in_ch=5, filters=(4, 3, 2), kernel_size=3, head=(6, 7, 5))
+        enc = rng.uniform(0, 1, (2, 3, 6, 4, 5)); dec = rng.uniform(0, 1, (2, 1, 6, 4, 5))
+    elif kind == "conv1d":
+        w = _rand_weights(kn.init_convlstm_seq2seq, in_ch=3, filters=(4, 3, 2), kernel_size=3, head=(6, 7, 3), head_kind="conv1d")
+        enc = rng.uniform(-1, 1, (2, 3, 1, 8, 3)); dec = rng.uniform(-1, 1, (2, 1, 1, 8, 3))
+    else:
+        w = _rand_weights(kn.init_convlstm_seq2seq, in_ch=6, filters=(4, 3, 2), kernel_size=3, head_kind="dense", flat_dim=9)
+        enc = rng.uniform(-1, 1, (2, 3, 1, 1, 6)); dec = rng.uniform(-1, 1, (2, 1, 1, 1, 6))
+    a = kn.convlstm_seq2seq_forward(w, enc, dec, head_kind=kind, steps=3)
+    b = kt.convlstm_seq2seq_forward(kt.to_torch(w), torch.tensor(enc), torch.tensor(dec), head_kind=kind, steps=3)
+    np.testing.assert_allclose(a, b.numpy(), atol=1e-10)
+
+
+def test_convlstm_dilation_and_dropout_masks_numpy_vs_torch():
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(2, 3, 5, 6, 3)); K = rng.normal(size=(3, 3, 3, 8)) * .3
+    R = rng.normal(size=(3, 3, 2, 8)) * .3; b = rng.normal(size=8) * .1
+    masks = [(rng.uniform(size=(2, 5, 6, 3)) > 0.3) / 0.7 for _ in range(4)]
+    a, _, _ = kn.convlstm2d(x, K, R, b, dilation=(2, 2), dropout_masks=masks)
+    t = lambda v: torch.tensor(v)
+    bb, _, _ = kt.convlstm2d(t(x), t(K), t(R), t(b), dilation=(2, 2), dropout_masks=[t(m) for m in masks])
+    np.testing.assert_allclose(a, bb.numpy(), atol=1e-10)
+
+
+def test_losses_numpy_vs_torch():
+    rng = np.random.default_rng(6)
+    yt, yp = rng.uniform(-1, 1, (3, 10, 90)), rng.uniform(-1, 1, (3, 10, 6))
+    np.testing.assert_allclose(kn.gauss_nll(yt, yp), kt.gauss_nll(torch.tensor(yt), torch.tensor(yp)).item(), rtol=1e-12)
+    p = kn.softmax(rng.normal(size=(2, 4, 3, 5))); t1 = np.eye(5)[rng.integers(0, 5, (2, 4, 3))]
+    np.testing.assert_allclose(kn.categorical_crossentropy(t1, p), kt.categorical_crossentropy(torch.tensor(t1), torch.tensor(p)).item(), rtol=1e-12)
+
+
+def test_optimisers_numpy_vs_torch():
+    rng = np.random.default_rng(7)
+    p0 = rng.normal(size=9); w = {"p": torch.tensor(p0.copy())}
+    adam = kt.KerasAdam(w); p, m, v = p0.copy(), np.zeros(9), np.zeros(9)
+    for t in range(1, 4):
+        g = rng.normal(size=9)
+        p, m, v = kn.adam_step(p, g, m, v, t)
+        adam.step({"p": torch.tensor(g)})
+    np.testing.assert_allclose(p, w["p"].numpy(), atol=1e-14)
+    w = {"p": torch.tensor(p0.copy())}; rms = kt.KerasRMSprop(w); p, a = p0.copy(), np.zeros(9)
+    for t in range(3):
+        g = rng.normal(size=9)
+        p, a = kn.rmsprop_step(p, g, a); rms.step({"p": torch.tensor(g)})
+    np.testing.assert_allclose(p, w["p"].numpy(), atol=1e-14)
+
+
+# ---------------- finite differences pin the autograd gradients ------------ #
+
+def test_m3_gradients_finite_difference():
+    rng = np.random.default_rng(8)
+    w = _rand_weights(kn.init_others_lstm_span_whole, num_user=4, scale=0.5)
+    enc = rng.uniform(-1, 1, (2, 10, 6)); oth = rng.uniform(-1, 1, (2, 20, 1, 3, 6)); dec = rng.uniform(-1, 1, (2, 1, 6))
+    tgt = [rng.uniform(-1, 1, (2, 10, 6)), rng.uniform(-1, 1, (2, 20, 18)), rng.uniform(-1, 1, (2, 10, 6))]
+
+    def total(wd):
+        o = kn.others_lstm_span_whole_forward(wd, enc, oth, dec)
+        return sum(kn.mse(t, y) for t, y in zip(tgt, o))
+
+    wt = kt.to_torch(w)
+    _, _, grads = kt.loss_and_grads(kt.others_lstm_span_whole_forward, wt,
+                                    [torch.tensor(enc), torch.tensor(oth), torch.tensor(dec)],
+                                    [torch.tensor(t) for t in tgt], [kt.mse] * 3)
+    eps = 1e-6
+    for name in ["oth_convlstm0/recurrent_kernel", "oth_convlstm1/kernel", "decoder/recurrent_kernel",
+                 "decoder_dense/kernel", "oth_flat_dense/kernel", "encoder/kernel", "encoder_dense/bias"]:
+        flat_idx = rng.integers(0, w[name].size, 3)
+        for fi in flat_idx:
+            idx = np.unravel_index(fi, w[name].shape)
+            wp = {k: v.copy() for k, v in w.items()}; wp[name][idx] += eps
+            wm = {k: v.copy() for k, v in w.items()}; wm[name][idx] -= eps
+            fd = (total(wp) - total(wm)) / (2 * eps)
+            assert abs(fd - grads[name][idx].item()) < 1e-6 + 1e-4 * abs(fd), (name, idx, fd, grads[name][idx].item())
