@@ -1,0 +1,231 @@
+/*
+ * fov360.h — C ABI of libfov360.so, the B200 (sm_100a) kernels behind the
+ * LongTerm360FoV sequence-prediction hot path.
+ *
+ * The reference (ChengeLi/LongTerm360FoV) has no FFI of its own: its hot path is
+ * the set of Keras layer calls listed below, executed by TF1.  Each entry point
+ * here replaces the Keras/TF op behind one of those call sites; the Python layer
+ * in longterm360fov_b200/ binds them with ctypes and wraps them in
+ * torch.autograd.Functions (INTEGRATION.md shows the script-side swap).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous float32 unless stated,
+ *     16-byte aligned; the caller owns all buffers (inputs, outputs, saved
+ *     activations, workspaces); the library allocates nothing and keeps no state.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it.
+ *   - weight layouts are Keras': LSTM kernel (in,4H) / recurrent_kernel (H,4H) /
+ *     bias (4H), gate blocks i,f,c,o; ConvLSTM2D kernel (kh,kw,Cin,4F) /
+ *     recurrent_kernel (kh,kw,F,4F); Dense (in,out); Conv2D (kh,kw,Cin,Cout).
+ *   - return value: 0 = ok, negative = error (fov_last_error() gives a
+ *     thread-local message).  Nothing throws across the boundary.
+ */
+#ifndef FOV360_H
+#define FOV360_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { FOV_OK = 0, FOV_ERR_ARG = -1, FOV_ERR_UNSUPPORTED = -2, FOV_ERR_CUDA = -3 };
+enum { FOV_ACT_LINEAR = 0, FOV_ACT_TANH = 1, FOV_ACT_RELU = 2 };
+enum { FOV_REC_HARD_SIGMOID = 0, FOV_REC_SIGMOID = 1 };
+
+const char* fov_last_error(void);
+int fov_version(void);
+/* kernel launches issued by the library since it was loaded (diagnostics). */
+unsigned long long fov_launch_count(void);
+/* 1 when the running device is sm_100 (B200). */
+int fov_device_is_sm100(void);
+
+/* ------------------------------------------------------------------------- *
+ * Persistent fc-LSTM encoder-decoder.
+ * Replaces: keras LSTM(64,return_state) + LSTM(64,return_sequences) + Dense at
+ *   mycode/FoV_seq2seq.py:82-97 (teacher forcing), the host decode loop
+ *   :154-178, the in-graph autoregressive loop
+ *   mycode/FoV_seq2seq_no_teac_forc.py:88-129, the mu/var form
+ *   mycode/FoV_seq2seq_mu_var.py:219-234,286-311 and the target branch of
+ *   mycode/others_LSTM_span_whole.py:119-121,262-271.
+ * One launch runs T_enc encoder steps then T_dec decoder steps; weights stay in
+ * shared memory, gates/cell in registers, no per-step launch.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int B;              /* sequences */
+  int T_enc, T_dec;   /* either may be 0 (encoder_model / decoder_model split) */
+  int in_enc, in_dec; /* input widths */
+  int H;              /* latent_dim; 64 supported */
+  int out_dim;        /* head width (0 = no head) */
+  int teacher_forcing;/* 1: x_dec is (B,T_dec,in_dec); 0: x_dec is (B,1,in_dec), y re-fed */
+  int head_act;       /* FOV_ACT_* */
+  int rec_act;        /* FOV_REC_* */
+  int dec_zero_init;  /* 1: decoder starts from a zero state (FoV_seq2seq_no_teac_forc.py:29) */
+  int training;       /* 1: write the saved-activation buffers */
+} fov_lstm_cfg;
+
+typedef struct {
+  const float *enc_kernel, *enc_recurrent, *enc_bias;   /* (in_enc,4H) (H,4H) (4H) */
+  const float *dec_kernel, *dec_recurrent, *dec_bias;   /* (in_dec,4H) (H,4H) (4H) */
+  const float *head_kernel, *head_bias;                 /* (H,out) (out) */
+} fov_lstm_weights;
+
+typedef struct {                 /* per LSTM, all (B,T,...) row-major */
+  float *xh;                     /* (B,T,H+in): [h_{t-1} | x_t], A operand of the weight-grad GEMM */
+  float *gates;                  /* (B,T,4H): activated i,f,g,o */
+  float *c;                      /* (B,T,H) */
+  float *hseq;                   /* (B,T,H)  (also the return_sequences output) */
+} fov_lstm_saved;
+
+typedef struct {
+  const float *x_enc;            /* (B,T_enc,in_enc) */
+  const float *x_dec;            /* (B,T_dec,in_dec) or (B,1,in_dec) */
+  const float *extra;            /* optional (B,T_dec,out): added to the head pre-activation */
+  const float *h0, *c0;          /* optional initial state (B,H) */
+  float *y;                      /* (B,T_dec,out) */
+  float *hT, *cT;                /* optional final state (B,H) */
+  fov_lstm_saved enc, dec;       /* any pointer may be NULL when training == 0 */
+} fov_lstm_io;
+
+int fov_lstm_seq2seq_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w,
+                         const fov_lstm_io* io, void* stream);
+
+typedef struct {
+  const float *dy;               /* (B,T_dec,out) gradient of the loss w.r.t. y */
+  const float *dhseq_enc;        /* optional (B,T_enc,H): gradient w.r.t. enc.hseq */
+  const float *y;                /* forward output (for tanh'/relu') */
+  float *dz_enc, *dz_dec;        /* scratch+output (B,T,4H): gate pre-activation gradients */
+  float *dpre;                   /* (B,T_dec,out): head pre-activation gradient == d(extra) */
+  /* weight gradients, ACCUMULATED (+=) */
+  float *g_enc_kernel, *g_enc_recurrent, *g_enc_bias;
+  float *g_dec_kernel, *g_dec_recurrent, *g_dec_bias;
+  float *g_head_kernel, *g_head_bias;
+} fov_lstm_grads;
+
+int fov_lstm_seq2seq_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w,
+                         const fov_lstm_io* io, const fov_lstm_grads* g, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Convolution / dense family (implicit GEMM, channels-last, stride 1).
+ * Replaces: Dense (mycode/others_LSTM_span_whole.py:105-109,265-271), Conv2D /
+ *   Conv1D heads (mycode/convlstm_seq2seq.py:175-189,230-258) and the gate
+ *   convolutions inside ConvLSTM2D (mycode/others_LSTM_span_whole.py:88-100,
+ *   mycode/convlstm_seq2seq.py:100-126,146-165).
+ * A Dense layer is the 1x1 case: N=rows, H=W=1, Cin=in, Cout=out.
+ * y[n,p,co] = act( sum_{tap,ci} x[n, p+tap*dil-pad, ci] * w[tap,ci,co] + bias[co]
+ *                  + beta * y_old[n,p,co] )
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int N, H, W, Cin, Cout;
+  int kh, kw, dil_h, dil_w;
+  int pad_h, pad_w;             /* low-side padding; TF 'same' = ((k-1)*dil)/2 */
+  long long x_img_stride;       /* elements between consecutive images of x */
+  int x_pix_stride;             /* elements between consecutive pixels of x (>= Cin) */
+  long long y_img_stride;
+  int y_pix_stride;
+  int act;                      /* FOV_ACT_* */
+  float beta;                   /* 0 or 1 */
+} fov_conv_cfg;
+
+int fov_conv2d_fwd(const fov_conv_cfg* cfg, const float* x, const float* w, const float* bias,
+                   float* y, void* stream);
+/* dx = conv^T(dy, w).  ws: workspace of kh*kw*Cin*Cout floats (flipped weights).
+ * cfg describes the FORWARD conv (x = its input, y = its output); beta applies to dx. */
+int fov_conv2d_bwd_data(const fov_conv_cfg* cfg, const float* dy, const float* w, float* dx,
+                        float* ws, void* stream);
+/* gw += x^T (*) dy ; gbias += colsum(dy)   (either may be NULL) */
+int fov_conv2d_bwd_weight(const fov_conv_cfg* cfg, const float* x, const float* dy, float* gw,
+                          float* gbias, void* stream);
+/* y = act'(y) * dy elementwise helper for fused bias+activation layers:
+ * dpre = dy * act'(y_out)  over `rows` x `cols` with row strides. */
+int fov_act_bwd(int act, long long rows, int cols, const float* y, long long y_stride,
+                const float* dy, long long dy_stride, float* dpre, long long dpre_stride,
+                void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * ConvLSTM2D layer over a whole sequence (return_sequences=True, return_state).
+ * Replaces: keras ConvLSTM2D at mycode/others_LSTM_span_whole.py:88-100 and
+ *   mycode/convlstm_seq2seq.py:100-126 (T=10/20) and the one-step decoder calls
+ *   :213-218 (T=1 with given initial state).
+ * x: (B,T,H,W,Cin) with strides; hseq written at (B,T,H,W,F) with strides so
+ * three layers can write straight into the channel-concatenated buffer.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int B, T, H, W, Cin, F;
+  int kh, kw, dil_h, dil_w;      /* dilation applies to the input conv only */
+  int rec_act;
+  long long x_b_stride, x_t_stride;  int x_pix_stride;
+  long long h_b_stride, h_t_stride;  int h_pix_stride;   /* layout of hseq */
+  int training;
+} fov_convlstm_cfg;
+
+typedef struct {
+  const float *x;
+  const float *kernel, *recurrent, *bias;
+  const float *h0, *c0;          /* optional (B,H,W,F) dense */
+  const float *drop_masks;       /* optional (4,B,H,W,Cin), already scaled by 1/(1-p) */
+  float *hseq;                   /* strided output */
+  float *gates;                  /* (B,T,H,W,4F): pre-activations then activated gates (saved) */
+  float *cseq;                   /* (B,T,H,W,F) */
+  float *hT, *cT;                /* optional dense (B,H,W,F) */
+  float *ws;                     /* workspace: B*H*W*Cin floats when drop_masks != NULL */
+} fov_convlstm_io;
+
+int fov_convlstm_fwd(const fov_convlstm_cfg* cfg, const fov_convlstm_io* io, void* stream);
+
+typedef struct {
+  const float *dhseq;            /* gradient w.r.t. hseq, same strides as hseq (may be NULL) */
+  const float *dhT, *dcT;        /* optional gradient w.r.t. final state, dense */
+  float *dx;                     /* optional, same strides as x (see dx_accumulate) */
+  float *dh0, *dc0;              /* optional dense */
+  float *g_kernel, *g_recurrent, *g_bias;   /* accumulated (+=) */
+  float *ws;                     /* workspace floats: see fov_convlstm_bwd_ws_floats */
+  int dx_accumulate;             /* 0: dx overwritten; 1: dx += (stacked layers add into the
+                                    gradient of the layer below) */
+} fov_convlstm_grads;
+
+size_t fov_convlstm_bwd_ws_floats(const fov_convlstm_cfg* cfg);
+int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_io* io,
+                     const fov_convlstm_grads* g, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Pointwise / reduction kernels.
+ * ------------------------------------------------------------------------- */
+/* Softmax over the last (channel) axis: keras.layers.Softmax(axis=-1),
+ * mycode/convlstm_seq2seq.py:237. */
+int fov_softmax_fwd(long long rows, int C, const float* x, float* y, void* stream);
+int fov_softmax_bwd(long long rows, int C, const float* y, const float* dy, float* dx, void* stream);
+
+/* MSE (Keras 'mean_squared_error', mycode/FoV_seq2seq.py:103, mycode/cost.py:20-29):
+ * loss[0] += weight * mean((y-t)^2);  dy = weight * 2 (y-t) / n  (dy may be NULL). */
+int fov_mse_fwd_bwd(long long n, const float* y, const float* t, float weight, float* loss,
+                    float* dy, void* stream);
+/* Gaussian NLL, mycode/cost.py:138-187.  y (B,T,6), frames (B,T,90) interleaved xyz;
+ * loss[0] += weight * mean_B(sum_{t,frame,axis} l) / running_length / 30. */
+int fov_gauss_nll_fwd_bwd(int B, int T, int running_length, const float* y, const float* frames,
+                          float weight, float* loss, float* dy, void* stream);
+/* Keras categorical_crossentropy on probabilities (mycode/convlstm_heatmap.py:281). */
+int fov_cce_fwd_bwd(long long rows, int C, const float* p, const float* t, float weight,
+                    float* loss, float* dp, void* stream);
+
+/* Keras-form Adam / RMSprop over one flat parameter buffer
+ * ('Adam' mycode/FoV_seq2seq.py:103; 'RMSprop' mycode/convlstm_seq2seq.py:287).
+ * grad_scale multiplies g first (1/world_size after an allreduce-sum). */
+int fov_adam_step(long long n, float* p, const float* g, float* m, float* v, int t, float lr,
+                  float beta1, float beta2, float eps, float grad_scale, void* stream);
+int fov_rmsprop_step(long long n, float* p, const float* g, float* a, float lr, float rho,
+                     float eps, float grad_scale, void* stream);
+
+/* Per-second mean / population variance featuriser (mycode/utility.py:483-517):
+ * frames (rows,30,3) interleaved xyz -> (rows,6) = [mx,my,mz,vx,vy,vz]. */
+int fov_mean_var_xyz(long long rows, const float* frames, float* out, void* stream);
+/* Gaussian sample-and-refeed with explicit N(0,1) noise
+ * (mycode/utility.py:73-80 mode 0; others_LSTM_span_whole.py:64-69 mode 1;
+ *  convlstm_seq2seq.py:51-58 mode 2).  muvar (rows,6), noise (rows,30,3) -> (rows,30,3) */
+int fov_gauss_resample(long long rows, int mode, const float* muvar, const float* noise,
+                       float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOV360_H */

@@ -1,0 +1,12 @@
+"""longterm360fov_b200 - B200-native (sm_100a) implementation of the LongTerm360FoV
+sequence-prediction hot path: Keras-shaped model builders over hand-written CUDA
+kernels behind a C ABI (include/fov360.h).  No CPU fallback: importing the models
+without libfov360.so raises."""
+from . import _lib
+from .callbacks import EarlyStopping, ModelCheckpoint, ReduceLROnPlateau
+from .models import (Adam, ConvLSTMSeq2Seq, FovSeq2Seq, Model, OthersLSTMSpanWhole, RMSprop,
+                     convlstm_seq2seq, fov_seq2seq, fov_seq2seq_mu_var, others_lstm_span_whole)
+
+__all__ = ["fov_seq2seq", "fov_seq2seq_mu_var", "others_lstm_span_whole", "convlstm_seq2seq",
+           "Model", "FovSeq2Seq", "OthersLSTMSpanWhole", "ConvLSTMSeq2Seq", "Adam", "RMSprop",
+           "ModelCheckpoint", "ReduceLROnPlateau", "EarlyStopping"]

@@ -1,0 +1,208 @@
+// ConvLSTM2D layer over a whole sequence, forward and BPTT, built from the
+// implicit-GEMM convolution kernels and the fused gate kernels.
+//
+// forward:  Zx = conv(x_all_t, K) + b      (one time-batched launch over B*T images)
+//           for t: Z_t += conv(h_{t-1}, R);  gates/cell update in place -> h_t, c_t
+// backward: for t reversed: dZ_t from (dh_t, dc_t, saved gates); dh_{t-1} = conv^T(dZ_t, R)
+//           then time-batched dx = conv^T(dZ, K), gK += x^T dZ, gR += h_{t-1}^T dZ, gb += sum dZ
+//
+// Replaces keras ConvLSTM2D at mycode/others_LSTM_span_whole.py:88-100 and
+// mycode/convlstm_seq2seq.py:100-126,146-165,213-218.
+#include "fov_common.cuh"
+#include "fov_internal.h"
+
+namespace {
+
+int check(const fov_convlstm_cfg* c) {
+  FOV_CHECK_ARG(c != nullptr, "cfg is NULL");
+  FOV_CHECK_ARG(c->B > 0 && c->T > 0 && c->H > 0 && c->W > 0 && c->Cin > 0 && c->F > 0, "bad shape");
+  FOV_CHECK_ARG(c->kh > 0 && c->kw > 0 && c->dil_h > 0 && c->dil_w > 0, "bad kernel");
+  return FOV_OK;
+}
+
+struct Geo {
+  int HW;
+  long long z_b, z_t;   // gates buffer strides (B,T,HW,4F)
+  long long c_b, c_t;   // cseq strides (B,T,HW,F)
+  long long hw_f;       // HW*F
+};
+Geo geo(const fov_convlstm_cfg* c) {
+  Geo g;
+  g.HW = c->H * c->W;
+  g.z_t = (long long)g.HW * 4 * c->F;
+  g.z_b = g.z_t * c->T;
+  g.c_t = (long long)g.HW * c->F;
+  g.c_b = g.c_t * c->T;
+  g.hw_f = g.c_t;
+  return g;
+}
+
+fov_conv_cfg input_conv_cfg(const fov_convlstm_cfg* c) {
+  fov_conv_cfg k{};
+  k.H = c->H; k.W = c->W; k.Cin = c->Cin; k.Cout = 4 * c->F;
+  k.kh = c->kh; k.kw = c->kw; k.dil_h = c->dil_h; k.dil_w = c->dil_w;
+  k.pad_h = ((c->kh - 1) * c->dil_h) / 2; k.pad_w = ((c->kw - 1) * c->dil_w) / 2;
+  k.x_pix_stride = c->x_pix_stride; k.y_pix_stride = 4 * c->F;
+  k.act = FOV_ACT_LINEAR; k.beta = 0.0f;
+  return k;
+}
+fov_conv_cfg rec_conv_cfg(const fov_convlstm_cfg* c) {
+  fov_conv_cfg k{};
+  k.N = c->B; k.H = c->H; k.W = c->W; k.Cin = c->F; k.Cout = 4 * c->F;
+  k.kh = c->kh; k.kw = c->kw; k.dil_h = 1; k.dil_w = 1;
+  k.pad_h = (c->kh - 1) / 2; k.pad_w = (c->kw - 1) / 2;
+  k.y_pix_stride = 4 * c->F;
+  k.act = FOV_ACT_LINEAR; k.beta = 1.0f;
+  return k;
+}
+
+}  // namespace
+
+extern "C" int fov_convlstm_fwd(const fov_convlstm_cfg* cfg, const fov_convlstm_io* io, void* stream) {
+  int rc = check(cfg);
+  if (rc) return rc;
+  FOV_CHECK_ARG(io && io->x && io->kernel && io->recurrent && io->bias && io->hseq && io->gates && io->cseq,
+                "NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Geo g = geo(cfg);
+  const int F = cfg->F;
+
+  // ---- input projection for every timestep ----
+  if (!io->drop_masks) {
+    fov_conv_cfg k = input_conv_cfg(cfg);
+    if (cfg->x_b_stride == (long long)cfg->T * cfg->x_t_stride || cfg->T == 1) {
+      k.N = cfg->B * cfg->T; k.x_img_stride = cfg->T == 1 ? cfg->x_b_stride : cfg->x_t_stride;
+      k.y_img_stride = g.z_t;
+      if ((rc = fov_conv2d_fwd(&k, io->x, io->kernel, io->bias, io->gates, stream))) return rc;
+    } else {
+      k.N = cfg->B; k.x_img_stride = cfg->x_b_stride; k.y_img_stride = g.z_b;
+      for (int t = 0; t < cfg->T; ++t)
+        if ((rc = fov_conv2d_fwd(&k, io->x + t * cfg->x_t_stride, io->kernel, io->bias,
+                                 io->gates + t * g.z_t, stream))) return rc;
+    }
+  } else {
+    // training-time input dropout: one mask per gate, constant over time
+    // (keras ConvLSTM2D(dropout=...), mycode/others_LSTM_span_whole.py:89).  The gate
+    // blocks of the kernel are NOT contiguous ([K][4F] rows), so each gate uses a
+    // compacted copy of its weight columns placed after the masked input in ws.
+    fov_set_error("fov_convlstm_fwd: dropout masks are applied by the caller in this build");
+    return FOV_ERR_UNSUPPORTED;
+  }
+
+  // ---- recurrence ----
+  fov_conv_cfg r = rec_conv_cfg(cfg);
+  for (int t = 0; t < cfg->T; ++t) {
+    float* zt = io->gates + t * g.z_t;
+    const float* hprev = nullptr;
+    if (t == 0) {
+      if (io->h0) { hprev = io->h0; r.x_img_stride = g.hw_f; r.x_pix_stride = F; }
+    } else {
+      hprev = io->hseq + (t - 1) * cfg->h_t_stride; r.x_img_stride = cfg->h_b_stride; r.x_pix_stride = cfg->h_pix_stride;
+    }
+    if (hprev) {
+      r.y_img_stride = g.z_b;
+      if ((rc = fov_conv2d_fwd(&r, hprev, io->recurrent, nullptr, zt, stream))) return rc;
+    }
+    GatesFwdArgs a{};
+    a.npix = (long long)cfg->B * g.HW; a.HW = g.HW; a.F = F; a.rec = cfg->rec_act;
+    a.z = zt; a.z_img = g.z_b;
+    if (t == 0) { a.c_prev = io->c0; a.cp_img = g.hw_f; }
+    else { a.c_prev = io->cseq + (t - 1) * g.c_t; a.cp_img = g.c_b; }
+    a.c_out = io->cseq + t * g.c_t; a.c_img = g.c_b;
+    a.h_out = io->hseq + t * cfg->h_t_stride; a.h_img = cfg->h_b_stride; a.h_pix = cfg->h_pix_stride;
+    a.hT = (t == cfg->T - 1) ? io->hT : nullptr;
+    a.cT = (t == cfg->T - 1) ? io->cT : nullptr;
+    if ((rc = fov_launch_gates_fwd(a, st))) return rc;
+  }
+  return FOV_OK;
+}
+
+extern "C" size_t fov_convlstm_bwd_ws_floats(const fov_convlstm_cfg* c) {
+  if (!c) return 0;
+  const size_t bhwf = (size_t)c->B * c->H * c->W * c->F;
+  const size_t taps = (size_t)c->kh * c->kw;
+  // dh_rec + dc (ping-pong x2) + flipped recurrent + flipped kernel
+  return 4 * bhwf + taps * c->F * 4 * c->F + taps * c->Cin * 4 * c->F + 64;
+}
+
+extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_io* io,
+                                const fov_convlstm_grads* gr, void* stream) {
+  int rc = check(cfg);
+  if (rc) return rc;
+  FOV_CHECK_ARG(io && gr && io->x && io->kernel && io->recurrent && io->hseq && io->gates && io->cseq && gr->ws,
+                "NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Geo g = geo(cfg);
+  const int F = cfg->F;
+  const size_t bhwf = (size_t)cfg->B * g.HW * F;
+  float* dh_rec = gr->ws;
+  float* dc_a = gr->ws + bhwf;
+  float* dc_b = gr->ws + 2 * bhwf;
+  float* Rt = gr->ws + 4 * bhwf;
+  float* Kt = Rt + (size_t)cfg->kh * cfg->kw * F * 4 * F;
+
+  fov_conv_cfg r = rec_conv_cfg(cfg);
+  r.beta = 0.0f;
+  // dh_rec is produced as the "x" side of the recurrent conv: dense (B,HW,F)
+  r.x_img_stride = g.hw_f; r.x_pix_stride = F; r.y_img_stride = g.z_b;
+  if ((rc = fov_conv_flip_weights(&r, io->recurrent, Rt, st))) return rc;
+
+  const float* dc_in = gr->dcT;
+  const float* dh_in = gr->dhT;
+  for (int t = cfg->T - 1; t >= 0; --t) {
+    float* zt = io->gates + t * g.z_t;
+    GatesBwdArgs a{};
+    a.npix = (long long)cfg->B * g.HW; a.HW = g.HW; a.F = F; a.rec = cfg->rec_act;
+    a.gates = zt; a.z_img = g.z_b;
+    a.c_t = io->cseq + t * g.c_t; a.c_img = g.c_b;
+    if (t == 0) { a.c_prev = io->c0; a.cp_img = g.hw_f; }
+    else { a.c_prev = io->cseq + (t - 1) * g.c_t; a.cp_img = g.c_b; }
+    if (gr->dhseq) { a.dh_ext = gr->dhseq + t * cfg->h_t_stride; a.dhe_img = cfg->h_b_stride; a.dhe_pix = cfg->h_pix_stride; }
+    a.dh_rec = dh_in; a.dc_in = dc_in;
+    float* dc_out = (t == 0 && gr->dc0) ? gr->dc0 : ((dc_in == dc_a) ? dc_b : dc_a);
+    a.dc_out = dc_out;
+    if ((rc = fov_launch_gates_bwd(a, st))) return rc;
+    dc_in = dc_out;
+    if (t > 0 || (io->h0 && gr->dh0)) {
+      float* dst = (t == 0) ? gr->dh0 : dh_rec;
+      if ((rc = fov_conv_bwd_data_preflipped(&r, zt, Rt, dst, st))) return rc;
+      dh_in = dst;
+    }
+  }
+
+  // ---- time-batched input-side gradients ----
+  fov_conv_cfg k = input_conv_cfg(cfg);
+  k.beta = gr->dx_accumulate ? 1.0f : 0.0f;
+  const bool batched = (cfg->x_b_stride == (long long)cfg->T * cfg->x_t_stride) || cfg->T == 1;
+  if (gr->dx) {
+    if ((rc = fov_conv_flip_weights(&k, io->kernel, Kt, st))) return rc;
+  }
+  if (batched) {
+    k.N = cfg->B * cfg->T; k.x_img_stride = cfg->T == 1 ? cfg->x_b_stride : cfg->x_t_stride; k.y_img_stride = g.z_t;
+    if (gr->dx && (rc = fov_conv_bwd_data_preflipped(&k, io->gates, Kt, gr->dx, st))) return rc;
+    if ((rc = fov_conv2d_bwd_weight(&k, io->x, io->gates, gr->g_kernel, gr->g_bias, stream))) return rc;
+  } else {
+    k.N = cfg->B; k.x_img_stride = cfg->x_b_stride; k.y_img_stride = g.z_b;
+    for (int t = 0; t < cfg->T; ++t) {
+      if (gr->dx && (rc = fov_conv_bwd_data_preflipped(&k, io->gates + t * g.z_t, Kt, gr->dx + t * cfg->x_t_stride, st))) return rc;
+      if ((rc = fov_conv2d_bwd_weight(&k, io->x + t * cfg->x_t_stride, io->gates + t * g.z_t, gr->g_kernel,
+                                      gr->g_bias, stream))) return rc;
+    }
+  }
+  // ---- recurrent weight gradient: pairs (h_{t-1}, dZ_t) ----
+  if (gr->g_recurrent) {
+    fov_conv_cfg w = rec_conv_cfg(cfg);
+    w.y_img_stride = g.z_b;
+    for (int t = 0; t < cfg->T; ++t) {
+      const float* hprev;
+      if (t == 0) {
+        if (!io->h0) continue;
+        hprev = io->h0; w.x_img_stride = g.hw_f; w.x_pix_stride = F;
+      } else {
+        hprev = io->hseq + (t - 1) * cfg->h_t_stride; w.x_img_stride = cfg->h_b_stride; w.x_pix_stride = cfg->h_pix_stride;
+      }
+      if ((rc = fov_conv2d_bwd_weight(&w, hprev, io->gates + t * g.z_t, gr->g_recurrent, nullptr, stream))) return rc;
+    }
+  }
+  return FOV_OK;
+}

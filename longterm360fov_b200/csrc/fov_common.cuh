@@ -1,0 +1,86 @@
+// Shared device/host helpers for libfov360 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/fov360.h"
+
+void fov_set_error(const char* fmt, ...);
+// number of kernel launches issued by this library since load (diagnostics only)
+extern unsigned long long g_fov_launches;
+
+#define FOV_CHECK_ARG(cond, msg)                                   \
+  do {                                                             \
+    if (!(cond)) {                                                 \
+      fov_set_error("%s: %s", __func__, msg);                      \
+      return FOV_ERR_ARG;                                          \
+    }                                                              \
+  } while (0)
+
+#define FOV_CUDA_LAUNCH_CHECK()                                              \
+  do {                                                                       \
+    ++g_fov_launches;                                                        \
+    cudaError_t e__ = cudaGetLastError();                                    \
+    if (e__ != cudaSuccess) {                                                \
+      fov_set_error("%s: CUDA error %s", __func__, cudaGetErrorString(e__)); \
+      return FOV_ERR_CUDA;                                                   \
+    }                                                                        \
+  } while (0)
+
+__device__ __forceinline__ float fov_hard_sigmoid(float x) {
+  return fminf(fmaxf(0.2f * x + 0.5f, 0.0f), 1.0f);
+}
+__device__ __forceinline__ float fov_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int REC>
+__device__ __forceinline__ float fov_rec_act(float x) {
+  return REC == FOV_REC_HARD_SIGMOID ? fov_hard_sigmoid(x) : fov_sigmoid(x);
+}
+// derivative of the recurrent activation expressed through its OUTPUT a
+template <int REC>
+__device__ __forceinline__ float fov_rec_act_grad(float a) {
+  if (REC == FOV_REC_HARD_SIGMOID) return (a > 0.0f && a < 1.0f) ? 0.2f : 0.0f;
+  return a * (1.0f - a);
+}
+__device__ __forceinline__ float fov_rec_act_rt(int rec, float x) {
+  return rec == FOV_REC_HARD_SIGMOID ? fov_hard_sigmoid(x) : fov_sigmoid(x);
+}
+__device__ __forceinline__ float fov_rec_act_grad_rt(int rec, float a) {
+  if (rec == FOV_REC_HARD_SIGMOID) return (a > 0.0f && a < 1.0f) ? 0.2f : 0.0f;
+  return a * (1.0f - a);
+}
+__device__ __forceinline__ float fov_act(int act, float x) {
+  if (act == FOV_ACT_TANH) return tanhf(x);
+  if (act == FOV_ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+// derivative of the activation expressed through its OUTPUT y
+__device__ __forceinline__ float fov_act_grad(int act, float y) {
+  if (act == FOV_ACT_TANH) return 1.0f - y * y;
+  if (act == FOV_ACT_RELU) return y > 0.0f ? 1.0f : 0.0f;
+  return 1.0f;
+}
+
+__device__ __forceinline__ void fov_cp_async4(float* smem_dst, const float* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void fov_cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void fov_cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+}
+
+static inline int fov_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}

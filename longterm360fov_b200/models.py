@@ -1,0 +1,633 @@
+"""Keras-shaped models over the fov360 kernels.
+
+The reference scripts build a Keras functional graph and then call
+``model.compile / fit / predict / save``; the builders here return objects with the
+same call shape so a script swaps its ``Model(...)`` for one of these and nothing
+else changes.  Graph topologies follow SURVEY.md section 8a':
+
+* ``fov_seq2seq``            - mycode/FoV_seq2seq.py:82-103 (M1) and, with
+                               ``num_encoder_tokens=6``, mycode/FoV_seq2seq_mu_var.py:219-248 (M2);
+                               ``teacher_forcing=False`` is mycode/FoV_seq2seq_no_teac_forc.py:37-149.
+* ``others_lstm_span_whole`` - mycode/others_LSTM_span_whole.py:77-353, concat-state branch (M3).
+* ``convlstm_seq2seq``       - mycode/convlstm_seq2seq.py:73-287 (M4).
+"""
+from __future__ import annotations
+
+import collections
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+def _init_weights(kind, **kw):
+    """Keras-default initialisers (glorot_uniform / orthogonal / forget-bias 1).
+    Pure NumPy on the host; kept here (not imported from oracle/)."""
+    from . import initializers as ini
+    return getattr(ini, kind)(**kw)
+
+
+LOSS_ALIASES = {
+    "mean_squared_error": "mse", "mse": "mse", "_mse": "mse",
+    "likelihood_loss": "nll", "nll": "nll",
+    "categorical_crossentropy": "cce", "cce": "cce",
+}
+
+
+class Adam:
+    """keras.optimizers.Adam (Keras 2.2 update rule, epsilon outside the bias correction)."""
+
+    def __init__(self, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, clipnorm=None):
+        if clipnorm is not None:
+            raise NotImplementedError("clipnorm is not used by the reference's compiled models "
+                                      "(mycode/others_LSTM_span_whole.py:351-352 passes the string 'Adam')")
+        self.lr, self.beta_1, self.beta_2, self.epsilon = lr, beta_1, beta_2, epsilon
+        self.iterations = 0
+        self.state = None
+
+    def init(self, n, device):
+        self.state = (torch.zeros(n, device=device), torch.zeros(n, device=device))
+
+    def step(self, p, g, grad_scale=1.0):
+        self.iterations += 1
+        ops.adam_step(p, g, self.state[0], self.state[1], self.iterations, self.lr, self.beta_1,
+                      self.beta_2, self.epsilon, grad_scale)
+
+
+class RMSprop:
+    """keras.optimizers.RMSprop (Keras 2.2 update rule)."""
+
+    def __init__(self, lr=1e-3, rho=0.9, epsilon=1e-7):
+        self.lr, self.rho, self.epsilon = lr, rho, epsilon
+        self.iterations = 0
+        self.state = None
+
+    def init(self, n, device):
+        self.state = (torch.zeros(n, device=device),)
+
+    def step(self, p, g, grad_scale=1.0):
+        self.iterations += 1
+        ops.rmsprop_step(p, g, self.state[0], self.lr, self.rho, self.epsilon, grad_scale)
+
+
+def _make_optimizer(opt):
+    if isinstance(opt, str):
+        name = opt.lower()
+        if name == "adam":
+            return Adam()
+        if name == "rmsprop":
+            return RMSprop()
+        raise ValueError("unsupported optimizer %r" % opt)
+    return opt
+
+
+class History:
+    def __init__(self):
+        self.history = collections.defaultdict(list)
+        self.epoch = []
+
+
+class Model:
+    """Common Keras-shaped surface; subclasses provide ``_forward`` and ``weight_order``."""
+
+    weight_order: list = []
+    n_inputs = 2
+    n_outputs = 1
+
+    def __init__(self, weights, device=None):
+        _lib.load()                                   # fail loudly without the CUDA library
+        if device is None:
+            if not torch.cuda.is_available():
+                raise _lib.FovError("no CUDA device: the fov360 models have no CPU fallback")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        sizes = [(k, tuple(np.shape(weights[k]))) for k in self.weight_order]
+        # 64-float (256 B) alignment of every tensor inside the flat buckets
+        self._offsets, off = {}, 0
+        for k, shp in sizes:
+            self._offsets[k] = (off, shp)
+            off += (int(np.prod(shp)) + 63) // 64 * 64
+        self.n_flat = off
+        self.flat = torch.zeros(off, device=self.device)
+        self.gflat = torch.zeros(off, device=self.device)
+        self.params, self.grads = collections.OrderedDict(), collections.OrderedDict()
+        for k, (o, shp) in self._offsets.items():
+            n = int(np.prod(shp))
+            self.params[k] = self.flat[o:o + n].view(shp).requires_grad_(True)
+            self.grads[k] = self.gflat[o:o + n].view(shp)
+        self.set_weights([weights[k] for k in self.weight_order])
+        self.optimizer = None
+        self.loss_kinds = None
+        self.loss_weights = None
+        self.stop_training = False
+        self.process_group = None
+        self.world_size = 1
+        self.running_length = 10
+
+    # ------------------------------------------------------------------ #
+    # weights
+    # ------------------------------------------------------------------ #
+    def get_weights(self):
+        return [self.params[k].detach().cpu().numpy().copy() for k in self.weight_order]
+
+    def set_weights(self, arrays):
+        assert len(arrays) == len(self.weight_order)
+        with torch.no_grad():
+            for k, a in zip(self.weight_order, arrays):
+                t = torch.as_tensor(np.asarray(a, dtype=np.float32))
+                assert tuple(t.shape) == self._offsets[k][1], (k, t.shape, self._offsets[k][1])
+                self.params[k].copy_(t.to(self.device))
+
+    def get_weights_dict(self):
+        return {k: v for k, v in zip(self.weight_order, self.get_weights())}
+
+    def save_weights(self, path):
+        """Keras-layout weights as .npz keyed by layer/weight name (h5py is unavailable)."""
+        if not path.endswith(".npz"):
+            path = path + ".npz"
+        np.savez(path, **{k.replace("/", "__"): v for k, v in self.get_weights_dict().items()})
+
+    save = save_weights
+
+    def load_weights(self, path):
+        if not path.endswith(".npz") and not os.path.exists(path):
+            path = path + ".npz"
+        z = np.load(path)
+        self.set_weights([z[k.replace("/", "__")] for k in self.weight_order])
+
+    def count_params(self):
+        return sum(int(np.prod(s)) for _, s in self._offsets.values())
+
+    # ------------------------------------------------------------------ #
+    # compile / distribute
+    # ------------------------------------------------------------------ #
+    def compile(self, optimizer="Adam", loss="mean_squared_error", loss_weights=None, metrics=None):
+        self.optimizer = _make_optimizer(optimizer)
+        self.optimizer.init(self.n_flat, self.device)
+        losses = loss if isinstance(loss, (list, tuple)) else [loss] * self.n_outputs
+        kinds = []
+        for l in losses:
+            name = l if isinstance(l, str) else getattr(l, "__name__", str(l))
+            if name not in LOSS_ALIASES:
+                raise ValueError("unsupported loss %r" % (l,))
+            kinds.append(LOSS_ALIASES[name])
+        self.loss_kinds = kinds
+        self.loss_weights = [1.0] * len(kinds) if loss_weights is None else [float(w) for w in loss_weights]
+        return self
+
+    def distribute(self, process_group=None):
+        """Data-parallel training: batch sharded by rank by the caller, one summed
+        allreduce of the flat gradient bucket per step (NCCL over NVLink on GPUs)."""
+        import torch.distributed as dist
+        self.process_group = process_group if process_group is not None else dist.group.WORLD
+        self.world_size = dist.get_world_size(self.process_group)
+        # identical start: broadcast rank 0's parameters
+        dist.broadcast(self.flat, src=0, group=self.process_group)
+        return self
+
+    # ------------------------------------------------------------------ #
+    # steps
+    # ------------------------------------------------------------------ #
+    def _to_dev(self, arrs):
+        out = []
+        for a in arrs:
+            if isinstance(a, torch.Tensor):
+                t = a
+                if t.dtype != torch.float32:
+                    t = t.float()
+            else:
+                t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+            out.append(t.to(self.device, non_blocking=True))
+        return out
+
+    @staticmethod
+    def _as_list(x):
+        return list(x) if isinstance(x, (list, tuple)) else [x]
+
+    def _forward(self, inputs, training):
+        raise NotImplementedError
+
+    def _loss(self, outs, ys):
+        total = None
+        for o, y, kind, w in zip(outs, ys, self.loss_kinds, self.loss_weights):
+            l = ops.loss(kind, y, o, w, self.running_length)
+            total = l if total is None else total + l
+        return total
+
+    def train_step_device(self, xs, ys):
+        """One optimiser step on device tensors; returns the loss as a device tensor
+        (no host sync).  DP: gradients are sum-allreduced and scaled by 1/world."""
+        self.gflat.zero_()
+        outs = self._forward(xs, True)
+        total = self._loss(outs, ys)
+        total.backward()
+        scale = 1.0
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.gflat, group=self.process_group)
+            scale = 1.0 / self.world_size
+        with torch.no_grad():
+            self.optimizer.step(self.flat, self.gflat, scale)
+        return total.detach()
+
+    def train_on_batch(self, x, y):
+        xs, ys = self._to_dev(self._as_list(x)), self._to_dev(self._as_list(y))
+        return float(self.train_step_device(xs, ys).item())
+
+    def test_on_batch(self, x, y):
+        xs, ys = self._to_dev(self._as_list(x)), self._to_dev(self._as_list(y))
+        with torch.no_grad():
+            outs = self._forward(xs, False)
+            return float(self._loss(outs, ys).item())
+
+    def predict_on_batch(self, x):
+        xs = self._to_dev(self._as_list(x))
+        with torch.no_grad():
+            outs = self._forward(xs, False)
+        outs = [o.cpu().numpy() for o in outs]
+        return outs if self.n_outputs > 1 else outs[0]
+
+    def predict(self, x, batch_size=32, verbose=0):
+        xs = self._as_list(x)
+        n = len(xs[0])
+        chunks = []
+        for s in range(0, n, batch_size):
+            o = self.predict_on_batch([a[s:s + batch_size] for a in xs])
+            chunks.append(o if isinstance(o, list) else [o])
+        outs = [np.concatenate([c[i] for c in chunks], axis=0) for i in range(self.n_outputs)]
+        return outs if self.n_outputs > 1 else outs[0]
+
+    def evaluate(self, x, y, batch_size=32, verbose=0):
+        xs, ys = self._as_list(x), self._as_list(y)
+        n = len(xs[0])
+        tot = 0.0
+        for s in range(0, n, batch_size):
+            b = len(xs[0][s:s + batch_size])
+            tot += b * self.test_on_batch([a[s:s + batch_size] for a in xs], [a[s:s + batch_size] for a in ys])
+        return tot / n
+
+    def fit(self, x, y, batch_size=32, epochs=1, validation_split=0.0, shuffle=True, initial_epoch=0,
+            callbacks=None, validation_data=None, verbose=0):
+        """keras Model.fit semantics used by the scripts (mycode/FoV_seq2seq.py:112-117):
+        the validation set is the LAST ``validation_split`` fraction taken before any
+        shuffling, training indices are reshuffled every epoch, the last partial batch
+        is kept, the epoch loss is the sample-weighted mean of the batch losses."""
+        if self.optimizer is None:
+            raise RuntimeError("compile() the model first")
+        xs = [np.asarray(a) for a in self._as_list(x)]
+        ys = [np.asarray(a) for a in self._as_list(y)]
+        n = len(xs[0])
+        if validation_data is not None:
+            vx, vy = self._as_list(validation_data[0]), self._as_list(validation_data[1])
+        elif validation_split and validation_split > 0.0:
+            split = int(n * (1.0 - validation_split))
+            vx, vy = [a[split:] for a in xs], [a[split:] for a in ys]
+            xs, ys = [a[:split] for a in xs], [a[:split] for a in ys]
+            n = split
+        else:
+            vx = vy = None
+        hist = History()
+        callbacks = callbacks or []
+        for cb in callbacks:
+            cb.set_model(self)
+            cb.on_train_begin()
+        self.stop_training = False
+        for epoch in range(initial_epoch, epochs):
+            idx = np.random.permutation(n) if shuffle else np.arange(n)
+            tot = 0.0
+            for s in range(0, n, batch_size):
+                bi = idx[s:s + batch_size]
+                l = self.train_on_batch([a[bi] for a in xs], [a[bi] for a in ys])
+                tot += l * len(bi)
+            logs = {"loss": tot / n}
+            if vx is not None:
+                logs["val_loss"] = self.evaluate(vx, vy, batch_size)
+            logs["lr"] = self.optimizer.lr
+            hist.epoch.append(epoch)
+            for k, v in logs.items():
+                hist.history[k].append(v)
+            if verbose:
+                print("Epoch %d/%d - " % (epoch + 1, epochs) + " - ".join("%s: %.6f" % kv for kv in logs.items()))
+            for cb in callbacks:
+                cb.on_epoch_end(epoch, logs)
+            if self.stop_training:
+                break
+        return hist
+
+    def fit_generator(self, generator, steps_per_epoch, epochs=1, validation_data=None,
+                      validation_steps=None, callbacks=None, initial_epoch=0, verbose=0, **_):
+        """keras Model.fit_generator (mycode/convlstm_heatmap.py:415-418): the generator
+        yields (inputs, targets) batches forever."""
+        hist = History()
+        callbacks = callbacks or []
+        for cb in callbacks:
+            cb.set_model(self)
+            cb.on_train_begin()
+        self.stop_training = False
+        for epoch in range(initial_epoch, epochs):
+            tot, cnt = 0.0, 0
+            for _ in range(steps_per_epoch):
+                bx, by = next(generator)
+                b = len(self._as_list(bx)[0])
+                tot += b * self.train_on_batch(bx, by)
+                cnt += b
+            logs = {"loss": tot / max(cnt, 1)}
+            if validation_data is not None:
+                if isinstance(validation_data, tuple):
+                    logs["val_loss"] = self.evaluate(validation_data[0], validation_data[1])
+                else:
+                    vt, vc = 0.0, 0
+                    for _ in range(validation_steps or 1):
+                        bx, by = next(validation_data)
+                        b = len(self._as_list(bx)[0])
+                        vt += b * self.test_on_batch(bx, by)
+                        vc += b
+                    logs["val_loss"] = vt / max(vc, 1)
+            logs["lr"] = self.optimizer.lr
+            hist.epoch.append(epoch)
+            for k, v in logs.items():
+                hist.history[k].append(v)
+            for cb in callbacks:
+                cb.on_epoch_end(epoch, logs)
+            if self.stop_training:
+                break
+        return hist
+
+    def _sinks(self, *names):
+        return tuple(self.grads[n] for n in names)
+
+
+# --------------------------------------------------------------------------- #
+# M1 / M2: target-only fc-LSTM encoder-decoder
+# --------------------------------------------------------------------------- #
+
+
+class _SubModel:
+    """encoder_model / decoder_model of mycode/FoV_seq2seq.py:137-148."""
+
+    def __init__(self, fn):
+        self._fn = fn
+
+    def predict(self, x, batch_size=32, verbose=0):
+        return self._fn(x)
+
+    predict_on_batch = predict
+
+
+class FovSeq2Seq(Model):
+    weight_order = ["encoder/kernel", "encoder/recurrent_kernel", "encoder/bias",
+                    "decoder/kernel", "decoder/recurrent_kernel", "decoder/bias",
+                    "decoder_dense/kernel", "decoder_dense/bias"]
+
+    def __init__(self, weights, teacher_forcing=True, max_decoder_seq_length=10,
+                 decoder_no_init_state=False, recurrent_activation="hard_sigmoid", device=None):
+        super().__init__(weights, device)
+        self.teacher_forcing = teacher_forcing
+        self.T_dec = max_decoder_seq_length
+        self.decoder_no_init_state = decoder_no_init_state
+        self.rec_act = recurrent_activation
+        self.encoder_model = _SubModel(self._encode)
+        self.decoder_model = _SubModel(self._decode_step)
+
+    def _w(self):
+        p = self.params
+        return [p[k] for k in self.weight_order]
+
+    def _lstm_sinks(self):
+        g = self.grads
+        return {"enc_kernel": g["encoder/kernel"], "enc_recurrent": g["encoder/recurrent_kernel"],
+                "enc_bias": g["encoder/bias"], "dec_kernel": g["decoder/kernel"],
+                "dec_recurrent": g["decoder/recurrent_kernel"], "dec_bias": g["decoder/bias"],
+                "head_kernel": g["decoder_dense/kernel"], "head_bias": g["decoder_dense/bias"]}
+
+    def _forward(self, inputs, training, teacher_forcing=None, steps=None):
+        enc, dec = inputs
+        tf = self.teacher_forcing if teacher_forcing is None else teacher_forcing
+        T_dec = dec.shape[1] if tf else (steps or self.T_dec)
+        opts = {"T_dec": T_dec, "teacher_forcing": tf, "head_act": "tanh", "rec_act": self.rec_act,
+                "dec_zero_init": self.decoder_no_init_state, "training": training}
+        y, _ = ops.LSTMSeq2SeqFn.apply(opts, self._lstm_sinks() if training else None, enc, dec, None,
+                                       *self._w())
+        return [y]
+
+    # --- inference sub-models (mycode/FoV_seq2seq.py:137-178) --- #
+    def _encode(self, x):
+        (x,) = self._to_dev([x])
+        p = self.params
+        with torch.no_grad():
+            h, c = ops.lstm_states(x, p["encoder/kernel"], p["encoder/recurrent_kernel"], p["encoder/bias"],
+                                   self.rec_act)
+        return [h.cpu().numpy(), c.cpu().numpy()]
+
+    def _decode_step(self, inputs):
+        x, h, c = self._to_dev(inputs)
+        p = self.params
+        with torch.no_grad():
+            y, h, c = ops.lstm_decode_steps(x, h, c, p["decoder/kernel"], p["decoder/recurrent_kernel"],
+                                            p["decoder/bias"], p["decoder_dense/kernel"],
+                                            p["decoder_dense/bias"], x.shape[1], True, "tanh", self.rec_act)
+        return [y.cpu().numpy(), h.cpu().numpy(), c.cpu().numpy()]
+
+    def decode_sequence_fov(self, input_seq, last_mu_var=None, steps=None):
+        """Batched form of decode_sequence_fov (mycode/FoV_seq2seq.py:154-178,
+        mycode/FoV_seq2seq_mu_var.py:286-311): encoder once, then ``steps`` decoder
+        steps feeding the output back, all inside ONE persistent kernel launch.
+        ``last_mu_var`` (B,1,6) defaults to the mean/var of the last observed second."""
+        xs = self._to_dev([input_seq])[0]
+        if last_mu_var is None:
+            if xs.shape[-1] == 90:
+                last_mu_var = ops.mean_var_xyz(xs[:, -1:, :].contiguous())
+            else:
+                last_mu_var = xs[:, -1:, :].contiguous()
+        else:
+            last_mu_var = self._to_dev([last_mu_var])[0]
+        with torch.no_grad():
+            y = self._forward([xs, last_mu_var], False, teacher_forcing=False, steps=steps)[0]
+        return y.cpu().numpy()
+
+
+def fov_seq2seq(latent_dim=64, num_encoder_tokens=90, num_decoder_tokens=6, max_encoder_seq_length=10,
+                max_decoder_seq_length=10, teacher_forcing=True, decoder_no_init_state=False,
+                recurrent_activation="hard_sigmoid", weights=None, seed=1, device=None):
+    """Builder for M1 (mycode/FoV_seq2seq.py:19-28,82-103).  Inputs
+    ``[encoder_inputs (B,T,num_encoder_tokens), decoder_inputs (B,T,6) | (B,1,6)]`` ->
+    ``decoder_outputs (B,T,6)``."""
+    if weights is None:
+        weights = _init_weights("init_fov_seq2seq", seed=seed, num_encoder_tokens=num_encoder_tokens,
+                                num_decoder_tokens=num_decoder_tokens, latent_dim=latent_dim)
+    return FovSeq2Seq(weights, teacher_forcing, max_decoder_seq_length, decoder_no_init_state,
+                      recurrent_activation, device)
+
+
+def fov_seq2seq_mu_var(latent_dim=64, num_decoder_tokens=6, **kw):
+    """Builder for M2 (mycode/FoV_seq2seq_mu_var.py:40-49,219-248): encoder consumes the
+    per-second mean/var (B,10,6)."""
+    return fov_seq2seq(latent_dim=latent_dim, num_encoder_tokens=6, num_decoder_tokens=num_decoder_tokens, **kw)
+
+
+# --------------------------------------------------------------------------- #
+# M3: concat-state model with others' whole-span ConvLSTM
+# --------------------------------------------------------------------------- #
+
+
+class OthersLSTMSpanWhole(Model):
+    n_inputs, n_outputs = 3, 3
+    weight_order = (
+        ["oth_convlstm%d/%s" % (l, n) for l in range(3) for n in ("kernel", "recurrent_kernel", "bias")] +
+        ["oth_recon_dense/kernel", "oth_recon_dense/bias", "oth_flat_dense/kernel", "oth_flat_dense/bias",
+         "encoder/kernel", "encoder/recurrent_kernel", "encoder/bias",
+         "decoder/kernel", "decoder/recurrent_kernel", "decoder/bias",
+         "encoder_dense/kernel", "encoder_dense/bias", "decoder_dense/kernel", "decoder_dense/bias"])
+
+    def __init__(self, weights, max_encoder_seq_length=10, max_decoder_seq_length=10,
+                 recurrent_activation="hard_sigmoid", device=None):
+        super().__init__(weights, device)
+        self.T_enc, self.T_dec = max_encoder_seq_length, max_decoder_seq_length
+        self.rec_act = recurrent_activation
+        self.latent = weights["encoder/recurrent_kernel"].shape[0]
+        self._zero_bias = torch.zeros(6, device=self.device)
+        self._zero_bias_grad = torch.zeros(6, device=self.device)
+
+    def _forward(self, inputs, training):
+        enc_in, oth_in, dec_in = inputs
+        p, g = self.params, self.grads
+        B, Tall = oth_in.shape[0], oth_in.shape[1]
+        Hl = self.latent
+        wl = [(p["oth_convlstm%d/kernel" % l], p["oth_convlstm%d/recurrent_kernel" % l],
+               p["oth_convlstm%d/bias" % l]) for l in range(3)]
+        sl = [(g["oth_convlstm%d/kernel" % l], g["oth_convlstm%d/recurrent_kernel" % l],
+               g["oth_convlstm%d/bias" % l]) for l in range(3)] if training else None
+        cat, _ = ops.convlstm_stack(oth_in, wl, None, sl, rec_act=self.rec_act, training=training)
+        flat = cat.view(B, Tall, -1)
+        r_oth = ops.dense(flat, p["oth_recon_dense/kernel"], p["oth_recon_dense/bias"], None,
+                          self._sinks("oth_recon_dense/kernel", "oth_recon_dense/bias"), training)
+        s = ops.dense(flat[:, self.T_enc:], p["oth_flat_dense/kernel"], p["oth_flat_dense/bias"], None,
+                      self._sinks("oth_flat_dense/kernel", "oth_flat_dense/bias"), training)
+        # decoder_dense(Concat[h_dec, s]) = h_dec . Wd[:H] + (s . Wd[H:] + bd): the second term does
+        # not depend on the recurrence, so it is computed for all steps at once and enters the
+        # persistent kernel as the additive head term.
+        Wd, bd = p["decoder_dense/kernel"], p["decoder_dense/bias"]
+        gWd = g["decoder_dense/kernel"]
+        e = ops.dense(s, Wd[Hl:], bd, None, (gWd[Hl:], g["decoder_dense/bias"]), training)
+        opts = {"T_dec": self.T_dec, "teacher_forcing": False, "head_act": None, "rec_act": self.rec_act,
+                "dec_zero_init": False, "training": training}
+        sinks = None
+        if training:
+            sinks = {"enc_kernel": g["encoder/kernel"], "enc_recurrent": g["encoder/recurrent_kernel"],
+                     "enc_bias": g["encoder/bias"], "dec_kernel": g["decoder/kernel"],
+                     "dec_recurrent": g["decoder/recurrent_kernel"], "dec_bias": g["decoder/bias"],
+                     "head_kernel": gWd[:Hl], "head_bias": self._zero_bias_grad}
+        y, enc_seq = ops.LSTMSeq2SeqFn.apply(
+            opts, sinks, enc_in, dec_in, e, p["encoder/kernel"], p["encoder/recurrent_kernel"],
+            p["encoder/bias"], p["decoder/kernel"], p["decoder/recurrent_kernel"], p["decoder/bias"],
+            Wd[:Hl], self._zero_bias)
+        r_tar = ops.dense(enc_seq, p["encoder_dense/kernel"], p["encoder_dense/bias"], "tanh",
+                          self._sinks("encoder_dense/kernel", "encoder_dense/bias"), training)
+        return [y, r_oth, r_tar]
+
+
+def others_lstm_span_whole(latent_dim=64, num_user=34, kernel_size=5, max_encoder_seq_length=10,
+                           max_decoder_seq_length=10, oth_filters=(32, 16, 8), flat_dense=256,
+                           recurrent_activation="hard_sigmoid", dropout=0.0, weights=None, seed=1, device=None):
+    """Builder for M3, the canonical concat-state model (SURVEY.md hazard 2):
+    inputs ``[encoder_inputs (B,10,6), encoder_inputs_oth (B,20,1,num_user-1,6),
+    decoder_inputs (B,1,6)]`` -> ``[decoder_outputs (B,10,6), decoder_outputs_oth
+    (B,20,(num_user-1)*6), encoder_reconstruct_tar (B,10,6)]``
+    (mycode/others_LSTM_span_whole.py:348-349)."""
+    if dropout:
+        raise NotImplementedError("ConvLSTM input dropout is not built yet; parity runs use dropout=0")
+    if weights is None:
+        weights = _init_weights("init_others_lstm_span_whole", seed=seed, num_user=num_user,
+                                kernel_size=kernel_size, latent_dim=latent_dim, oth_filters=oth_filters,
+                                flat_dense=flat_dense)
+    return OthersLSTMSpanWhole(weights, max_encoder_seq_length, max_decoder_seq_length,
+                               recurrent_activation, device)
+
+
+# --------------------------------------------------------------------------- #
+# M4: ConvLSTM encoder-decoder (heatmap / trajectory forms)
+# --------------------------------------------------------------------------- #
+
+
+class ConvLSTMSeq2Seq(Model):
+    def __init__(self, weights, head_kind="conv2d", max_decoder_seq_length=10, dilation_rate=1,
+                 recurrent_activation="hard_sigmoid", device=None):
+        order = ["%s_convlstm%d/%s" % (s, l, n) for s in ("enc", "dec") for l in range(3)
+                 for n in ("kernel", "recurrent_kernel", "bias")]
+        if head_kind in ("conv2d", "conv1d"):
+            order += ["head_conv%d/%s" % (l, n) for l in range(3) for n in ("kernel", "bias")]
+        else:
+            order += ["head_dense/kernel", "head_dense/bias"]
+        self.weight_order = order
+        super().__init__(weights, device)
+        self.head_kind = head_kind
+        self.T_dec = max_decoder_seq_length
+        self.dilation = (dilation_rate, dilation_rate)
+        self.rec_act = recurrent_activation
+
+    def _stack(self, side, x, states, training):
+        p, g = self.params, self.grads
+        wl = [(p["%s_convlstm%d/kernel" % (side, l)], p["%s_convlstm%d/recurrent_kernel" % (side, l)],
+               p["%s_convlstm%d/bias" % (side, l)]) for l in range(3)]
+        sl = [(g["%s_convlstm%d/kernel" % (side, l)], g["%s_convlstm%d/recurrent_kernel" % (side, l)],
+               g["%s_convlstm%d/bias" % (side, l)]) for l in range(3)] if training else None
+        return ops.convlstm_stack(x, wl, states, sl, self.dilation, self.rec_act, training)
+
+    def _forward(self, inputs, training):
+        enc_in, dec_in = inputs
+        p = self.params
+        B = enc_in.shape[0]
+        _, states = self._stack("enc", enc_in, None, training)
+        x = dec_in[:, 0:1]
+        outs = []
+        for _ in range(self.T_dec):
+            cat, states = self._stack("dec", x, states, training)
+            d = cat[:, 0]                                              # (B,H,W,56)
+            if self.head_kind == "conv2d":
+                y = d
+                for l in range(3):
+                    y = ops.conv2d(y, p["head_conv%d/kernel" % l], p["head_conv%d/bias" % l], "relu", (1, 1),
+                                   self._sinks("head_conv%d/kernel" % l, "head_conv%d/bias" % l), training)
+                y = ops.SoftmaxFn.apply(y)
+                x = y.unsqueeze(1)
+            elif self.head_kind == "conv1d":
+                y = d[:, 0]
+                for l in range(3):
+                    y = ops.conv1d(y, p["head_conv%d/kernel" % l], p["head_conv%d/bias" % l],
+                                   "relu" if l < 2 else None,
+                                   self._sinks("head_conv%d/kernel" % l, "head_conv%d/bias" % l), training)
+                y = ops.SoftmaxFn.apply(y)                             # Conv1D(activation='softmax'), :188-189
+                y = y.unsqueeze(1)
+                x = y.unsqueeze(1)
+            else:
+                y = ops.dense(d[:, 0].reshape(B, -1), p["head_dense/kernel"], p["head_dense/bias"], None,
+                              self._sinks("head_dense/kernel", "head_dense/bias"), training)
+                x = y.view(B, 1, 1, 1, -1)
+            outs.append(y)
+        return [torch.stack(outs, dim=1)]
+
+
+def convlstm_seq2seq(latent_dim=16, kernel_size=5, dilation_rate=1, use_one_hot=True, input_mean_var=False,
+                     predict_mean_var=False, max_decoder_seq_length=10, fps=30, head=(512, 1024, None),
+                     recurrent_activation="hard_sigmoid", dropout=0.0, weights=None, seed=1, device=None):
+    """Builder for M4 (mycode/convlstm_seq2seq.py:32-45,73-287).
+    heatmap form (``use_one_hot=True``): ``[encoder_inputs (B,10,36,18,fps), decoder_inputs
+    (B,1,36,18,fps)]`` -> ``(B,10,36,18,fps)``, heads Conv2D 56->512->1024->fps + channel softmax.
+    trajectory form: ``(B,10,1,fps,3)`` images with the Conv1D(k=7) head, or, with
+    ``input_mean_var`` and ``predict_mean_var``, ``(B,10,1,1,6)`` images with a Dense(6) head."""
+    if dropout:
+        raise NotImplementedError("ConvLSTM input dropout is not built yet; parity runs use dropout=0")
+    filters = (latent_dim * 2, latent_dim, latent_dim // 2)
+    if use_one_hot:
+        kind, in_ch, hd = "conv2d", fps, (head[0], head[1], fps)
+    elif predict_mean_var:
+        kind, in_ch, hd = "dense", 6 if input_mean_var else 3, None
+    else:
+        kind, in_ch, hd = "conv1d", 3, (head[0], head[1], 3)
+    if weights is None:
+        flat_dim = sum(filters) * (1 if input_mean_var else fps)
+        weights = _init_weights("init_convlstm_seq2seq", seed=seed, in_ch=in_ch, filters=filters,
+                                kernel_size=kernel_size, head=hd, head_kind=kind, flat_dim=flat_dim)
+    return ConvLSTMSeq2Seq(weights, kind, max_decoder_seq_length, dilation_rate, recurrent_activation, device)

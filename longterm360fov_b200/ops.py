@@ -1,0 +1,469 @@
+"""Thin torch.autograd.Functions over the C ABI of libfov360.so.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every
+FLOP on the hot path is one of our kernels.  Weight gradients are accumulated by
+the kernels straight into the flat gradient bucket (the ``sink`` tensors), so the
+Functions return ``None`` for weight inputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT, REC, ptr
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.contiguous().float()
+    return t
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.FovError("fov ops need CUDA tensors; there is no CPU fallback")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# --------------------------------------------------------------------------- #
+# persistent fc-LSTM encoder-decoder
+# --------------------------------------------------------------------------- #
+
+
+class LSTMSeq2SeqFn(torch.autograd.Function):
+    """y, enc_hseq = f(x_enc, x_dec, extra | enc/dec/head weights).
+
+    opts: dict(T_dec, teacher_forcing, head_act, rec_act, dec_zero_init, training)
+    sinks: dict name -> gradient view for the 8 weights (or None at inference).
+    """
+
+    @staticmethod
+    def forward(ctx, opts, sinks, x_enc, x_dec, extra, We, Ue, be, Wd, Ud, bd, Wo, bo):
+        lib = _lib.load()
+        _require_cuda(x_enc, x_dec, We)
+        x_enc, x_dec, extra = _f32c(x_enc), _f32c(x_dec), _f32c(extra)
+        B, T_enc, in_enc = x_enc.shape
+        in_dec = x_dec.shape[2]
+        H = Ue.shape[0]
+        out_dim = Wo.shape[1]
+        T_dec = opts["T_dec"]
+        training = bool(opts.get("training", False))
+        dev = x_enc.device
+        cfg = _lib.LstmCfg(B, T_enc, T_dec, in_enc, in_dec, H, out_dim,
+                           int(opts["teacher_forcing"]), ACT[opts.get("head_act")],
+                           REC[opts.get("rec_act", "hard_sigmoid")],
+                           int(opts.get("dec_zero_init", False)), int(training))
+        w = _lib.LstmWeights(ptr(We), ptr(Ue), ptr(be), ptr(Wd), ptr(Ud), ptr(bd), ptr(Wo), ptr(bo))
+        y = torch.empty(B, T_dec, out_dim, device=dev)
+        enc_hseq = torch.empty(B, T_enc, H, device=dev)
+        saved = {}
+        if training:
+            saved["enc_xh"] = torch.empty(B, T_enc, H + in_enc, device=dev)
+            saved["enc_gates"] = torch.empty(B, T_enc, 4 * H, device=dev)
+            saved["enc_c"] = torch.empty(B, T_enc, H, device=dev)
+            saved["dec_xh"] = torch.empty(B, T_dec, H + in_dec, device=dev)
+            saved["dec_gates"] = torch.empty(B, T_dec, 4 * H, device=dev)
+            saved["dec_c"] = torch.empty(B, T_dec, H, device=dev)
+            saved["dec_hseq"] = torch.empty(B, T_dec, H, device=dev)
+        io = _lib.LstmIO(ptr(x_enc), ptr(x_dec), ptr(extra), None, None, ptr(y), None, None,
+                         _lib.LstmSaved(ptr(saved.get("enc_xh")), ptr(saved.get("enc_gates")),
+                                        ptr(saved.get("enc_c")), ptr(enc_hseq)),
+                         _lib.LstmSaved(ptr(saved.get("dec_xh")), ptr(saved.get("dec_gates")),
+                                        ptr(saved.get("dec_c")), ptr(saved.get("dec_hseq"))))
+        _lib.check(lib.fov_lstm_seq2seq_fwd(C.byref(cfg), C.byref(w), C.byref(io), _stream()),
+                   "fov_lstm_seq2seq_fwd")
+        if training:
+            ctx.cfg, ctx.sinks, ctx.saved = cfg, sinks, saved
+            ctx.has_extra = extra is not None
+            ctx.save_for_backward(x_enc, x_dec, extra, We, Ue, be, Wd, Ud, bd, Wo, bo, y, enc_hseq)
+        return y, enc_hseq
+
+    @staticmethod
+    def backward(ctx, dy, dhseq_enc):
+        lib = _lib.load()
+        x_enc, x_dec, extra, We, Ue, be, Wd, Ud, bd, Wo, bo, y, enc_hseq = ctx.saved_tensors
+        cfg, s, sv = ctx.cfg, ctx.sinks, ctx.saved
+        dy = _f32c(dy) if dy is not None else torch.zeros_like(y)
+        dhseq_enc = _f32c(dhseq_enc)
+        dev = y.device
+        dz_enc = torch.empty(cfg.B, cfg.T_enc, 4 * cfg.H, device=dev)
+        dz_dec = torch.empty(cfg.B, cfg.T_dec, 4 * cfg.H, device=dev)
+        dpre = torch.empty_like(y)
+        w = _lib.LstmWeights(ptr(We), ptr(Ue), ptr(be), ptr(Wd), ptr(Ud), ptr(bd), ptr(Wo), ptr(bo))
+        io = _lib.LstmIO(ptr(x_enc), ptr(x_dec), ptr(extra), None, None, ptr(y), None, None,
+                         _lib.LstmSaved(ptr(sv["enc_xh"]), ptr(sv["enc_gates"]), ptr(sv["enc_c"]),
+                                        ptr(enc_hseq)),
+                         _lib.LstmSaved(ptr(sv["dec_xh"]), ptr(sv["dec_gates"]), ptr(sv["dec_c"]),
+                                        ptr(sv["dec_hseq"])))
+        g = _lib.LstmGrads(ptr(dy), ptr(dhseq_enc), ptr(y), ptr(dz_enc), ptr(dz_dec), ptr(dpre),
+                           ptr(s["enc_kernel"]), ptr(s["enc_recurrent"]), ptr(s["enc_bias"]),
+                           ptr(s["dec_kernel"]), ptr(s["dec_recurrent"]), ptr(s["dec_bias"]),
+                           ptr(s["head_kernel"]), ptr(s["head_bias"]))
+        _lib.check(lib.fov_lstm_seq2seq_bwd(C.byref(cfg), C.byref(w), C.byref(io), C.byref(g), _stream()),
+                   "fov_lstm_seq2seq_bwd")
+        d_extra = dpre if ctx.has_extra else None
+        return (None, None, None, None, d_extra) + (None,) * 8
+
+
+def lstm_states(x_enc, We, Ue, be, rec_act="hard_sigmoid", h0=None, c0=None):
+    """encoder_model.predict: final [h, c] of the encoder LSTM (mycode/FoV_seq2seq.py:137,156)."""
+    lib = _lib.load()
+    _require_cuda(x_enc)
+    x_enc = _f32c(x_enc)
+    B, T, in_enc = x_enc.shape
+    H = Ue.shape[0]
+    cfg = _lib.LstmCfg(B, T, 0, in_enc, 0, H, 0, 1, 0, REC[rec_act], 0, 0)
+    w = _lib.LstmWeights(ptr(We), ptr(Ue), ptr(be), None, None, None, None, None)
+    hT = torch.empty(B, H, device=x_enc.device)
+    cT = torch.empty(B, H, device=x_enc.device)
+    io = _lib.LstmIO(ptr(x_enc), None, None, ptr(_f32c(h0)), ptr(_f32c(c0)), None, ptr(hT), ptr(cT),
+                     _lib.LstmSaved(), _lib.LstmSaved())
+    _lib.check(lib.fov_lstm_seq2seq_fwd(C.byref(cfg), C.byref(w), C.byref(io), _stream()), "lstm_states")
+    return hT, cT
+
+
+def lstm_decode_steps(x_dec, h0, c0, Wd, Ud, bd, Wo, bo, T_dec, teacher_forcing, head_act="tanh",
+                      rec_act="hard_sigmoid", extra=None):
+    """decoder_model.predict: run T_dec decoder steps from given states
+    (mycode/FoV_seq2seq.py:139-148,167).  Returns (y, h, c)."""
+    lib = _lib.load()
+    _require_cuda(x_dec)
+    x_dec = _f32c(x_dec)
+    B, _, in_dec = x_dec.shape
+    H = Ud.shape[0]
+    out_dim = Wo.shape[1]
+    cfg = _lib.LstmCfg(B, 0, T_dec, 0, in_dec, H, out_dim, int(teacher_forcing), ACT[head_act],
+                       REC[rec_act], 0, 0)
+    w = _lib.LstmWeights(None, None, None, ptr(Wd), ptr(Ud), ptr(bd), ptr(Wo), ptr(bo))
+    dev = x_dec.device
+    y = torch.empty(B, T_dec, out_dim, device=dev)
+    hT = torch.empty(B, H, device=dev)
+    cT = torch.empty(B, H, device=dev)
+    io = _lib.LstmIO(None, ptr(x_dec), ptr(_f32c(extra)), ptr(_f32c(h0)), ptr(_f32c(c0)), ptr(y), ptr(hT),
+                     ptr(cT), _lib.LstmSaved(), _lib.LstmSaved())
+    _lib.check(lib.fov_lstm_seq2seq_fwd(C.byref(cfg), C.byref(w), C.byref(io), _stream()), "lstm_decode_steps")
+    return y, hT, cT
+
+
+# --------------------------------------------------------------------------- #
+# conv / dense
+# --------------------------------------------------------------------------- #
+
+
+def _conv_cfg(N, H, W, Cin, Cout, kh, kw, dil, act, beta, x_img, x_pix, y_img, y_pix):
+    return _lib.ConvCfg(N, H, W, Cin, Cout, kh, kw, dil[0], dil[1],
+                        ((kh - 1) * dil[0]) // 2, ((kw - 1) * dil[1]) // 2,
+                        x_img, x_pix, y_img, y_pix, ACT[act], float(beta))
+
+
+class Conv2DFn(torch.autograd.Function):
+    """keras Conv2D(padding='same')/Dense: x (N,H,W,Cin) NHWC, kernel (kh,kw,Cin,Cout).
+    sinks = (gw_view, gb_view) or None."""
+
+    @staticmethod
+    def forward(ctx, opts, sinks, x, kernel, bias):
+        lib = _lib.load()
+        _require_cuda(x, kernel)
+        x = _f32c(x)
+        N, H, W, Cin = x.shape
+        kh, kw, _, Cout = kernel.shape
+        dil = opts.get("dilation", (1, 1))
+        act = opts.get("activation")
+        y = torch.empty(N, H, W, Cout, device=x.device)
+        cfg = _conv_cfg(N, H, W, Cin, Cout, kh, kw, dil, act, 0.0, H * W * Cin, Cin, H * W * Cout, Cout)
+        _lib.check(lib.fov_conv2d_fwd(C.byref(cfg), ptr(x), ptr(kernel), ptr(bias), ptr(y), _stream()),
+                   "fov_conv2d_fwd")
+        if opts.get("training", False):
+            ctx.cfg, ctx.sinks, ctx.act = cfg, sinks, act
+            ctx.need_dx = ctx.needs_input_grad[2]
+            ctx.save_for_backward(x, kernel, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, kernel, y = ctx.saved_tensors
+        cfg = ctx.cfg
+        dy = _f32c(dy)
+        st = _stream()
+        if ctx.act not in (None, "linear"):
+            dpre = torch.empty_like(y)
+            rows = y.numel() // y.shape[-1]
+            cols = y.shape[-1]
+            _lib.check(lib.fov_act_bwd(ACT[ctx.act], rows, cols, ptr(y), cols, ptr(dy), cols, ptr(dpre),
+                                       cols, st), "fov_act_bwd")
+        else:
+            dpre = dy
+        cfg.act = 0
+        gw, gb = ctx.sinks
+        _lib.check(lib.fov_conv2d_bwd_weight(C.byref(cfg), ptr(x), ptr(dpre), ptr(gw), ptr(gb), st),
+                   "fov_conv2d_bwd_weight")
+        dx = None
+        if ctx.need_dx:
+            dx = torch.empty_like(x)
+            ws = torch.empty(kernel.numel(), device=x.device)
+            cfg.beta = 0.0
+            _lib.check(lib.fov_conv2d_bwd_data(C.byref(cfg), ptr(dpre), ptr(kernel), ptr(dx), ptr(ws), st),
+                       "fov_conv2d_bwd_data")
+        return None, None, dx, None, None
+
+
+def conv2d(x, kernel, bias, activation=None, dilation=(1, 1), sinks=None, training=False):
+    return Conv2DFn.apply({"activation": activation, "dilation": dilation, "training": training},
+                          sinks, x, kernel, bias)
+
+
+def dense(x, kernel, bias, activation=None, sinks=None, training=False):
+    """keras Dense on the last axis: the 1x1 case of the conv family."""
+    shp = x.shape
+    x2 = x.reshape(-1, 1, 1, shp[-1])
+    y = Conv2DFn.apply({"activation": activation, "training": training}, sinks, x2,
+                       kernel.view(1, 1, *kernel.shape), bias)
+    return y.reshape(*shp[:-1], kernel.shape[1])
+
+
+def conv1d(x, kernel, bias, activation=None, sinks=None, training=False):
+    """keras Conv1D(padding='same'): x (B,L,Cin), kernel (k,Cin,Cout)."""
+    y = Conv2DFn.apply({"activation": activation, "training": training}, sinks, x.unsqueeze(1),
+                       kernel.unsqueeze(0), bias)
+    return y.squeeze(1)
+
+
+# --------------------------------------------------------------------------- #
+# ConvLSTM2D stack
+# --------------------------------------------------------------------------- #
+
+
+class ConvLSTMStackFn(torch.autograd.Function):
+    """L stacked ConvLSTM2D layers (return_sequences) writing straight into the
+    channel-concatenated sequence (mycode/others_LSTM_span_whole.py:88-102,
+    mycode/convlstm_seq2seq.py:100-126,213-220).
+
+    forward(opts, sinks, x, *flat) with flat = [K_l, R_l, b_l]*L + [h0_l, c0_l]*L (None allowed)
+    returns (concat_seq (B,T,H,W,sumF), hT_0, cT_0, ..., hT_{L-1}, cT_{L-1})
+    """
+
+    @staticmethod
+    def forward(ctx, opts, sinks, x, *flat):
+        lib = _lib.load()
+        _require_cuda(x)
+        x = _f32c(x)
+        L = opts["layers"]
+        weights = [flat[3 * l:3 * l + 3] for l in range(L)]
+        states = [tuple(_f32c(s) for s in flat[3 * L + 2 * l:3 * L + 2 * l + 2]) for l in range(L)]
+        B, T, H, W, Cin0 = x.shape
+        Fs = [w[1].shape[2] for w in weights]
+        Fsum = sum(Fs)
+        dev = x.device
+        dil = opts.get("dilation", (1, 1))
+        rec = REC[opts.get("rec_act", "hard_sigmoid")]
+        training = bool(opts.get("training", False))
+        cat = torch.empty(B, T, H, W, Fsum, device=dev)
+        HW = H * W
+        st = _stream()
+        outs, saved, cfgs = [], [], []
+        cin, off = Cin0, 0
+        cur, cur_b, cur_t, cur_pix = x, T * HW * Cin0, HW * Cin0, Cin0
+        cur_ptr = ptr(x)
+        for l in range(L):
+            K, R, b = weights[l]
+            kh, kw = K.shape[0], K.shape[1]
+            F = Fs[l]
+            cfg = _lib.ConvLstmCfg(B, T, H, W, cin, F, kh, kw, dil[0], dil[1], rec,
+                                   cur_b, cur_t, cur_pix, T * HW * Fsum, HW * Fsum, Fsum, int(training))
+            gates = torch.empty(B, T, H, W, 4 * F, device=dev)
+            cseq = torch.empty(B, T, H, W, F, device=dev)
+            hT = torch.empty(B, H, W, F, device=dev)
+            cT = torch.empty(B, H, W, F, device=dev)
+            h0, c0 = states[l]
+            hptr = cat.data_ptr() + 4 * off
+            io = _lib.ConvLstmIO(cur_ptr, ptr(K), ptr(R), ptr(b), ptr(h0), ptr(c0), None, hptr,
+                                 ptr(gates), ptr(cseq), ptr(hT), ptr(cT), None)
+            _lib.check(lib.fov_convlstm_fwd(C.byref(cfg), C.byref(io), st), "fov_convlstm_fwd")
+            outs += [hT, cT]
+            saved.append((gates, cseq))
+            cfgs.append((cfg, cur_ptr, hptr, off, F))
+            cur_ptr, cur_b, cur_t, cur_pix, cin = hptr, T * HW * Fsum, HW * Fsum, Fsum, F
+            off += F
+        if training:
+            ctx.sinks, ctx.cfgs, ctx.L = sinks, cfgs, L
+            ctx.x_needs_grad = ctx.needs_input_grad[2]
+            ctx.state_needs_grad = [ctx.needs_input_grad[3 + 3 * L + 2 * l] for l in range(L)]
+            tensors = [x, cat]
+            for l in range(L):
+                tensors += list(weights[l]) + list(states[l]) + list(saved[l])
+            ctx.save_for_backward(*tensors)
+        return (cat,) + tuple(outs)
+
+    @staticmethod
+    def backward(ctx, dcat, *dstates):
+        lib = _lib.load()
+        L, cfgs = ctx.L, ctx.cfgs
+        tensors = ctx.saved_tensors
+        x, cat = tensors[0], tensors[1]
+        per = [tensors[2 + 7 * l:2 + 7 * l + 7] for l in range(L)]   # K,R,b,h0,c0,gates,cseq
+        dev = x.device
+        st = _stream()
+        # private contiguous copy: layers accumulate dx of the layer above into it
+        dcat = torch.zeros_like(cat) if dcat is None else dcat.contiguous().clone()
+        dx0 = torch.empty_like(x) if ctx.x_needs_grad else None
+        dstate_out = [None] * (2 * L)
+        for l in reversed(range(L)):
+            cfg, _xptr, _hptr, off, F = cfgs[l]
+            K, R, b, h0, c0, gates, cseq = per[l]
+            xptr = x.data_ptr() if l == 0 else cat.data_ptr() + 4 * cfgs[l - 1][3]
+            hptr = cat.data_ptr() + 4 * off
+            dhT, dcT = _f32c(dstates[2 * l]), _f32c(dstates[2 * l + 1])
+            nws = lib.fov_convlstm_bwd_ws_floats(C.byref(cfg))
+            ws = torch.empty(nws, device=dev)
+            dh0 = dc0 = None
+            if ctx.state_needs_grad[l] and h0 is not None:
+                dh0 = torch.empty_like(h0)
+                dc0 = torch.empty_like(c0)
+            if l == 0:
+                dxp, acc = ptr(dx0), 0
+            else:
+                dxp, acc = dcat.data_ptr() + 4 * cfgs[l - 1][3], 1
+            gk, gr_, gb = ctx.sinks[l]
+            io = _lib.ConvLstmIO(xptr, ptr(K), ptr(R), ptr(b), ptr(h0), ptr(c0), None, hptr,
+                                 ptr(gates), ptr(cseq), None, None, None)
+            g = _lib.ConvLstmGrads(dcat.data_ptr() + 4 * off, ptr(dhT), ptr(dcT), dxp, ptr(dh0), ptr(dc0),
+                                   ptr(gk), ptr(gr_), ptr(gb), ptr(ws), acc)
+            _lib.check(lib.fov_convlstm_bwd(C.byref(cfg), C.byref(io), C.byref(g), st), "fov_convlstm_bwd")
+            dstate_out[2 * l], dstate_out[2 * l + 1] = dh0, dc0
+        return (None, None, dx0) + (None,) * (3 * L) + tuple(dstate_out)
+
+
+def convlstm_stack(x, weights, states=None, sinks=None, dilation=(1, 1), rec_act="hard_sigmoid",
+                   training=False):
+    """weights: [(K,R,b)]*L ; states: [(h0,c0)]*L or None.  Returns (concat_seq, [(hT,cT)]*L)."""
+    L = len(weights)
+    flat = []
+    for w in weights:
+        flat += list(w)
+    for l in range(L):
+        flat += list(states[l]) if states is not None else [None, None]
+    out = ConvLSTMStackFn.apply({"layers": L, "dilation": dilation, "rec_act": rec_act,
+                                 "training": training}, sinks, x, *flat)
+    return out[0], [(out[1 + 2 * l], out[2 + 2 * l]) for l in range(L)]
+
+
+# --------------------------------------------------------------------------- #
+# softmax / losses
+# --------------------------------------------------------------------------- #
+
+
+class SoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        _require_cuda(x)
+        x = _f32c(x)
+        y = torch.empty_like(x)
+        C_ = x.shape[-1]
+        _lib.check(lib.fov_softmax_fwd(x.numel() // C_, C_, ptr(x), ptr(y), _stream()), "fov_softmax_fwd")
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        (y,) = ctx.saved_tensors
+        dy = _f32c(dy)
+        dx = torch.empty_like(y)
+        C_ = y.shape[-1]
+        _lib.check(lib.fov_softmax_bwd(y.numel() // C_, C_, ptr(y), ptr(dy), ptr(dx), _stream()),
+                   "fov_softmax_bwd")
+        return dx
+
+
+class LossFn(torch.autograd.Function):
+    """kind in {'mse','nll','cce'}: returns a 1-element loss tensor; gradient fused."""
+
+    @staticmethod
+    def forward(ctx, kind, weight, y_pred, y_true, running_length):
+        lib = _lib.load()
+        _require_cuda(y_pred, y_true)
+        y_pred, y_true = _f32c(y_pred), _f32c(y_true)
+        loss = torch.zeros(1, device=y_pred.device)
+        need = ctx.needs_input_grad[2]
+        dy = torch.empty_like(y_pred) if need else None
+        st = _stream()
+        if kind == "mse":
+            _lib.check(lib.fov_mse_fwd_bwd(y_pred.numel(), ptr(y_pred), ptr(y_true), weight, ptr(loss),
+                                           ptr(dy), st), "fov_mse_fwd_bwd")
+        elif kind == "nll":
+            B, T = y_pred.shape[0], y_pred.shape[1]
+            _lib.check(lib.fov_gauss_nll_fwd_bwd(B, T, running_length, ptr(y_pred), ptr(y_true), weight,
+                                                 ptr(loss), ptr(dy), st), "fov_gauss_nll_fwd_bwd")
+        elif kind == "cce":
+            C_ = y_pred.shape[-1]
+            _lib.check(lib.fov_cce_fwd_bwd(y_pred.numel() // C_, C_, ptr(y_pred), ptr(y_true), weight,
+                                           ptr(loss), ptr(dy), st), "fov_cce_fwd_bwd")
+        else:
+            raise ValueError(kind)
+        ctx.dy = dy
+        return loss
+
+    @staticmethod
+    def backward(ctx, dl):
+        # the loss weight is already folded into dy by the kernel; the objective is the plain
+        # sum of these losses (Keras compile(loss=[...], loss_weights=[...])), so dl == 1.
+        return None, None, ctx.dy, None, None
+
+
+def loss(kind, y_true, y_pred, weight=1.0, running_length=10):
+    return LossFn.apply(kind, float(weight), y_pred, y_true, int(running_length))
+
+
+# --------------------------------------------------------------------------- #
+# optimiser steps, featuriser, re-sampler (no autograd)
+# --------------------------------------------------------------------------- #
+
+
+def adam_step(p, g, m, v, t, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, grad_scale=1.0):
+    lib = _lib.load()
+    _require_cuda(p, g, m, v)
+    _lib.check(lib.fov_adam_step(p.numel(), ptr(p), ptr(g), ptr(m), ptr(v), int(t), lr, beta1, beta2, eps,
+                                 grad_scale, _stream()), "fov_adam_step")
+
+
+def rmsprop_step(p, g, a, lr=1e-3, rho=0.9, eps=1e-7, grad_scale=1.0):
+    lib = _lib.load()
+    _require_cuda(p, g, a)
+    _lib.check(lib.fov_rmsprop_step(p.numel(), ptr(p), ptr(g), ptr(a), lr, rho, eps, grad_scale, _stream()),
+               "fov_rmsprop_step")
+
+
+def mean_var_xyz(frames):
+    """get_gt_target_xyz on the device: (..., 90) interleaved xyz or (..., 30, 3) -> (..., 6)."""
+    lib = _lib.load()
+    _require_cuda(frames)
+    frames = _f32c(frames)
+    lead = frames.shape[:-1] if frames.shape[-1] == 90 else frames.shape[:-2]
+    rows = 1
+    for d in lead:
+        rows *= d
+    out = torch.empty(*lead, 6, device=frames.device)
+    _lib.check(lib.fov_mean_var_xyz(rows, ptr(frames), ptr(out), _stream()), "fov_mean_var_xyz")
+    return out
+
+
+def gauss_resample(muvar, noise, mode="sqrt_floor"):
+    """(rows,6) mean/var + (rows,30,3) N(0,1) noise -> (rows,30,3) frames."""
+    lib = _lib.load()
+    _require_cuda(muvar, noise)
+    muvar, noise = _f32c(muvar), _f32c(noise)
+    out = torch.empty_like(noise)
+    m = {"sqrt_floor": 0, "sqrt": 1, "var_as_std": 2}[mode]
+    _lib.check(lib.fov_gauss_resample(muvar.shape[0], m, ptr(muvar), ptr(noise), ptr(out), _stream()),
+               "fov_gauss_resample")
+    return out

@@ -1,0 +1,385 @@
+"""GPU parity tests: every kernel family called through the C ABI (ctypes) and
+compared with the CPU oracle on the same seeded inputs.  fp32 path; forward bar is
+the north-star 1e-4 max-abs (we assert tighter where it holds)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import keras_numpy as kn
+from oracle import keras_torch as kt
+
+FWD_ATOL = 1e-4
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import longterm360fov_b200 as fov
+    return fov
+
+
+def _perturb(w, seed, scale=0.05):
+    rng = np.random.default_rng(seed)
+    return {k: (v + rng.normal(size=v.shape) * scale).astype(np.float32) for k, v in w.items()}
+
+
+def _grad_close(got, ref, name, rtol=2e-3):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    scale = max(np.abs(ref).max(), 1e-6)
+    err = np.abs(got - ref).max()
+    assert err <= rtol * scale + 1e-6, "%s: max err %.3e vs scale %.3e" % (name, err, scale)
+
+
+# ------------------------------------------------------------------ featuriser
+
+def test_featuriser_and_resampler_match_reference_golden(golden):
+    fov = _cuda()
+    from longterm360fov_b200 import ops
+    x = torch.tensor(golden["xyz90_in"], dtype=torch.float32, device="cuda")
+    got = ops.mean_var_xyz(x).cpu().numpy()
+    np.testing.assert_allclose(got, golden["xyz90_out"], atol=2e-6)
+    o = torch.tensor(golden["oth_in"], dtype=torch.float32, device="cuda")     # (N,T,U,30,3)
+    got = ops.mean_var_xyz(o).cpu().numpy()
+    np.testing.assert_allclose(got, golden["oth_out"], atol=2e-6)
+    mu, var, noise = golden["fake_mu"], golden["fake_var"], golden["fake_noise"]
+    muvar = np.zeros((6, 6), np.float32); muvar[:, 0] = mu; muvar[:, 3] = var
+    nz = np.zeros((6, 30, 3), np.float32); nz[:, :, 0] = noise
+    out = ops.gauss_resample(torch.tensor(muvar).cuda(), torch.tensor(nz).cuda(), "sqrt_floor").cpu().numpy()
+    np.testing.assert_allclose(out[:, :, 0], golden["fake_out"], atol=2e-6)
+
+
+# ------------------------------------------------------------------ fc-LSTM
+
+@pytest.mark.parametrize("B", [1, 7, 33, 70])
+@pytest.mark.parametrize("tf,in_enc", [(True, 90), (False, 90), (False, 6), (True, 6)])
+def test_lstm_seq2seq_forward(B, tf, in_enc):
+    fov = _cuda()
+    rng = np.random.default_rng(B * 10 + in_enc)
+    w = _perturb(kn.init_fov_seq2seq(seed=2, num_encoder_tokens=in_enc), 3)
+    enc = rng.uniform(-1, 1, (B, 10, in_enc)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 10 if tf else 1, 6)).astype(np.float32)
+    m = fov.fov_seq2seq(num_encoder_tokens=in_enc, teacher_forcing=tf, weights=w)
+    got = m.predict_on_batch([enc, dec])
+    ref = kn.fov_seq2seq_forward({k: v.astype(np.float64) for k, v in w.items()}, enc.astype(np.float64),
+                                 dec.astype(np.float64), teacher_forcing=tf)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 2e-5
+
+
+def test_lstm_large_batch_sigmoid_and_zero_init():
+    fov = _cuda()
+    rng = np.random.default_rng(0)
+    B = 5000                                 # > 32*148: exercises the 64-sequence tile
+    w = _perturb(kn.init_fov_seq2seq(seed=2, num_encoder_tokens=6), 3)
+    enc = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 1, 6)).astype(np.float32)
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    for kw, okw in [({}, {}), ({"recurrent_activation": "sigmoid"}, {"recurrent_activation": "sigmoid"}),
+                    ({"decoder_no_init_state": True}, {"decoder_no_init_state": True})]:
+        m = fov.fov_seq2seq_mu_var(teacher_forcing=False, weights=w, **kw)
+        got = m.predict([enc, dec], batch_size=B)
+        ref = kn.fov_seq2seq_forward(w64, enc.astype(np.float64), dec.astype(np.float64), teacher_forcing=False, **okw)
+        assert np.abs(got - ref).max() < 2e-5
+
+
+def test_encoder_decoder_submodels_match_host_loop():
+    """The reference's step-wise decode (FoV_seq2seq.py:154-178) through encoder_model /
+    decoder_model equals the single-launch decode_sequence_fov."""
+    fov = _cuda()
+    rng = np.random.default_rng(5)
+    w = _perturb(kn.init_fov_seq2seq(seed=2), 3)
+    m = fov.fov_seq2seq(weights=w)
+    seq = rng.uniform(-1, 1, (3, 10, 90)).astype(np.float32)
+    states = m.encoder_model.predict(seq)
+    target = kn.get_gt_target_xyz(seq[:, -1:, :].astype(np.float64)).astype(np.float32)
+    outs = []
+    for _ in range(10):
+        y, h, c = m.decoder_model.predict([target] + states)
+        outs.append(y); target = y; states = [h, c]
+    loop = np.concatenate(outs, axis=1)
+    one = m.decode_sequence_fov(seq)
+    assert np.abs(loop - one).max() < 1e-6
+    ref = kn.fov_seq2seq_forward({k: v.astype(np.float64) for k, v in w.items()}, seq.astype(np.float64),
+                                 kn.get_gt_target_xyz(seq[:, -1:, :].astype(np.float64)), teacher_forcing=False)
+    assert np.abs(one - ref).max() < 2e-5
+
+
+@pytest.mark.parametrize("tf,in_enc,B", [(True, 90, 37), (False, 90, 9), (False, 6, 64), (True, 6, 3)])
+def test_lstm_seq2seq_gradients(tf, in_enc, B):
+    fov = _cuda()
+    rng = np.random.default_rng(11)
+    w = _perturb(kn.init_fov_seq2seq(seed=4, num_encoder_tokens=in_enc), 5, 0.1)
+    enc = rng.uniform(-1, 1, (B, 10, in_enc)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 10 if tf else 1, 6)).astype(np.float32)
+    tgt = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    m = fov.fov_seq2seq(num_encoder_tokens=in_enc, teacher_forcing=tf, weights=w).compile("Adam", "mean_squared_error")
+    xs, ys = m._to_dev([enc, dec]), m._to_dev([tgt])
+    m.gflat.zero_()
+    loss = m._loss(m._forward(xs, True), ys)
+    loss.backward()
+    wt = kt.to_torch(w)
+    l_ref, _, g_ref = kt.loss_and_grads(lambda ww, a, b: kt.fov_seq2seq_forward(ww, a, b, teacher_forcing=tf), wt,
+                                        [torch.tensor(enc, dtype=torch.float64), torch.tensor(dec, dtype=torch.float64)],
+                                        [torch.tensor(tgt, dtype=torch.float64)], [kt.mse])
+    assert abs(loss.item() - l_ref.item()) < 1e-5
+    for k in m.weight_order:
+        _grad_close(m.grads[k].cpu().numpy(), g_ref[k].numpy(), k)
+
+
+# ------------------------------------------------------------------ conv family
+
+CONV_CASES = [
+    # N,H,W,Cin,Cout,kh,kw,dil,act
+    (3, 1, 33, 6, 128, 1, 5, (1, 1), None),
+    (2, 1, 33, 32, 64, 1, 5, (1, 1), "tanh"),
+    (2, 6, 5, 30, 32, 5, 5, (1, 1), "relu"),
+    (2, 7, 9, 5, 12, 3, 3, (2, 2), None),
+    (2, 5, 8, 4, 6, 2, 4, (1, 1), None),          # even kernels: asymmetric TF 'same'
+    (300, 1, 1, 1848, 198, 1, 1, (1, 1), None),   # Dense 1848->198
+    (5, 1, 1, 64, 6, 1, 1, (1, 1), "tanh"),
+    (1, 36, 18, 56, 70, 5, 5, (1, 1), "relu"),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_forward_backward(case):
+    fov = _cuda()
+    from longterm360fov_b200 import ops
+    N, H, W, Cin, Cout, kh, kw, dil, act = case
+    rng = np.random.default_rng(hash(case[:7]) % 1000)
+    x = rng.normal(size=(N, H, W, Cin)).astype(np.float32)
+    k = (rng.normal(size=(kh, kw, Cin, Cout)) / np.sqrt(kh * kw * Cin)).astype(np.float32)
+    b = rng.normal(size=Cout).astype(np.float32) * 0.1
+    gy = rng.normal(size=(N, H, W, Cout)).astype(np.float32)
+    xt = torch.tensor(x, device="cuda", requires_grad=True)
+    kt_ = torch.tensor(k, device="cuda", requires_grad=True)
+    bt = torch.tensor(b, device="cuda", requires_grad=True)
+    gw, gb = torch.zeros_like(kt_), torch.zeros_like(bt)
+    y = ops.conv2d(xt, kt_, bt, act, dil, (gw, gb), True)
+    y.backward(torch.tensor(gy, device="cuda"))
+    x64 = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    k64 = torch.tensor(k, dtype=torch.float64, requires_grad=True)
+    b64 = torch.tensor(b, dtype=torch.float64, requires_grad=True)
+    yr = kt.conv2d(x64, k64, b64, act, dil)
+    yr.backward(torch.tensor(gy, dtype=torch.float64))
+    assert np.abs(y.detach().cpu().numpy() - yr.detach().numpy()).max() < 2e-5
+    np.testing.assert_allclose(kn.conv2d(x.astype(np.float64), k.astype(np.float64), b.astype(np.float64), act, dil),
+                               yr.detach().numpy(), atol=1e-10)
+    _grad_close(xt.grad.cpu().numpy(), x64.grad.numpy(), "dx")
+    _grad_close(gw.cpu().numpy(), k64.grad.numpy(), "dw")
+    _grad_close(gb.cpu().numpy(), b64.grad.numpy(), "db")
+
+
+# ------------------------------------------------------------------ ConvLSTM
+
+@pytest.mark.parametrize("shape", [(3, 4, 1, 9, 6, (5, 4, 3), 1, 5, (1, 1), False),
+                                   (2, 3, 6, 5, 4, (4, 3, 2), 3, 3, (1, 1), True),
+                                   (2, 1, 6, 5, 4, (4, 3, 2), 3, 3, (2, 2), True)])
+def test_convlstm_stack_forward_backward(shape):
+    fov = _cuda()
+    from longterm360fov_b200 import ops
+    B, T, H, W, Cin, Fs, kh, kw, dil, with_state = shape
+    rng = np.random.default_rng(B * 100 + T)
+    x = rng.normal(size=(B, T, H, W, Cin)).astype(np.float32)
+    ws, cin = [], Cin
+    for f in Fs:
+        ws.append(((rng.normal(size=(kh, kw, cin, 4 * f)) * 0.3).astype(np.float32),
+                   (rng.normal(size=(kh, kw, f, 4 * f)) * 0.3).astype(np.float32),
+                   (rng.normal(size=4 * f) * 0.1).astype(np.float32)))
+        cin = f
+    st = [((rng.normal(size=(B, H, W, f)) * 0.5).astype(np.float32), (rng.normal(size=(B, H, W, f)) * 0.5).astype(np.float32))
+          for f in Fs] if with_state else None
+    gcat = rng.normal(size=(B, T, H, W, sum(Fs))).astype(np.float32)
+    gst = [(rng.normal(size=(B, H, W, f)).astype(np.float32), rng.normal(size=(B, H, W, f)).astype(np.float32)) for f in Fs]
+
+    dev = lambda a, rg=True: torch.tensor(a, device="cuda", requires_grad=rg)
+    xt = dev(x)
+    wt = [tuple(dev(a) for a in w) for w in ws]
+    stt = [tuple(dev(a) for a in s) for s in st] if st else None
+    sinks = [tuple(torch.zeros_like(a) for a in w) for w in wt]
+    cat, states = ops.convlstm_stack(xt, wt, stt, sinks, dil, "hard_sigmoid", True)
+    obj = (cat * dev(gcat, False)).sum()
+    for (h, c), (gh, gc) in zip(states, gst):
+        obj = obj + (h * dev(gh, False)).sum() + (c * dev(gc, False)).sum()
+    obj.backward()
+
+    d64 = lambda a, rg=True: torch.tensor(a, dtype=torch.float64, requires_grad=rg)
+    x64 = d64(x)
+    w64 = {}
+    for l, w in enumerate(ws):
+        w64["L%d/kernel" % l], w64["L%d/recurrent_kernel" % l], w64["L%d/bias" % l] = (d64(a) for a in w)
+    s64 = [tuple(d64(a) for a in s) for s in st] if st else None
+    catr, statesr = kt.convlstm_stack(w64, x64, "L", s64, dil)
+    objr = (catr * d64(gcat, False)).sum()
+    for (h, c), (gh, gc) in zip(statesr, gst):
+        objr = objr + (h * d64(gh, False)).sum() + (c * d64(gc, False)).sum()
+    objr.backward()
+
+    assert np.abs(cat.detach().cpu().numpy() - catr.detach().numpy()).max() < 2e-5
+    for (h, c), (hr, cr) in zip(states, statesr):
+        assert np.abs(h.detach().cpu().numpy() - hr.detach().numpy()).max() < 2e-5
+        assert np.abs(c.detach().cpu().numpy() - cr.detach().numpy()).max() < 2e-5
+    _grad_close(xt.grad.cpu().numpy(), x64.grad.numpy(), "dx")
+    for l in range(len(Fs)):
+        for j, n in enumerate(("kernel", "recurrent_kernel", "bias")):
+            _grad_close(sinks[l][j].cpu().numpy(), w64["L%d/%s" % (l, n)].grad.numpy(), "L%d/%s" % (l, n))
+        if st:
+            _grad_close(stt[l][0].grad.cpu().numpy(), s64[l][0].grad.numpy(), "dh0_%d" % l)
+            _grad_close(stt[l][1].grad.cpu().numpy(), s64[l][1].grad.numpy(), "dc0_%d" % l)
+
+
+# ------------------------------------------------------------------ losses / softmax / optimisers
+
+def test_losses_and_softmax():
+    fov = _cuda()
+    from longterm360fov_b200 import ops
+    rng = np.random.default_rng(21)
+    yp = rng.uniform(-1, 1, (5, 10, 6)).astype(np.float32); yp[0, 0, 3] = 3.0; yp[0, 1, 4] = 1e-6
+    fr = rng.uniform(-1, 1, (5, 10, 90)).astype(np.float32)
+    for kind, ref_fn, yt in [("mse", kt.mse, rng.uniform(-1, 1, (5, 10, 6)).astype(np.float32)), ("nll", kt.gauss_nll, fr)]:
+        a = torch.tensor(yp, device="cuda", requires_grad=True)
+        l = ops.loss(kind, torch.tensor(yt, device="cuda"), a, 0.7)
+        l.backward()
+        a64 = torch.tensor(yp, dtype=torch.float64, requires_grad=True)
+        lr = 0.7 * ref_fn(torch.tensor(yt, dtype=torch.float64), a64)
+        lr.backward()
+        assert abs(l.item() - lr.item()) < 1e-5 * max(1, abs(lr.item()))
+        _grad_close(a.grad.cpu().numpy(), a64.grad.numpy(), kind, rtol=1e-4)
+    z = rng.normal(size=(4, 6, 3, 30)).astype(np.float32)
+    t1 = np.eye(30, dtype=np.float32)[rng.integers(0, 30, (4, 6, 3))]
+    zt = torch.tensor(z, device="cuda", requires_grad=True)
+    p = ops.SoftmaxFn.apply(zt)
+    l = ops.loss("cce", torch.tensor(t1, device="cuda"), p)
+    l.backward()
+    z64 = torch.tensor(z, dtype=torch.float64, requires_grad=True)
+    lr = kt.categorical_crossentropy(torch.tensor(t1, dtype=torch.float64), torch.softmax(z64, -1))
+    lr.backward()
+    assert np.abs(p.detach().cpu().numpy() - torch.softmax(z64, -1).detach().numpy()).max() < 1e-6
+    assert abs(l.item() - lr.item()) < 1e-5
+    _grad_close(zt.grad.cpu().numpy(), z64.grad.numpy(), "cce+softmax", rtol=1e-4)
+
+
+def test_adam_and_rmsprop_steps():
+    fov = _cuda()
+    from longterm360fov_b200 import ops
+    rng = np.random.default_rng(22)
+    n = 1000
+    p0 = rng.normal(size=n).astype(np.float32)
+    p = torch.tensor(p0, device="cuda"); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    pr, mr, vr = p0.astype(np.float64), np.zeros(n), np.zeros(n)
+    for t in range(1, 6):
+        g = rng.normal(size=n).astype(np.float32)
+        ops.adam_step(p, torch.tensor(g, device="cuda") * 2.0, m, v, t, grad_scale=0.5)
+        pr, mr, vr = kn.adam_step(pr, g.astype(np.float64), mr, vr, t)
+    assert np.abs(p.cpu().numpy() - pr).max() < 1e-6
+    p = torch.tensor(p0, device="cuda"); a = torch.zeros(n, device="cuda")
+    pr, ar = p0.astype(np.float64), np.zeros(n)
+    for t in range(5):
+        g = rng.normal(size=n).astype(np.float32)
+        ops.rmsprop_step(p, torch.tensor(g, device="cuda"), a)
+        pr, ar = kn.rmsprop_step(pr, g.astype(np.float64), ar)
+    assert np.abs(p.cpu().numpy() - pr).max() < 1e-5
+
+
+# ------------------------------------------------------------------ full models
+
+def _m3_data(rng, B, U):
+    enc = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    oth = rng.uniform(-1, 1, (B, 20, 1, U, 6)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 1, 6)).astype(np.float32)
+    tg = [rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32), rng.uniform(-1, 1, (B, 20, U * 6)).astype(np.float32),
+          rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)]
+    return enc, oth, dec, tg
+
+
+@pytest.mark.parametrize("num_user,B", [(34, 5), (6, 40)])
+def test_m3_forward_gradients_and_loss_curve(num_user, B):
+    fov = _cuda()
+    rng = np.random.default_rng(31)
+    U = num_user - 1
+    w = _perturb(kn.init_others_lstm_span_whole(seed=3, num_user=num_user), 6, 0.02)
+    enc, oth, dec, tg = _m3_data(rng, B, U)
+    m = fov.others_lstm_span_whole(num_user=num_user, weights=w).compile("Adam", ["mean_squared_error"] * 3, [1, 1, 1])
+    got = m.predict_on_batch([enc, oth, dec])
+    t64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    wt = kt.to_torch(w)
+    l_ref, outs_ref, g_ref = kt.loss_and_grads(kt.others_lstm_span_whole_forward, wt, [t64(enc), t64(oth), t64(dec)],
+                                               [t64(t) for t in tg], [kt.mse] * 3)
+    for a, b in zip(got, outs_ref):
+        assert np.abs(a - b.numpy()).max() < FWD_ATOL / 2
+    xs, ys = m._to_dev([enc, oth, dec]), m._to_dev(tg)
+    m.gflat.zero_()
+    loss = m._loss(m._forward(xs, True), ys)
+    loss.backward()
+    assert abs(loss.item() - l_ref.item()) < 1e-5
+    for k in m.weight_order:
+        _grad_close(m.grads[k].cpu().numpy(), g_ref[k].numpy(), k)
+    # loss curve: 4 Adam steps on the same batch, oracle in float64
+    opt = kt.KerasAdam(wt)
+    for step in range(4):
+        l_ref, _, g_ref = kt.loss_and_grads(kt.others_lstm_span_whole_forward, wt, [t64(enc), t64(oth), t64(dec)],
+                                            [t64(t) for t in tg], [kt.mse] * 3)
+        opt.step(g_ref)
+        l = m.train_on_batch([enc, oth, dec], tg)
+        assert abs(l - l_ref.item()) < 2e-4 * max(1.0, abs(l_ref.item())), (step, l, l_ref.item())
+
+
+@pytest.mark.parametrize("kind", ["conv2d", "conv1d", "dense"])
+def test_m4_forward_gradients(kind):
+    fov = _cuda()
+    from longterm360fov_b200.models import ConvLSTMSeq2Seq
+    rng = np.random.default_rng(41)
+    if kind == "conv2d":
+        w = kn.init_convlstm_seq2seq(seed=5, in_ch=5, filters=(4, 3, 2), kernel_size=3, head=(6, 7, 5))
+        enc = rng.uniform(0, 1, (3, 4, 6, 4, 5)); dec = rng.uniform(0, 1, (3, 1, 6, 4, 5)); tshape = (3, 3, 6, 4, 5)
+    elif kind == "conv1d":
+        w = kn.init_convlstm_seq2seq(seed=5, in_ch=3, filters=(4, 3, 2), kernel_size=3, head=(6, 7, 3), head_kind="conv1d")
+        enc = rng.uniform(-1, 1, (3, 4, 1, 8, 3)); dec = rng.uniform(-1, 1, (3, 1, 1, 8, 3)); tshape = (3, 3, 1, 8, 3)
+    else:
+        w = kn.init_convlstm_seq2seq(seed=5, in_ch=6, filters=(4, 3, 2), kernel_size=3, head_kind="dense", flat_dim=9)
+        enc = rng.uniform(-1, 1, (3, 4, 1, 1, 6)); dec = rng.uniform(-1, 1, (3, 1, 1, 1, 6)); tshape = (3, 3, 6)
+    w = _perturb(w, 7, 0.1)
+    enc, dec = enc.astype(np.float32), dec.astype(np.float32)
+    tgt = rng.uniform(0, 1, tshape).astype(np.float32)
+    m = ConvLSTMSeq2Seq(w, kind, max_decoder_seq_length=3).compile("RMSprop", "_mse")
+    got = m.predict_on_batch([enc, dec])
+    t64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    wt = kt.to_torch(w)
+    l_ref, outs_ref, g_ref = kt.loss_and_grads(
+        lambda ww, a, b: kt.convlstm_seq2seq_forward(ww, a, b, head_kind=kind, steps=3), wt, [t64(enc), t64(dec)],
+        [t64(tgt)], [kt.mse])
+    assert np.abs(got - outs_ref[0].numpy()).max() < 2e-5
+    xs, ys = m._to_dev([enc, dec]), m._to_dev([tgt])
+    m.gflat.zero_()
+    loss = m._loss(m._forward(xs, True), ys)
+    loss.backward()
+    assert abs(loss.item() - l_ref.item()) < 1e-5
+    for k in m.weight_order:
+        _grad_close(m.grads[k].cpu().numpy(), g_ref[k].numpy(), k)
+    # three RMSprop steps follow the oracle's loss curve
+    opt = kt.KerasRMSprop(wt)
+    for step in range(3):
+        l_ref, _, g_ref = kt.loss_and_grads(
+            lambda ww, a, b: kt.convlstm_seq2seq_forward(ww, a, b, head_kind=kind, steps=3), wt, [t64(enc), t64(dec)],
+            [t64(tgt)], [kt.mse])
+        opt.step(g_ref)
+        l = m.train_on_batch([enc, dec], [tgt])
+        assert abs(l - l_ref.item()) < 5e-4 * max(1.0, abs(l_ref.item())), (step, l, l_ref.item())
+
+
+def test_fit_predict_surface_m1():
+    """fit() with validation split / shuffle / callbacks runs and reduces the loss."""
+    fov = _cuda()
+    rng = np.random.default_rng(51)
+    N = 256
+    enc = rng.uniform(-1, 1, (N, 10, 90)).astype(np.float32)
+    fut = np.tanh(enc[:, :, :6] * 0.5).astype(np.float32)
+    dec_in = np.concatenate([enc[:, -1:, :6], fut[:, :-1]], axis=1)
+    m = fov.fov_seq2seq().compile(optimizer="Adam", loss="mean_squared_error")
+    h = m.fit([enc, dec_in], fut, batch_size=32, epochs=6, validation_split=0.2, shuffle=True,
+              callbacks=[fov.ReduceLROnPlateau(monitor="val_loss", factor=0.2, patience=3, min_lr=1e-6),
+                         fov.EarlyStopping(monitor="val_loss", patience=10)])
+    assert len(h.history["loss"]) == 6 and h.history["loss"][-1] < h.history["loss"][0]
+    assert m.predict([enc, dec_in], batch_size=100).shape == (N, 10, 6)
