@@ -173,6 +173,7 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
   // ---- time-batched input-side gradients ----
   fov_conv_cfg k = input_conv_cfg(cfg);
   k.beta = gr->dx_accumulate ? 1.0f : 0.0f;
+  k.N = cfg->B;
   const bool batched = (cfg->x_b_stride == (long long)cfg->T * cfg->x_t_stride) || cfg->T == 1;
   if (gr->dx) {
     if ((rc = fov_conv_flip_weights(&k, io->kernel, Kt, st))) return rc;
