@@ -203,6 +203,14 @@ def run_ours(args):
     value = world * B * args.steps / (ms / 1e3)
     final_loss = float(loss.item())
 
+    if args.profile_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps,
+                              "gpu_launches": launches, "profile_only": True}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---------------- end-to-end through the public API ----------------
     e2e_steps = max(3, min(args.steps, 10))
     for i in range(2):
@@ -311,6 +319,8 @@ def main():
     ap.add_argument("--batch", type=int, default=2048, help="sequences per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=64, help="sequences per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true",
+                    help="only the device-resident timed region (for ncu runs): no e2e / infer / cpu legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -20,7 +20,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, parallel
 
 def _init_weights(kind, **kw):
     """Keras-default initialisers (glorot_uniform / orthogonal / forget-bias 1).
@@ -225,9 +225,7 @@ class Model:
         total.backward()
         scale = 1.0
         if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.gflat, group=self.process_group)
-            scale = 1.0 / self.world_size
+            scale = parallel.allreduce_gradients(self.gflat, self.process_group)
         with torch.no_grad():
             self.optimizer.step(self.flat, self.gflat, scale)
         return total.detach()
