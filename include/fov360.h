@@ -143,6 +143,24 @@ int fov_act_bwd(int act, long long rows, int cols, const float* y, long long y_s
                 void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Tensor-core (tcgen05 / TMEM) forms of the convolution family.
+ * Same operands and semantics as fov_conv2d_fwd / _bwd_data / _bwd_weight; the
+ * activations and weights stay fp32 in HBM and are split on the fly into `math`
+ * bf16 terms per operand, accumulated in fp32 in tensor memory:
+ *   FOV_MATH_BF16   1 term  (1 MMA  per k-step, ~8 mantissa bits per operand)
+ *   FOV_MATH_BF16X2 2 terms (3 MMAs per k-step, ~16 bits)
+ *   FOV_MATH_BF16X3 3 terms (6 MMAs per k-step, ~24 bits: fp32-grade results)
+ * `ws` is a caller-owned workspace of fov_conv_tc_ws_bytes() bytes that receives
+ * the repacked weights (the call repacks them every time; it keeps no state).
+ * ------------------------------------------------------------------------- */
+enum { FOV_MATH_FP32 = 0, FOV_MATH_BF16 = 1, FOV_MATH_BF16X2 = 2, FOV_MATH_BF16X3 = 3 };
+size_t fov_conv_tc_ws_bytes(const fov_conv_cfg* cfg, int math, int bwd_data);
+int fov_conv2d_fwd_tc(const fov_conv_cfg* cfg, const float* x, const float* w, const float* bias,
+                      float* y, void* ws, int math, void* stream);
+int fov_conv2d_bwd_data_tc(const fov_conv_cfg* cfg, const float* dy, const float* w, float* dx,
+                           void* ws, int math, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * ConvLSTM2D layer over a whole sequence (return_sequences=True, return_state).
  * Replaces: keras ConvLSTM2D at mycode/others_LSTM_span_whole.py:88-100 and
  *   mycode/convlstm_seq2seq.py:100-126 (T=10/20) and the one-step decoder calls
@@ -157,6 +175,9 @@ typedef struct {
   long long x_b_stride, x_t_stride;  int x_pix_stride;
   long long h_b_stride, h_t_stride;  int h_pix_stride;   /* layout of hseq */
   int training;
+  int math;                      /* FOV_MATH_*: 0 = fp32 CUDA-core kernels; 1..3 = tcgen05 kernels with that
+                                    many bf16 terms per operand (the step becomes ONE fused launch:
+                                    [x taps | h taps] x [K;R] GEMM + gate algebra + cell update) */
 } fov_convlstm_cfg;
 
 typedef struct {
@@ -168,9 +189,10 @@ typedef struct {
   float *gates;                  /* (B,T,H,W,4F): pre-activations then activated gates (saved) */
   float *cseq;                   /* (B,T,H,W,F) */
   float *hT, *cT;                /* optional dense (B,H,W,F) */
-  float *ws;                     /* workspace: B*H*W*Cin floats when drop_masks != NULL */
+  float *ws;                     /* workspace of fov_convlstm_fwd_ws_bytes() bytes (math != 0) */
 } fov_convlstm_io;
 
+size_t fov_convlstm_fwd_ws_bytes(const fov_convlstm_cfg* cfg);
 int fov_convlstm_fwd(const fov_convlstm_cfg* cfg, const fov_convlstm_io* io, void* stream);
 
 typedef struct {

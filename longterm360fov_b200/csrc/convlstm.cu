@@ -56,7 +56,91 @@ fov_conv_cfg rec_conv_cfg(const fov_convlstm_cfg* c) {
   return k;
 }
 
+// fused tensor-core step: z = [x_t taps | h_{t-1} taps] x [K ; R], gates + cell update in the epilogue
+TcConv step_conv(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const Geo& g) {
+  TcConv k{};
+  k.nseg = 2;
+  k.N_img = c->B; k.T_inner = 1; k.H = c->H; k.W = c->W;
+  k.Cout = 4 * c->F; k.math = c->math; k.epi = TC_EPI_LSTM;
+  TcSeg& a = k.seg[0];
+  a.img_outer = c->x_b_stride; a.img_inner = 0; a.pix_stride = c->x_pix_stride; a.Cin = c->Cin;
+  a.kh = c->kh; a.kw = c->kw; a.dil_h = c->dil_h; a.dil_w = c->dil_w;
+  a.pad_h = ((c->kh - 1) * c->dil_h) / 2; a.pad_w = ((c->kw - 1) * c->dil_w) / 2;
+  a.w = io->kernel; a.w_mode = 0;
+  TcSeg& h = k.seg[1];
+  h.Cin = c->F; h.kh = c->kh; h.kw = c->kw; h.dil_h = 1; h.dil_w = 1;
+  h.pad_h = (c->kh - 1) / 2; h.pad_w = (c->kw - 1) / 2;
+  h.w = io->recurrent; h.w_mode = 0;
+  k.bias = io->bias; k.rec_act = c->rec_act;
+  k.c_outer = g.c_b; k.h_outer = c->h_b_stride; k.h_pix_stride = c->h_pix_stride; k.g_outer = g.z_b;
+  return k;
+}
+
+// dh_{t-1} = conv^T(dZ_t, R) on tensor cores: "x" = dZ_t (B,HW,4F), output dense (B,HW,F)
+TcConv rec_bwd_conv(const fov_convlstm_cfg* c, const float* recurrent, const Geo& g) {
+  TcConv k{};
+  k.nseg = 1; k.N_img = c->B; k.T_inner = 1; k.H = c->H; k.W = c->W;
+  k.Cout = c->F; k.math = c->math; k.epi = TC_EPI_CONV;
+  TcSeg& a = k.seg[0];
+  a.img_outer = g.z_b; a.img_inner = 0; a.pix_stride = 4 * c->F; a.Cin = 4 * c->F;
+  a.kh = c->kh; a.kw = c->kw; a.dil_h = 1; a.dil_w = 1;
+  a.pad_h = (c->kh - 1) - (c->kh - 1) / 2; a.pad_w = (c->kw - 1) - (c->kw - 1) / 2;
+  a.w = recurrent; a.w_mode = 1;
+  k.y_outer = g.hw_f; k.y_inner = 0; k.y_pix_stride = c->F; k.act = FOV_ACT_LINEAR; k.beta = 0.0f;
+  return k;
+}
+// dx = conv^T(dZ, K) for every (b,t) image in one launch
+TcConv in_bwd_conv(const fov_convlstm_cfg* c, const float* kernel, const Geo& g) {
+  TcConv k{};
+  k.nseg = 1; k.N_img = c->B * c->T; k.T_inner = c->T; k.H = c->H; k.W = c->W;
+  k.Cout = c->Cin; k.math = c->math; k.epi = TC_EPI_CONV;
+  TcSeg& a = k.seg[0];
+  a.img_outer = g.z_b; a.img_inner = g.z_t; a.pix_stride = 4 * c->F; a.Cin = 4 * c->F;
+  a.kh = c->kh; a.kw = c->kw; a.dil_h = c->dil_h; a.dil_w = c->dil_w;
+  a.pad_h = (c->kh - 1) * c->dil_h - ((c->kh - 1) * c->dil_h) / 2;
+  a.pad_w = (c->kw - 1) * c->dil_w - ((c->kw - 1) * c->dil_w) / 2;
+  a.w = kernel; a.w_mode = 1;
+  k.y_outer = c->x_b_stride; k.y_inner = c->x_t_stride; k.y_pix_stride = c->x_pix_stride;
+  k.act = FOV_ACT_LINEAR;
+  return k;
+}
+
 }  // namespace
+
+extern "C" size_t fov_convlstm_fwd_ws_bytes(const fov_convlstm_cfg* cfg) {
+  if (!cfg || cfg->math == 0 || check(cfg)) return 0;
+  fov_convlstm_io io{};
+  return tc_conv_ws_bytes(step_conv(cfg, &io, geo(cfg)));
+}
+
+static int convlstm_fwd_tc(const fov_convlstm_cfg* cfg, const fov_convlstm_io* io, cudaStream_t st) {
+  FOV_CHECK_ARG(io->ws != nullptr, "math != 0 needs io->ws (fov_convlstm_fwd_ws_bytes)");
+  FOV_CHECK_ARG(!io->drop_masks, "dropout masks are applied by the caller in this build");
+  const Geo g = geo(cfg);
+  const int F = cfg->F;
+  TcConv k = step_conv(cfg, io, g);
+  k.ws = io->ws;
+  for (int t = 0; t < cfg->T; ++t) {
+    k.prepacked = t > 0;
+    k.seg[0].x = io->x + t * cfg->x_t_stride;
+    if (t == 0) {
+      k.seg[1].x = io->h0; k.seg[1].img_outer = g.hw_f; k.seg[1].pix_stride = F;
+      k.c_prev = io->c0; k.cp_outer = g.hw_f;
+    } else {
+      k.seg[1].x = io->hseq + (t - 1) * cfg->h_t_stride; k.seg[1].img_outer = cfg->h_b_stride;
+      k.seg[1].pix_stride = cfg->h_pix_stride;
+      k.c_prev = io->cseq + (t - 1) * g.c_t; k.cp_outer = g.c_b;
+    }
+    k.c_out = io->cseq + t * g.c_t;
+    k.h_out = io->hseq + t * cfg->h_t_stride;
+    k.gates_out = cfg->training ? io->gates + t * g.z_t : nullptr;
+    k.hT = (t == cfg->T - 1) ? io->hT : nullptr;
+    k.cT = (t == cfg->T - 1) ? io->cT : nullptr;
+    int rc = tc_conv_run(k, st);
+    if (rc) return rc;
+  }
+  return FOV_OK;
+}
 
 extern "C" int fov_convlstm_fwd(const fov_convlstm_cfg* cfg, const fov_convlstm_io* io, void* stream) {
   int rc = check(cfg);
@@ -64,6 +148,7 @@ extern "C" int fov_convlstm_fwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
   FOV_CHECK_ARG(io && io->x && io->kernel && io->recurrent && io->bias && io->hseq && io->gates && io->cseq,
                 "NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (cfg->math != 0) return convlstm_fwd_tc(cfg, io, st);
   const Geo g = geo(cfg);
   const int F = cfg->F;
 
@@ -122,7 +207,12 @@ extern "C" size_t fov_convlstm_bwd_ws_floats(const fov_convlstm_cfg* c) {
   const size_t bhwf = (size_t)c->B * c->H * c->W * c->F;
   const size_t taps = (size_t)c->kh * c->kw;
   // dh_rec + dc (ping-pong x2) + flipped recurrent + flipped kernel
-  return 4 * bhwf + taps * c->F * 4 * c->F + taps * c->Cin * 4 * c->F + 64;
+  size_t n = 4 * bhwf + taps * c->F * 4 * c->F + taps * c->Cin * 4 * c->F + 64;
+  if (c->math != 0) {   // packed bf16 weights of the two tensor-core backward-data convolutions
+    const Geo g = geo(c);
+    n += (tc_conv_ws_bytes(rec_bwd_conv(c, nullptr, g)) + tc_conv_ws_bytes(in_bwd_conv(c, nullptr, g))) / 4 + 128;
+  }
+  return n;
 }
 
 extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_io* io,
@@ -145,7 +235,18 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
   r.beta = 0.0f;
   // dh_rec is produced as the "x" side of the recurrent conv: dense (B,HW,F)
   r.x_img_stride = g.hw_f; r.x_pix_stride = F; r.y_img_stride = g.z_b;
-  if ((rc = fov_conv_flip_weights(&r, io->recurrent, Rt, st))) return rc;
+  const bool tcm = cfg->math != 0;
+  TcConv rT = rec_bwd_conv(cfg, io->recurrent, g);
+  TcConv kT = in_bwd_conv(cfg, io->kernel, g);
+  if (tcm) {
+    float* pk = Kt + (size_t)cfg->kh * cfg->kw * cfg->Cin * 4 * F + 64;
+    rT.ws = pk;
+    kT.ws = pk + tc_conv_ws_bytes(rT) / 4 + 64;
+    if ((rc = tc_conv_pack(rT, st))) return rc;
+    rT.prepacked = 1;
+  } else {
+    if ((rc = fov_conv_flip_weights(&r, io->recurrent, Rt, st))) return rc;
+  }
 
   const float* dc_in = gr->dcT;
   const float* dh_in = gr->dhT;
@@ -165,7 +266,12 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
     dc_in = dc_out;
     if (t > 0 || (io->h0 && gr->dh0)) {
       float* dst = (t == 0) ? gr->dh0 : dh_rec;
-      if ((rc = fov_conv_bwd_data_preflipped(&r, zt, Rt, dst, st))) return rc;
+      if (tcm) {
+        rT.seg[0].x = zt; rT.y = dst;
+        if ((rc = tc_conv_run(rT, st))) return rc;
+      } else {
+        if ((rc = fov_conv_bwd_data_preflipped(&r, zt, Rt, dst, st))) return rc;
+      }
       dh_in = dst;
     }
   }
@@ -175,17 +281,20 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
   k.beta = gr->dx_accumulate ? 1.0f : 0.0f;
   k.N = cfg->B;
   const bool batched = (cfg->x_b_stride == (long long)cfg->T * cfg->x_t_stride) || cfg->T == 1;
-  if (gr->dx) {
+  if (gr->dx && tcm) {
+    kT.seg[0].x = io->gates; kT.y = gr->dx; kT.beta = gr->dx_accumulate ? 1.0f : 0.0f;
+    if ((rc = tc_conv_run(kT, st))) return rc;
+  } else if (gr->dx) {
     if ((rc = fov_conv_flip_weights(&k, io->kernel, Kt, st))) return rc;
   }
   if (batched) {
     k.N = cfg->B * cfg->T; k.x_img_stride = cfg->T == 1 ? cfg->x_b_stride : cfg->x_t_stride; k.y_img_stride = g.z_t;
-    if (gr->dx && (rc = fov_conv_bwd_data_preflipped(&k, io->gates, Kt, gr->dx, st))) return rc;
+    if (gr->dx && !tcm && (rc = fov_conv_bwd_data_preflipped(&k, io->gates, Kt, gr->dx, st))) return rc;
     if ((rc = fov_conv2d_bwd_weight(&k, io->x, io->gates, gr->g_kernel, gr->g_bias, stream))) return rc;
   } else {
     k.N = cfg->B; k.x_img_stride = cfg->x_b_stride; k.y_img_stride = g.z_b;
     for (int t = 0; t < cfg->T; ++t) {
-      if (gr->dx && (rc = fov_conv_bwd_data_preflipped(&k, io->gates + t * g.z_t, Kt, gr->dx + t * cfg->x_t_stride, st))) return rc;
+      if (gr->dx && !tcm && (rc = fov_conv_bwd_data_preflipped(&k, io->gates + t * g.z_t, Kt, gr->dx + t * cfg->x_t_stride, st))) return rc;
       if ((rc = fov_conv2d_bwd_weight(&k, io->x + t * cfg->x_t_stride, io->gates + t * g.z_t, gr->g_kernel,
                                       gr->g_bias, stream))) return rc;
     }

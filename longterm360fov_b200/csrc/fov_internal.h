@@ -34,3 +34,44 @@ int fov_launch_mul_mask(long long n_img, long long img_elems, int C, const float
 int fov_conv_flip_weights(const fov_conv_cfg* fwd_cfg, const float* w, float* wt, cudaStream_t st);
 int fov_conv_bwd_data_preflipped(const fov_conv_cfg* fwd_cfg, const float* dy, const float* wt, float* dx,
                                  cudaStream_t st);
+
+// ---- tensor-core (tcgen05) implicit-GEMM convolution family (conv_tc.cu) -------------------
+// One K segment of the implicit-GEMM A operand: an NHWC activation tensor convolved with its
+// own (kh,kw) taps.  Two segments = the fused ConvLSTM gate GEMM [x taps | h taps] x [K ; R].
+struct TcSeg {
+  const float* x;
+  long long img_outer, img_inner;   // element offset of image n: (n / T_inner)*outer + (n % T_inner)*inner
+  int pix_stride;
+  int Cin;
+  int kh, kw, dil_h, dil_w, pad_h, pad_w;
+  const float* w;                   // Keras-layout weights of this segment
+  int w_mode;                       // 0: w[(tap*Cin+ci)*Cout+n]   1 (backward-data): w[((taps-1-tap)*Cout+n)*Cin+ci]
+};
+enum { TC_EPI_CONV = 0, TC_EPI_LSTM = 1 };
+struct TcConv {
+  int nseg;
+  TcSeg seg[2];
+  int N_img, T_inner, H, W;
+  int Cout;
+  int math;                         // bf16 terms per operand: 1 (bf16), 2 (3 MMAs), 3 (6 MMAs, ~fp32)
+  void* ws;                         // packed-weight workspace, tc_conv_ws_bytes() bytes
+  int prepacked;                    // 1: ws already holds the packed weights of this exact problem
+  // TC_EPI_CONV epilogue: y = act(acc + bias + beta*y)
+  int epi;
+  const float* bias;
+  float* y;
+  long long y_outer, y_inner;
+  int y_pix_stride;
+  int act;
+  float beta;
+  // TC_EPI_LSTM epilogue (Cout = 4F, gate blocks i,f,c,o): c_t = f*c_prev + i*tanh(zc); h = o*tanh(c_t)
+  int rec_act;
+  const float* c_prev; long long cp_outer, cp_inner;   // pixel stride F; may be NULL (zero state)
+  float* c_out;        long long c_outer, c_inner;     // pixel stride F
+  float* h_out;        long long h_outer, h_inner; int h_pix_stride;
+  float* gates_out;    long long g_outer, g_inner;     // optional activated gates (pixel stride 4F)
+  float *hT, *cT;                                      // optional dense copies (N_img,HW,F)
+};
+size_t tc_conv_ws_bytes(const TcConv& c);
+int tc_conv_pack(const TcConv& c, cudaStream_t st);
+int tc_conv_run(const TcConv& c, cudaStream_t st);

@@ -1,0 +1,313 @@
+// Stand-alone bring-up / regression harness for the tensor-core kernels of libfov360.so.
+// Compares every tcgen05 entry point with the fp32 CUDA-core kernel of the same C ABI on the
+// same random inputs (the fp32 kernels are the ones pinned to the oracle by tests/), prints the
+// max-abs errors and a few timings.  No torch, no Python: starts in milliseconds on the GPU box.
+//
+//   build:  longterm360fov_b200/csrc/build.sh   (-> csrc/build/tc_selftest)
+//   run:    longterm360fov_b200/csrc/build/tc_selftest [quick]
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/fov360.h"
+
+#define CK(x)                                                                         \
+  do {                                                                                \
+    cudaError_t e_ = (x);                                                             \
+    if (e_ != cudaSuccess) {                                                          \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                        \
+    }                                                                                 \
+  } while (0)
+#define FK(x)                                                                  \
+  do {                                                                         \
+    int r_ = (x);                                                              \
+    if (r_ != 0) {                                                             \
+      printf("fov error %d (%s) at %s:%d\n", r_, fov_last_error(), __FILE__, __LINE__); \
+      exit(3);                                                                 \
+    }                                                                          \
+  } while (0)
+
+static unsigned long long g_seed = 0x9E3779B97F4A7C15ull;
+static float frand() {   // uniform (-1,1)
+  g_seed ^= g_seed << 13; g_seed ^= g_seed >> 7; g_seed ^= g_seed << 17;
+  return (float)((g_seed >> 11) * (1.0 / 9007199254740992.0)) * 2.0f - 1.0f;
+}
+static float* dev_rand(size_t n, float scale) {
+  std::vector<float> h(n);
+  for (size_t i = 0; i < n; ++i) h[i] = frand() * scale;
+  float* d;
+  CK(cudaMalloc(&d, n * sizeof(float) + 256));
+  CK(cudaMemcpy(d, h.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  return d;
+}
+static float* dev_zero(size_t n) {
+  float* d;
+  CK(cudaMalloc(&d, n * sizeof(float) + 256));
+  CK(cudaMemset(d, 0, n * sizeof(float) + 256));
+  return d;
+}
+static float* dev_copy(const float* src, size_t n) {
+  float* d;
+  CK(cudaMalloc(&d, n * sizeof(float) + 256));
+  CK(cudaMemcpy(d, src, n * sizeof(float), cudaMemcpyDeviceToDevice));
+  return d;
+}
+struct Err { double max_abs, max_ref; };
+static Err compare(const float* a, const float* ref, size_t n) {
+  std::vector<float> ha(n), hr(n);
+  CK(cudaMemcpy(ha.data(), a, n * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hr.data(), ref, n * sizeof(float), cudaMemcpyDeviceToHost));
+  Err e{0.0, 0.0};
+  for (size_t i = 0; i < n; ++i) {
+    double d = fabs((double)ha[i] - (double)hr[i]);
+    if (!(d == d)) d = 1e30;
+    if (d > e.max_abs) e.max_abs = d;
+    if (fabs((double)hr[i]) > e.max_ref) e.max_ref = fabs((double)hr[i]);
+  }
+  return e;
+}
+static int g_fail = 0;
+static void report(const char* what, int math, Err e, double tol_rel) {
+  const double rel = e.max_abs / (e.max_ref > 0 ? e.max_ref : 1.0);
+  const bool ok = rel <= tol_rel;
+  if (!ok) ++g_fail;
+  printf("  %-34s math=%d max_abs=%.3e max_ref=%.3e rel=%.3e %s\n", what, math, e.max_abs, e.max_ref, rel,
+         ok ? "ok" : "FAIL");
+}
+static const double kTol[4] = {0, 2e-2, 2e-4, 1e-4};
+
+struct Timer {
+  cudaEvent_t a, b;
+  Timer() { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); }
+  void start() { CK(cudaEventRecord(a)); }
+  float stop_ms() { CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b)); float ms; CK(cudaEventElapsedTime(&ms, a, b)); return ms; }
+};
+
+static fov_conv_cfg mkcfg(int N, int H, int W, int Cin, int Cout, int kh, int kw, int dh, int dw, int act, float beta) {
+  fov_conv_cfg c{};
+  c.N = N; c.H = H; c.W = W; c.Cin = Cin; c.Cout = Cout; c.kh = kh; c.kw = kw; c.dil_h = dh; c.dil_w = dw;
+  c.pad_h = ((kh - 1) * dh) / 2; c.pad_w = ((kw - 1) * dw) / 2;
+  c.x_img_stride = (long long)H * W * Cin; c.x_pix_stride = Cin;
+  c.y_img_stride = (long long)H * W * Cout; c.y_pix_stride = Cout;
+  c.act = act; c.beta = beta;
+  return c;
+}
+
+static void test_conv(const char* name, fov_conv_cfg c, bool time_it) {
+  printf("[conv] %s N=%d HxW=%dx%d Cin=%d Cout=%d k=%dx%d dil=%d,%d act=%d beta=%g\n", name, c.N, c.H, c.W, c.Cin,
+         c.Cout, c.kh, c.kw, c.dil_h, c.dil_w, c.act, c.beta);
+  const size_t nx = (size_t)c.N * c.H * c.W * c.Cin, ny = (size_t)c.N * c.H * c.W * c.Cout;
+  const size_t nw = (size_t)c.kh * c.kw * c.Cin * c.Cout;
+  float* x = dev_rand(nx, 1.0f);
+  float* w = dev_rand(nw, 1.0f / sqrtf((float)(c.kh * c.kw * c.Cin)));
+  float* b = dev_rand(c.Cout, 0.5f);
+  float* y0 = dev_rand(ny, 1.0f);
+  float* yref = dev_copy(y0, ny);
+  FK(fov_conv2d_fwd(&c, x, w, b, yref, nullptr));
+  // backward-data reference: dy random, dx0 random (beta)
+  float* dy = dev_rand(ny, 1.0f);
+  float* dx0 = dev_rand(nx, 1.0f);
+  float* dxref = dev_copy(dx0, nx);
+  float* wsf = dev_zero(nw);
+  FK(fov_conv2d_bwd_data(&c, dy, w, dxref, wsf, nullptr));
+  CK(cudaDeviceSynchronize());
+  // fp64 truth on a sample of outputs (host): true error of the fp32 kernel and of each tensor-core mode
+  const int NSAMP = 512;
+  std::vector<size_t> sidx(NSAMP);
+  std::vector<double> struth(NSAMP);
+  {
+    std::vector<float> hx(nx), hw(nw), hb(c.Cout), hy0(ny);
+    CK(cudaMemcpy(hx.data(), x, nx * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hw.data(), w, nw * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hb.data(), b, c.Cout * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hy0.data(), y0, ny * 4, cudaMemcpyDeviceToHost));
+    for (int s = 0; s < NSAMP; ++s) {
+      const size_t idx = (size_t)((frand() * 0.5 + 0.5) * (double)(ny - 1));
+      sidx[s] = idx;
+      const int co = (int)(idx % c.Cout);
+      size_t r = idx / c.Cout;
+      const int xx0 = (int)(r % c.W); r /= c.W;
+      const int yy0 = (int)(r % c.H);
+      const int n = (int)(r / c.H);
+      double acc = hb[co] + c.beta * hy0[idx];
+      for (int ty = 0; ty < c.kh; ++ty)
+        for (int tx = 0; tx < c.kw; ++tx) {
+          const int yy = yy0 + ty * c.dil_h - c.pad_h, xx = xx0 + tx * c.dil_w - c.pad_w;
+          if (yy < 0 || yy >= c.H || xx < 0 || xx >= c.W) continue;
+          for (int ci = 0; ci < c.Cin; ++ci)
+            acc += (double)hx[(((size_t)n * c.H + yy) * c.W + xx) * c.Cin + ci] *
+                   (double)hw[((size_t)(ty * c.kw + tx) * c.Cin + ci) * c.Cout + co];
+        }
+      if (c.act == FOV_ACT_TANH) acc = tanh(acc);
+      if (c.act == FOV_ACT_RELU) acc = acc > 0 ? acc : 0;
+      struth[s] = acc;
+    }
+  }
+  auto true_err = [&](const float* yd, const char* tag) {
+    std::vector<float> hy(ny);
+    CK(cudaMemcpy(hy.data(), yd, ny * 4, cudaMemcpyDeviceToHost));
+    double e = 0;
+    for (int s = 0; s < NSAMP; ++s) { const double d = fabs((double)hy[sidx[s]] - struth[s]); if (d > e) e = d; }
+    printf("  true max-abs error vs fp64 (%d samples) %-12s %.3e\n", NSAMP, tag, e);
+  };
+  true_err(yref, "fp32 SIMT");
+  Timer tm;
+  for (int math = 1; math <= 3; ++math) {
+    size_t wb = fov_conv_tc_ws_bytes(&c, math, 0), wb2 = fov_conv_tc_ws_bytes(&c, math, 1);
+    void *ws, *ws2;
+    CK(cudaMalloc(&ws, wb + 256)); CK(cudaMalloc(&ws2, wb2 + 256));
+    float* y = dev_copy(y0, ny);
+    FK(fov_conv2d_fwd_tc(&c, x, w, b, y, ws, math, nullptr));
+    CK(cudaDeviceSynchronize());
+    report("fwd", math, compare(y, yref, ny), kTol[math]);
+    { char tag[32]; snprintf(tag, sizeof tag, "tc math=%d", math); true_err(y, tag); }
+    float* dx = dev_copy(dx0, nx);
+    FK(fov_conv2d_bwd_data_tc(&c, dy, w, dx, ws2, math, nullptr));
+    CK(cudaDeviceSynchronize());
+    report("bwd_data", math, compare(dx, dxref, nx), kTol[math]);
+    if (time_it) {
+      fov_conv_cfg ct = c; ct.beta = 0.f;
+      for (int i = 0; i < 3; ++i) FK(fov_conv2d_fwd_tc(&ct, x, w, b, y, ws, math, nullptr));
+      tm.start();
+      for (int i = 0; i < 10; ++i) FK(fov_conv2d_fwd_tc(&ct, x, w, b, y, ws, math, nullptr));
+      const float ms = tm.stop_ms() / 10;
+      const double fl = 2.0 * c.N * c.H * c.W * (double)c.Cout * c.kh * c.kw * c.Cin;
+      printf("  time fwd_tc math=%d: %.3f ms  (%.1f TFLOP/s algorithmic)\n", math, ms, fl / ms * 1e-9);
+    }
+    cudaFree(ws); cudaFree(ws2); cudaFree(y); cudaFree(dx);
+  }
+  if (time_it) {
+    fov_conv_cfg ct = c; ct.beta = 0.f;
+    for (int i = 0; i < 2; ++i) FK(fov_conv2d_fwd(&ct, x, w, b, yref, nullptr));
+    tm.start();
+    for (int i = 0; i < 5; ++i) FK(fov_conv2d_fwd(&ct, x, w, b, yref, nullptr));
+    const float ms = tm.stop_ms() / 5;
+    const double fl = 2.0 * c.N * c.H * c.W * (double)c.Cout * c.kh * c.kw * c.Cin;
+    printf("  time fwd fp32 SIMT : %.3f ms  (%.1f TFLOP/s)\n", ms, fl / ms * 1e-9);
+  }
+  cudaFree(x); cudaFree(w); cudaFree(b); cudaFree(y0); cudaFree(yref); cudaFree(dy); cudaFree(dx0); cudaFree(dxref);
+  cudaFree(wsf);
+}
+
+// ConvLSTM layer: SIMT (math 0) vs fused tensor-core step (math 1..3), forward + BPTT
+static void test_convlstm(const char* name, int B, int T, int H, int W, int Cin, int F, int kh, int kw, bool with_state,
+                          bool time_it) {
+  printf("[convlstm] %s B=%d T=%d HxW=%dx%d Cin=%d F=%d k=%dx%d state=%d\n", name, B, T, H, W, Cin, F, kh, kw,
+         (int)with_state);
+  const size_t HW = (size_t)H * W;
+  const size_t nx = (size_t)B * T * HW * Cin, nh = (size_t)B * T * HW * F, nz = nh * 4, ns = (size_t)B * HW * F;
+  const size_t nK = (size_t)kh * kw * Cin * 4 * F, nR = (size_t)kh * kw * F * 4 * F;
+  float* x = dev_rand(nx, 1.0f);
+  float* K = dev_rand(nK, 1.0f / sqrtf((float)(kh * kw * Cin)));
+  float* R = dev_rand(nR, 1.0f / sqrtf((float)(kh * kw * F)));
+  float* bias = dev_rand(4 * F, 0.5f);
+  float* h0 = with_state ? dev_rand(ns, 0.5f) : nullptr;
+  float* c0 = with_state ? dev_rand(ns, 0.5f) : nullptr;
+  float* dhseq = dev_rand(nh, 1.0f);
+  float* dhT = dev_rand(ns, 1.0f);
+  float* dcT = dev_rand(ns, 1.0f);
+
+  struct Out { float *hseq, *gates, *cseq, *hT, *cT, *dx, *dh0, *dc0, *gK, *gR, *gb; };
+  Out o[4];
+  Timer tm;
+  for (int math = 0; math <= 3; ++math) {
+    fov_convlstm_cfg c{};
+    c.B = B; c.T = T; c.H = H; c.W = W; c.Cin = Cin; c.F = F; c.kh = kh; c.kw = kw; c.dil_h = 1; c.dil_w = 1;
+    c.rec_act = FOV_REC_HARD_SIGMOID;
+    c.x_b_stride = (long long)T * HW * Cin; c.x_t_stride = (long long)HW * Cin; c.x_pix_stride = Cin;
+    c.h_b_stride = (long long)T * HW * F; c.h_t_stride = (long long)HW * F; c.h_pix_stride = F;
+    c.training = 1; c.math = math;
+    Out& r = o[math];
+    r.hseq = dev_zero(nh); r.gates = dev_zero(nz); r.cseq = dev_zero(nh); r.hT = dev_zero(ns); r.cT = dev_zero(ns);
+    r.dx = dev_zero(nx); r.dh0 = dev_zero(ns); r.dc0 = dev_zero(ns); r.gK = dev_zero(nK); r.gR = dev_zero(nR);
+    r.gb = dev_zero(4 * F);
+    fov_convlstm_io io{};
+    io.x = x; io.kernel = K; io.recurrent = R; io.bias = bias; io.h0 = h0; io.c0 = c0;
+    io.hseq = r.hseq; io.gates = r.gates; io.cseq = r.cseq; io.hT = r.hT; io.cT = r.cT;
+    const size_t fws = fov_convlstm_fwd_ws_bytes(&c);
+    void* wsf = nullptr;
+    if (fws) CK(cudaMalloc(&wsf, fws + 256));
+    io.ws = (float*)wsf;
+    FK(fov_convlstm_fwd(&c, &io, nullptr));
+    CK(cudaDeviceSynchronize());
+    if (time_it) {
+      tm.start();
+      for (int i = 0; i < 3; ++i) FK(fov_convlstm_fwd(&c, &io, nullptr));
+      printf("  time convlstm fwd math=%d: %.3f ms\n", math, tm.stop_ms() / 3);
+    }
+    fov_convlstm_grads g{};
+    g.dhseq = dhseq; g.dhT = dhT; g.dcT = dcT; g.dx = r.dx;
+    g.dh0 = with_state ? r.dh0 : nullptr; g.dc0 = with_state ? r.dc0 : nullptr;
+    g.g_kernel = r.gK; g.g_recurrent = r.gR; g.g_bias = r.gb;
+    const size_t bws = fov_convlstm_bwd_ws_floats(&c);
+    g.ws = dev_zero(bws);
+    g.dx_accumulate = 0;
+    // the BPTT overwrites the saved gates: keep a copy for the comparison
+    float* gates_keep = dev_copy(r.gates, nz);
+    if (time_it) tm.start();
+    FK(fov_convlstm_bwd(&c, &io, &g, nullptr));
+    if (time_it) printf("  time convlstm bwd math=%d: %.3f ms\n", math, tm.stop_ms());
+    CK(cudaDeviceSynchronize());
+    cudaFree(r.gates); r.gates = gates_keep;
+    cudaFree(g.ws);
+    if (wsf) cudaFree(wsf);
+    if (math > 0) {
+      const double tol = kTol[math] * 4;
+      report("hseq", math, compare(r.hseq, o[0].hseq, nh), tol);
+      report("cseq", math, compare(r.cseq, o[0].cseq, nh), tol);
+      report("gates", math, compare(r.gates, o[0].gates, nz), tol);
+      report("hT", math, compare(r.hT, o[0].hT, ns), tol);
+      report("cT", math, compare(r.cT, o[0].cT, ns), tol);
+      report("dx", math, compare(r.dx, o[0].dx, nx), tol * 4);
+      report("g_kernel", math, compare(r.gK, o[0].gK, nK), tol * 4);
+      report("g_recurrent", math, compare(r.gR, o[0].gR, nR), tol * 4);
+      report("g_bias", math, compare(r.gb, o[0].gb, 4 * F), tol * 4);
+      if (with_state) {
+        report("dh0", math, compare(r.dh0, o[0].dh0, ns), tol * 4);
+        report("dc0", math, compare(r.dc0, o[0].dc0, ns), tol * 4);
+      }
+    }
+  }
+  for (int m = 0; m <= 3; ++m) {
+    Out& r = o[m];
+    cudaFree(r.hseq); cudaFree(r.gates); cudaFree(r.cseq); cudaFree(r.hT); cudaFree(r.cT); cudaFree(r.dx);
+    cudaFree(r.dh0); cudaFree(r.dc0); cudaFree(r.gK); cudaFree(r.gR); cudaFree(r.gb);
+  }
+  cudaFree(x); cudaFree(K); cudaFree(R); cudaFree(bias); cudaFree(dhseq); cudaFree(dhT); cudaFree(dcT);
+  if (h0) { cudaFree(h0); cudaFree(c0); }
+}
+
+int main(int argc, char** argv) {
+  const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  if (!fov_device_is_sm100()) { printf("not an sm_100 device\n"); return 1; }
+  // --- convolution family ---
+  test_conv("dense 64->16", mkcfg(300, 1, 1, 64, 16, 1, 1, 1, 1, FOV_ACT_LINEAR, 0.f), false);
+  test_conv("m3 L0 rec", mkcfg(64, 1, 33, 32, 128, 1, 5, 1, 1, FOV_ACT_LINEAR, 1.f), false);
+  test_conv("m3 L0 in (Cin 6)", mkcfg(40, 1, 33, 6, 128, 1, 5, 1, 1, FOV_ACT_TANH, 0.f), false);
+  test_conv("5x5 30->32 36x18", mkcfg(3, 36, 18, 30, 32, 5, 5, 1, 1, FOV_ACT_RELU, 0.f), false);
+  test_conv("4x3 dil 2 odd", mkcfg(2, 9, 7, 5, 7, 4, 3, 2, 1, FOV_ACT_LINEAR, 1.f), false);
+  test_conv("dense 1848->256", mkcfg(500, 1, 1, 1848, 256, 1, 1, 1, 1, FOV_ACT_LINEAR, 0.f), false);
+  test_conv("dense 1848->198", mkcfg(200, 1, 1, 1848, 198, 1, 1, 1, 1, FOV_ACT_LINEAR, 0.f), false);
+  test_conv("head 5x5 56->512", mkcfg(2, 36, 18, 56, 512, 5, 5, 1, 1, FOV_ACT_RELU, 0.f), false);
+  test_conv("conv1d k7 56->40", mkcfg(5, 1, 30, 56, 40, 1, 7, 1, 1, FOV_ACT_RELU, 0.f), false);
+  // --- fused ConvLSTM ---
+  test_convlstm("m3 L0", 6, 4, 1, 33, 6, 32, 1, 5, false, false);
+  test_convlstm("m3 L1", 5, 3, 1, 33, 32, 16, 1, 5, true, false);
+  test_convlstm("m3 L2", 5, 3, 1, 33, 16, 8, 1, 5, false, false);
+  test_convlstm("m4 L0", 2, 3, 36, 18, 30, 32, 5, 5, true, false);
+  if (!quick) {
+    // --- timings at bench size (config 2, B=4096) ---
+    test_conv("T m3 L0 rec B=4096", mkcfg(4096, 1, 33, 32, 128, 1, 5, 1, 1, FOV_ACT_LINEAR, 0.f), true);
+    test_conv("T dense256 B=4096", mkcfg(40960, 1, 1, 1848, 256, 1, 1, 1, 1, FOV_ACT_LINEAR, 0.f), true);
+    test_conv("T head 56->512 B=32", mkcfg(32, 36, 18, 56, 512, 5, 5, 1, 1, FOV_ACT_RELU, 0.f), true);
+    test_conv("T head 512->1024 B=32", mkcfg(32, 36, 18, 512, 1024, 5, 5, 1, 1, FOV_ACT_RELU, 0.f), true);
+    test_convlstm("T m3 L0 B=2048", 2048, 20, 1, 33, 6, 32, 1, 5, false, true);
+  }
+  printf(g_fail ? "SELFTEST FAILED (%d)\n" : "SELFTEST OK (%d failures)\n", g_fail);
+  return g_fail ? 1 : 0;
+}
