@@ -157,6 +157,7 @@ def run_ours(args):
 
     model = fov.others_lstm_span_whole(num_user=NUM_USER, seed=1, device=dev)
     model.compile(optimizer="Adam", loss=["mean_squared_error"] * 3, loss_weights=[1, 1, 1])
+    model.set_compute(args.compute)
     if world > 1:
         model.distribute()
 
@@ -318,6 +319,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=2048, help="sequences per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=64, help="sequences per step of the CPU reference arm")
+    ap.add_argument("--compute", default="bf16x2", choices=["fp32", "bf16", "bf16x2", "bf16x3"],
+                    help="arithmetic of the conv/dense/ConvLSTM kernels: fp32 = CUDA cores; bf16x2 (default) = "
+                         "tcgen05 with two bf16 terms per operand, fp32 accumulate (fp32-grade results)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true",
                     help="only the device-resident timed region (for ncu runs): no e2e / infer / cpu legs")

@@ -159,6 +159,9 @@ int fov_conv2d_fwd_tc(const fov_conv_cfg* cfg, const float* x, const float* w, c
                       float* y, void* ws, int math, void* stream);
 int fov_conv2d_bwd_data_tc(const fov_conv_cfg* cfg, const float* dy, const float* w, float* dx,
                            void* ws, int math, void* stream);
+/* gw += x^T (*) dy ; gbias += colsum(dy): pixel reduction on tensor cores, split across CTAs */
+int fov_conv2d_bwd_weight_tc(const fov_conv_cfg* cfg, const float* x, const float* dy, float* gw,
+                             float* gbias, int math, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * ConvLSTM2D layer over a whole sequence (return_sequences=True, return_state).

@@ -12,6 +12,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfov360.so")
 
 ACT = {None: 0, "linear": 0, "tanh": 1, "relu": 2}
+# arithmetic of the convolution / dense / ConvLSTM family (include/fov360.h FOV_MATH_*):
+# fp32 = CUDA-core kernels; bf16 / bf16x2 / bf16x3 = tcgen05 kernels with 1 / 2 / 3 bf16 terms per
+# operand and fp32 accumulation in tensor memory (bf16x2 is fp32-grade: ~1e-5 max-abs error)
+MATH = {"fp32": 0, "bf16": 1, "bf16x2": 2, "bf16x3": 3}
 REC = {"hard_sigmoid": 0, "sigmoid": 1}
 
 c_float_p = C.c_void_p      # device pointers travel as integers
@@ -60,7 +64,7 @@ class ConvLstmCfg(C.Structure):
                 ("dil_w", C.c_int), ("rec_act", C.c_int),
                 ("x_b_stride", C.c_longlong), ("x_t_stride", C.c_longlong), ("x_pix_stride", C.c_int),
                 ("h_b_stride", C.c_longlong), ("h_t_stride", C.c_longlong), ("h_pix_stride", C.c_int),
-                ("training", C.c_int)]
+                ("training", C.c_int), ("math", C.c_int)]
 
 
 class ConvLstmIO(C.Structure):
@@ -91,8 +95,13 @@ SYMBOLS = {
     "fov_conv2d_fwd": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P]),
     "fov_conv2d_bwd_data": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P]),
     "fov_conv2d_bwd_weight": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P]),
+    "fov_conv_tc_ws_bytes": (C.c_size_t, [C.POINTER(ConvCfg), _I, _I]),
+    "fov_conv2d_fwd_tc": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P, _I, _P]),
+    "fov_conv2d_bwd_data_tc": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _I, _P]),
+    "fov_conv2d_bwd_weight_tc": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _I, _P]),
     "fov_act_bwd": (_I, [_I, _LL, _I, _P, _LL, _P, _LL, _P, _LL, _P]),
     "fov_convlstm_fwd": (_I, [C.POINTER(ConvLstmCfg), C.POINTER(ConvLstmIO), _P]),
+    "fov_convlstm_fwd_ws_bytes": (C.c_size_t, [C.POINTER(ConvLstmCfg)]),
     "fov_convlstm_bwd_ws_floats": (C.c_size_t, [C.POINTER(ConvLstmCfg)]),
     "fov_convlstm_bwd": (_I, [C.POINTER(ConvLstmCfg), C.POINTER(ConvLstmIO), C.POINTER(ConvLstmGrads), _P]),
     "fov_softmax_fwd": (_I, [_LL, _I, _P, _P, _P]),

@@ -37,6 +37,15 @@ Geo geo(const fov_convlstm_cfg* c) {
   return g;
 }
 
+// The fused tensor-core step covers the filter counts of the reference models (32/16/8, also 64)
+// with 16-byte aligned hidden-state rows; other shapes run the fp32 CUDA-core kernels.
+bool tc_step_ok(const fov_convlstm_cfg* c) {
+  if (c->math == 0) return false;
+  const int F = c->F;
+  if (!(F == 8 || F == 16 || F == 32 || F == 64)) return false;
+  return c->h_pix_stride % 4 == 0 && c->h_b_stride % 4 == 0 && c->h_t_stride % 4 == 0;
+}
+
 fov_conv_cfg input_conv_cfg(const fov_convlstm_cfg* c) {
   fov_conv_cfg k{};
   k.H = c->H; k.W = c->W; k.Cin = c->Cin; k.Cout = 4 * c->F;
@@ -108,7 +117,7 @@ TcConv in_bwd_conv(const fov_convlstm_cfg* c, const float* kernel, const Geo& g)
 }  // namespace
 
 extern "C" size_t fov_convlstm_fwd_ws_bytes(const fov_convlstm_cfg* cfg) {
-  if (!cfg || cfg->math == 0 || check(cfg)) return 0;
+  if (!cfg || check(cfg) || !tc_step_ok(cfg)) return 0;
   fov_convlstm_io io{};
   return tc_conv_ws_bytes(step_conv(cfg, &io, geo(cfg)));
 }
@@ -148,7 +157,7 @@ extern "C" int fov_convlstm_fwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
   FOV_CHECK_ARG(io && io->x && io->kernel && io->recurrent && io->bias && io->hseq && io->gates && io->cseq,
                 "NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (cfg->math != 0) return convlstm_fwd_tc(cfg, io, st);
+  if (tc_step_ok(cfg)) return convlstm_fwd_tc(cfg, io, st);
   const Geo g = geo(cfg);
   const int F = cfg->F;
 
@@ -208,7 +217,7 @@ extern "C" size_t fov_convlstm_bwd_ws_floats(const fov_convlstm_cfg* c) {
   const size_t taps = (size_t)c->kh * c->kw;
   // dh_rec + dc (ping-pong x2) + flipped recurrent + flipped kernel
   size_t n = 4 * bhwf + taps * c->F * 4 * c->F + taps * c->Cin * 4 * c->F + 64;
-  if (c->math != 0) {   // packed bf16 weights of the two tensor-core backward-data convolutions
+  if (tc_step_ok(c)) {   // packed bf16 weights of the two tensor-core backward-data convolutions
     const Geo g = geo(c);
     n += (tc_conv_ws_bytes(rec_bwd_conv(c, nullptr, g)) + tc_conv_ws_bytes(in_bwd_conv(c, nullptr, g))) / 4 + 128;
   }
@@ -235,7 +244,7 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
   r.beta = 0.0f;
   // dh_rec is produced as the "x" side of the recurrent conv: dense (B,HW,F)
   r.x_img_stride = g.hw_f; r.x_pix_stride = F; r.y_img_stride = g.z_b;
-  const bool tcm = cfg->math != 0;
+  const bool tcm = tc_step_ok(cfg);
   TcConv rT = rec_bwd_conv(cfg, io->recurrent, g);
   TcConv kT = in_bwd_conv(cfg, io->kernel, g);
   if (tcm) {
@@ -276,25 +285,60 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
     }
   }
 
+  if (tcm) {
+    // ---- tensor-core path: dx, gK (+ bias gradient) and gR, each one launch over every (b,t) image ----
+    if (gr->dx) {
+      kT.seg[0].x = io->gates; kT.y = gr->dx; kT.beta = gr->dx_accumulate ? 1.0f : 0.0f;
+      if ((rc = tc_conv_run(kT, st))) return rc;
+    }
+    TcWgrad w{};
+    w.N_img = cfg->B * cfg->T; w.T_inner = cfg->T; w.H = cfg->H; w.W = cfg->W; w.math = cfg->math;
+    w.x = io->x; w.x_outer = cfg->x_b_stride; w.x_inner = cfg->x_t_stride; w.x_pix_stride = cfg->x_pix_stride;
+    w.Cin = cfg->Cin; w.kh = cfg->kh; w.kw = cfg->kw; w.dil_h = cfg->dil_h; w.dil_w = cfg->dil_w;
+    w.pad_h = ((cfg->kh - 1) * cfg->dil_h) / 2; w.pad_w = ((cfg->kw - 1) * cfg->dil_w) / 2;
+    w.dy = io->gates; w.dy_outer = g.z_b; w.dy_inner = g.z_t; w.dy_pix_stride = 4 * F; w.Cout = 4 * F;
+    w.gw = gr->g_kernel; w.gbias = gr->g_bias;
+    if (w.gw || w.gbias) {
+      if (!w.gw) {
+        fov_set_error("fov_convlstm_bwd: g_kernel is required on the tensor-core path");
+        return FOV_ERR_ARG;
+      }
+      if ((rc = tc_wgrad_run(w, st))) return rc;
+    }
+    if (gr->g_recurrent) {
+      w.dil_h = 1; w.dil_w = 1; w.pad_h = (cfg->kh - 1) / 2; w.pad_w = (cfg->kw - 1) / 2;
+      w.Cin = F; w.gw = gr->g_recurrent; w.gbias = nullptr;
+      if (cfg->T > 1) {   // pairs (h_{t-1}, dZ_t), t = 1..T-1
+        w.N_img = cfg->B * (cfg->T - 1); w.T_inner = cfg->T - 1;
+        w.x = io->hseq; w.x_outer = cfg->h_b_stride; w.x_inner = cfg->h_t_stride; w.x_pix_stride = cfg->h_pix_stride;
+        w.dy = io->gates + g.z_t;
+        if ((rc = tc_wgrad_run(w, st))) return rc;
+      }
+      if (io->h0) {       // pair (h0, dZ_0)
+        w.N_img = cfg->B; w.T_inner = 1;
+        w.x = io->h0; w.x_outer = g.hw_f; w.x_inner = 0; w.x_pix_stride = F;
+        w.dy = io->gates;
+        if ((rc = tc_wgrad_run(w, st))) return rc;
+      }
+    }
+    return FOV_OK;
+  }
   // ---- time-batched input-side gradients ----
   fov_conv_cfg k = input_conv_cfg(cfg);
   k.beta = gr->dx_accumulate ? 1.0f : 0.0f;
   k.N = cfg->B;
   const bool batched = (cfg->x_b_stride == (long long)cfg->T * cfg->x_t_stride) || cfg->T == 1;
-  if (gr->dx && tcm) {
-    kT.seg[0].x = io->gates; kT.y = gr->dx; kT.beta = gr->dx_accumulate ? 1.0f : 0.0f;
-    if ((rc = tc_conv_run(kT, st))) return rc;
-  } else if (gr->dx) {
+  if (gr->dx) {
     if ((rc = fov_conv_flip_weights(&k, io->kernel, Kt, st))) return rc;
   }
   if (batched) {
     k.N = cfg->B * cfg->T; k.x_img_stride = cfg->T == 1 ? cfg->x_b_stride : cfg->x_t_stride; k.y_img_stride = g.z_t;
-    if (gr->dx && !tcm && (rc = fov_conv_bwd_data_preflipped(&k, io->gates, Kt, gr->dx, st))) return rc;
+    if (gr->dx && (rc = fov_conv_bwd_data_preflipped(&k, io->gates, Kt, gr->dx, st))) return rc;
     if ((rc = fov_conv2d_bwd_weight(&k, io->x, io->gates, gr->g_kernel, gr->g_bias, stream))) return rc;
   } else {
     k.N = cfg->B; k.x_img_stride = cfg->x_b_stride; k.y_img_stride = g.z_b;
     for (int t = 0; t < cfg->T; ++t) {
-      if (gr->dx && !tcm && (rc = fov_conv_bwd_data_preflipped(&k, io->gates + t * g.z_t, Kt, gr->dx + t * cfg->x_t_stride, st))) return rc;
+      if (gr->dx && (rc = fov_conv_bwd_data_preflipped(&k, io->gates + t * g.z_t, Kt, gr->dx + t * cfg->x_t_stride, st))) return rc;
       if ((rc = fov_conv2d_bwd_weight(&k, io->x + t * cfg->x_t_stride, io->gates + t * g.z_t, gr->g_kernel,
                                       gr->g_bias, stream))) return rc;
     }

@@ -75,3 +75,17 @@ struct TcConv {
 size_t tc_conv_ws_bytes(const TcConv& c);
 int tc_conv_pack(const TcConv& c, cudaStream_t st);
 int tc_conv_run(const TcConv& c, cudaStream_t st);
+
+// Tensor-core weight gradient: gw[(tap*Cin+ci)*Cout+n] += sum_pixels x(pixel+tap, ci) * dy(pixel, n),
+// gbias[n] += sum_pixels dy(pixel, n).  Both operands are read in their natural NHWC layout and
+// fed to tcgen05.mma as MN-major tiles; the pixel reduction is split across CTAs (atomic adds).
+struct TcWgrad {
+  const float* x;  long long x_outer, x_inner;   int x_pix_stride;  int Cin;
+  int kh, kw, dil_h, dil_w, pad_h, pad_w;
+  const float* dy; long long dy_outer, dy_inner; int dy_pix_stride; int Cout;
+  int N_img, T_inner, H, W;
+  int math;
+  float* gw;       // may be NULL (bias gradient only)
+  float* gbias;    // may be NULL
+};
+int tc_wgrad_run(const TcWgrad& c, cudaStream_t st);

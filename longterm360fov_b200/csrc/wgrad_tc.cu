@@ -1,0 +1,387 @@
+// Tensor-core (tcgen05 + TMEM) weight gradient of the convolution family for sm_100a.
+//
+//   gw[k][n] += sum_m A(m,k) * dY[m][n]        k = (tap, channel), m = pixel, n = output channel
+//   gbias[n] += sum_m dY[m][n]
+//
+// As a tcgen05 GEMM the reduction index is the pixel: D[128 k][BLOCK_N n] += A'[k][pixel] B'[n][pixel].
+// Both operands are contiguous along their M/N index in HBM (channels-last), so they are staged
+// as MN-major 128-byte-swizzled tiles: one shared-memory row per pixel, 64 bf16 along k (or n).
+// 256 producer threads gather 64 pixels per stage (coalesced float4 along channels), split every
+// value into NS bf16 terms and keep the loads of the next pixel block in flight while the
+// current one is converted; one thread issues the MMAs; the pixel range is split across
+// blockIdx.z and the partial tiles are added to gw with coalesced red.global.add.
+// The bias gradient is a by-product of the dY gather (per-thread column sums).
+//
+// Replaces the weight-gradient ops TF1 generates for Dense / Conv2D / ConvLSTM2D
+// (mycode/others_LSTM_span_whole.py:88-109, mycode/convlstm_seq2seq.py:100-126,175-181).
+#include "fov_common.cuh"
+#include "fov_internal.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int WG_M = 128;            // k rows per CTA (MMA M)
+constexpr int WG_PIX = 64;           // pixels per pipeline stage (4 MMA K-steps of 16)
+constexpr int WG_GRP = WG_PIX * 128; // bytes of one 64-wide MN group (64 pixel rows x 128 B)
+constexpr int kProd = 256;           // producer threads (warps 0-7)
+constexpr int kThr = 320;            // + table warp (8) + MMA warp (9)
+constexpr int kStagesMax = 3;
+constexpr int RS = 36;
+
+struct WgParams {
+  const float* x; long long x_outer, x_inner; int x_pix_stride, Cin, Cin_p, kw, taps, dil_h, dil_w, pad_h, pad_w, x_vec;
+  const float* dy; long long dy_outer, dy_inner; int dy_pix_stride, Cout, dy_vec;
+  int H, W, HW, T_inner, M;
+  int BLOCK_N, tmem_cols, stages, stage_bytes, b_term_bytes, data_bytes;
+  int nblocks, blocks_per_split;
+  float* gw; float* gbias;
+};
+
+struct RowTab {
+  long long offx[WG_PIX], offdy[WG_PIX];
+  int py[WG_PIX], px[WG_PIX];
+};
+struct Book {
+  RowTab tab[kStagesMax];
+  int dstrow[WG_M];                 // row of gw this accumulator row adds to, or -1
+  uint64_t full[kStagesMax], empty[kStagesMax], tabrdy[kStagesMax], tmem_full;
+  uint32_t tmem_ptr;
+};
+
+__device__ __forceinline__ float4 ld4(const float* __restrict__ p, int nvalid, int vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec == 4) {
+    v = __ldg(reinterpret_cast<const float4*>(p));
+  } else if (vec == 2) {
+    if (nvalid >= 2) { const float2 a = __ldg(reinterpret_cast<const float2*>(p)); v.x = a.x; v.y = a.y; }
+    if (nvalid >= 4) { const float2 b = __ldg(reinterpret_cast<const float2*>(p + 2)); v.z = b.x; v.w = b.y; }
+  } else {
+    if (nvalid > 0) v.x = __ldg(p);
+    if (nvalid > 1) v.y = __ldg(p + 1);
+    if (nvalid > 2) v.z = __ldg(p + 2);
+    if (nvalid > 3) v.w = __ldg(p + 3);
+  }
+  return v;
+}
+
+template <int NS>
+__device__ __forceinline__ void store_split(uint8_t* tile0, int term_bytes, uint32_t off, const float4& v) {
+  float t0[NS], t1[NS], t2[NS], t3[NS];
+  bf16_split<NS>(v.x, t0); bf16_split<NS>(v.y, t1); bf16_split<NS>(v.z, t2); bf16_split<NS>(v.w, t3);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    uint2 pk;
+    pk.x = pack_bf16x2(t0[s], t1[s]);
+    pk.y = pack_bf16x2(t2[s], t3[s]);
+    *reinterpret_cast<uint2*>(tile0 + s * term_bytes + off) = pk;
+  }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  Book* bk = reinterpret_cast<Book*>(smem + p.data_bytes);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int k_tile = blockIdx.x, n0 = blockIdx.y * p.BLOCK_N;
+  const int S = p.stages;
+  const int blk0 = blockIdx.z * p.blocks_per_split;
+  int nblk = p.nblocks - blk0;
+  if (nblk > p.blocks_per_split) nblk = p.blocks_per_split;
+  constexpr int A_TERM = 2 * WG_GRP;   // 128 k values = two 64-wide groups
+
+  if (tid < WG_M) {
+    const int k = k_tile * WG_M + tid;
+    const int tap = k / p.Cin_p, ci = k - tap * p.Cin_p;
+    bk->dstrow[tid] = (tap < p.taps && ci < p.Cin) ? tap * p.Cin + ci : -1;
+  }
+  if (warp == 9 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&bk->full[s]), kProd);
+      mbar_init(smem_u32(&bk->empty[s]), 1);
+      mbar_init(smem_u32(&bk->tabrdy[s]), 1);
+    }
+    mbar_init(smem_u32(&bk->tmem_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(smem_u32(&bk->tmem_ptr), (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = bk->tmem_ptr;
+
+  float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int f4 = p.BLOCK_N >> 2;          // float4 per dY row of this n tile (4..32)
+  const int nb = (WG_PIX * f4) / kProd;   // dY loads per thread per block (1..8)
+  const int b_c4 = tid % f4;              // fixed float4 column of this thread
+  const int b_row0 = tid / f4, b_rstep = kProd / f4;
+
+  if (warp < 8) {
+    // ---------------- producers ----------------
+    const int q = tid & 31, rsub = tid >> 5;           // A': float4 slot along k, row phase
+    const int k = k_tile * WG_M + q * 4;
+    const int tap = k / p.Cin_p, ci = k - tap * p.Cin_p;
+    int a_nvalid = (tap < p.taps) ? (p.Cin - ci) : 0;
+    a_nvalid = a_nvalid < 0 ? 0 : (a_nvalid > 4 ? 4 : a_nvalid);
+    const int ty = tap / p.kw, tx = tap - ty * p.kw;
+    const int tdy = ty * p.dil_h - p.pad_h, tdx = tx * p.dil_w - p.pad_w;
+    const float* xb = p.x + ci;
+    const uint32_t a_col = (uint32_t)(q >> 4) * WG_GRP + (uint32_t)(q & 1) * 8u;
+    const int a_chunk = (q & 15) >> 1;
+    const int bcol = n0 + b_c4 * 4;
+    int b_nvalid = p.Cout - bcol;
+    b_nvalid = b_nvalid < 0 ? 0 : (b_nvalid > 4 ? 4 : b_nvalid);
+    const float* dyb = p.dy + bcol;
+    const uint32_t b_col = (uint32_t)(b_c4 >> 4) * WG_GRP + (uint32_t)(b_c4 & 1) * 8u;
+    const int b_chunk = (b_c4 & 15) >> 1;
+
+    auto issue = [&](int stage, float4 (&va)[8], float4 (&vb)[8]) {
+      const RowTab& t = bk->tab[stage];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = j * 8 + rsub;
+        const int yy = t.py[r] + tdy, xx = t.px[r] + tdx;
+        va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a_nvalid > 0 && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+          va[j] = ld4(xb + t.offx[r] + (long long)(yy * p.W + xx) * p.x_pix_stride, a_nvalid, p.x_vec);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        vb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < nb) {
+          const int r = b_row0 + j * b_rstep;
+          if (b_nvalid > 0 && t.py[r] >= 0) vb[j] = ld4(dyb + t.offdy[r], b_nvalid, p.dy_vec);
+        }
+      }
+    };
+    auto store = [&](int stage, const float4 (&va)[8], const float4 (&vb)[8]) {
+      uint8_t* a_tile = smem + (size_t)stage * p.stage_bytes;
+      uint8_t* b_tile = a_tile + NS * A_TERM;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = j * 8 + rsub;
+        store_split<NS>(a_tile, A_TERM, a_col + (uint32_t)r * 128u + ((uint32_t)(a_chunk ^ (r & 7)) << 4), va[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < nb) {
+          const int r = b_row0 + j * b_rstep;
+          store_split<NS>(b_tile, p.b_term_bytes, b_col + (uint32_t)r * 128u + ((uint32_t)(b_chunk ^ (r & 7)) << 4),
+                          vb[j]);
+          bsum.x += vb[j].x; bsum.y += vb[j].y; bsum.z += vb[j].z; bsum.w += vb[j].w;
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&bk->full[stage]));
+    };
+    float4 a0[8], b0[8], a1[8], b1[8];
+    mbar_wait(smem_u32(&bk->tabrdy[0]), 0);
+    issue(0, a0, b0);
+    for (int i = 0; i < nblk; i += 2) {
+      // block i lives in (a0,b0); prefetch block i+1 into (a1,b1), then the roles swap
+      if (i + 1 < nblk) {
+        const int s1 = (i + 1) % S;
+        mbar_wait(smem_u32(&bk->tabrdy[s1]), (uint32_t)((i + 1) / S) & 1u);
+        issue(s1, a1, b1);
+      }
+      store(i % S, a0, b0);
+      if (i + 1 < nblk) {
+        if (i + 2 < nblk) {
+          const int s2 = (i + 2) % S;
+          mbar_wait(smem_u32(&bk->tabrdy[s2]), (uint32_t)((i + 2) / S) & 1u);
+          issue(s2, a0, b0);
+        }
+        store((i + 1) % S, a1, b1);
+      }
+    }
+  } else if (warp == 8) {
+    // ---------------- row-table builder: pixel -> (image offsets, y, x) for each stage ----------------
+    for (int i = 0; i < nblk; ++i) {
+      const int stage = i % S;
+      mbar_wait(smem_u32(&bk->empty[stage]), ((uint32_t)(i / S) & 1u) ^ 1u);
+      RowTab& t = bk->tab[stage];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = lane + h * 32;
+        const int m = (blk0 + i) * WG_PIX + r;
+        if (m < p.M) {
+          const int n = m / p.HW, pix = m - n * p.HW;
+          const int no = n / p.T_inner, ni = n - no * p.T_inner;
+          t.py[r] = pix / p.W;
+          t.px[r] = pix - (pix / p.W) * p.W;
+          t.offx[r] = (long long)no * p.x_outer + (long long)ni * p.x_inner;
+          t.offdy[r] = (long long)no * p.dy_outer + (long long)ni * p.dy_inner + (long long)pix * p.dy_pix_stride;
+        } else {
+          t.py[r] = -(1 << 28); t.px[r] = 0; t.offx[r] = 0; t.offdy[r] = 0;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bk->tabrdy[stage]));
+    }
+  } else {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16_f32(WG_M, p.BLOCK_N, 1, 1);
+      for (int i = 0; i < nblk; ++i) {
+        const int stage = i % S;
+        mbar_wait(smem_u32(&bk->full[stage]), (uint32_t)(i / S) & 1u);
+        tc_fence_after();
+        const uint32_t a_base = base + (uint32_t)stage * p.stage_bytes;
+        const uint32_t b_base = a_base + NS * A_TERM;
+#pragma unroll
+        for (int k4 = 0; k4 < WG_PIX / 16; ++k4) {
+#pragma unroll
+          for (int sum = NS - 1; sum >= 0; --sum) {
+#pragma unroll
+            for (int sa = 0; sa <= sum; ++sa) {
+              const int sb = sum - sa;
+              // 16 pixel rows per K step = 2048 B; LBO = stride between 64-wide M/N groups, SBO = 8 pixel rows
+              const uint64_t ad = smem_desc_sw128(a_base + sa * A_TERM + k4 * 2048, WG_GRP, 1024);
+              const uint64_t bd = smem_desc_sw128(b_base + sb * p.b_term_bytes + k4 * 2048, WG_GRP, 1024);
+              const uint32_t acc = (i > 0 || k4 > 0 || sum != NS - 1 || sa > 0) ? 1u : 0u;
+              umma_bf16(tmem_d, ad, bd, idesc, acc);
+            }
+          }
+        }
+        umma_commit(smem_u32(&bk->empty[stage]));
+      }
+      umma_commit(smem_u32(&bk->tmem_full));
+    }
+  }
+
+  // ---------------- epilogue: warps 0-3 add the partial tile into gw ----------------
+  if (warp < 4 && p.gw) {
+    mbar_wait(smem_u32(&bk->tmem_full), 0);
+    tc_fence_after();
+    const int r0 = warp * 32;
+    const uint32_t t_row = tmem_d + ((uint32_t)r0 << 16);
+    float* stg = reinterpret_cast<float*>(smem) + warp * (32 * RS);
+    for (int c0 = 0; c0 < p.BLOCK_N; c0 += 32) {
+      float v[32];
+      tmem_ld16(t_row + c0, v);
+      tmem_ld16(t_row + c0 + 16, v + 16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(&stg[lane * RS + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      __syncwarp();
+      const int col = n0 + c0 + lane;
+      const bool col_ok = (c0 + lane < p.BLOCK_N) && (col < p.Cout);
+      for (int rr = 0; rr < 32; ++rr) {
+        const int dr = bk->dstrow[r0 + rr];
+        if (dr >= 0 && col_ok) atomicAdd(p.gw + (long long)dr * p.Cout + col, stg[rr * RS + lane]);
+      }
+      __syncwarp();
+    }
+  }
+  if (warp < 8 && p.gbias && k_tile == 0) {
+    const int bcol = n0 + b_c4 * 4;
+    if (bcol < p.Cout) atomicAdd(p.gbias + bcol, bsum.x);
+    if (bcol + 1 < p.Cout) atomicAdd(p.gbias + bcol + 1, bsum.y);
+    if (bcol + 2 < p.Cout) atomicAdd(p.gbias + bcol + 2, bsum.z);
+    if (bcol + 3 < p.Cout) atomicAdd(p.gbias + bcol + 3, bsum.w);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
+}
+
+int vec_of(const void* ptr, long long a, long long b, long long c, long long d) {
+  auto al = [&](long long m) {
+    return ((uintptr_t)ptr % (4 * m) == 0) && a % m == 0 && b % m == 0 && c % m == 0 && d % m == 0;
+  };
+  if (al(4)) return 4;
+  if (al(2)) return 2;
+  return 1;
+}
+
+template <int NS>
+int launch(const WgParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      fov_set_error("tc_wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return FOV_ERR_CUDA;
+    }
+    configured = true;
+  }
+  tc_wgrad_kernel<NS><<<grid, kThr, smem, st>>>(p);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
+
+}  // namespace
+
+int tc_wgrad_run(const TcWgrad& c, cudaStream_t st) {
+  FOV_CHECK_ARG(c.math >= 1 && c.math <= 3, "math must be 1..3 bf16 terms");
+  FOV_CHECK_ARG(c.x && c.dy && (c.gw || c.gbias), "NULL pointer");
+  FOV_CHECK_ARG(c.N_img > 0 && c.H > 0 && c.W > 0 && c.Cin > 0 && c.Cout > 0 && c.T_inner > 0, "bad shape");
+  const long long M = (long long)c.N_img * c.H * c.W;
+  FOV_CHECK_ARG(M < (1LL << 31) - WG_PIX, "too many pixels for 32-bit indexing");
+  WgParams p{};
+  p.x = c.x; p.x_outer = c.x_outer; p.x_inner = c.x_inner; p.x_pix_stride = c.x_pix_stride;
+  p.Cin = c.Cin; p.Cin_p = (c.Cin + 7) / 8 * 8; p.kw = c.kw; p.taps = c.kh * c.kw;
+  p.dil_h = c.dil_h; p.dil_w = c.dil_w; p.pad_h = c.pad_h; p.pad_w = c.pad_w;
+  p.x_vec = vec_of(c.x, c.x_outer, c.x_inner, c.x_pix_stride, c.Cin);
+  p.dy = c.dy; p.dy_outer = c.dy_outer; p.dy_inner = c.dy_inner; p.dy_pix_stride = c.dy_pix_stride; p.Cout = c.Cout;
+  p.dy_vec = vec_of(c.dy, c.dy_outer, c.dy_inner, c.dy_pix_stride, c.Cout);
+  p.H = c.H; p.W = c.W; p.HW = c.H * c.W; p.T_inner = c.T_inner; p.M = (int)M;
+  p.gw = c.gw; p.gbias = c.gbias;
+  // n tile: 16/32/64/128 wide (the dY row of a thread must keep a fixed float4 column)
+  int bn = 16;
+  while (bn < c.Cout && bn < 128) bn <<= 1;
+  p.BLOCK_N = bn;
+  const int n_tiles = (c.Cout + bn - 1) / bn;
+  const int k_tiles = c.gw ? (p.taps * p.Cin_p + WG_M - 1) / WG_M : 1;
+  p.tmem_cols = (int)tmem_cols_for(bn);
+  p.b_term_bytes = (bn + 63) / 64 * WG_GRP;
+  p.stage_bytes = c.math * (2 * WG_GRP + p.b_term_bytes);
+  int stg = (227 * 1024 - (int)sizeof(Book) - 2048) / p.stage_bytes;
+  if (stg > kStagesMax) stg = kStagesMax;
+  FOV_CHECK_ARG(stg >= 2, "tile does not fit shared memory");
+  p.stages = stg;
+  p.data_bytes = stg * p.stage_bytes;
+  if (p.data_bytes < 4 * 32 * RS * 4) p.data_bytes = 4 * 32 * RS * 4;
+  p.data_bytes = (p.data_bytes + 1023) / 1024 * 1024;
+  const size_t smem = (size_t)p.data_bytes + sizeof(Book) + 1024;
+  p.nblocks = (int)((M + WG_PIX - 1) / WG_PIX);
+  // split the pixel reduction so that ~2 waves of CTAs cover the SMs, at least 8 blocks per CTA
+  long long want = (2LL * fov_num_sms() + (long long)k_tiles * n_tiles - 1) / ((long long)k_tiles * n_tiles);
+  long long max_splits = (p.nblocks + 7) / 8;
+  if (want > max_splits) want = max_splits;
+  if (want < 1) want = 1;
+  if (want > 65535) want = 65535;
+  p.blocks_per_split = (int)((p.nblocks + want - 1) / want);
+  const int splits = (p.nblocks + p.blocks_per_split - 1) / p.blocks_per_split;
+  dim3 grid((unsigned)k_tiles, (unsigned)n_tiles, (unsigned)splits);
+  if (c.math == 1) return launch<1>(p, grid, smem, st);
+  if (c.math == 2) return launch<2>(p, grid, smem, st);
+  return launch<3>(p, grid, smem, st);
+}
+
+extern "C" int fov_conv2d_bwd_weight_tc(const fov_conv_cfg* cfg, const float* x, const float* dy, float* gw,
+                                        float* gbias, int math, void* stream) {
+  FOV_CHECK_ARG(cfg != nullptr, "cfg is NULL");
+  FOV_CHECK_ARG(cfg->N > 0 && cfg->H > 0 && cfg->W > 0 && cfg->Cin > 0 && cfg->Cout > 0, "bad shape");
+  FOV_CHECK_ARG(cfg->kh > 0 && cfg->kw > 0 && cfg->dil_h > 0 && cfg->dil_w > 0, "bad kernel/dilation");
+  FOV_CHECK_ARG(dy != nullptr && (gw == nullptr || x != nullptr), "NULL pointer");
+  if (!gw) return fov_conv2d_bwd_weight(cfg, x, dy, nullptr, gbias, stream);   // bias only: column-sum kernel
+  TcWgrad c{};
+  c.x = x; c.x_outer = cfg->x_img_stride; c.x_inner = 0; c.x_pix_stride = cfg->x_pix_stride; c.Cin = cfg->Cin;
+  c.kh = cfg->kh; c.kw = cfg->kw; c.dil_h = cfg->dil_h; c.dil_w = cfg->dil_w; c.pad_h = cfg->pad_h; c.pad_w = cfg->pad_w;
+  c.dy = dy; c.dy_outer = cfg->y_img_stride; c.dy_inner = 0; c.dy_pix_stride = cfg->y_pix_stride; c.Cout = cfg->Cout;
+  c.N_img = cfg->N; c.T_inner = 1; c.H = cfg->H; c.W = cfg->W;
+  c.math = math; c.gw = gw; c.gbias = gbias;
+  return tc_wgrad_run(c, (cudaStream_t)stream);
+}

@@ -125,6 +125,16 @@ class Model:
         self.process_group = None
         self.world_size = 1
         self.running_length = 10
+        # arithmetic of the conv / dense / ConvLSTM kernels (ops.set_math): tensor cores with 2 bf16
+        # terms per operand by default (fp32-grade results); "fp32" selects the CUDA-core kernels
+        self.compute = os.environ.get("FOV_COMPUTE", "bf16x2")
+
+    def set_compute(self, mode):
+        """'fp32' | 'bf16' | 'bf16x2' | 'bf16x3' (see _lib.MATH)."""
+        if mode not in _lib.MATH:
+            raise ValueError("compute must be one of %s" % sorted(_lib.MATH))
+        self.compute = mode
+        return self
 
     # ------------------------------------------------------------------ #
     # weights
@@ -220,6 +230,7 @@ class Model:
         """One optimiser step on device tensors; returns the loss as a device tensor
         (no host sync).  DP: gradients are sum-allreduced and scaled by 1/world."""
         self.gflat.zero_()
+        ops.set_math(self.compute)
         outs = self._forward(xs, True)
         total = self._loss(outs, ys)
         total.backward()
@@ -237,12 +248,14 @@ class Model:
     def test_on_batch(self, x, y):
         xs, ys = self._to_dev(self._as_list(x)), self._to_dev(self._as_list(y))
         with torch.no_grad():
+            ops.set_math(self.compute)
             outs = self._forward(xs, False)
             return float(self._loss(outs, ys).item())
 
     def predict_on_batch(self, x):
         xs = self._to_dev(self._as_list(x))
         with torch.no_grad():
+            ops.set_math(self.compute)
             outs = self._forward(xs, False)
         outs = [o.cpu().numpy() for o in outs]
         return outs if self.n_outputs > 1 else outs[0]

@@ -33,6 +33,24 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# arithmetic used by the conv / dense / ConvLSTM Functions built from now on (see _lib.MATH);
+# each Function records the mode of its forward for its backward.
+_MATH = [_lib.MATH["bf16x2"]]
+
+
+def set_math(mode):
+    """mode: 'fp32' (CUDA cores), 'bf16', 'bf16x2' (default, fp32-grade on tensor cores), 'bf16x3'."""
+    _MATH[0] = _lib.MATH[mode] if isinstance(mode, str) else int(mode)
+
+
+def get_math():
+    return _MATH[0]
+
+
+def _ws(nbytes, device):
+    return torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+
+
 # --------------------------------------------------------------------------- #
 # persistent fc-LSTM encoder-decoder
 # --------------------------------------------------------------------------- #
@@ -179,9 +197,16 @@ class Conv2DFn(torch.autograd.Function):
         act = opts.get("activation")
         y = torch.empty(N, H, W, Cout, device=x.device)
         cfg = _conv_cfg(N, H, W, Cin, Cout, kh, kw, dil, act, 0.0, H * W * Cin, Cin, H * W * Cout, Cout)
-        _lib.check(lib.fov_conv2d_fwd(C.byref(cfg), ptr(x), ptr(kernel), ptr(bias), ptr(y), _stream()),
-                   "fov_conv2d_fwd")
+        math = opts.get("math", _MATH[0])
+        if math == 0:
+            _lib.check(lib.fov_conv2d_fwd(C.byref(cfg), ptr(x), ptr(kernel), ptr(bias), ptr(y), _stream()),
+                       "fov_conv2d_fwd")
+        else:
+            ws = _ws(lib.fov_conv_tc_ws_bytes(C.byref(cfg), math, 0), x.device)
+            _lib.check(lib.fov_conv2d_fwd_tc(C.byref(cfg), ptr(x), ptr(kernel), ptr(bias), ptr(y), ptr(ws),
+                                             math, _stream()), "fov_conv2d_fwd_tc")
         if opts.get("training", False):
+            ctx.math = math
             ctx.cfg, ctx.sinks, ctx.act = cfg, sinks, act
             ctx.need_dx = ctx.needs_input_grad[2]
             ctx.save_for_backward(x, kernel, y)
@@ -204,15 +229,25 @@ class Conv2DFn(torch.autograd.Function):
             dpre = dy
         cfg.act = 0
         gw, gb = ctx.sinks
-        _lib.check(lib.fov_conv2d_bwd_weight(C.byref(cfg), ptr(x), ptr(dpre), ptr(gw), ptr(gb), st),
-                   "fov_conv2d_bwd_weight")
+        math = ctx.math
+        if math == 0:
+            _lib.check(lib.fov_conv2d_bwd_weight(C.byref(cfg), ptr(x), ptr(dpre), ptr(gw), ptr(gb), st),
+                       "fov_conv2d_bwd_weight")
+        else:
+            _lib.check(lib.fov_conv2d_bwd_weight_tc(C.byref(cfg), ptr(x), ptr(dpre), ptr(gw), ptr(gb), math, st),
+                       "fov_conv2d_bwd_weight_tc")
         dx = None
         if ctx.need_dx:
             dx = torch.empty_like(x)
-            ws = torch.empty(kernel.numel(), device=x.device)
             cfg.beta = 0.0
-            _lib.check(lib.fov_conv2d_bwd_data(C.byref(cfg), ptr(dpre), ptr(kernel), ptr(dx), ptr(ws), st),
-                       "fov_conv2d_bwd_data")
+            if math == 0:
+                ws = torch.empty(kernel.numel(), device=x.device)
+                _lib.check(lib.fov_conv2d_bwd_data(C.byref(cfg), ptr(dpre), ptr(kernel), ptr(dx), ptr(ws), st),
+                           "fov_conv2d_bwd_data")
+            else:
+                ws = _ws(lib.fov_conv_tc_ws_bytes(C.byref(cfg), math, 1), x.device)
+                _lib.check(lib.fov_conv2d_bwd_data_tc(C.byref(cfg), ptr(dpre), ptr(kernel), ptr(dx), ptr(ws),
+                                                      math, st), "fov_conv2d_bwd_data_tc")
         return None, None, dx, None, None
 
 
@@ -266,6 +301,7 @@ class ConvLSTMStackFn(torch.autograd.Function):
         dil = opts.get("dilation", (1, 1))
         rec = REC[opts.get("rec_act", "hard_sigmoid")]
         training = bool(opts.get("training", False))
+        math = opts.get("math", _MATH[0])
         cat = torch.empty(B, T, H, W, Fsum, device=dev)
         HW = H * W
         st = _stream()
@@ -278,15 +314,18 @@ class ConvLSTMStackFn(torch.autograd.Function):
             kh, kw = K.shape[0], K.shape[1]
             F = Fs[l]
             cfg = _lib.ConvLstmCfg(B, T, H, W, cin, F, kh, kw, dil[0], dil[1], rec,
-                                   cur_b, cur_t, cur_pix, T * HW * Fsum, HW * Fsum, Fsum, int(training))
-            gates = torch.empty(B, T, H, W, 4 * F, device=dev)
+                                   cur_b, cur_t, cur_pix, T * HW * Fsum, HW * Fsum, Fsum, int(training), math)
+            # saved gates exist only for BPTT; the fused tensor-core step never materialises them otherwise
+            fws_bytes = lib.fov_convlstm_fwd_ws_bytes(C.byref(cfg))     # > 0: the fused tensor-core step runs
+            gates = torch.empty((B, T, H, W, 4 * F) if (training or fws_bytes == 0) else (1,), device=dev)
+            fws = _ws(fws_bytes, dev) if fws_bytes else None
             cseq = torch.empty(B, T, H, W, F, device=dev)
             hT = torch.empty(B, H, W, F, device=dev)
             cT = torch.empty(B, H, W, F, device=dev)
             h0, c0 = states[l]
             hptr = cat.data_ptr() + 4 * off
             io = _lib.ConvLstmIO(cur_ptr, ptr(K), ptr(R), ptr(b), ptr(h0), ptr(c0), None, hptr,
-                                 ptr(gates), ptr(cseq), ptr(hT), ptr(cT), None)
+                                 ptr(gates), ptr(cseq), ptr(hT), ptr(cT), ptr(fws))
             _lib.check(lib.fov_convlstm_fwd(C.byref(cfg), C.byref(io), st), "fov_convlstm_fwd")
             outs += [hT, cT]
             saved.append((gates, cseq))

@@ -115,6 +115,15 @@ static void test_conv(const char* name, fov_conv_cfg c, bool time_it) {
   float* dxref = dev_copy(dx0, nx);
   float* wsf = dev_zero(nw);
   FK(fov_conv2d_bwd_data(&c, dy, w, dxref, wsf, nullptr));
+  // weight / bias gradient reference (accumulating into random initial values)
+  float* gw0 = dev_rand(nw, 1.0f);
+  float* gb0 = dev_rand(c.Cout, 1.0f);
+  float* gwref = dev_copy(gw0, nw);
+  float* gbref = dev_copy(gb0, c.Cout);
+  {
+    fov_conv_cfg cl = c; cl.act = FOV_ACT_LINEAR;
+    FK(fov_conv2d_bwd_weight(&cl, x, dy, gwref, gbref, nullptr));
+  }
   CK(cudaDeviceSynchronize());
   // fp64 truth on a sample of outputs (host): true error of the fp32 kernel and of each tensor-core mode
   const int NSAMP = 512;
@@ -170,6 +179,23 @@ static void test_conv(const char* name, fov_conv_cfg c, bool time_it) {
     FK(fov_conv2d_bwd_data_tc(&c, dy, w, dx, ws2, math, nullptr));
     CK(cudaDeviceSynchronize());
     report("bwd_data", math, compare(dx, dxref, nx), kTol[math]);
+    {
+      float* gw = dev_copy(gw0, nw);
+      float* gb = dev_copy(gb0, c.Cout);
+      FK(fov_conv2d_bwd_weight_tc(&c, x, dy, gw, gb, math, nullptr));
+      CK(cudaDeviceSynchronize());
+      report("bwd_weight", math, compare(gw, gwref, nw), kTol[math] * 2);
+      report("bwd_bias", math, compare(gb, gbref, c.Cout), 1e-4);
+      if (time_it) {
+        for (int i = 0; i < 2; ++i) FK(fov_conv2d_bwd_weight_tc(&c, x, dy, gw, gb, math, nullptr));
+        tm.start();
+        for (int i = 0; i < 5; ++i) FK(fov_conv2d_bwd_weight_tc(&c, x, dy, gw, gb, math, nullptr));
+        const float ms = tm.stop_ms() / 5;
+        const double fl = 2.0 * c.N * c.H * c.W * (double)c.Cout * c.kh * c.kw * c.Cin;
+        printf("  time wgrad_tc math=%d: %.3f ms  (%.1f TFLOP/s algorithmic)\n", math, ms, fl / ms * 1e-9);
+      }
+      cudaFree(gw); cudaFree(gb);
+    }
     if (time_it) {
       fov_conv_cfg ct = c; ct.beta = 0.f;
       for (int i = 0; i < 3; ++i) FK(fov_conv2d_fwd_tc(&ct, x, w, b, y, ws, math, nullptr));
@@ -189,7 +215,11 @@ static void test_conv(const char* name, fov_conv_cfg c, bool time_it) {
     const float ms = tm.stop_ms() / 5;
     const double fl = 2.0 * c.N * c.H * c.W * (double)c.Cout * c.kh * c.kw * c.Cin;
     printf("  time fwd fp32 SIMT : %.3f ms  (%.1f TFLOP/s)\n", ms, fl / ms * 1e-9);
+    tm.start();
+    for (int i = 0; i < 3; ++i) FK(fov_conv2d_bwd_weight(&ct, x, dy, gwref, gbref, nullptr));
+    printf("  time wgrad fp32 SIMT : %.3f ms\n", tm.stop_ms() / 3);
   }
+  cudaFree(gw0); cudaFree(gb0); cudaFree(gwref); cudaFree(gbref);
   cudaFree(x); cudaFree(w); cudaFree(b); cudaFree(y0); cudaFree(yref); cudaFree(dy); cudaFree(dx0); cudaFree(dxref);
   cudaFree(wsf);
 }
