@@ -67,28 +67,12 @@ struct DevParams {
 
 // shared-memory bookkeeping placed after the data region (pipeline stages / epilogue staging)
 struct Book {
-  long long off_x[2][BLOCK_M];     // gather offsets per row per segment (image part only)
+  const float* rp[2][BLOCK_M];     // per row, per segment: address of the row's own pixel (channel 0)
   long long off_o[5][BLOCK_M];     // epilogue element offsets per row (image + pixel), see O_*
-  int py[BLOCK_M], px[BLOCK_M];    // pixel coordinates; py < 0 marks a row past M
+  int pyx[BLOCK_M];                // (y << 16) | x of the row's pixel; y = 0x4000 marks a row past M
   uint64_t full[kMaxStages], empty[kMaxStages], tmem_full;
   uint32_t tmem_ptr;
 };
-
-__device__ __forceinline__ float4 gather4(const float* __restrict__ p, int nvalid, int vec) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (vec == 4) {
-    v = __ldg(reinterpret_cast<const float4*>(p));
-  } else if (vec == 2) {
-    if (nvalid >= 2) { const float2 a = __ldg(reinterpret_cast<const float2*>(p)); v.x = a.x; v.y = a.y; }
-    if (nvalid >= 4) { const float2 b = __ldg(reinterpret_cast<const float2*>(p + 2)); v.z = b.x; v.w = b.y; }
-  } else {
-    if (nvalid > 0) v.x = __ldg(p);
-    if (nvalid > 1) v.y = __ldg(p + 1);
-    if (nvalid > 2) v.z = __ldg(p + 2);
-    if (nvalid > 3) v.w = __ldg(p + 3);
-  }
-  return v;
-}
 
 // element offset of image n in an (outer, inner) strided tensor
 __device__ __forceinline__ long long img_off(long long n, int T_inner, long long outer, long long inner) {
@@ -128,10 +112,12 @@ __global__ void __launch_bounds__(kThreads) tc_conv_kernel(const DevParams p) {
     if (m < p.M) {
       const long long n = m / p.HW;
       const int pix = (int)(m - n * p.HW);
-      bk->py[tid] = pix / p.W;
-      bk->px[tid] = pix - (pix / p.W) * p.W;
-      bk->off_x[0][tid] = img_off(n, p.T_inner, p.x_outer[0], p.x_inner[0]);
-      bk->off_x[1][tid] = p.nseg > 1 ? img_off(n, p.T_inner, p.x_outer[1], p.x_inner[1]) : 0;
+      bk->pyx[tid] = ((pix / p.W) << 16) | (pix - (pix / p.W) * p.W);
+      bk->rp[0][tid] = p.seg[0].x + img_off(n, p.T_inner, p.x_outer[0], p.x_inner[0]) +
+                       (long long)pix * p.seg[0].pix_stride;
+      bk->rp[1][tid] = p.nseg > 1 ? p.seg[1].x + img_off(n, p.T_inner, p.x_outer[1], p.x_inner[1]) +
+                                        (long long)pix * p.seg[1].pix_stride
+                                  : nullptr;
       if (EPI == TC_EPI_CONV) {
         bk->off_o[O_OUT][tid] = img_off(n, p.T_inner, p.y_outer, p.y_inner) + (long long)pix * p.y_pix_stride;
       } else {
@@ -142,8 +128,8 @@ __global__ void __launch_bounds__(kThreads) tc_conv_kernel(const DevParams p) {
         bk->off_o[O_DENSE][tid] = (n * p.HW + pix) * p.F;
       }
     } else {
-      bk->py[tid] = -(1 << 28); bk->px[tid] = 0;
-      bk->off_x[0][tid] = 0; bk->off_x[1][tid] = 0;
+      bk->pyx[tid] = 0x4000 << 16;
+      bk->rp[0][tid] = nullptr; bk->rp[1][tid] = nullptr;
     }
   }
   if (warp == 5 && lane == 0) {
@@ -169,7 +155,7 @@ __global__ void __launch_bounds__(kThreads) tc_conv_kernel(const DevParams p) {
     // the next half k-block are always in flight while the current half is converted and stored.
     const int q = tid & 15;          // float4 slot inside the 64-wide k slice
     const int rsub = tid >> 4;       // 0..7
-    struct KDec { const float* xb; int si, dy, dx, nvalid, pix_stride, vec; };
+    struct KDec { int si, dy, dx, nvalid, delta, vec; };
     auto decode = [&](int kb) {
       KDec d;
       const int k = kb * BLOCK_K + q * 4;
@@ -182,35 +168,32 @@ __global__ void __launch_bounds__(kThreads) tc_conv_kernel(const DevParams p) {
       d.nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
       const int ty = tap / sg.kw, tx = tap - ty * sg.kw;
       d.dy = ty * sg.dil_h - sg.pad_h; d.dx = tx * sg.dil_w - sg.pad_w;
-      d.xb = sg.x + ci; d.pix_stride = sg.pix_stride; d.vec = sg.vec;
+      d.delta = (d.dy * p.W + d.dx) * sg.pix_stride + ci;   // tap + channel offset from the row's own pixel
+      d.vec = sg.vec;
       return d;
     };
     auto issue = [&](const KDec& d, int half, float4 (&v)[8]) {
-      const long long* offx = bk->off_x[d.si];
+      const float* const* rp = bk->rp[d.si];
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const int row = (half * 8 + jj) * 8 + rsub;
-        const int yy = bk->py[row] + d.dy, xx = bk->px[row] + d.dx;
+        const int pyx = bk->pyx[row];
+        const unsigned yy = (unsigned)((pyx >> 16) + d.dy), xx = (unsigned)((pyx & 0xffff) + d.dx);
         v[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (d.nvalid > 0 && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-          v[jj] = gather4(d.xb + offx[row] + (long long)(yy * p.W + xx) * d.pix_stride, d.nvalid, d.vec);
+        if (d.nvalid > 0 && yy < (unsigned)p.H && xx < (unsigned)p.W)
+          v[jj] = ldg_vec4(rp[row] + d.delta, d.nvalid, d.vec);
       }
     };
+    // row = 8*(...) + rsub, so the swizzle phase (row & 7) is the thread constant rsub
+    const uint32_t st_off = (uint32_t)rsub * 128u + ((uint32_t)((q >> 1) ^ rsub) << 4) + (uint32_t)(q & 1) * 8u;
     auto store = [&](uint8_t* a_stage, int half, const float4 (&v)[8]) {
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
-        const int row = (half * 8 + jj) * 8 + rsub;
-        const uint32_t off = (uint32_t)row * 128u + ((uint32_t)((q >> 1) ^ (row & 7)) << 4) + (uint32_t)(q & 1) * 8u;
-        float t0[NS], t1[NS], t2[NS], t3[NS];
-        bf16_split<NS>(v[jj].x, t0); bf16_split<NS>(v[jj].y, t1);
-        bf16_split<NS>(v[jj].z, t2); bf16_split<NS>(v[jj].w, t3);
+        uint2 pk[NS];
+        split4<NS>(v[jj], pk);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          uint2 pk;
-          pk.x = pack_bf16x2(t0[s], t1[s]);
-          pk.y = pack_bf16x2(t2[s], t3[s]);
-          *reinterpret_cast<uint2*>(a_stage + s * A_TILE_BYTES + off) = pk;
-        }
+        for (int s = 0; s < NS; ++s)
+          *reinterpret_cast<uint2*>(a_stage + s * A_TILE_BYTES + (half * 8 + jj) * 1024 + st_off) = pk[s];
       }
     };
     float4 va[8], vb[8];
@@ -306,7 +289,7 @@ __global__ void __launch_bounds__(kThreads) tc_conv_kernel(const DevParams p) {
 #pragma unroll 2
           for (int it = 0; it < 32; it += 4) {
             const int rr = it + (lane >> 3), row = r0 + rr;
-            if (col_ok && bk->py[row] >= 0) {
+            if (col_ok && (bk->pyx[row] >> 16) != 0x4000) {
               float* dst = p.y + bk->off_o[O_OUT][row] + col;
               float4 a = *reinterpret_cast<const float4*>(&stg[rr * CONV_RS + c4]);
               a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
@@ -324,7 +307,7 @@ __global__ void __launch_bounds__(kThreads) tc_conv_kernel(const DevParams p) {
           const float bv = (col_ok && p.bias) ? __ldg(&p.bias[col]) : 0.0f;
           for (int rr = 0; rr < 32; ++rr) {
             const int row = r0 + rr;
-            if (bk->py[row] < 0) break;
+            if ((bk->pyx[row] >> 16) == 0x4000) break;
             if (col_ok) {
               float* dst = p.y + bk->off_o[O_OUT][row] + col;
               float val = stg[rr * CONV_RS + lane] + bv;
@@ -350,7 +333,7 @@ __global__ void __launch_bounds__(kThreads) tc_conv_kernel(const DevParams p) {
         if (!dst) return;
         for (int it = 0; it < 32; it += rpi) {
           const int rr = it + srow, row = r0 + rr;
-          if (bk->py[row] >= 0) {
+          if ((bk->pyx[row] >> 16) != 0x4000) {
             const float4 v = *reinterpret_cast<const float4*>(&stg[rr * RS + stage_col + sc4]);
             *reinterpret_cast<float4*>(dst + bk->off_o[oidx][row] + dst_col + sc4) = v;
             if (dense) *reinterpret_cast<float4*>(dense + bk->off_o[O_DENSE][row] + dst_col + sc4) = v;
@@ -362,7 +345,7 @@ __global__ void __launch_bounds__(kThreads) tc_conv_kernel(const DevParams p) {
           for (int it = 0; it < 32; it += rpi) {
             const int rr = it + srow, row = r0 + rr;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bk->py[row] >= 0)
+            if ((bk->pyx[row] >> 16) != 0x4000)
               v = __ldg(reinterpret_cast<const float4*>(p.c_prev + bk->off_o[O_CPREV][row] + cpass + sc4));
             *reinterpret_cast<float4*>(&stg[rr * RS + 4 * CW + sc4]) = v;
           }
@@ -522,18 +505,18 @@ int make_plan(const TcConv& c, Plan* pl) {
   } else {
     staging = 4 * 32 * CONV_RS * 4;
   }
-  // stage count: as many CTAs per SM as the shared memory allows while keeping >= 2 stages when the
-  // K loop is long (the gather of stage s+1 overlaps the MMAs of stage s); short K loops rely on
-  // several co-resident CTAs instead.
+  // Stage count.  The gather (not the MMA) bounds these kernels, so latency is hidden by co-resident
+  // CTAs: aim at 4 CTAs per SM for narrow tiles, 3 up to N=128, 2 beyond (TMEM: CTAs x columns <= 512),
+  // and give each CTA as many stages as its share of the shared memory holds.
   const int kUsable = 227 * 1024, book = (int)sizeof(Book) + 1024 + 1024;
-  int st;
-  if (pl->KB <= 4) {
-    st = (kUsable / 3 - book) / pl->stage_bytes;
-    if (st < 1) st = (kUsable / 2 - book) / pl->stage_bytes;
-  } else {
-    st = (kUsable / 2 - book) / pl->stage_bytes;
-    if (st < 2) st = (kUsable - book) / pl->stage_bytes;
+  int target = pl->BLOCK_N <= 64 ? 4 : (pl->BLOCK_N <= 128 ? 3 : 2);
+  int st = 0;
+  for (; target >= 1 && st < 1; --target) {
+    int share = kUsable / target - book;
+    if (share < staging) continue;
+    st = share / pl->stage_bytes;
   }
+  if (st > 2 && pl->BLOCK_N <= 64) st = 2;
   if (st > kMaxStages) st = kMaxStages;
   if (st > pl->KB) st = pl->KB;
   if (st < 1) st = 1;

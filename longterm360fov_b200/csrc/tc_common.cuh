@@ -156,5 +156,35 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// Split four floats into NS bf16 terms, packed as the 8 bytes each term's tile stores:
+// one cvt.rn.bf16x2 per pair and term, residuals formed by bit-expanding the packed bf16 back.
+template <int NS>
+__device__ __forceinline__ void split4(float4 v, uint2 (&out)[NS]) {
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const uint32_t p01 = pack_bf16x2(v.x, v.y), p23 = pack_bf16x2(v.z, v.w);
+    out[s] = make_uint2(p01, p23);
+    if (s + 1 < NS) {
+      v.x -= __uint_as_float(p01 << 16); v.y -= __uint_as_float(p01 & 0xffff0000u);
+      v.z -= __uint_as_float(p23 << 16); v.w -= __uint_as_float(p23 & 0xffff0000u);
+    }
+  }
+}
+// 4-element gather with the widest load the tensor's alignment allows (vec = 4, 2 or 1 floats)
+__device__ __forceinline__ float4 ldg_vec4(const float* __restrict__ p, int nvalid, int vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec == 4) {
+    v = __ldg(reinterpret_cast<const float4*>(p));
+  } else if (vec == 2) {
+    if (nvalid >= 2) { const float2 a = __ldg(reinterpret_cast<const float2*>(p)); v.x = a.x; v.y = a.y; }
+    if (nvalid >= 4) { const float2 b = __ldg(reinterpret_cast<const float2*>(p + 2)); v.z = b.x; v.w = b.y; }
+  } else {
+    if (nvalid > 0) v.x = __ldg(p);
+    if (nvalid > 1) v.y = __ldg(p + 1);
+    if (nvalid > 2) v.z = __ldg(p + 2);
+    if (nvalid > 3) v.w = __ldg(p + 3);
+  }
+  return v;
+}
 
 }  // namespace tc

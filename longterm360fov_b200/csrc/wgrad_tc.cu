@@ -40,8 +40,9 @@ struct WgParams {
 };
 
 struct RowTab {
-  long long offx[WG_PIX], offdy[WG_PIX];
-  int py[WG_PIX], px[WG_PIX];
+  const float* xp[WG_PIX];    // address of the row's own pixel in x (channel 0)
+  const float* dyp[WG_PIX];   // address of the row's pixel in dy (channel 0)
+  int pyx[WG_PIX];            // (y << 16) | x; y = 0x4000 marks a row past the end
 };
 struct Book {
   RowTab tab[kStagesMax];
@@ -49,35 +50,6 @@ struct Book {
   uint64_t full[kStagesMax], empty[kStagesMax], tabrdy[kStagesMax], tmem_full;
   uint32_t tmem_ptr;
 };
-
-__device__ __forceinline__ float4 ld4(const float* __restrict__ p, int nvalid, int vec) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (vec == 4) {
-    v = __ldg(reinterpret_cast<const float4*>(p));
-  } else if (vec == 2) {
-    if (nvalid >= 2) { const float2 a = __ldg(reinterpret_cast<const float2*>(p)); v.x = a.x; v.y = a.y; }
-    if (nvalid >= 4) { const float2 b = __ldg(reinterpret_cast<const float2*>(p + 2)); v.z = b.x; v.w = b.y; }
-  } else {
-    if (nvalid > 0) v.x = __ldg(p);
-    if (nvalid > 1) v.y = __ldg(p + 1);
-    if (nvalid > 2) v.z = __ldg(p + 2);
-    if (nvalid > 3) v.w = __ldg(p + 3);
-  }
-  return v;
-}
-
-template <int NS>
-__device__ __forceinline__ void store_split(uint8_t* tile0, int term_bytes, uint32_t off, const float4& v) {
-  float t0[NS], t1[NS], t2[NS], t3[NS];
-  bf16_split<NS>(v.x, t0); bf16_split<NS>(v.y, t1); bf16_split<NS>(v.z, t2); bf16_split<NS>(v.w, t3);
-#pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    uint2 pk;
-    pk.x = pack_bf16x2(t0[s], t1[s]);
-    pk.y = pack_bf16x2(t2[s], t3[s]);
-    *reinterpret_cast<uint2*>(tile0 + s * term_bytes + off) = pk;
-  }
-}
 
 template <int NS>
 __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
@@ -134,32 +106,33 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
     a_nvalid = a_nvalid < 0 ? 0 : (a_nvalid > 4 ? 4 : a_nvalid);
     const int ty = tap / p.kw, tx = tap - ty * p.kw;
     const int tdy = ty * p.dil_h - p.pad_h, tdx = tx * p.dil_w - p.pad_w;
-    const float* xb = p.x + ci;
-    const uint32_t a_col = (uint32_t)(q >> 4) * WG_GRP + (uint32_t)(q & 1) * 8u;
-    const int a_chunk = (q & 15) >> 1;
+    const int a_delta = (tdy * p.W + tdx) * p.x_pix_stride + ci;
+    // rows are 8*j + rsub (A') and b_row0 + j*b_rstep with b_rstep % 8 == 0 (B'): constant swizzle phase
+    const uint32_t a_off = (uint32_t)(q >> 4) * WG_GRP + (uint32_t)(q & 1) * 8u + (uint32_t)rsub * 128u +
+                           ((uint32_t)(((q & 15) >> 1) ^ rsub) << 4);
     const int bcol = n0 + b_c4 * 4;
     int b_nvalid = p.Cout - bcol;
     b_nvalid = b_nvalid < 0 ? 0 : (b_nvalid > 4 ? 4 : b_nvalid);
-    const float* dyb = p.dy + bcol;
-    const uint32_t b_col = (uint32_t)(b_c4 >> 4) * WG_GRP + (uint32_t)(b_c4 & 1) * 8u;
-    const int b_chunk = (b_c4 & 15) >> 1;
+    const uint32_t b_off = (uint32_t)(b_c4 >> 4) * WG_GRP + (uint32_t)(b_c4 & 1) * 8u + (uint32_t)b_row0 * 128u +
+                           ((uint32_t)(((b_c4 & 15) >> 1) ^ (b_row0 & 7)) << 4);
 
     auto issue = [&](int stage, float4 (&va)[8], float4 (&vb)[8]) {
       const RowTab& t = bk->tab[stage];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int r = j * 8 + rsub;
-        const int yy = t.py[r] + tdy, xx = t.px[r] + tdx;
+        const int pyx = t.pyx[r];
+        const unsigned yy = (unsigned)((pyx >> 16) + tdy), xx = (unsigned)((pyx & 0xffff) + tdx);
         va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a_nvalid > 0 && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-          va[j] = ld4(xb + t.offx[r] + (long long)(yy * p.W + xx) * p.x_pix_stride, a_nvalid, p.x_vec);
+        if (a_nvalid > 0 && yy < (unsigned)p.H && xx < (unsigned)p.W)
+          va[j] = ldg_vec4(t.xp[r] + a_delta, a_nvalid, p.x_vec);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         vb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < nb) {
           const int r = b_row0 + j * b_rstep;
-          if (b_nvalid > 0 && t.py[r] >= 0) vb[j] = ld4(dyb + t.offdy[r], b_nvalid, p.dy_vec);
+          if (b_nvalid > 0 && (t.pyx[r] >> 16) != 0x4000) vb[j] = ldg_vec4(t.dyp[r] + bcol, b_nvalid, p.dy_vec);
         }
       }
     };
@@ -168,15 +141,19 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
       uint8_t* b_tile = a_tile + NS * A_TERM;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int r = j * 8 + rsub;
-        store_split<NS>(a_tile, A_TERM, a_col + (uint32_t)r * 128u + ((uint32_t)(a_chunk ^ (r & 7)) << 4), va[j]);
+        uint2 pk[NS];
+        split4<NS>(va[j], pk);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(a_tile + s * A_TERM + j * 1024 + a_off) = pk[s];
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (j < nb) {
-          const int r = b_row0 + j * b_rstep;
-          store_split<NS>(b_tile, p.b_term_bytes, b_col + (uint32_t)r * 128u + ((uint32_t)(b_chunk ^ (r & 7)) << 4),
-                          vb[j]);
+          uint2 pk[NS];
+          split4<NS>(vb[j], pk);
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+            *reinterpret_cast<uint2*>(b_tile + s * p.b_term_bytes + j * b_rstep * 128 + b_off) = pk[s];
           bsum.x += vb[j].x; bsum.y += vb[j].y; bsum.z += vb[j].z; bsum.w += vb[j].w;
         }
       }
@@ -216,12 +193,11 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
         if (m < p.M) {
           const int n = m / p.HW, pix = m - n * p.HW;
           const int no = n / p.T_inner, ni = n - no * p.T_inner;
-          t.py[r] = pix / p.W;
-          t.px[r] = pix - (pix / p.W) * p.W;
-          t.offx[r] = (long long)no * p.x_outer + (long long)ni * p.x_inner;
-          t.offdy[r] = (long long)no * p.dy_outer + (long long)ni * p.dy_inner + (long long)pix * p.dy_pix_stride;
+          t.pyx[r] = ((pix / p.W) << 16) | (pix - (pix / p.W) * p.W);
+          t.xp[r] = p.x + (long long)no * p.x_outer + (long long)ni * p.x_inner + (long long)pix * p.x_pix_stride;
+          t.dyp[r] = p.dy + (long long)no * p.dy_outer + (long long)ni * p.dy_inner + (long long)pix * p.dy_pix_stride;
         } else {
-          t.py[r] = -(1 << 28); t.px[r] = 0; t.offx[r] = 0; t.offdy[r] = 0;
+          t.pyx[r] = 0x4000 << 16; t.xp[r] = nullptr; t.dyp[r] = nullptr;
         }
       }
       __syncwarp();

@@ -79,7 +79,7 @@ static void report(const char* what, int math, Err e, double tol_rel) {
   printf("  %-34s math=%d max_abs=%.3e max_ref=%.3e rel=%.3e %s\n", what, math, e.max_abs, e.max_ref, rel,
          ok ? "ok" : "FAIL");
 }
-static const double kTol[4] = {0, 2e-2, 2e-4, 1e-4};
+static const double kTol[4] = {0, 2e-2, 2e-4, 2e-4};
 
 struct Timer {
   cudaEvent_t a, b;
@@ -312,9 +312,47 @@ static void test_convlstm(const char* name, int B, int T, int H, int W, int Cin,
   if (h0) { cudaFree(h0); cudaFree(c0); }
 }
 
+// a handful of bench-sized launches (math = bf16x2 only) for `ncu --set full`
+static void profile_mode() {
+  const int B = 4096, math = 2;
+  {   // conv: ConvLSTM L0 backward-data shape (dZ_t 128 ch -> dh 32 ch, 1x5) and the forward recurrent conv
+    fov_conv_cfg c = mkcfg(B, 1, 33, 32, 128, 1, 5, 1, 1, FOV_ACT_LINEAR, 0.f);
+    const size_t nx = (size_t)B * 33 * 32, ny = (size_t)B * 33 * 128, nw = 5 * 32 * 128;
+    float *x = dev_rand(nx, 1.f), *w = dev_rand(nw, 0.1f), *b = dev_rand(128, 0.1f), *y = dev_zero(ny), *dx = dev_zero(nx);
+    float *gw = dev_zero(nw), *gb = dev_zero(128);
+    void *ws, *ws2;
+    CK(cudaMalloc(&ws, fov_conv_tc_ws_bytes(&c, math, 0) + 256));
+    CK(cudaMalloc(&ws2, fov_conv_tc_ws_bytes(&c, math, 1) + 256));
+    for (int i = 0; i < 2; ++i) {
+      FK(fov_conv2d_fwd_tc(&c, x, w, b, y, ws, math, nullptr));
+      FK(fov_conv2d_bwd_data_tc(&c, y, w, dx, ws2, math, nullptr));
+      FK(fov_conv2d_bwd_weight_tc(&c, x, y, gw, gb, math, nullptr));
+    }
+    CK(cudaDeviceSynchronize());
+  }
+  {   // fused ConvLSTM step, layer 0 of config 2 (training: saves the activated gates)
+    const int T = 2, Cin = 6, F = 32;
+    const size_t HW = 33, nx = (size_t)B * T * HW * Cin, nh = (size_t)B * T * HW * F;
+    float *x = dev_rand(nx, 1.f), *K = dev_rand(5 * Cin * 4 * F, 0.2f), *R = dev_rand(5 * F * 4 * F, 0.1f), *bias = dev_rand(4 * F, 0.1f);
+    fov_convlstm_cfg c{};
+    c.B = B; c.T = T; c.H = 1; c.W = 33; c.Cin = Cin; c.F = F; c.kh = 1; c.kw = 5; c.dil_h = 1; c.dil_w = 1;
+    c.x_b_stride = (long long)T * HW * Cin; c.x_t_stride = (long long)HW * Cin; c.x_pix_stride = Cin;
+    c.h_b_stride = (long long)T * HW * F; c.h_t_stride = (long long)HW * F; c.h_pix_stride = F;
+    c.training = 1; c.math = math;
+    fov_convlstm_io io{};
+    io.x = x; io.kernel = K; io.recurrent = R; io.bias = bias;
+    io.hseq = dev_zero(nh); io.gates = dev_zero(nh * 4); io.cseq = dev_zero(nh);
+    void* wsf; CK(cudaMalloc(&wsf, fov_convlstm_fwd_ws_bytes(&c) + 256)); io.ws = (float*)wsf;
+    for (int i = 0; i < 2; ++i) FK(fov_convlstm_fwd(&c, &io, nullptr));
+    CK(cudaDeviceSynchronize());
+  }
+  printf("profile mode done\n");
+}
+
 int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   if (!fov_device_is_sm100()) { printf("not an sm_100 device\n"); return 1; }
+  if (argc > 1 && !strcmp(argv[1], "profile")) { profile_mode(); return 0; }
   // --- convolution family ---
   test_conv("dense 64->16", mkcfg(300, 1, 1, 64, 16, 1, 1, 1, 1, FOV_ACT_LINEAR, 0.f), false);
   test_conv("m3 L0 rec", mkcfg(64, 1, 33, 32, 128, 1, 5, 1, 1, FOV_ACT_LINEAR, 1.f), false);
