@@ -75,9 +75,9 @@ struct Book {
 };
 
 // element offset of image n in an (outer, inner) strided tensor
-__device__ __forceinline__ long long img_off(long long n, int T_inner, long long outer, long long inner) {
-  const long long no = n / T_inner;
-  return no * outer + (n - no * T_inner) * inner;
+__device__ __forceinline__ long long img_off(int n, int T_inner, long long outer, long long inner) {
+  const int no = n / T_inner;
+  return (long long)no * outer + (long long)(n - no * T_inner) * inner;
 }
 
 // exp-based activations for the fused epilogue (abs error ~1e-7, far inside the bf16-split budget)
@@ -91,7 +91,7 @@ __device__ __forceinline__ float fast_rec(int rec, float x) {
 }
 
 template <int NS, int EPI>
-__global__ void __launch_bounds__(kThreads) tc_conv_kernel(const DevParams p) {
+__global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const DevParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(kThreads) tc_conv_kernel(const DevParams p) {
   if (tid < BLOCK_M) {
     const long long m = m0 + tid;
     if (m < p.M) {
-      const long long n = m / p.HW;
-      const int pix = (int)(m - n * p.HW);
+      const int n = (int)((unsigned)m / (unsigned)p.HW);     // M < 2^31 (checked on the host)
+      const int pix = (int)m - n * p.HW;
       bk->pyx[tid] = ((pix / p.W) << 16) | (pix - (pix / p.W) * p.W);
       bk->rp[0][tid] = p.seg[0].x + img_off(n, p.T_inner, p.x_outer[0], p.x_inner[0]) +
                        (long long)pix * p.seg[0].pix_stride;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kThreads) tc_conv_kernel(const DevParams p) {
         bk->off_o[O_H][tid] = img_off(n, p.T_inner, p.h_outer, p.h_inner) + (long long)pix * p.h_pix_stride;
         bk->off_o[O_GATES][tid] = img_off(n, p.T_inner, p.g_outer, p.g_inner) + (long long)pix * 4 * p.F;
         bk->off_o[O_CPREV][tid] = img_off(n, p.T_inner, p.cp_outer, p.cp_inner) + (long long)pix * p.F;
-        bk->off_o[O_DENSE][tid] = (n * p.HW + pix) * p.F;
+        bk->off_o[O_DENSE][tid] = ((long long)n * p.HW + pix) * p.F;
       }
     } else {
       bk->pyx[tid] = 0x4000 << 16;
@@ -471,6 +471,8 @@ int make_plan(const TcConv& c, Plan* pl) {
   FOV_CHECK_ARG(c.nseg == 1 || c.nseg == 2, "nseg must be 1 or 2");
   FOV_CHECK_ARG(c.math >= 1 && c.math <= 3, "math must be 1..3 bf16 terms");
   FOV_CHECK_ARG(c.N_img > 0 && c.H > 0 && c.W > 0 && c.Cout > 0 && c.T_inner > 0, "bad shape");
+  FOV_CHECK_ARG((long long)c.N_img * c.H * c.W < (1LL << 31) - BLOCK_M && c.H < 0x4000 && c.W < 0x10000,
+                "too many pixels for 32-bit indexing");
   int k = 0;
   for (int s = 0; s < c.nseg; ++s) {
     const TcSeg& g = c.seg[s];

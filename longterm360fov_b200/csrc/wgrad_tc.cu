@@ -181,7 +181,21 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
       }
     }
   } else if (warp == 8) {
-    // ---------------- row-table builder: pixel -> (image offsets, y, x) for each stage ----------------
+    // ---------------- row-table builder: pixel -> (addresses, y, x) for each stage ----------------
+    // lane owns rows lane and lane+32; their pixel advances by 64 per block, tracked with carries
+    // (one division set at the start, none in the loop).
+    const int dq = WG_PIX / p.HW, dr = WG_PIX - dq * p.HW;       // 64 pixels = dq images + dr pixels
+    const int dry = dr / p.W, drx = dr - dry * p.W;
+    const int dno = dq / p.T_inner, dni = dq - dno * p.T_inner;
+    int no[2], ni[2], py[2], px[2];
+    bool live[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = blk0 * WG_PIX + lane + h * 32;               // may exceed M: rows past the end stay dead
+      const int n = m / p.HW, pix = m - n * p.HW;
+      no[h] = n / p.T_inner; ni[h] = n - no[h] * p.T_inner;
+      py[h] = pix / p.W; px[h] = pix - py[h] * p.W;
+    }
     for (int i = 0; i < nblk; ++i) {
       const int stage = i % S;
       mbar_wait(smem_u32(&bk->empty[stage]), ((uint32_t)(i / S) & 1u) ^ 1u);
@@ -189,16 +203,24 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int r = lane + h * 32;
-        const int m = (blk0 + i) * WG_PIX + r;
-        if (m < p.M) {
-          const int n = m / p.HW, pix = m - n * p.HW;
-          const int no = n / p.T_inner, ni = n - no * p.T_inner;
-          t.pyx[r] = ((pix / p.W) << 16) | (pix - (pix / p.W) * p.W);
-          t.xp[r] = p.x + (long long)no * p.x_outer + (long long)ni * p.x_inner + (long long)pix * p.x_pix_stride;
-          t.dyp[r] = p.dy + (long long)no * p.dy_outer + (long long)ni * p.dy_inner + (long long)pix * p.dy_pix_stride;
+        live[h] = (blk0 + i) * WG_PIX + r < p.M;
+        if (live[h]) {
+          const int pix = py[h] * p.W + px[h];
+          t.pyx[r] = (py[h] << 16) | px[h];
+          t.xp[r] = p.x + (long long)no[h] * p.x_outer + (long long)ni[h] * p.x_inner + (long long)pix * p.x_pix_stride;
+          t.dyp[r] = p.dy + (long long)no[h] * p.dy_outer + (long long)ni[h] * p.dy_inner +
+                     (long long)pix * p.dy_pix_stride;
         } else {
           t.pyx[r] = 0x4000 << 16; t.xp[r] = nullptr; t.dyp[r] = nullptr;
         }
+        // advance this row by 64 pixels
+        px[h] += drx; py[h] += dry;
+        if (px[h] >= p.W) { px[h] -= p.W; ++py[h]; }
+        int carry = 0;
+        if (py[h] >= p.H) { py[h] -= p.H; carry = 1; }
+        ni[h] += dni + carry; no[h] += dno;
+        if (ni[h] >= p.T_inner) { ni[h] -= p.T_inner; ++no[h]; }
+        if (ni[h] >= p.T_inner) { ni[h] -= p.T_inner; ++no[h]; }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bk->tabrdy[stage]));
