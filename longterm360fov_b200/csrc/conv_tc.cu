@@ -1,25 +1,32 @@
 // Tensor-core (tcgen05 + TMEM) implicit-GEMM convolution family for sm_100a.
 //
-//   D[m][n] = sum_k A(m,k) * Wp[k][n]      m = pixel (image, y, x), n = output channel,
+//   D[m][n] = sum_k A(m,k) * Wp[k][n]      m = pixel, n = output channel,
 //                                          k = (segment, tap, channel) of the im2col row
 //
-// * A is never materialised in HBM: 128 producer threads gather the im2col rows of a
-//   128-pixel tile straight from the fp32 NHWC activations (coalesced along channels),
-//   split each value into 1..3 bf16 terms and store them into the 128-byte-swizzled
-//   K-major shared-memory tiles tcgen05.mma reads.
-// * The weights are repacked once per call (tc_pack_kernel) into the exact shared-memory
-//   image of each (n-tile, k-block) B tile, so one TMA-engine bulk copy
-//   (cp.async.bulk -> UBLKCP) per pipeline stage brings them in, completion on an mbarrier.
-// * One elected thread issues tcgen05.mma (M=128, N=BLOCK_N<=256, K=16 per instruction),
-//   accumulating in TMEM in fp32; with NS bf16 terms per operand it issues the NS(NS+1)/2
-//   cross products whose weight is above 2^-8NS (bf16x3 ~ fp32 accuracy on tensor cores).
-// * Epilogues read the accumulator with tcgen05.ld and write through a per-warp
-//   shared-memory transpose so every global access is a full 128-byte line:
-//     TC_EPI_CONV: y = act(acc + bias + beta*y)
-//     TC_EPI_LSTM: ConvLSTM2D gate algebra + cell update fused (keras ConvLSTM2D step,
-//                  mycode/others_LSTM_span_whole.py:88-100, mycode/convlstm_seq2seq.py:100-126)
-//
-// Also here: the tensor-core weight-gradient kernel (MN-major operands, split over pixels).
+// Shifted-tap design: the im2col matrix is never built, not even in shared memory.
+//   * Pixels are numbered in a zero-PADDED linear frame: image n, row y, column x sits at
+//     L = n*Hp*Wp + (y+PLh)*Wp + (x+PLw), where the frame is padded by the 'same' padding of the
+//     convolution.  In this frame a kernel tap (ty,tx) is ONE constant row offset
+//     (ty*dil_h - pad_h)*Wp + (tx*dil_w - pad_w) for every pixel, and TF 'same' zero padding
+//     is just the zero rows of the frame.
+//   * A CTA owns 128 consecutive frame positions (the D rows; pad positions are computed and
+//     dropped).  Its producers stage the activations of those positions plus the halo ONCE:
+//     one 128-byte, 128B-swizzled shared-memory row per position holding up to 64 channels
+//     (fp32 -> 1..3 bf16 terms, split on the fly).
+//   * tcgen05.mma operand descriptors address shared memory by absolute address (the 128B swizzle
+//     is a function of the address bits: tests/cuda/tc_shift_probe.cu), so the A operand of tap t
+//     is the SAME staged tile with its start address moved by shift(t) rows: kh*kw MMAs per
+//     16-channel slice, no replicated data, each activation element loaded and converted once.
+//   * Weights are repacked once per call into the swizzled image of every (n-tile, k-block) B tile
+//     and streamed through an mbarrier ring by TMA-engine bulk copies (UBLKCP).
+//   * Accumulation in TMEM (fp32); with NS bf16 terms per operand the NS(NS+1)/2 significant cross
+//     products are issued (bf16x2: 3 MMAs, ~1e-5 max-abs error; bf16x3: 6 MMAs).
+//   * Epilogues read the accumulator with tcgen05.ld and go through a per-warp shared-memory
+//     transpose so that global accesses are coalesced float4 row segments:
+//       TC_EPI_CONV: y = act(acc + bias + beta*y)
+//       TC_EPI_LSTM: ConvLSTM2D gate algebra + cell update of one timestep, A = [x_t | h_{t-1}]
+//                    (keras ConvLSTM2D, mycode/others_LSTM_span_whole.py:88-100,
+//                     mycode/convlstm_seq2seq.py:100-126,146-165)
 #include "fov_common.cuh"
 #include "fov_internal.h"
 #include "tc_common.cuh"
@@ -29,26 +36,30 @@ namespace {
 using namespace tc;
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;                    // bf16 per 128-byte swizzle row
-constexpr int A_TILE_BYTES = BLOCK_M * 128;    // 16 KB per bf16 term
-constexpr int kProducers = 128;
-constexpr int kThreads = 192;                  // 4 producer/epilogue warps + B-copy warp + MMA warp
-constexpr int kMaxStages = 4;
-constexpr int CONV_RS = 36;                    // conv epilogue staging row stride (floats): 32 cols + pad
+constexpr int BLOCK_K = 64;                    // bf16 per 128-byte swizzle row / weight k-block
+constexpr int kProducers = 256;
+constexpr int kEpiWarps = 8;                   // warps 0-7: producers, then epilogue (warp w: TMEM lanes 32*(w&3)..)
+constexpr int kThreads = 320;                  // + weight-copy warp (8) + MMA warp (9)
+constexpr int kMaxBStages = 4;
+constexpr int kMaxRegionRows = 384;            // 128 D rows + halo
+constexpr int kMaxTaps = 64;
+constexpr int CONV_RS = 36;                    // conv epilogue staging row stride (floats)
 enum { O_OUT = 0, O_H = 1, O_GATES = 2, O_CPREV = 3, O_DENSE = 4 };
 
 struct DevSeg {
   const float* x;
-  int pix_stride, Cin, Cin_p, kw, taps, dil_h, dil_w, pad_h, pad_w, k_begin, vec;
+  long long outer, inner;
+  int pix_stride, Cin, Cin_p, cp_log2, cw, nch, lpr_log2, kw, taps, dil_h, dil_w, pad_h, pad_w, k_begin, vec;
+  int minshift, R, region_off, nbuf;
+  int row_bytes, swz_mask, term_bytes;   // staged row = cw bf16 (32/64/128 B) in the matching swizzle mode
+  uint32_t desc_hi;                      // high word of the A descriptors of this segment
 };
 
 struct DevParams {
   DevSeg seg[2];
-  int nseg;
-  long long x_outer[2], x_inner[2];
-  int H, W, HW, T_inner;
-  long long M;
-  int KB, Cout, BLOCK_N, stages, tmem_cols, stage_bytes, data_bytes;
+  int nseg, mode_b, dbg;
+  int H, W, Hp, Wp, PLh, PLw, HpWp, T_inner, N_img, total_pos;
+  int K_total, KB, Cout, BLOCK_N, b_stages, tmem_cols, b_off, b_stage_bytes, data_bytes;
   const uint8_t* wpk;
   // conv epilogue
   const float* bias;
@@ -65,16 +76,21 @@ struct DevParams {
   float *hT, *cT;
 };
 
-// shared-memory bookkeeping placed after the data region (pipeline stages / epilogue staging)
+// shared-memory bookkeeping placed after the data area (activation regions, weight ring / staging)
 struct Book {
-  const float* rp[2][BLOCK_M];     // per row, per segment: address of the row's own pixel (channel 0)
-  long long off_o[5][BLOCK_M];     // epilogue element offsets per row (image + pixel), see O_*
-  int pyx[BLOCK_M];                // (y << 16) | x of the row's pixel; y = 0x4000 marks a row past M
-  uint64_t full[kMaxStages], empty[kMaxStages], tmem_full;
+  int rp[2][kMaxRegionRows];            // per region row: element offset of that position's pixel, -1 = zero row
+  int off_o[5][BLOCK_M];                // epilogue element offsets of the D rows (image + pixel), see O_*
+  int valid[BLOCK_M];                   // D row is a real pixel
+  float bias_s[256];                    // LSTM epilogue: the 4F gate biases
+  int tapshift[2][kMaxTaps];            // row offset of every tap relative to the region start
+  uint64_t b_full[kMaxBStages], b_empty[kMaxBStages], a_full[2], a_empty[2], tmem_full;
   uint32_t tmem_ptr;
 };
 
-// element offset of image n in an (outer, inner) strided tensor
+// optional per-CTA phase timestamps (fov_debug_timeline): [cta][0..5] = start, setup done, activations
+// staged, accumulator complete, epilogue done, smid
+__device__ unsigned long long g_tc_timeline[256 * 8];
+
 __device__ __forceinline__ long long img_off(int n, int T_inner, long long outer, long long inner) {
   const int no = n / T_inner;
   return (long long)no * outer + (long long)(n - no * T_inner) * inner;
@@ -90,8 +106,14 @@ __device__ __forceinline__ float fast_rec(int rec, float x) {
   return __fdividef(1.0f, 1.0f + __expf(-x));
 }
 
+// descriptor = high word (SBO, version 1, swizzle mode) | low word (start address, LBO = 16 B)
+constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t desc_at(uint32_t hi, uint32_t saddr) {
+  return ((uint64_t)hi << 32) | (uint64_t)(((saddr >> 4) & 0x3FFFu) | (1u << 16));
+}
+
 template <int NS, int EPI>
-__global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const DevParams p) {
+__global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -100,47 +122,76 @@ __global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const DevParams p)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const long long m0 = (long long)blockIdx.x * BLOCK_M;
+  const int L0 = blockIdx.x * BLOCK_M;          // first frame position of this tile
   const int n_tile = blockIdx.y;
   const int n0 = n_tile * p.BLOCK_N;
-  const int S = p.stages;
+  const int S = p.b_stages;
   const uint32_t b_tile_bytes = (uint32_t)p.BLOCK_N * 128u;
+  const bool dbg = p.dbg && blockIdx.x < 256 && blockIdx.y == 0 && tid == 0;
+  if (dbg) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_tc_timeline[blockIdx.x * 8 + 0] = clock64();
+    g_tc_timeline[blockIdx.x * 8 + 5] = smid;
+  }
 
-  // ---------------- setup ----------------
+  // ---------------- setup: frame position -> pixel tables ----------------
   if (tid < BLOCK_M) {
-    const long long m = m0 + tid;
-    if (m < p.M) {
-      const int n = (int)((unsigned)m / (unsigned)p.HW);     // M < 2^31 (checked on the host)
-      const int pix = (int)m - n * p.HW;
-      bk->pyx[tid] = ((pix / p.W) << 16) | (pix - (pix / p.W) * p.W);
-      bk->rp[0][tid] = p.seg[0].x + img_off(n, p.T_inner, p.x_outer[0], p.x_inner[0]) +
-                       (long long)pix * p.seg[0].pix_stride;
-      bk->rp[1][tid] = p.nseg > 1 ? p.seg[1].x + img_off(n, p.T_inner, p.x_outer[1], p.x_inner[1]) +
-                                        (long long)pix * p.seg[1].pix_stride
-                                  : nullptr;
-      if (EPI == TC_EPI_CONV) {
-        bk->off_o[O_OUT][tid] = img_off(n, p.T_inner, p.y_outer, p.y_inner) + (long long)pix * p.y_pix_stride;
-      } else {
-        bk->off_o[O_OUT][tid] = img_off(n, p.T_inner, p.c_outer, p.c_inner) + (long long)pix * p.F;
-        bk->off_o[O_H][tid] = img_off(n, p.T_inner, p.h_outer, p.h_inner) + (long long)pix * p.h_pix_stride;
-        bk->off_o[O_GATES][tid] = img_off(n, p.T_inner, p.g_outer, p.g_inner) + (long long)pix * 4 * p.F;
-        bk->off_o[O_CPREV][tid] = img_off(n, p.T_inner, p.cp_outer, p.cp_inner) + (long long)pix * p.F;
-        bk->off_o[O_DENSE][tid] = ((long long)n * p.HW + pix) * p.F;
+    const int L = L0 + tid;
+    int ok = 0;
+    if (L < p.total_pos) {
+      const int n = L / p.HpWp, rem = L - n * p.HpWp;
+      const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
+      const int y = yp - p.PLh, x = xp - p.PLw;
+      if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) {
+        ok = 1;
+        const int pix = y * p.W + x;
+        if (EPI == TC_EPI_CONV) {
+          bk->off_o[O_OUT][tid] = (int)(img_off(n, p.T_inner, p.y_outer, p.y_inner) + (long long)pix * p.y_pix_stride);
+        } else {
+          bk->off_o[O_OUT][tid] = (int)(img_off(n, p.T_inner, p.c_outer, p.c_inner) + (long long)pix * p.F);
+          bk->off_o[O_H][tid] = (int)(img_off(n, p.T_inner, p.h_outer, p.h_inner) + (long long)pix * p.h_pix_stride);
+          bk->off_o[O_GATES][tid] = (int)(img_off(n, p.T_inner, p.g_outer, p.g_inner) + (long long)pix * 4 * p.F);
+          bk->off_o[O_CPREV][tid] = (int)(img_off(n, p.T_inner, p.cp_outer, p.cp_inner) + (long long)pix * p.F);
+          bk->off_o[O_DENSE][tid] = (n * p.H * p.W + pix) * p.F;
+        }
       }
-    } else {
-      bk->pyx[tid] = 0x4000 << 16;
-      bk->rp[0][tid] = nullptr; bk->rp[1][tid] = nullptr;
+    }
+    bk->valid[tid] = ok;
+  }
+  for (int s = 0; s < p.nseg; ++s) {
+    const DevSeg& sg = p.seg[s];
+    for (int i = tid; i < sg.R; i += kThreads) {
+      const int L = L0 + sg.minshift + i;
+      int ptr = -1;
+      if (L >= 0 && L < p.total_pos && sg.x != nullptr) {
+        const int n = L / p.HpWp, rem = L - n * p.HpWp;
+        const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
+        const int y = yp - p.PLh, x = xp - p.PLw;
+        if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W)
+          ptr = (int)(img_off(n, p.T_inner, sg.outer, sg.inner) + (long long)(y * p.W + x) * sg.pix_stride);
+      }
+      bk->rp[s][i] = ptr;
+    }
+    for (int t = tid; t < sg.taps; t += kThreads) {
+      const int ty = t / sg.kw, tx = t - ty * sg.kw;
+      bk->tapshift[s][t] = (ty * sg.dil_h - sg.pad_h) * p.Wp + (tx * sg.dil_w - sg.pad_w) - sg.minshift;
     }
   }
-  if (warp == 5 && lane == 0) {
+  if (EPI == TC_EPI_LSTM && tid < 4 * p.F) bk->bias_s[tid] = __ldg(&p.bias[tid]);
+  if (warp == 9 && lane == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&bk->full[s]), kProducers + 1);
-      mbar_init(smem_u32(&bk->empty[s]), 1);
+      mbar_init(smem_u32(&bk->b_full[s]), 1);
+      mbar_init(smem_u32(&bk->b_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bk->a_full[s]), kProducers);
+      mbar_init(smem_u32(&bk->a_empty[s]), 1);
     }
     mbar_init(smem_u32(&bk->tmem_full), 1);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     tmem_alloc(smem_u32(&bk->tmem_ptr), (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
@@ -148,83 +199,78 @@ __global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const DevParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = bk->tmem_ptr;
+  if (dbg) g_tc_timeline[blockIdx.x * 8 + 1] = clock64();
 
-  if (warp < 4) {
-    // ---------------- A producers: gather + split + swizzled store ----------------
-    // thread (q, rsub) owns the 4 consecutive k values q*4.. of rows rsub, rsub+8, ... ; the loads of
-    // the next half k-block are always in flight while the current half is converted and stored.
-    const int q = tid & 15;          // float4 slot inside the 64-wide k slice
-    const int rsub = tid >> 4;       // 0..7
-    struct KDec { int si, dy, dx, nvalid, delta, vec; };
-    auto decode = [&](int kb) {
-      KDec d;
-      const int k = kb * BLOCK_K + q * 4;
-      d.si = (p.nseg > 1 && k >= p.seg[1].k_begin) ? 1 : 0;
-      const DevSeg& sg = p.seg[d.si];
-      const int kk = k - sg.k_begin;
-      const int tap = kk / sg.Cin_p;
-      const int ci = kk - tap * sg.Cin_p;
-      int nvalid = (tap < sg.taps && sg.x != nullptr) ? (sg.Cin - ci) : 0;
-      d.nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
-      const int ty = tap / sg.kw, tx = tap - ty * sg.kw;
-      d.dy = ty * sg.dil_h - sg.pad_h; d.dx = tx * sg.dil_w - sg.pad_w;
-      d.delta = (d.dy * p.W + d.dx) * sg.pix_stride + ci;   // tap + channel offset from the row's own pixel
-      d.vec = sg.vec;
-      return d;
-    };
-    auto issue = [&](const KDec& d, int half, float4 (&v)[8]) {
-      const float* const* rp = bk->rp[d.si];
+  if (warp < kEpiWarps) {
+    // ---------------- activation producers ----------------
+    // Stage one 64-channel slice of a segment: region row i <- frame position L0 + minshift + i.
+    auto load_region = [&](int s, int cc, int buf) {
+      const DevSeg& sg = p.seg[s];
+      uint8_t* reg = smem + sg.region_off + (size_t)buf * NS * sg.term_bytes;
+      const int lg = sg.lpr_log2, lpr = 1 << lg;
+      const int c4 = tid & (lpr - 1);
+      const int row0 = tid >> lg, rstep = kProducers >> lg;        // rstep is a multiple of 8 rows
+      const int ch = cc * BLOCK_K + c4 * 4;
+      int nvalid = sg.Cin - ch;
+      nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
+      // absolute-address swizzle of this thread's slot in row0; rows row0 + 8k keep the same phase
+      const uint32_t a0 = (uint32_t)row0 * sg.row_bytes + (uint32_t)c4 * 8u;
+      const uint32_t st_off = a0 ^ (((a0 >> 7) & (uint32_t)sg.swz_mask) << 4);
+      const int* rp = bk->rp[s];
+      const float* xb = sg.x + ch;
+      for (int r = row0; r < sg.R; r += 8 * rstep) {
+        float4 v[8];
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int row = (half * 8 + jj) * 8 + rsub;
-        const int pyx = bk->pyx[row];
-        const unsigned yy = (unsigned)((pyx >> 16) + d.dy), xx = (unsigned)((pyx & 0xffff) + d.dx);
-        v[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (d.nvalid > 0 && yy < (unsigned)p.H && xx < (unsigned)p.W)
-          v[jj] = ldg_vec4(rp[row] + d.delta, d.nvalid, d.vec);
+        for (int j = 0; j < 8; ++j) {
+          const int row = r + j * rstep;
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < sg.R && nvalid > 0) {
+            const int off = rp[row];
+            if (off >= 0) v[j] = ldg_vec4(xb + off, nvalid, sg.vec);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int row = r + j * rstep;
+          if (row < sg.R) {
+            uint2 pk[NS];
+            split4<NS>(v[j], pk);
+#pragma unroll
+            for (int t = 0; t < NS; ++t)
+              *reinterpret_cast<uint2*>(reg + t * sg.term_bytes + (row - row0) * sg.row_bytes + st_off) = pk[t];
+          }
+        }
       }
     };
-    // row = 8*(...) + rsub, so the swizzle phase (row & 7) is the thread constant rsub
-    const uint32_t st_off = (uint32_t)rsub * 128u + ((uint32_t)((q >> 1) ^ rsub) << 4) + (uint32_t)(q & 1) * 8u;
-    auto store = [&](uint8_t* a_stage, int half, const float4 (&v)[8]) {
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        uint2 pk[NS];
-        split4<NS>(v[jj], pk);
-#pragma unroll
-        for (int s = 0; s < NS; ++s)
-          *reinterpret_cast<uint2*>(a_stage + s * A_TILE_BYTES + (half * 8 + jj) * 1024 + st_off) = pk[s];
-      }
-    };
-    float4 va[8], vb[8];
-    KDec dcur = decode(0);
-    issue(dcur, 0, va);
-    for (int kb = 0; kb < p.KB; ++kb) {
-      const int stage = kb % S;
-      const uint32_t phase = (uint32_t)(kb / S) & 1u;
-      issue(dcur, 1, vb);
-      mbar_wait(smem_u32(&bk->empty[stage]), phase ^ 1u);
-      uint8_t* a_stage = smem + (size_t)stage * p.stage_bytes;
-      store(a_stage, 0, va);
-      if (kb + 1 < p.KB) {
-        dcur = decode(kb + 1);
-        issue(dcur, 0, va);
-      }
-      store(a_stage, 1, vb);
+    if (!p.mode_b) {
+      for (int s = 0; s < p.nseg; ++s) load_region(s, 0, 0);
       fence_proxy_async_smem();
-      mbar_arrive(smem_u32(&bk->full[stage]));
+      mbar_arrive(smem_u32(&bk->a_full[0]));
+      if (dbg) g_tc_timeline[blockIdx.x * 8 + 2] = clock64();
+    } else {
+      const int nch = p.seg[0].nch;
+      for (int cc = 0; cc < nch; ++cc) {
+        const int buf = cc & 1;
+        mbar_wait(smem_u32(&bk->a_empty[buf]), ((uint32_t)(cc >> 1) & 1u) ^ 1u);
+        load_region(0, cc, buf);
+        fence_proxy_async_smem();
+        mbar_arrive(smem_u32(&bk->a_full[buf]));
+      }
     }
-  } else if (warp == 4) {
-    // ---------------- B producer: one bulk copy per stage ----------------
+  } else if (warp == 8) {
+    // ---------------- weight producer: one bulk copy per k-block, in MMA consumption order ----------------
     if (lane == 0) {
       const uint8_t* src = p.wpk + (size_t)n_tile * p.KB * NS * b_tile_bytes;
-      for (int kb = 0; kb < p.KB; ++kb) {
-        const int stage = kb % S;
-        const uint32_t phase = (uint32_t)(kb / S) & 1u;
-        mbar_wait(smem_u32(&bk->empty[stage]), phase ^ 1u);
-        const uint32_t bar = smem_u32(&bk->full[stage]);
+      const int taps = p.seg[0].taps, nch = p.seg[0].nch;
+      int cc = 0, tap = 0;
+      for (int it = 0; it < p.KB; ++it) {
+        const int kb = p.mode_b ? tap * nch + cc : it;
+        if (p.mode_b && ++tap == taps) { tap = 0; ++cc; }
+        const int stage = it % S;
+        mbar_wait(smem_u32(&bk->b_empty[stage]), ((uint32_t)(it / S) & 1u) ^ 1u);
+        const uint32_t bar = smem_u32(&bk->b_full[stage]);
         mbar_arrive_expect_tx(bar, NS * b_tile_bytes);
-        bulk_g2s(base + (uint32_t)stage * p.stage_bytes + NS * A_TILE_BYTES, src + (size_t)kb * NS * b_tile_bytes,
+        bulk_g2s(base + p.b_off + (uint32_t)stage * p.b_stage_bytes, src + (size_t)kb * NS * b_tile_bytes,
                  NS * b_tile_bytes, bar);
       }
     }
@@ -232,46 +278,81 @@ __global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const DevParams p)
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16_f32(BLOCK_M, p.BLOCK_N, 0, 0);
-      for (int kb = 0; kb < p.KB; ++kb) {
-        const int stage = kb % S;
-        const uint32_t phase = (uint32_t)(kb / S) & 1u;
-        mbar_wait(smem_u32(&bk->full[stage]), phase);
-        tc_fence_after();
-        const uint32_t a0 = base + (uint32_t)stage * p.stage_bytes;
-        const uint32_t b0 = a0 + NS * A_TILE_BYTES;
+      uint32_t first = 1;
+      // one 16-wide K step: A = staged region of (seg, buffer) shifted by the tap, B = weight ring slot
+      auto kstep = [&](uint32_t a_hi, uint32_t a_addr, uint32_t a_term, uint32_t b_addr) {
 #pragma unroll
-        for (int k4 = 0; k4 < BLOCK_K / 16; ++k4) {
-          // smallest cross terms first, the hi*hi product last
+        for (int sum = NS - 1; sum >= 0; --sum) {     // smallest cross terms first, hi*hi last
 #pragma unroll
-          for (int sum = NS - 1; sum >= 0; --sum) {
-#pragma unroll
-            for (int sa = 0; sa <= sum; ++sa) {
-              const int sb = sum - sa;
-              const uint64_t ad = smem_desc_sw128(a0 + sa * A_TILE_BYTES + k4 * 32, 16, 1024);
-              const uint64_t bd = smem_desc_sw128(b0 + sb * b_tile_bytes + k4 * 32, 16, 1024);
-              const uint32_t acc = (kb > 0 || k4 > 0 || sum != NS - 1 || sa > 0) ? 1u : 0u;
-              umma_bf16(tmem_d, ad, bd, idesc, acc);
-            }
+          for (int sa = 0; sa <= sum; ++sa) {
+            const int sb = sum - sa;
+            umma_bf16(tmem_d, desc_at(a_hi, a_addr + sa * a_term), desc_at(kDescHi128, b_addr + sb * b_tile_bytes), idesc,
+                      first ^ 1u);
+            first = 0;
           }
         }
-        umma_commit(smem_u32(&bk->empty[stage]));
+      };
+      if (!p.mode_b) {
+        mbar_wait(smem_u32(&bk->a_full[0]), 0);
+        tc_fence_after();
+        for (int kb = 0; kb < p.KB; ++kb) {
+          const int stage = kb % S;
+          mbar_wait(smem_u32(&bk->b_full[stage]), (uint32_t)(kb / S) & 1u);
+          tc_fence_after();
+          const uint32_t b0 = base + p.b_off + (uint32_t)stage * p.b_stage_bytes;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int k = kb * BLOCK_K + k4 * 16;
+            if (k < p.K_total) {
+              const int s = (p.nseg > 1 && k >= p.seg[1].k_begin) ? 1 : 0;
+              const DevSeg& sg = p.seg[s];
+              const int kk = k - sg.k_begin;
+              const int tap = kk >> sg.cp_log2, c0 = kk & (sg.Cin_p - 1);
+              const uint32_t a_addr = base + sg.region_off + (uint32_t)bk->tapshift[s][tap] * sg.row_bytes + (uint32_t)c0 * 2u;
+              kstep(sg.desc_hi, a_addr, (uint32_t)sg.term_bytes, b0 + k4 * 32);
+            }
+          }
+          umma_commit(smem_u32(&bk->b_empty[stage]));
+        }
+      } else {
+        const DevSeg& sg = p.seg[0];
+        const uint32_t a_term = (uint32_t)sg.term_bytes;
+        int it = 0;
+        for (int cc = 0; cc < sg.nch; ++cc) {
+          const int buf = cc & 1;
+          mbar_wait(smem_u32(&bk->a_full[buf]), (uint32_t)(cc >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t areg = base + sg.region_off + (uint32_t)buf * NS * a_term;
+          for (int tap = 0; tap < sg.taps; ++tap, ++it) {
+            const int stage = it % S;
+            mbar_wait(smem_u32(&bk->b_full[stage]), (uint32_t)(it / S) & 1u);
+            tc_fence_after();
+            const uint32_t b0 = base + p.b_off + (uint32_t)stage * p.b_stage_bytes;
+            const uint32_t a0 = areg + (uint32_t)bk->tapshift[0][tap] * 128u;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) kstep(sg.desc_hi, a0 + k4 * 32, a_term, b0 + k4 * 32);
+            umma_commit(smem_u32(&bk->b_empty[stage]));
+          }
+          umma_commit(smem_u32(&bk->a_empty[buf]));
+        }
       }
       umma_commit(smem_u32(&bk->tmem_full));
     }
   }
 
-  // ---------------- epilogue (warps 0-3; warp w owns TMEM lanes / tile rows 32w..32w+31) ----------------
-  // all MMAs have completed when tmem_full fires, so the pipeline stages are free: the per-warp
-  // staging rows alias them.  Every global access below is a coalesced float4 row segment.
-  if (warp < 4) {
-    mbar_wait(smem_u32(&bk->tmem_full), 0);
-    tc_fence_after();
-    const int r0 = warp * 32;
+  // ---------------- epilogue (warps 0-7; warp w owns TMEM lanes / D rows 32*(w&3).., every other column pass) -------
+  // all MMAs have completed when tmem_full fires, so the data area is free: the staging rows alias it.
+  if (warp < kEpiWarps) {
+    const int q = warp & 3, half = warp >> 2;
+    const int r0 = q * 32;
     const uint32_t t_row = tmem_d + ((uint32_t)r0 << 16);
+    float* stg = reinterpret_cast<float*>(smem) + warp * (32 * CONV_RS);     // 32 rows x 32 floats (+4 pad)
 
     if (EPI == TC_EPI_CONV) {
-      float* stg = reinterpret_cast<float*>(smem) + warp * (32 * CONV_RS);
-      for (int c0 = 0; c0 < p.BLOCK_N; c0 += 32) {
+      mbar_wait(smem_u32(&bk->tmem_full), 0);
+      tc_fence_after();
+      if (dbg) g_tc_timeline[blockIdx.x * 8 + 3] = clock64();
+      for (int c0 = half * 32; c0 < p.BLOCK_N; c0 += 64) {
         float v[32];
         tmem_ld16(t_row + c0, v);
         tmem_ld16(t_row + c0 + 16, v + 16);
@@ -289,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const DevParams p)
 #pragma unroll 2
           for (int it = 0; it < 32; it += 4) {
             const int rr = it + (lane >> 3), row = r0 + rr;
-            if (col_ok && (bk->pyx[row] >> 16) != 0x4000) {
+            if (col_ok && bk->valid[row]) {
               float* dst = p.y + bk->off_o[O_OUT][row] + col;
               float4 a = *reinterpret_cast<const float4*>(&stg[rr * CONV_RS + c4]);
               a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
@@ -297,7 +378,9 @@ __global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const DevParams p)
                 const float4 o = *reinterpret_cast<const float4*>(dst);
                 a.x += p.beta * o.x; a.y += p.beta * o.y; a.z += p.beta * o.z; a.w += p.beta * o.w;
               }
-              a.x = fov_act(p.act, a.x); a.y = fov_act(p.act, a.y); a.z = fov_act(p.act, a.z); a.w = fov_act(p.act, a.w);
+              if (p.act != FOV_ACT_LINEAR) {
+                a.x = fov_act(p.act, a.x); a.y = fov_act(p.act, a.y); a.z = fov_act(p.act, a.z); a.w = fov_act(p.act, a.w);
+              }
               *reinterpret_cast<float4*>(dst) = a;
             }
           }
@@ -307,8 +390,7 @@ __global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const DevParams p)
           const float bv = (col_ok && p.bias) ? __ldg(&p.bias[col]) : 0.0f;
           for (int rr = 0; rr < 32; ++rr) {
             const int row = r0 + rr;
-            if ((bk->pyx[row] >> 16) == 0x4000) break;
-            if (col_ok) {
+            if (col_ok && bk->valid[row]) {
               float* dst = p.y + bk->off_o[O_OUT][row] + col;
               float val = stg[rr * CONV_RS + lane] + bv;
               if (p.beta != 0.0f) val += p.beta * *dst;
@@ -319,99 +401,120 @@ __global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const DevParams p)
         __syncwarp();
       }
     } else {
-      // Fused ConvLSTM step.  Accumulator columns: [i | f | c~ | o], each F wide.  Channels are
-      // processed CW at a time; staging row = [i f g o | c | h] (CW floats each) + 4 pad floats.
+      // Fused ConvLSTM step.  Accumulator columns: [i | f | c~ | o], each F wide, processed 8 channels per
+      // pass; the two warps of a lane quarter take alternate passes.  Row-per-thread values go through the
+      // staging rows two 8-wide segments at a time and leave as coalesced float4 row segments.
       const int F = p.F;
-      const int CW = F < 16 ? F : 16;
-      const int RS = 6 * CW + 4;
-      float* stg = reinterpret_cast<float*>(smem) + warp * (32 * RS);
-      const int lpr = CW >> 2;                  // float4 lanes per row segment
-      const int rpi = 32 / lpr;                 // rows per warp access
-      const int srow = lane / lpr, sc4 = (lane - srow * lpr) * 4;
-      // coalesced copy of one CW-wide segment between the staging rows and a global tensor
+      constexpr int CW = 8;
+      const int npass = F / CW;
+      const int srow = lane >> 1, sc4 = (lane & 1) * 4;        // 2 float4 lanes per 8-wide row segment
+      // prefetch c_{t-1} of this warp's first two passes while the MMAs are still running
+      float4 cpre[2][2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          cpre[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int pass = half + 2 * u;
+          const int row = r0 + i * 16 + srow;
+          if (p.c_prev && pass < npass && bk->valid[row])
+            cpre[u][i] = __ldg(reinterpret_cast<const float4*>(p.c_prev + bk->off_o[O_CPREV][row] + pass * CW + sc4));
+        }
+      mbar_wait(smem_u32(&bk->tmem_full), 0);
+      tc_fence_after();
+      if (dbg) g_tc_timeline[blockIdx.x * 8 + 3] = clock64();
+      const int row_a = r0 + srow, row_b = r0 + 16 + srow;
+      const bool ok_a = bk->valid[row_a] != 0, ok_b = bk->valid[row_b] != 0;
+      // coalesced store of one staged 8-wide segment
       auto seg_store = [&](int stage_col, float* dst, int oidx, int dst_col, float* dense) {
         if (!dst) return;
-        for (int it = 0; it < 32; it += rpi) {
-          const int rr = it + srow, row = r0 + rr;
-          if ((bk->pyx[row] >> 16) != 0x4000) {
-            const float4 v = *reinterpret_cast<const float4*>(&stg[rr * RS + stage_col + sc4]);
-            *reinterpret_cast<float4*>(dst + bk->off_o[oidx][row] + dst_col + sc4) = v;
-            if (dense) *reinterpret_cast<float4*>(dense + bk->off_o[O_DENSE][row] + dst_col + sc4) = v;
-          }
+        if (ok_a) {
+          const float4 v = *reinterpret_cast<const float4*>(&stg[srow * CONV_RS + stage_col + sc4]);
+          *reinterpret_cast<float4*>(dst + bk->off_o[oidx][row_a] + dst_col + sc4) = v;
+          if (dense) *reinterpret_cast<float4*>(dense + bk->off_o[O_DENSE][row_a] + dst_col + sc4) = v;
+        }
+        if (ok_b) {
+          const float4 v = *reinterpret_cast<const float4*>(&stg[(16 + srow) * CONV_RS + stage_col + sc4]);
+          *reinterpret_cast<float4*>(dst + bk->off_o[oidx][row_b] + dst_col + sc4) = v;
+          if (dense) *reinterpret_cast<float4*>(dense + bk->off_o[O_DENSE][row_b] + dst_col + sc4) = v;
         }
       };
-      for (int cpass = 0; cpass < F; cpass += CW) {
+      float* myrow = stg + lane * CONV_RS;
+      for (int pass = half, u = 0; pass < npass; pass += 2, ++u) {
+        const int cpass = pass * CW;
+        // ---- c_{t-1}: coalesced block -> staging -> one row per thread ----
+        float cpv[CW];
+#pragma unroll
+        for (int j = 0; j < CW; ++j) cpv[j] = 0.0f;
         if (p.c_prev) {
-          for (int it = 0; it < 32; it += rpi) {
-            const int rr = it + srow, row = r0 + rr;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if ((bk->pyx[row] >> 16) != 0x4000)
-              v = __ldg(reinterpret_cast<const float4*>(p.c_prev + bk->off_o[O_CPREV][row] + cpass + sc4));
-            *reinterpret_cast<float4*>(&stg[rr * RS + 4 * CW + sc4]) = v;
+          float4 va, vb;
+          if (u < 2) {
+            va = u == 0 ? cpre[0][0] : cpre[1][0];
+            vb = u == 0 ? cpre[0][1] : cpre[1][1];
+          } else {
+            va = vb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok_a) va = __ldg(reinterpret_cast<const float4*>(p.c_prev + bk->off_o[O_CPREV][row_a] + cpass + sc4));
+            if (ok_b) vb = __ldg(reinterpret_cast<const float4*>(p.c_prev + bk->off_o[O_CPREV][row_b] + cpass + sc4));
           }
+          *reinterpret_cast<float4*>(&stg[srow * CONV_RS + sc4]) = va;
+          *reinterpret_cast<float4*>(&stg[(16 + srow) * CONV_RS + sc4]) = vb;
+          __syncwarp();
+          const float4 t0 = *reinterpret_cast<const float4*>(&myrow[0]);
+          const float4 t1 = *reinterpret_cast<const float4*>(&myrow[4]);
+          cpv[0] = t0.x; cpv[1] = t0.y; cpv[2] = t0.z; cpv[3] = t0.w;
+          cpv[4] = t1.x; cpv[5] = t1.y; cpv[6] = t1.z; cpv[7] = t1.w;
           __syncwarp();
         }
         // ---- gates from TMEM ----
-        float g[4][16];
-        if (CW == 16) {
+        float g[4][CW];
 #pragma unroll
-          for (int gi = 0; gi < 4; ++gi) tmem_ld16(t_row + gi * F + cpass, g[gi]);
-          tmem_ld_wait();
-        } else {   // F == 8: the four 8-wide gate blocks are the 32 accumulator columns
-          float v[32];
-          tmem_ld16(t_row, v);
-          tmem_ld16(t_row + 16, v + 16);
-          tmem_ld_wait();
+        for (int gi = 0; gi < 4; ++gi) tmem_ld8(t_row + gi * F + cpass, g[gi]);
+        tmem_ld_wait();
+        float cn[CW], hn[CW];
 #pragma unroll
-          for (int gi = 0; gi < 4; ++gi)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) g[gi][j] = v[gi * 8 + j];
+        for (int j = 0; j < CW; ++j) {
+          const int ch = cpass + j;
+          const float ai = fast_rec(p.rec_act, g[0][j] + bk->bias_s[ch]);
+          const float af = fast_rec(p.rec_act, g[1][j] + bk->bias_s[F + ch]);
+          const float ag = fast_tanh(g[2][j] + bk->bias_s[2 * F + ch]);
+          const float ao = fast_rec(p.rec_act, g[3][j] + bk->bias_s[3 * F + ch]);
+          cn[j] = af * cpv[j] + ai * ag;
+          hn[j] = ao * fast_tanh(cn[j]);
+          g[0][j] = ai; g[1][j] = af; g[2][j] = ag; g[3][j] = ao;
         }
-        float* myrow = stg + lane * RS;
-#pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4) {
-          if (j4 < CW) {
-            float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.c_prev) cp = *reinterpret_cast<const float4*>(&myrow[4 * CW + j4]);
-            const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
-            float cn[4], hn[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = j4 + e, ch = cpass + j;
-              const float ai = fast_rec(p.rec_act, g[0][j] + __ldg(&p.bias[ch]));
-              const float af = fast_rec(p.rec_act, g[1][j] + __ldg(&p.bias[F + ch]));
-              const float ag = fast_tanh(g[2][j] + __ldg(&p.bias[2 * F + ch]));
-              const float ao = fast_rec(p.rec_act, g[3][j] + __ldg(&p.bias[3 * F + ch]));
-              cn[e] = af * cpv[e] + ai * ag;
-              hn[e] = ao * fast_tanh(cn[e]);
-              g[0][j] = ai; g[1][j] = af; g[2][j] = ag; g[3][j] = ao;
-            }
-#pragma unroll
-            for (int gi = 0; gi < 4; ++gi)
-              *reinterpret_cast<float4*>(&myrow[gi * CW + j4]) =
-                  make_float4(g[gi][j4], g[gi][j4 + 1], g[gi][j4 + 2], g[gi][j4 + 3]);
-            *reinterpret_cast<float4*>(&myrow[4 * CW + j4]) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            *reinterpret_cast<float4*>(&myrow[5 * CW + j4]) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-          }
-        }
+        // ---- rounds of staged segments: (c, h), then the four activated gates ----
+        auto put = [&](int col, const float (&a)[CW]) {
+          *reinterpret_cast<float4*>(&myrow[col]) = make_float4(a[0], a[1], a[2], a[3]);
+          *reinterpret_cast<float4*>(&myrow[col + 4]) = make_float4(a[4], a[5], a[6], a[7]);
+        };
+        put(0, cn); put(8, hn);
+        if (p.gates_out) { put(16, g[0]); put(24, g[1]); }
         __syncwarp();
-        seg_store(4 * CW, p.c_out, O_OUT, cpass, p.cT);
-        seg_store(5 * CW, p.h_out, O_H, cpass, p.hT);
-#pragma unroll
-        for (int gi = 0; gi < 4; ++gi) seg_store(gi * CW, p.gates_out, O_GATES, gi * F + cpass, nullptr);
+        seg_store(0, p.c_out, O_OUT, cpass, p.cT);
+        seg_store(8, p.h_out, O_H, cpass, p.hT);
+        if (p.gates_out) {
+          seg_store(16, p.gates_out, O_GATES, cpass, nullptr);
+          seg_store(24, p.gates_out, O_GATES, F + cpass, nullptr);
+          __syncwarp();
+          put(0, g[2]); put(8, g[3]);
+          __syncwarp();
+          seg_store(0, p.gates_out, O_GATES, 2 * F + cpass, nullptr);
+          seg_store(8, p.gates_out, O_GATES, 3 * F + cpass, nullptr);
+        }
         __syncwarp();
       }
     }
   }
 
+  if (dbg) g_tc_timeline[blockIdx.x * 8 + 4] = clock64();
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
+  if (warp == 8) tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Weight packing: Keras-layout fp32 weights -> bf16 terms in the swizzled smem image of every
-// (n-tile, k-block) B tile.  One thread per 16-byte chunk.
+// (n-tile, k-block) B tile; k = k_begin(seg) + tap*Cin_p + channel.  One thread per 16-byte chunk.
 // ---------------------------------------------------------------------------------------------
 struct PackSeg {
   const float* w;
@@ -461,69 +564,102 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const PackParams p) {
   }
 }
 
+struct SegPlan {
+  int Cin_p, cp_log2, cw, nch, lpr_log2, k_begin, taps, minshift, R, region_off, nbuf, row_bytes, term_bytes;
+};
 struct Plan {
-  int Cin_p[2], k_begin[2], taps[2];
-  int K_total, KB, BLOCK_N, n_tiles, NS, stages, stage_bytes, tmem_cols, data_bytes;
+  SegPlan sp[2];
+  int PLh, PLw, Hp, Wp, mode_b;
+  int K_total, KB, BLOCK_N, n_tiles, NS, b_stages, b_stage_bytes, b_off, tmem_cols, data_bytes;
+  long long total_pos;
   size_t smem_bytes, ws_bytes;
 };
+
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 int make_plan(const TcConv& c, Plan* pl) {
   FOV_CHECK_ARG(c.nseg == 1 || c.nseg == 2, "nseg must be 1 or 2");
   FOV_CHECK_ARG(c.math >= 1 && c.math <= 3, "math must be 1..3 bf16 terms");
   FOV_CHECK_ARG(c.N_img > 0 && c.H > 0 && c.W > 0 && c.Cout > 0 && c.T_inner > 0, "bad shape");
-  FOV_CHECK_ARG((long long)c.N_img * c.H * c.W < (1LL << 31) - BLOCK_M && c.H < 0x4000 && c.W < 0x10000,
-                "too many pixels for 32-bit indexing");
-  int k = 0;
+  pl->NS = c.math;
+  // common zero-padded frame
+  int PLh = 0, PHh = 0, PLw = 0, PHw = 0;
   for (int s = 0; s < c.nseg; ++s) {
     const TcSeg& g = c.seg[s];
-    FOV_CHECK_ARG(g.Cin > 0 && g.kh > 0 && g.kw > 0 && g.dil_h > 0 && g.dil_w > 0, "bad segment");
-    pl->Cin_p[s] = (g.Cin + 7) / 8 * 8;
-    pl->taps[s] = g.kh * g.kw;
-    pl->k_begin[s] = k;
-    k += pl->taps[s] * pl->Cin_p[s];
+    FOV_CHECK_ARG(g.Cin > 0 && g.kh > 0 && g.kw > 0 && g.dil_h > 0 && g.dil_w > 0 && g.pad_h >= 0 && g.pad_w >= 0,
+                  "bad segment");
+    FOV_CHECK_ARG(g.kh * g.kw <= kMaxTaps, "too many kernel taps");
+    const int hh = (g.kh - 1) * g.dil_h - g.pad_h, hw = (g.kw - 1) * g.dil_w - g.pad_w;
+    PLh = g.pad_h > PLh ? g.pad_h : PLh; PLw = g.pad_w > PLw ? g.pad_w : PLw;
+    PHh = hh > PHh ? hh : PHh; PHw = hw > PHw ? hw : PHw;
   }
+  pl->PLh = PLh; pl->PLw = PLw;
+  pl->Hp = c.H + PLh + PHh; pl->Wp = c.W + PLw + PHw;
+  pl->total_pos = (long long)c.N_img * pl->Hp * pl->Wp;
+  FOV_CHECK_ARG(pl->total_pos < (1LL << 31) - 2 * kMaxRegionRows, "too many pixels for 32-bit indexing");
+  int k = 0, any_multi = 0, region_bytes = 0;
+  for (int s = 0; s < c.nseg; ++s) {
+    const TcSeg& g = c.seg[s];
+    SegPlan& sp = pl->sp[s];
+    sp.Cin_p = g.Cin <= 16 ? 16 : (g.Cin <= 32 ? 32 : (g.Cin + 63) / 64 * 64);
+    sp.cp_log2 = ilog2(sp.Cin_p);       // only used when Cin_p <= 64 (a power of two there)
+    sp.cw = sp.Cin_p < 64 ? sp.Cin_p : 64;
+    sp.nch = sp.Cin_p <= 64 ? 1 : sp.Cin_p / 64;
+    sp.lpr_log2 = ilog2(sp.cw / 4);
+    sp.taps = g.kh * g.kw;
+    sp.k_begin = k;
+    k += sp.taps * sp.Cin_p;
+    sp.minshift = -(g.pad_h * pl->Wp + g.pad_w);
+    const int maxshift = ((g.kh - 1) * g.dil_h - g.pad_h) * pl->Wp + ((g.kw - 1) * g.dil_w - g.pad_w);
+    sp.R = (BLOCK_M + maxshift - sp.minshift + 7) / 8 * 8;
+    FOV_CHECK_ARG(sp.R <= kMaxRegionRows, "convolution halo too large for the shifted-tap kernel");
+    sp.nbuf = sp.nch > 1 ? 2 : 1;
+    any_multi |= sp.nch > 1;
+    sp.row_bytes = sp.cw * 2;
+    sp.term_bytes = (sp.R * sp.row_bytes + 1023) / 1024 * 1024;
+    sp.region_off = region_bytes;
+    region_bytes += sp.nbuf * pl->NS * sp.term_bytes;
+  }
+  FOV_CHECK_ARG(!(c.nseg == 2 && any_multi), "two-segment GEMM needs <= 64 channels per segment");
+  pl->mode_b = any_multi;
   pl->K_total = k;
   pl->KB = (k + BLOCK_K - 1) / BLOCK_K;
-  pl->NS = c.math;
-  const int n_pad = (c.Cout + 15) / 16 * 16;
-  if (c.epi == TC_EPI_LSTM) {
-    FOV_CHECK_ARG(c.Cout % 4 == 0, "LSTM epilogue needs Cout = 4F");
-    const int F = c.Cout / 4;
-    FOV_CHECK_ARG(F == 8 || F == 16 || F == 32 || F == 64, "LSTM epilogue supports F in {8,16,32,64}");
-    pl->n_tiles = 1;
-    pl->BLOCK_N = c.Cout;
-  } else {
-    const int max_n = pl->NS >= 3 ? 128 : 256;   // keep >= 2 pipeline stages in shared memory
-    pl->n_tiles = (n_pad + max_n - 1) / max_n;
-    pl->BLOCK_N = ((n_pad + pl->n_tiles - 1) / pl->n_tiles + 15) / 16 * 16;
-  }
-  pl->tmem_cols = (int)tmem_cols_for(pl->BLOCK_N);
-  pl->stage_bytes = pl->NS * (A_TILE_BYTES + pl->BLOCK_N * 128);
-  // epilogue staging (aliases the pipeline stages)
+  // epilogue staging (aliases the data area)
   int staging;
   if (c.epi == TC_EPI_LSTM) {
+    FOV_CHECK_ARG(c.Cout % 4 == 0, "LSTM epilogue needs Cout = 4F");
     const int F = c.Cout / 4, CW = F < 16 ? F : 16;
-    staging = 4 * 32 * (6 * CW + 4) * 4;
+    FOV_CHECK_ARG(F == 8 || F == 16 || F == 32 || F == 64, "LSTM epilogue supports F in {8,16,32,64}");
+    (void)CW;
+    staging = kEpiWarps * 32 * CONV_RS * 4;
   } else {
-    staging = 4 * 32 * CONV_RS * 4;
+    staging = kEpiWarps * 32 * CONV_RS * 4;
   }
-  // Stage count.  The gather (not the MMA) bounds these kernels, so latency is hidden by co-resident
-  // CTAs: aim at 4 CTAs per SM for narrow tiles, 3 up to N=128, 2 beyond (TMEM: CTAs x columns <= 512),
-  // and give each CTA as many stages as its share of the shared memory holds.
+  // n tiling + weight ring depth
   const int kUsable = 227 * 1024, book = (int)sizeof(Book) + 1024 + 1024;
-  int target = pl->BLOCK_N <= 64 ? 4 : (pl->BLOCK_N <= 128 ? 3 : 2);
-  int st = 0;
-  for (; target >= 1 && st < 1; --target) {
-    int share = kUsable / target - book;
-    if (share < staging) continue;
-    st = share / pl->stage_bytes;
+  const int n_pad = (c.Cout + 15) / 16 * 16;
+  int max_n = c.epi == TC_EPI_LSTM ? c.Cout : 256;
+  for (;;) {
+    pl->n_tiles = (n_pad + max_n - 1) / max_n;
+    pl->BLOCK_N = c.epi == TC_EPI_LSTM ? c.Cout : ((n_pad + pl->n_tiles - 1) / pl->n_tiles + 15) / 16 * 16;
+    pl->b_stage_bytes = pl->NS * pl->BLOCK_N * 128;
+    int st = (kUsable - book - region_bytes) / pl->b_stage_bytes;
+    const int want = pl->KB < 3 ? pl->KB : 3;
+    if (st >= want || max_n <= 32 || c.epi == TC_EPI_LSTM) {
+      if (st > kMaxBStages) st = kMaxBStages;
+      if (st > pl->KB) st = pl->KB;
+      FOV_CHECK_ARG(st >= 1, "tile does not fit shared memory");
+      pl->b_stages = st;
+      break;
+    }
+    max_n /= 2;
   }
-  if (st > 2 && pl->BLOCK_N <= 64) st = 2;
-  if (st > kMaxStages) st = kMaxStages;
-  if (st > pl->KB) st = pl->KB;
-  if (st < 1) st = 1;
-  pl->stages = st;
-  pl->data_bytes = st * pl->stage_bytes > staging ? st * pl->stage_bytes : staging;
+  // several CTAs per SM hide the load latency of short K loops: do not take more ring slots than needed
+  if (pl->KB <= 6 && pl->b_stages > 2) pl->b_stages = 2;
+  pl->tmem_cols = (int)tmem_cols_for(pl->BLOCK_N);
+  pl->b_off = region_bytes;
+  pl->data_bytes = region_bytes + pl->b_stages * pl->b_stage_bytes;
+  if (pl->data_bytes < staging) pl->data_bytes = staging;
   pl->data_bytes = (pl->data_bytes + 1023) / 1024 * 1024;
   pl->smem_bytes = (size_t)pl->data_bytes + sizeof(Book) + 1024;
   FOV_CHECK_ARG(pl->smem_bytes <= (size_t)kUsable, "tile does not fit shared memory");
@@ -543,23 +679,35 @@ int pick_vec(const TcSeg& g) {
 
 template <int NS, int EPI>
 int launch_conv(const DevParams& dp, const Plan& pl, cudaStream_t st) {
-  static size_t configured = 0;
-  if (pl.smem_bytes > configured) {
+  static bool configured = false;
+  if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<NS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(227 * 1024));
     if (e != cudaSuccess) {
       fov_set_error("tc_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return FOV_ERR_CUDA;
     }
-    configured = 227 * 1024;
+    configured = true;
   }
-  dim3 grid((unsigned)((dp.M + BLOCK_M - 1) / BLOCK_M), (unsigned)pl.n_tiles);
+  dim3 grid((unsigned)((pl.total_pos + BLOCK_M - 1) / BLOCK_M), (unsigned)pl.n_tiles);
   tc_conv_kernel<NS, EPI><<<grid, kThreads, pl.smem_bytes, st>>>(dp);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
 
 }  // namespace
+
+static int g_tc_debug = 0;
+// diagnostics (not part of include/fov360.h): per-CTA phase timestamps of the next conv launches
+extern "C" void fov_debug_timeline_enable(int on) { g_tc_debug = on; }
+extern "C" int fov_debug_timeline_read(unsigned long long* out, int n_words) {
+  return (int)cudaMemcpyFromSymbol(out, g_tc_timeline, sizeof(unsigned long long) * (size_t)n_words);
+}
+
+bool tc_conv_supported(const TcConv& c) {
+  Plan pl;
+  return make_plan(c, &pl) == FOV_OK;
+}
 
 size_t tc_conv_ws_bytes(const TcConv& c) {
   Plan pl;
@@ -577,7 +725,7 @@ int tc_conv_pack(const TcConv& c, cudaStream_t st) {
   pp.out = reinterpret_cast<uint8_t*>(((uintptr_t)c.ws + 255) & ~(uintptr_t)255);
   for (int s = 0; s < c.nseg; ++s) {
     FOV_CHECK_ARG(c.seg[s].w != nullptr, "NULL weights");
-    pp.seg[s] = PackSeg{c.seg[s].w, c.seg[s].Cin, pl.Cin_p[s], pl.taps[s], pl.k_begin[s], c.seg[s].w_mode};
+    pp.seg[s] = PackSeg{c.seg[s].w, c.seg[s].Cin, pl.sp[s].Cin_p, pl.sp[s].taps, pl.sp[s].k_begin, c.seg[s].w_mode};
   }
   const long long total = (long long)(pl.ws_bytes / 16);
   long long blocks = (total + 255) / 256;
@@ -595,28 +743,50 @@ int tc_conv_run(const TcConv& c, cudaStream_t st) {
   if (!c.prepacked && (rc = tc_conv_pack(c, st))) return rc;
 
   DevParams dp{};
-  dp.nseg = c.nseg;
+  dp.nseg = c.nseg; dp.mode_b = pl.mode_b; dp.dbg = g_tc_debug;
   for (int s = 0; s < c.nseg; ++s) {
     const TcSeg& g = c.seg[s];
+    const SegPlan& sp = pl.sp[s];
+    DevSeg& d = dp.seg[s];
     // g.x == NULL: the segment reads as zeros (ConvLSTM step 0 with a zero initial state)
-    dp.seg[s] = DevSeg{g.x, g.pix_stride, g.Cin, pl.Cin_p[s], g.kw, pl.taps[s], g.dil_h, g.dil_w,
-                       g.pad_h, g.pad_w, pl.k_begin[s], pick_vec(g)};
-    dp.x_outer[s] = g.img_outer; dp.x_inner[s] = g.img_inner;
+    d.x = g.x; d.outer = g.img_outer; d.inner = g.img_inner; d.pix_stride = g.pix_stride;
+    d.Cin = g.Cin; d.Cin_p = sp.Cin_p; d.cp_log2 = sp.cp_log2; d.cw = sp.cw; d.nch = sp.nch; d.lpr_log2 = sp.lpr_log2;
+    d.kw = g.kw; d.taps = sp.taps; d.dil_h = g.dil_h; d.dil_w = g.dil_w; d.pad_h = g.pad_h; d.pad_w = g.pad_w;
+    d.k_begin = sp.k_begin; d.vec = pick_vec(g);
+    d.minshift = sp.minshift; d.R = sp.R; d.region_off = sp.region_off; d.nbuf = sp.nbuf;
+    d.row_bytes = sp.row_bytes; d.term_bytes = sp.term_bytes;
+    d.swz_mask = sp.row_bytes == 128 ? 7 : (sp.row_bytes == 64 ? 3 : 1);
+    const uint32_t layout = sp.row_bytes == 128 ? 2u : (sp.row_bytes == 64 ? 4u : 6u);
+    d.desc_hi = ((uint32_t)(8 * sp.row_bytes) >> 4) | (1u << 14) | (layout << 29);
+    // the staging tables hold 32-bit element offsets
+    const long long span = (long long)((c.N_img + c.T_inner - 1) / c.T_inner) * (g.img_outer > 0 ? g.img_outer : 1) +
+                           (long long)c.T_inner * (g.img_inner > 0 ? g.img_inner : 0) +
+                           (long long)c.H * c.W * g.pix_stride;
+    FOV_CHECK_ARG(span < (1LL << 31), "activation tensor too large for 32-bit offsets");
   }
-  dp.H = c.H; dp.W = c.W; dp.HW = c.H * c.W; dp.T_inner = c.T_inner;
-  dp.M = (long long)c.N_img * c.H * c.W;
-  dp.KB = pl.KB; dp.Cout = c.Cout; dp.BLOCK_N = pl.BLOCK_N; dp.stages = pl.stages; dp.tmem_cols = pl.tmem_cols;
-  dp.stage_bytes = pl.stage_bytes; dp.data_bytes = pl.data_bytes;
+  dp.H = c.H; dp.W = c.W; dp.Hp = pl.Hp; dp.Wp = pl.Wp; dp.PLh = pl.PLh; dp.PLw = pl.PLw; dp.HpWp = pl.Hp * pl.Wp;
+  dp.T_inner = c.T_inner; dp.N_img = c.N_img; dp.total_pos = (int)pl.total_pos;
+  dp.K_total = pl.K_total; dp.KB = pl.KB; dp.Cout = c.Cout; dp.BLOCK_N = pl.BLOCK_N; dp.b_stages = pl.b_stages;
+  dp.tmem_cols = pl.tmem_cols; dp.b_off = pl.b_off; dp.b_stage_bytes = pl.b_stage_bytes; dp.data_bytes = pl.data_bytes;
   dp.wpk = reinterpret_cast<const uint8_t*>(((uintptr_t)c.ws + 255) & ~(uintptr_t)255);
   dp.bias = c.bias;
+  auto span_ok = [&](long long outer, long long inner, long long pix_stride) {
+    return (long long)((c.N_img + c.T_inner - 1) / c.T_inner) * (outer > 0 ? outer : 1) + (long long)c.T_inner * inner +
+               (long long)c.H * c.W * pix_stride < (1LL << 31);
+  };
   if (c.epi == TC_EPI_CONV) {
     FOV_CHECK_ARG(c.y != nullptr, "NULL output");
+    FOV_CHECK_ARG(span_ok(c.y_outer, c.y_inner, c.y_pix_stride), "output tensor too large for 32-bit offsets");
     dp.y = c.y; dp.y_outer = c.y_outer; dp.y_inner = c.y_inner; dp.y_pix_stride = c.y_pix_stride;
     dp.act = c.act; dp.beta = c.beta;
     dp.vec_out = ((uintptr_t)c.y % 16 == 0) && (c.y_pix_stride % 4 == 0) && (c.y_outer % 4 == 0) &&
                  (c.y_inner % 4 == 0) && (c.Cout % 4 == 0) && (!c.bias || (uintptr_t)c.bias % 16 == 0);
   } else {
     FOV_CHECK_ARG(c.bias && c.c_out && c.h_out, "NULL LSTM epilogue pointer");
+    FOV_CHECK_ARG(span_ok(c.c_outer, c.c_inner, c.Cout / 4) && span_ok(c.h_outer, c.h_inner, c.h_pix_stride) &&
+                      span_ok(c.g_outer, c.g_inner, c.Cout) && span_ok(c.cp_outer, c.cp_inner, c.Cout / 4) &&
+                      (long long)c.N_img * c.H * c.W * (c.Cout / 4) < (1LL << 31),
+                  "state tensors too large for 32-bit offsets");
     dp.F = c.Cout / 4; dp.rec_act = c.rec_act;
     dp.c_prev = c.c_prev; dp.cp_outer = c.cp_outer; dp.cp_inner = c.cp_inner;
     dp.c_out = c.c_out; dp.c_outer = c.c_outer; dp.c_inner = c.c_inner;
@@ -655,15 +825,27 @@ int conv_from_cfg(const fov_conv_cfg* cfg, int math, TcConv* c) {
   c->epi = TC_EPI_CONV;
   return FOV_OK;
 }
+void fwd_seg(const fov_conv_cfg* cfg, TcConv* c) {
+  TcSeg& g = c->seg[0];
+  g.img_outer = cfg->x_img_stride; g.img_inner = 0; g.pix_stride = cfg->x_pix_stride;
+  g.Cin = cfg->Cin; g.kh = cfg->kh; g.kw = cfg->kw; g.dil_h = cfg->dil_h; g.dil_w = cfg->dil_w;
+  g.pad_h = cfg->pad_h; g.pad_w = cfg->pad_w; g.w_mode = 0;
+  c->Cout = cfg->Cout;
+}
+void bwd_seg(const fov_conv_cfg* cfg, TcConv* c) {
+  TcSeg& g = c->seg[0];
+  g.img_outer = cfg->y_img_stride; g.img_inner = 0; g.pix_stride = cfg->y_pix_stride;
+  g.Cin = cfg->Cout; g.kh = cfg->kh; g.kw = cfg->kw; g.dil_h = cfg->dil_h; g.dil_w = cfg->dil_w;
+  g.pad_h = (cfg->kh - 1) * cfg->dil_h - cfg->pad_h; g.pad_w = (cfg->kw - 1) * cfg->dil_w - cfg->pad_w;
+  g.w_mode = 1;
+  c->Cout = cfg->Cin;
+}
 }  // namespace
 
 extern "C" size_t fov_conv_tc_ws_bytes(const fov_conv_cfg* cfg, int math, int bwd_data) {
   TcConv c;
   if (conv_from_cfg(cfg, math, &c)) return 0;
-  TcSeg& g = c.seg[0];
-  g.kh = cfg->kh; g.kw = cfg->kw; g.dil_h = cfg->dil_h; g.dil_w = cfg->dil_w;
-  g.Cin = bwd_data ? cfg->Cout : cfg->Cin;
-  c.Cout = bwd_data ? cfg->Cin : cfg->Cout;
+  if (bwd_data) bwd_seg(cfg, &c); else fwd_seg(cfg, &c);
   return tc_conv_ws_bytes(c);
 }
 
@@ -673,11 +855,9 @@ extern "C" int fov_conv2d_fwd_tc(const fov_conv_cfg* cfg, const float* x, const 
   int rc = conv_from_cfg(cfg, math, &c);
   if (rc) return rc;
   FOV_CHECK_ARG(x && w && y && ws, "NULL pointer");
-  TcSeg& g = c.seg[0];
-  g.x = x; g.img_outer = cfg->x_img_stride; g.img_inner = 0; g.pix_stride = cfg->x_pix_stride;
-  g.Cin = cfg->Cin; g.kh = cfg->kh; g.kw = cfg->kw; g.dil_h = cfg->dil_h; g.dil_w = cfg->dil_w;
-  g.pad_h = cfg->pad_h; g.pad_w = cfg->pad_w; g.w = w; g.w_mode = 0;
-  c.Cout = cfg->Cout; c.ws = ws;
+  fwd_seg(cfg, &c);
+  c.seg[0].x = x; c.seg[0].w = w;
+  c.ws = ws;
   c.bias = bias; c.y = y; c.y_outer = cfg->y_img_stride; c.y_inner = 0; c.y_pix_stride = cfg->y_pix_stride;
   c.act = cfg->act; c.beta = cfg->beta;
   return tc_conv_run(c, (cudaStream_t)stream);
@@ -689,12 +869,9 @@ extern "C" int fov_conv2d_bwd_data_tc(const fov_conv_cfg* cfg, const float* dy, 
   int rc = conv_from_cfg(cfg, math, &c);
   if (rc) return rc;
   FOV_CHECK_ARG(dy && w && dx && ws, "NULL pointer");
-  TcSeg& g = c.seg[0];
-  g.x = dy; g.img_outer = cfg->y_img_stride; g.img_inner = 0; g.pix_stride = cfg->y_pix_stride;
-  g.Cin = cfg->Cout; g.kh = cfg->kh; g.kw = cfg->kw; g.dil_h = cfg->dil_h; g.dil_w = cfg->dil_w;
-  g.pad_h = (cfg->kh - 1) * cfg->dil_h - cfg->pad_h; g.pad_w = (cfg->kw - 1) * cfg->dil_w - cfg->pad_w;
-  g.w = w; g.w_mode = 1;
-  c.Cout = cfg->Cin; c.ws = ws;
+  bwd_seg(cfg, &c);
+  c.seg[0].x = dy; c.seg[0].w = w;
+  c.ws = ws;
   c.bias = nullptr; c.y = dx; c.y_outer = cfg->x_img_stride; c.y_inner = 0; c.y_pix_stride = cfg->x_pix_stride;
   c.act = FOV_ACT_LINEAR; c.beta = cfg->beta;
   return tc_conv_run(c, (cudaStream_t)stream);

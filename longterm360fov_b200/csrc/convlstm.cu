@@ -37,15 +37,6 @@ Geo geo(const fov_convlstm_cfg* c) {
   return g;
 }
 
-// The fused tensor-core step covers the filter counts of the reference models (32/16/8, also 64)
-// with 16-byte aligned hidden-state rows; other shapes run the fp32 CUDA-core kernels.
-bool tc_step_ok(const fov_convlstm_cfg* c) {
-  if (c->math == 0) return false;
-  const int F = c->F;
-  if (!(F == 8 || F == 16 || F == 32 || F == 64)) return false;
-  return c->h_pix_stride % 4 == 0 && c->h_b_stride % 4 == 0 && c->h_t_stride % 4 == 0;
-}
-
 fov_conv_cfg input_conv_cfg(const fov_convlstm_cfg* c) {
   fov_conv_cfg k{};
   k.H = c->H; k.W = c->W; k.Cin = c->Cin; k.Cout = 4 * c->F;
@@ -112,6 +103,21 @@ TcConv in_bwd_conv(const fov_convlstm_cfg* c, const float* kernel, const Geo& g)
   k.y_outer = c->x_b_stride; k.y_inner = c->x_t_stride; k.y_pix_stride = c->x_pix_stride;
   k.act = FOV_ACT_LINEAR;
   return k;
+}
+
+// The fused tensor-core step covers the filter counts of the reference models (8/16/32/64) with
+// <= 64 input channels and 16-byte aligned hidden-state rows; other shapes run the fp32 CUDA-core kernels.
+bool tc_step_ok(const fov_convlstm_cfg* c) {
+  if (c->math == 0) return false;
+  const int F = c->F;
+  if (!(F == 8 || F == 16 || F == 32 || F == 64)) return false;
+  if (!(c->h_pix_stride % 4 == 0 && c->h_b_stride % 4 == 0 && c->h_t_stride % 4 == 0)) return false;
+  fov_convlstm_io io{};
+  const Geo g = geo(c);
+  const bool ok = tc_conv_supported(step_conv(c, &io, g)) && tc_conv_supported(rec_bwd_conv(c, nullptr, g)) &&
+                  tc_conv_supported(in_bwd_conv(c, nullptr, g));
+  fov_set_error("");
+  return ok;
 }
 
 }  // namespace

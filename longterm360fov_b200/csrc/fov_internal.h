@@ -72,6 +72,7 @@ struct TcConv {
   float* gates_out;    long long g_outer, g_inner;     // optional activated gates (pixel stride 4F)
   float *hT, *cT;                                      // optional dense copies (N_img,HW,F)
 };
+bool tc_conv_supported(const TcConv& c);   // shape fits the shifted-tap kernel (no error is recorded)
 size_t tc_conv_ws_bytes(const TcConv& c);
 int tc_conv_pack(const TcConv& c, cudaStream_t st);
 int tc_conv_run(const TcConv& c, cudaStream_t st);

@@ -312,6 +312,25 @@ static void test_convlstm(const char* name, int B, int T, int H, int W, int Cin,
   if (h0) { cudaFree(h0); cudaFree(c0); }
 }
 
+extern "C" void fov_debug_timeline_enable(int on);
+extern "C" int fov_debug_timeline_read(unsigned long long* out, int n_words);
+static void print_timeline(const char* what) {
+  std::vector<unsigned long long> t(256 * 8);
+  fov_debug_timeline_read(t.data(), 256 * 8);
+  double ph[4] = {0, 0, 0, 0};
+  int n = 0;
+  unsigned long long tmin = ~0ull, tmax = 0;
+  for (int c = 0; c < 148; ++c) {
+    const unsigned long long* r = &t[c * 8];
+    if (r[4] <= r[0]) continue;
+    ph[0] += (double)(r[1] - r[0]); ph[1] += (double)(r[2] - r[1]); ph[2] += (double)(r[3] - r[2]); ph[3] += (double)(r[4] - r[3]);
+    ++n;
+  }
+  if (n)
+    printf("  timeline %-22s (cycles, mean of %d CTAs): setup %.0f | stage activations %.0f | to accumulator ready %.0f | epilogue %.0f\n",
+           what, n, ph[0] / n, ph[1] / n, ph[2] / n, ph[3] / n);
+}
+
 // a handful of bench-sized launches (math = bf16x2 only) for `ncu --set full`
 static void profile_mode() {
   const int B = 4096, math = 2;
@@ -329,6 +348,14 @@ static void profile_mode() {
       FK(fov_conv2d_bwd_weight_tc(&c, x, y, gw, gb, math, nullptr));
     }
     CK(cudaDeviceSynchronize());
+    fov_debug_timeline_enable(1);
+    FK(fov_conv2d_fwd_tc(&c, x, w, b, y, ws, math, nullptr));
+    CK(cudaDeviceSynchronize());
+    print_timeline("conv fwd 32->128");
+    FK(fov_conv2d_bwd_data_tc(&c, y, w, dx, ws2, math, nullptr));
+    CK(cudaDeviceSynchronize());
+    print_timeline("conv bwd-data 128->32");
+    fov_debug_timeline_enable(0);
   }
   {   // fused ConvLSTM step, layer 0 of config 2 (training: saves the activated gates)
     const int T = 2, Cin = 6, F = 32;
@@ -345,6 +372,11 @@ static void profile_mode() {
     void* wsf; CK(cudaMalloc(&wsf, fov_convlstm_fwd_ws_bytes(&c) + 256)); io.ws = (float*)wsf;
     for (int i = 0; i < 2; ++i) FK(fov_convlstm_fwd(&c, &io, nullptr));
     CK(cudaDeviceSynchronize());
+    fov_debug_timeline_enable(1);
+    FK(fov_convlstm_fwd(&c, &io, nullptr));
+    CK(cudaDeviceSynchronize());
+    print_timeline("fused LSTM step (t=1)");
+    fov_debug_timeline_enable(0);
   }
   printf("profile mode done\n");
 }

@@ -68,6 +68,67 @@ __global__ void probe(const __nv_bfloat16* Afull, const __nv_bfloat16* Bm, float
   if (tid < 32) tmem_dealloc(td, 32);
 }
 
+// Second probe: the same question for 64-byte and 32-byte swizzled K-major tiles (rows of 32 / 16 bf16),
+// data written with the absolute-address swizzle  phys = a ^ (((a >> 7) & mask) << 4).
+__global__ void probe_narrow(const __nv_bfloat16* Afull, const __nv_bfloat16* Bm, float* D, int shift, int row_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint8_t* As = smem;
+  uint8_t* Bs = smem + 32 * 1024;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tptr;
+  const int tid = threadIdx.x;
+  const int cpr = row_bytes / 16;                       // 16-byte chunks per row: 4 (SW64) or 2 (SW32)
+  const uint32_t mask = row_bytes == 64 ? 3u : 1u;
+  const uint32_t layout = row_bytes == 64 ? 4u : 6u;    // SWIZZLE_64B / SWIZZLE_32B
+  const int kelems = row_bytes / 2;                     // K per row
+  for (int idx = tid; idx < ROWS * cpr; idx += blockDim.x) {
+    const int r = idx / cpr, c = idx % cpr;
+    uint4 v = *reinterpret_cast<const uint4*>(Afull + r * 64 + c * 8);
+    const uint32_t a = (uint32_t)(r * row_bytes + c * 16);
+    *reinterpret_cast<uint4*>(As + (a ^ (((a >> 7) & mask) << 4))) = v;
+  }
+  for (int idx = tid; idx < N * cpr; idx += blockDim.x) {
+    const int r = idx / cpr, c = idx % cpr;
+    uint4 v = *reinterpret_cast<const uint4*>(Bm + r * 64 + c * 8);
+    const uint32_t a = (uint32_t)(r * row_bytes + c * 16);
+    *reinterpret_cast<uint4*>(Bs + (a ^ (((a >> 7) & mask) << 4))) = v;
+  }
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+  if (tid < 32) { tmem_alloc(smem_u32(&tptr), 32); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t td = tptr;
+  if (tid == 0) {
+    const uint32_t idesc = idesc_bf16_f32(128, N, 0, 0);
+    const uint32_t sbo = 8 * row_bytes;
+    auto desc = [&](uint32_t addr) {
+      return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) |
+             ((uint64_t)layout << 61);
+    };
+    for (int k4 = 0; k4 < kelems / 16; ++k4)
+      umma_bf16(td, desc(base + shift * row_bytes + k4 * 32), desc(base + 32 * 1024 + k4 * 32), idesc, k4 > 0);
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  if (tid < 128) {
+    const int warp = tid >> 5;
+    float v[32];
+    tmem_ld16(td + ((uint32_t)(warp * 32) << 16), v);
+    tmem_ld16(td + ((uint32_t)(warp * 32) << 16) + 16, v + 16);
+    tmem_ld_wait();
+    for (int j = 0; j < N; ++j) D[tid * N + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(td, 32);
+}
+
 int main() {
   std::vector<__nv_bfloat16> hA(ROWS * 64), hB(N * 64);
   std::vector<float> fA(ROWS * 64), fB(N * 64);
@@ -99,5 +160,24 @@ int main() {
       }
       printf("\n");
     }
+  cudaFuncSetAttribute(probe_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  for (int rb = 64; rb >= 32; rb /= 2) {
+    printf("K-major SWIZZLE_%dB, absolute-address swizzle, row shifts:", rb);
+    for (int shift = 0; shift <= 12; ++shift) {
+      probe_narrow<<<1, 128, 64 * 1024>>>(dA, dB, dD, shift, rb);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf(" CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+      cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost);
+      double err = 0;
+      for (int i = 0; i < 128; ++i)
+        for (int n = 0; n < N; ++n) {
+          double acc = 0;
+          for (int k = 0; k < rb / 2; ++k) acc += (double)fA[(i + shift) * 64 + k] * fB[n * 64 + k];
+          err = fmax(err, fabs(acc - hD[i * N + n]));
+        }
+      printf(" s%d:%s", shift, err < 1e-3 ? "OK" : "bad");
+    }
+    printf("\n");
+  }
   return 0;
 }
