@@ -25,8 +25,10 @@ using namespace tc;
 constexpr int WG_M = 128;            // k rows per CTA (MMA M)
 constexpr int WG_PIX = 64;           // pixels per pipeline stage (4 MMA K-steps of 16)
 constexpr int WG_GRP = WG_PIX * 128; // bytes of one 64-wide MN group (64 pixel rows x 128 B)
-constexpr int kProd = 256;           // producer threads (warps 0-7)
-constexpr int kThr = 320;            // + table warp (8) + MMA warp (9)
+constexpr int kProd = 512;           // producer threads (warps 0-15)
+constexpr int kTabWarp = 16, kMmaWarp = 17;
+constexpr int kThr = 576;            // + table warp (16) + MMA warp (17)
+constexpr int NA = 4, NBMAX = 4;     // float4 loads per thread per pixel block: x rows / dy rows
 constexpr int kStagesMax = 3;
 constexpr int RS = 36;
 
@@ -35,7 +37,7 @@ struct WgParams {
   const float* dy; long long dy_outer, dy_inner; int dy_pix_stride, Cout, dy_vec;
   int H, W, HW, T_inner, M;
   int BLOCK_N, tmem_cols, stages, stage_bytes, b_term_bytes, data_bytes;
-  int nblocks, blocks_per_split;
+  int nblocks, blocks_per_split, dbg;
   float* gw; float* gbias;
 };
 
@@ -51,7 +53,13 @@ struct Book {
   uint32_t tmem_ptr;
 };
 
-template <int NS>
+// loads of out-of-range taps / rows are redirected here, so the gather needs no predicated loads
+__device__ float4 g_zero_page[4];
+
+// diagnostics: cycles CTA (0,0,0) spent per producer phase / in the MMA thread (fov_debug_wgrad_read)
+__device__ unsigned long long g_wg_timeline[8];
+
+template <int NS, bool FAST>
 __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -73,7 +81,7 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
     const int tap = k / p.Cin_p, ci = k - tap * p.Cin_p;
     bk->dstrow[tid] = (tap < p.taps && ci < p.Cin) ? tap * p.Cin + ci : -1;
   }
-  if (warp == 9 && lane == 0) {
+  if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&bk->full[s]), kProd);
       mbar_init(smem_u32(&bk->empty[s]), 1);
@@ -82,7 +90,7 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
     mbar_init(smem_u32(&bk->tmem_full), 1);
     fence_mbar_init();
   }
-  if (warp == 8) {
+  if (warp == kTabWarp) {
     tmem_alloc(smem_u32(&bk->tmem_ptr), (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
@@ -93,13 +101,13 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
 
   float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
   const int f4 = p.BLOCK_N >> 2;          // float4 per dY row of this n tile (4..32)
-  const int nb = (WG_PIX * f4) / kProd;   // dY loads per thread per block (1..8)
+  const int nb = (WG_PIX * f4 + kProd - 1) / kProd;   // dY loads per thread per block (1..4)
   const int b_c4 = tid % f4;              // fixed float4 column of this thread
   const int b_row0 = tid / f4, b_rstep = kProd / f4;
 
-  if (warp < 8) {
+  if (warp < kProd / 32) {
     // ---------------- producers ----------------
-    const int q = tid & 31, rsub = tid >> 5;           // A': float4 slot along k, row phase
+    const int q = tid & 31, rsub = tid >> 5;           // A': float4 slot along k, row phase (0..15)
     const int k = k_tile * WG_M + q * 4;
     const int tap = k / p.Cin_p, ci = k - tap * p.Cin_p;
     int a_nvalid = (tap < p.taps) ? (p.Cin - ci) : 0;
@@ -107,20 +115,40 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
     const int ty = tap / p.kw, tx = tap - ty * p.kw;
     const int tdy = ty * p.dil_h - p.pad_h, tdx = tx * p.dil_w - p.pad_w;
     const int a_delta = (tdy * p.W + tdx) * p.x_pix_stride + ci;
-    // rows are 8*j + rsub (A') and b_row0 + j*b_rstep with b_rstep % 8 == 0 (B'): constant swizzle phase
+    // rows are 16*j + rsub (A') and b_row0 + j*b_rstep with b_rstep % 8 == 0 (B'): constant swizzle phase
     const uint32_t a_off = (uint32_t)(q >> 4) * WG_GRP + (uint32_t)(q & 1) * 8u + (uint32_t)rsub * 128u +
-                           ((uint32_t)(((q & 15) >> 1) ^ rsub) << 4);
+                           ((uint32_t)(((q & 15) >> 1) ^ (rsub & 7)) << 4);
     const int bcol = n0 + b_c4 * 4;
     int b_nvalid = p.Cout - bcol;
     b_nvalid = b_nvalid < 0 ? 0 : (b_nvalid > 4 ? 4 : b_nvalid);
     const uint32_t b_off = (uint32_t)(b_c4 >> 4) * WG_GRP + (uint32_t)(b_c4 & 1) * 8u + (uint32_t)b_row0 * 128u +
                            ((uint32_t)(((b_c4 & 15) >> 1) ^ (b_row0 & 7)) << 4);
 
-    auto issue = [&](int stage, float4 (&va)[8], float4 (&vb)[8]) {
+    // FAST (every tensor 16-byte aligned): unconditional float4 loads, out-of-range ones redirected to a
+    // zero page, so all loads of a block are in flight at once and nothing is merged after them
+    const float* zp = reinterpret_cast<const float*>(g_zero_page);
+    auto issue = [&](int stage, float4 (&va)[NA], float4 (&vb)[NBMAX]) {
       const RowTab& t = bk->tab[stage];
+      if (FAST) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = j * 8 + rsub;
+        for (int j = 0; j < NA; ++j) {
+          const int r = j * 16 + rsub;
+          const int pyx = t.pyx[r];
+          const unsigned yy = (unsigned)((pyx >> 16) + tdy), xx = (unsigned)((pyx & 0xffff) + tdx);
+          const bool ok = a_nvalid > 0 && yy < (unsigned)p.H && xx < (unsigned)p.W;
+          va[j] = __ldg(reinterpret_cast<const float4*>(ok ? t.xp[r] + a_delta : zp));
+        }
+#pragma unroll
+        for (int j = 0; j < NBMAX; ++j) {
+          const int r = b_row0 + j * b_rstep;
+          const bool ok = j < nb && r < WG_PIX && b_nvalid > 0 && (t.pyx[r & (WG_PIX - 1)] >> 16) != 0x4000;
+          vb[j] = __ldg(reinterpret_cast<const float4*>(ok ? t.dyp[r & (WG_PIX - 1)] + bcol : zp));
+        }
+        return;
+      }
+#pragma unroll
+      for (int j = 0; j < NA; ++j) {
+        const int r = j * 16 + rsub;
         const int pyx = t.pyx[r];
         const unsigned yy = (unsigned)((pyx >> 16) + tdy), xx = (unsigned)((pyx & 0xffff) + tdx);
         va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -128,27 +156,27 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
           va[j] = ldg_vec4(t.xp[r] + a_delta, a_nvalid, p.x_vec);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < NBMAX; ++j) {
         vb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < nb) {
+        if (j < nb && b_row0 + j * b_rstep < WG_PIX) {
           const int r = b_row0 + j * b_rstep;
           if (b_nvalid > 0 && (t.pyx[r] >> 16) != 0x4000) vb[j] = ldg_vec4(t.dyp[r] + bcol, b_nvalid, p.dy_vec);
         }
       }
     };
-    auto store = [&](int stage, const float4 (&va)[8], const float4 (&vb)[8]) {
+    auto store = [&](int stage, const float4 (&va)[NA], const float4 (&vb)[NBMAX]) {
       uint8_t* a_tile = smem + (size_t)stage * p.stage_bytes;
       uint8_t* b_tile = a_tile + NS * A_TERM;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < NA; ++j) {
         uint2 pk[NS];
         split4<NS>(va[j], pk);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(a_tile + s * A_TERM + j * 1024 + a_off) = pk[s];
+        for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(a_tile + s * A_TERM + j * 2048 + a_off) = pk[s];
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < nb) {
+      for (int j = 0; j < NBMAX; ++j) {
+        if (j < nb && b_row0 + j * b_rstep < WG_PIX) {
           uint2 pk[NS];
           split4<NS>(vb[j], pk);
 #pragma unroll
@@ -160,7 +188,7 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&bk->full[stage]));
     };
-    float4 a0[8], b0[8], a1[8], b1[8];
+    float4 a0[NA], b0[NBMAX], a1[NA], b1[NBMAX];
     mbar_wait(smem_u32(&bk->tabrdy[0]), 0);
     issue(0, a0, b0);
     for (int i = 0; i < nblk; i += 2) {
@@ -180,7 +208,8 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
         store((i + 1) % S, a1, b1);
       }
     }
-  } else if (warp == 8) {
+
+  } else if (warp == kTabWarp) {
     // ---------------- row-table builder: pixel -> (addresses, y, x) for each stage ----------------
     // lane owns rows lane and lane+32; their pixel advances by 64 per block, tracked with carries
     // (one division set at the start, none in the loop).
@@ -229,9 +258,15 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16_f32(WG_M, p.BLOCK_N, 1, 1);
+      const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      long long t_full = 0;
+      const long long t_begin = clock64();
+      if (dbg) g_wg_timeline[3] = (unsigned long long)nblk;
       for (int i = 0; i < nblk; ++i) {
         const int stage = i % S;
+        const long long tw = clock64();
         mbar_wait(smem_u32(&bk->full[stage]), (uint32_t)(i / S) & 1u);
+        t_full += clock64() - tw;
         tc_fence_after();
         const uint32_t a_base = base + (uint32_t)stage * p.stage_bytes;
         const uint32_t b_base = a_base + NS * A_TERM;
@@ -253,6 +288,7 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
         umma_commit(smem_u32(&bk->empty[stage]));
       }
       umma_commit(smem_u32(&bk->tmem_full));
+      if (dbg) { g_wg_timeline[4] = (unsigned long long)t_full; g_wg_timeline[5] = (unsigned long long)(clock64() - t_begin); }
     }
   }
 
@@ -281,7 +317,7 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
       __syncwarp();
     }
   }
-  if (warp < 8 && p.gbias && k_tile == 0) {
+  if (warp < kProd / 32 && p.gbias && k_tile == 0) {
     const int bcol = n0 + b_c4 * 4;
     if (bcol < p.Cout) atomicAdd(p.gbias + bcol, bsum.x);
     if (bcol + 1 < p.Cout) atomicAdd(p.gbias + bcol + 1, bsum.y);
@@ -291,7 +327,7 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
+  if (warp == kTabWarp) tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
 }
 
 int vec_of(const void* ptr, long long a, long long b, long long c, long long d) {
@@ -303,23 +339,29 @@ int vec_of(const void* ptr, long long a, long long b, long long c, long long d) 
   return 1;
 }
 
-template <int NS>
+template <int NS, bool FAST>
 int launch(const WgParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<NS, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       fov_set_error("tc_wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return FOV_ERR_CUDA;
     }
     configured = true;
   }
-  tc_wgrad_kernel<NS><<<grid, kThr, smem, st>>>(p);
+  tc_wgrad_kernel<NS, FAST><<<grid, kThr, smem, st>>>(p);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
 
 }  // namespace
+
+static int g_wg_debug = 0;
+extern "C" void fov_debug_wgrad_enable(int on) { g_wg_debug = on; }
+extern "C" int fov_debug_wgrad_read(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_wg_timeline, sizeof(unsigned long long) * 8);
+}
 
 int tc_wgrad_run(const TcWgrad& c, cudaStream_t st) {
   FOV_CHECK_ARG(c.math >= 1 && c.math <= 3, "math must be 1..3 bf16 terms");
@@ -335,7 +377,7 @@ int tc_wgrad_run(const TcWgrad& c, cudaStream_t st) {
   p.dy = c.dy; p.dy_outer = c.dy_outer; p.dy_inner = c.dy_inner; p.dy_pix_stride = c.dy_pix_stride; p.Cout = c.Cout;
   p.dy_vec = vec_of(c.dy, c.dy_outer, c.dy_inner, c.dy_pix_stride, c.Cout);
   p.H = c.H; p.W = c.W; p.HW = c.H * c.W; p.T_inner = c.T_inner; p.M = (int)M;
-  p.gw = c.gw; p.gbias = c.gbias;
+  p.gw = c.gw; p.gbias = c.gbias; p.dbg = g_wg_debug;
   // n tile: 16/32/64/128 wide (the dY row of a thread must keep a fixed float4 column)
   int bn = 16;
   while (bn < c.Cout && bn < 128) bn <<= 1;
@@ -363,9 +405,15 @@ int tc_wgrad_run(const TcWgrad& c, cudaStream_t st) {
   p.blocks_per_split = (int)((p.nblocks + want - 1) / want);
   const int splits = (p.nblocks + p.blocks_per_split - 1) / p.blocks_per_split;
   dim3 grid((unsigned)k_tiles, (unsigned)n_tiles, (unsigned)splits);
-  if (c.math == 1) return launch<1>(p, grid, smem, st);
-  if (c.math == 2) return launch<2>(p, grid, smem, st);
-  return launch<3>(p, grid, smem, st);
+  const bool fast = p.x_vec == 4 && p.dy_vec == 4 && p.Cout % 4 == 0;
+  if (fast) {
+    if (c.math == 1) return launch<1, true>(p, grid, smem, st);
+    if (c.math == 2) return launch<2, true>(p, grid, smem, st);
+    return launch<3, true>(p, grid, smem, st);
+  }
+  if (c.math == 1) return launch<1, false>(p, grid, smem, st);
+  if (c.math == 2) return launch<2, false>(p, grid, smem, st);
+  return launch<3, false>(p, grid, smem, st);
 }
 
 extern "C" int fov_conv2d_bwd_weight_tc(const fov_conv_cfg* cfg, const float* x, const float* dy, float* gw,

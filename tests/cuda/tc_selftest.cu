@@ -312,6 +312,8 @@ static void test_convlstm(const char* name, int B, int T, int H, int W, int Cin,
   if (h0) { cudaFree(h0); cudaFree(c0); }
 }
 
+extern "C" void fov_debug_wgrad_enable(int on);
+extern "C" int fov_debug_wgrad_read(unsigned long long* out);
 extern "C" void fov_debug_timeline_enable(int on);
 extern "C" int fov_debug_timeline_read(unsigned long long* out, int n_words);
 static void print_timeline(const char* what) {
@@ -356,6 +358,13 @@ static void profile_mode() {
     CK(cudaDeviceSynchronize());
     print_timeline("conv bwd-data 128->32");
     fov_debug_timeline_enable(0);
+    fov_debug_wgrad_enable(1);
+    FK(fov_conv2d_bwd_weight_tc(&c, x, y, gw, gb, math, nullptr));
+    CK(cudaDeviceSynchronize());
+    fov_debug_wgrad_enable(0);
+    unsigned long long wt[8];
+    fov_debug_wgrad_read(wt);
+    printf("  wgrad CTA0: %llu blocks; MMA thread cycles: wait-full %llu of %llu total\n", wt[3], wt[4], wt[5]);
   }
   {   // fused ConvLSTM step, layer 0 of config 2 (training: saves the activated gates)
     const int T = 2, Cin = 6, F = 32;
