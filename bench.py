@@ -33,6 +33,10 @@ UNIT = "sequences/s"
 FWD_FLOP_PER_SEQ = 82_307_200
 TRAIN_FLOP_PER_SEQ = 3 * FWD_FLOP_PER_SEQ
 NUM_USER = 34
+# arithmetic type of the GEMM/conv path per --compute mode (fp32 accumulation everywhere; gates, cell state,
+# losses and optimiser in fp32)
+DTYPE_OF = {"fp32": "fp32", "bf16": "bf16", "bf16x2": "bf16x2 (2-term split, fp32-grade)",
+            "bf16x3": "bf16x3 (3-term split)"}
 
 
 def _peaks():
@@ -50,6 +54,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.active = False        # samples are kept only while a timed leg is running
 
     def run(self):
         try:
@@ -62,18 +67,199 @@ class ClockSampler(threading.Thread):
                      "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
                      "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for n, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(n)
-                time.sleep(0.2)
+                if self.active:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for n, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(n)
+                time.sleep(0.02)
         except Exception as e:  # pragma: no cover - NVML missing
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 
     def result(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def _time_cuda(fn, reps=20, warm=3):
+    """Average device time of `fn` (ms) over `reps` back-to-back launches, CUDA events on torch's current
+    stream (the stream the C-ABI calls are given)."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed
+# `ncu --set full` capture (profiles/), keyed by per-GPU batch; None when no capture exists for it.
+NCU_TRAFFIC_BYTES = {}
+
+
+def kernel_rooflines(lib, dev, B, compute, peaks, seq_per_s_per_gpu):
+    """Rooflines of the kernels that dominate the config-2 train step (profiles/: weight gradient ~1/3,
+    fused ConvLSTM step ~1/5, dense GEMMs), at the step's own shapes.  Operands are > L2 (126 MB) or
+    rotated, so every launch streams from HBM."""
+    import ctypes as C
+    import torch
+    from longterm360fov_b200 import _lib
+    math = _lib.MATH[compute]
+    st = torch.cuda.current_stream().cuda_stream
+    W_, F0 = NUM_USER - 1, 32
+    out = []
+
+    # (1) weight gradient of the ConvLSTM-L0 recurrent kernel over all (b,t) pairs: gR[tap,ci,n] +=
+    #     sum_pix h_{t-1}[pix+tap,ci] * dZ_t[pix,n]; M = 5*32 = 160 k-rows, N = 4F = 128, reduction = B*19*33 pixels
+    Nimg = B * 19
+    h = torch.randn(Nimg, 1, W_, F0, device=dev)
+    dz = torch.randn(Nimg, 1, W_, 4 * F0, device=dev) * 0.01
+    gw = torch.zeros(1, 5, F0, 4 * F0, device=dev)
+    cfg = _lib.ConvCfg(Nimg, 1, W_, F0, 4 * F0, 1, 5, 1, 1, 0, 2, W_ * F0, F0, W_ * 4 * F0, 4 * F0, 0, 0.0)
+    if math == 0:
+        fn = lambda: _lib.check(lib.fov_conv2d_bwd_weight(C.byref(cfg), h.data_ptr(), dz.data_ptr(), gw.data_ptr(),
+                                                          None, st))
+        kname = "conv_wgrad_kernel (fp32 SIMT)"
+    else:
+        fn = lambda: _lib.check(lib.fov_conv2d_bwd_weight_tc(C.byref(cfg), h.data_ptr(), dz.data_ptr(),
+                                                             gw.data_ptr(), None, math, st))
+        kname = "tc_wgrad_kernel<%d> (tcgen05, MN-major operands, %d bf16 term(s))" % (math, math)
+    ms = _time_cuda(fn)
+    npix = Nimg * W_
+    byts = npix * (F0 + 4 * F0) * 4 + gw.numel() * 4
+    flop = 2.0 * npix * 160 * 128
+    gbs = byts / (ms * 1e-3) / 1e9
+    main = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+            "traffic": NCU_TRAFFIC_BYTES.get(B),
+            "kernel": kname + ": ConvLSTM-L0 recurrent weight gradient, %d images of 1x%d, Cin=32, Cout=128, k=1x5"
+                      % (Nimg, W_),
+            "algorithmic_bytes_per_launch": byts, "ms_per_launch": ms,
+            "algorithmic_tflops": flop / (ms * 1e-3) / 1e12,
+            "why_hbm": "64 algorithmic FLOP per byte (x3 issued in bf16x2) is below the machine balance of "
+                       "%.0f FLOP/B" % (peaks["bf16"] * 1e3 / peaks["hbm_gbs"]),
+            "peak_is": "%s copy bandwidth (MEASURED_PEAKS.json)" % peaks["which"]}
+    del h, dz, gw
+
+    # (2) fused ConvLSTM-L0 step (implicit GEMM [x_t taps | h_{t-1} taps] x [K;R] + gate algebra + cell update
+    #     in the epilogue), 20 timestep launches of one layer call; bytes = x + h_prev + c_prev + c + h + 4 gates
+    T = 20
+    x = torch.randn(B, T, 1, W_, 6, device=dev)
+    K0 = torch.randn(1, 5, 6, 4 * F0, device=dev) * 0.1
+    R0 = torch.randn(1, 5, F0, 4 * F0, device=dev) * 0.1
+    b0 = torch.zeros(4 * F0, device=dev)
+    hseq = torch.empty(B, T, 1, W_, 56, device=dev)
+    gates = torch.empty(B, T, 1, W_, 4 * F0, device=dev)
+    cseq = torch.empty(B, T, 1, W_, F0, device=dev)
+    hT = torch.empty(B, 1, W_, F0, device=dev)
+    cT = torch.empty(B, 1, W_, F0, device=dev)
+    lcfg = _lib.ConvLstmCfg(B, T, 1, W_, 6, F0, 1, 5, 1, 1, 0, T * W_ * 6, W_ * 6, 6, T * W_ * 56, W_ * 56, 56, 1, math)
+    wsb = lib.fov_convlstm_fwd_ws_bytes(C.byref(lcfg))
+    ws = torch.empty(int(wsb) + 256, dtype=torch.uint8, device=dev) if wsb else None
+    io = _lib.ConvLstmIO(x.data_ptr(), K0.data_ptr(), R0.data_ptr(), b0.data_ptr(), None, None, None,
+                         hseq.data_ptr(), gates.data_ptr(), cseq.data_ptr(), hT.data_ptr(), cT.data_ptr(),
+                         ws.data_ptr() if ws is not None else None)
+    ms = _time_cuda(lambda: _lib.check(lib.fov_convlstm_fwd(C.byref(lcfg), C.byref(io), st)), reps=5, warm=2)
+    npix = B * T * W_
+    byts = npix * (6 + F0 + F0 + F0 + F0 + 4 * F0) * 4
+    flop = 2.0 * npix * 5 * (6 + F0) * 4 * F0
+    gbs = byts / (ms * 1e-3) / 1e9
+    out.append({"kernel": "tc_conv_kernel<%d,LSTM> x%d timesteps: ConvLSTM-L0 forward (training, gates saved)" % (math, T),
+                "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                "ms_per_launch": ms / T, "algorithmic_tflops": flop / (ms * 1e-3) / 1e12})
+    del x, hseq, gates, cseq
+
+    # (3) Dense 1848 -> 256 over the 10 future slices (concat-state fusion): M = B*10 rows, K = 1848, N = 256
+    rows = B * 10
+    a = torch.randn(rows, 1, 1, 1848, device=dev)
+    wd = torch.randn(1, 1, 1848, 256, device=dev) * 0.02
+    bd = torch.zeros(256, device=dev)
+    y = torch.empty(rows, 1, 1, 256, device=dev)
+    dcfg = _lib.ConvCfg(rows, 1, 1, 1848, 256, 1, 1, 1, 1, 0, 0, 1848, 1848, 256, 256, 0, 0.0)
+    if math == 0:
+        fn = lambda: _lib.check(lib.fov_conv2d_fwd(C.byref(dcfg), a.data_ptr(), wd.data_ptr(), bd.data_ptr(),
+                                                   y.data_ptr(), st))
+    else:
+        wsd = torch.empty(int(lib.fov_conv_tc_ws_bytes(C.byref(dcfg), math, 0)) + 256, dtype=torch.uint8, device=dev)
+        fn = lambda: _lib.check(lib.fov_conv2d_fwd_tc(C.byref(dcfg), a.data_ptr(), wd.data_ptr(), bd.data_ptr(),
+                                                      y.data_ptr(), wsd.data_ptr(), math, st))
+    ms = _time_cuda(fn)
+    flop = 2.0 * rows * 1848 * 256
+    tf = flop / (ms * 1e-3) / 1e12
+    issue = {0: 1, 1: 1, 2: 3, 3: 6}[math]
+    out.append({"kernel": "tc_conv_kernel<%d,CONV>: Dense 1848->256 (+ weight repack), M=%d" % (math, rows),
+                "bound": "tensor", "achieved": tf, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": tf / peaks["bf16"],
+                "ms_per_launch": ms, "issued_mma_per_mac": issue,
+                "hbm_gbs": (rows * (1848 + 256) * 4) / (ms * 1e-3) / 1e9})
+    step_tflops = seq_per_s_per_gpu * TRAIN_FLOP_PER_SEQ / 1e12
+    main["kernels"] = out
+    main["whole_step"] = {"achieved": step_tflops, "peak": peaks["bf16_sustained"],
+                          "frac": step_tflops / peaks["bf16_sustained"], "unit": "TFLOP/s",
+                          "flop_per_seq": TRAIN_FLOP_PER_SEQ,
+                          "note": "algorithmic train FLOPs x seq/s per GPU against the sustained bf16 tensor peak"}
+    return main
+
+
+def other_workloads(dev, peaks, compute):
+    """The other BASELINE.json configs, a few steps each (reported, not the headline): ConvLSTM heatmaps/s
+    (config 5), large-batch autoregressive mu/var inference (config 3), teacher-forced fc-LSTM training
+    (config 1's model on the GPU).  Inputs resident in HBM; CUDA events."""
+    import torch
+    import longterm360fov_b200 as fov
+    from longterm360fov_b200 import data
+    res = {}
+
+    # ---- config 5: convlstm_seq2seq heatmap form, one heatmap = one predicted (36,18,30) second ----
+    Bh = 32
+    m4 = fov.convlstm_seq2seq(seed=2, device=dev).compile("RMSprop", "mean_squared_error")
+    m4.set_compute(compute)
+    x, y = data.make_m4_batch(Bh, seed=7)
+    xs, ys = m4._to_dev(x), m4._to_dev(y)
+    ms_t = _time_cuda(lambda: m4.train_step_device(xs, ys), reps=3, warm=2)
+    with torch.no_grad():
+        ms_i = _time_cuda(lambda: m4._forward(xs, False), reps=3, warm=1)
+    flop_fwd = 10 * 381.5e6 + 10 * (381.5e6 + 18.9e9)         # SURVEY.md 8a: encoder + decoder steps + heads
+    res["convlstm_seq2seq_heatmap"] = {
+        "batch": Bh, "unit": "heatmaps/s", "train": Bh * 10 / (ms_t * 1e-3), "infer": Bh * 10 / (ms_i * 1e-3),
+        "train_ms_per_step": ms_t, "infer_ms_per_step": ms_i,
+        "train_algorithmic_tflops": 3 * flop_fwd * Bh / (ms_t * 1e-3) / 1e12,
+        "infer_algorithmic_tflops": flop_fwd * Bh / (ms_i * 1e-3) / 1e12,
+        "tensor_peak_tflops": peaks["bf16"], "compute": compute}
+    del m4, xs, ys
+    torch.cuda.empty_cache()
+
+    # ---- config 3: FoV_seq2seq_mu_var, autoregressive decode without teacher forcing, large batch:
+    #      ONE persistent launch = 10 encoder + 10 decoder steps (Dense+tanh inside the recurrence) ----
+    Bi = 148 * 64 * 8
+    m2 = fov.fov_seq2seq_mu_var(seed=3, device=dev)
+    enc = torch.randn(Bi, 10, 6, device=dev) * 0.3
+    last = enc[:, -1:, :].contiguous()
+    with torch.no_grad():
+        ms = _time_cuda(lambda: m2._forward([enc, last], False, teacher_forcing=False, steps=10), reps=10, warm=3)
+    flop = Bi * (10 * 2 * (6 + 64) * 256 + 10 * (2 * (6 + 64) * 256 + 2 * 64 * 6))
+    byts = Bi * (10 * 6 + 6 + 10 * 6 + 10 * 64) * 4           # inputs + outputs (+ the encoder h sequence it emits)
+    res["fov_seq2seq_mu_var_autoregressive_infer"] = {
+        "batch": Bi, "unit": "sequences/s", "value": Bi / (ms * 1e-3), "ms_per_launch": ms,
+        "us_per_timestep_per_cta_wave": 1e3 * ms / 20 / max(1, -(-Bi // 64) / 148.0),
+        "fp32_tflops": flop / (ms * 1e-3) / 1e12, "hbm_gbs": byts / (ms * 1e-3) / 1e9,
+        "note": "latency/FMA-bound persistent recurrence (fp32 CUDA cores, weights resident in shared memory)"}
+
+    # ---- config 1 model (FoV_seq2seq, teacher forcing) training on the GPU ----
+    Bt = 8192
+    m1 = fov.fov_seq2seq(seed=4, device=dev).compile("Adam", "mean_squared_error")
+    e, d, t, _ = data.make_m1_batch(512, seed=9)
+    rep = Bt // 512
+    xs = m1._to_dev([np.tile(e, (rep, 1, 1)), np.tile(d, (rep, 1, 1))])
+    ys = m1._to_dev([np.tile(t, (rep, 1, 1))])
+    ms = _time_cuda(lambda: m1.train_step_device(xs, ys), reps=10, warm=3)
+    res["fov_seq2seq_teacher_forced_train"] = {"batch": Bt, "unit": "sequences/s", "value": Bt / (ms * 1e-3),
+                                               "ms_per_step": ms}
+    return res
 
 
 def _cpu_oracle_step_fn(batch, dtype_name="float32"):
@@ -178,12 +364,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing ----------------
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(args.warmup):
         xs, ys = dev_batches[i % 2]
         model.train_step_device(xs, ys)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.active = True
     n0 = lib.fov_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -194,8 +381,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches = int(lib.fov_launch_count() - n0)
     ms = e0.elapsed_time(e1)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.active = False
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -205,6 +391,7 @@ def run_ours(args):
     final_loss = float(loss.item())
 
     if args.profile_only:
+        sampler.stop_flag = True
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps,
                               "gpu_launches": launches, "profile_only": True}))
@@ -217,6 +404,7 @@ def run_ours(args):
     for i in range(2):
         model.train_on_batch(*host_batches[i % 2])
     barrier()
+    sampler.active = True
     e0.record()
     for i in range(e2e_steps):
         model.train_on_batch(*host_batches[i % 2])          # H2D of inputs+targets, step, D2H of the loss
@@ -241,57 +429,33 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
     ms_inf = e0.elapsed_time(e1)
+    sampler.active = False
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
     if world > 1:
         t = torch.tensor([ms_inf], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_inf = float(t.item())
     infer_val = world * B * args.steps / (ms_inf / 1e3)
 
-    # ---------------- dominant kernel, timed alone (rank 0) ----------------
+    # ---------------- dominant kernels, each timed alone with CUDA events (rank 0) ----------------
     roofline = None
     if rank == 0:
-        # recurrent gate convolution of others-ConvLSTM layer 0: M=B*33 pixels, N=4F=128, K=5*32=160
-        Mpix, N, K = B * 33, 128, 160
-        h = torch.randn(B, 1, 33, 32, device=dev)
-        R = torch.randn(1, 5, 32, 128, device=dev) * 0.05
-        z = torch.zeros(B, 1, 33, 128, device=dev)
-        cfg = _lib.ConvCfg(B, 1, 33, 32, 128, 1, 5, 1, 1, 0, 2, 33 * 32, 32, 33 * 128, 128, 0, 1.0)
-        st = torch.cuda.current_stream().cuda_stream
-        reps = 20
-        for _ in range(3):
-            _lib.check(lib.fov_conv2d_fwd(C.byref(cfg), h.data_ptr(), R.data_ptr(), None, z.data_ptr(), st))
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            _lib.check(lib.fov_conv2d_fwd(C.byref(cfg), h.data_ptr(), R.data_ptr(), None, z.data_ptr(), st))
-        e1.record()
-        torch.cuda.synchronize()
-        k_ms = e0.elapsed_time(e1) / reps
-        k_tflops = 2.0 * Mpix * N * K / (k_ms * 1e-3) / 1e12
-        step_tflops = (value / world) * TRAIN_FLOP_PER_SEQ / 1e12
-        roofline = {
-            "bound": "tensor", "achieved": k_tflops, "peak": peaks["bf16"], "unit": "TFLOP/s",
-            "frac": k_tflops / peaks["bf16"], "traffic": None,
-            "kernel": "conv_fwd_kernel<128,128,8,8> (ConvLSTM L0 recurrent gate conv, M=%d N=128 K=160), fp32 SIMT, "
-                      "timed alone with CUDA events (%d launches, %.3f ms each)" % (Mpix, reps, k_ms),
-            "peak_is": "%s bf16 tensor burst (the path's target roofline; this parity build computes in fp32 on "
-                       "CUDA cores, nominal fp32 FMA peak ~74 TFLOP/s)" % peaks["which"],
-            "whole_step": {"achieved": step_tflops, "peak": peaks["bf16_sustained"],
-                           "frac": step_tflops / peaks["bf16_sustained"],
-                           "flop_per_seq": TRAIN_FLOP_PER_SEQ, "note": "algorithmic train FLOPs x seq/s per GPU"}}
+        roofline = kernel_rooflines(lib, dev, B, args.compute, peaks, value / world)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    extras = other_workloads(dev, peaks, args.compute) if world == 1 and not args.no_extras else None
     cpu = cpu_baseline() if world == 1 and not args.no_cpu_baseline else None
     saved_gb = B * (20 * 33 * (56 * 5 + 56) * 4 + 20 * 1848 * 4) / 1e9
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp32", "data": "synthetic",
+        "dtype": DTYPE_OF[args.compute], "data": "synthetic",
         "config": {"workload": "configs[1]: others_LSTM_span_whole concat-state seq2seq (enc (B,10,6), others "
-                               "(B,20,1,33,6), dec0 (B,1,6)), fp32, train step = fwd + BPTT + 3xMSE + Adam",
+                               "(B,20,1,33,6), dec0 (B,1,6)), train step = fwd + BPTT + 3xMSE + Adam; compute=%s" % args.compute,
                    "per_gpu_batch": B, "global_batch": world * B, "parallelism": "dp%d" % world,
                    "params": model.count_params(),
                    "l2": "no flush needed: per-step working set (saved activations ~%.1f GB) >> 126 MB L2; "
@@ -304,6 +468,8 @@ def run_ours(args):
         "roofline": roofline,
         "clocks": sampler.result(),
     }
+    if extras is not None:
+        out["other_workloads"] = extras
     if cpu is not None:
         out["cpu_baseline"] = cpu
     print(json.dumps(out))
@@ -323,6 +489,7 @@ def main():
                     help="arithmetic of the conv/dense/ConvLSTM kernels: fp32 = CUDA cores; bf16x2 (default) = "
                          "tcgen05 with two bf16 terms per operand, fp32 accumulate (fp32-grade results)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other_workloads legs (configs 1, 3, 5)")
     ap.add_argument("--profile-only", action="store_true",
                     help="only the device-resident timed region (for ncu runs): no e2e / infer / cpu legs")
     args = ap.parse_args()

@@ -1,0 +1,113 @@
+// Hardware probe 2: MN-major operands addressed at a start shifted by whole rows.
+//   D[m][n] = sum_k A[k][m] * B[k + shift][n],   A: MN-major SWIZZLE_128B (M = 128, two 64-wide groups),
+//   B: MN-major tile whose rows are pixels (K index) holding N channels, row = 128 / 64 / 32 bytes
+//   (SWIZZLE_128B / 64B / 32B), data written with the absolute-address swizzle.
+// If row shifts work, the taps of a convolution weight gradient become descriptor offsets into ONE
+// staged activation tile (no per-tap gather).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include "../../longterm360fov_b200/csrc/tc_common.cuh"
+using namespace tc;
+
+constexpr int KROWS = 64, BROWS = 96, M = 128;
+
+__global__ void probe(const __nv_bfloat16* Am, const __nv_bfloat16* Bm, float* D, int shift, int row_bytes, int N,
+                      int a_shift) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint8_t* As = smem;                 // 2 groups x BROWS rows x 128 B (group stride 16 KB)
+  uint8_t* Bs = smem + 32 * 1024;     // BROWS rows x row_bytes
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tptr;
+  const int tid = threadIdx.x;
+  // A[k][m]: row k, group g = m / 64, chunk c = (m % 64) / 8
+  for (int idx = tid; idx < BROWS * 16; idx += blockDim.x) {
+    const int r = idx >> 4, c16 = idx & 15, g = c16 >> 3, c = c16 & 7;
+    uint4 v = *reinterpret_cast<const uint4*>(Am + r * M + c16 * 8);
+    const uint32_t a = (uint32_t)(r * 128 + c * 16);
+    *reinterpret_cast<uint4*>(As + g * 16384 + (a ^ (((a >> 7) & 7u) << 4))) = v;
+  }
+  const int cpr = row_bytes / 16;
+  const uint32_t mask = row_bytes == 128 ? 7u : (row_bytes == 64 ? 3u : 1u);
+  const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  for (int idx = tid; idx < BROWS * cpr; idx += blockDim.x) {
+    const int r = idx / cpr, c = idx % cpr;
+    uint4 v = *reinterpret_cast<const uint4*>(Bm + r * 64 + c * 8);
+    const uint32_t a = (uint32_t)(r * row_bytes + c * 16);
+    *reinterpret_cast<uint4*>(Bs + (a ^ (((a >> 7) & mask) << 4))) = v;
+  }
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+  if (tid < 32) { tmem_alloc(smem_u32(&tptr), 64); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t td = tptr;
+  if (tid == 0) {
+    const uint32_t idesc = idesc_bf16_f32(M, N, 1, 1);
+    const uint32_t sbo_b = 8 * row_bytes;
+    auto bdesc = [&](uint32_t addr) {
+      return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((sbo_b >> 4) & 0x3FFFu) << 16) |
+             ((uint64_t)((sbo_b >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+    };
+    for (int k4 = 0; k4 < KROWS / 16; ++k4) {
+      const uint64_t ad = smem_desc_sw128(base + (a_shift + k4 * 16) * 128, 16384, 1024);
+      umma_bf16(td, ad, bdesc(base + 32 * 1024 + (shift + k4 * 16) * row_bytes), idesc, k4 > 0);
+    }
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  if (tid < 128) {
+    const int warp = tid >> 5;
+    float v[32];
+    tmem_ld16(td + ((uint32_t)(warp * 32) << 16), v);
+    tmem_ld16(td + ((uint32_t)(warp * 32) << 16) + 16, v + 16);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) D[tid * 32 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(td, 64);
+}
+
+int main() {
+  std::vector<__nv_bfloat16> hA(BROWS * M), hB(BROWS * 64);
+  std::vector<float> fA(BROWS * M), fB(BROWS * 64);
+  srand(2);
+  for (size_t i = 0; i < hA.size(); ++i) { float x = (rand() % 17 - 8) / 8.0f; hA[i] = __float2bfloat16(x); fA[i] = x; }
+  for (size_t i = 0; i < hB.size(); ++i) { float x = (rand() % 13 - 6) / 4.0f; hB[i] = __float2bfloat16(x); fB[i] = x; }
+  __nv_bfloat16 *dA, *dB; float* dD;
+  cudaMalloc(&dA, hA.size() * 2); cudaMalloc(&dB, hB.size() * 2); cudaMalloc(&dD, 128 * 32 * 4);
+  cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
+  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  std::vector<float> hD(128 * 32);
+  const int rbs[4] = {128, 128, 64, 32}, ns[4] = {64 > 32 ? 32 : 32, 16, 32, 16};
+  for (int v = 0; v < 4; ++v)
+    for (int as = 0; as <= 3; as += 3) {
+      const int rb = rbs[v], N = ns[v];
+      printf("B MN-major SWIZZLE_%dB N=%d, A row shift %d, B row shifts:", rb, N, as);
+      for (int shift = 0; shift <= 12; ++shift) {
+        probe<<<1, 128, 64 * 1024>>>(dA, dB, dD, shift, rb, N, as);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf(" CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+        cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost);
+        double err = 0;
+        for (int m = 0; m < M; ++m)
+          for (int n = 0; n < N; ++n) {
+            double acc = 0;
+            for (int k = 0; k < KROWS; ++k) acc += (double)fA[(k + as) * M + m] * fB[(k + shift) * 64 + n];
+            err = fmax(err, fabs(acc - hD[m * 32 + n]));
+          }
+        printf(" s%d:%s", shift, err < 1e-3 ? "OK" : "bad");
+      }
+      printf("\n");
+    }
+  return 0;
+}
