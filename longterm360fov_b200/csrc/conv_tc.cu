@@ -96,22 +96,6 @@ __device__ __forceinline__ long long img_off(int n, int T_inner, long long outer
   return (long long)no * outer + (long long)(n - no * T_inner) * inner;
 }
 
-// exp-based activations for the fused epilogue (abs error ~1e-7, far inside the bf16-split budget)
-__device__ __forceinline__ float fast_tanh(float x) {
-  const float e = __expf(2.0f * x);
-  return 1.0f - __fdividef(2.0f, e + 1.0f);
-}
-__device__ __forceinline__ float fast_rec(int rec, float x) {
-  if (rec == FOV_REC_HARD_SIGMOID) return fov_hard_sigmoid(x);
-  return __fdividef(1.0f, 1.0f + __expf(-x));
-}
-
-// descriptor = high word (SBO, version 1, swizzle mode) | low word (start address, LBO = 16 B)
-constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
-__device__ __forceinline__ uint64_t desc_at(uint32_t hi, uint32_t saddr) {
-  return ((uint64_t)hi << 32) | (uint64_t)(((saddr >> 4) & 0x3FFFu) | (1u << 16));
-}
-
 template <int NS, int EPI>
 __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -713,6 +697,32 @@ static int g_tc_debug = 0;
 extern "C" void fov_debug_timeline_enable(int on) { g_tc_debug = on; }
 extern "C" int fov_debug_timeline_read(unsigned long long* out, int n_words) {
   return (int)cudaMemcpyFromSymbol(out, g_tc_timeline, sizeof(unsigned long long) * (size_t)n_words);
+}
+
+// plan of a whole-K-resident shifted-tap GEMM, for the persistent ConvLSTM kernels (convlstm_seq_tc.cu)
+int tc_conv_step_plan(const TcConv& c, TcStepPlan* out) {
+  Plan pl;
+  int rc = make_plan(c, &pl);
+  if (rc) return rc;
+  FOV_CHECK_ARG(!pl.mode_b && pl.n_tiles == 1, "not a single-tile, <= 64-channel problem");
+  *out = TcStepPlan{};
+  out->nseg = c.nseg;
+  for (int s = 0; s < c.nseg; ++s) {
+    const TcSeg& g = c.seg[s];
+    const SegPlan& sp = pl.sp[s];
+    TcStepSeg& d = out->seg[s];
+    d.Cin = g.Cin; d.Cin_p = sp.Cin_p; d.cp_log2 = sp.cp_log2; d.cw = sp.cw; d.lpr_log2 = sp.lpr_log2;
+    d.row_bytes = sp.row_bytes; d.term_bytes = sp.term_bytes; d.R = sp.R; d.minshift = sp.minshift;
+    d.swz_mask = sp.row_bytes == 128 ? 7 : (sp.row_bytes == 64 ? 3 : 1);
+    const uint32_t layout = sp.row_bytes == 128 ? 2u : (sp.row_bytes == 64 ? 4u : 6u);
+    d.desc_hi = ((uint32_t)(8 * sp.row_bytes) >> 4) | (1u << 14) | (layout << 29);
+    d.taps = sp.taps; d.kw = g.kw; d.dil_h = g.dil_h; d.dil_w = g.dil_w; d.pad_h = g.pad_h; d.pad_w = g.pad_w;
+    d.k_begin = sp.k_begin;
+  }
+  out->Hp = pl.Hp; out->Wp = pl.Wp; out->PLh = pl.PLh; out->PLw = pl.PLw;
+  out->K_total = pl.K_total; out->KB = pl.KB; out->BLOCK_N = pl.BLOCK_N; out->NS = pl.NS;
+  out->w_bytes = pl.ws_bytes;
+  return FOV_OK;
 }
 
 bool tc_conv_supported(const TcConv& c) {

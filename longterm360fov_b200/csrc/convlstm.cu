@@ -135,6 +135,8 @@ static int convlstm_fwd_tc(const fov_convlstm_cfg* cfg, const fov_convlstm_io* i
   const int F = cfg->F;
   TcConv k = step_conv(cfg, io, g);
   k.ws = io->ws;
+  // whole images per MMA tile: one persistent launch runs every timestep (convlstm_seq_tc.cu)
+  if (tc_convlstm_seq_supported(cfg, k)) return tc_convlstm_seq_fwd(cfg, io, k, st);
   for (int t = 0; t < cfg->T; ++t) {
     k.prepacked = t > 0;
     k.seg[0].x = io->x + t * cfg->x_t_stride;

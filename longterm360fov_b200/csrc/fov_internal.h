@@ -72,10 +72,27 @@ struct TcConv {
   float* gates_out;    long long g_outer, g_inner;     // optional activated gates (pixel stride 4F)
   float *hT, *cT;                                      // optional dense copies (N_img,HW,F)
 };
+// Geometry of a shifted-tap GEMM whose whole K extent stays resident in shared memory (<= 64 channels per
+// segment, one n tile): what the persistent ConvLSTM kernels need to stage operands and issue MMAs.
+struct TcStepSeg {
+  int Cin, Cin_p, cp_log2, cw, lpr_log2, row_bytes, swz_mask, term_bytes, R, minshift;
+  int taps, kw, dil_h, dil_w, pad_h, pad_w, k_begin;
+  unsigned desc_hi;
+};
+struct TcStepPlan {
+  TcStepSeg seg[2];
+  int nseg, Hp, Wp, PLh, PLw, K_total, KB, BLOCK_N, NS;
+  size_t w_bytes;   // packed weights: KB x NS x BLOCK_N x 128 B
+};
+int tc_conv_step_plan(const TcConv& c, TcStepPlan* out);
 bool tc_conv_supported(const TcConv& c);   // shape fits the shifted-tap kernel (no error is recorded)
 size_t tc_conv_ws_bytes(const TcConv& c);
 int tc_conv_pack(const TcConv& c, cudaStream_t st);
 int tc_conv_run(const TcConv& c, cudaStream_t st);
+
+// Persistent ConvLSTM2D layer (convlstm_seq_tc.cu): every timestep in one launch when whole images fit a tile.
+bool tc_convlstm_seq_supported(const fov_convlstm_cfg* c, const TcConv& step);
+int tc_convlstm_seq_fwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const TcConv& step, cudaStream_t st);
 
 // Tensor-core weight gradient: gw[(tap*Cin+ci)*Cout+n] += sum_pixels x(pixel+tap, ci) * dy(pixel, n),
 // gbias[n] += sum_pixels dy(pixel, n).  Both operands are read in their natural NHWC layout and

@@ -147,6 +147,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM: thread i writes lane (warp%4)*32+i, 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- bf16 splitting -------------------------------------------------------------------------
 // x ~= t0 + t1 + t2 with each term a bf16: 1 term = plain bf16, 2 terms ~ 16 mantissa bits,
@@ -195,5 +204,23 @@ __device__ __forceinline__ float4 ldg_vec4(const float* __restrict__ p, int nval
   }
   return v;
 }
+
+// ---- shared by the shifted-tap kernels -------------------------------------------------------
+// exp-based activations for the fused epilogue (abs error ~1e-7, far inside the bf16-split budget)
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+__device__ __forceinline__ float fast_rec(int rec, float x) {
+  if (rec == 0 /* FOV_REC_HARD_SIGMOID */) return fminf(fmaxf(0.2f * x + 0.5f, 0.0f), 1.0f);
+  return __fdividef(1.0f, 1.0f + __expf(-x));
+}
+
+// descriptor = high word (SBO, version 1, swizzle mode) | low word (start address, LBO = 16 B)
+constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t desc_at(uint32_t hi, uint32_t saddr) {
+  return ((uint64_t)hi << 32) | (uint64_t)(((saddr >> 4) & 0x3FFFu) | (1u << 16));
+}
+
 
 }  // namespace tc

@@ -312,6 +312,81 @@ static void test_convlstm(const char* name, int B, int T, int H, int W, int Cin,
   if (h0) { cudaFree(h0); cudaFree(c0); }
 }
 
+// Persistent (one launch for all T) vs per-timestep fused ConvLSTM forward at the same arithmetic: same MMA
+// order and same fp32 epilogue, so the results must agree to rounding noise.  Strided layouts as in the stacked
+// models: x is a channel slice of a wider buffer, h goes into a channel slice of the concat buffer.
+extern "C" void fov_debug_convlstm_persistent(int enable);
+extern "C" void fov_debug_seq_enable(int on);
+extern "C" int fov_debug_seq_read(unsigned long long* out);
+static void test_convlstm_seq(const char* name, int B, int T, int H, int W, int Cin, int F, int kh, int kw,
+                              bool with_state, int training, bool time_it) {
+  printf("[convlstm persistent] %s B=%d T=%d HxW=%dx%d Cin=%d F=%d k=%dx%d state=%d training=%d\n", name, B, T, H, W,
+         Cin, F, kh, kw, (int)with_state, training);
+  const size_t HW = (size_t)H * W;
+  const int XP = Cin + 8, HP = F + 24;            // pixel strides of the wider buffers
+  const size_t nx = (size_t)B * T * HW * XP, nh = (size_t)B * T * HW * HP, nc = (size_t)B * T * HW * F, nz = nc * 4,
+               ns = (size_t)B * HW * F;
+  const size_t nK = (size_t)kh * kw * Cin * 4 * F, nR = (size_t)kh * kw * F * 4 * F;
+  float* x = dev_rand(nx, 1.0f);
+  float* K = dev_rand(nK, 1.0f / sqrtf((float)(kh * kw * Cin)));
+  float* R = dev_rand(nR, 1.0f / sqrtf((float)(kh * kw * F)));
+  float* bias = dev_rand(4 * F, 0.5f);
+  float* h0 = with_state ? dev_rand(ns, 0.5f) : nullptr;
+  float* c0 = with_state ? dev_rand(ns, 0.5f) : nullptr;
+  Timer tm;
+  for (int math = 1; math <= 3; ++math) {
+    fov_convlstm_cfg c{};
+    c.B = B; c.T = T; c.H = H; c.W = W; c.Cin = Cin; c.F = F; c.kh = kh; c.kw = kw; c.dil_h = 1; c.dil_w = 1;
+    c.rec_act = FOV_REC_HARD_SIGMOID;
+    c.x_b_stride = (long long)T * HW * XP; c.x_t_stride = (long long)HW * XP; c.x_pix_stride = XP;
+    c.h_b_stride = (long long)T * HW * HP; c.h_t_stride = (long long)HW * HP; c.h_pix_stride = HP;
+    c.training = training; c.math = math;
+    float* out[2][5];
+    for (int mode = 0; mode < 2; ++mode) {
+      fov_debug_convlstm_persistent(mode);
+      float* hseq = dev_zero(nh); float* gates = dev_zero(nz); float* cseq = dev_zero(nc);
+      float* hT = dev_zero(ns); float* cT = dev_zero(ns);
+      fov_convlstm_io io{};
+      io.x = x + 4; io.kernel = K; io.recurrent = R; io.bias = bias; io.h0 = h0; io.c0 = c0;
+      io.hseq = hseq + 8; io.gates = gates; io.cseq = cseq; io.hT = hT; io.cT = cT;
+      const size_t fws = fov_convlstm_fwd_ws_bytes(&c);
+      void* wsf = nullptr;
+      CK(cudaMalloc(&wsf, fws + 256));
+      io.ws = (float*)wsf;
+      FK(fov_convlstm_fwd(&c, &io, nullptr));
+      CK(cudaDeviceSynchronize());
+      if (time_it) {
+        tm.start();
+        for (int i = 0; i < 3; ++i) FK(fov_convlstm_fwd(&c, &io, nullptr));
+        printf("  time convlstm fwd math=%d %s: %.3f ms\n", math, mode ? "persistent" : "per-step  ", tm.stop_ms() / 3);
+        if (mode) {
+          fov_debug_seq_enable(1);
+          FK(fov_convlstm_fwd(&c, &io, nullptr));
+          CK(cudaDeviceSynchronize());
+          fov_debug_seq_enable(0);
+          unsigned long long w[8];
+          fov_debug_seq_read(w);
+          printf("    CTA0 cycles: worker wait-mma %llu, phase A %llu, phase B %llu, x-store %llu, total %llu | mma thread: "
+                 "wait-operands %llu, issue %llu, total %llu\n", w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+        }
+      }
+      cudaFree(wsf);
+      out[mode][0] = hseq; out[mode][1] = gates; out[mode][2] = cseq; out[mode][3] = hT; out[mode][4] = cT;
+    }
+    const double tol = 2e-6;
+    report("hseq  (persistent vs per-step)", math, compare(out[1][0], out[0][0], nh), tol);
+    if (training) report("gates (persistent vs per-step)", math, compare(out[1][1], out[0][1], nz), tol);
+    report("cseq  (persistent vs per-step)", math, compare(out[1][2], out[0][2], nc), tol);
+    report("hT    (persistent vs per-step)", math, compare(out[1][3], out[0][3], ns), tol);
+    report("cT    (persistent vs per-step)", math, compare(out[1][4], out[0][4], ns), tol);
+    for (int mode = 0; mode < 2; ++mode)
+      for (int i = 0; i < 5; ++i) cudaFree(out[mode][i]);
+  }
+  fov_debug_convlstm_persistent(1);
+  cudaFree(x); cudaFree(K); cudaFree(R); cudaFree(bias);
+  if (h0) { cudaFree(h0); cudaFree(c0); }
+}
+
 extern "C" void fov_debug_wgrad_enable(int on);
 extern "C" int fov_debug_wgrad_read(unsigned long long* out);
 extern "C" void fov_debug_timeline_enable(int on);
@@ -394,6 +469,18 @@ int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   if (!fov_device_is_sm100()) { printf("not an sm_100 device\n"); return 1; }
   if (argc > 1 && !strcmp(argv[1], "profile")) { profile_mode(); return 0; }
+  if (argc > 1 && !strcmp(argv[1], "seq")) {
+    test_convlstm_seq("m3 L0", 7, 5, 1, 33, 6, 32, 1, 5, false, 1, false);
+    test_convlstm_seq("m3 L1", 50, 20, 1, 33, 32, 16, 1, 5, true, 1, false);
+    test_convlstm_seq("m3 L2", 13, 4, 1, 33, 16, 8, 1, 5, false, 0, false);
+    test_convlstm_seq("3x3 on 5x4", 9, 3, 5, 4, 12, 16, 3, 3, true, 1, false);
+    test_convlstm_seq("traj 1x30 Cin 3", 4, 6, 1, 30, 3, 32, 1, 5, true, 0, false);
+    test_convlstm_seq("T m3 L0 B=2048", 2048, 20, 1, 33, 6, 32, 1, 5, false, 1, true);
+    test_convlstm_seq("T m3 L1 B=2048", 2048, 20, 1, 33, 32, 16, 1, 5, false, 1, true);
+    test_convlstm_seq("T m3 L2 B=2048", 2048, 20, 1, 33, 16, 8, 1, 5, false, 1, true);
+    printf(g_fail ? "SELFTEST FAILED (%d)\n" : "SELFTEST OK (%d failures)\n", g_fail);
+    return g_fail ? 1 : 0;
+  }
   // --- convolution family ---
   test_conv("dense 64->16", mkcfg(300, 1, 1, 64, 16, 1, 1, 1, 1, FOV_ACT_LINEAR, 0.f), false);
   test_conv("m3 L0 rec", mkcfg(64, 1, 33, 32, 128, 1, 5, 1, 1, FOV_ACT_LINEAR, 1.f), false);
@@ -409,6 +496,12 @@ int main(int argc, char** argv) {
   test_convlstm("m3 L1", 5, 3, 1, 33, 32, 16, 1, 5, true, false);
   test_convlstm("m3 L2", 5, 3, 1, 33, 16, 8, 1, 5, false, false);
   test_convlstm("m4 L0", 2, 3, 36, 18, 30, 32, 5, 5, true, false);
+  // --- persistent ConvLSTM (whole images per tile) vs the per-timestep launches ---
+  test_convlstm_seq("m3 L0", 7, 5, 1, 33, 6, 32, 1, 5, false, 1, false);
+  test_convlstm_seq("m3 L1", 50, 20, 1, 33, 32, 16, 1, 5, true, 1, false);
+  test_convlstm_seq("m3 L2", 13, 4, 1, 33, 16, 8, 1, 5, false, 0, false);
+  test_convlstm_seq("3x3 on 5x4", 9, 3, 5, 4, 12, 16, 3, 3, true, 1, false);
+  test_convlstm_seq("traj 1x30 Cin 3", 4, 6, 1, 30, 3, 32, 1, 5, true, 0, false);
   if (!quick) {
     // --- timings at bench size (config 2, B=4096) ---
     test_conv("T m3 L0 rec B=4096", mkcfg(4096, 1, 33, 32, 128, 1, 5, 1, 1, FOV_ACT_LINEAR, 0.f), true);
@@ -416,6 +509,9 @@ int main(int argc, char** argv) {
     test_conv("T head 56->512 B=32", mkcfg(32, 36, 18, 56, 512, 5, 5, 1, 1, FOV_ACT_RELU, 0.f), true);
     test_conv("T head 512->1024 B=32", mkcfg(32, 36, 18, 512, 1024, 5, 5, 1, 1, FOV_ACT_RELU, 0.f), true);
     test_convlstm("T m3 L0 B=2048", 2048, 20, 1, 33, 6, 32, 1, 5, false, true);
+    test_convlstm_seq("T m3 L0 B=2048", 2048, 20, 1, 33, 6, 32, 1, 5, false, 1, true);
+    test_convlstm_seq("T m3 L1 B=2048", 2048, 20, 1, 33, 32, 16, 1, 5, false, 1, true);
+    test_convlstm_seq("T m3 L2 B=2048", 2048, 20, 1, 33, 16, 8, 1, 5, false, 1, true);
   }
   printf(g_fail ? "SELFTEST FAILED (%d)\n" : "SELFTEST OK (%d failures)\n", g_fail);
   return g_fail ? 1 : 0;
