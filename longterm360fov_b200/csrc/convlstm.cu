@@ -299,6 +299,24 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
       kT.seg[0].x = io->gates; kT.y = gr->dx; kT.beta = gr->dx_accumulate ? 1.0f : 0.0f;
       if ((rc = tc_conv_run(kT, st))) return rc;
     }
+    // fused weight gradient (gK, gR, gb in one launch, no gather) when the taps fit the TMEM columns
+    if (gr->g_kernel && gr->g_recurrent) {
+      TcWgradRows wr{};
+      wr.nseg = 2; wr.dz = io->gates; wr.B = cfg->B; wr.T = cfg->T; wr.H = cfg->H; wr.W = cfg->W;
+      wr.Cout = 4 * F; wr.math = cfg->math; wr.gbias = gr->g_bias;
+      TcWgradRowsSeg& sx = wr.seg[0];
+      sx.x = io->x; sx.b_stride = cfg->x_b_stride; sx.t_stride = cfg->x_t_stride; sx.pix_stride = cfg->x_pix_stride;
+      sx.t_shift = 0; sx.Cin = cfg->Cin; sx.kh = cfg->kh; sx.kw = cfg->kw; sx.dil_h = cfg->dil_h; sx.dil_w = cfg->dil_w;
+      sx.pad_h = ((cfg->kh - 1) * cfg->dil_h) / 2; sx.pad_w = ((cfg->kw - 1) * cfg->dil_w) / 2;
+      sx.gw = gr->g_kernel;
+      TcWgradRowsSeg& sh = wr.seg[1];
+      sh.x = io->hseq; sh.b_stride = cfg->h_b_stride; sh.t_stride = cfg->h_t_stride; sh.pix_stride = cfg->h_pix_stride;
+      sh.x0 = io->h0; sh.x0_b_stride = g.hw_f; sh.x0_pix_stride = F;
+      sh.t_shift = -1; sh.Cin = F; sh.kh = cfg->kh; sh.kw = cfg->kw; sh.dil_h = 1; sh.dil_w = 1;
+      sh.pad_h = (cfg->kh - 1) / 2; sh.pad_w = (cfg->kw - 1) / 2;
+      sh.gw = gr->g_recurrent;
+      if (tc_wgrad_rows_supported(wr)) return tc_wgrad_rows_run(wr, st);
+    }
     TcWgrad w{};
     w.N_img = cfg->B * cfg->T; w.T_inner = cfg->T; w.H = cfg->H; w.W = cfg->W; w.math = cfg->math;
     w.x = io->x; w.x_outer = cfg->x_b_stride; w.x_inner = cfg->x_t_stride; w.x_pix_stride = cfg->x_pix_stride;

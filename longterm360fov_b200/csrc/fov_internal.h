@@ -107,3 +107,22 @@ struct TcWgrad {
   float* gbias;    // may be NULL
 };
 int tc_wgrad_run(const TcWgrad& c, cudaStream_t st);
+
+// Fused ConvLSTM weight gradient (wgrad_rows_tc.cu): gK, gR and gb of a layer in one launch, taps as descriptor
+// offsets (no gather).  dZ is the dense (B,T,HW,Cout) gate-gradient buffer; segment s pairs image (b, t + t_shift)
+// of its tensor with dZ image (b,t); images with t + t_shift < 0 come from x0 (or read as zeros).
+struct TcWgradRowsSeg {
+  const float* x;  long long b_stride, t_stride; int pix_stride;
+  const float* x0; long long x0_b_stride; int x0_pix_stride;
+  int t_shift, Cin, kh, kw, dil_h, dil_w, pad_h, pad_w;
+  float* gw;       // (kh,kw,Cin,Cout), accumulated; may be NULL
+};
+struct TcWgradRows {
+  int nseg;
+  TcWgradRowsSeg seg[2];
+  const float* dz;
+  int B, T, H, W, Cout, math;
+  float* gbias;    // may be NULL
+};
+bool tc_wgrad_rows_supported(const TcWgradRows& c);
+int tc_wgrad_rows_run(const TcWgradRows& c, cudaStream_t st);

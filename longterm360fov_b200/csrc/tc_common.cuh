@@ -218,6 +218,10 @@ __device__ __forceinline__ float fast_rec(int rec, float x) {
 
 // descriptor = high word (SBO, version 1, swizzle mode) | low word (start address, LBO = 16 B)
 constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+// same with an explicit leading-dimension byte offset (MN-major tiles: stride between the N / M groups)
+__device__ __forceinline__ uint64_t desc_at_lbo(uint32_t hi, uint32_t saddr, uint32_t lbo_bytes) {
+  return ((uint64_t)hi << 32) | (uint64_t)(((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16));
+}
 __device__ __forceinline__ uint64_t desc_at(uint32_t hi, uint32_t saddr) {
   return ((uint64_t)hi << 32) | (uint64_t)(((saddr >> 4) & 0x3FFFu) | (1u << 16));
 }

@@ -225,6 +225,8 @@ static void test_conv(const char* name, fov_conv_cfg c, bool time_it) {
 }
 
 // ConvLSTM layer: SIMT (math 0) vs fused tensor-core step (math 1..3), forward + BPTT
+extern "C" void fov_debug_wgrad_rows_timeline(int on);
+extern "C" int fov_debug_wgrad_rows_read(unsigned long long* out);
 static void test_convlstm(const char* name, int B, int T, int H, int W, int Cin, int F, int kh, int kw, bool with_state,
                           bool time_it) {
   printf("[convlstm] %s B=%d T=%d HxW=%dx%d Cin=%d F=%d k=%dx%d state=%d\n", name, B, T, H, W, Cin, F, kh, kw,
@@ -279,9 +281,17 @@ static void test_convlstm(const char* name, int B, int T, int H, int W, int Cin,
     g.dx_accumulate = 0;
     // the BPTT overwrites the saved gates: keep a copy for the comparison
     float* gates_keep = dev_copy(r.gates, nz);
-    if (time_it) tm.start();
+    if (time_it) { tm.start(); fov_debug_wgrad_rows_timeline(1); }
     FK(fov_convlstm_bwd(&c, &io, &g, nullptr));
-    if (time_it) printf("  time convlstm bwd math=%d: %.3f ms\n", math, tm.stop_ms());
+    if (time_it) {
+      printf("  time convlstm bwd math=%d: %.3f ms\n", math, tm.stop_ms());
+      fov_debug_wgrad_rows_timeline(0);
+      unsigned long long w[8];
+      fov_debug_wgrad_rows_read(w);
+      if (math > 0)
+        printf("    wgrad_rows CTA0 (%llu tiles) cycles: producer wait %llu, dZ stage %llu, rows %llu, total %llu | mma: wait %llu, "
+               "issue %llu, total %llu\n", w[7], w[0], w[1], w[2], w[3], w[4], w[5], w[6]);
+    }
     CK(cudaDeviceSynchronize());
     cudaFree(r.gates); r.gates = gates_keep;
     cudaFree(g.ws);
@@ -317,6 +327,8 @@ static void test_convlstm(const char* name, int B, int T, int H, int W, int Cin,
 // models: x is a channel slice of a wider buffer, h goes into a channel slice of the concat buffer.
 extern "C" void fov_debug_convlstm_persistent(int enable);
 extern "C" void fov_debug_seq_enable(int on);
+extern "C" void fov_debug_wgrad_rows(int enable);
+
 extern "C" int fov_debug_seq_read(unsigned long long* out);
 static void test_convlstm_seq(const char* name, int B, int T, int H, int W, int Cin, int F, int kh, int kw,
                               bool with_state, int training, bool time_it) {
@@ -469,6 +481,22 @@ int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   if (!fov_device_is_sm100()) { printf("not an sm_100 device\n"); return 1; }
   if (argc > 1 && !strcmp(argv[1], "profile")) { profile_mode(); return 0; }
+  if (argc > 1 && !strcmp(argv[1], "wr")) {      // fused row-shift weight gradient: parity vs fp32, timing on/off
+    test_convlstm("m3 L0", 6, 4, 1, 33, 6, 32, 1, 5, false, false);
+    test_convlstm("m3 L1", 5, 3, 1, 33, 32, 16, 1, 5, true, false);
+    test_convlstm("m3 L2", 5, 3, 1, 33, 16, 8, 1, 5, false, false);
+    test_convlstm("3x3 on 5x4", 9, 3, 5, 4, 12, 16, 3, 3, true, false);
+    test_convlstm("traj 1x30 Cin 3", 4, 6, 1, 30, 3, 32, 1, 5, true, false);
+    for (int on = 0; on < 2; ++on) {
+      fov_debug_wgrad_rows(on);
+      printf("=== fused row-shift wgrad %s ===\n", on ? "ON" : "OFF");
+      test_convlstm("T m3 L0 B=2048", 2048, 20, 1, 33, 6, 32, 1, 5, false, true);
+      test_convlstm("T m3 L1 B=2048", 2048, 20, 1, 33, 32, 16, 1, 5, false, true);
+      test_convlstm("T m3 L2 B=2048", 2048, 20, 1, 33, 16, 8, 1, 5, false, true);
+    }
+    printf(g_fail ? "SELFTEST FAILED (%d)\n" : "SELFTEST OK (%d failures)\n", g_fail);
+    return g_fail ? 1 : 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "seq")) {
     test_convlstm_seq("m3 L0", 7, 5, 1, 33, 6, 32, 1, 5, false, 1, false);
     test_convlstm_seq("m3 L1", 50, 20, 1, 33, 32, 16, 1, 5, true, 1, false);
