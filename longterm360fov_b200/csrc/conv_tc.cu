@@ -704,7 +704,7 @@ int tc_conv_step_plan(const TcConv& c, TcStepPlan* out) {
   Plan pl;
   int rc = make_plan(c, &pl);
   if (rc) return rc;
-  FOV_CHECK_ARG(!pl.mode_b && pl.n_tiles == 1, "not a single-tile, <= 64-channel problem");
+  FOV_CHECK_ARG(pl.n_tiles == 1, "not a single-n-tile problem");
   *out = TcStepPlan{};
   out->nseg = c.nseg;
   for (int s = 0; s < c.nseg; ++s) {
@@ -717,8 +717,9 @@ int tc_conv_step_plan(const TcConv& c, TcStepPlan* out) {
     const uint32_t layout = sp.row_bytes == 128 ? 2u : (sp.row_bytes == 64 ? 4u : 6u);
     d.desc_hi = ((uint32_t)(8 * sp.row_bytes) >> 4) | (1u << 14) | (layout << 29);
     d.taps = sp.taps; d.kw = g.kw; d.dil_h = g.dil_h; d.dil_w = g.dil_w; d.pad_h = g.pad_h; d.pad_w = g.pad_w;
-    d.k_begin = sp.k_begin;
+    d.k_begin = sp.k_begin; d.nch = sp.nch;
   }
+  out->mode_b = pl.mode_b;
   out->Hp = pl.Hp; out->Wp = pl.Wp; out->PLh = pl.PLh; out->PLw = pl.PLw;
   out->K_total = pl.K_total; out->KB = pl.KB; out->BLOCK_N = pl.BLOCK_N; out->NS = pl.NS;
   out->w_bytes = pl.ws_bytes;

@@ -255,19 +255,27 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
   const bool tcm = tc_step_ok(cfg);
   TcConv rT = rec_bwd_conv(cfg, io->recurrent, g);
   TcConv kT = in_bwd_conv(cfg, io->kernel, g);
+  bool seq = false;
   if (tcm) {
     float* pk = Kt + (size_t)cfg->kh * cfg->kw * cfg->Cin * 4 * F + 64;
     rT.ws = pk;
     kT.ws = pk + tc_conv_ws_bytes(rT) / 4 + 64;
-    if ((rc = tc_conv_pack(rT, st))) return rc;
-    rT.prepacked = 1;
+    // whole images per MMA tile and no gradient w.r.t. an initial hidden state: the persistent kernel walks the
+    // whole reverse time loop in one launch (convlstm_seq_bwd_tc.cu)
+    seq = !(io->h0 && gr->dh0) && tc_convlstm_seq_bwd_supported(cfg, rT);
+    if (seq) {
+      if ((rc = tc_convlstm_seq_bwd(cfg, io, gr, rT, st))) return rc;
+    } else {
+      if ((rc = tc_conv_pack(rT, st))) return rc;
+      rT.prepacked = 1;
+    }
   } else {
     if ((rc = fov_conv_flip_weights(&r, io->recurrent, Rt, st))) return rc;
   }
 
   const float* dc_in = gr->dcT;
   const float* dh_in = gr->dhT;
-  for (int t = cfg->T - 1; t >= 0; --t) {
+  for (int t = cfg->T - 1; t >= 0 && !seq; --t) {
     float* zt = io->gates + t * g.z_t;
     GatesBwdArgs a{};
     a.npix = (long long)cfg->B * g.HW; a.HW = g.HW; a.F = F; a.rec = cfg->rec_act;

@@ -1,0 +1,408 @@
+// Persistent ConvLSTM2D BPTT on tensor cores (tcgen05 + TMEM): ONE launch walks every timestep backwards.
+//
+// Same residency idea as the forward kernel (convlstm_seq_tc.cu): a group of G whole images (zero-padded frame,
+// G * Hp*Wp <= 128 positions) stays on one SM for the whole sequence.
+//   * R^T (the flipped / transposed recurrent kernel, every k-block, all bf16 terms) is bulk-copied to shared
+//     memory once;
+//   * per step t (T-1 .. 0) the 256 worker threads of the group compute the gate gradients
+//         dh = dh_ext[t] + dh_rec ;  dc_t = dh * o * (1 - tanh(c_t)^2) + dc ;  dZ_t = (di, df, dg, do)
+//     with a CHANNEL-fastest thread mapping, so every global access (saved gates, c_t, c_{t-1}, dh_ext, dZ_t) is a
+//     coalesced float4 row segment; dc stays in registers;
+//   * dZ_t is written to HBM (in place of the saved gates: the weight-gradient and input-gradient kernels read
+//     it later) AND, split into bf16 terms, into the swizzled operand rows of the recurrent backward-data GEMM
+//         dh_rec_{t-1}[pos][F] = sum_taps dZ_t[pos + shift][4F] x R^T        (shifted-tap descriptors, conv_tc.cu)
+//     whose accumulator lives in TMEM; the workers read it back through a small shared-memory transpose
+//     (accumulator rows are one-row-per-thread, the gate algebra wants channel-fastest);
+//   * the next step's saved tensors are fetched into registers BEFORE waiting for the MMAs of the current one.
+// No per-step launch (the per-timestep path needs 2 launches per step) and no dh/dc round trip through HBM.
+//
+// Replaces the reverse ConvLSTM2D time loop of TF1's BPTT.
+#include "fov_common.cuh"
+#include "fov_internal.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int kRows = 128;
+constexpr int kWorkers = 256;            // warps 0-7: (row, 4-channel) items, channel fastest
+constexpr int kBWWarp = 8, kBMmaWarp = 9;
+constexpr int kBThr = 320;
+constexpr int kMaxSteps = 256;           // k16 steps of the GEMM (taps * 4F / 16)
+constexpr int kMaxItems = 8;             // (row, c4) items per worker thread: 128 * F/4 / 256
+
+struct BwdParams {
+  int B, T, H, W, HW, Hp, Wp, PLh, PLw, HpWp, G, rec_act, dbg;
+  int F, Cin_p, nch, row_bytes, swz_mask, term_bytes, R, minshift, taps, kw, pad_h, pad_w;
+  uint32_t desc_hi;
+  int K_total, KB, BLOCK_N;
+  uint32_t w_bytes, kb_bytes, chunk_bytes, act_off, dh_off, data_bytes, tmem_cols;
+  const uint8_t* wpk;
+  float* gates; long long z_b, z_t;              // in: activated gates, out: dZ   (B,T,HW,4F)
+  const float* cseq; long long c_b, c_t;         // (B,T,HW,F)
+  const float* c0;                               // optional dense (B,HW,F)
+  const float* dhseq; long long dh_b, dh_t; int dh_pix;   // optional gradient w.r.t. the hidden sequence
+  const float *dhT, *dcT;                        // optional dense (B,HW,F)
+  float* dc0;                                    // optional dense (B,HW,F)
+};
+
+struct BwdBook {
+  uint2 ops[kMaxSteps];                          // per k16 step: (a_rel, b_rel)
+  uint64_t w_full, a_full, tmem_full;
+  uint32_t tmem_ptr;
+};
+
+__device__ unsigned long long g_bwd_timeline[8];
+
+template <int NS, int F>
+__global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_kernel(const BwdParams p) {
+  constexpr int N4F = 4 * F;
+  constexpr int LPR = F / 4;                       // float4 per row of an F-channel tensor
+  constexpr int NIT = kRows * LPR / kWorkers;      // items per worker thread (1, 2, 4, 8)
+  constexpr int RSTEP = kWorkers / LPR;            // rows between the items of a thread
+  constexpr int DHS = F + 4;                       // floats per row of the dh transpose tile
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  BwdBook* bk = reinterpret_cast<BwdBook*>(smem + p.data_bytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nsteps = p.K_total / 16;
+
+  if (warp == kBMmaWarp && lane == 0) {
+    mbar_init(smem_u32(&bk->w_full), 1);
+    mbar_init(smem_u32(&bk->a_full), kWorkers);
+    mbar_init(smem_u32(&bk->tmem_full), 1);
+    fence_mbar_init();
+    // operand addresses of every k16 step: k = tap * Cin_p + channel; channel chunk cc = 64-wide region
+    for (int e = 0; e < nsteps; ++e) {
+      const int k = e * 16;
+      const int tap = k / p.Cin_p, ci0 = k - tap * p.Cin_p;
+      const int cc = ci0 >> 6, c0 = ci0 & 63;
+      const int ty = tap / p.kw, tx = tap - ty * p.kw;
+      const int shift = (ty - p.pad_h) * p.Wp + (tx - p.pad_w) - p.minshift;
+      const int kb = p.nch > 1 ? tap * p.nch + cc : k >> 6;
+      bk->ops[e] = make_uint2(p.act_off + (uint32_t)cc * p.chunk_bytes + (uint32_t)shift * p.row_bytes + (uint32_t)c0 * 2u,
+                              (uint32_t)kb * p.kb_bytes + (uint32_t)((k >> 4) & 3) * 32u);
+    }
+  }
+  if (warp == kBWWarp) {
+    tmem_alloc(smem_u32(&bk->tmem_ptr), p.tmem_cols);
+    tmem_relinquish();
+  }
+  // dZ rows of pad positions stay zero for the whole sequence
+  for (uint32_t i = (uint32_t)tid * 16u; i < (uint32_t)p.nch * p.chunk_bytes; i += (uint32_t)kBThr * 16u)
+    *reinterpret_cast<uint4*>(smem + p.act_off + i) = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = bk->tmem_ptr;
+
+  if (warp < kWorkers / 32) {
+    // ---------------- workers ----------------
+    const int b0 = blockIdx.x * p.G;
+    const int npos = p.G * p.HpWp;
+    float* dh_s = reinterpret_cast<float*>(smem + p.dh_off);          // [128 rows][F + 4]
+    const int c4 = tid % LPR, ch = c4 * 4;
+    const int row0 = tid / LPR;
+    // my items: rows row0 + j * RSTEP, channels ch .. ch+3
+    int off_g[NIT], off_c[NIT], off_h[NIT], off_d[NIT];
+    uint32_t so[NIT];
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      const int m = row0 + j * RSTEP;
+      off_g[j] = off_c[j] = off_h[j] = off_d[j] = -1;
+      if (m < npos) {
+        const int bi = m / p.HpWp, rem = m - bi * p.HpWp;
+        const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
+        const int y = yp - p.PLh, x = xp - p.PLw;
+        const int b = b0 + bi;
+        if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && b < p.B) {
+          const int pix = y * p.W + x;
+          off_g[j] = (int)((long long)b * p.z_b + (long long)pix * N4F) + ch;
+          off_c[j] = (int)((long long)b * p.c_b + (long long)pix * F) + ch;
+          off_h[j] = (int)((long long)b * p.dh_b + (long long)pix * p.dh_pix) + ch;
+          off_d[j] = (int)(((long long)b * p.HW + pix) * F) + ch;
+        }
+      }
+      so[j] = (uint32_t)(m - p.minshift) * (uint32_t)p.row_bytes;      // my row of the dZ operand region
+    }
+    float4 dc[NIT];
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      dc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.dcT && off_d[j] >= 0) dc[j] = __ldg(reinterpret_cast<const float4*>(p.dcT + off_d[j]));
+    }
+    // accumulator read-back: warp w reads TMEM lanes 32*(w&3).., columns [(w>>2) * F/2, +F/2)
+    const int q = warp & 3, half = warp >> 2;
+    constexpr int HC = F / 2 < 8 ? 8 : F / 2;                         // columns per warp (8 at F = 8: both halves read all)
+    const uint32_t t_row = tmem_d + ((uint32_t)(q * 32) << 16);
+    const bool dbg = p.dbg && blockIdx.x == 0 && tid == 0;
+    long long tw = 0, tcmp = 0, k0 = 0, k1 = 0;
+    const long long t_begin = clock64();
+
+    float4 vg[NIT][4], vc[NIT], vp[NIT], vh[NIT];
+    auto load_step = [&](int t) {
+      const float* gt = p.gates + (long long)t * p.z_t;
+      const float* ct = p.cseq + (long long)t * p.c_t;
+#pragma unroll
+      for (int j = 0; j < NIT; ++j) {
+        const bool ok = off_g[j] >= 0;
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi)
+          vg[j][gi] = ok ? __ldg(reinterpret_cast<const float4*>(gt + off_g[j] + gi * F)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vc[j] = ok ? __ldg(reinterpret_cast<const float4*>(ct + off_c[j])) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+          if (t > 0) vp[j] = __ldg(reinterpret_cast<const float4*>(ct - p.c_t + off_c[j]));
+          else if (p.c0) vp[j] = __ldg(reinterpret_cast<const float4*>(p.c0 + off_d[j]));
+        }
+        vh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && p.dhseq) vh[j] = __ldg(reinterpret_cast<const float4*>(p.dhseq + (long long)t * p.dh_t + off_h[j]));
+      }
+    };
+    load_step(p.T - 1);
+    for (int t = p.T - 1; t >= 0; --t) {
+      // ---- dh_rec of this step: dhT at the last step, else the accumulator of the GEMM issued at step t+1 ----
+      float4 dr[NIT];
+      if (t == p.T - 1) {
+#pragma unroll
+        for (int j = 0; j < NIT; ++j) {
+          dr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.dhT && off_d[j] >= 0) dr[j] = __ldg(reinterpret_cast<const float4*>(p.dhT + off_d[j]));
+        }
+      } else {
+        if (dbg) k0 = clock64();
+        mbar_wait(smem_u32(&bk->tmem_full), (uint32_t)(p.T - 2 - t) & 1u);
+        tc_fence_after();
+        if (dbg) { k1 = clock64(); tw += k1 - k0; }
+        if (F >= 16 || half == 0) {
+          float v[HC];
+#pragma unroll
+          for (int c = 0; c < HC; c += 8) tmem_ld8(t_row + (uint32_t)((F >= 16 ? half * HC : 0) + c), v + c);
+          tmem_ld_wait();
+          float* dst = dh_s + (q * 32 + lane) * DHS + (F >= 16 ? half * HC : 0);
+#pragma unroll
+          for (int c = 0; c < HC; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
+#pragma unroll
+        for (int j = 0; j < NIT; ++j)
+          dr[j] = *reinterpret_cast<const float4*>(dh_s + (row0 + j * RSTEP) * DHS + ch);
+      }
+      // ---- gate gradients of my items ----
+      float* gz = p.gates + (long long)t * p.z_t;
+#pragma unroll
+      for (int j = 0; j < NIT; ++j) {
+        if (off_g[j] < 0) continue;
+        const float gi_[4] = {vg[j][0].x, vg[j][0].y, vg[j][0].z, vg[j][0].w};
+        const float gf_[4] = {vg[j][1].x, vg[j][1].y, vg[j][1].z, vg[j][1].w};
+        const float gg_[4] = {vg[j][2].x, vg[j][2].y, vg[j][2].z, vg[j][2].w};
+        const float go_[4] = {vg[j][3].x, vg[j][3].y, vg[j][3].z, vg[j][3].w};
+        const float ct_[4] = {vc[j].x, vc[j].y, vc[j].z, vc[j].w};
+        const float cp_[4] = {vp[j].x, vp[j].y, vp[j].z, vp[j].w};
+        const float dh_[4] = {vh[j].x + dr[j].x, vh[j].y + dr[j].y, vh[j].z + dr[j].z, vh[j].w + dr[j].w};
+        float dcv[4] = {dc[j].x, dc[j].y, dc[j].z, dc[j].w};
+        float dz[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float tc_ = tanhf(ct_[e]);
+          const float dog = dh_[e] * tc_;
+          const float dct = fmaf(dh_[e] * go_[e], 1.0f - tc_ * tc_, dcv[e]);
+          dcv[e] = dct * gf_[e];
+          dz[0][e] = dct * gg_[e] * fov_rec_act_grad_rt(p.rec_act, gi_[e]);
+          dz[1][e] = dct * cp_[e] * fov_rec_act_grad_rt(p.rec_act, gf_[e]);
+          dz[2][e] = dct * gi_[e] * (1.0f - gg_[e] * gg_[e]);
+          dz[3][e] = dog * fov_rec_act_grad_rt(p.rec_act, go_[e]);
+        }
+        dc[j] = make_float4(dcv[0], dcv[1], dcv[2], dcv[3]);
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          const float4 z4 = make_float4(dz[gi][0], dz[gi][1], dz[gi][2], dz[gi][3]);
+          *reinterpret_cast<float4*>(gz + off_g[j] + gi * F) = z4;
+          // bf16 terms into the operand rows: channel gi*F + ch of chunk (channel / 64)
+          const int zc = gi * F + ch;
+          const uint32_t a0 = so[j] + (uint32_t)(zc & 63) * 2u;
+          const uint32_t sw = a0 ^ (((a0 >> 7) & (uint32_t)p.swz_mask) << 4);
+          uint2 pk[NS];
+          split4<NS>(z4, pk);
+          uint8_t* dstc = smem + p.act_off + (uint32_t)(zc >> 6) * p.chunk_bytes;
+#pragma unroll
+          for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(dstc + s * p.term_bytes + sw) = pk[s];
+        }
+      }
+      if (t > 0) {
+        fence_proxy_async_smem();
+        mbar_arrive(smem_u32(&bk->a_full));
+        load_step(t - 1);                         // in flight while the GEMM of this step runs
+      } else if (p.dc0) {
+#pragma unroll
+        for (int j = 0; j < NIT; ++j)
+          if (off_d[j] >= 0) *reinterpret_cast<float4*>(p.dc0 + off_d[j]) = dc[j];
+      }
+      if (dbg) tcmp += clock64() - k1;
+    }
+    if (dbg) { g_bwd_timeline[0] = tw; g_bwd_timeline[1] = tcmp; g_bwd_timeline[2] = clock64() - t_begin; }
+  } else if (warp == kBWWarp) {
+    if (lane == 0) {
+      const uint32_t bar = smem_u32(&bk->w_full);
+      mbar_arrive_expect_tx(bar, p.w_bytes);
+      for (int kb = 0; kb < p.KB; ++kb)
+        bulk_g2s(base + (uint32_t)kb * p.kb_bytes, p.wpk + (size_t)kb * p.kb_bytes, p.kb_bytes, bar);
+    }
+  } else {
+    // ---------------- MMA issuer: dh_rec_{t-1} = conv^T(dZ_t, R), one chain per step ----------------
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16_f32(kRows, p.BLOCK_N, 0, 0);
+      const uint32_t b_term = (uint32_t)p.BLOCK_N * 128u;
+      mbar_wait(smem_u32(&bk->w_full), 0);
+      const bool dbg = p.dbg && blockIdx.x == 0;
+      long long mw = 0, mi = 0;
+      for (int t = p.T - 1; t > 0; --t) {
+        const long long q0 = clock64();
+        mbar_wait(smem_u32(&bk->a_full), (uint32_t)(p.T - 1 - t) & 1u);
+        tc_fence_after();
+        const long long q1 = clock64();
+        mw += q1 - q0;
+        for (int e = 0; e < nsteps; ++e) {
+          const uint2 o = bk->ops[e];
+#pragma unroll
+          for (int sum = NS - 1; sum >= 0; --sum) {
+#pragma unroll
+            for (int sa = 0; sa <= sum; ++sa) {
+              const int sb = sum - sa;
+              umma_bf16(tmem_d, desc_at(p.desc_hi, base + o.x + sa * p.term_bytes),
+                        desc_at(kDescHi128, base + o.y + sb * b_term), idesc, (e > 0 || sum != NS - 1 || sa > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(smem_u32(&bk->tmem_full));
+        mi += clock64() - q1;
+      }
+      if (dbg) { g_bwd_timeline[4] = mw; g_bwd_timeline[5] = mi; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kBWWarp) tmem_dealloc(tmem_d, p.tmem_cols);
+}
+
+struct BwdPlan {
+  TcStepPlan sp;
+  int G;
+  uint32_t chunk_bytes, act_off, dh_off, data_bytes, tmem_cols;
+  size_t smem_bytes;
+};
+
+int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, BwdPlan* out) {
+  BwdPlan pl{};
+  int rc = tc_conv_step_plan(rT, &pl.sp);
+  if (rc) return rc;
+  const TcStepPlan& sp = pl.sp;
+  const TcStepSeg& sg = sp.seg[0];
+  const int F = c->F;
+  FOV_CHECK_ARG(sp.nseg == 1, "single segment expected");
+  FOV_CHECK_ARG(F == 8 || F == 16 || F == 32 || F == 64, "F must be 8/16/32/64");
+  pl.G = kRows / (sp.Hp * sp.Wp);
+  FOV_CHECK_ARG(pl.G >= 1, "image larger than one MMA tile");
+  FOV_CHECK_ARG(sp.K_total / 16 <= kMaxSteps, "too many k steps");
+  FOV_CHECK_ARG(kRows * (F / 4) / kWorkers <= kMaxItems, "too many channels");
+  pl.chunk_bytes = (uint32_t)sp.NS * (uint32_t)sg.term_bytes;
+  pl.act_off = (uint32_t)((sp.w_bytes + 1023) / 1024 * 1024);
+  pl.dh_off = pl.act_off + (uint32_t)sg.nch * pl.chunk_bytes;
+  pl.data_bytes = (pl.dh_off + (uint32_t)(kRows * (F + 4) * 4) + 1023u) / 1024u * 1024u;
+  pl.smem_bytes = pl.data_bytes + sizeof(BwdBook) + 1024;
+  FOV_CHECK_ARG(pl.smem_bytes <= 227 * 1024, "persistent BPTT: weights + operands exceed shared memory");
+  pl.tmem_cols = tmem_cols_for(sp.BLOCK_N);
+  const long long HW = (long long)c->H * c->W;
+  FOV_CHECK_ARG((long long)c->B * c->T * HW * 4 * F < (1LL << 31) && (long long)c->B * c->h_b_stride < (1LL << 31),
+                "tensors too large for 32-bit offsets");
+  *out = pl;
+  return FOV_OK;
+}
+
+template <int NS, int F>
+int launch_bwd(const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(convlstm_seq_bwd_kernel<NS, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) {
+      fov_set_error("convlstm_seq_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return FOV_ERR_CUDA;
+    }
+    configured = true;
+  }
+  convlstm_seq_bwd_kernel<NS, F><<<grid, kBThr, pl.smem_bytes, st>>>(p);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
+template <int NS>
+int launch_bwd_f(int F, const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t st) {
+  switch (F) {
+    case 8: return launch_bwd<NS, 8>(p, pl, grid, st);
+    case 16: return launch_bwd<NS, 16>(p, pl, grid, st);
+    case 32: return launch_bwd<NS, 32>(p, pl, grid, st);
+    default: return launch_bwd<NS, 64>(p, pl, grid, st);
+  }
+}
+
+}  // namespace
+
+static int g_bwd_disable = 0, g_bwd_dbg = 0;
+extern "C" void fov_debug_convlstm_persistent_bwd(int enable) { g_bwd_disable = !enable; }
+extern "C" void fov_debug_seq_bwd_enable(int on) { g_bwd_dbg = on; }
+extern "C" int fov_debug_seq_bwd_read(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_bwd_timeline, sizeof(unsigned long long) * 8);
+}
+
+bool tc_convlstm_seq_bwd_supported(const fov_convlstm_cfg* c, const TcConv& rT) {
+  if (g_bwd_disable) return false;
+  BwdPlan pl;
+  const bool ok = bwd_plan(c, rT, &pl) == FOV_OK;
+  fov_set_error("");
+  return ok;
+}
+
+// rT: the recurrent backward-data convolution of this layer (convlstm.cu rec_bwd_conv) with ws = its packed-weight
+// workspace.  Runs the whole reverse time loop: gates (in: activated gates, out: dZ), optional dc0.  dh0 is not
+// produced (callers that need it use the per-timestep path).
+int tc_convlstm_seq_bwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const fov_convlstm_grads* gr,
+                        const TcConv& rT, cudaStream_t st) {
+  BwdPlan pl;
+  int rc = bwd_plan(c, rT, &pl);
+  if (rc) return rc;
+  if ((rc = tc_conv_pack(rT, st))) return rc;
+  const TcStepPlan& sp = pl.sp;
+  const TcStepSeg& sg = sp.seg[0];
+  BwdParams p{};
+  const int HW = c->H * c->W, F = c->F;
+  p.B = c->B; p.T = c->T; p.H = c->H; p.W = c->W; p.HW = HW; p.Hp = sp.Hp; p.Wp = sp.Wp; p.PLh = sp.PLh; p.PLw = sp.PLw;
+  p.HpWp = sp.Hp * sp.Wp; p.G = pl.G; p.rec_act = c->rec_act; p.dbg = g_bwd_dbg;
+  p.F = F; p.Cin_p = sg.Cin_p; p.nch = sg.nch; p.row_bytes = sg.row_bytes; p.swz_mask = sg.swz_mask;
+  p.term_bytes = sg.term_bytes; p.R = sg.R; p.minshift = sg.minshift; p.taps = sg.taps; p.kw = sg.kw;
+  p.pad_h = sg.pad_h; p.pad_w = sg.pad_w; p.desc_hi = sg.desc_hi;
+  p.K_total = sp.K_total; p.KB = sp.KB; p.BLOCK_N = sp.BLOCK_N;
+  p.w_bytes = (uint32_t)sp.w_bytes; p.kb_bytes = (uint32_t)(sp.NS * sp.BLOCK_N * 128);
+  p.chunk_bytes = pl.chunk_bytes; p.act_off = pl.act_off; p.dh_off = pl.dh_off; p.data_bytes = pl.data_bytes;
+  p.tmem_cols = pl.tmem_cols;
+  p.wpk = reinterpret_cast<const uint8_t*>(((uintptr_t)rT.ws + 255) & ~(uintptr_t)255);
+  p.gates = io->gates; p.z_t = (long long)HW * 4 * F; p.z_b = p.z_t * c->T;
+  p.cseq = io->cseq; p.c_t = (long long)HW * F; p.c_b = p.c_t * c->T;
+  p.c0 = io->c0;
+  p.dhseq = gr->dhseq; p.dh_b = c->h_b_stride; p.dh_t = c->h_t_stride; p.dh_pix = c->h_pix_stride;
+  p.dhT = gr->dhT; p.dcT = gr->dcT; p.dc0 = gr->dc0;
+  auto a16 = [](const void* q) { return (uintptr_t)q % 16 == 0; };
+  FOV_CHECK_ARG(a16(io->gates) && a16(io->cseq) && a16(io->c0) && a16(gr->dhseq) && a16(gr->dhT) && a16(gr->dcT) &&
+                    a16(gr->dc0) && c->h_pix_stride % 4 == 0 && c->h_b_stride % 4 == 0 && c->h_t_stride % 4 == 0,
+                "persistent BPTT needs 16-byte aligned tensors");
+  const int grid = (c->B + pl.G - 1) / pl.G;
+  switch (sp.NS) {
+    case 1: return launch_bwd_f<1>(F, p, pl, grid, st);
+    case 2: return launch_bwd_f<2>(F, p, pl, grid, st);
+    default: return launch_bwd_f<3>(F, p, pl, grid, st);
+  }
+}

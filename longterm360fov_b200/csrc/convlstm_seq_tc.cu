@@ -407,7 +407,7 @@ int seq_plan(const fov_convlstm_cfg* c, const TcConv& step, SeqPlan* out) {
   int rc = tc_conv_step_plan(step, &pl.sp);
   if (rc) return rc;
   const TcStepPlan& sp = pl.sp;
-  FOV_CHECK_ARG(sp.nseg == 2, "two-segment step expected");
+  FOV_CHECK_ARG(sp.nseg == 2 && !sp.mode_b, "two-segment step with <= 64 channels per segment expected");
   const int F = c->F;
   FOV_CHECK_ARG(F == 8 || F == 16 || F == 32 || F == 64, "F must be 8/16/32/64");
   pl.G = kRows / (sp.Hp * sp.Wp);

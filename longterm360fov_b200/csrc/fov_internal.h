@@ -77,10 +77,12 @@ struct TcConv {
 struct TcStepSeg {
   int Cin, Cin_p, cp_log2, cw, lpr_log2, row_bytes, swz_mask, term_bytes, R, minshift;
   int taps, kw, dil_h, dil_w, pad_h, pad_w, k_begin;
+  int nch;          // 64-channel chunks of the segment (> 1: k order is tap-major inside each chunk pair, see conv_tc.cu)
   unsigned desc_hi;
 };
 struct TcStepPlan {
   TcStepSeg seg[2];
+  int mode_b;       // segment wider than 64 channels: regions hold nch chunks of R rows x 128 B
   int nseg, Hp, Wp, PLh, PLw, K_total, KB, BLOCK_N, NS;
   size_t w_bytes;   // packed weights: KB x NS x BLOCK_N x 128 B
 };
@@ -93,6 +95,10 @@ int tc_conv_run(const TcConv& c, cudaStream_t st);
 // Persistent ConvLSTM2D layer (convlstm_seq_tc.cu): every timestep in one launch when whole images fit a tile.
 bool tc_convlstm_seq_supported(const fov_convlstm_cfg* c, const TcConv& step);
 int tc_convlstm_seq_fwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const TcConv& step, cudaStream_t st);
+
+bool tc_convlstm_seq_bwd_supported(const fov_convlstm_cfg* c, const TcConv& rT);
+int tc_convlstm_seq_bwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const fov_convlstm_grads* gr,
+                        const TcConv& rT, cudaStream_t st);
 
 // Tensor-core weight gradient: gw[(tap*Cin+ci)*Cout+n] += sum_pixels x(pixel+tap, ci) * dy(pixel, n),
 // gbias[n] += sum_pixels dy(pixel, n).  Both operands are read in their natural NHWC layout and

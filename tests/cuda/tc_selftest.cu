@@ -226,6 +226,8 @@ static void test_conv(const char* name, fov_conv_cfg c, bool time_it) {
 
 // ConvLSTM layer: SIMT (math 0) vs fused tensor-core step (math 1..3), forward + BPTT
 extern "C" void fov_debug_wgrad_rows_timeline(int on);
+extern "C" void fov_debug_seq_bwd_enable(int on);
+extern "C" int fov_debug_seq_bwd_read(unsigned long long* out);
 extern "C" int fov_debug_wgrad_rows_read(unsigned long long* out);
 static void test_convlstm(const char* name, int B, int T, int H, int W, int Cin, int F, int kh, int kw, bool with_state,
                           bool time_it) {
@@ -281,12 +283,17 @@ static void test_convlstm(const char* name, int B, int T, int H, int W, int Cin,
     g.dx_accumulate = 0;
     // the BPTT overwrites the saved gates: keep a copy for the comparison
     float* gates_keep = dev_copy(r.gates, nz);
-    if (time_it) { tm.start(); fov_debug_wgrad_rows_timeline(1); }
+    if (time_it) { tm.start(); fov_debug_wgrad_rows_timeline(1); fov_debug_seq_bwd_enable(1); }
     FK(fov_convlstm_bwd(&c, &io, &g, nullptr));
     if (time_it) {
       printf("  time convlstm bwd math=%d: %.3f ms\n", math, tm.stop_ms());
       fov_debug_wgrad_rows_timeline(0);
+      fov_debug_seq_bwd_enable(0);
       unsigned long long w[8];
+      fov_debug_seq_bwd_read(w);
+      if (math > 0)
+        printf("    seq_bwd CTA0 cycles: worker wait-mma %llu, compute+io %llu, total %llu | mma: wait %llu, issue %llu\n",
+               w[0], w[1], w[2], w[4], w[5]);
       fov_debug_wgrad_rows_read(w);
       if (math > 0)
         printf("    wgrad_rows CTA0 (%llu tiles) cycles: producer wait %llu, dZ stage %llu, rows %llu, total %llu | mma: wait %llu, "
@@ -328,6 +335,7 @@ static void test_convlstm(const char* name, int B, int T, int H, int W, int Cin,
 extern "C" void fov_debug_convlstm_persistent(int enable);
 extern "C" void fov_debug_seq_enable(int on);
 extern "C" void fov_debug_wgrad_rows(int enable);
+extern "C" void fov_debug_convlstm_persistent_bwd(int enable);
 
 extern "C" int fov_debug_seq_read(unsigned long long* out);
 static void test_convlstm_seq(const char* name, int B, int T, int H, int W, int Cin, int F, int kh, int kw,
@@ -487,9 +495,10 @@ int main(int argc, char** argv) {
     test_convlstm("m3 L2", 5, 3, 1, 33, 16, 8, 1, 5, false, false);
     test_convlstm("3x3 on 5x4", 9, 3, 5, 4, 12, 16, 3, 3, true, false);
     test_convlstm("traj 1x30 Cin 3", 4, 6, 1, 30, 3, 32, 1, 5, true, false);
-    for (int on = 0; on < 2; ++on) {
-      fov_debug_wgrad_rows(on);
-      printf("=== fused row-shift wgrad %s ===\n", on ? "ON" : "OFF");
+    for (int on = 0; on < 3; ++on) {
+      fov_debug_wgrad_rows(on >= 1);
+      fov_debug_convlstm_persistent_bwd(on >= 2);
+      printf("=== fused row-shift wgrad %s, persistent BPTT %s ===\n", on >= 1 ? "ON" : "OFF", on >= 2 ? "ON" : "OFF");
       test_convlstm("T m3 L0 B=2048", 2048, 20, 1, 33, 6, 32, 1, 5, false, true);
       test_convlstm("T m3 L1 B=2048", 2048, 20, 1, 33, 32, 16, 1, 5, false, true);
       test_convlstm("T m3 L2 B=2048", 2048, 20, 1, 33, 16, 8, 1, 5, false, true);
