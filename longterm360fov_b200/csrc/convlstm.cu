@@ -255,16 +255,19 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
   const bool tcm = tc_step_ok(cfg);
   TcConv rT = rec_bwd_conv(cfg, io->recurrent, g);
   TcConv kT = in_bwd_conv(cfg, io->kernel, g);
-  bool seq = false;
+  bool seq = false, dx_fused = false;
   if (tcm) {
     float* pk = Kt + (size_t)cfg->kh * cfg->kw * cfg->Cin * 4 * F + 64;
     rT.ws = pk;
     kT.ws = pk + tc_conv_ws_bytes(rT) / 4 + 64;
     // whole images per MMA tile and no gradient w.r.t. an initial hidden state: the persistent kernel walks the
     // whole reverse time loop in one launch (convlstm_seq_bwd_tc.cu)
-    seq = !(io->h0 && gr->dh0) && tc_convlstm_seq_bwd_supported(cfg, rT);
+    if (!(io->h0 && gr->dh0)) {
+      if (gr->dx && tc_convlstm_seq_bwd_supported(cfg, rT, &kT)) { seq = true; dx_fused = true; }
+      else if (tc_convlstm_seq_bwd_supported(cfg, rT, nullptr)) seq = true;
+    }
     if (seq) {
-      if ((rc = tc_convlstm_seq_bwd(cfg, io, gr, rT, st))) return rc;
+      if ((rc = tc_convlstm_seq_bwd(cfg, io, gr, rT, dx_fused ? &kT : nullptr, st))) return rc;
     } else {
       if ((rc = tc_conv_pack(rT, st))) return rc;
       rT.prepacked = 1;
@@ -303,7 +306,7 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
 
   if (tcm) {
     // ---- tensor-core path: dx, gK (+ bias gradient) and gR, each one launch over every (b,t) image ----
-    if (gr->dx) {
+    if (gr->dx && !dx_fused) {
       kT.seg[0].x = io->gates; kT.y = gr->dx; kT.beta = gr->dx_accumulate ? 1.0f : 0.0f;
       if ((rc = tc_conv_run(kT, st))) return rc;
     }

@@ -45,6 +45,10 @@ struct BwdParams {
   const float* dhseq; long long dh_b, dh_t; int dh_pix;   // optional gradient w.r.t. the hidden sequence
   const float *dhT, *dcT;                        // optional dense (B,HW,F)
   float* dc0;                                    // optional dense (B,HW,F)
+  // fused input gradient (optional): dx_t = conv^T(dZ_t, K) rides in the same MMAs as extra accumulator columns
+  float* dx; long long x_b, x_t; int x_pix, Cin, Cp, Fp, dx_accumulate;
+  const uint8_t* wpk2;                           // packed K^T (same k order), NULL: no dx
+  uint32_t kb1_bytes, kb2_bytes;                 // bytes of one (k-block, term) tile of R^T / K^T
 };
 
 struct BwdBook {
@@ -55,7 +59,8 @@ struct BwdBook {
 
 __device__ unsigned long long g_bwd_timeline[8];
 
-template <int NS, int F>
+// DXN: accumulator columns of the fused input gradient each worker thread reads back (0: no fused dx)
+template <int NS, int F, int DXN>
 __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_kernel(const BwdParams p) {
   constexpr int N4F = 4 * F;
   constexpr int LPR = F / 4;                       // float4 per row of an F-channel tensor
@@ -108,12 +113,12 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
     const int c4 = tid % LPR, ch = c4 * 4;
     const int row0 = tid / LPR;
     // my items: rows row0 + j * RSTEP, channels ch .. ch+3
-    int off_g[NIT], off_c[NIT], off_h[NIT], off_d[NIT];
+    int off_g[NIT], off_c[NIT], off_h[NIT], off_d[NIT], off_xc[NIT];
     uint32_t so[NIT];
 #pragma unroll
     for (int j = 0; j < NIT; ++j) {
       const int m = row0 + j * RSTEP;
-      off_g[j] = off_c[j] = off_h[j] = off_d[j] = -1;
+      off_g[j] = off_c[j] = off_h[j] = off_d[j] = off_xc[j] = -1;
       if (m < npos) {
         const int bi = m / p.HpWp, rem = m - bi * p.HpWp;
         const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
@@ -125,6 +130,7 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
           off_c[j] = (int)((long long)b * p.c_b + (long long)pix * F) + ch;
           off_h[j] = (int)((long long)b * p.dh_b + (long long)pix * p.dh_pix) + ch;
           off_d[j] = (int)(((long long)b * p.HW + pix) * F) + ch;
+          if (DXN > 0) off_xc[j] = (int)((long long)b * p.x_b + (long long)pix * p.x_pix) + ch;
         }
       }
       so[j] = (uint32_t)(m - p.minshift) * (uint32_t)p.row_bytes;      // my row of the dZ operand region
@@ -139,7 +145,48 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
     const int q = warp & 3, half = warp >> 2;
     constexpr int HC = F / 2 < 8 ? 8 : F / 2;                         // columns per warp (8 at F = 8: both halves read all)
     const uint32_t t_row = tmem_d + ((uint32_t)(q * 32) << 16);
-    const bool dbg = p.dbg && blockIdx.x == 0 && tid == 0;
+    // fused dx: my accumulator row (frame position 32q + lane) and my half of its Cin columns
+    constexpr int kDxMax = DXN > 0 ? DXN : 8;
+    constexpr int dxn = DXN;                                            // = Cin / 2 columns per warp half
+    const int dxc0 = half * dxn;
+    const bool dx_me = DXN > 0;
+    float dxr[kDxMax];
+    auto dx_read = [&]() {            // warp-collective TMEM read of my dx columns (8 at a time)
+#pragma unroll
+      for (int c = 0; c < kDxMax; c += 8)
+        if (c < dxn) tmem_ld8(t_row + (uint32_t)(p.Fp + dxc0 + c), dxr + c);
+      tmem_ld_wait();
+    };
+    // dx leaves through the dh transpose tile in two phases of F columns (Cin = 2F: warp half h holds phase h),
+    // so the global read-modify-write is a coalesced, channel-fastest float4 row segment like everything else
+    auto dx_store = [&](int t) {
+      float* dxt = p.dx + (long long)t * p.x_t;
+      asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");     // every dh read of this step has been done
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph) {
+        if (half == ph) {
+          float* dst = dh_s + (q * 32 + lane) * DHS;
+#pragma unroll
+          for (int c = 0; c < kDxMax; c += 4)
+            if (c < dxn) *reinterpret_cast<float4*>(dst + c) = make_float4(dxr[c], dxr[c + 1], dxr[c + 2], dxr[c + 3]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
+#pragma unroll
+        for (int j = 0; j < NIT; ++j) {
+          if (off_xc[j] >= 0) {
+            float4 v = *reinterpret_cast<const float4*>(dh_s + (row0 + j * RSTEP) * DHS + ch);
+            float* g = dxt + off_xc[j] + ph * F;
+            if (p.dx_accumulate) {
+              const float4 o = *reinterpret_cast<const float4*>(g);
+              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *reinterpret_cast<float4*>(g) = v;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
+      }
+    };
+    const bool dbg = (p.dbg & 1) && blockIdx.x == 0 && tid == 0;
     long long tw = 0, tcmp = 0, k0 = 0, k1 = 0;
     const long long t_begin = clock64();
 
@@ -187,6 +234,7 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
 #pragma unroll
           for (int c = 0; c < HC; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
         }
+        if (dx_me) dx_read();                      // dx_{t+1}, stored after this step's operands are handed over
         tc_fence_before();
         asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
 #pragma unroll
@@ -234,24 +282,40 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
           for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(dstc + s * p.term_bytes + sw) = pk[s];
         }
       }
-      if (t > 0) {
+      if (t > 0 || p.wpk2) {
         fence_proxy_async_smem();
         mbar_arrive(smem_u32(&bk->a_full));
-        load_step(t - 1);                         // in flight while the GEMM of this step runs
-      } else if (p.dc0) {
+      }
+      if (t > 0) load_step(t - 1);                // in flight while the GEMM of this step runs
+      if (DXN > 0 && t < p.T - 1) dx_store(t + 1);
+      if (t == 0 && p.dc0) {
 #pragma unroll
         for (int j = 0; j < NIT; ++j)
           if (off_d[j] >= 0) *reinterpret_cast<float4*>(p.dc0 + off_d[j]) = dc[j];
       }
       if (dbg) tcmp += clock64() - k1;
     }
+    if (p.wpk2) {                                 // dx_0 from the GEMM issued at step 0
+      mbar_wait(smem_u32(&bk->tmem_full), (uint32_t)(p.T - 1) & 1u);
+      tc_fence_after();
+      if (DXN > 0) { dx_read(); dx_store(0); }
+    }
     if (dbg) { g_bwd_timeline[0] = tw; g_bwd_timeline[1] = tcmp; g_bwd_timeline[2] = clock64() - t_begin; }
   } else if (warp == kBWWarp) {
-    if (lane == 0) {
-      const uint32_t bar = smem_u32(&bk->w_full);
-      mbar_arrive_expect_tx(bar, p.w_bytes);
-      for (int kb = 0; kb < p.KB; ++kb)
-        bulk_g2s(base + (uint32_t)kb * p.kb_bytes, p.wpk + (size_t)kb * p.kb_bytes, p.kb_bytes, bar);
+    // ---------------- weights, once: B tile of a (k-block, term) = [Fp rows of R^T | Cp rows of K^T] x 128 B ----
+    // Copied in 16-row (2048-byte) pieces, one piece per lane and round: larger pieces into the interleaved layout
+    // faulted on hardware (4096-byte K^T tiles next to 2048-byte R^T tiles), 2048-byte pieces do not.
+    const uint32_t bar = smem_u32(&bk->w_full);
+    if (lane == 0) mbar_arrive_expect_tx(bar, p.w_bytes);
+    __syncwarp();
+    const int ppt = (p.Fp + p.Cp) >> 4;                      // pieces per (k-block, term) tile
+    const int npieces = p.KB * NS * ppt;
+    for (int i = lane; i < npieces; i += 32) {
+      const int tile = i / ppt, r16 = i - tile * ppt;        // tile = kb * NS + s
+      const uint32_t dst = base + (uint32_t)tile * (p.kb1_bytes + p.kb2_bytes) + (uint32_t)r16 * 2048u;
+      const uint8_t* src = r16 * 16 < p.Fp ? p.wpk + (size_t)tile * p.kb1_bytes + (size_t)r16 * 2048
+                                           : p.wpk2 + (size_t)tile * p.kb2_bytes + (size_t)(r16 * 16 - p.Fp) * 128;
+      bulk_g2s(dst, src, 2048u, bar);
     }
   } else {
     // ---------------- MMA issuer: dh_rec_{t-1} = conv^T(dZ_t, R), one chain per step ----------------
@@ -259,9 +323,10 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
       const uint32_t idesc = idesc_bf16_f32(kRows, p.BLOCK_N, 0, 0);
       const uint32_t b_term = (uint32_t)p.BLOCK_N * 128u;
       mbar_wait(smem_u32(&bk->w_full), 0);
-      const bool dbg = p.dbg && blockIdx.x == 0;
+      const bool dbg = (p.dbg & 1) && blockIdx.x == 0;
       long long mw = 0, mi = 0;
-      for (int t = p.T - 1; t > 0; --t) {
+      const int t_last = p.wpk2 ? 0 : 1;
+      for (int t = p.T - 1; t >= t_last; --t) {
         const long long q0 = clock64();
         mbar_wait(smem_u32(&bk->a_full), (uint32_t)(p.T - 1 - t) & 1u);
         tc_fence_after();
@@ -291,16 +356,31 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
 }
 
 struct BwdPlan {
-  TcStepPlan sp;
-  int G;
+  TcStepPlan sp, sp2;
+  int G, Fp, Cp, fuse_dx;
+  size_t w_bytes;
   uint32_t chunk_bytes, act_off, dh_off, data_bytes, tmem_cols;
   size_t smem_bytes;
 };
 
-int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, BwdPlan* out) {
+int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT, BwdPlan* out) {
   BwdPlan pl{};
   int rc = tc_conv_step_plan(rT, &pl.sp);
   if (rc) return rc;
+  pl.Fp = pl.sp.BLOCK_N; pl.Cp = 0; pl.fuse_dx = 0;
+  if (kT) {
+    // dx rides along when K^T has the k order / taps of R^T (same kernel size, no dilation) and Cin splits into
+    // 8-column pieces per warp half
+    if ((rc = tc_conv_step_plan(*kT, &pl.sp2))) return rc;
+    const TcStepSeg &a = pl.sp.seg[0], &b = pl.sp2.seg[0];
+    FOV_CHECK_ARG(pl.sp2.nseg == 1 && pl.sp2.K_total == pl.sp.K_total && pl.sp2.KB == pl.sp.KB && b.Cin_p == a.Cin_p &&
+                      b.taps == a.taps && b.kw == a.kw && b.pad_h == a.pad_h && b.pad_w == a.pad_w && b.dil_h == 1 &&
+                      b.dil_w == 1 && b.minshift == a.minshift && pl.sp2.Hp == pl.sp.Hp && pl.sp2.Wp == pl.sp.Wp &&
+                      (c->Cin == 16 || c->Cin == 32) && c->Cin == 2 * c->F,
+                  "input gradient cannot share the recurrent GEMM");
+    pl.Cp = pl.sp2.BLOCK_N; pl.fuse_dx = 1;
+  }
+  pl.w_bytes = (size_t)pl.sp.KB * pl.sp.NS * (pl.Fp + pl.Cp) * 128;
   const TcStepPlan& sp = pl.sp;
   const TcStepSeg& sg = sp.seg[0];
   const int F = c->F;
@@ -311,12 +391,13 @@ int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, BwdPlan* out) {
   FOV_CHECK_ARG(sp.K_total / 16 <= kMaxSteps, "too many k steps");
   FOV_CHECK_ARG(kRows * (F / 4) / kWorkers <= kMaxItems, "too many channels");
   pl.chunk_bytes = (uint32_t)sp.NS * (uint32_t)sg.term_bytes;
-  pl.act_off = (uint32_t)((sp.w_bytes + 1023) / 1024 * 1024);
+  pl.act_off = (uint32_t)((pl.w_bytes + 1023) / 1024 * 1024);
   pl.dh_off = pl.act_off + (uint32_t)sg.nch * pl.chunk_bytes;
   pl.data_bytes = (pl.dh_off + (uint32_t)(kRows * (F + 4) * 4) + 1023u) / 1024u * 1024u;
   pl.smem_bytes = pl.data_bytes + sizeof(BwdBook) + 1024;
   FOV_CHECK_ARG(pl.smem_bytes <= 227 * 1024, "persistent BPTT: weights + operands exceed shared memory");
-  pl.tmem_cols = tmem_cols_for(sp.BLOCK_N);
+  pl.tmem_cols = tmem_cols_for(pl.Fp + pl.Cp);
+  FOV_CHECK_ARG(!pl.fuse_dx || (long long)c->B * c->x_b_stride < (1LL << 31), "input too large for 32-bit offsets");
   const long long HW = (long long)c->H * c->W;
   FOV_CHECK_ARG((long long)c->B * c->T * HW * 4 * F < (1LL << 31) && (long long)c->B * c->h_b_stride < (1LL << 31),
                 "tensors too large for 32-bit offsets");
@@ -324,11 +405,11 @@ int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, BwdPlan* out) {
   return FOV_OK;
 }
 
-template <int NS, int F>
+template <int NS, int F, int DXN>
 int launch_bwd(const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(convlstm_seq_bwd_kernel<NS, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(convlstm_seq_bwd_kernel<NS, F, DXN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) {
       fov_set_error("convlstm_seq_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -336,17 +417,26 @@ int launch_bwd(const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t st)
     }
     configured = true;
   }
-  convlstm_seq_bwd_kernel<NS, F><<<grid, kBThr, pl.smem_bytes, st>>>(p);
+  convlstm_seq_bwd_kernel<NS, F, DXN><<<grid, kBThr, pl.smem_bytes, st>>>(p);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
+}
+template <int NS, int F>
+int launch_bwd_dx(const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t st) {
+  switch (p.wpk2 ? p.Cin / 2 : 0) {
+    case 0: return launch_bwd<NS, F, 0>(p, pl, grid, st);
+    case 8: return launch_bwd<NS, F, 8>(p, pl, grid, st);
+    case 16: return launch_bwd<NS, F, 16>(p, pl, grid, st);
+    default: fov_set_error("persistent BPTT: unsupported fused dx width"); return FOV_ERR_UNSUPPORTED;
+  }
 }
 template <int NS>
 int launch_bwd_f(int F, const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t st) {
   switch (F) {
-    case 8: return launch_bwd<NS, 8>(p, pl, grid, st);
-    case 16: return launch_bwd<NS, 16>(p, pl, grid, st);
-    case 32: return launch_bwd<NS, 32>(p, pl, grid, st);
-    default: return launch_bwd<NS, 64>(p, pl, grid, st);
+    case 8: return launch_bwd_dx<NS, 8>(p, pl, grid, st);
+    case 16: return launch_bwd_dx<NS, 16>(p, pl, grid, st);
+    case 32: return launch_bwd_dx<NS, 32>(p, pl, grid, st);
+    default: return launch_bwd_dx<NS, 64>(p, pl, grid, st);
   }
 }
 
@@ -359,10 +449,10 @@ extern "C" int fov_debug_seq_bwd_read(unsigned long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_bwd_timeline, sizeof(unsigned long long) * 8);
 }
 
-bool tc_convlstm_seq_bwd_supported(const fov_convlstm_cfg* c, const TcConv& rT) {
+bool tc_convlstm_seq_bwd_supported(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT) {
   if (g_bwd_disable) return false;
   BwdPlan pl;
-  const bool ok = bwd_plan(c, rT, &pl) == FOV_OK;
+  const bool ok = bwd_plan(c, rT, kT, &pl) == FOV_OK;
   fov_set_error("");
   return ok;
 }
@@ -371,11 +461,12 @@ bool tc_convlstm_seq_bwd_supported(const fov_convlstm_cfg* c, const TcConv& rT) 
 // workspace.  Runs the whole reverse time loop: gates (in: activated gates, out: dZ), optional dc0.  dh0 is not
 // produced (callers that need it use the per-timestep path).
 int tc_convlstm_seq_bwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const fov_convlstm_grads* gr,
-                        const TcConv& rT, cudaStream_t st) {
+                        const TcConv& rT, const TcConv* kT, cudaStream_t st) {
   BwdPlan pl;
-  int rc = bwd_plan(c, rT, &pl);
+  int rc = bwd_plan(c, rT, kT, &pl);
   if (rc) return rc;
   if ((rc = tc_conv_pack(rT, st))) return rc;
+  if (kT && (rc = tc_conv_pack(*kT, st))) return rc;
   const TcStepPlan& sp = pl.sp;
   const TcStepSeg& sg = sp.seg[0];
   BwdParams p{};
@@ -385,8 +476,18 @@ int tc_convlstm_seq_bwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, co
   p.F = F; p.Cin_p = sg.Cin_p; p.nch = sg.nch; p.row_bytes = sg.row_bytes; p.swz_mask = sg.swz_mask;
   p.term_bytes = sg.term_bytes; p.R = sg.R; p.minshift = sg.minshift; p.taps = sg.taps; p.kw = sg.kw;
   p.pad_h = sg.pad_h; p.pad_w = sg.pad_w; p.desc_hi = sg.desc_hi;
-  p.K_total = sp.K_total; p.KB = sp.KB; p.BLOCK_N = sp.BLOCK_N;
-  p.w_bytes = (uint32_t)sp.w_bytes; p.kb_bytes = (uint32_t)(sp.NS * sp.BLOCK_N * 128);
+  p.K_total = sp.K_total; p.KB = sp.KB; p.BLOCK_N = pl.Fp + pl.Cp;
+  p.w_bytes = (uint32_t)pl.w_bytes; p.kb_bytes = (uint32_t)(sp.NS * (pl.Fp + pl.Cp) * 128);
+  p.kb1_bytes = (uint32_t)pl.Fp * 128u; p.kb2_bytes = (uint32_t)pl.Cp * 128u;
+  p.Fp = pl.Fp; p.Cp = pl.Cp; p.Cin = c->Cin;
+  if (kT) {
+    p.wpk2 = reinterpret_cast<const uint8_t*>(((uintptr_t)kT->ws + 255) & ~(uintptr_t)255);
+    p.dx = gr->dx; p.x_b = c->x_b_stride; p.x_t = c->x_t_stride; p.x_pix = c->x_pix_stride;
+    p.dx_accumulate = gr->dx_accumulate;
+    FOV_CHECK_ARG(gr->dx && (uintptr_t)gr->dx % 16 == 0 && c->x_pix_stride % 4 == 0 && c->x_b_stride % 4 == 0 &&
+                      c->x_t_stride % 4 == 0,
+                  "fused input gradient needs a 16-byte aligned dx");
+  }
   p.chunk_bytes = pl.chunk_bytes; p.act_off = pl.act_off; p.dh_off = pl.dh_off; p.data_bytes = pl.data_bytes;
   p.tmem_cols = pl.tmem_cols;
   p.wpk = reinterpret_cast<const uint8_t*>(((uintptr_t)rT.ws + 255) & ~(uintptr_t)255);

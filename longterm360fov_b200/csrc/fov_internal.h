@@ -96,9 +96,11 @@ int tc_conv_run(const TcConv& c, cudaStream_t st);
 bool tc_convlstm_seq_supported(const fov_convlstm_cfg* c, const TcConv& step);
 int tc_convlstm_seq_fwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const TcConv& step, cudaStream_t st);
 
-bool tc_convlstm_seq_bwd_supported(const fov_convlstm_cfg* c, const TcConv& rT);
+// kT (optional): the input backward-data convolution; when it shares the k order of rT its result dx rides in the
+// same MMAs (extra accumulator columns) and the separate time-batched dx launch is not needed.
+bool tc_convlstm_seq_bwd_supported(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT);
 int tc_convlstm_seq_bwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const fov_convlstm_grads* gr,
-                        const TcConv& rT, cudaStream_t st);
+                        const TcConv& rT, const TcConv* kT, cudaStream_t st);
 
 // Tensor-core weight gradient: gw[(tap*Cin+ci)*Cout+n] += sum_pixels x(pixel+tap, ci) * dy(pixel, n),
 // gbias[n] += sum_pixels dy(pixel, n).  Both operands are read in their natural NHWC layout and

@@ -21,7 +21,8 @@ cap() {  # name regex skip count
   sz=$(stat -c %s $OUT/prof_${TAG}_$1.ncu-rep)
   [ "$sz" -gt 16000000 ] && rm -f $OUT/prof_${TAG}_$1.ncu-rep
 }
-cap wgrad 'tc_wgrad' ${WG_SKIP:-42} ${WG_N:-14}
-cap conv 'tc_conv_kernel' ${CV_SKIP:-470} ${CV_N:-8}
-cap lstm 'lstm_seq2seq|convlstm_gates_bwd' ${LS_SKIP:-0} 3
+# one timed step (the 4th) of: the three persistent / fused ConvLSTM kernels per layer, the dense GEMMs, the fc-LSTM
+cap convlstm 'tc_wgrad_rows|convlstm_seq' ${CL_SKIP:-27} ${CL_N:-9}
+cap conv 'tc_conv_kernel|tc_wgrad_kernel' ${CV_SKIP:-39} ${CV_N:-13}
+cap lstm 'lstm_seq2seq' ${LS_SKIP:-6} 2
 du -sh $OUT

@@ -506,6 +506,14 @@ int main(int argc, char** argv) {
     printf(g_fail ? "SELFTEST FAILED (%d)\n" : "SELFTEST OK (%d failures)\n", g_fail);
     return g_fail ? 1 : 0;
   }
+  if (argc > 1 && !strcmp(argv[1], "bw")) {       // one mid-size stacked-layer backward (for compute-sanitizer runs)
+    const int B = argc > 2 ? atoi(argv[2]) : 300;
+    if (argc > 3) fov_debug_seq_bwd_enable(atoi(argv[3]));
+    test_convlstm("m3 L1 mid", B, 20, 1, 33, 32, 16, 1, 5, false, false);
+    test_convlstm("m3 L2 mid", B, 20, 1, 33, 16, 8, 1, 5, false, false);
+    printf(g_fail ? "SELFTEST FAILED (%d)\n" : "SELFTEST OK (%d failures)\n", g_fail);
+    return g_fail ? 1 : 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "seq")) {
     test_convlstm_seq("m3 L0", 7, 5, 1, 33, 6, 32, 1, 5, false, 1, false);
     test_convlstm_seq("m3 L1", 50, 20, 1, 33, 32, 16, 1, 5, true, 1, false);
