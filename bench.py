@@ -100,55 +100,24 @@ def _time_cuda(fn, reps=20, warm=3):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed
 # `ncu --set full` capture (profiles/), keyed by per-GPU batch; None when no capture exists for it.
-NCU_TRAFFIC_BYTES = {}
+NCU_TRAFFIC_BYTES = {2048: 1040990000}   # profiles/r01_ncu_full_*: 33.29 MB read + 1007.70 MB written
 
 
 def kernel_rooflines(lib, dev, B, compute, peaks, seq_per_s_per_gpu):
-    """Rooflines of the kernels that dominate the config-2 train step (profiles/: weight gradient ~1/3,
-    fused ConvLSTM step ~1/5, dense GEMMs), at the step's own shapes.  Operands are > L2 (126 MB) or
-    rotated, so every launch streams from HBM."""
+    """Rooflines of the kernels that dominate the config-2 train step (profiles/), at the step's own shapes:
+    the three ConvLSTM kernels of layer 0 (persistent forward = the largest single launch, persistent BPTT, fused
+    weight gradient) and the two dense GEMM shapes.  Every operand is far larger than the 126 MB L2, so each launch
+    streams from HBM.  Returns the `roofline` object: the main entry is the persistent forward kernel."""
     import ctypes as C
     import torch
     from longterm360fov_b200 import _lib
     math = _lib.MATH[compute]
     st = torch.cuda.current_stream().cuda_stream
-    W_, F0 = NUM_USER - 1, 32
-    out = []
+    W_, F0, T = NUM_USER - 1, 32, 20
+    npix = B * T * W_
+    hbm = peaks["hbm_gbs"]
 
-    # (1) weight gradient of the ConvLSTM-L0 recurrent kernel over all (b,t) pairs: gR[tap,ci,n] +=
-    #     sum_pix h_{t-1}[pix+tap,ci] * dZ_t[pix,n]; M = 5*32 = 160 k-rows, N = 4F = 128, reduction = B*19*33 pixels
-    Nimg = B * 19
-    h = torch.randn(Nimg, 1, W_, F0, device=dev)
-    dz = torch.randn(Nimg, 1, W_, 4 * F0, device=dev) * 0.01
-    gw = torch.zeros(1, 5, F0, 4 * F0, device=dev)
-    cfg = _lib.ConvCfg(Nimg, 1, W_, F0, 4 * F0, 1, 5, 1, 1, 0, 2, W_ * F0, F0, W_ * 4 * F0, 4 * F0, 0, 0.0)
-    if math == 0:
-        fn = lambda: _lib.check(lib.fov_conv2d_bwd_weight(C.byref(cfg), h.data_ptr(), dz.data_ptr(), gw.data_ptr(),
-                                                          None, st))
-        kname = "conv_wgrad_kernel (fp32 SIMT)"
-    else:
-        fn = lambda: _lib.check(lib.fov_conv2d_bwd_weight_tc(C.byref(cfg), h.data_ptr(), dz.data_ptr(),
-                                                             gw.data_ptr(), None, math, st))
-        kname = "tc_wgrad_kernel<%d> (tcgen05, MN-major operands, %d bf16 term(s))" % (math, math)
-    ms = _time_cuda(fn)
-    npix = Nimg * W_
-    byts = npix * (F0 + 4 * F0) * 4 + gw.numel() * 4
-    flop = 2.0 * npix * 160 * 128
-    gbs = byts / (ms * 1e-3) / 1e9
-    main = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-            "traffic": NCU_TRAFFIC_BYTES.get(B),
-            "kernel": kname + ": ConvLSTM-L0 recurrent weight gradient, %d images of 1x%d, Cin=32, Cout=128, k=1x5"
-                      % (Nimg, W_),
-            "algorithmic_bytes_per_launch": byts, "ms_per_launch": ms,
-            "algorithmic_tflops": flop / (ms * 1e-3) / 1e12,
-            "why_hbm": "64 algorithmic FLOP per byte (x3 issued in bf16x2) is below the machine balance of "
-                       "%.0f FLOP/B" % (peaks["bf16"] * 1e3 / peaks["hbm_gbs"]),
-            "peak_is": "%s copy bandwidth (MEASURED_PEAKS.json)" % peaks["which"]}
-    del h, dz, gw
-
-    # (2) fused ConvLSTM-L0 step (implicit GEMM [x_t taps | h_{t-1} taps] x [K;R] + gate algebra + cell update
-    #     in the epilogue), 20 timestep launches of one layer call; bytes = x + h_prev + c_prev + c + h + 4 gates
-    T = 20
+    # ---- ConvLSTM layer 0 (others' whole span): x (B,20,1,33,6) -> h into the 56-channel concat buffer ----
     x = torch.randn(B, T, 1, W_, 6, device=dev)
     K0 = torch.randn(1, 5, 6, 4 * F0, device=dev) * 0.1
     R0 = torch.randn(1, 5, F0, 4 * F0, device=dev) * 0.1
@@ -164,17 +133,49 @@ def kernel_rooflines(lib, dev, B, compute, peaks, seq_per_s_per_gpu):
     io = _lib.ConvLstmIO(x.data_ptr(), K0.data_ptr(), R0.data_ptr(), b0.data_ptr(), None, None, None,
                          hseq.data_ptr(), gates.data_ptr(), cseq.data_ptr(), hT.data_ptr(), cT.data_ptr(),
                          ws.data_ptr() if ws is not None else None)
-    ms = _time_cuda(lambda: _lib.check(lib.fov_convlstm_fwd(C.byref(lcfg), C.byref(io), st)), reps=5, warm=2)
-    npix = B * T * W_
-    byts = npix * (6 + F0 + F0 + F0 + F0 + 4 * F0) * 4
-    flop = 2.0 * npix * 5 * (6 + F0) * 4 * F0
-    gbs = byts / (ms * 1e-3) / 1e9
-    out.append({"kernel": "tc_conv_kernel<%d,LSTM> x%d timesteps: ConvLSTM-L0 forward (training, gates saved)" % (math, T),
-                "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                "ms_per_launch": ms / T, "algorithmic_tflops": flop / (ms * 1e-3) / 1e12})
-    del x, hseq, gates, cseq
+    n0 = lib.fov_launch_count()
+    _lib.check(lib.fov_convlstm_fwd(C.byref(lcfg), C.byref(io), st))
+    fwd_launches = int(lib.fov_launch_count() - n0)            # 2 = weight repack + ONE persistent kernel
+    ms_f = _time_cuda(lambda: _lib.check(lib.fov_convlstm_fwd(C.byref(lcfg), C.byref(io), st)), reps=10, warm=2)
+    # algorithmic bytes per pixel-step: x_t in, h_t + c_t + 4 activated gates out (h_{t-1}, c_{t-1} never leave the SM)
+    byts_f = npix * (6 + F0 + F0 + 4 * F0) * 4
+    flop_f = 2.0 * npix * 5 * (6 + F0) * 4 * F0
+    gbs = byts_f / (ms_f * 1e-3) / 1e9
+    persistent = fwd_launches <= 3
+    main = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+            "traffic": NCU_TRAFFIC_BYTES.get(B),
+            "kernel": ("convlstm_seq_fwd_kernel<%d,32,2> (persistent ConvLSTM-L0 forward, all %d timesteps in ONE launch, "
+                       "tcgen05 + TMEM, training mode: gates saved)" % (math, T)) if persistent else
+                      "ConvLSTM-L0 forward, %d launches (compute=%s)" % (fwd_launches, compute),
+            "algorithmic_bytes_per_launch": byts_f, "ms_per_launch": ms_f, "launches_per_call": fwd_launches,
+            "algorithmic_tflops": flop_f / (ms_f * 1e-3) / 1e12,
+            "why_hbm": "61 algorithmic FLOP per byte (x3 issued in bf16x2) is below the machine balance of %.0f FLOP/B"
+                       % (peaks["bf16"] * 1e3 / hbm),
+            "peak_is": "%s copy bandwidth (MEASURED_PEAKS.json)" % peaks["which"]}
+    out = []
 
-    # (3) Dense 1848 -> 256 over the 10 future slices (concat-state fusion): M = B*10 rows, K = 1848, N = 256
+    # ---- BPTT of the same layer: persistent reverse-time kernel + fused weight-gradient kernel (2 launches + repack) ----
+    dcat = torch.randn(B, T, 1, W_, 56, device=dev) * 0.01
+    gK, gR, gb = torch.zeros_like(K0), torch.zeros_like(R0), torch.zeros_like(b0)
+    nws = lib.fov_convlstm_bwd_ws_floats(C.byref(lcfg))
+    bws = torch.empty(int(nws), device=dev)
+    gr = _lib.ConvLstmGrads(dcat.data_ptr(), None, None, None, None, None, gK.data_ptr(), gR.data_ptr(), gb.data_ptr(),
+                            bws.data_ptr(), 0)
+
+    def bwd():
+        # the BPTT overwrites the saved gates with dZ; re-running it on dZ is the same memory traffic
+        _lib.check(lib.fov_convlstm_bwd(C.byref(lcfg), C.byref(io), C.byref(gr), st))
+    ms_b = _time_cuda(bwd, reps=10, warm=2)
+    byts_b = npix * ((4 * F0 + F0 + F0 + F0) + 4 * F0) * 4 + npix * (4 * F0 + F0 + 6) * 4   # BPTT in/out + wgrad reads
+    gbs_b = byts_b / (ms_b * 1e-3) / 1e9
+    out.append({"kernel": "convlstm_seq_bwd_kernel + tc_wgrad_rows_kernel: ConvLSTM-L0 BPTT (persistent reverse time loop) "
+                          "+ fused gK/gR/gb weight gradient",
+                "bound": "hbm", "achieved": gbs_b, "peak": hbm, "unit": "GB/s", "frac": gbs_b / hbm, "ms_per_call": ms_b,
+                "algorithmic_bytes_per_call": byts_b,
+                "algorithmic_tflops": 2 * flop_f / (ms_b * 1e-3) / 1e12})
+    del x, hseq, gates, cseq, dcat, bws
+
+    # ---- Dense 1848 -> 256 over the 10 future slices (concat-state fusion): M = B*10 rows ----
     rows = B * 10
     a = torch.randn(rows, 1, 1, 1848, device=dev)
     wd = torch.randn(1, 1, 1848, 256, device=dev) * 0.02
@@ -284,6 +285,7 @@ def _cpu_oracle_step_fn(batch, dtype_name="float32"):
 
 def cpu_baseline(seconds=12.0, batch=32):
     import torch
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     step = _cpu_oracle_step_fn(batch)
     step()
     t0, n = time.perf_counter(), 0
@@ -302,6 +304,8 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every host core it can
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     batch = args.ref_batch
     step = _cpu_oracle_step_fn(batch)
     for _ in range(args.warmup):
