@@ -426,11 +426,17 @@ extern "C" int fov_lstm_seq2seq_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
   if (P.cfg.T_dec == 0) P.cfg.out_dim = 0;
   cudaStream_t st = (cudaStream_t)stream;
   // 64 sequences per CTA when the operand tile fits, else 32
+  // ... and 16 when even 32-sequence tiles would leave SMs idle (the recurrence is latency bound: smaller tiles =
+  // more CTAs in flight and a shorter per-step chain)
   int spt = 16;
   if (fwd_smem_bytes(P.cfg, 16) > 200 * 1024 || cfg->B <= 32 * fov_num_sms()) spt = 8;
+  if (cfg->B <= 24 * fov_num_sms()) spt = 4;
   const int bt = 4 * spt, grid = (cfg->B + bt - 1) / bt;
   const size_t smem = fwd_smem_bytes(P.cfg, spt);
   const bool hs = cfg->rec_act == FOV_REC_HARD_SIGMOID;
+  if (spt == 4)
+    return hs ? launch(lstm_seq2seq_fwd_kernel<4, FOV_REC_HARD_SIGMOID>, P, grid, smem, st)
+              : launch(lstm_seq2seq_fwd_kernel<4, FOV_REC_SIGMOID>, P, grid, smem, st);
   if (spt == 16)
     return hs ? launch(lstm_seq2seq_fwd_kernel<16, FOV_REC_HARD_SIGMOID>, P, grid, smem, st)
               : launch(lstm_seq2seq_fwd_kernel<16, FOV_REC_SIGMOID>, P, grid, smem, st);
@@ -451,12 +457,16 @@ extern "C" int fov_lstm_seq2seq_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
   P.cfg = *cfg; P.w = *w; P.io = *io; P.g = *g;
   if (P.cfg.T_dec == 0) P.cfg.out_dim = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  constexpr int spt = 8;
+  const int spt = cfg->B <= 24 * fov_num_sms() ? 4 : 8;
   const int bt = 4 * spt, grid = (cfg->B + bt - 1) / bt;
   const size_t smem = bwd_smem_bytes(spt);
-  rc = cfg->rec_act == FOV_REC_HARD_SIGMOID
-           ? launch(lstm_seq2seq_bwd_kernel<spt, FOV_REC_HARD_SIGMOID>, P, grid, smem, st)
-           : launch(lstm_seq2seq_bwd_kernel<spt, FOV_REC_SIGMOID>, P, grid, smem, st);
+  const bool hsb = cfg->rec_act == FOV_REC_HARD_SIGMOID;
+  if (spt == 4)
+    rc = hsb ? launch(lstm_seq2seq_bwd_kernel<4, FOV_REC_HARD_SIGMOID>, P, grid, smem, st)
+             : launch(lstm_seq2seq_bwd_kernel<4, FOV_REC_SIGMOID>, P, grid, smem, st);
+  else
+    rc = hsb ? launch(lstm_seq2seq_bwd_kernel<8, FOV_REC_HARD_SIGMOID>, P, grid, smem, st)
+             : launch(lstm_seq2seq_bwd_kernel<8, FOV_REC_SIGMOID>, P, grid, smem, st);
   if (rc) return rc;
 
   // time-batched weight gradients: [dU; dW] = [h_{t-1} | x_t]^T dZ over all (b,t) rows

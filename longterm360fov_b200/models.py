@@ -512,10 +512,12 @@ class OthersLSTMSpanWhole(Model):
                g["oth_convlstm%d/bias" % l]) for l in range(3)] if training else None
         cat, _ = ops.convlstm_stack(oth_in, wl, None, sl, rec_act=self.rec_act, training=training)
         flat = cat.view(B, Tall, -1)
-        r_oth = ops.dense(flat, p["oth_recon_dense/kernel"], p["oth_recon_dense/bias"], None,
-                          self._sinks("oth_recon_dense/kernel", "oth_recon_dense/bias"), training)
-        s = ops.dense(flat[:, self.T_enc:], p["oth_flat_dense/kernel"], p["oth_flat_dense/bias"], None,
-                      self._sinks("oth_flat_dense/kernel", "oth_flat_dense/bias"), training)
+        # reconstruction head on all 20 slices + concat-state Dense256 on the 10 future slices: one Function, the
+        # two input gradients accumulate into one buffer and the strided future view is read in place
+        r_oth, s = ops.dual_dense(flat, p["oth_recon_dense/kernel"], p["oth_recon_dense/bias"],
+                                  p["oth_flat_dense/kernel"], p["oth_flat_dense/bias"], self.T_enc,
+                                  self._sinks("oth_recon_dense/kernel", "oth_recon_dense/bias"),
+                                  self._sinks("oth_flat_dense/kernel", "oth_flat_dense/bias"), training)
         # decoder_dense(Concat[h_dec, s]) = h_dec . Wd[:H] + (s . Wd[H:] + bd): the second term does
         # not depend on the recurrence, so it is computed for all steps at once and enters the
         # persistent kernel as the additive head term.

@@ -265,6 +265,91 @@ def dense(x, kernel, bias, activation=None, sinks=None, training=False):
     return y.reshape(*shp[:-1], kernel.shape[1])
 
 
+class DualDenseFn(torch.autograd.Function):
+    """Two Dense layers reading the SAME (B,T,C) sequence: y1 = x.W1 + b1 on every time slice and
+    y2 = x[:, t0:].W2 + b2 on the slices from t0 on (the reconstruction head and the concat-state
+    fusion of mycode/others_LSTM_span_whole.py:105-109,261-271).  One Function so that the two input
+    gradients are accumulated by the kernels into ONE buffer (beta = 1 on the strided view) instead of
+    slice-backward zero fills, copies and adds; the strided view is read in place (no contiguous copy).
+
+    forward(opts, sinks1, sinks2, x, W1, b1, W2, b2) -> (y1 (B,T,C1), y2 (B,T-t0,C2))"""
+
+    @staticmethod
+    def _cfgs(B, T, t0, Cin, C1, C2):
+        full = _conv_cfg(B * T, 1, 1, Cin, C1, 1, 1, (1, 1), None, 0.0, Cin, Cin, C1, C1)
+        Ts = T - t0
+        part = _conv_cfg(B, 1, Ts, Cin, C2, 1, 1, (1, 1), None, 0.0, T * Cin, Cin, Ts * C2, C2)
+        return full, part
+
+    @staticmethod
+    def forward(ctx, opts, sinks1, sinks2, x, W1, b1, W2, b2):
+        lib = _lib.load()
+        _require_cuda(x, W1, W2)
+        x = _f32c(x)
+        B, T, Cin = x.shape
+        t0 = int(opts["t0"])
+        C1, C2 = W1.shape[-1], W2.shape[-1]
+        math = opts.get("math", _MATH[0])
+        full, part = DualDenseFn._cfgs(B, T, t0, Cin, C1, C2)
+        y1 = torch.empty(B, T, C1, device=x.device)
+        y2 = torch.empty(B, T - t0, C2, device=x.device)
+        xs = x.data_ptr() + 4 * t0 * Cin
+        st = _stream()
+        for cfg, xp, W, b, y in ((full, x.data_ptr(), W1, b1, y1), (part, xs, W2, b2, y2)):
+            if math == 0:
+                _lib.check(lib.fov_conv2d_fwd(C.byref(cfg), xp, ptr(W), ptr(b), ptr(y), st), "fov_conv2d_fwd")
+            else:
+                ws = _ws(lib.fov_conv_tc_ws_bytes(C.byref(cfg), math, 0), x.device)
+                _lib.check(lib.fov_conv2d_fwd_tc(C.byref(cfg), xp, ptr(W), ptr(b), ptr(y), ptr(ws), math, st),
+                           "fov_conv2d_fwd_tc")
+        if opts.get("training", False):
+            ctx.math, ctx.t0, ctx.sinks = math, t0, (sinks1, sinks2)
+            ctx.need_dx = ctx.needs_input_grad[3]
+            ctx.save_for_backward(x, W1, W2)
+        return y1, y2
+
+    @staticmethod
+    def backward(ctx, dy1, dy2):
+        lib = _lib.load()
+        x, W1, W2 = ctx.saved_tensors
+        B, T, Cin = x.shape
+        t0, math = ctx.t0, ctx.math
+        C1, C2 = W1.shape[-1], W2.shape[-1]
+        full, part = DualDenseFn._cfgs(B, T, t0, Cin, C1, C2)
+        dy1 = _f32c(dy1) if dy1 is not None else torch.zeros(B, T, C1, device=x.device)
+        dy2 = _f32c(dy2) if dy2 is not None else torch.zeros(B, T - t0, C2, device=x.device)
+        st = _stream()
+        xs = x.data_ptr() + 4 * t0 * Cin
+        dx = torch.empty_like(x) if ctx.need_dx else None
+        for cfg, xp, W, dy, sinks, beta, off in ((full, x.data_ptr(), W1, dy1, ctx.sinks[0], 0.0, 0),
+                                                 (part, xs, W2, dy2, ctx.sinks[1], 1.0, 4 * t0 * Cin)):
+            gw, gb = sinks
+            if math == 0:
+                _lib.check(lib.fov_conv2d_bwd_weight(C.byref(cfg), xp, ptr(dy), ptr(gw), ptr(gb), st),
+                           "fov_conv2d_bwd_weight")
+            else:
+                _lib.check(lib.fov_conv2d_bwd_weight_tc(C.byref(cfg), xp, ptr(dy), ptr(gw), ptr(gb), math, st),
+                           "fov_conv2d_bwd_weight_tc")
+            if dx is not None:
+                cfg.beta = beta
+                dxp = dx.data_ptr() + off
+                if math == 0:
+                    ws = torch.empty(W.numel(), device=x.device)
+                    _lib.check(lib.fov_conv2d_bwd_data(C.byref(cfg), ptr(dy), ptr(W), dxp, ptr(ws), st),
+                               "fov_conv2d_bwd_data")
+                else:
+                    ws = _ws(lib.fov_conv_tc_ws_bytes(C.byref(cfg), math, 1), x.device)
+                    _lib.check(lib.fov_conv2d_bwd_data_tc(C.byref(cfg), ptr(dy), ptr(W), dxp, ptr(ws), math, st),
+                               "fov_conv2d_bwd_data_tc")
+        return None, None, None, dx, None, None, None, None
+
+
+def dual_dense(x, W1, b1, W2, b2, t0, sinks1=None, sinks2=None, training=False):
+    """(x.W1 + b1 on all T slices, x[:, t0:].W2 + b2): see DualDenseFn."""
+    return DualDenseFn.apply({"t0": t0, "training": training}, sinks1, sinks2, x, W1.view(1, 1, *W1.shape), b1,
+                             W2.view(1, 1, *W2.shape), b2)
+
+
 def conv1d(x, kernel, bias, activation=None, sinks=None, training=False):
     """keras Conv1D(padding='same'): x (B,L,Cin), kernel (k,Cin,Cout)."""
     y = Conv2DFn.apply({"activation": activation, "training": training}, sinks, x.unsqueeze(1),
@@ -351,8 +436,9 @@ class ConvLSTMStackFn(torch.autograd.Function):
         per = [tensors[2 + 7 * l:2 + 7 * l + 7] for l in range(L)]   # K,R,b,h0,c0,gates,cseq
         dev = x.device
         st = _stream()
-        # private contiguous copy: layers accumulate dx of the layer above into it
-        dcat = torch.zeros_like(cat) if dcat is None else dcat.contiguous().clone()
+        # layers accumulate dx of the layer above into the incoming gradient buffer in place (it is owned by the
+        # autograd engine and handed to this node only; no retain_graph use on this path)
+        dcat = torch.zeros_like(cat) if dcat is None else dcat.contiguous()
         dx0 = torch.empty_like(x) if ctx.x_needs_grad else None
         dstate_out = [None] * (2 * L)
         for l in reversed(range(L)):
