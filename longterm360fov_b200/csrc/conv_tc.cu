@@ -639,7 +639,10 @@ int make_plan(const TcConv& c, Plan* pl) {
     pl->BLOCK_N = c.epi == TC_EPI_LSTM ? c.Cout : ((n_pad + pl->n_tiles - 1) / pl->n_tiles + 15) / 16 * 16;
     pl->b_stage_bytes = pl->NS * pl->BLOCK_N * 128;
     int st = (kUsable - book - region_bytes) / pl->b_stage_bytes;
-    const int want = pl->KB < 3 ? pl->KB : 3;
+    // dense layers (1x1 kernel, wide Cin) are bound by the activation staging, which is repeated per n tile: prefer
+    // ONE n tile with a two-slot weight ring over two n tiles with three slots
+    const bool dense_like = c.nseg == 1 && c.seg[0].kh * c.seg[0].kw == 1 && c.seg[0].Cin >= 256;
+    const int want = pl->KB < 3 ? pl->KB : (dense_like ? 2 : 3);
     if (st >= want || max_n <= 32 || c.epi == TC_EPI_LSTM) {
       if (st > kMaxBStages) st = kMaxBStages;
       if (st > pl->KB) st = pl->KB;
