@@ -36,7 +36,7 @@ struct BwdParams {
   int B, T, H, W, HW, Hp, Wp, PLh, PLw, HpWp, G, rec_act, dbg;
   int F, Cin_p, nch, row_bytes, swz_mask, term_bytes, R, minshift, taps, kw, pad_h, pad_w;
   uint32_t desc_hi;
-  int K_total, KB, BLOCK_N;
+  int K_total, KB, BLOCK_N, stack;
   uint32_t w_bytes, kb_bytes, chunk_bytes, act_off, dh_off, data_bytes, tmem_cols;
   const uint8_t* wpk;
   float* gates; long long z_b, z_t;              // in: activated gates, out: dZ   (B,T,HW,4F)
@@ -156,6 +156,19 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
       for (int c = 0; c < kDxMax; c += 8)
         if (c < dxn) tmem_ld8(t_row + (uint32_t)(p.Fp + dxc0 + c), dxr + c);
       tmem_ld_wait();
+      if (p.stack) {
+#pragma unroll
+        for (int sb = 1; sb < NS; ++sb) {
+          float w[kDxMax];
+#pragma unroll
+          for (int c = 0; c < kDxMax; c += 8)
+            if (c < dxn) tmem_ld8(t_row + (uint32_t)(sb * p.BLOCK_N + p.Fp + dxc0 + c), w + c);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < kDxMax; ++c)
+            if (c < dxn) dxr[c] += w[c];
+        }
+      }
     };
     // dx leaves through the dh transpose tile in two phases of F columns (Cin = 2F: warp half h holds phase h),
     // so the global read-modify-write is a coalesced, channel-fastest float4 row segment like everything else
@@ -191,11 +204,11 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
     const long long t_begin = clock64();
 
     float4 vg[NIT][4], vc[NIT], vp[NIT], vh[NIT];
-    auto load_step = [&](int t) {
+    // saved tensors of item j at step t -> registers
+    auto load_item = [&](int t, int j) {
       const float* gt = p.gates + (long long)t * p.z_t;
       const float* ct = p.cseq + (long long)t * p.c_t;
-#pragma unroll
-      for (int j = 0; j < NIT; ++j) {
+      {
         const bool ok = off_g[j] >= 0;
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi)
@@ -210,7 +223,8 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
         if (ok && p.dhseq) vh[j] = __ldg(reinterpret_cast<const float4*>(p.dhseq + (long long)t * p.dh_t + off_h[j]));
       }
     };
-    load_step(p.T - 1);
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) load_item(p.T - 1, j);
     for (int t = p.T - 1; t >= 0; --t) {
       // ---- dh_rec of this step: dhT at the last step, else the accumulator of the GEMM issued at step t+1 ----
       float4 dr[NIT];
@@ -230,6 +244,18 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
 #pragma unroll
           for (int c = 0; c < HC; c += 8) tmem_ld8(t_row + (uint32_t)((F >= 16 ? half * HC : 0) + c), v + c);
           tmem_ld_wait();
+          if (p.stack) {
+#pragma unroll
+            for (int sb = 1; sb < NS; ++sb) {
+              float w[HC];
+#pragma unroll
+              for (int c = 0; c < HC; c += 8)
+                tmem_ld8(t_row + (uint32_t)(sb * p.BLOCK_N + (F >= 16 ? half * HC : 0) + c), w + c);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < HC; ++c) v[c] += w[c];
+            }
+          }
           float* dst = dh_s + (q * 32 + lane) * DHS + (F >= 16 ? half * HC : 0);
 #pragma unroll
           for (int c = 0; c < HC; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
@@ -245,7 +271,7 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
       float* gz = p.gates + (long long)t * p.z_t;
 #pragma unroll
       for (int j = 0; j < NIT; ++j) {
-        if (off_g[j] < 0) continue;
+        if (off_g[j] < 0) continue;               // not a pixel: nothing to compute, nothing to fetch
         const float gi_[4] = {vg[j][0].x, vg[j][0].y, vg[j][0].z, vg[j][0].w};
         const float gf_[4] = {vg[j][1].x, vg[j][1].y, vg[j][1].z, vg[j][1].w};
         const float gg_[4] = {vg[j][2].x, vg[j][2].y, vg[j][2].z, vg[j][2].w};
@@ -286,7 +312,10 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
         fence_proxy_async_smem();
         mbar_arrive(smem_u32(&bk->a_full));
       }
-      if (t > 0) load_step(t - 1);                // in flight while the GEMM of this step runs
+      if (t > 0) {                                 // in flight while the GEMM of this step runs
+#pragma unroll
+        for (int j = 0; j < NIT; ++j) load_item(t - 1, j);
+      }
       if (DXN > 0 && t < p.T - 1) dx_store(t + 1);
       if (t == 0 && p.dc0) {
 #pragma unroll
@@ -332,15 +361,28 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
         tc_fence_after();
         const long long q1 = clock64();
         mw += q1 - q0;
-        for (int e = 0; e < nsteps; ++e) {
-          const uint2 o = bk->ops[e];
+        if (p.stack) {
+          // the bf16 terms of a weight tile are adjacent in shared memory, so ONE MMA with N = (NS - sa) * BLOCK_N
+          // multiplies A term sa by the B terms 0 .. NS-1-sa: NS MMAs per k step instead of NS (NS + 1) / 2; product
+          // (sa, sb) lands in accumulator columns [sb * BLOCK_N, +BLOCK_N) and the read-back sums the column blocks
+          for (int e = 0; e < nsteps; ++e) {
+            const uint2 o = bk->ops[e];
 #pragma unroll
-          for (int sum = NS - 1; sum >= 0; --sum) {
+            for (int sa = 0; sa < NS; ++sa)
+              umma_bf16(tmem_d, desc_at(p.desc_hi, base + o.x + sa * p.term_bytes), desc_at(kDescHi128, base + o.y),
+                        idesc_bf16_f32(kRows, (NS - sa) * p.BLOCK_N, 0, 0), (e > 0 || sa > 0) ? 1u : 0u);
+          }
+        } else {
+          for (int e = 0; e < nsteps; ++e) {
+            const uint2 o = bk->ops[e];
 #pragma unroll
-            for (int sa = 0; sa <= sum; ++sa) {
-              const int sb = sum - sa;
-              umma_bf16(tmem_d, desc_at(p.desc_hi, base + o.x + sa * p.term_bytes),
-                        desc_at(kDescHi128, base + o.y + sb * b_term), idesc, (e > 0 || sum != NS - 1 || sa > 0) ? 1u : 0u);
+            for (int sum = NS - 1; sum >= 0; --sum) {
+#pragma unroll
+              for (int sa = 0; sa <= sum; ++sa) {
+                const int sb = sum - sa;
+                umma_bf16(tmem_d, desc_at(p.desc_hi, base + o.x + sa * p.term_bytes),
+                          desc_at(kDescHi128, base + o.y + sb * b_term), idesc, (e > 0 || sum != NS - 1 || sa > 0) ? 1u : 0u);
+              }
             }
           }
         }
@@ -357,7 +399,7 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
 
 struct BwdPlan {
   TcStepPlan sp, sp2;
-  int G, Fp, Cp, fuse_dx;
+  int G, Fp, Cp, fuse_dx, stack;
   size_t w_bytes;
   uint32_t chunk_bytes, act_off, dh_off, data_bytes, tmem_cols;
   size_t smem_bytes;
@@ -396,7 +438,8 @@ int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT, BwdP
   pl.data_bytes = (pl.dh_off + (uint32_t)(kRows * (F + 4) * 4) + 1023u) / 1024u * 1024u;
   pl.smem_bytes = pl.data_bytes + sizeof(BwdBook) + 1024;
   FOV_CHECK_ARG(pl.smem_bytes <= 227 * 1024, "persistent BPTT: weights + operands exceed shared memory");
-  pl.tmem_cols = tmem_cols_for(pl.Fp + pl.Cp);
+  pl.stack = (sp.NS > 1 && sp.NS * (pl.Fp + pl.Cp) <= 256) ? 1 : 0;
+  pl.tmem_cols = tmem_cols_for((pl.stack ? sp.NS : 1) * (pl.Fp + pl.Cp));
   FOV_CHECK_ARG(!pl.fuse_dx || (long long)c->B * c->x_b_stride < (1LL << 31), "input too large for 32-bit offsets");
   const long long HW = (long long)c->H * c->W;
   FOV_CHECK_ARG((long long)c->B * c->T * HW * 4 * F < (1LL << 31) && (long long)c->B * c->h_b_stride < (1LL << 31),
@@ -442,7 +485,8 @@ int launch_bwd_f(int F, const BwdParams& p, const BwdPlan& pl, int grid, cudaStr
 
 }  // namespace
 
-static int g_bwd_disable = 0, g_bwd_dbg = 0;
+static int g_bwd_disable = 0, g_bwd_dbg = 0, g_bwd_nostack = 0;
+extern "C" void fov_debug_seq_bwd_nostack(int on) { g_bwd_nostack = on; }
 extern "C" void fov_debug_convlstm_persistent_bwd(int enable) { g_bwd_disable = !enable; }
 extern "C" void fov_debug_seq_bwd_enable(int on) { g_bwd_dbg = on; }
 extern "C" int fov_debug_seq_bwd_read(unsigned long long* out) {
@@ -476,7 +520,7 @@ int tc_convlstm_seq_bwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, co
   p.F = F; p.Cin_p = sg.Cin_p; p.nch = sg.nch; p.row_bytes = sg.row_bytes; p.swz_mask = sg.swz_mask;
   p.term_bytes = sg.term_bytes; p.R = sg.R; p.minshift = sg.minshift; p.taps = sg.taps; p.kw = sg.kw;
   p.pad_h = sg.pad_h; p.pad_w = sg.pad_w; p.desc_hi = sg.desc_hi;
-  p.K_total = sp.K_total; p.KB = sp.KB; p.BLOCK_N = pl.Fp + pl.Cp;
+  p.K_total = sp.K_total; p.KB = sp.KB; p.BLOCK_N = pl.Fp + pl.Cp; p.stack = g_bwd_nostack ? 0 : pl.stack;
   p.w_bytes = (uint32_t)pl.w_bytes; p.kb_bytes = (uint32_t)(sp.NS * (pl.Fp + pl.Cp) * 128);
   p.kb1_bytes = (uint32_t)pl.Fp * 128u; p.kb2_bytes = (uint32_t)pl.Cp * 128u;
   p.Fp = pl.Fp; p.Cp = pl.Cp; p.Cin = c->Cin;

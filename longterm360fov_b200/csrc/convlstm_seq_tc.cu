@@ -53,7 +53,9 @@ struct SeqParams {
 constexpr int kStgStride = 36;   // floats per row of a warp's 32 x 32 staging tile (144 B: conflict-free float4 rows)
 constexpr int kStgBytes = 32 * kStgStride * 4;
 
+constexpr int kSeqMaxSteps = 128;   // k16 steps of the gate GEMM
 struct SeqBook {
+  uint4 ops[kSeqMaxSteps];           // per k16 step: a_rel (within the group's operand area), a_term, desc_hi, b_rel
   int tapshift[2][kSeqMaxTaps];
   float bias_s[256];             // [pass][gate][8]: the 32 biases a pass needs are contiguous
   uint64_t w_full, a_full[2], tmem_full[2];
@@ -343,6 +345,22 @@ __global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_s
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16_f32(kRows, N4F, 0, 0);
       const uint32_t b_term = (uint32_t)N4F * 128u;
+      // operand addresses of every k16 step, computed once
+      int nsteps = 0;
+      for (int kb = 0; kb < p.KB; ++kb)
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int k = kb * 64 + k4 * 16;
+          if (k >= p.K_total) break;
+          const int s = k >= p.seg[1].k_begin ? 1 : 0;
+          const SeqSeg& sg = p.seg[s];
+          const int kk = k - sg.k_begin;
+          const int tap = kk >> sg.cp_log2, c0 = kk & (sg.Cin_p - 1);
+          const int ty = tap / sg.kw, tx = tap - ty * sg.kw;
+          const int shift = (ty * sg.dil_h - sg.pad_h) * p.Wp + (tx * sg.dil_w - sg.pad_w) - sg.minshift;
+          bk->ops[nsteps++] = make_uint4((s ? (uint32_t)NS * p.seg[0].term_bytes : 0u) + (uint32_t)shift * sg.row_bytes +
+                                             (uint32_t)c0 * 2u,
+                                         (uint32_t)sg.term_bytes, sg.desc_hi, (uint32_t)kb * p.kb_bytes + (uint32_t)k4 * 32u);
+        }
       mbar_wait(smem_u32(&bk->w_full), 0);
       const bool dbg = p.dbg && blockIdx.x == 0;
       long long mw = 0, mi = 0;
@@ -356,29 +374,15 @@ __global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_s
           mw += k1 - k0;
           const uint32_t greg = base + p.act_off + (uint32_t)g * p.grp_bytes;
           const uint32_t d = tmem_d + (uint32_t)(g * 6 * F);
-          uint32_t first = 1;
-          for (int kb = 0; kb < p.KB; ++kb) {
-            const uint32_t b0a = base + (uint32_t)kb * p.kb_bytes;
+          for (int e = 0; e < nsteps; ++e) {
+            const uint4 o = bk->ops[e];
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const int k = kb * 64 + k4 * 16;
-              if (k < p.K_total) {
-                const int s = k >= p.seg[1].k_begin ? 1 : 0;
-                const SeqSeg& sg = p.seg[s];
-                const int kk = k - sg.k_begin;
-                const int tap = kk >> sg.cp_log2, c0 = kk & (sg.Cin_p - 1);
-                const uint32_t a_addr = greg + (s ? (uint32_t)NS * p.seg[0].term_bytes : 0u) +
-                                        (uint32_t)bk->tapshift[s][tap] * sg.row_bytes + (uint32_t)c0 * 2u;
+            for (int sum = NS - 1; sum >= 0; --sum) {
 #pragma unroll
-                for (int sum = NS - 1; sum >= 0; --sum) {
-#pragma unroll
-                  for (int sa = 0; sa <= sum; ++sa) {
-                    const int sb = sum - sa;
-                    umma_bf16(d, desc_at(sg.desc_hi, a_addr + sa * sg.term_bytes),
-                              desc_at(kDescHi128, b0a + k4 * 32 + sb * b_term), idesc, first ^ 1u);
-                    first = 0;
-                  }
-                }
+              for (int sa = 0; sa <= sum; ++sa) {
+                const int sb = sum - sa;
+                umma_bf16(d, desc_at(o.z, greg + o.x + sa * o.y), desc_at(kDescHi128, base + o.w + sb * b_term), idesc,
+                          (e > 0 || sum != NS - 1 || sa > 0) ? 1u : 0u);
               }
             }
           }
@@ -413,7 +417,8 @@ int seq_plan(const fov_convlstm_cfg* c, const TcConv& step, SeqPlan* out) {
   pl.G = kRows / (sp.Hp * sp.Wp);
   FOV_CHECK_ARG(pl.G >= 1, "image larger than one MMA tile");
   FOV_CHECK_ARG(sp.seg[0].R * (1 << sp.seg[0].lpr_log2) <= kXI * kRows, "input frame too wide to prefetch");
-  FOV_CHECK_ARG(sp.seg[0].taps <= kSeqMaxTaps && sp.seg[1].taps <= kSeqMaxTaps, "too many taps");
+  FOV_CHECK_ARG(sp.seg[0].taps <= kSeqMaxTaps && sp.seg[1].taps <= kSeqMaxTaps && sp.K_total / 16 <= kSeqMaxSteps,
+                "too many taps");
   pl.grp_bytes = (uint32_t)sp.NS * (uint32_t)(sp.seg[0].term_bytes + sp.seg[1].term_bytes);
   pl.act_off = (uint32_t)((sp.w_bytes + 1023) / 1024 * 1024);
   const size_t book = sizeof(SeqBook) + 1024;
