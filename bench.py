@@ -487,7 +487,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=2048, help="sequences per GPU per step")
+    ap.add_argument("--batch", type=int, default=4096, help="sequences per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=64, help="sequences per step of the CPU reference arm")
     ap.add_argument("--compute", default="bf16x2", choices=["fp32", "bf16", "bf16x2", "bf16x3"],
                     help="arithmetic of the conv/dense/ConvLSTM kernels: fp32 = CUDA cores; bf16x2 (default) = "

@@ -226,12 +226,16 @@ class Model:
             total = l if total is None else total + l
         return total
 
-    def train_step_device(self, xs, ys):
+    def train_step_device(self, xs, ys, targets_ready=None):
         """One optimiser step on device tensors; returns the loss as a device tensor
-        (no host sync).  DP: gradients are sum-allreduced and scaled by 1/world."""
+        (no host sync).  DP: gradients are sum-allreduced and scaled by 1/world.
+        ``targets_ready``: optional CUDA event after which ``ys`` may be read (their H2D copy
+        runs on a side stream while the forward pass computes)."""
         self.gflat.zero_()
         ops.set_math(self.compute)
         outs = self._forward(xs, True)
+        if targets_ready is not None:
+            torch.cuda.current_stream().wait_event(targets_ready)
         total = self._loss(outs, ys)
         total.backward()
         scale = 1.0
@@ -242,8 +246,19 @@ class Model:
         return total.detach()
 
     def train_on_batch(self, x, y):
-        xs, ys = self._to_dev(self._as_list(x)), self._to_dev(self._as_list(y))
-        return float(self.train_step_device(xs, ys).item())
+        """keras Model.train_on_batch.  The inputs are copied on the compute stream; the targets - only needed by the
+        loss at the end of the forward pass - are copied on a side stream, so their H2D transfer overlaps the forward."""
+        xs = self._to_dev(self._as_list(x))
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self._copy_stream):
+            ys = self._to_dev(self._as_list(y))
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        for t in ys:
+            t.record_stream(main)
+        return float(self.train_step_device(xs, ys, ready).item())
 
     def test_on_batch(self, x, y):
         xs, ys = self._to_dev(self._as_list(x)), self._to_dev(self._as_list(y))
