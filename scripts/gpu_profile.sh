@@ -3,7 +3,7 @@
 # usage: scripts/gpu_profile.sh <tag> [batch]
 # The .ncu-rep files are exported to CSV on the box and deleted when large (gpurun_out/ is capped at 64 MiB).
 TAG="${1:-r}"
-B="${2:-2048}"
+B="${2:-4096}"
 OUT=gpurun_out
 mkdir -p $OUT
 cd "$(dirname "$0")/.."
@@ -23,6 +23,6 @@ cap() {  # name regex skip count
 }
 # one timed step (the 4th) of: the three persistent / fused ConvLSTM kernels per layer, the dense GEMMs, the fc-LSTM
 cap convlstm 'tc_wgrad_rows|convlstm_seq' ${CL_SKIP:-27} ${CL_N:-9}
-cap conv 'tc_conv_kernel|tc_wgrad_kernel' ${CV_SKIP:-39} ${CV_N:-13}
+cap conv 'tc_conv_kernel|tc_wgrad_kernel' ${CV_SKIP:-36} ${CV_N:-12}
 cap lstm 'lstm_seq2seq' ${LS_SKIP:-6} 2
 du -sh $OUT

@@ -245,6 +245,56 @@ def test_convlstm_stack_forward_backward(shape, mode):
             _grad_close(stt[l][1].grad.cpu().numpy(), s64[l][1].grad.numpy(), "dc0_%d" % l)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T", [(1, 1), (5, 20), (130, 7)])
+def test_persistent_convlstm_kernels_match_per_timestep_launches(B, T):
+    """The persistent forward / BPTT kernels and the fused weight gradient (one launch per layer) against the
+    per-timestep launches they replace, same arithmetic (bf16x2), on the stacked M3 layers with the concat-buffer
+    strides: forward bit-identical (same MMA order, same fp32 epilogue), gradients to rounding noise."""
+    fov = _cuda()
+    from longterm360fov_b200 import ops, _lib
+    lib = _lib.load()
+    ops.set_math("bf16x2")
+    rng = np.random.default_rng(B * 7 + T)
+    H, W, Cin, Fs = 1, 33, 6, (32, 16, 8)
+    x = rng.normal(size=(B, T, H, W, Cin)).astype(np.float32)
+    ws, cin = [], Cin
+    for f in Fs:
+        ws.append(((rng.normal(size=(1, 5, cin, 4 * f)) * 0.3).astype(np.float32),
+                   (rng.normal(size=(1, 5, f, 4 * f)) * 0.3).astype(np.float32),
+                   (rng.normal(size=4 * f) * 0.1).astype(np.float32)))
+        cin = f
+    gcat = rng.normal(size=(B, T, H, W, sum(Fs))).astype(np.float32)
+
+    def run(persistent):
+        for name in ("fov_debug_convlstm_persistent", "fov_debug_convlstm_persistent_bwd", "fov_debug_wgrad_rows"):
+            getattr(lib, name)(int(persistent))
+        try:
+            xt = torch.tensor(x, device="cuda", requires_grad=True)
+            wt = [tuple(torch.tensor(a, device="cuda", requires_grad=True) for a in w) for w in ws]
+            sinks = [tuple(torch.zeros_like(a) for a in w) for w in wt]
+            n0 = lib.fov_launch_count()
+            cat, _ = ops.convlstm_stack(xt, wt, None, sinks, (1, 1), "hard_sigmoid", True)
+            (cat * torch.tensor(gcat, device="cuda")).sum().backward()
+            torch.cuda.synchronize()
+            launches = int(lib.fov_launch_count() - n0)
+            return (cat.detach().cpu().numpy(), xt.grad.cpu().numpy(), [[g.cpu().numpy() for g in s] for s in sinks],
+                    launches)
+        finally:
+            for name in ("fov_debug_convlstm_persistent", "fov_debug_convlstm_persistent_bwd", "fov_debug_wgrad_rows"):
+                getattr(lib, name)(1)
+
+    cat1, dx1, g1, n1 = run(True)
+    cat0, dx0, g0, n0 = run(False)
+    assert np.array_equal(cat1, cat0), "persistent forward must be bit-identical to the per-timestep launches"
+    _grad_close(dx1, dx0, "dx", rtol=2e-5)
+    for l in range(3):
+        for j, n in enumerate(("kernel", "recurrent_kernel", "bias")):
+            _grad_close(g1[l][j], g0[l][j], "L%d/%s" % (l, n), rtol=2e-5)
+    if T > 1:
+        assert n1 < n0, "the persistent path must need fewer launches (%d vs %d)" % (n1, n0)
+
+
 # ------------------------------------------------------------------ losses / softmax / optimisers
 
 def test_losses_and_softmax():
