@@ -57,7 +57,7 @@ struct DevSeg {
 
 struct DevParams {
   DevSeg seg[2];
-  int nseg, mode_b, dbg;
+  int nseg, mode_b, dbg, n_tiles;
   int H, W, Hp, Wp, PLh, PLw, HpWp, T_inner, N_img, total_pos;
   int K_total, KB, Cout, BLOCK_N, b_stages, tmem_cols, b_off, b_stage_bytes, data_bytes;
   const uint8_t* wpk;
@@ -106,17 +106,20 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int L0 = blockIdx.x * BLOCK_M;          // first frame position of this tile
-  const int n_tile = blockIdx.y;
+  // 1-D grid, n tile fastest: the CTAs that share the activations of an M tile run together, so the rows they
+  // stage come from L2 after the first touch (backward-data of the wide dense layers has 15 n tiles per M tile)
+  const int m_tile = (int)(blockIdx.x / (unsigned)p.n_tiles);
+  const int n_tile = (int)(blockIdx.x - (unsigned)m_tile * (unsigned)p.n_tiles);
+  const int L0 = m_tile * BLOCK_M;              // first frame position of this tile
   const int n0 = n_tile * p.BLOCK_N;
   const int S = p.b_stages;
   const uint32_t b_tile_bytes = (uint32_t)p.BLOCK_N * 128u;
-  const bool dbg = p.dbg && blockIdx.x < 256 && blockIdx.y == 0 && tid == 0;
+  const bool dbg = p.dbg && m_tile < 256 && n_tile == 0 && tid == 0;
   if (dbg) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    g_tc_timeline[blockIdx.x * 8 + 0] = clock64();
-    g_tc_timeline[blockIdx.x * 8 + 5] = smid;
+    g_tc_timeline[m_tile * 8 + 0] = clock64();
+    g_tc_timeline[m_tile * 8 + 5] = smid;
   }
 
   // ---------------- setup: frame position -> pixel tables ----------------
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = bk->tmem_ptr;
-  if (dbg) g_tc_timeline[blockIdx.x * 8 + 1] = clock64();
+  if (dbg) g_tc_timeline[m_tile * 8 + 1] = clock64();
 
   if (warp < kEpiWarps) {
     // ---------------- activation producers ----------------
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
       for (int s = 0; s < p.nseg; ++s) load_region(s, 0, 0);
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&bk->a_full[0]));
-      if (dbg) g_tc_timeline[blockIdx.x * 8 + 2] = clock64();
+      if (dbg) g_tc_timeline[m_tile * 8 + 2] = clock64();
     } else {
       const int nch = p.seg[0].nch;
       for (int cc = 0; cc < nch; ++cc) {
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
     if (EPI == TC_EPI_CONV) {
       mbar_wait(smem_u32(&bk->tmem_full), 0);
       tc_fence_after();
-      if (dbg) g_tc_timeline[blockIdx.x * 8 + 3] = clock64();
+      if (dbg) g_tc_timeline[m_tile * 8 + 3] = clock64();
       for (int c0 = half * 32; c0 < p.BLOCK_N; c0 += 64) {
         float v[32];
         tmem_ld16(t_row + c0, v);
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
         }
       mbar_wait(smem_u32(&bk->tmem_full), 0);
       tc_fence_after();
-      if (dbg) g_tc_timeline[blockIdx.x * 8 + 3] = clock64();
+      if (dbg) g_tc_timeline[m_tile * 8 + 3] = clock64();
       const int row_a = r0 + srow, row_b = r0 + 16 + srow;
       const bool ok_a = bk->valid[row_a] != 0, ok_b = bk->valid[row_b] != 0;
       // coalesced store of one staged 8-wide segment
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
     }
   }
 
-  if (dbg) g_tc_timeline[blockIdx.x * 8 + 4] = clock64();
+  if (dbg) g_tc_timeline[m_tile * 8 + 4] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
@@ -687,7 +690,9 @@ int launch_conv(const DevParams& dp, const Plan& pl, cudaStream_t st) {
     }
     configured = true;
   }
-  dim3 grid((unsigned)((pl.total_pos + BLOCK_M - 1) / BLOCK_M), (unsigned)pl.n_tiles);
+  const long long m_tiles = (pl.total_pos + BLOCK_M - 1) / BLOCK_M;
+  if (m_tiles * pl.n_tiles >= (1LL << 31)) { fov_set_error("tc_conv: grid too large"); return FOV_ERR_ARG; }
+  dim3 grid((unsigned)(m_tiles * pl.n_tiles));
   tc_conv_kernel<NS, EPI><<<grid, kThreads, pl.smem_bytes, st>>>(dp);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
@@ -768,7 +773,7 @@ int tc_conv_run(const TcConv& c, cudaStream_t st) {
   if (!c.prepacked && (rc = tc_conv_pack(c, st))) return rc;
 
   DevParams dp{};
-  dp.nseg = c.nseg; dp.mode_b = pl.mode_b; dp.dbg = g_tc_debug;
+  dp.nseg = c.nseg; dp.mode_b = pl.mode_b; dp.dbg = g_tc_debug; dp.n_tiles = pl.n_tiles;
   for (int s = 0; s < c.nseg; ++s) {
     const TcSeg& g = c.seg[s];
     const SegPlan& sp = pl.sp[s];

@@ -430,7 +430,7 @@ extern "C" int fov_lstm_seq2seq_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
   // more CTAs in flight and a shorter per-step chain)
   int spt = 16;
   if (fwd_smem_bytes(P.cfg, 16) > 200 * 1024 || cfg->B <= 32 * fov_num_sms()) spt = 8;
-  if (cfg->B <= 24 * fov_num_sms()) spt = 4;
+  if (cfg->B <= 48 * fov_num_sms()) spt = 4;
   const int bt = 4 * spt, grid = (cfg->B + bt - 1) / bt;
   const size_t smem = fwd_smem_bytes(P.cfg, spt);
   const bool hs = cfg->rec_act == FOV_REC_HARD_SIGMOID;
@@ -457,7 +457,7 @@ extern "C" int fov_lstm_seq2seq_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
   P.cfg = *cfg; P.w = *w; P.io = *io; P.g = *g;
   if (P.cfg.T_dec == 0) P.cfg.out_dim = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int spt = cfg->B <= 24 * fov_num_sms() ? 4 : 8;
+  const int spt = cfg->B <= 48 * fov_num_sms() ? 4 : 8;
   const int bt = 4 * spt, grid = (cfg->B + bt - 1) / bt;
   const size_t smem = bwd_smem_bytes(spt);
   const bool hsb = cfg->rec_act == FOV_REC_HARD_SIGMOID;
