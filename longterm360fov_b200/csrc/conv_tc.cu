@@ -57,7 +57,7 @@ struct DevSeg {
 
 struct DevParams {
   DevSeg seg[2];
-  int nseg, mode_b, dbg, n_tiles;
+  int nseg, mode_b, dbg, n_tiles, pipe;
   int H, W, Hp, Wp, PLh, PLw, HpWp, T_inner, N_img, total_pos;
   int K_total, KB, Cout, BLOCK_N, b_stages, tmem_cols, b_off, b_stage_bytes, data_bytes;
   const uint8_t* wpk;
@@ -245,6 +245,61 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&bk->a_full[0]));
       if (dbg) g_tc_timeline[m_tile * 8 + 2] = clock64();
+    } else if (p.pipe) {
+      // wide dense / 1x1 layers (one 8-row batch per thread and chunk, aligned rows): the loads of chunk cc+1 are
+      // issued before chunk cc is converted, so the HBM latency hides behind the conversion and the ring wait
+      const DevSeg& sg = p.seg[0];
+      const int nch = sg.nch;
+      const int lg = sg.lpr_log2, lpr = 1 << lg;
+      const int c4 = tid & (lpr - 1);
+      const int row0 = tid >> lg, rstep = kProducers >> lg;
+      const uint32_t a0 = (uint32_t)row0 * sg.row_bytes + (uint32_t)c4 * 8u;
+      const uint32_t st_off = a0 ^ (((a0 >> 7) & (uint32_t)sg.swz_mask) << 4);
+      int offs[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int row = row0 + j * rstep;
+        offs[j] = row < sg.R ? bk->rp[0][row] : -1;
+      }
+      auto issue = [&](int cc, float4 (&v)[8]) {
+        const int ch = cc * BLOCK_K + c4 * 4;
+        const bool ok = ch < sg.Cin;                       // Cin % 4 == 0 on this path
+        const float* xb = sg.x + ch;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && offs[j] >= 0) v[j] = __ldg(reinterpret_cast<const float4*>(xb + offs[j]));
+        }
+      };
+      auto commit = [&](int buf, const float4 (&v)[8]) {
+        uint8_t* reg = smem + sg.region_off + (size_t)buf * NS * sg.term_bytes;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (row0 + j * rstep < sg.R) {
+            uint2 pk[NS];
+            split4<NS>(v[j], pk);
+#pragma unroll
+            for (int t = 0; t < NS; ++t)
+              *reinterpret_cast<uint2*>(reg + t * sg.term_bytes + (j * rstep) * sg.row_bytes + st_off) = pk[t];
+          }
+        }
+      };
+      float4 va[8], vb[8];
+      issue(0, va);
+      for (int cc = 0; cc < nch; cc += 2) {
+        if (cc + 1 < nch) issue(cc + 1, vb);
+        mbar_wait(smem_u32(&bk->a_empty[0]), ((uint32_t)(cc >> 1) & 1u) ^ 1u);
+        commit(0, va);
+        fence_proxy_async_smem();
+        mbar_arrive(smem_u32(&bk->a_full[0]));
+        if (cc + 1 < nch) {
+          if (cc + 2 < nch) issue(cc + 2, va);
+          mbar_wait(smem_u32(&bk->a_empty[1]), ((uint32_t)(cc >> 1) & 1u) ^ 1u);
+          commit(1, vb);
+          fence_proxy_async_smem();
+          mbar_arrive(smem_u32(&bk->a_full[1]));
+        }
+      }
     } else {
       const int nch = p.seg[0].nch;
       for (int cc = 0; cc < nch; ++cc) {
@@ -799,6 +854,9 @@ int tc_conv_run(const TcConv& c, cudaStream_t st) {
   dp.K_total = pl.K_total; dp.KB = pl.KB; dp.Cout = c.Cout; dp.BLOCK_N = pl.BLOCK_N; dp.b_stages = pl.b_stages;
   dp.tmem_cols = pl.tmem_cols; dp.b_off = pl.b_off; dp.b_stage_bytes = pl.b_stage_bytes; dp.data_bytes = pl.data_bytes;
   dp.wpk = reinterpret_cast<const uint8_t*>(((uintptr_t)c.ws + 255) & ~(uintptr_t)255);
+  // software-pipelined producer: multi-chunk segment, aligned rows, one 8-row batch per thread and chunk
+  dp.pipe = pl.mode_b && dp.seg[0].vec == 4 && dp.seg[0].x != nullptr &&
+            dp.seg[0].R <= 8 * (kProducers >> dp.seg[0].lpr_log2);
   dp.bias = c.bias;
   auto span_ok = [&](long long outer, long long inner, long long pix_stride) {
     return (long long)((c.N_img + c.T_inner - 1) / c.T_inner) * (outer > 0 ? outer : 1) + (long long)c.T_inner * inner +
