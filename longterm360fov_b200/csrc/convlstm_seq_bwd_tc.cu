@@ -269,9 +269,14 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
       }
       // ---- gate gradients of my items ----
       float* gz = p.gates + (long long)t * p.z_t;
+      const bool hard = p.rec_act == FOV_REC_HARD_SIGMOID;
+      auto rec_grad = [hard](float a) {             // derivative of the recurrent activation through its output
+        const float gh = (a > 0.0f && a < 1.0f) ? 0.2f : 0.0f, gs = a * (1.0f - a);
+        return hard ? gh : gs;
+      };
 #pragma unroll
       for (int j = 0; j < NIT; ++j) {
-        if (off_g[j] < 0) continue;               // not a pixel: nothing to compute, nothing to fetch
+        const bool ok = off_g[j] >= 0;               // not a pixel: inputs read as zeros, nothing is stored
         const float gi_[4] = {vg[j][0].x, vg[j][0].y, vg[j][0].z, vg[j][0].w};
         const float gf_[4] = {vg[j][1].x, vg[j][1].y, vg[j][1].z, vg[j][1].w};
         const float gg_[4] = {vg[j][2].x, vg[j][2].y, vg[j][2].z, vg[j][2].w};
@@ -283,19 +288,21 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
         float dz[4][4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float tc_ = tanhf(ct_[e]);
+          // branch-free (selects only): the 16 element chains of a thread stay interleavable
+          const float tc_ = fast_tanh(ct_[e]);
           const float dog = dh_[e] * tc_;
           const float dct = fmaf(dh_[e] * go_[e], 1.0f - tc_ * tc_, dcv[e]);
           dcv[e] = dct * gf_[e];
-          dz[0][e] = dct * gg_[e] * fov_rec_act_grad_rt(p.rec_act, gi_[e]);
-          dz[1][e] = dct * cp_[e] * fov_rec_act_grad_rt(p.rec_act, gf_[e]);
+          dz[0][e] = dct * gg_[e] * rec_grad(gi_[e]);
+          dz[1][e] = dct * cp_[e] * rec_grad(gf_[e]);
           dz[2][e] = dct * gi_[e] * (1.0f - gg_[e] * gg_[e]);
-          dz[3][e] = dog * fov_rec_act_grad_rt(p.rec_act, go_[e]);
+          dz[3][e] = dog * rec_grad(go_[e]);
         }
         dc[j] = make_float4(dcv[0], dcv[1], dcv[2], dcv[3]);
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) {
           const float4 z4 = make_float4(dz[gi][0], dz[gi][1], dz[gi][2], dz[gi][3]);
+          if (!ok) continue;
           *reinterpret_cast<float4*>(gz + off_g[j] + gi * F) = z4;
           // bf16 terms into the operand rows: channel gi*F + ch of chunk (channel / 64)
           const int zc = gi * F + ch;

@@ -25,6 +25,8 @@ namespace {
 
 using namespace tc;
 
+int g_seq_wpg = 0;               // diagnostics: force 4 or 8 worker warps per group (0 = choose)
+
 constexpr int kRows = 128;       // D rows (frame positions) of one image group
 constexpr int kSeqMaxTaps = 64;
 constexpr int kXI = 9;           // float4 of the next input frame each worker thread keeps in flight
@@ -64,12 +66,20 @@ struct SeqBook {
 
 // diagnostics: cycles CTA 0 spent per phase (fov_debug_seq_read): [0] worker wait tmem_full, [1] phase A, [2] phase B,
 // [3] x store + arrive, [4] total worker loop, [5] MMA wait a_full, [6] MMA issue, [7] MMA total
-__device__ unsigned long long g_seq_timeline[8];
+__device__ unsigned long long g_seq_timeline[16];   // [8..12]: phase A split: tmem ld, gate math, h store, tmem st, pair barrier
 
-template <int NS, int F, int NG>
-__global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_seq_fwd_kernel(const SeqParams p) {
-  constexpr int kWWarp = 4 * NG, kMmaWarp = 4 * NG + 1, kThr = 32 * (4 * NG + 2);
+// WPG = worker warps per image group: 4 (one thread per accumulator row does all F channels) or 8 (the two warps of
+// a TMEM lane quarter split the channel passes and the copy-out chunks: twice the threads for the gate algebra)
+template <int NS, int F, int NG, int WPG>
+__global__ void __launch_bounds__(32 * (WPG * NG + 2), NG == 1 ? 2 : 1) convlstm_seq_fwd_kernel(const SeqParams p) {
+  constexpr int kWWarp = WPG * NG, kMmaWarp = WPG * NG + 1, kThr = 32 * (WPG * NG + 2);
   constexpr int N4F = 4 * F;
+  constexpr int GT = WPG * 32;                       // worker threads per group
+  constexpr int XI = WPG == 8 ? 5 : kXI;             // float4 of the next input frame per worker thread
+  constexpr int TW = WPG == 8 ? 16 : 32;             // accumulator columns per copy-out chunk
+  constexpr int STS = TW + 4;                        // floats per row of a warp's staging tile
+  constexpr int NP = F / 8;                          // 8-channel passes
+  constexpr int PPW = WPG == 8 ? (NP + 1) / 2 : NP;  // passes per warp
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -89,7 +99,7 @@ __global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_s
   if (warp == kMmaWarp && lane == 0) {
     mbar_init(smem_u32(&bk->w_full), 1);
     for (int g = 0; g < NG; ++g) {
-      mbar_init(smem_u32(&bk->a_full[g]), kRows);
+      mbar_init(smem_u32(&bk->a_full[g]), GT);
       mbar_init(smem_u32(&bk->tmem_full[g]), 1);
     }
     fence_mbar_init();
@@ -107,9 +117,11 @@ __global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_s
   tc_fence_after();
   const uint32_t tmem_d = bk->tmem_ptr;
 
-  if (warp < 4 * NG) {
-    // ---------------- workers: 128 threads per image group, thread = one frame position (D row) ----------------
-    const int g = warp >> 2, wt = tid & (kRows - 1), q = warp & 3;
+  if (warp < WPG * NG) {
+    // ---------------- workers: thread = one frame position (D row) [x one half of the channel passes at WPG = 8] ----
+    const int g = warp / WPG, wg = warp % WPG, q = wg & 3, half = wg >> 2;
+    const int wt = q * 32 + lane;                    // my accumulator row / TMEM lane
+    const int gtd = wg * 32 + lane;                  // my index among the group's worker threads
     const int b0 = (blockIdx.x * NG + g) * p.G;
     uint8_t* xreg = smem + p.act_off + (uint32_t)g * p.grp_bytes;
     uint8_t* hreg = xreg + NS * p.seg[0].term_bytes;
@@ -132,18 +144,18 @@ __global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_s
     const int off_g = valid ? (int)((long long)b * p.z_b + (long long)pix * N4F) : -1;
     const int off_h = valid ? (int)((long long)b * p.h_b + (long long)pix * p.h_pix) : -1;
     const int off_d = valid ? (int)(((long long)b * p.HW + pix) * F) : -1;
-    float* stg = reinterpret_cast<float*>(smem + p.stg_off) + (size_t)warp * (32 * kStgStride);
+    float* stg = reinterpret_cast<float*>(smem + p.stg_off) + (size_t)warp * (32 * STS);
     // my row of the recurrent operand region, absolute-address swizzle (region bases are 1024-byte aligned)
     const uint32_t hrow = (uint32_t)(wt - sh.minshift) * (uint32_t)sh.row_bytes;
 
     // input staging items: idx -> (region row, 4-channel slot)
     const int lg = sx.lpr_log2, lpr = 1 << lg;
     const int n_items = sx.R * lpr;
-    int goff[kXI];
+    int goff[XI];
 #pragma unroll
-    for (int j = 0; j < kXI; ++j) {
+    for (int j = 0; j < XI; ++j) {
       goff[j] = -1;
-      const int idx = wt + j * kRows;
+      const int idx = gtd + j * GT;
       if (idx < n_items) {
         const int row = idx >> lg, ch = (idx & (lpr - 1)) * 4;
         const int pos = sx.minshift + row;
@@ -156,24 +168,24 @@ __global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_s
         }
       }
     }
-    auto x_load = [&](int t, float4 (&xv)[kXI]) {
+    auto x_load = [&](int t, float4 (&xv)[XI]) {
       const float* xt = p.x + (long long)t * p.x_t;
 #pragma unroll
-      for (int j = 0; j < kXI; ++j) {
+      for (int j = 0; j < XI; ++j) {
         xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (goff[j] >= 0) {
-          const int ch = ((wt + j * kRows) & (lpr - 1)) * 4;
+          const int ch = ((gtd + j * GT) & (lpr - 1)) * 4;
           int nv = sx.Cin - ch;
           nv = nv > 4 ? 4 : nv;
           xv[j] = ldg_vec4(xt + goff[j], nv, p.x_vec);
         }
       }
     };
-    auto x_store = [&](const float4 (&xv)[kXI]) {
+    auto x_store = [&](const float4 (&xv)[XI]) {
 #pragma unroll
-      for (int j = 0; j < kXI; ++j) {
+      for (int j = 0; j < XI; ++j) {
         if (goff[j] >= 0) {
-          const int idx = wt + j * kRows;
+          const int idx = gtd + j * GT;
           const uint32_t a0 = (uint32_t)(idx >> lg) * (uint32_t)sx.row_bytes + (uint32_t)(idx & (lpr - 1)) * 8u;
           const uint32_t so = a0 ^ (((a0 >> 7) & (uint32_t)sx.swz_mask) << 4);
           uint2 pk[NS];
@@ -196,27 +208,30 @@ __global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_s
     };
 
     // initial state
-    float cst[F];
+    // my channel passes: pass = half + 2 * pi (WPG = 8) or pi (WPG = 4); cell state of pass pi in cst[8 * pi ..]
+    float cst[PPW * 8];
 #pragma unroll
-    for (int j = 0; j < F; ++j) cst[j] = 0.0f;
-    if (valid && p.c0) {
+    for (int j = 0; j < PPW * 8; ++j) cst[j] = 0.0f;
 #pragma unroll
-      for (int j = 0; j < F; j += 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p.c0 + off_d + j));
-        cst[j] = v.x; cst[j + 1] = v.y; cst[j + 2] = v.z; cst[j + 3] = v.w;
-      }
-    }
-    if (valid && p.h0) {
-#pragma unroll
-      for (int pass = 0; pass < F / 8; ++pass) {
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(p.h0 + off_d + pass * 8));
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(p.h0 + off_d + pass * 8 + 4));
-        const float hn[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        h_store(pass, hn);
+    for (int pi = 0; pi < PPW; ++pi) {
+      const int pass = WPG == 8 ? half + 2 * pi : pi;
+      if (pass < NP && valid) {
+        if (p.c0) {
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(p.c0 + off_d + pass * 8));
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(p.c0 + off_d + pass * 8 + 4));
+          cst[pi * 8 + 0] = v0.x; cst[pi * 8 + 1] = v0.y; cst[pi * 8 + 2] = v0.z; cst[pi * 8 + 3] = v0.w;
+          cst[pi * 8 + 4] = v1.x; cst[pi * 8 + 5] = v1.y; cst[pi * 8 + 6] = v1.z; cst[pi * 8 + 7] = v1.w;
+        }
+        if (p.h0) {
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(p.h0 + off_d + pass * 8));
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(p.h0 + off_d + pass * 8 + 4));
+          const float hn[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          h_store(pass, hn);
+        }
       }
     }
 
-    float4 xv[kXI];
+    float4 xv[XI];
     x_load(0, xv);
     x_store(xv);
     fence_proxy_async_smem();
@@ -235,7 +250,7 @@ __global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_s
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < WD; j += 4)
-        *reinterpret_cast<float4*>(&stg[lane * kStgStride + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        *reinterpret_cast<float4*>(&stg[lane * STS + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       __syncwarp();
       const int rsub = lane / LPR, c4 = (lane % LPR) * 4;
 #pragma unroll
@@ -244,7 +259,7 @@ __global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_s
         const int o = __shfl_sync(0xffffffffu, my_off, r);
         const int o2 = __shfl_sync(0xffffffffu, my_off2, r);
         if (o >= 0) {
-          const float4 a = *reinterpret_cast<const float4*>(&stg[r * kStgStride + c4]);
+          const float4 a = *reinterpret_cast<const float4*>(&stg[r * STS + c4]);
           *reinterpret_cast<float4*>(dst + o + c4) = a;
           if (dst2) *reinterpret_cast<float4*>(dst2 + o2 + c4) = a;
         }
@@ -252,7 +267,7 @@ __global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_s
       __syncwarp();
     };
     const bool dbg = p.dbg && blockIdx.x == 0 && tid == 0;
-    long long tw = 0, ta = 0, tb = 0, tx = 0, c0k = 0, c1k = 0, c2k = 0, c3k = 0;
+    long long tw = 0, ta = 0, tb = 0, tx = 0, c0k = 0, c1k = 0, c2k = 0, c3k = 0, a_ld = 0, a_math = 0, a_hst = 0, a_st = 0;
     const long long t_begin = clock64();
     for (int t = 0; t < p.T; ++t) {
       if (t + 1 < p.T) x_load(t + 1, xv);
@@ -263,60 +278,92 @@ __global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_s
       const bool last = t == p.T - 1;
       // ---- phase A: gate algebra on my row, 8 channels per pass; results go back to TMEM ----
 #pragma unroll
-      for (int pass = 0; pass < F / 8; ++pass) {
+      for (int pi = 0; pi < PPW; ++pi) {
+        const int pass = WPG == 8 ? half + 2 * pi : pi;
+        if (pass >= NP) continue;                     // F = 8 at WPG = 8: the upper warp has no pass
         const int cp = pass * 8;
         float gt[4][8];
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) tmem_ld8(t_row + gi * F + cp, gt[gi]);
-        float bs[4][8];
-#pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {
-          const float4 b0v = *reinterpret_cast<const float4*>(&bk->bias_s[pass * 32 + gi * 8]);
-          const float4 b1v = *reinterpret_cast<const float4*>(&bk->bias_s[pass * 32 + gi * 8 + 4]);
-          bs[gi][0] = b0v.x; bs[gi][1] = b0v.y; bs[gi][2] = b0v.z; bs[gi][3] = b0v.w;
-          bs[gi][4] = b1v.x; bs[gi][5] = b1v.y; bs[gi][6] = b1v.z; bs[gi][7] = b1v.w;
-        }
+        const float* bp = &bk->bias_s[pass * 32];
+        long long d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+        if (dbg) d0 = clock64();
         tmem_ld_wait();
+        if (dbg) { d1 = clock64(); a_ld += d1 - d0; }
         float cn[8], hn[8];
+        // the recurrent-activation choice is hoisted out of the channel loop: a per-call branch would fence the eight
+        // independent channel chains off from each other (no ILP for the MUFU latencies)
+        if (p.rec_act == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int ch = cp + j;
-          const float ai = fast_rec(p.rec_act, gt[0][j] + bs[0][j]);
-          const float af = fast_rec(p.rec_act, gt[1][j] + bs[1][j]);
-          const float ag = fast_tanh(gt[2][j] + bs[2][j]);
-          const float ao = fast_rec(p.rec_act, gt[3][j] + bs[3][j]);
-          cn[j] = af * cst[ch] + ai * ag;
-          hn[j] = ao * fast_tanh(cn[j]);
-          cst[ch] = cn[j];
-          gt[0][j] = ai; gt[1][j] = af; gt[2][j] = ag; gt[3][j] = ao;
+          for (int j = 0; j < 8; ++j) {
+            const float ai = fminf(fmaxf(0.2f * (gt[0][j] + bp[j]) + 0.5f, 0.0f), 1.0f);
+            const float af = fminf(fmaxf(0.2f * (gt[1][j] + bp[8 + j]) + 0.5f, 0.0f), 1.0f);
+            const float ag = fast_tanh(gt[2][j] + bp[16 + j]);
+            const float ao = fminf(fmaxf(0.2f * (gt[3][j] + bp[24 + j]) + 0.5f, 0.0f), 1.0f);
+            cn[j] = af * cst[pi * 8 + j] + ai * ag;
+            hn[j] = ao * fast_tanh(cn[j]);
+            cst[pi * 8 + j] = cn[j];
+            gt[0][j] = ai; gt[1][j] = af; gt[2][j] = ag; gt[3][j] = ao;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float ai = __fdividef(1.0f, 1.0f + __expf(-(gt[0][j] + bp[j])));
+            const float af = __fdividef(1.0f, 1.0f + __expf(-(gt[1][j] + bp[8 + j])));
+            const float ag = fast_tanh(gt[2][j] + bp[16 + j]);
+            const float ao = __fdividef(1.0f, 1.0f + __expf(-(gt[3][j] + bp[24 + j])));
+            cn[j] = af * cst[pi * 8 + j] + ai * ag;
+            hn[j] = ao * fast_tanh(cn[j]);
+            cst[pi * 8 + j] = cn[j];
+            gt[0][j] = ai; gt[1][j] = af; gt[2][j] = ag; gt[3][j] = ao;
+          }
         }
+        if (dbg) { d2 = clock64(); a_math += d2 - d1; }
         if (valid) h_store(pass, hn);
+        if (dbg) { d3 = clock64(); a_hst += d3 - d2; }
         if (p.training) {
 #pragma unroll
           for (int gi = 0; gi < 4; ++gi) tmem_st8(t_row + gi * F + cp, gt[gi]);
         }
         tmem_st8(t_row + 4 * F + cp, cn);
         tmem_st8(t_row + 5 * F + cp, hn);
+        if (dbg) a_st += clock64() - d3;
       }
+      long long e0 = 0;
+      if (dbg) e0 = clock64();
       tmem_st_wait();
-      if (dbg) { c2k = clock64(); ta += c2k - c1k; }
-      // ---- phase B: coalesced stores of the activated gates, c_t and h_t ----
-      if (p.training) {
-        float* g_dst = p.gates + (long long)t * p.z_t;
-#pragma unroll
-        for (int c0 = 0; c0 < N4F; c0 += 32)
-          copy_out(std::integral_constant<int, 32>{}, (uint32_t)c0, g_dst + c0, off_g, nullptr, 0);
+      if (dbg) a_st += clock64() - e0;
+      if (WPG == 8) {
+        // the copy-out chunks below read columns written by the partner warp of my lane quarter
+        tc_fence_before();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + g * 4 + q) : "memory");
+        tc_fence_after();
       }
+      if (dbg) { c2k = clock64(); ta += c2k - c1k; }
+      // ---- phase B: coalesced stores of the activated gates, c_t and h_t, TW accumulator columns per chunk; at
+      //      WPG = 8 the two warps of a lane quarter take alternate chunks ----
       {
-        constexpr int WD = F < 32 ? F : 32;
+        int k = 0;
+        if (p.training) {
+          float* g_dst = p.gates + (long long)t * p.z_t;
+#pragma unroll
+          for (int c0 = 0; c0 < N4F; c0 += TW, ++k)
+            if (WPG == 4 || (k & 1) == half)
+              copy_out(std::integral_constant<int, TW>{}, (uint32_t)c0, g_dst + c0, off_g, nullptr, 0);
+        }
+        constexpr int WD = F < TW ? F : TW;
         float* c_dst = p.cseq + (long long)t * p.c_t;
         float* h_dst = p.hseq + (long long)t * p.h_t;
 #pragma unroll
         for (int c0 = 0; c0 < F; c0 += WD) {
-          copy_out(std::integral_constant<int, WD>{}, (uint32_t)(4 * F + c0), c_dst + c0, off_c,
-                   (last && p.cT) ? p.cT + c0 : nullptr, off_d);
-          copy_out(std::integral_constant<int, WD>{}, (uint32_t)(5 * F + c0), h_dst + c0, off_h,
-                   (last && p.hT) ? p.hT + c0 : nullptr, off_d);
+          if (WPG == 4 || (k & 1) == half)
+            copy_out(std::integral_constant<int, WD>{}, (uint32_t)(4 * F + c0), c_dst + c0, off_c,
+                     (last && p.cT) ? p.cT + c0 : nullptr, off_d);
+          ++k;
+          if (WPG == 4 || (k & 1) == half)
+            copy_out(std::integral_constant<int, WD>{}, (uint32_t)(5 * F + c0), h_dst + c0, off_h,
+                     (last && p.hT) ? p.hT + c0 : nullptr, off_d);
+          ++k;
         }
       }
       if (dbg) { c3k = clock64(); tb += c3k - c2k; }
@@ -331,6 +378,7 @@ __global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_s
     if (dbg) {
       g_seq_timeline[0] = tw; g_seq_timeline[1] = ta; g_seq_timeline[2] = tb; g_seq_timeline[3] = tx;
       g_seq_timeline[4] = clock64() - t_begin;
+      g_seq_timeline[8] = a_ld; g_seq_timeline[9] = a_math; g_seq_timeline[10] = a_hst; g_seq_timeline[11] = a_st;
     }
   } else if (warp == kWWarp) {
     // ---------------- weights: every k-block, once ----------------
@@ -401,7 +449,7 @@ __global__ void __launch_bounds__(32 * (4 * NG + 2), NG == 1 ? 2 : 1) convlstm_s
 
 struct SeqPlan {
   TcStepPlan sp;
-  int G, NG;
+  int G, NG, WPG;
   uint32_t grp_bytes, act_off, stg_off, data_bytes, tmem_cols;
   size_t smem_bytes;
 };
@@ -416,21 +464,38 @@ int seq_plan(const fov_convlstm_cfg* c, const TcConv& step, SeqPlan* out) {
   FOV_CHECK_ARG(F == 8 || F == 16 || F == 32 || F == 64, "F must be 8/16/32/64");
   pl.G = kRows / (sp.Hp * sp.Wp);
   FOV_CHECK_ARG(pl.G >= 1, "image larger than one MMA tile");
-  FOV_CHECK_ARG(sp.seg[0].R * (1 << sp.seg[0].lpr_log2) <= kXI * kRows, "input frame too wide to prefetch");
+  const int x_items = sp.seg[0].R * (1 << sp.seg[0].lpr_log2);
+  FOV_CHECK_ARG(x_items <= kXI * kRows, "input frame too wide to prefetch");
   FOV_CHECK_ARG(sp.seg[0].taps <= kSeqMaxTaps && sp.seg[1].taps <= kSeqMaxTaps && sp.K_total / 16 <= kSeqMaxSteps,
                 "too many taps");
   pl.grp_bytes = (uint32_t)sp.NS * (uint32_t)(sp.seg[0].term_bytes + sp.seg[1].term_bytes);
   pl.act_off = (uint32_t)((sp.w_bytes + 1023) / 1024 * 1024);
   const size_t book = sizeof(SeqBook) + 1024;
-  const size_t grp = pl.grp_bytes + 4 * kStgBytes;                      // operands + the staging tiles of 4 warps
-  const size_t one = pl.act_off + grp + book, two = one + grp;
   const size_t kUsable = 227 * 1024;
-  if (2 * (one + 1024) <= 228 * 1024) pl.NG = 1;                       // two CTAs per SM overlap each other
-  else if (two <= kUsable && 2 * 6 * F <= 512) pl.NG = 2;              // one CTA per SM, two groups inside
-  else if (one <= kUsable) pl.NG = 1;
-  else { fov_set_error("persistent ConvLSTM: weights + operands exceed shared memory"); return FOV_ERR_ARG; }
-  pl.stg_off = pl.act_off + (uint32_t)pl.NG * pl.grp_bytes;
-  pl.data_bytes = pl.stg_off + (uint32_t)pl.NG * 4 * kStgBytes;
+  // 8 worker warps per group (16-column staging tiles) when the input frame fits their prefetch registers and the
+  // shared memory allows it, else 4 (32-column tiles)
+  // preference: configurations that overlap MMA and epilogue (two CTAs per SM, or two groups per CTA) first, 8 worker
+  // warps before 4 when a warp gets at least one full pass (F >= 16)
+  int found = 0;
+  for (int round = 0; round < 2 && !found; ++round) {          // round 0: overlapping configurations only
+    for (int wpg = 8; wpg >= 4 && !found; wpg -= 4) {
+      if (g_seq_wpg && wpg != g_seq_wpg) continue;
+      if (wpg == 8 && (x_items > 5 * 256 || F < 16)) continue;
+      const size_t tile = (size_t)32 * ((wpg == 8 ? 16 : 32) + 4) * 4;
+      const size_t grp = pl.grp_bytes + wpg * tile;                      // operands + the staging tiles of the group
+      const size_t one = pl.act_off + grp + book, two = one + grp;
+      int ng = 0;
+      if (2 * (one + 1024) <= 228 * 1024) ng = 1;                        // two CTAs per SM overlap each other
+      else if (two <= kUsable && 2 * 6 * F <= 512) ng = 2;               // one CTA per SM, two groups inside
+      else if (round == 1 && one <= kUsable) ng = 1;
+      if (!ng) continue;
+      found = 1;
+      pl.WPG = wpg; pl.NG = ng;
+      pl.stg_off = pl.act_off + (uint32_t)ng * pl.grp_bytes;
+      pl.data_bytes = pl.stg_off + (uint32_t)(ng * wpg * tile);
+    }
+  }
+  if (!found) { fov_set_error("persistent ConvLSTM: weights + operands exceed shared memory"); return FOV_ERR_ARG; }
   pl.smem_bytes = pl.data_bytes + book;
   pl.tmem_cols = tmem_cols_for(pl.NG * 6 * F);
   // 32-bit element offsets inside the kernel
@@ -442,11 +507,11 @@ int seq_plan(const fov_convlstm_cfg* c, const TcConv& step, SeqPlan* out) {
   return FOV_OK;
 }
 
-template <int NS, int F, int NG>
+template <int NS, int F, int NG, int WPG>
 int launch_seq(const SeqParams& p, const SeqPlan& pl, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(convlstm_seq_fwd_kernel<NS, F, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(convlstm_seq_fwd_kernel<NS, F, NG, WPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) {
       fov_set_error("convlstm_seq: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -454,14 +519,15 @@ int launch_seq(const SeqParams& p, const SeqPlan& pl, int grid, cudaStream_t st)
     }
     configured = true;
   }
-  convlstm_seq_fwd_kernel<NS, F, NG><<<grid, 32 * (4 * NG + 2), pl.smem_bytes, st>>>(p);
+  convlstm_seq_fwd_kernel<NS, F, NG, WPG><<<grid, 32 * (WPG * NG + 2), pl.smem_bytes, st>>>(p);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
 
 template <int NS, int F>
 int launch_seq_ng(const SeqParams& p, const SeqPlan& pl, int grid, cudaStream_t st) {
-  return pl.NG == 2 ? launch_seq<NS, F, 2>(p, pl, grid, st) : launch_seq<NS, F, 1>(p, pl, grid, st);
+  if (pl.WPG == 8) return pl.NG == 2 ? launch_seq<NS, F, 2, 8>(p, pl, grid, st) : launch_seq<NS, F, 1, 8>(p, pl, grid, st);
+  return pl.NG == 2 ? launch_seq<NS, F, 2, 4>(p, pl, grid, st) : launch_seq<NS, F, 1, 4>(p, pl, grid, st);
 }
 template <int NS>
 int launch_seq_f(int F, const SeqParams& p, const SeqPlan& pl, int grid, cudaStream_t st) {
@@ -476,9 +542,10 @@ int launch_seq_f(int F, const SeqParams& p, const SeqPlan& pl, int grid, cudaStr
 }  // namespace
 
 static int g_seq_disable = 0, g_seq_dbg = 0;
+extern "C" void fov_debug_seq_wpg(int wpg) { g_seq_wpg = wpg; }
 extern "C" void fov_debug_seq_enable(int on) { g_seq_dbg = on; }
 extern "C" int fov_debug_seq_read(unsigned long long* out) {
-  return (int)cudaMemcpyFromSymbol(out, g_seq_timeline, sizeof(unsigned long long) * 8);
+  return (int)cudaMemcpyFromSymbol(out, g_seq_timeline, sizeof(unsigned long long) * 16);
 }
 // diagnostics / A-B testing: 1 = always run the per-timestep launches
 extern "C" void fov_debug_convlstm_persistent(int enable) { g_seq_disable = !enable; }

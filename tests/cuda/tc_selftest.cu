@@ -384,10 +384,11 @@ static void test_convlstm_seq(const char* name, int B, int T, int H, int W, int 
           FK(fov_convlstm_fwd(&c, &io, nullptr));
           CK(cudaDeviceSynchronize());
           fov_debug_seq_enable(0);
-          unsigned long long w[8];
+          unsigned long long w[16];
           fov_debug_seq_read(w);
           printf("    CTA0 cycles: worker wait-mma %llu, phase A %llu, phase B %llu, x-store %llu, total %llu | mma thread: "
                  "wait-operands %llu, issue %llu, total %llu\n", w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+          printf("      phase A split: tmem-ld wait %llu, gate math %llu, h store %llu, tmem st %llu\n", w[8], w[9], w[10], w[11]);
         }
       }
       cudaFree(wsf);
