@@ -145,8 +145,8 @@ def kernel_rooflines(lib, dev, B, compute, peaks, seq_per_s_per_gpu):
     persistent = fwd_launches <= 3
     main = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
             "traffic": NCU_TRAFFIC_BYTES.get(B),
-            "kernel": ("convlstm_seq_fwd_kernel<%d,32,2> (persistent ConvLSTM-L0 forward, all %d timesteps in ONE launch, "
-                       "tcgen05 + TMEM, training mode: gates saved)" % (math, T)) if persistent else
+            "kernel": ("convlstm_seq_fwd_kernel<NS=%d,F=32,...> (persistent ConvLSTM-L0 forward, all %d timesteps in ONE "
+                       "launch, tcgen05 + TMEM, training mode: gates saved)" % (math, T)) if persistent else
                       "ConvLSTM-L0 forward, %d launches (compute=%s)" % (fwd_launches, compute),
             "algorithmic_bytes_per_launch": byts_f, "ms_per_launch": ms_f, "launches_per_call": fwd_launches,
             "algorithmic_tflops": flop_f / (ms_f * 1e-3) / 1e12,

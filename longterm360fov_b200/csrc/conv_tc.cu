@@ -524,16 +524,31 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
         for (int gi = 0; gi < 4; ++gi) tmem_ld8(t_row + gi * F + cpass, g[gi]);
         tmem_ld_wait();
         float cn[CW], hn[CW];
+        // recurrent-activation choice hoisted out of the channel loop (a per-call branch serialises the channel chains)
+        if (p.rec_act == 0) {
 #pragma unroll
-        for (int j = 0; j < CW; ++j) {
-          const int ch = cpass + j;
-          const float ai = fast_rec(p.rec_act, g[0][j] + bk->bias_s[ch]);
-          const float af = fast_rec(p.rec_act, g[1][j] + bk->bias_s[F + ch]);
-          const float ag = fast_tanh(g[2][j] + bk->bias_s[2 * F + ch]);
-          const float ao = fast_rec(p.rec_act, g[3][j] + bk->bias_s[3 * F + ch]);
-          cn[j] = af * cpv[j] + ai * ag;
-          hn[j] = ao * fast_tanh(cn[j]);
-          g[0][j] = ai; g[1][j] = af; g[2][j] = ag; g[3][j] = ao;
+          for (int j = 0; j < CW; ++j) {
+            const int ch = cpass + j;
+            const float ai = fminf(fmaxf(0.2f * (g[0][j] + bk->bias_s[ch]) + 0.5f, 0.0f), 1.0f);
+            const float af = fminf(fmaxf(0.2f * (g[1][j] + bk->bias_s[F + ch]) + 0.5f, 0.0f), 1.0f);
+            const float ag = fast_tanh(g[2][j] + bk->bias_s[2 * F + ch]);
+            const float ao = fminf(fmaxf(0.2f * (g[3][j] + bk->bias_s[3 * F + ch]) + 0.5f, 0.0f), 1.0f);
+            cn[j] = af * cpv[j] + ai * ag;
+            hn[j] = ao * fast_tanh(cn[j]);
+            g[0][j] = ai; g[1][j] = af; g[2][j] = ag; g[3][j] = ao;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const int ch = cpass + j;
+            const float ai = __fdividef(1.0f, 1.0f + __expf(-(g[0][j] + bk->bias_s[ch])));
+            const float af = __fdividef(1.0f, 1.0f + __expf(-(g[1][j] + bk->bias_s[F + ch])));
+            const float ag = fast_tanh(g[2][j] + bk->bias_s[2 * F + ch]);
+            const float ao = __fdividef(1.0f, 1.0f + __expf(-(g[3][j] + bk->bias_s[3 * F + ch])));
+            cn[j] = af * cpv[j] + ai * ag;
+            hn[j] = ao * fast_tanh(cn[j]);
+            g[0][j] = ai; g[1][j] = af; g[2][j] = ag; g[3][j] = ao;
+          }
         }
         // ---- rounds of staged segments: (c, h), then the four activated gates ----
         auto put = [&](int col, const float (&a)[CW]) {

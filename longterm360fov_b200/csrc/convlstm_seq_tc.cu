@@ -253,16 +253,23 @@ __global__ void __launch_bounds__(32 * (WPG * NG + 2), NG == 1 ? 2 : 1) convlstm
         *reinterpret_cast<float4*>(&stg[lane * STS + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       __syncwarp();
       const int rsub = lane / LPR, c4 = (lane % LPR) * 4;
+      // all shuffles and tile reads first (independent), then the predicated stores: no per-iteration control flow
+      float4 a[LPR];
+      int o[LPR], o2[LPR];
 #pragma unroll
       for (int it = 0; it < LPR; ++it) {
         const int r = it * RPI + rsub;
-        const int o = __shfl_sync(0xffffffffu, my_off, r);
-        const int o2 = __shfl_sync(0xffffffffu, my_off2, r);
-        if (o >= 0) {
-          const float4 a = *reinterpret_cast<const float4*>(&stg[r * STS + c4]);
-          *reinterpret_cast<float4*>(dst + o + c4) = a;
-          if (dst2) *reinterpret_cast<float4*>(dst2 + o2 + c4) = a;
-        }
+        o[it] = __shfl_sync(0xffffffffu, my_off, r);
+        o2[it] = __shfl_sync(0xffffffffu, my_off2, r);
+        a[it] = *reinterpret_cast<const float4*>(&stg[r * STS + c4]);
+      }
+#pragma unroll
+      for (int it = 0; it < LPR; ++it)
+        if (o[it] >= 0) *reinterpret_cast<float4*>(dst + o[it] + c4) = a[it];
+      if (dst2) {
+#pragma unroll
+        for (int it = 0; it < LPR; ++it)
+          if (o[it] >= 0) *reinterpret_cast<float4*>(dst2 + o2[it] + c4) = a[it];
       }
       __syncwarp();
     };
