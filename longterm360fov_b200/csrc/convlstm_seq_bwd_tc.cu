@@ -30,6 +30,7 @@ constexpr int kWorkers = 256;            // warps 0-7: (row, 4-channel) items, c
 constexpr int kBWWarp = 8, kBMmaWarp = 9;
 constexpr int kBThr = 320;
 constexpr int kMaxSteps = 256;           // k16 steps of the GEMM (taps * 4F / 16)
+constexpr int kMaxMmas = 512;            // MMAs of one timestep's chain (k16 steps x term products)
 constexpr int kMaxItems = 8;             // (row, c4) items per worker thread: 128 * F/4 / 256
 
 struct BwdParams {
@@ -37,7 +38,7 @@ struct BwdParams {
   int F, Cin_p, nch, row_bytes, swz_mask, term_bytes, R, minshift, taps, kw, pad_h, pad_w;
   uint32_t desc_hi;
   int K_total, KB, BLOCK_N, stack;
-  uint32_t w_bytes, kb_bytes, chunk_bytes, act_off, dh_off, data_bytes, tmem_cols;
+  uint32_t w_bytes, kb_bytes, chunk_bytes, act_off, dh_off, mma_off, data_bytes, tmem_cols;
   const uint8_t* wpk;
   float* gates; long long z_b, z_t;              // in: activated gates, out: dZ   (B,T,HW,4F)
   const float* cseq; long long c_b, c_t;         // (B,T,HW,F)
@@ -52,7 +53,6 @@ struct BwdParams {
 };
 
 struct BwdBook {
-  uint2 ops[kMaxSteps];                          // per k16 step: (a_rel, b_rel)
   uint64_t w_full, a_full, tmem_full;
   uint32_t tmem_ptr;
 };
@@ -80,7 +80,13 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
     mbar_init(smem_u32(&bk->a_full), kWorkers);
     mbar_init(smem_u32(&bk->tmem_full), 1);
     fence_mbar_init();
-    // operand addresses of every k16 step: k = tap * Cin_p + channel; channel chunk cc = 64-wide region
+    // Every MMA of a timestep's chain, fully resolved once (A/B descriptor low words, instruction descriptor,
+    // accumulate flag): the issue loop is one 16-byte table read + one tcgen05.mma.  A lone thread computing
+    // descriptors costs ~100 cycles per MMA; the tensor pipe needs 45-64 (tests/cuda/tc_mma_rate_probe.cu).
+    // k16 step e: k = tap * Cin_p + channel; channel chunk cc = 64-wide operand region.
+    uint4* mtab = reinterpret_cast<uint4*>(smem + p.mma_off);
+    const uint32_t b_term = (uint32_t)p.BLOCK_N * 128u;
+    int n = 0;
     for (int e = 0; e < nsteps; ++e) {
       const int k = e * 16;
       const int tap = k / p.Cin_p, ci0 = k - tap * p.Cin_p;
@@ -88,8 +94,20 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
       const int ty = tap / p.kw, tx = tap - ty * p.kw;
       const int shift = (ty - p.pad_h) * p.Wp + (tx - p.pad_w) - p.minshift;
       const int kb = p.nch > 1 ? tap * p.nch + cc : k >> 6;
-      bk->ops[e] = make_uint2(p.act_off + (uint32_t)cc * p.chunk_bytes + (uint32_t)shift * p.row_bytes + (uint32_t)c0 * 2u,
-                              (uint32_t)kb * p.kb_bytes + (uint32_t)((k >> 4) & 3) * 32u);
+      const uint32_t a_addr = base + p.act_off + (uint32_t)cc * p.chunk_bytes + (uint32_t)shift * p.row_bytes + (uint32_t)c0 * 2u;
+      const uint32_t b_addr = base + (uint32_t)kb * p.kb_bytes + (uint32_t)((k >> 4) & 3) * 32u;
+      if (p.stack) {
+        for (int sa = 0; sa < NS; ++sa)
+          mtab[n++] = make_uint4((((a_addr + sa * p.term_bytes) >> 4) & 0x3FFFu) | (1u << 16),
+                                 ((b_addr >> 4) & 0x3FFFu) | (1u << 16),
+                                 idesc_bf16_f32(kRows, (NS - sa) * p.BLOCK_N, 0, 0), n > 0 ? 1u : 0u);
+      } else {
+        for (int sum = NS - 1; sum >= 0; --sum)
+          for (int sa = 0; sa <= sum; ++sa)
+            mtab[n++] = make_uint4((((a_addr + sa * p.term_bytes) >> 4) & 0x3FFFu) | (1u << 16),
+                                   (((b_addr + (sum - sa) * b_term) >> 4) & 0x3FFFu) | (1u << 16),
+                                   idesc_bf16_f32(kRows, p.BLOCK_N, 0, 0), n > 0 ? 1u : 0u);
+      }
     }
   }
   if (warp == kBWWarp) {
@@ -356,8 +374,8 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
   } else {
     // ---------------- MMA issuer: dh_rec_{t-1} = conv^T(dZ_t, R), one chain per step ----------------
     if (lane == 0) {
-      const uint32_t idesc = idesc_bf16_f32(kRows, p.BLOCK_N, 0, 0);
-      const uint32_t b_term = (uint32_t)p.BLOCK_N * 128u;
+      const int nmma = nsteps * (p.stack ? NS : NS * (NS + 1) / 2);
+      const uint4* mtab = reinterpret_cast<const uint4*>(smem + p.mma_off);
       mbar_wait(smem_u32(&bk->w_full), 0);
       const bool dbg = (p.dbg & 1) && blockIdx.x == 0;
       long long mw = 0, mi = 0;
@@ -368,30 +386,13 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
         tc_fence_after();
         const long long q1 = clock64();
         mw += q1 - q0;
-        if (p.stack) {
-          // the bf16 terms of a weight tile are adjacent in shared memory, so ONE MMA with N = (NS - sa) * BLOCK_N
-          // multiplies A term sa by the B terms 0 .. NS-1-sa: NS MMAs per k step instead of NS (NS + 1) / 2; product
-          // (sa, sb) lands in accumulator columns [sb * BLOCK_N, +BLOCK_N) and the read-back sums the column blocks
-          for (int e = 0; e < nsteps; ++e) {
-            const uint2 o = bk->ops[e];
-#pragma unroll
-            for (int sa = 0; sa < NS; ++sa)
-              umma_bf16(tmem_d, desc_at(p.desc_hi, base + o.x + sa * p.term_bytes), desc_at(kDescHi128, base + o.y),
-                        idesc_bf16_f32(kRows, (NS - sa) * p.BLOCK_N, 0, 0), (e > 0 || sa > 0) ? 1u : 0u);
-          }
-        } else {
-          for (int e = 0; e < nsteps; ++e) {
-            const uint2 o = bk->ops[e];
-#pragma unroll
-            for (int sum = NS - 1; sum >= 0; --sum) {
-#pragma unroll
-              for (int sa = 0; sa <= sum; ++sa) {
-                const int sb = sum - sa;
-                umma_bf16(tmem_d, desc_at(p.desc_hi, base + o.x + sa * p.term_bytes),
-                          desc_at(kDescHi128, base + o.y + sb * b_term), idesc, (e > 0 || sum != NS - 1 || sa > 0) ? 1u : 0u);
-              }
-            }
-          }
+        // stacked terms: the bf16 terms of a weight tile are adjacent in shared memory, so ONE MMA with
+        // N = (NS - sa) * BLOCK_N multiplies A term sa by the B terms 0 .. NS-1-sa (NS MMAs per k step instead of
+        // NS (NS + 1) / 2; product (sa, sb) lands in accumulator columns [sb * BLOCK_N, +BLOCK_N), summed at read-back)
+#pragma unroll 4
+        for (int i = 0; i < nmma; ++i) {
+          const uint4 m = mtab[i];
+          umma_bf16(tmem_d, ((uint64_t)p.desc_hi << 32) | m.x, ((uint64_t)kDescHi128 << 32) | m.y, m.z, m.w);
         }
         umma_commit(smem_u32(&bk->tmem_full));
         mi += clock64() - q1;
@@ -408,7 +409,7 @@ struct BwdPlan {
   TcStepPlan sp, sp2;
   int G, Fp, Cp, fuse_dx, stack;
   size_t w_bytes;
-  uint32_t chunk_bytes, act_off, dh_off, data_bytes, tmem_cols;
+  uint32_t chunk_bytes, act_off, dh_off, mma_off, data_bytes, tmem_cols;
   size_t smem_bytes;
 };
 
@@ -437,12 +438,13 @@ int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT, BwdP
   FOV_CHECK_ARG(F == 8 || F == 16 || F == 32 || F == 64, "F must be 8/16/32/64");
   pl.G = kRows / (sp.Hp * sp.Wp);
   FOV_CHECK_ARG(pl.G >= 1, "image larger than one MMA tile");
-  FOV_CHECK_ARG(sp.K_total / 16 <= kMaxSteps, "too many k steps");
+  FOV_CHECK_ARG(sp.K_total / 16 <= kMaxSteps && (sp.K_total / 16) * (sp.NS * (sp.NS + 1) / 2) <= kMaxMmas, "too many k steps");
   FOV_CHECK_ARG(kRows * (F / 4) / kWorkers <= kMaxItems, "too many channels");
   pl.chunk_bytes = (uint32_t)sp.NS * (uint32_t)sg.term_bytes;
   pl.act_off = (uint32_t)((pl.w_bytes + 1023) / 1024 * 1024);
   pl.dh_off = pl.act_off + (uint32_t)sg.nch * pl.chunk_bytes;
-  pl.data_bytes = (pl.dh_off + (uint32_t)(kRows * (F + 4) * 4) + 1023u) / 1024u * 1024u;
+  pl.mma_off = pl.dh_off + (uint32_t)(kRows * (F + 4) * 4);
+  pl.data_bytes = (pl.mma_off + (uint32_t)((sp.K_total / 16) * (sp.NS * (sp.NS + 1) / 2) * 16) + 1023u) / 1024u * 1024u;
   pl.smem_bytes = pl.data_bytes + sizeof(BwdBook) + 1024;
   FOV_CHECK_ARG(pl.smem_bytes <= 227 * 1024, "persistent BPTT: weights + operands exceed shared memory");
   pl.stack = (sp.NS > 1 && sp.NS * (pl.Fp + pl.Cp) <= 256) ? 1 : 0;
@@ -539,7 +541,7 @@ int tc_convlstm_seq_bwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, co
                       c->x_t_stride % 4 == 0,
                   "fused input gradient needs a 16-byte aligned dx");
   }
-  p.chunk_bytes = pl.chunk_bytes; p.act_off = pl.act_off; p.dh_off = pl.dh_off; p.data_bytes = pl.data_bytes;
+  p.chunk_bytes = pl.chunk_bytes; p.act_off = pl.act_off; p.dh_off = pl.dh_off; p.mma_off = pl.mma_off; p.data_bytes = pl.data_bytes;
   p.tmem_cols = pl.tmem_cols;
   p.wpk = reinterpret_cast<const uint8_t*>(((uintptr_t)rT.ws + 255) & ~(uintptr_t)255);
   p.gates = io->gates; p.z_t = (long long)HW * 4 * F; p.z_b = p.z_t * c->T;
