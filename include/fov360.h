@@ -250,6 +250,20 @@ int fov_mean_var_xyz(long long rows, const float* frames, float* out, void* stre
 int fov_gauss_resample(long long rows, int mode, const float* muvar, const float* noise,
                        float* out, void* stream);
 
+/* ConvLSTM2D input dropout (keras ConvLSTM2D(dropout=0.3), mycode/others_LSTM_span_whole.py:89,
+ * mycode/convlstm_seq2seq.py:100-126): one mask per gate, shape (B,H,W,Cin), constant over time, applied to the
+ * layer input before the input convolution of that gate.  It is expressed with the unchanged ConvLSTM kernels by
+ * widening the input: x4[b,t,p, g*Cin + c] = x[b,t,p,c] * mask[g,b,p,c] and a block kernel
+ * K4[tap, g*Cin + c, n] = K[tap,c,n] if n is a column of gate g, else 0; the reduce calls fold the gradients back.
+ * masks (4,B,HW,Cin) dense, already scaled by 1/(1-rate); x / dx (B,T,HW,Cin) with strides; x4 / dx4 dense. */
+int fov_dropout_expand(int B, int T, int HW, int Cin, const float* x, long long x_b_stride, long long x_t_stride,
+                       int x_pix_stride, const float* masks, float* x4, void* stream);
+int fov_dropout_reduce(int B, int T, int HW, int Cin, const float* dx4, const float* masks, float* dx,
+                       long long x_b_stride, long long x_t_stride, int x_pix_stride, int accumulate, void* stream);
+int fov_gate_kernel_expand(int taps, int Cin, int F, const float* kernel, float* kernel4, void* stream);
+/* g_kernel[tap,c,n] += g_kernel4[tap, gate(n)*Cin + c, n] */
+int fov_gate_kernel_reduce(int taps, int Cin, int F, const float* g_kernel4, float* g_kernel, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -360,3 +360,101 @@ extern "C" int fov_gauss_resample(long long rows, int mode, const float* muvar, 
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// ConvLSTM2D input dropout as a widened input (include/fov360.h): expand / reduce helpers
+// ---------------------------------------------------------------------------------------------
+namespace {
+// x4[((b*T + t)*HW + p), g*Cin + c] = x[b,t,p,c] * masks[g,b,p,c]
+__global__ void dropout_expand_kernel(long long n, int B, int T, int HW, int Cin, const float* __restrict__ x,
+                                      long long xb, long long xt, int xp, const float* __restrict__ masks,
+                                      float* __restrict__ x4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cin);
+    long long r = i / Cin;
+    const int g = (int)(r & 3); r >>= 2;
+    const int p = (int)(r % HW); r /= HW;
+    const int t = (int)(r % T);
+    const long long b = r / T;
+    const float m = __ldg(&masks[(((long long)g * B + b) * HW + p) * Cin + c]);
+    x4[i] = __ldg(&x[b * xb + (long long)t * xt + (long long)p * xp + c]) * m;
+  }
+}
+// dx[b,t,p,c] (+)= sum_g dx4[(b,t,p), g*Cin + c] * masks[g,b,p,c]
+__global__ void dropout_reduce_kernel(long long n, int B, int T, int HW, int Cin, const float* __restrict__ dx4,
+                                      const float* __restrict__ masks, float* __restrict__ dx, long long xb, long long xt,
+                                      int xp, int accumulate) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cin);
+    long long r = i / Cin;
+    const int p = (int)(r % HW); r /= HW;
+    const int t = (int)(r % T);
+    const long long b = r / T;
+    const float* src = dx4 + (((b * T + t) * HW + p) * 4) * (long long)Cin + c;
+    float acc = 0.0f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      acc = fmaf(__ldg(&src[(long long)g * Cin]), __ldg(&masks[(((long long)g * B + b) * HW + p) * Cin + c]), acc);
+    float* dst = dx + b * xb + (long long)t * xt + (long long)p * xp + c;
+    *dst = accumulate ? *dst + acc : acc;
+  }
+}
+// K4[tap, g*Cin + c, n] = K[tap,c,n] when n / F == g, else 0
+__global__ void gate_kernel_expand_kernel(long long n, int Cin, int F, const float* __restrict__ k, float* __restrict__ k4) {
+  const int N4 = 4 * F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % N4);
+    long long r = i / N4;
+    const int gc = (int)(r % (4 * Cin));
+    const long long tap = r / (4 * Cin);
+    const int g = gc / Cin, c = gc - g * Cin;
+    k4[i] = (col / F == g) ? __ldg(&k[(tap * Cin + c) * N4 + col]) : 0.0f;
+  }
+}
+// gK[tap,c,n] += gK4[tap, (n / F)*Cin + c, n]
+__global__ void gate_kernel_reduce_kernel(long long n, int Cin, int F, const float* __restrict__ g4, float* __restrict__ gk) {
+  const int N4 = 4 * F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % N4);
+    long long r = i / N4;
+    const int c = (int)(r % Cin);
+    const long long tap = r / Cin;
+    gk[i] += __ldg(&g4[((tap * 4 + col / F) * Cin + c) * N4 + col]);
+  }
+}
+}  // namespace
+
+extern "C" int fov_dropout_expand(int B, int T, int HW, int Cin, const float* x, long long x_b_stride,
+                                  long long x_t_stride, int x_pix_stride, const float* masks, float* x4, void* stream) {
+  FOV_CHECK_ARG(B > 0 && T > 0 && HW > 0 && Cin > 0 && x && masks && x4, "bad args");
+  const long long n = (long long)B * T * HW * 4 * Cin;
+  dropout_expand_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, B, T, HW, Cin, x, x_b_stride, x_t_stride,
+                                                                     x_pix_stride, masks, x4);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
+extern "C" int fov_dropout_reduce(int B, int T, int HW, int Cin, const float* dx4, const float* masks, float* dx,
+                                  long long x_b_stride, long long x_t_stride, int x_pix_stride, int accumulate,
+                                  void* stream) {
+  FOV_CHECK_ARG(B > 0 && T > 0 && HW > 0 && Cin > 0 && dx4 && masks && dx, "bad args");
+  const long long n = (long long)B * T * HW * Cin;
+  dropout_reduce_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, B, T, HW, Cin, dx4, masks, dx, x_b_stride,
+                                                                     x_t_stride, x_pix_stride, accumulate);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
+extern "C" int fov_gate_kernel_expand(int taps, int Cin, int F, const float* kernel, float* kernel4, void* stream) {
+  FOV_CHECK_ARG(taps > 0 && Cin > 0 && F > 0 && kernel && kernel4, "bad args");
+  const long long n = (long long)taps * 4 * Cin * 4 * F;
+  gate_kernel_expand_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, Cin, F, kernel, kernel4);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
+extern "C" int fov_gate_kernel_reduce(int taps, int Cin, int F, const float* g_kernel4, float* g_kernel, void* stream) {
+  FOV_CHECK_ARG(taps > 0 && Cin > 0 && F > 0 && g_kernel4 && g_kernel, "bad args");
+  const long long n = (long long)taps * Cin * 4 * F;
+  gate_kernel_reduce_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, Cin, F, g_kernel4, g_kernel);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
