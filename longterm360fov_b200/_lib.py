@@ -113,6 +113,10 @@ SYMBOLS = {
     "fov_rmsprop_step": (_I, [_LL, _P, _P, _P, _F, _F, _F, _F, _P]),
     "fov_mean_var_xyz": (_I, [_LL, _P, _P, _P]),
     "fov_gauss_resample": (_I, [_LL, _I, _P, _P, _P, _P]),
+    "fov_dropout_expand": (_I, [_I, _I, _I, _I, _P, _LL, _LL, _I, _P, _P, _P]),
+    "fov_dropout_reduce": (_I, [_I, _I, _I, _I, _P, _P, _P, _LL, _LL, _I, _I, _P]),
+    "fov_gate_kernel_expand": (_I, [_I, _I, _I, _P, _P, _P]),
+    "fov_gate_kernel_reduce": (_I, [_I, _I, _I, _P, _P, _P]),
 }
 
 _lib = None

@@ -384,6 +384,19 @@ class Model:
     def _sinks(self, *names):
         return tuple(self.grads[n] for n in names)
 
+    def _dropout_masks(self, rate, B, H, W, cins):
+        """keras ConvLSTM2D(dropout=rate) input masks of one stack call: per layer a (4,B,H,W,Cin_l) tensor (one mask per
+        gate, constant over the timesteps of the call), inverted-dropout scaling.  Drawn with a per-model torch
+        generator (``self.dropout_seed``); Keras' own random stream cannot be reproduced."""
+        if not rate:
+            return None
+        if getattr(self, "_drop_gen", None) is None:
+            self._drop_gen = torch.Generator(device=self.device)
+            self._drop_gen.manual_seed(int(getattr(self, "dropout_seed", 0)))
+        keep = 1.0 - float(rate)
+        return [(torch.rand(4, B, H, W, c, device=self.device, generator=self._drop_gen) < keep).float() / keep
+                for c in cins]
+
 
 # --------------------------------------------------------------------------- #
 # M1 / M2: target-only fc-LSTM encoder-decoder
@@ -508,10 +521,11 @@ class OthersLSTMSpanWhole(Model):
          "encoder_dense/kernel", "encoder_dense/bias", "decoder_dense/kernel", "decoder_dense/bias"])
 
     def __init__(self, weights, max_encoder_seq_length=10, max_decoder_seq_length=10,
-                 recurrent_activation="hard_sigmoid", device=None):
+                 recurrent_activation="hard_sigmoid", dropout=0.0, device=None):
         super().__init__(weights, device)
         self.T_enc, self.T_dec = max_encoder_seq_length, max_decoder_seq_length
         self.rec_act = recurrent_activation
+        self.dropout = float(dropout)
         self.latent = weights["encoder/recurrent_kernel"].shape[0]
         self._zero_bias = torch.zeros(6, device=self.device)
         self._zero_bias_grad = torch.zeros(6, device=self.device)
@@ -525,7 +539,12 @@ class OthersLSTMSpanWhole(Model):
                p["oth_convlstm%d/bias" % l]) for l in range(3)]
         sl = [(g["oth_convlstm%d/kernel" % l], g["oth_convlstm%d/recurrent_kernel" % l],
                g["oth_convlstm%d/bias" % l]) for l in range(3)] if training else None
-        cat, _ = ops.convlstm_stack(oth_in, wl, None, sl, rec_act=self.rec_act, training=training)
+        masks = None
+        if training and self.dropout:
+            masks = self._dropout_masks(self.dropout, B, oth_in.shape[2], oth_in.shape[3],
+                                        [oth_in.shape[4]] + [w[1].shape[2] for w in wl[:-1]])
+        cat, _ = ops.convlstm_stack(oth_in, wl, None, sl, rec_act=self.rec_act, training=training,
+                                    dropout_masks=masks)
         flat = cat.view(B, Tall, -1)
         # reconstruction head on all 20 slices + concat-state Dense256 on the 10 future slices: one Function, the
         # two input gradients accumulate into one buffer and the strided future view is read in place
@@ -564,14 +583,12 @@ def others_lstm_span_whole(latent_dim=64, num_user=34, kernel_size=5, max_encode
     decoder_inputs (B,1,6)]`` -> ``[decoder_outputs (B,10,6), decoder_outputs_oth
     (B,20,(num_user-1)*6), encoder_reconstruct_tar (B,10,6)]``
     (mycode/others_LSTM_span_whole.py:348-349)."""
-    if dropout:
-        raise NotImplementedError("ConvLSTM input dropout is not built yet; parity runs use dropout=0")
     if weights is None:
         weights = _init_weights("init_others_lstm_span_whole", seed=seed, num_user=num_user,
                                 kernel_size=kernel_size, latent_dim=latent_dim, oth_filters=oth_filters,
                                 flat_dense=flat_dense)
     return OthersLSTMSpanWhole(weights, max_encoder_seq_length, max_decoder_seq_length,
-                               recurrent_activation, device)
+                               recurrent_activation, dropout, device)
 
 
 # --------------------------------------------------------------------------- #
@@ -581,7 +598,7 @@ def others_lstm_span_whole(latent_dim=64, num_user=34, kernel_size=5, max_encode
 
 class ConvLSTMSeq2Seq(Model):
     def __init__(self, weights, head_kind="conv2d", max_decoder_seq_length=10, dilation_rate=1,
-                 recurrent_activation="hard_sigmoid", device=None):
+                 recurrent_activation="hard_sigmoid", dropout=0.0, device=None):
         order = ["%s_convlstm%d/%s" % (s, l, n) for s in ("enc", "dec") for l in range(3)
                  for n in ("kernel", "recurrent_kernel", "bias")]
         if head_kind in ("conv2d", "conv1d"):
@@ -594,6 +611,7 @@ class ConvLSTMSeq2Seq(Model):
         self.T_dec = max_decoder_seq_length
         self.dilation = (dilation_rate, dilation_rate)
         self.rec_act = recurrent_activation
+        self.dropout = float(dropout)
 
     def _stack(self, side, x, states, training):
         p, g = self.params, self.grads
@@ -601,7 +619,11 @@ class ConvLSTMSeq2Seq(Model):
                p["%s_convlstm%d/bias" % (side, l)]) for l in range(3)]
         sl = [(g["%s_convlstm%d/kernel" % (side, l)], g["%s_convlstm%d/recurrent_kernel" % (side, l)],
                g["%s_convlstm%d/bias" % (side, l)]) for l in range(3)] if training else None
-        return ops.convlstm_stack(x, wl, states, sl, self.dilation, self.rec_act, training)
+        masks = None
+        if training and self.dropout:       # a fresh set of masks per layer call, as Keras draws them
+            masks = self._dropout_masks(self.dropout, x.shape[0], x.shape[2], x.shape[3],
+                                        [x.shape[4]] + [w[1].shape[2] for w in wl[:-1]])
+        return ops.convlstm_stack(x, wl, states, sl, self.dilation, self.rec_act, training, dropout_masks=masks)
 
     def _forward(self, inputs, training):
         enc_in, dec_in = inputs
@@ -645,8 +667,6 @@ def convlstm_seq2seq(latent_dim=16, kernel_size=5, dilation_rate=1, use_one_hot=
     (B,1,36,18,fps)]`` -> ``(B,10,36,18,fps)``, heads Conv2D 56->512->1024->fps + channel softmax.
     trajectory form: ``(B,10,1,fps,3)`` images with the Conv1D(k=7) head, or, with
     ``input_mean_var`` and ``predict_mean_var``, ``(B,10,1,1,6)`` images with a Dense(6) head."""
-    if dropout:
-        raise NotImplementedError("ConvLSTM input dropout is not built yet; parity runs use dropout=0")
     filters = (latent_dim * 2, latent_dim, latent_dim // 2)
     if use_one_hot:
         kind, in_ch, hd = "conv2d", fps, (head[0], head[1], fps)
@@ -658,4 +678,4 @@ def convlstm_seq2seq(latent_dim=16, kernel_size=5, dilation_rate=1, use_one_hot=
         flat_dim = sum(filters) * (1 if input_mean_var else fps)
         weights = _init_weights("init_convlstm_seq2seq", seed=seed, in_ch=in_ch, filters=filters,
                                 kernel_size=kernel_size, head=hd, head_kind=kind, flat_dim=flat_dim)
-    return ConvLSTMSeq2Seq(weights, kind, max_decoder_seq_length, dilation_rate, recurrent_activation, device)
+    return ConvLSTMSeq2Seq(weights, kind, max_decoder_seq_length, dilation_rate, recurrent_activation, dropout, device)

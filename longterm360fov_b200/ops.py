@@ -394,12 +394,30 @@ class ConvLSTMStackFn(torch.autograd.Function):
         cin, off = Cin0, 0
         cur, cur_b, cur_t, cur_pix = x, T * HW * Cin0, HW * Cin0, Cin0
         cur_ptr = ptr(x)
+        masks = opts.get("dropout_masks") or [None] * L
+        drop = []
         for l in range(L):
             K, R, b = weights[l]
             kh, kw = K.shape[0], K.shape[1]
             F = Fs[l]
-            cfg = _lib.ConvLstmCfg(B, T, H, W, cin, F, kh, kw, dil[0], dil[1], rec,
-                                   cur_b, cur_t, cur_pix, T * HW * Fsum, HW * Fsum, Fsum, int(training), math)
+            mask = masks[l] if training else None
+            x4 = K4 = None
+            if mask is not None:
+                # keras ConvLSTM2D(dropout=p): one input mask per gate, constant over time == a 4x wider input
+                # [x*m_i | x*m_f | x*m_c | x*m_o] with a block kernel (include/fov360.h fov_dropout_expand)
+                mask = _f32c(mask)
+                assert tuple(mask.shape) == (4, B, H, W, cin), (mask.shape, (4, B, H, W, cin))
+                x4 = torch.empty(B, T, H, W, 4 * cin, device=dev)
+                K4 = torch.empty(kh, kw, 4 * cin, 4 * F, device=dev)
+                _lib.check(lib.fov_dropout_expand(B, T, HW, cin, cur_ptr, cur_b, cur_t, cur_pix, ptr(mask), ptr(x4), st),
+                           "fov_dropout_expand")
+                _lib.check(lib.fov_gate_kernel_expand(kh * kw, cin, F, ptr(K), ptr(K4), st), "fov_gate_kernel_expand")
+                lx_ptr, lx_b, lx_t, lx_pix, lcin, lK = ptr(x4), T * HW * 4 * cin, HW * 4 * cin, 4 * cin, 4 * cin, K4
+            else:
+                lx_ptr, lx_b, lx_t, lx_pix, lcin, lK = cur_ptr, cur_b, cur_t, cur_pix, cin, K
+            drop.append((mask, x4, K4))
+            cfg = _lib.ConvLstmCfg(B, T, H, W, lcin, F, kh, kw, dil[0], dil[1], rec,
+                                   lx_b, lx_t, lx_pix, T * HW * Fsum, HW * Fsum, Fsum, int(training), math)
             # saved gates exist only for BPTT; the fused tensor-core step never materialises them otherwise
             fws_bytes = lib.fov_convlstm_fwd_ws_bytes(C.byref(cfg))     # > 0: the fused tensor-core step runs
             gates = torch.empty((B, T, H, W, 4 * F) if (training or fws_bytes == 0) else (1,), device=dev)
@@ -409,16 +427,16 @@ class ConvLSTMStackFn(torch.autograd.Function):
             cT = torch.empty(B, H, W, F, device=dev)
             h0, c0 = states[l]
             hptr = cat.data_ptr() + 4 * off
-            io = _lib.ConvLstmIO(cur_ptr, ptr(K), ptr(R), ptr(b), ptr(h0), ptr(c0), None, hptr,
+            io = _lib.ConvLstmIO(lx_ptr, ptr(lK), ptr(R), ptr(b), ptr(h0), ptr(c0), None, hptr,
                                  ptr(gates), ptr(cseq), ptr(hT), ptr(cT), ptr(fws))
             _lib.check(lib.fov_convlstm_fwd(C.byref(cfg), C.byref(io), st), "fov_convlstm_fwd")
             outs += [hT, cT]
             saved.append((gates, cseq))
-            cfgs.append((cfg, cur_ptr, hptr, off, F))
+            cfgs.append((cfg, cur_ptr, hptr, off, F, (cur_b, cur_t, cur_pix, cin)))
             cur_ptr, cur_b, cur_t, cur_pix, cin = hptr, T * HW * Fsum, HW * Fsum, Fsum, F
             off += F
         if training:
-            ctx.sinks, ctx.cfgs, ctx.L = sinks, cfgs, L
+            ctx.sinks, ctx.cfgs, ctx.L, ctx.drop = sinks, cfgs, L, drop
             ctx.x_needs_grad = ctx.needs_input_grad[2]
             ctx.state_needs_grad = [ctx.needs_input_grad[3 + 3 * L + 2 * l] for l in range(L)]
             tensors = [x, cat]
@@ -442,8 +460,9 @@ class ConvLSTMStackFn(torch.autograd.Function):
         dx0 = torch.empty_like(x) if ctx.x_needs_grad else None
         dstate_out = [None] * (2 * L)
         for l in reversed(range(L)):
-            cfg, _xptr, _hptr, off, F = cfgs[l]
+            cfg, _xptr, _hptr, off, F, xgeo = cfgs[l]
             K, R, b, h0, c0, gates, cseq = per[l]
+            mask, x4, K4 = ctx.drop[l]
             xptr = x.data_ptr() if l == 0 else cat.data_ptr() + 4 * cfgs[l - 1][3]
             hptr = cat.data_ptr() + 4 * off
             dhT, dcT = _f32c(dstates[2 * l]), _f32c(dstates[2 * l + 1])
@@ -458,18 +477,36 @@ class ConvLSTMStackFn(torch.autograd.Function):
             else:
                 dxp, acc = dcat.data_ptr() + 4 * cfgs[l - 1][3], 1
             gk, gr_, gb = ctx.sinks[l]
-            io = _lib.ConvLstmIO(xptr, ptr(K), ptr(R), ptr(b), ptr(h0), ptr(c0), None, hptr,
-                                 ptr(gates), ptr(cseq), None, None, None)
-            g = _lib.ConvLstmGrads(dcat.data_ptr() + 4 * off, ptr(dhT), ptr(dcT), dxp, ptr(dh0), ptr(dc0),
-                                   ptr(gk), ptr(gr_), ptr(gb), ptr(ws), acc)
-            _lib.check(lib.fov_convlstm_bwd(C.byref(cfg), C.byref(io), C.byref(g), st), "fov_convlstm_bwd")
+            if mask is None:
+                io = _lib.ConvLstmIO(xptr, ptr(K), ptr(R), ptr(b), ptr(h0), ptr(c0), None, hptr,
+                                     ptr(gates), ptr(cseq), None, None, None)
+                g = _lib.ConvLstmGrads(dcat.data_ptr() + 4 * off, ptr(dhT), ptr(dcT), dxp, ptr(dh0), ptr(dc0),
+                                       ptr(gk), ptr(gr_), ptr(gb), ptr(ws), acc)
+                _lib.check(lib.fov_convlstm_bwd(C.byref(cfg), C.byref(io), C.byref(g), st), "fov_convlstm_bwd")
+            else:
+                # widened-input form: gradients w.r.t. x4 / K4, folded back through the masks / the gate blocks
+                xb_, xt_, xpix_, cin_ = xgeo
+                gk4 = torch.zeros_like(K4)
+                dx4 = torch.empty_like(x4) if dxp else None
+                io = _lib.ConvLstmIO(ptr(x4), ptr(K4), ptr(R), ptr(b), ptr(h0), ptr(c0), None, hptr,
+                                     ptr(gates), ptr(cseq), None, None, None)
+                g = _lib.ConvLstmGrads(dcat.data_ptr() + 4 * off, ptr(dhT), ptr(dcT), ptr(dx4), ptr(dh0), ptr(dc0),
+                                       ptr(gk4), ptr(gr_), ptr(gb), ptr(ws), 0)
+                _lib.check(lib.fov_convlstm_bwd(C.byref(cfg), C.byref(io), C.byref(g), st), "fov_convlstm_bwd")
+                _lib.check(lib.fov_gate_kernel_reduce(K.shape[0] * K.shape[1], cin_, F, ptr(gk4), ptr(gk), st),
+                           "fov_gate_kernel_reduce")
+                if dxp:
+                    _lib.check(lib.fov_dropout_reduce(cfg.B, cfg.T, cfg.H * cfg.W, cin_, ptr(dx4), ptr(mask), dxp,
+                                                      xb_, xt_, xpix_, acc, st), "fov_dropout_reduce")
             dstate_out[2 * l], dstate_out[2 * l + 1] = dh0, dc0
         return (None, None, dx0) + (None,) * (3 * L) + tuple(dstate_out)
 
 
 def convlstm_stack(x, weights, states=None, sinks=None, dilation=(1, 1), rec_act="hard_sigmoid",
-                   training=False):
-    """weights: [(K,R,b)]*L ; states: [(h0,c0)]*L or None.  Returns (concat_seq, [(hT,cT)]*L)."""
+                   training=False, dropout_masks=None):
+    """weights: [(K,R,b)]*L ; states: [(h0,c0)]*L or None; dropout_masks: per layer None or a
+    (4,B,H,W,Cin_l) tensor of keep-masks already scaled by 1/(1-rate) (training only).
+    Returns (concat_seq, [(hT,cT)]*L)."""
     L = len(weights)
     flat = []
     for w in weights:
@@ -477,7 +514,7 @@ def convlstm_stack(x, weights, states=None, sinks=None, dilation=(1, 1), rec_act
     for l in range(L):
         flat += list(states[l]) if states is not None else [None, None]
     out = ConvLSTMStackFn.apply({"layers": L, "dilation": dilation, "rec_act": rec_act,
-                                 "training": training}, sinks, x, *flat)
+                                 "training": training, "dropout_masks": dropout_masks}, sinks, x, *flat)
     return out[0], [(out[1 + 2 * l], out[2 + 2 * l]) for l in range(L)]
 
 

@@ -118,14 +118,14 @@ def convlstm2d(x, kernel, rk, bias, h0=None, c0=None, dilation=(1, 1), ra="hard_
     return torch.stack(seq, 1), h, c
 
 
-def convlstm_stack(w, x, prefix, h0c0=None, dilation=(1, 1), ra="hard_sigmoid", n_layers=3):
+def convlstm_stack(w, x, prefix, h0c0=None, dilation=(1, 1), ra="hard_sigmoid", n_layers=3, dropout_masks=None):
     seqs, states = [], []
     cur = x
     for l in range(n_layers):
         p = "%s%d" % (prefix, l)
         h0, c0 = (None, None) if h0c0 is None else h0c0[l]
         cur, h, c = convlstm2d(cur, w[p + "/kernel"], w[p + "/recurrent_kernel"], w[p + "/bias"],
-                               h0, c0, dilation, ra)
+                               h0, c0, dilation, ra, None if dropout_masks is None else dropout_masks[l])
         seqs.append(cur)
         states.append((h, c))
     return torch.cat(seqs, -1), states

@@ -295,6 +295,63 @@ def test_persistent_convlstm_kernels_match_per_timestep_launches(B, T):
         assert n1 < n0, "the persistent path must need fewer launches (%d vs %d)" % (n1, n0)
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_convlstm_input_dropout_masks(mode):
+    """keras ConvLSTM2D(dropout=p) semantics (one input mask per gate, constant over time) with explicit masks against
+    the oracle, forward and gradients, on the stacked M3 layers (mycode/others_LSTM_span_whole.py:88-100)."""
+    fov = _cuda()
+    from longterm360fov_b200 import ops
+    ops.set_math(mode)
+    rng = np.random.default_rng(77)
+    B, T, H, W, Cin, Fs = 4, 5, 1, 33, 6, (32, 16, 8)
+    x = rng.normal(size=(B, T, H, W, Cin)).astype(np.float32)
+    ws, masks, cin = [], [], Cin
+    for f in Fs:
+        ws.append(((rng.normal(size=(1, 5, cin, 4 * f)) * 0.3).astype(np.float32),
+                   (rng.normal(size=(1, 5, f, 4 * f)) * 0.3).astype(np.float32),
+                   (rng.normal(size=4 * f) * 0.1).astype(np.float32)))
+        masks.append(((rng.uniform(size=(4, B, H, W, cin)) < 0.7) / 0.7).astype(np.float32))
+        cin = f
+    gcat = rng.normal(size=(B, T, H, W, sum(Fs))).astype(np.float32)
+    xt = torch.tensor(x, device="cuda", requires_grad=True)
+    wt = [tuple(torch.tensor(a, device="cuda", requires_grad=True) for a in w) for w in ws]
+    sinks = [tuple(torch.zeros_like(a) for a in w) for w in wt]
+    cat, _ = ops.convlstm_stack(xt, wt, None, sinks, (1, 1), "hard_sigmoid", True,
+                                dropout_masks=[torch.tensor(m, device="cuda") for m in masks])
+    (cat * torch.tensor(gcat, device="cuda")).sum().backward()
+
+    d64 = lambda a, rg=True: torch.tensor(a, dtype=torch.float64, requires_grad=rg)
+    x64, w64 = d64(x), {}
+    for l, w in enumerate(ws):
+        w64["L%d/kernel" % l], w64["L%d/recurrent_kernel" % l], w64["L%d/bias" % l] = (d64(a) for a in w)
+    catr, _ = kt.convlstm_stack(w64, x64, "L", None, (1, 1), dropout_masks=[d64(m, False) for m in masks])
+    (catr * d64(gcat, False)).sum().backward()
+    assert np.abs(cat.detach().cpu().numpy() - catr.detach().numpy()).max() < TIGHT[mode][0]
+    _grad_close(xt.grad.cpu().numpy(), x64.grad.numpy(), "dx")
+    for l in range(3):
+        for j, n in enumerate(("kernel", "recurrent_kernel", "bias")):
+            _grad_close(sinks[l][j].cpu().numpy(), w64["L%d/%s" % (l, n)].grad.numpy(), "L%d/%s" % (l, n))
+    # without masks at inference: identical to the no-dropout forward
+    with torch.no_grad():
+        a, _ = ops.convlstm_stack(xt, wt, None, None, (1, 1), "hard_sigmoid", False,
+                                  dropout_masks=[torch.tensor(m, device="cuda") for m in masks])
+        b, _ = ops.convlstm_stack(xt, wt, None, None, (1, 1), "hard_sigmoid", False)
+    assert torch.equal(a, b)
+
+
+def test_m3_trains_with_dropout():
+    """others_lstm_span_whole(dropout=0.3) (the reference's setting): training steps run, the loss stays finite and
+    falls, inference is deterministic (no dropout)."""
+    fov = _cuda()
+    from longterm360fov_b200 import data
+    m = fov.others_lstm_span_whole(num_user=8, dropout=0.3, seed=3).compile("Adam", ["mean_squared_error"] * 3, [1, 1, 1])
+    x, y = data.make_m3_batch(16, 8, seed=1)
+    losses = [m.train_on_batch(x, y) for _ in range(12)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    p1, p2 = m.predict_on_batch(x), m.predict_on_batch(x)
+    assert all(np.array_equal(a, b) for a, b in zip(p1, p2))
+
+
 # ------------------------------------------------------------------ losses / softmax / optimisers
 
 def test_losses_and_softmax():
