@@ -714,7 +714,7 @@ int make_plan(const TcConv& c, Plan* pl) {
     int st = (kUsable - book - region_bytes) / pl->b_stage_bytes;
     // dense layers (1x1 kernel, wide Cin) are bound by the activation staging, which is repeated per n tile: prefer
     // ONE n tile with a two-slot weight ring over two n tiles with three slots
-    const bool dense_like = c.nseg == 1 && c.seg[0].kh * c.seg[0].kw == 1 && c.seg[0].Cin >= 256;
+    const bool dense_like = c.nseg == 1 && c.seg[0].kh * c.seg[0].kw == 1 && c.seg[0].Cin >= 128;
     const int want = pl->KB < 3 ? pl->KB : (dense_like ? 2 : 3);
     if (st >= want || max_n <= 32 || c.epi == TC_EPI_LSTM) {
       if (st > kMaxBStages) st = kMaxBStages;
