@@ -35,6 +35,7 @@ constexpr int kProd = 256;                 // producer threads (warps 0-7)
 constexpr int kTabWarp = 8, kMmaWarp = 9;  // warp 8 owns the TMEM allocation
 constexpr int kThr = 320;
 constexpr int kStages = 2;
+constexpr int kPfTiles = 3;                // L2 prefetch distance, in tiles of this CTA
 constexpr int kMaxFrameRows = 192;         // 128 + halo
 constexpr int kAGroup = kTile * 128;       // bytes of one 64-channel group of the dZ tile (per term)
 
@@ -159,6 +160,33 @@ __global__ void __launch_bounds__(kThr, 2) tc_wgrad_rows_kernel(const WrParams p
         if (zr >= 0 && zr < kTile) tb.offz[zr] = oz;
         tb.offs[0][r] = o0;
         tb.offs[1][r] = o1;
+      } else if (tid >= 128 && tid - 128 < p.frame_rows && i + kPfTiles < my_tiles) {
+        // otherwise idle threads: L2 prefetch of the rows of the tile kPfTiles ahead (the producers keep one tile of
+        // loads in flight in registers; with the rows already in L2 that hides the HBM latency)
+        const int r = tid - 128;
+        const long long L = (long long)(blockIdx.x + (long long)(i + kPfTiles) * gridDim.x) * kTile + p.frame_min + r;
+        if (L >= 0 && L < p.total_pos) {
+          const unsigned Lu = (unsigned)L;
+          const unsigned n = Lu / (unsigned)p.HpWp, rem = Lu - n * (unsigned)p.HpWp;
+          const unsigned yp = rem / (unsigned)p.Wp, xp = rem - yp * (unsigned)p.Wp;
+          const int y = (int)yp - p.PLh, x = (int)xp - p.PLw;
+          if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) {
+            const int b = (int)(n / (unsigned)p.T), t = (int)n - b * p.T, pix = y * p.W + x;
+            const int zr = r + p.frame_min;
+            if (zr >= 0 && zr < kTile) {
+              const float* z = p.dz + (long long)b * p.z_b + (long long)t * p.z_t + (long long)pix * p.Cout;
+              for (int l = 0; l < p.Cout; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(z + l));
+            }
+            for (int s = 0; s < p.nseg; ++s) {
+              const WrSeg& sg = p.seg[s];
+              const int ts = t + sg.t_shift;
+              if (ts >= 0) {
+                const float* xr = sg.x + (long long)b * sg.b_stride + (long long)ts * sg.t_stride + (long long)pix * sg.pix_stride;
+                for (int l = 0; l < sg.Cin; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + l));
+              }
+            }
+          }
+        }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory");
       mbar_wait(smem_u32(&bk->empty[stage]), ph ^ 1u);

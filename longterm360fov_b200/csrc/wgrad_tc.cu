@@ -30,6 +30,7 @@ constexpr int kTabWarp = 16, kMmaWarp = 17;
 constexpr int kThr = 576;            // + table warp (16) + MMA warp (17)
 constexpr int NA = 4, NBMAX = 4;     // float4 loads per thread per pixel block: x rows / dy rows
 constexpr int kStagesMax = 3;
+constexpr int kPfDist = 4;           // L2 prefetch distance of the 1x1-layer operand rows, in 64-pixel blocks
 constexpr int RS = 36;
 
 struct WgParams {
@@ -253,6 +254,28 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bk->tabrdy[stage]));
+      // L2 prefetch of the operand rows kPfDist blocks ahead (1x1 layers: one contiguous row segment per pixel).  The
+      // producers keep only ONE block of loads in flight in registers; with the rows already in L2 that is enough.
+      if (p.taps == 1 && i + kPfDist < nblk) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const long long m = (long long)(blk0 + i + kPfDist) * WG_PIX + lane + h * 32;
+          if (m < p.M) {
+            const int n = (int)(m / p.HW), pix = (int)(m - (long long)n * p.HW);
+            const int nno = n / p.T_inner, nni = n - nno * p.T_inner;
+            const float* xr = p.x + (long long)nno * p.x_outer + (long long)nni * p.x_inner + (long long)pix * p.x_pix_stride +
+                              k_tile * WG_M;
+            const float* dr_ = p.dy + (long long)nno * p.dy_outer + (long long)nni * p.dy_inner +
+                               (long long)pix * p.dy_pix_stride + n0;
+            const int xa = p.Cin - k_tile * WG_M, da = p.Cout - n0;
+#pragma unroll
+            for (int l = 0; l < WG_M / 32; ++l)
+              if (l * 32 < xa) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + l * 32));
+            for (int l = 0; l * 32 < p.BLOCK_N; ++l)
+              if (l * 32 < da) asm volatile("prefetch.global.L2 [%0];" ::"l"(dr_ + l * 32));
+          }
+        }
+      }
     }
   } else {
     // ---------------- MMA issuer ----------------

@@ -507,6 +507,43 @@ int main(int argc, char** argv) {
     printf(g_fail ? "SELFTEST FAILED (%d)\n" : "SELFTEST OK (%d failures)\n", g_fail);
     return g_fail ? 1 : 0;
   }
+  if (argc > 1 && !strcmp(argv[1], "dense")) {    // phase timelines + timings of the wide dense layers of config 2 (B = 4096)
+    const int math = 2;
+    const int shapes[2][3] = {{81920, 1848, 198}, {40960, 1848, 256}};
+    for (int si = 0; si < 2; ++si) {
+      const int rows = shapes[si][0], Cin = shapes[si][1], Cout = shapes[si][2];
+      fov_conv_cfg c = mkcfg(rows, 1, 1, Cin, Cout, 1, 1, 1, 1, FOV_ACT_LINEAR, 0.f);
+      float *x = dev_rand((size_t)rows * Cin, 1.f), *w = dev_rand((size_t)Cin * Cout, 0.05f), *b = dev_rand(Cout, 0.1f);
+      float *y = dev_zero((size_t)rows * Cout), *dx = dev_zero((size_t)rows * Cin), *gw = dev_zero((size_t)Cin * Cout), *gb = dev_zero(Cout);
+      void *ws, *ws2;
+      CK(cudaMalloc(&ws, fov_conv_tc_ws_bytes(&c, math, 0) + 256));
+      CK(cudaMalloc(&ws2, fov_conv_tc_ws_bytes(&c, math, 1) + 256));
+      printf("[dense] rows=%d %d -> %d\n", rows, Cin, Cout);
+      Timer tm;
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass) tm.start();
+        for (int i = 0; i < (pass ? 5 : 1); ++i) FK(fov_conv2d_fwd_tc(&c, x, w, b, y, ws, math, nullptr));
+        if (pass) printf("  fwd      %.3f ms\n", tm.stop_ms() / 5);
+        if (pass) tm.start();
+        for (int i = 0; i < (pass ? 5 : 1); ++i) FK(fov_conv2d_bwd_data_tc(&c, y, w, dx, ws2, math, nullptr));
+        if (pass) printf("  bwd-data %.3f ms\n", tm.stop_ms() / 5);
+        if (pass) tm.start();
+        for (int i = 0; i < (pass ? 5 : 1); ++i) FK(fov_conv2d_bwd_weight_tc(&c, x, y, gw, gb, math, nullptr));
+        if (pass) printf("  wgrad    %.3f ms\n", tm.stop_ms() / 5);
+      }
+      CK(cudaDeviceSynchronize());
+      fov_debug_timeline_enable(1);
+      FK(fov_conv2d_fwd_tc(&c, x, w, b, y, ws, math, nullptr));
+      CK(cudaDeviceSynchronize());
+      print_timeline("dense fwd");
+      FK(fov_conv2d_bwd_data_tc(&c, y, w, dx, ws2, math, nullptr));
+      CK(cudaDeviceSynchronize());
+      print_timeline("dense bwd-data");
+      fov_debug_timeline_enable(0);
+      cudaFree(x); cudaFree(w); cudaFree(b); cudaFree(y); cudaFree(dx); cudaFree(gw); cudaFree(gb); cudaFree(ws); cudaFree(ws2);
+    }
+    return 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "bw")) {       // one mid-size stacked-layer backward (for compute-sanitizer runs)
     const int B = argc > 2 ? atoi(argv[2]) : 300;
     if (argc > 3) fov_debug_seq_bwd_enable(atoi(argv[3]));
