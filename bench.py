@@ -251,6 +251,23 @@ def other_workloads(dev, peaks, compute):
         "fp32_tflops": flop / (ms * 1e-3) / 1e12, "hbm_gbs": byts / (ms * 1e-3) / 1e9,
         "note": "latency/FMA-bound persistent recurrence (fp32 CUDA cores, weights resident in shared memory)"}
 
+    # ---- config 2 at the reference's own batch size (32): launch-bound, eager vs CUDA-graph replay ----
+    Bs = 32
+    px, py = data.make_m3_batch(Bs, NUM_USER, seed=11)
+    small = {}
+    for graphed in (False, True):
+        ms3 = fov.others_lstm_span_whole(num_user=NUM_USER, seed=1, device=dev)
+        ms3.compile(optimizer="Adam", loss=["mean_squared_error"] * 3, loss_weights=[1, 1, 1])
+        ms3.set_compute(compute)
+        ms3.enable_cuda_graphs(graphed)
+        xs, ys = ms3._to_dev(px), ms3._to_dev(py)
+        ms = _time_cuda(lambda: ms3.train_step_device(xs, ys), reps=30, warm=5)
+        small["cuda_graph" if graphed else "eager"] = {"value": Bs / (ms * 1e-3), "ms_per_step": ms}
+        del ms3
+    res["others_lstm_span_whole_train_batch32"] = dict(small, batch=Bs, unit="sequences/s",
+                                                       note="the reference's batch size; the step is launch bound, "
+                                                            "model.enable_cuda_graphs() replays forward + BPTT from one graph")
+
     # ---- config 1 model (FoV_seq2seq, teacher forcing) training on the GPU ----
     Bt = 8192
     m1 = fov.fov_seq2seq(seed=4, device=dev).compile("Adam", "mean_squared_error")

@@ -89,6 +89,46 @@ class History:
         self.epoch = []
 
 
+class _GraphedStep:
+    """One training step (zero grads + forward + losses + BPTT) of fixed input shapes captured in a CUDA graph: a replay
+    costs one launch from the host instead of ~50 kernel launches plus the autograd bookkeeping, which is what bounds
+    the step at the reference's batch sizes (32-64).  The optimiser step stays outside (its step count and learning
+    rate are host-side arguments) and so does the gradient allreduce."""
+
+    def __init__(self, model, xs, ys):
+        self.model = model
+        self.sx = [torch.empty_like(t) for t in xs]
+        self.sy = [torch.empty_like(t) for t in ys]
+        self._load(xs, ys)
+        side = torch.cuda.Stream(device=model.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):            # warm-up off the capture: kernel attributes, allocator pool
+            for _ in range(2):
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd()
+
+    def _load(self, xs, ys):
+        for dst, src in zip(self.sx + self.sy, list(xs) + list(ys)):
+            dst.copy_(src, non_blocking=True)
+
+    def _fwd_bwd(self):
+        m = self.model
+        m.gflat.zero_()
+        ops.set_math(m.compute)
+        outs = m._forward(self.sx, True)
+        total = m._loss(outs, self.sy)
+        total.backward()
+        return total.detach()
+
+    def run(self, xs, ys):
+        self._load(xs, ys)
+        self.graph.replay()
+        return self.loss
+
+
 class Model:
     """Common Keras-shaped surface; subclasses provide ``_forward`` and ``weight_order``."""
 
@@ -128,6 +168,17 @@ class Model:
         # arithmetic of the conv / dense / ConvLSTM kernels (ops.set_math): tensor cores with 2 bf16
         # terms per operand by default (fp32-grade results); "fp32" selects the CUDA-core kernels
         self.compute = os.environ.get("FOV_COMPUTE", "bf16x2")
+        self._graphs, self._use_graphs = {}, False
+
+    def enable_cuda_graphs(self, on=True):
+        """Replay the training step from a CUDA graph (captured per input-shape set on first use).  Worth it when the
+        step is launch bound (small batches); not available with ConvLSTM input dropout (fresh masks every step)."""
+        if on and getattr(self, "dropout", 0.0):
+            raise NotImplementedError("CUDA-graph replay needs a mask-free step (dropout=0)")
+        self._use_graphs = bool(on)
+        if not on:
+            self._graphs = {}
+        return self
 
     def set_compute(self, mode):
         """'fp32' | 'bf16' | 'bf16x2' | 'bf16x3' (see _lib.MATH)."""
@@ -231,19 +282,28 @@ class Model:
         (no host sync).  DP: gradients are sum-allreduced and scaled by 1/world.
         ``targets_ready``: optional CUDA event after which ``ys`` may be read (their H2D copy
         runs on a side stream while the forward pass computes)."""
-        self.gflat.zero_()
-        ops.set_math(self.compute)
-        outs = self._forward(xs, True)
-        if targets_ready is not None:
-            torch.cuda.current_stream().wait_event(targets_ready)
-        total = self._loss(outs, ys)
-        total.backward()
+        if self._use_graphs:
+            if targets_ready is not None:
+                torch.cuda.current_stream().wait_event(targets_ready)
+            key = (self.compute,) + tuple(tuple(t.shape) for t in list(xs) + list(ys))
+            step = self._graphs.get(key)
+            if step is None:
+                step = self._graphs[key] = _GraphedStep(self, xs, ys)
+            total = step.run(xs, ys)
+        else:
+            self.gflat.zero_()
+            ops.set_math(self.compute)
+            outs = self._forward(xs, True)
+            if targets_ready is not None:
+                torch.cuda.current_stream().wait_event(targets_ready)
+            total = self._loss(outs, ys)
+            total.backward()
         scale = 1.0
         if self.world_size > 1:
             scale = parallel.allreduce_gradients(self.gflat, self.process_group)
         with torch.no_grad():
             self.optimizer.step(self.flat, self.gflat, scale)
-        return total.detach()
+        return total.detach() if not self._use_graphs else total.clone()
 
     def train_on_batch(self, x, y):
         """keras Model.train_on_batch.  The inputs are copied on the compute stream; the targets - only needed by the

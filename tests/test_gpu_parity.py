@@ -352,6 +352,31 @@ def test_m3_trains_with_dropout():
     assert all(np.array_equal(a, b) for a, b in zip(p1, p2))
 
 
+@pytest.mark.parametrize("which", ["m3", "m1"])
+def test_cuda_graph_train_step_matches_eager(which):
+    """enable_cuda_graphs(): the captured forward + BPTT replays to the same losses and weights as the eager step."""
+    fov = _cuda()
+    from longterm360fov_b200 import data
+    def build():
+        if which == "m3":
+            m = fov.others_lstm_span_whole(num_user=8, seed=5).compile("Adam", ["mean_squared_error"] * 3, [1, 1, 1])
+            x, y = data.make_m3_batch(12, 8, seed=2)
+        else:
+            m = fov.fov_seq2seq(seed=5).compile("Adam", "mean_squared_error")
+            e, d, t, _ = data.make_m1_batch(12, seed=2)
+            x, y = [e, d], [t]
+        return m, x, y
+    m0, x, y = build()
+    l0 = [m0.train_on_batch(x, y) for _ in range(4)]
+    m1, _, _ = build()
+    m1.enable_cuda_graphs()
+    l1 = [m1.train_on_batch(x, y) for _ in range(4)]
+    np.testing.assert_allclose(l1, l0, rtol=1e-5, atol=1e-7)
+    for a, b in zip(m1.get_weights(), m0.get_weights()):
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-6)
+    assert len(m1._graphs) == 1
+
+
 # ------------------------------------------------------------------ losses / softmax / optimisers
 
 def test_losses_and_softmax():
