@@ -23,12 +23,11 @@ namespace {
 using namespace tc;
 
 constexpr int WG_M = 128;            // k rows per CTA (MMA M)
-constexpr int WG_PIX = 64;           // pixels per pipeline stage (4 MMA K-steps of 16)
-constexpr int WG_GRP = WG_PIX * 128; // bytes of one 64-wide MN group (64 pixel rows x 128 B)
+constexpr int WG_PIX_MAX = 64;       // pixels per pipeline stage: 64 (n tiles <= 128 wide) or 32 (256-wide n tiles)
 constexpr int kProd = 512;           // producer threads (warps 0-15)
 constexpr int kTabWarp = 16, kMmaWarp = 17;
 constexpr int kThr = 576;            // + table warp (16) + MMA warp (17)
-constexpr int NA = 4, NBMAX = 4;     // float4 loads per thread per pixel block: x rows / dy rows
+constexpr int NBMAX = 4;             // dy float4 loads per thread per pixel block (x rows: PIX / 16)
 constexpr int kStagesMax = 3;
 constexpr int kPfDist = 4;           // L2 prefetch distance of the 1x1-layer operand rows, in 64-pixel blocks
 constexpr int RS = 36;
@@ -43,9 +42,9 @@ struct WgParams {
 };
 
 struct RowTab {
-  const float* xp[WG_PIX];    // address of the row's own pixel in x (channel 0)
-  const float* dyp[WG_PIX];   // address of the row's pixel in dy (channel 0)
-  int pyx[WG_PIX];            // (y << 16) | x; y = 0x4000 marks a row past the end
+  const float* xp[WG_PIX_MAX];    // address of the row's own pixel in x (channel 0)
+  const float* dyp[WG_PIX_MAX];   // address of the row's pixel in dy (channel 0)
+  int pyx[WG_PIX_MAX];            // (y << 16) | x; y = 0x4000 marks a row past the end
 };
 struct Book {
   RowTab tab[kStagesMax];
@@ -60,8 +59,10 @@ __device__ float4 g_zero_page[4];
 // diagnostics: cycles CTA (0,0,0) spent per producer phase / in the MMA thread (fov_debug_wgrad_read)
 __device__ unsigned long long g_wg_timeline[8];
 
-template <int NS, bool FAST>
+template <int NS, bool FAST, int WG_PIX>
 __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
+  constexpr int WG_GRP = WG_PIX * 128;   // bytes of one 64-wide MN group (WG_PIX pixel rows x 128 B)
+  constexpr int NA = WG_PIX / 16;        // x float4 loads per thread per pixel block
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -217,10 +218,11 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
     const int dq = WG_PIX / p.HW, dr = WG_PIX - dq * p.HW;       // 64 pixels = dq images + dr pixels
     const int dry = dr / p.W, drx = dr - dry * p.W;
     const int dno = dq / p.T_inner, dni = dq - dno * p.T_inner;
-    int no[2], ni[2], py[2], px[2];
-    bool live[2];
+    constexpr int RPL = WG_PIX / 32;                            // rows per lane
+    int no[RPL], ni[RPL], py[RPL], px[RPL];
+    bool live[RPL];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < RPL; ++h) {
       const int m = blk0 * WG_PIX + lane + h * 32;               // may exceed M: rows past the end stay dead
       const int n = m / p.HW, pix = m - n * p.HW;
       no[h] = n / p.T_inner; ni[h] = n - no[h] * p.T_inner;
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
       mbar_wait(smem_u32(&bk->empty[stage]), ((uint32_t)(i / S) & 1u) ^ 1u);
       RowTab& t = bk->tab[stage];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < RPL; ++h) {
         const int r = lane + h * 32;
         live[h] = (blk0 + i) * WG_PIX + r < p.M;
         if (live[h]) {
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
       // producers keep only ONE block of loads in flight in registers; with the rows already in L2 that is enough.
       if (p.taps == 1 && i + kPfDist < nblk) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < RPL; ++h) {
           const long long m = (long long)(blk0 + i + kPfDist) * WG_PIX + lane + h * 32;
           if (m < p.M) {
             const int n = (int)(m / p.HW), pix = (int)(m - (long long)n * p.HW);
@@ -362,25 +364,26 @@ int vec_of(const void* ptr, long long a, long long b, long long c, long long d) 
   return 1;
 }
 
-template <int NS, bool FAST>
+template <int NS, bool FAST, int PIX>
 int launch(const WgParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<NS, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<NS, FAST, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       fov_set_error("tc_wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return FOV_ERR_CUDA;
     }
     configured = true;
   }
-  tc_wgrad_kernel<NS, FAST><<<grid, kThr, smem, st>>>(p);
+  tc_wgrad_kernel<NS, FAST, PIX><<<grid, kThr, smem, st>>>(p);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
 
 }  // namespace
 
-static int g_wg_debug = 0;
+static int g_wg_debug = 0, g_wg_narrow = 0;
+extern "C" void fov_debug_wgrad_narrow(int on) { g_wg_narrow = on; }
 extern "C" void fov_debug_wgrad_enable(int on) { g_wg_debug = on; }
 extern "C" int fov_debug_wgrad_read(unsigned long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_wg_timeline, sizeof(unsigned long long) * 8);
@@ -391,7 +394,7 @@ int tc_wgrad_run(const TcWgrad& c, cudaStream_t st) {
   FOV_CHECK_ARG(c.x && c.dy && (c.gw || c.gbias), "NULL pointer");
   FOV_CHECK_ARG(c.N_img > 0 && c.H > 0 && c.W > 0 && c.Cin > 0 && c.Cout > 0 && c.T_inner > 0, "bad shape");
   const long long M = (long long)c.N_img * c.H * c.W;
-  FOV_CHECK_ARG(M < (1LL << 31) - WG_PIX, "too many pixels for 32-bit indexing");
+  FOV_CHECK_ARG(M < (1LL << 31) - WG_PIX_MAX, "too many pixels for 32-bit indexing");
   WgParams p{};
   p.x = c.x; p.x_outer = c.x_outer; p.x_inner = c.x_inner; p.x_pix_stride = c.x_pix_stride;
   p.Cin = c.Cin; p.Cin_p = (c.Cin + 7) / 8 * 8; p.kw = c.kw; p.taps = c.kh * c.kw;
@@ -401,9 +404,13 @@ int tc_wgrad_run(const TcWgrad& c, cudaStream_t st) {
   p.dy_vec = vec_of(c.dy, c.dy_outer, c.dy_inner, c.dy_pix_stride, c.Cout);
   p.H = c.H; p.W = c.W; p.HW = c.H * c.W; p.T_inner = c.T_inner; p.M = (int)M;
   p.gw = c.gw; p.gbias = c.gbias; p.dbg = g_wg_debug;
-  // n tile: 16/32/64/128 wide (the dY row of a thread must keep a fixed float4 column)
+  // n tile: 16/32/64/128 wide with 64-pixel stages, or 256 wide with 32-pixel stages when Cout > 128 (x is then read
+  // by half as many n tiles; the dY row of a thread must keep a fixed float4 column)
   int bn = 16;
   while (bn < c.Cout && bn < 128) bn <<= 1;
+  const bool wide = c.Cout > 128 && !g_wg_narrow;
+  if (wide) bn = 256;
+  const int WG_PIX = wide ? 32 : 64, WG_GRP = WG_PIX * 128;
   p.BLOCK_N = bn;
   const int n_tiles = (c.Cout + bn - 1) / bn;
   const int k_tiles = c.gw ? (p.taps * p.Cin_p + WG_M - 1) / WG_M : 1;
@@ -429,14 +436,24 @@ int tc_wgrad_run(const TcWgrad& c, cudaStream_t st) {
   const int splits = (p.nblocks + p.blocks_per_split - 1) / p.blocks_per_split;
   dim3 grid((unsigned)k_tiles, (unsigned)n_tiles, (unsigned)splits);
   const bool fast = p.x_vec == 4 && p.dy_vec == 4 && p.Cout % 4 == 0;
-  if (fast) {
-    if (c.math == 1) return launch<1, true>(p, grid, smem, st);
-    if (c.math == 2) return launch<2, true>(p, grid, smem, st);
-    return launch<3, true>(p, grid, smem, st);
+  if (wide) {
+    if (fast) {
+      if (c.math == 1) return launch<1, true, 32>(p, grid, smem, st);
+      if (c.math == 2) return launch<2, true, 32>(p, grid, smem, st);
+      return launch<3, true, 32>(p, grid, smem, st);
+    }
+    if (c.math == 1) return launch<1, false, 32>(p, grid, smem, st);
+    if (c.math == 2) return launch<2, false, 32>(p, grid, smem, st);
+    return launch<3, false, 32>(p, grid, smem, st);
   }
-  if (c.math == 1) return launch<1, false>(p, grid, smem, st);
-  if (c.math == 2) return launch<2, false>(p, grid, smem, st);
-  return launch<3, false>(p, grid, smem, st);
+  if (fast) {
+    if (c.math == 1) return launch<1, true, 64>(p, grid, smem, st);
+    if (c.math == 2) return launch<2, true, 64>(p, grid, smem, st);
+    return launch<3, true, 64>(p, grid, smem, st);
+  }
+  if (c.math == 1) return launch<1, false, 64>(p, grid, smem, st);
+  if (c.math == 2) return launch<2, false, 64>(p, grid, smem, st);
+  return launch<3, false, 64>(p, grid, smem, st);
 }
 
 extern "C" int fov_conv2d_bwd_weight_tc(const fov_conv_cfg* cfg, const float* x, const float* dy, float* gw,
