@@ -48,7 +48,7 @@ struct RowTab {
 };
 struct Book {
   RowTab tab[kStagesMax];
-  int dstrow[WG_M];                 // row of gw this accumulator row adds to, or -1
+  int dstrow[2 * WG_M];             // row of gw each accumulator row adds to, or -1 (two M tiles at most)
   uint64_t full[kStagesMax], empty[kStagesMax], tabrdy[kStagesMax], tmem_full;
   uint32_t tmem_ptr;
 };
@@ -59,10 +59,12 @@ __device__ float4 g_zero_page[4];
 // diagnostics: cycles CTA (0,0,0) spent per producer phase / in the MMA thread (fov_debug_wgrad_read)
 __device__ unsigned long long g_wg_timeline[8];
 
-template <int NS, bool FAST, int WG_PIX>
+// MT = M tiles (128 k rows each) per CTA: with two, dY is staged once for twice the k rows (half the dY re-reads)
+template <int NS, bool FAST, int WG_PIX, int MT>
 __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
   constexpr int WG_GRP = WG_PIX * 128;   // bytes of one 64-wide MN group (WG_PIX pixel rows x 128 B)
-  constexpr int NA = WG_PIX / 16;        // x float4 loads per thread per pixel block
+  constexpr int NA = WG_PIX * MT / 16;   // x float4 loads per thread per pixel block
+  constexpr int KT = WG_M * MT;          // k rows of this CTA
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -76,10 +78,10 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
   const int blk0 = blockIdx.z * p.blocks_per_split;
   int nblk = p.nblocks - blk0;
   if (nblk > p.blocks_per_split) nblk = p.blocks_per_split;
-  constexpr int A_TERM = 2 * WG_GRP;   // 128 k values = two 64-wide groups
+  constexpr int A_TERM = 2 * MT * WG_GRP;   // KT k values = 2 MT 64-wide groups
 
-  if (tid < WG_M) {
-    const int k = k_tile * WG_M + tid;
+  if (tid < KT) {
+    const int k = k_tile * KT + tid;
     const int tap = k / p.Cin_p, ci = k - tap * p.Cin_p;
     bk->dstrow[tid] = (tap < p.taps && ci < p.Cin) ? tap * p.Cin + ci : -1;
   }
@@ -109,8 +111,9 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
 
   if (warp < kProd / 32) {
     // ---------------- producers ----------------
-    const int q = tid & 31, rsub = tid >> 5;           // A': float4 slot along k, row phase (0..15)
-    const int k = k_tile * WG_M + q * 4;
+    const int q = tid % (32 * MT), rsub = tid / (32 * MT);   // A': float4 slot along k, row phase (0..16/MT-1)
+    constexpr int ASTEP = 16 / MT;                            // rows between a thread's x loads
+    const int k = k_tile * KT + q * 4;
     const int tap = k / p.Cin_p, ci = k - tap * p.Cin_p;
     int a_nvalid = (tap < p.taps) ? (p.Cin - ci) : 0;
     a_nvalid = a_nvalid < 0 ? 0 : (a_nvalid > 4 ? 4 : a_nvalid);
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
       if (FAST) {
 #pragma unroll
         for (int j = 0; j < NA; ++j) {
-          const int r = j * 16 + rsub;
+          const int r = j * ASTEP + rsub;
           const int pyx = t.pyx[r];
           const unsigned yy = (unsigned)((pyx >> 16) + tdy), xx = (unsigned)((pyx & 0xffff) + tdx);
           const bool ok = a_nvalid > 0 && yy < (unsigned)p.H && xx < (unsigned)p.W;
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
       }
 #pragma unroll
       for (int j = 0; j < NA; ++j) {
-        const int r = j * 16 + rsub;
+        const int r = j * ASTEP + rsub;
         const int pyx = t.pyx[r];
         const unsigned yy = (unsigned)((pyx >> 16) + tdy), xx = (unsigned)((pyx & 0xffff) + tdx);
         va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
         uint2 pk[NS];
         split4<NS>(va[j], pk);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(a_tile + s * A_TERM + j * 2048 + a_off) = pk[s];
+        for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(a_tile + s * A_TERM + j * (ASTEP * 128) + a_off) = pk[s];
       }
 #pragma unroll
       for (int j = 0; j < NBMAX; ++j) {
@@ -266,12 +269,12 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
             const int n = (int)(m / p.HW), pix = (int)(m - (long long)n * p.HW);
             const int nno = n / p.T_inner, nni = n - nno * p.T_inner;
             const float* xr = p.x + (long long)nno * p.x_outer + (long long)nni * p.x_inner + (long long)pix * p.x_pix_stride +
-                              k_tile * WG_M;
+                              k_tile * KT;
             const float* dr_ = p.dy + (long long)nno * p.dy_outer + (long long)nni * p.dy_inner +
                                (long long)pix * p.dy_pix_stride + n0;
-            const int xa = p.Cin - k_tile * WG_M, da = p.Cout - n0;
+            const int xa = p.Cin - k_tile * KT, da = p.Cout - n0;
 #pragma unroll
-            for (int l = 0; l < WG_M / 32; ++l)
+            for (int l = 0; l < KT / 32; ++l)
               if (l * 32 < xa) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + l * 32));
             for (int l = 0; l * 32 < p.BLOCK_N; ++l)
               if (l * 32 < da) asm volatile("prefetch.global.L2 [%0];" ::"l"(dr_ + l * 32));
@@ -303,10 +306,13 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
             for (int sa = 0; sa <= sum; ++sa) {
               const int sb = sum - sa;
               // 16 pixel rows per K step = 2048 B; LBO = stride between 64-wide M/N groups, SBO = 8 pixel rows
-              const uint64_t ad = smem_desc_sw128(a_base + sa * A_TERM + k4 * 2048, WG_GRP, 1024);
               const uint64_t bd = smem_desc_sw128(b_base + sb * p.b_term_bytes + k4 * 2048, WG_GRP, 1024);
               const uint32_t acc = (i > 0 || k4 > 0 || sum != NS - 1 || sa > 0) ? 1u : 0u;
-              umma_bf16(tmem_d, ad, bd, idesc, acc);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint64_t ad = smem_desc_sw128(a_base + sa * A_TERM + mt * 2 * WG_GRP + k4 * 2048, WG_GRP, 1024);
+                umma_bf16(tmem_d + (uint32_t)(mt * p.BLOCK_N), ad, bd, idesc, acc);
+              }
             }
           }
         }
@@ -324,10 +330,11 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
     const int r0 = warp * 32;
     const uint32_t t_row = tmem_d + ((uint32_t)r0 << 16);
     float* stg = reinterpret_cast<float*>(smem) + warp * (32 * RS);
+    for (int mt = 0; mt < MT; ++mt)
     for (int c0 = 0; c0 < p.BLOCK_N; c0 += 32) {
       float v[32];
-      tmem_ld16(t_row + c0, v);
-      tmem_ld16(t_row + c0 + 16, v + 16);
+      tmem_ld16(t_row + mt * p.BLOCK_N + c0, v);
+      tmem_ld16(t_row + mt * p.BLOCK_N + c0 + 16, v + 16);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(kThr, 1) tc_wgrad_kernel(const WgParams p) {
       const int col = n0 + c0 + lane;
       const bool col_ok = (c0 + lane < p.BLOCK_N) && (col < p.Cout);
       for (int rr = 0; rr < 32; ++rr) {
-        const int dr = bk->dstrow[r0 + rr];
+        const int dr = bk->dstrow[mt * WG_M + r0 + rr];
         if (dr >= 0 && col_ok) atomicAdd(p.gw + (long long)dr * p.Cout + col, stg[rr * RS + lane]);
       }
       __syncwarp();
@@ -364,25 +371,26 @@ int vec_of(const void* ptr, long long a, long long b, long long c, long long d) 
   return 1;
 }
 
-template <int NS, bool FAST, int PIX>
+template <int NS, bool FAST, int PIX, int MT>
 int launch(const WgParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<NS, FAST, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<NS, FAST, PIX, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       fov_set_error("tc_wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return FOV_ERR_CUDA;
     }
     configured = true;
   }
-  tc_wgrad_kernel<NS, FAST, PIX><<<grid, kThr, smem, st>>>(p);
+  tc_wgrad_kernel<NS, FAST, PIX, MT><<<grid, kThr, smem, st>>>(p);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
 
 }  // namespace
 
-static int g_wg_debug = 0, g_wg_narrow = 0;
+static int g_wg_debug = 0, g_wg_narrow = 0, g_wg_single_m = 0;
+extern "C" void fov_debug_wgrad_single_m(int on) { g_wg_single_m = on; }
 extern "C" void fov_debug_wgrad_narrow(int on) { g_wg_narrow = on; }
 extern "C" void fov_debug_wgrad_enable(int on) { g_wg_debug = on; }
 extern "C" int fov_debug_wgrad_read(unsigned long long* out) {
@@ -413,10 +421,12 @@ int tc_wgrad_run(const TcWgrad& c, cudaStream_t st) {
   const int WG_PIX = wide ? 32 : 64, WG_GRP = WG_PIX * 128;
   p.BLOCK_N = bn;
   const int n_tiles = (c.Cout + bn - 1) / bn;
-  const int k_tiles = c.gw ? (p.taps * p.Cin_p + WG_M - 1) / WG_M : 1;
-  p.tmem_cols = (int)tmem_cols_for(bn);
+  // two M tiles per CTA on the wide path when there are at least two: dY is then re-read by half as many CTAs
+  const int MT = (wide && p.taps * p.Cin_p > WG_M && !g_wg_single_m) ? 2 : 1;
+  const int k_tiles = c.gw ? (p.taps * p.Cin_p + WG_M * MT - 1) / (WG_M * MT) : 1;
+  p.tmem_cols = (int)tmem_cols_for(bn * MT);
   p.b_term_bytes = (bn + 63) / 64 * WG_GRP;
-  p.stage_bytes = c.math * (2 * WG_GRP + p.b_term_bytes);
+  p.stage_bytes = c.math * (2 * MT * WG_GRP + p.b_term_bytes);
   int stg = (227 * 1024 - (int)sizeof(Book) - 2048) / p.stage_bytes;
   if (stg > kStagesMax) stg = kStagesMax;
   FOV_CHECK_ARG(stg >= 2, "tile does not fit shared memory");
@@ -436,24 +446,34 @@ int tc_wgrad_run(const TcWgrad& c, cudaStream_t st) {
   const int splits = (p.nblocks + p.blocks_per_split - 1) / p.blocks_per_split;
   dim3 grid((unsigned)k_tiles, (unsigned)n_tiles, (unsigned)splits);
   const bool fast = p.x_vec == 4 && p.dy_vec == 4 && p.Cout % 4 == 0;
+  if (wide && MT == 2) {
+    if (fast) {
+      if (c.math == 1) return launch<1, true, 32, 2>(p, grid, smem, st);
+      if (c.math == 2) return launch<2, true, 32, 2>(p, grid, smem, st);
+      return launch<3, true, 32, 2>(p, grid, smem, st);
+    }
+    if (c.math == 1) return launch<1, false, 32, 2>(p, grid, smem, st);
+    if (c.math == 2) return launch<2, false, 32, 2>(p, grid, smem, st);
+    return launch<3, false, 32, 2>(p, grid, smem, st);
+  }
   if (wide) {
     if (fast) {
-      if (c.math == 1) return launch<1, true, 32>(p, grid, smem, st);
-      if (c.math == 2) return launch<2, true, 32>(p, grid, smem, st);
-      return launch<3, true, 32>(p, grid, smem, st);
+      if (c.math == 1) return launch<1, true, 32, 1>(p, grid, smem, st);
+      if (c.math == 2) return launch<2, true, 32, 1>(p, grid, smem, st);
+      return launch<3, true, 32, 1>(p, grid, smem, st);
     }
-    if (c.math == 1) return launch<1, false, 32>(p, grid, smem, st);
-    if (c.math == 2) return launch<2, false, 32>(p, grid, smem, st);
-    return launch<3, false, 32>(p, grid, smem, st);
+    if (c.math == 1) return launch<1, false, 32, 1>(p, grid, smem, st);
+    if (c.math == 2) return launch<2, false, 32, 1>(p, grid, smem, st);
+    return launch<3, false, 32, 1>(p, grid, smem, st);
   }
   if (fast) {
-    if (c.math == 1) return launch<1, true, 64>(p, grid, smem, st);
-    if (c.math == 2) return launch<2, true, 64>(p, grid, smem, st);
-    return launch<3, true, 64>(p, grid, smem, st);
+    if (c.math == 1) return launch<1, true, 64, 1>(p, grid, smem, st);
+    if (c.math == 2) return launch<2, true, 64, 1>(p, grid, smem, st);
+    return launch<3, true, 64, 1>(p, grid, smem, st);
   }
-  if (c.math == 1) return launch<1, false, 64>(p, grid, smem, st);
-  if (c.math == 2) return launch<2, false, 64>(p, grid, smem, st);
-  return launch<3, false, 64>(p, grid, smem, st);
+  if (c.math == 1) return launch<1, false, 64, 1>(p, grid, smem, st);
+  if (c.math == 2) return launch<2, false, 64, 1>(p, grid, smem, st);
+  return launch<3, false, 64, 1>(p, grid, smem, st);
 }
 
 extern "C" int fov_conv2d_bwd_weight_tc(const fov_conv_cfg* cfg, const float* x, const float* dy, float* gw,
