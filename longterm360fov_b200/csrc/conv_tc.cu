@@ -438,17 +438,37 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
             }
           }
         } else {
+          // Cout not a multiple of 4 (e.g. the 198-wide reconstruction head): one column per lane, 8 rows per batch
+          // with the loads / stores grouped so that the batch has no per-row control flow
           const int col = n0 + c0 + lane;
           const bool col_ok = (c0 + lane < p.BLOCK_N) && (col < p.Cout);
           const float bv = (col_ok && p.bias) ? __ldg(&p.bias[col]) : 0.0f;
-          for (int rr = 0; rr < 32; ++rr) {
-            const int row = r0 + rr;
-            if (col_ok && bk->valid[row]) {
-              float* dst = p.y + bk->off_o[O_OUT][row] + col;
-              float val = stg[rr * CONV_RS + lane] + bv;
-              if (p.beta != 0.0f) val += p.beta * *dst;
-              *dst = fov_act(p.act, val);
+          for (int rr0 = 0; rr0 < 32; rr0 += 8) {
+            float val[8];
+            float* dst[8];
+            bool ok[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int row = r0 + rr0 + j;
+              ok[j] = col_ok && bk->valid[row] != 0;
+              dst[j] = p.y + (ok[j] ? bk->off_o[O_OUT][row] + col : 0);
+              val[j] = stg[(rr0 + j) * CONV_RS + lane] + bv;
             }
+            if (p.beta != 0.0f) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (ok[j]) val[j] += p.beta * *dst[j];
+            }
+            if (p.act == FOV_ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) val[j] = fmaxf(val[j], 0.0f);
+            } else if (p.act == FOV_ACT_TANH) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) val[j] = tanhf(val[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (ok[j]) *dst[j] = val[j];
           }
         }
         __syncwarp();
