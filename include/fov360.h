@@ -62,6 +62,8 @@ typedef struct {
   int rec_act;        /* FOV_REC_* */
   int dec_zero_init;  /* 1: decoder starts from a zero state (FoV_seq2seq_no_teac_forc.py:29) */
   int training;       /* 1: write the saved-activation buffers */
+  int math;           /* FOV_MATH_* (declared below): 0 = fp32 CUDA-core kernel; 1..3 = the forward runs on tensor
+                         cores (tcgen05, that many bf16 terms per operand) when in_enc, in_dec <= 16 */
 } fov_lstm_cfg;
 
 typedef struct {

@@ -24,7 +24,7 @@ c_float_p = C.c_void_p      # device pointers travel as integers
 class LstmCfg(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "B", "T_enc", "T_dec", "in_enc", "in_dec", "H", "out_dim", "teacher_forcing",
-        "head_act", "rec_act", "dec_zero_init", "training")]
+        "head_act", "rec_act", "dec_zero_init", "training", "math")]
 
 
 class LstmWeights(C.Structure):

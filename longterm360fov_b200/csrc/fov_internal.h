@@ -35,6 +35,10 @@ int fov_conv_flip_weights(const fov_conv_cfg* fwd_cfg, const float* w, float* wt
 int fov_conv_bwd_data_preflipped(const fov_conv_cfg* fwd_cfg, const float* dy, const float* wt, float* dx,
                                  cudaStream_t st);
 
+// Persistent fc-LSTM forward on tensor cores (lstm_seq2seq_tc.cu); same contract as fov_lstm_seq2seq_fwd
+bool lstm_tc_supported(const fov_lstm_cfg* cfg);
+int lstm_tc_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w, const fov_lstm_io* io, cudaStream_t st);
+
 // ---- tensor-core (tcgen05) implicit-GEMM convolution family (conv_tc.cu) -------------------
 // One K segment of the implicit-GEMM A operand: an NHWC activation tensor convolved with its
 // own (kh,kw) taps.  Two segments = the fused ConvLSTM gate GEMM [x taps | h taps] x [K ; R].

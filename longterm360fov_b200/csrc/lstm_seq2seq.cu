@@ -9,6 +9,11 @@
 //
 // Replaces the Keras LSTM/Dense calls cited in include/fov360.h.
 #include "fov_common.cuh"
+#include "fov_internal.h"
+
+// diagnostics / A-B testing: -1 = never use the tensor-core forward, 0 = choose, 1 = whenever the shape allows
+static int g_lstm_tc_mode = 0;
+extern "C" void fov_debug_lstm_tc(int mode) { g_lstm_tc_mode = mode; }
 
 namespace {
 
@@ -425,6 +430,10 @@ extern "C" int fov_lstm_seq2seq_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
   P.cfg = *cfg; P.w = *w; P.io = *io;
   if (P.cfg.T_dec == 0) P.cfg.out_dim = 0;
   cudaStream_t st = (cudaStream_t)stream;
+  // tensor-core forward (lstm_seq2seq_tc.cu): 128-sequence tiles; below a few tiles the 16-sequence fp32 CTAs win
+  if (cfg->math != FOV_MATH_FP32 && g_lstm_tc_mode >= 0 && lstm_tc_supported(cfg) &&
+      (g_lstm_tc_mode > 0 || cfg->B >= 1024))
+    return lstm_tc_fwd(&P.cfg, w, io, st);
   // 64 sequences per CTA when the operand tile fits, else 32
   // ... and 16 when even 32-sequence tiles would leave SMs idle (the recurrence is latency bound: smaller tiles =
   // more CTAs in flight and a shorter per-step chain)

@@ -1,0 +1,530 @@
+// Persistent fc-LSTM encoder-decoder forward on tensor cores (tcgen05 + TMEM): ONE launch runs the T_enc encoder
+// steps and the T_dec decoder steps (teacher forced or autoregressive) of 128 sequences per image group.
+//
+//   * a group = 128 sequences = the 128 rows (TMEM lanes) of one accumulator tile; a CTA runs NG groups with their own
+//     TMEM columns and barriers so the gate algebra of one group overlaps the MMAs of the other;
+//   * the gate weights [W ; U] of the running phase are converted ONCE per phase from their Keras layout
+//     (in,4H) / (H,4H) into bf16 terms in K-major 128-byte-swizzled shared-memory tiles (B operand, N = 4H = 256);
+//   * per step and group one tcgen05.mma chain  D[128 x 256] = [x_t | h_{t-1}] x [W ; U]  (K = 16 + 64, every
+//     significant product of the bf16 terms), issued by one elected thread of the group once its 128 rows are staged
+//     (no dedicated MMA warp: 8 warps per CTA keep the full 255-register budget for the 64-float cell state);
+//   * the epilogue thread of a row reads its 256 gate pre-activations with tcgen05.ld, keeps the cell state of its
+//     sequence (64 floats) in registers, writes h_t as bf16 terms straight into the swizzled A-operand rows of the next
+//     step (h never goes through HBM), runs the Dense head (+ optional additive term) on the h it just produced and,
+//     when decoding autoregressively, writes the head output as the next step's x operand: no per-step launch and no
+//     host round trip (mycode/FoV_seq2seq.py:154-178 does 11 predict() calls per sample here);
+//   * teacher-forced inputs x_{t+1} are prefetched into registers while the MMAs of step t run.
+// In training mode the saved tensors the BPTT kernel needs (lstm_seq2seq.cu) are written by the row's thread.
+//
+// Replaces the Keras LSTM/Dense calls cited in include/fov360.h when cfg.math != 0.
+#include "fov_common.cuh"
+#include "fov_internal.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int kH = 64;                     // latent_dim
+constexpr int kG = 256;                    // 4H = MMA N
+constexpr int kRows = 128;                 // sequences per group = MMA M
+constexpr int kXK = 16;                    // K extent of the x operand (in_dim <= 16)
+constexpr uint32_t kBTerm = kG * 128;      // bytes of one bf16 term of a weight tile (256 rows x 128 B)
+constexpr uint32_t kATerm = kRows * 128;   // bytes of one bf16 term of an operand tile (128 rows x 128 B)
+
+struct TcPhase {
+  const float *Wk, *Uk, *bk;               // Keras layout
+  const float* x;                          // (B, x_T, in_dim)
+  int in_dim, T, x_T;
+  int ar, has_head, zero_init;
+  const float* extra;                      // optional (B,T,out)
+  float* y;                                // (B,T,out)
+  fov_lstm_saved sv;
+};
+
+struct LstmTcParams {
+  TcPhase ph[2];
+  int nph;
+  int B, out_dim, head_act, training, dbg;
+  const float *Wo, *bo;
+  const float *h0, *c0;
+  float *hT, *cT;
+};
+
+template <int OD>
+struct LstmTcBook {
+  float4 bias4[kH];                        // (b_i, b_f, b_c, b_o) of a hidden unit
+  float Wo_s[kH * OD];                     // head kernel, rows padded to OD columns
+  float bo_s[OD];
+  uint64_t tmem_full[2];
+  uint32_t tmem_ptr;
+};
+
+// diagnostics (fov_debug_lstm_tc_read): cycles CTA 0 / thread 0 spent [0] waiting for the accumulator, [1] in the gate
+// algebra, [2] head + stores + operand writes, [3] whole step loop, [5] issuing the MMAs
+__device__ unsigned long long g_lstm_tc_timeline[8];
+
+__device__ __forceinline__ void bar_workers(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
+__device__ __forceinline__ void bar_group(int g) { asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory"); }
+
+// tanh(x) = 1 - 2 / (1 + 2^(x * 2 log2 e)): FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA (abs error ~1e-7)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh5(float x) {
+  return fmaf(-2.0f, rcp_approx(ex2_approx(x * 2.885390082f) + 1.0f), 1.0f);
+}
+__device__ __forceinline__ float head_act_fn(int act, float x) {
+  if (act == FOV_ACT_TANH) return tanh5(x);
+  if (act == FOV_ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+
+// 16 floats -> global row segment with the widest store the row alignment allows (vec = 4, 2 or 1 floats)
+__device__ __forceinline__ void store16(float* dst, const float (&v)[16], int vec) {
+  if (vec == 4) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  } else if (vec == 2) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) *reinterpret_cast<float2*>(dst + j) = make_float2(v[j], v[j + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dst[j] = v[j];
+  }
+}
+
+template <int NS, int NG, int REC, int OD>
+__global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid_constant__ LstmTcParams P) {
+  constexpr int NW = kRows * NG;           // threads: one per sequence
+  constexpr uint32_t kWbOff = NS * kBTerm;                 // x-part weights (all terms in one tile, 32-byte chunks)
+  constexpr uint32_t kActOff = kWbOff + kBTerm;
+  constexpr uint32_t kGrpBytes = (NS + 1) * kATerm;        // h terms, then the x tile (terms as 32-byte chunks)
+  using Book = LstmTcBook<OD>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  Book* bk = reinterpret_cast<Book*>(smem + kActOff + NG * kGrpBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---------------- setup ----------------
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int g = 0; g < NG; ++g) mbar_init(smem_u32(&bk->tmem_full[g]), 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&bk->tmem_ptr), NG * kG);
+    tmem_relinquish();
+  }
+  for (int idx = tid; idx < kH * OD; idx += blockDim.x) {
+    const int u = idx / OD, d = idx - u * OD;
+    bk->Wo_s[idx] = (P.out_dim > 0 && d < P.out_dim) ? __ldg(&P.Wo[u * P.out_dim + d]) : 0.0f;
+  }
+  if (tid < OD) bk->bo_s[tid] = (P.out_dim > 0 && tid < P.out_dim) ? __ldg(&P.bo[tid]) : 0.0f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = bk->tmem_ptr;
+
+  {
+    // ---------------- thread = one sequence (accumulator row) ----------------
+    const int g = warp >> 2, q = warp & 3, r = q * 32 + lane;
+    const long long b = ((long long)blockIdx.x * NG + g) * kRows + r;
+    const bool valid = b < P.B;
+    uint8_t* hA = smem + kActOff + (uint32_t)g * kGrpBytes;
+    uint8_t* xA = hA + NS * kATerm;
+    const uint32_t rowoff = (uint32_t)r * 128u, rsw = (uint32_t)(r & 7);
+    const uint32_t t_row = tmem_d + (uint32_t)(g * kG) + ((uint32_t)(q * 32) << 16);
+    const bool dbg = P.dbg && blockIdx.x == 0 && tid == 0;
+    long long tw = 0, ta = 0, tb = 0, tm = 0;
+    const long long t_begin = clock64();
+    const uint32_t idesc = idesc_bf16_f32(kRows, kG, 0, 0);
+    // D[128 x 256] = [x_t | h_{t-1}] x [W ; U] for my group: called by ONE thread after the group barrier
+    auto issue_mmas = [&]() {
+      tc_fence_after();
+      const uint32_t hA_s = base + kActOff + (uint32_t)g * kGrpBytes, xA_s = hA_s + NS * kATerm;
+      const uint32_t d = tmem_d + (uint32_t)(g * kG);
+      uint32_t acc = 0;
+      // x part: one k16 step, the terms are 32-byte chunks of the same tile
+#pragma unroll
+      for (int sum = NS - 1; sum >= 0; --sum) {
+#pragma unroll
+        for (int sa = 0; sa <= sum; ++sa) {
+          const int sb = sum - sa;
+          umma_bf16(d, desc_at(kDescHi128, xA_s + sa * 32), desc_at(kDescHi128, base + kWbOff + sb * 32), idesc, acc);
+          acc = 1;
+        }
+      }
+      // h part: four k16 steps
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+#pragma unroll
+        for (int sum = NS - 1; sum >= 0; --sum) {
+#pragma unroll
+          for (int sa = 0; sa <= sum; ++sa) {
+            const int sb = sum - sa;
+            umma_bf16(d, desc_at(kDescHi128, hA_s + sa * kATerm + k4 * 32),
+                      desc_at(kDescHi128, base + sb * kBTerm + k4 * 32), idesc, 1u);
+          }
+        }
+      }
+      umma_commit(smem_u32(&bk->tmem_full[g]));
+    };
+
+    // 8 consecutive hidden units of my row -> bf16 terms, chunk c8 of the h operand tile
+    auto h_store8 = [&](int c8, const float* hn) {
+      uint2 lo[NS], hi[NS];
+      split4<NS>(make_float4(hn[0], hn[1], hn[2], hn[3]), lo);
+      split4<NS>(make_float4(hn[4], hn[5], hn[6], hn[7]), hi);
+      const uint32_t so = rowoff + ((((uint32_t)c8) ^ rsw) << 4);
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        *reinterpret_cast<uint4*>(hA + s * kATerm + so) = make_uint4(lo[s].x, lo[s].y, hi[s].x, hi[s].y);
+    };
+    // the 16 input features of my row -> term s in the 32-byte chunk pair (2s, 2s+1) of the x tile
+    auto x_store = [&](const float (&xn)[kXK]) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint2 lo[NS], hi[NS];
+        split4<NS>(make_float4(xn[hf * 8 + 0], xn[hf * 8 + 1], xn[hf * 8 + 2], xn[hf * 8 + 3]), lo);
+        split4<NS>(make_float4(xn[hf * 8 + 4], xn[hf * 8 + 5], xn[hf * 8 + 6], xn[hf * 8 + 7]), hi);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          *reinterpret_cast<uint4*>(xA + rowoff + ((((uint32_t)(2 * s + hf)) ^ rsw) << 4)) =
+              make_uint4(lo[s].x, lo[s].y, hi[s].x, hi[s].y);
+      }
+    };
+
+    float c[kH];
+#pragma unroll
+    for (int u = 0; u < kH; ++u) c[u] = 0.0f;
+
+    int step = 0;
+    for (int pi = 0; pi < P.nph; ++pi) {
+      const TcPhase& ph = P.ph[pi];
+      const int in_dim = ph.in_dim, T = ph.T, K = kH + in_dim;
+      const bool save = P.training != 0;
+      const int xh_vec = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);
+      const int Kn = (pi + 1 < P.nph) ? kH + P.ph[pi + 1].in_dim : K;      // xh row width of the next phase
+      const int xhn_vec = (Kn % 4 == 0) ? 4 : ((Kn % 2 == 0) ? 2 : 1);
+      // every MMA of the previous phase has completed once all workers got here (each group waited for its last commit)
+      tc_fence_before();
+      bar_workers(NW);
+      // ---- gate weights of this phase -> bf16 terms, K-major swizzled rows (row n = gate column n) ----
+      for (int n = tid; n < kG; n += NW) {
+        const uint32_t nsw = (uint32_t)(n & 7), noff = (uint32_t)n * 128u;
+#pragma unroll 2
+        for (int c8 = 0; c8 < 8; ++c8) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __ldg(&ph.Uk[(c8 * 8 + j) * kG + n]);
+          uint2 lo[NS], hi[NS];
+          split4<NS>(make_float4(v[0], v[1], v[2], v[3]), lo);
+          split4<NS>(make_float4(v[4], v[5], v[6], v[7]), hi);
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+            *reinterpret_cast<uint4*>(smem + s * kBTerm + noff + ((((uint32_t)c8) ^ nsw) << 4)) =
+                make_uint4(lo[s].x, lo[s].y, hi[s].x, hi[s].y);
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = hf * 8 + j;
+            v[j] = k < in_dim ? __ldg(&ph.Wk[k * kG + n]) : 0.0f;
+          }
+          uint2 lo[NS], hi[NS];
+          split4<NS>(make_float4(v[0], v[1], v[2], v[3]), lo);
+          split4<NS>(make_float4(v[4], v[5], v[6], v[7]), hi);
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+            *reinterpret_cast<uint4*>(smem + kWbOff + noff + ((((uint32_t)(2 * s + hf)) ^ nsw) << 4)) =
+                make_uint4(lo[s].x, lo[s].y, hi[s].x, hi[s].y);
+        }
+      }
+      // biases with the affine part of the recurrent activation folded in: hard_sigmoid(z + b) = sat(0.2 z + (0.2 b + 0.5)),
+      // sigmoid(z + b) = 1 / (1 + 2^(-log2e z - log2e b))
+      if (tid < kH) {
+        const float bi = __ldg(&ph.bk[tid]), bf = __ldg(&ph.bk[kH + tid]), bc = __ldg(&ph.bk[2 * kH + tid]),
+                    bo = __ldg(&ph.bk[3 * kH + tid]);
+        if (REC == FOV_REC_HARD_SIGMOID)
+          bk->bias4[tid] = make_float4(fmaf(0.2f, bi, 0.5f), fmaf(0.2f, bf, 0.5f), bc, fmaf(0.2f, bo, 0.5f));
+        else
+          bk->bias4[tid] = make_float4(-1.442695041f * bi, -1.442695041f * bf, bc, -1.442695041f * bo);
+      }
+      // ---- initial state of this phase ----
+      if (pi == 0 || ph.zero_init) {
+        const float* h0 = (pi == 0 && !ph.zero_init && valid) ? P.h0 : nullptr;
+        const float* c0 = (pi == 0 && !ph.zero_init && valid) ? P.c0 : nullptr;
+        float* xh0 = (save && valid && ph.sv.xh) ? ph.sv.xh + (size_t)b * T * K : nullptr;
+#pragma unroll
+        for (int p16 = 0; p16 < 4; ++p16) {
+          float hv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            hv[j] = h0 ? __ldg(&h0[(size_t)b * kH + p16 * 16 + j]) : 0.0f;
+            c[p16 * 16 + j] = c0 ? __ldg(&c0[(size_t)b * kH + p16 * 16 + j]) : 0.0f;
+          }
+          h_store8(p16 * 2, hv);
+          h_store8(p16 * 2 + 1, hv + 8);
+          if (xh0) store16(xh0 + p16 * 16, hv, xh_vec);
+        }
+      }
+      // ---- x_0 ----
+      {
+        float xn[kXK];
+#pragma unroll
+        for (int k = 0; k < kXK; ++k)
+          xn[k] = (valid && k < in_dim) ? __ldg(&ph.x[(size_t)b * ph.x_T * in_dim + k]) : 0.0f;
+        x_store(xn);
+        if (save && valid && ph.sv.xh) {
+          float* xr = ph.sv.xh + (size_t)b * T * K + kH;
+#pragma unroll
+          for (int k = 0; k < kXK; ++k)
+            if (k < in_dim) xr[k] = xn[k];
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      bar_workers(NW);
+      if (r == 0) issue_mmas();
+
+      const bool next_phase_carries = (pi + 1 < P.nph) && !P.ph[pi + 1].zero_init;
+      for (int t = 0; t < T; ++t) {
+        const bool more = t + 1 < T;
+        float xn[kXK];
+#pragma unroll
+        for (int k = 0; k < kXK; ++k) xn[k] = 0.0f;
+        if (!ph.ar && more) {
+#pragma unroll
+          for (int k = 0; k < kXK; ++k)
+            xn[k] = (valid && k < in_dim) ? __ldg(&ph.x[((size_t)b * ph.x_T + t + 1) * in_dim + k]) : 0.0f;
+        }
+        const size_t rowt = (size_t)b * T + t;
+        float* gates_p = (save && valid && ph.sv.gates) ? ph.sv.gates + rowt * kG : nullptr;
+        float* c_p = (save && valid && ph.sv.c) ? ph.sv.c + rowt * kH : nullptr;
+        float* hseq_p = (valid && ph.sv.hseq) ? ph.sv.hseq + rowt * kH : nullptr;
+        float* xh_next = nullptr;
+        if (save && valid) {
+          if (more) xh_next = ph.sv.xh ? ph.sv.xh + (rowt + 1) * K : nullptr;
+          else if (next_phase_carries && P.ph[pi + 1].sv.xh)
+            xh_next = P.ph[pi + 1].sv.xh + (size_t)b * P.ph[pi + 1].T * Kn;
+        }
+        const int xh_next_vec = more ? xh_vec : xhn_vec;
+        float* hT_p = (!more && pi + 1 == P.nph && valid && P.hT) ? P.hT + (size_t)b * kH : nullptr;
+
+        long long k0 = 0, k1 = 0, k2 = 0;
+        if (dbg) k0 = clock64();
+        mbar_wait(smem_u32(&bk->tmem_full[g]), (uint32_t)step & 1u);
+        __syncwarp();
+        tc_fence_after();
+        if (dbg) { k1 = clock64(); tw += k1 - k0; }
+
+        float yacc[OD];
+#pragma unroll
+        for (int d = 0; d < OD; ++d) yacc[d] = 0.0f;
+#pragma unroll
+        for (int p16 = 0; p16 < 4; ++p16) {
+          float gt[4][16];
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi) tmem_ld16(t_row + gi * kH + p16 * 16, gt[gi]);
+          tmem_ld_wait();
+          float hn[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int u = p16 * 16 + j;
+            const float4 bb = bk->bias4[u];
+            float ai, af, ao;
+            if (REC == FOV_REC_HARD_SIGMOID) {
+              ai = __saturatef(fmaf(0.2f, gt[0][j], bb.x));
+              af = __saturatef(fmaf(0.2f, gt[1][j], bb.y));
+              ao = __saturatef(fmaf(0.2f, gt[3][j], bb.w));
+            } else {
+              ai = rcp_approx(1.0f + ex2_approx(fmaf(-1.442695041f, gt[0][j], bb.x)));
+              af = rcp_approx(1.0f + ex2_approx(fmaf(-1.442695041f, gt[1][j], bb.y)));
+              ao = rcp_approx(1.0f + ex2_approx(fmaf(-1.442695041f, gt[3][j], bb.w)));
+            }
+            const float ag = tanh5(gt[2][j] + bb.z);
+            const float cn = fmaf(af, c[u], ai * ag);
+            c[u] = cn;
+            hn[j] = ao * tanh5(cn);
+            gt[0][j] = ai; gt[1][j] = af; gt[2][j] = ag; gt[3][j] = ao;
+          }
+          h_store8(p16 * 2, hn);
+          h_store8(p16 * 2 + 1, hn + 8);
+          if (ph.has_head) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float4* wr = reinterpret_cast<const float4*>(&bk->Wo_s[(p16 * 16 + j) * OD]);
+#pragma unroll
+              for (int d4 = 0; d4 < OD / 4; ++d4) {
+                const float4 w4 = wr[d4];
+                yacc[d4 * 4 + 0] = fmaf(hn[j], w4.x, yacc[d4 * 4 + 0]);
+                yacc[d4 * 4 + 1] = fmaf(hn[j], w4.y, yacc[d4 * 4 + 1]);
+                yacc[d4 * 4 + 2] = fmaf(hn[j], w4.z, yacc[d4 * 4 + 2]);
+                yacc[d4 * 4 + 3] = fmaf(hn[j], w4.w, yacc[d4 * 4 + 3]);
+              }
+            }
+          }
+          if (gates_p) {
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) store16(gates_p + gi * kH + p16 * 16, gt[gi], 4);
+          }
+          if (c_p) {
+            float cv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cv[j] = c[p16 * 16 + j];
+            store16(c_p + p16 * 16, cv, 4);
+          }
+          if (hseq_p) store16(hseq_p + p16 * 16, hn, 4);
+          if (xh_next) store16(xh_next + p16 * 16, hn, xh_next_vec);
+          if (hT_p) store16(hT_p + p16 * 16, hn, 4);
+        }
+        tc_fence_before();                 // my tcgen05.ld of this accumulator are complete before the next MMAs
+        if (dbg) { k2 = clock64(); ta += k2 - k1; }
+
+        if (ph.has_head) {
+          const size_t o = rowt * (size_t)P.out_dim;
+#pragma unroll
+          for (int d = 0; d < OD; ++d) {
+            float sum = yacc[d] + bk->bo_s[d];
+            const bool live = d < P.out_dim;
+            if (live && valid && ph.extra) sum += __ldg(&ph.extra[o + d]);
+            const float yv = head_act_fn(P.head_act, sum);
+            if (live && valid) ph.y[o + d] = yv;
+            if (ph.ar && d < kXK) xn[d] = live ? yv : 0.0f;
+          }
+        }
+        if (more) {
+          x_store(xn);
+          if (save && valid && ph.sv.xh) {
+            float* xr = ph.sv.xh + (rowt + 1) * K + kH;
+#pragma unroll
+            for (int k = 0; k < kXK; ++k)
+              if (k < in_dim) xr[k] = xn[k];
+          }
+          fence_proxy_async_smem();
+          bar_group(g);
+          long long k3 = 0;
+          if (dbg) k3 = clock64();
+          if (r == 0) issue_mmas();
+          if (dbg) tm += clock64() - k3;
+        }
+        ++step;
+        if (dbg) tb += clock64() - k2;
+      }
+    }
+    if (valid && P.cT) {
+#pragma unroll
+      for (int p16 = 0; p16 < 4; ++p16) {
+        float cv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) cv[j] = c[p16 * 16 + j];
+        store16(P.cT + (size_t)b * kH + p16 * 16, cv, 4);
+      }
+    }
+    if (dbg) {
+      g_lstm_tc_timeline[0] = tw; g_lstm_tc_timeline[1] = ta; g_lstm_tc_timeline[2] = tb;
+      g_lstm_tc_timeline[3] = clock64() - t_begin;
+      g_lstm_tc_timeline[5] = tm;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, NG * kG);
+}
+
+template <int NS, int NG, int OD>
+size_t tc_smem_bytes() {
+  return (size_t)(NS + 1) * kBTerm + (size_t)NG * (NS + 1) * kATerm + sizeof(LstmTcBook<OD>) + 1024;
+}
+
+template <int NS, int NG, int REC, int OD>
+int launch_tc(const LstmTcParams& P, cudaStream_t st) {
+  const size_t smem = tc_smem_bytes<NS, NG, OD>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_tc_fwd_kernel<NS, NG, REC, OD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) {
+      fov_set_error("fov_lstm (tensor-core): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return FOV_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int per_cta = kRows * NG;
+  const int grid = (P.B + per_cta - 1) / per_cta;
+  lstm_tc_fwd_kernel<NS, NG, REC, OD><<<grid, kRows * NG, smem, st>>>(P);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
+
+template <int NS, int NG>
+int launch_tc_ro(const LstmTcParams& P, int rec, cudaStream_t st) {
+  const bool hs = rec == FOV_REC_HARD_SIGMOID;
+  if (P.out_dim <= 8)
+    return hs ? launch_tc<NS, NG, FOV_REC_HARD_SIGMOID, 8>(P, st) : launch_tc<NS, NG, FOV_REC_SIGMOID, 8>(P, st);
+  return hs ? launch_tc<NS, NG, FOV_REC_HARD_SIGMOID, 16>(P, st) : launch_tc<NS, NG, FOV_REC_SIGMOID, 16>(P, st);
+}
+
+int g_lstm_tc_dbg = 0;
+
+}  // namespace
+
+extern "C" void fov_debug_lstm_tc_enable(int on) { g_lstm_tc_dbg = on; }
+extern "C" int fov_debug_lstm_tc_read(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_lstm_tc_timeline, sizeof(unsigned long long) * 8);
+}
+
+bool lstm_tc_supported(const fov_lstm_cfg* cfg) {
+  if (cfg->H != kH || cfg->math < FOV_MATH_BF16 || cfg->math > FOV_MATH_BF16X3) return false;
+  if (cfg->T_enc > 0 && cfg->in_enc > kXK) return false;
+  if (cfg->T_dec > 0 && cfg->in_dec > kXK) return false;
+  if (cfg->out_dim > 16) return false;
+  return true;
+}
+
+int lstm_tc_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w, const fov_lstm_io* io, cudaStream_t st) {
+  LstmTcParams P{};
+  P.B = cfg->B; P.out_dim = cfg->T_dec > 0 ? cfg->out_dim : 0; P.head_act = cfg->head_act; P.training = cfg->training;
+  P.dbg = g_lstm_tc_dbg;
+  P.Wo = w->head_kernel; P.bo = w->head_bias; P.h0 = io->h0; P.c0 = io->c0; P.hT = io->hT; P.cT = io->cT;
+  int n = 0;
+  if (cfg->T_enc > 0) {
+    TcPhase& ph = P.ph[n++];
+    ph.Wk = w->enc_kernel; ph.Uk = w->enc_recurrent; ph.bk = w->enc_bias;
+    ph.x = io->x_enc; ph.in_dim = cfg->in_enc; ph.T = cfg->T_enc; ph.x_T = cfg->T_enc;
+    ph.ar = 0; ph.has_head = 0; ph.zero_init = 0; ph.extra = nullptr; ph.y = nullptr; ph.sv = io->enc;
+  }
+  if (cfg->T_dec > 0) {
+    TcPhase& ph = P.ph[n++];
+    ph.Wk = w->dec_kernel; ph.Uk = w->dec_recurrent; ph.bk = w->dec_bias;
+    ph.x = io->x_dec; ph.in_dim = cfg->in_dec; ph.T = cfg->T_dec;
+    ph.ar = cfg->teacher_forcing == 0; ph.x_T = ph.ar ? 1 : cfg->T_dec;
+    ph.has_head = P.out_dim > 0; ph.zero_init = cfg->dec_zero_init ? 1 : 0;
+    ph.extra = io->extra; ph.y = io->y; ph.sv = io->dec;
+  }
+  P.nph = n;
+  auto a16 = [](const void* q) { return (uintptr_t)q % 16 == 0; };
+  FOV_CHECK_ARG(a16(io->enc.gates) && a16(io->enc.c) && a16(io->enc.hseq) && a16(io->dec.gates) && a16(io->dec.c) &&
+                    a16(io->dec.hseq) && a16(io->enc.xh) && a16(io->dec.xh) && a16(io->hT) && a16(io->cT),
+                "tensor-core fc-LSTM needs 16-byte aligned state / saved tensors");
+  // two groups per CTA (MMA / epilogue overlap) once there are enough sequences to fill the SMs with one group each
+  const bool two = cfg->math <= FOV_MATH_BF16X2 && cfg->B > kRows * fov_num_sms();
+  switch (cfg->math) {
+    case FOV_MATH_BF16: return two ? launch_tc_ro<1, 2>(P, cfg->rec_act, st) : launch_tc_ro<1, 1>(P, cfg->rec_act, st);
+    case FOV_MATH_BF16X2: return two ? launch_tc_ro<2, 2>(P, cfg->rec_act, st) : launch_tc_ro<2, 1>(P, cfg->rec_act, st);
+    default: return launch_tc_ro<3, 1>(P, cfg->rec_act, st);
+  }
+}

@@ -506,7 +506,7 @@ class FovSeq2Seq(Model):
         tf = self.teacher_forcing if teacher_forcing is None else teacher_forcing
         T_dec = dec.shape[1] if tf else (steps or self.T_dec)
         opts = {"T_dec": T_dec, "teacher_forcing": tf, "head_act": "tanh", "rec_act": self.rec_act,
-                "dec_zero_init": self.decoder_no_init_state, "training": training}
+                "dec_zero_init": self.decoder_no_init_state, "training": training, "need_enc_hseq": False}
         y, _ = ops.LSTMSeq2SeqFn.apply(opts, self._lstm_sinks() if training else None, enc, dec, None,
                                        *self._w())
         return [y]

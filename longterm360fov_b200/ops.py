@@ -78,10 +78,11 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
         cfg = _lib.LstmCfg(B, T_enc, T_dec, in_enc, in_dec, H, out_dim,
                            int(opts["teacher_forcing"]), ACT[opts.get("head_act")],
                            REC[opts.get("rec_act", "hard_sigmoid")],
-                           int(opts.get("dec_zero_init", False)), int(training))
+                           int(opts.get("dec_zero_init", False)), int(training), _MATH[0])
         w = _lib.LstmWeights(ptr(We), ptr(Ue), ptr(be), ptr(Wd), ptr(Ud), ptr(bd), ptr(Wo), ptr(bo))
         y = torch.empty(B, T_dec, out_dim, device=dev)
-        enc_hseq = torch.empty(B, T_enc, H, device=dev)
+        # the encoder's h sequence is an output only for callers that read it (M3's target-past head)
+        enc_hseq = torch.empty(B, T_enc, H, device=dev) if opts.get("need_enc_hseq", True) else None
         saved = {}
         if training:
             saved["enc_xh"] = torch.empty(B, T_enc, H + in_enc, device=dev)
@@ -102,6 +103,9 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
             ctx.cfg, ctx.sinks, ctx.saved = cfg, sinks, saved
             ctx.has_extra = extra is not None
             ctx.save_for_backward(x_enc, x_dec, extra, We, Ue, be, Wd, Ud, bd, Wo, bo, y, enc_hseq)
+        if enc_hseq is None:
+            enc_hseq = y.new_empty(0)
+            ctx.mark_non_differentiable(enc_hseq)
         return y, enc_hseq
 
     @staticmethod
@@ -110,7 +114,7 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
         x_enc, x_dec, extra, We, Ue, be, Wd, Ud, bd, Wo, bo, y, enc_hseq = ctx.saved_tensors
         cfg, s, sv = ctx.cfg, ctx.sinks, ctx.saved
         dy = _f32c(dy) if dy is not None else torch.zeros_like(y)
-        dhseq_enc = _f32c(dhseq_enc)
+        dhseq_enc = _f32c(dhseq_enc) if enc_hseq is not None else None
         dev = y.device
         dz_enc = torch.empty(cfg.B, cfg.T_enc, 4 * cfg.H, device=dev)
         dz_dec = torch.empty(cfg.B, cfg.T_dec, 4 * cfg.H, device=dev)
@@ -138,7 +142,7 @@ def lstm_states(x_enc, We, Ue, be, rec_act="hard_sigmoid", h0=None, c0=None):
     x_enc = _f32c(x_enc)
     B, T, in_enc = x_enc.shape
     H = Ue.shape[0]
-    cfg = _lib.LstmCfg(B, T, 0, in_enc, 0, H, 0, 1, 0, REC[rec_act], 0, 0)
+    cfg = _lib.LstmCfg(B, T, 0, in_enc, 0, H, 0, 1, 0, REC[rec_act], 0, 0, _MATH[0])
     w = _lib.LstmWeights(ptr(We), ptr(Ue), ptr(be), None, None, None, None, None)
     hT = torch.empty(B, H, device=x_enc.device)
     cT = torch.empty(B, H, device=x_enc.device)
@@ -159,7 +163,7 @@ def lstm_decode_steps(x_dec, h0, c0, Wd, Ud, bd, Wo, bo, T_dec, teacher_forcing,
     H = Ud.shape[0]
     out_dim = Wo.shape[1]
     cfg = _lib.LstmCfg(B, 0, T_dec, 0, in_dec, H, out_dim, int(teacher_forcing), ACT[head_act],
-                       REC[rec_act], 0, 0)
+                       REC[rec_act], 0, 0, _MATH[0])
     w = _lib.LstmWeights(None, None, None, ptr(Wd), ptr(Ud), ptr(bd), ptr(Wo), ptr(bo))
     dev = x_dec.device
     y = torch.empty(B, T_dec, out_dim, device=dev)
