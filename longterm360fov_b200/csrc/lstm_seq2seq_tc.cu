@@ -101,6 +101,24 @@ __device__ __forceinline__ void store16(float* dst, const float (&v)[16], int ve
   }
 }
 
+__device__ __forceinline__ void store8(float* dst, const float (&v)[8], int vec) {
+  if (vec == 4) {
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else if (vec == 2) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) *reinterpret_cast<float2*>(dst + j) = make_float2(v[j], v[j + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = v[j];
+  }
+}
+// Orders every later use of v[] after the preceding tcgen05.wait::ld (volatile asm statements keep their order; the
+// loads that fill v[] were issued a whole pass earlier).
+__device__ __forceinline__ void pin8(float (&v)[8]) {
+  asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
+}
+
 template <int NS, int NG, int REC, int OD>
 __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid_constant__ LstmTcParams P) {
   constexpr int NW = kRows * NG;           // threads: one per sequence
@@ -333,39 +351,46 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
         float yacc[OD];
 #pragma unroll
         for (int d = 0; d < OD; ++d) yacc[d] = 0.0f;
+        // 8 hidden units per pass; the accumulator columns of pass p+1 are in flight (tcgen05.ld) during the math of p
+        float gt[2][4][8];
 #pragma unroll
-        for (int p16 = 0; p16 < 4; ++p16) {
-          float gt[4][16];
+        for (int gi = 0; gi < 4; ++gi) tmem_ld8(t_row + gi * kH, gt[0][gi]);
+        tmem_ld_wait();
 #pragma unroll
-          for (int gi = 0; gi < 4; ++gi) tmem_ld16(t_row + gi * kH + p16 * 16, gt[gi]);
-          tmem_ld_wait();
-          float hn[16];
+        for (int gi = 0; gi < 4; ++gi) pin8(gt[0][gi]);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int u = p16 * 16 + j;
+        for (int p8 = 0; p8 < 8; ++p8) {
+          float (&ga)[4][8] = gt[p8 & 1];
+          if (p8 + 1 < 8) {
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) tmem_ld8(t_row + gi * kH + (p8 + 1) * 8, gt[(p8 + 1) & 1][gi]);
+          }
+          float hn[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int u = p8 * 8 + j;
             const float4 bb = bk->bias4[u];
             float ai, af, ao;
             if (REC == FOV_REC_HARD_SIGMOID) {
-              ai = __saturatef(fmaf(0.2f, gt[0][j], bb.x));
-              af = __saturatef(fmaf(0.2f, gt[1][j], bb.y));
-              ao = __saturatef(fmaf(0.2f, gt[3][j], bb.w));
+              ai = __saturatef(fmaf(0.2f, ga[0][j], bb.x));
+              af = __saturatef(fmaf(0.2f, ga[1][j], bb.y));
+              ao = __saturatef(fmaf(0.2f, ga[3][j], bb.w));
             } else {
-              ai = rcp_approx(1.0f + ex2_approx(fmaf(-1.442695041f, gt[0][j], bb.x)));
-              af = rcp_approx(1.0f + ex2_approx(fmaf(-1.442695041f, gt[1][j], bb.y)));
-              ao = rcp_approx(1.0f + ex2_approx(fmaf(-1.442695041f, gt[3][j], bb.w)));
+              ai = rcp_approx(1.0f + ex2_approx(fmaf(-1.442695041f, ga[0][j], bb.x)));
+              af = rcp_approx(1.0f + ex2_approx(fmaf(-1.442695041f, ga[1][j], bb.y)));
+              ao = rcp_approx(1.0f + ex2_approx(fmaf(-1.442695041f, ga[3][j], bb.w)));
             }
-            const float ag = tanh5(gt[2][j] + bb.z);
+            const float ag = tanh5(ga[2][j] + bb.z);
             const float cn = fmaf(af, c[u], ai * ag);
             c[u] = cn;
             hn[j] = ao * tanh5(cn);
-            gt[0][j] = ai; gt[1][j] = af; gt[2][j] = ag; gt[3][j] = ao;
+            ga[0][j] = ai; ga[1][j] = af; ga[2][j] = ag; ga[3][j] = ao;
           }
-          h_store8(p16 * 2, hn);
-          h_store8(p16 * 2 + 1, hn + 8);
+          h_store8(p8, hn);
           if (ph.has_head) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float4* wr = reinterpret_cast<const float4*>(&bk->Wo_s[(p16 * 16 + j) * OD]);
+            for (int j = 0; j < 8; ++j) {
+              const float4* wr = reinterpret_cast<const float4*>(&bk->Wo_s[(p8 * 8 + j) * OD]);
 #pragma unroll
               for (int d4 = 0; d4 < OD / 4; ++d4) {
                 const float4 w4 = wr[d4];
@@ -378,17 +403,22 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
           }
           if (gates_p) {
 #pragma unroll
-            for (int gi = 0; gi < 4; ++gi) store16(gates_p + gi * kH + p16 * 16, gt[gi], 4);
+            for (int gi = 0; gi < 4; ++gi) store8(gates_p + gi * kH + p8 * 8, ga[gi], 4);
           }
           if (c_p) {
-            float cv[16];
+            float cv[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) cv[j] = c[p16 * 16 + j];
-            store16(c_p + p16 * 16, cv, 4);
+            for (int j = 0; j < 8; ++j) cv[j] = c[p8 * 8 + j];
+            store8(c_p + p8 * 8, cv, 4);
           }
-          if (hseq_p) store16(hseq_p + p16 * 16, hn, 4);
-          if (xh_next) store16(xh_next + p16 * 16, hn, xh_next_vec);
-          if (hT_p) store16(hT_p + p16 * 16, hn, 4);
+          if (hseq_p) store8(hseq_p + p8 * 8, hn, 4);
+          if (xh_next) store8(xh_next + p8 * 8, hn, xh_next_vec);
+          if (hT_p) store8(hT_p + p8 * 8, hn, 4);
+          if (p8 + 1 < 8) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) pin8(gt[(p8 + 1) & 1][gi]);
+          }
         }
         tc_fence_before();                 // my tcgen05.ld of this accumulator are complete before the next MMAs
         if (dbg) { k2 = clock64(); ta += k2 - k1; }

@@ -134,6 +134,124 @@ def test_lstm_seq2seq_gradients(tf, in_enc, B):
         _grad_close(m.grads[k].cpu().numpy(), g_ref[k].numpy(), k)
 
 
+# ------------------------------------------------------------------ fc-LSTM on tensor cores
+
+@pytest.fixture
+def force_lstm_tc():
+    """Route every fc-LSTM forward whose shape allows it through the tcgen05 kernel (lstm_seq2seq_tc.cu),
+    whatever the batch size; restored afterwards."""
+    import ctypes
+    from longterm360fov_b200 import _lib
+    lib = _lib.load()
+    lib.fov_debug_lstm_tc.argtypes = [ctypes.c_int]
+    lib.fov_debug_lstm_tc(1)
+    yield lib
+    lib.fov_debug_lstm_tc(0)
+
+
+@pytest.mark.parametrize("B", [1, 130, 300])
+@pytest.mark.parametrize("tf", [True, False])
+@pytest.mark.parametrize("kw", [{}, {"recurrent_activation": "sigmoid"}, {"decoder_no_init_state": True}])
+def test_lstm_tensor_core_forward(B, tf, kw, force_lstm_tc):
+    """Encoder + teacher-forced / autoregressive decoder on tcgen05 (two bf16 terms per operand) against the
+    float64 oracle at the north-star bar, and against the fp32 kernel."""
+    fov = _cuda()
+    rng = np.random.default_rng(B + 7)
+    w = _perturb(kn.init_fov_seq2seq(seed=2, num_encoder_tokens=6), 3)
+    enc = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 10 if tf else 1, 6)).astype(np.float32)
+    ref = kn.fov_seq2seq_forward({k: v.astype(np.float64) for k, v in w.items()}, enc.astype(np.float64),
+                                 dec.astype(np.float64), teacher_forcing=tf, **kw)
+    m = fov.fov_seq2seq_mu_var(teacher_forcing=tf, weights=w, **kw)
+    n0 = force_lstm_tc.fov_launch_count()
+    got = m.predict([enc, dec], batch_size=B)
+    assert force_lstm_tc.fov_launch_count() == n0 + 1          # ONE launch for all 20 timesteps
+    assert np.abs(got - ref).max() < 1e-5                      # far inside FWD_ATOL
+    force_lstm_tc.fov_debug_lstm_tc(-1)
+    fp32 = m.predict([enc, dec], batch_size=B)
+    assert np.abs(got - fp32).max() < 1e-5
+    m.set_compute("bf16")                                      # one term: the stated bf16 tolerance
+    force_lstm_tc.fov_debug_lstm_tc(1)
+    assert np.abs(m.predict([enc, dec], batch_size=B) - ref).max() < BF16_ATOL
+
+
+def test_lstm_tensor_core_two_groups_per_cta_and_submodels(force_lstm_tc):
+    """B > 128 x 148 runs two 128-sequence groups per CTA; encoder_model / decoder_model (T_dec = 0 / T_enc = 0,
+    given initial state, final state out) chain to the same result as the single launch."""
+    fov = _cuda()
+    rng = np.random.default_rng(3)
+    B = 128 * 148 + 77
+    w = _perturb(kn.init_fov_seq2seq(seed=2, num_encoder_tokens=6), 3)
+    enc = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 1, 6)).astype(np.float32)
+    ref = kn.fov_seq2seq_forward({k: v.astype(np.float64) for k, v in w.items()}, enc.astype(np.float64),
+                                 dec.astype(np.float64), teacher_forcing=False)
+    m = fov.fov_seq2seq_mu_var(teacher_forcing=False, weights=w)
+    got = m.predict([enc, dec], batch_size=B)
+    assert np.abs(got - ref).max() < 1e-5
+    states = m.encoder_model.predict(enc[:300])
+    target, outs = dec[:300], []
+    for _ in range(10):
+        y, h, c = m.decoder_model.predict([target] + states)
+        outs.append(y); target = y; states = [h, c]
+    assert np.abs(np.concatenate(outs, axis=1) - got[:300]).max() < 1e-5
+
+
+@pytest.mark.parametrize("tf,B", [(True, 37), (False, 200)])
+def test_lstm_tensor_core_forward_feeds_bptt(tf, B, force_lstm_tc):
+    """Training mode: the saved tensors written by the tensor-core forward ([h|x] rows, activated gates, cell
+    states, h sequence) drive the BPTT kernel to the oracle's loss and gradients."""
+    fov = _cuda()
+    rng = np.random.default_rng(11)
+    w = _perturb(kn.init_fov_seq2seq(seed=4, num_encoder_tokens=6), 5, 0.1)
+    enc = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 10 if tf else 1, 6)).astype(np.float32)
+    tgt = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    m = fov.fov_seq2seq_mu_var(teacher_forcing=tf, weights=w).compile("Adam", "mean_squared_error")
+    xs, ys = m._to_dev([enc, dec]), m._to_dev([tgt])
+    m.gflat.zero_()
+    loss = m._loss(m._forward(xs, True), ys)
+    loss.backward()
+    l_ref, _, g_ref = kt.loss_and_grads(lambda ww, a, b: kt.fov_seq2seq_forward(ww, a, b, teacher_forcing=tf),
+                                        kt.to_torch(w),
+                                        [torch.tensor(enc, dtype=torch.float64), torch.tensor(dec, dtype=torch.float64)],
+                                        [torch.tensor(tgt, dtype=torch.float64)], [kt.mse])
+    assert abs(loss.item() - l_ref.item()) < 1e-5
+    for k in m.weight_order:
+        _grad_close(m.grads[k].cpu().numpy(), g_ref[k].numpy(), k)
+
+
+def test_m3_with_tensor_core_target_lstm(force_lstm_tc):
+    """Config 2's graph with the target fc-LSTM on tensor cores (additive head term from the others branch,
+    encoder h sequence read by the reconstruction head): forward + gradients against the oracle."""
+    fov = _cuda()
+    rng = np.random.default_rng(21)
+    B, num_user = 9, 7
+    w = _perturb(kn.init_others_lstm_span_whole(seed=3, num_user=num_user), 6, 0.02)
+    enc, oth, dec, tg = _m3_data(rng, B, num_user - 1)
+    m = fov.others_lstm_span_whole(num_user=num_user, weights=w).compile("Adam", ["mean_squared_error"] * 3, [1, 1, 1])
+    n0 = force_lstm_tc.fov_launch_count()
+    got = m.predict_on_batch([enc, oth, dec])
+    n_tc = force_lstm_tc.fov_launch_count() - n0
+    force_lstm_tc.fov_debug_lstm_tc(-1)
+    n0 = force_lstm_tc.fov_launch_count()
+    m.predict_on_batch([enc, oth, dec])
+    assert force_lstm_tc.fov_launch_count() - n0 == n_tc       # same launch count either way: one LSTM launch
+    force_lstm_tc.fov_debug_lstm_tc(1)
+    t64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    l_ref, outs_ref, g_ref = kt.loss_and_grads(kt.others_lstm_span_whole_forward, kt.to_torch(w),
+                                               [t64(enc), t64(oth), t64(dec)], [t64(t) for t in tg], [kt.mse] * 3)
+    for a, b in zip(got, outs_ref):
+        assert np.abs(a - b.numpy()).max() < FWD_ATOL / 2
+    xs, ys = m._to_dev([enc, oth, dec]), m._to_dev(tg)
+    m.gflat.zero_()
+    loss = m._loss(m._forward(xs, True), ys)
+    loss.backward()
+    assert abs(loss.item() - l_ref.item()) < 5e-5
+    for k in m.weight_order:
+        _grad_close(m.grads[k].cpu().numpy(), g_ref[k].numpy(), k)
+
+
 # ------------------------------------------------------------------ conv family
 
 CONV_CASES = [
