@@ -239,17 +239,25 @@ def other_workloads(dev, peaks, compute):
     #      ONE persistent launch = 10 encoder + 10 decoder steps (Dense+tanh inside the recurrence) ----
     Bi = 148 * 64 * 8
     m2 = fov.fov_seq2seq_mu_var(seed=3, device=dev)
+    m2.set_compute(compute)
+    from longterm360fov_b200 import ops as _ops
+    _ops.set_math(compute)
     enc = torch.randn(Bi, 10, 6, device=dev) * 0.3
     last = enc[:, -1:, :].contiguous()
     with torch.no_grad():
         ms = _time_cuda(lambda: m2._forward([enc, last], False, teacher_forcing=False, steps=10), reps=10, warm=3)
     flop = Bi * (10 * 2 * (6 + 64) * 256 + 10 * (2 * (6 + 64) * 256 + 2 * 64 * 6))
-    byts = Bi * (10 * 6 + 6 + 10 * 6 + 10 * 64) * 4           # inputs + outputs (+ the encoder h sequence it emits)
+    byts = Bi * (10 * 6 + 6 + 10 * 6) * 4                     # inputs + outputs
     res["fov_seq2seq_mu_var_autoregressive_infer"] = {
         "batch": Bi, "unit": "sequences/s", "value": Bi / (ms * 1e-3), "ms_per_launch": ms,
-        "us_per_timestep_per_cta_wave": 1e3 * ms / 20 / max(1, -(-Bi // 64) / 148.0),
-        "fp32_tflops": flop / (ms * 1e-3) / 1e12, "hbm_gbs": byts / (ms * 1e-3) / 1e9,
-        "note": "latency/FMA-bound persistent recurrence (fp32 CUDA cores, weights resident in shared memory)"}
+        "us_per_timestep_per_cta_wave": 1e3 * ms / 20 / max(1, -(-Bi // (64 if compute == "fp32" else 256)) / 148.0),
+        "algorithmic_tflops": flop / (ms * 1e-3) / 1e12, "hbm_gbs": byts / (ms * 1e-3) / 1e9,
+        "issued_bf16_tflops": (3 if compute == "bf16x2" else {"bf16": 1, "bf16x3": 6}.get(compute, 0)) *
+                              Bi * 20 * 2 * (16 + 64) * 256 / (ms * 1e-3) / 1e12,
+        "compute": compute,
+        "note": "persistent recurrence, ONE launch: tcgen05 gate GEMM per step (weights + h resident on the SM, "
+                "Dense+tanh head and re-feed in the epilogue) unless compute=fp32; bound by the gate algebra "
+                "(MUFU/issue), not by HBM or the tensor pipe"}
 
     # ---- config 2 at the reference's own batch size (32): launch-bound, eager vs CUDA-graph replay ----
     Bs = 32
@@ -267,6 +275,23 @@ def other_workloads(dev, peaks, compute):
     res["others_lstm_span_whole_train_batch32"] = dict(small, batch=Bs, unit="sequences/s",
                                                        note="the reference's batch size; the step is launch bound, "
                                                             "model.enable_cuda_graphs() replays forward + BPTT from one graph")
+
+    # ---- sample builders: windows of a full-size video, one-hot heatmaps; HBM-bound ----
+    from longterm360fov_b200 import ops as _o
+    vid = torch.rand(48, 600, 90, device=dev) * 2 - 1
+    ms = _time_cuda(lambda: _o.reshape2second_stacks(vid, collapse_user=False, stride=1), reps=10, warm=3)
+    nwin = 600 - 10 + 1 - 10
+    wbytes = 3 * nwin * 48 * 10 * 90 * 4                      # three window tensors written; the source stays in L2
+    fr = torch.nn.functional.normalize(torch.randn(4096, 30, 3, device=dev), dim=-1)
+    ms_h = _time_cuda(lambda: _o.one_hot_heatmaps(fr), reps=10, warm=3)
+    hbytes = 4096 * 36 * 18 * 30 * 4
+    res["sample_builders"] = {
+        "window_stacks": {"shape": "48 viewers x 600 s x 90, stride 1", "windows_per_s": nwin * 48 / (ms * 1e-3),
+                          "ms": ms, "hbm_gbs": wbytes / (ms * 1e-3) / 1e9, "frac_of_copy_peak": wbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+        "one_hot_heatmaps": {"shape": "4096 seconds x 30 frames -> (36,18,30)", "heatmaps_per_s": 4096 / (ms_h * 1e-3),
+                             "ms": ms_h, "hbm_gbs": hbytes / (ms_h * 1e-3) / 1e9,
+                             "frac_of_copy_peak": hbytes / (ms_h * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+    del vid, fr
 
     # ---- config 1 model (FoV_seq2seq, teacher forcing) training on the GPU ----
     Bt = 8192

@@ -266,6 +266,25 @@ int fov_gate_kernel_expand(int taps, int Cin, int F, const float* kernel, float*
 /* g_kernel[tap,c,n] += g_kernel4[tap, gate(n)*Cin + c, n] */
 int fov_gate_kernel_reduce(int taps, int Cin, int F, const float* g_kernel4, float* g_kernel, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Sample builders just before the hot path.
+ * ------------------------------------------------------------------------- */
+/* reshape2second_stacks (mycode/utility.py:264-305): per-video seconds src (U,S,C) -> windows of L =
+ * cfg.running_length seconds every `stride` seconds; future = the window L//stride rows later; future_input =
+ * [last past second, future[:-1]].  purely_testing appends L//stride zero seconds (cfg.purelly_testing).
+ * Outputs, n = fov_window_count(): collapse_user=1 (n*U, L, C) window-major; 0: (U, n, L, C). */
+int fov_window_count(int S, int L, int stride, int purely_testing);
+int fov_window_stacks(int U, int S, int C, int L, int stride, int purely_testing, int collapse_user,
+                      const float* src, float* past, float* future, float* future_input, void* stream);
+/* get_whole_span (mycode/others_LSTM_span_whole.py:403-419): x (N, half) rows (half = L * everything after the
+ * time axis) -> out (N, 2*half): out[i] = [x[i] ; x[i+1]], the last row is all zero. */
+int fov_whole_span(long long N, long long half, const float* x, float* out, void* stream);
+/* One-hot FoV-centre heatmaps: xyz (rows, frames, 3) -> out (rows, 360/bin, 180/bin, frames), one 1 per frame at
+ * (theta bin, phi bin) with theta, phi of mycode/dataIO.py:77-82 and the binning of mycode/utility.py:533-539,
+ * _create_one_hot :546-556; frames stacked as channels as mycode/data_generator_for_heatmap.py:32,65-67 feeds them.
+ * Angles are evaluated in float64 so the bin indices equal NumPy's. */
+int fov_onehot_heatmaps(long long rows, int frames, int bin_size, const float* xyz, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,6 +117,10 @@ SYMBOLS = {
     "fov_dropout_reduce": (_I, [_I, _I, _I, _I, _P, _P, _P, _LL, _LL, _I, _I, _P]),
     "fov_gate_kernel_expand": (_I, [_I, _I, _I, _P, _P, _P]),
     "fov_gate_kernel_reduce": (_I, [_I, _I, _I, _P, _P, _P]),
+    "fov_window_count": (_I, [_I, _I, _I, _I]),
+    "fov_window_stacks": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "fov_whole_span": (_I, [_LL, _LL, _P, _P, _P]),
+    "fov_onehot_heatmaps": (_I, [_LL, _I, _I, _P, _P, _P]),
 }
 
 _lib = None

@@ -633,3 +633,53 @@ def gauss_resample(muvar, noise, mode="sqrt_floor"):
     _lib.check(lib.fov_gauss_resample(muvar.shape[0], m, ptr(muvar), ptr(noise), ptr(out), _stream()),
                "fov_gauss_resample")
     return out
+
+
+# --------------------------------------------------------------------------- #
+# sample builders: windows, whole spans, one-hot heatmaps on the device
+# --------------------------------------------------------------------------- #
+
+
+def reshape2second_stacks(per_video_db, collapse_user=False, stride=10, running_length=10, purelly_testing=False):
+    """mycode/utility.py:264-305 on the device: (U,S,C) seconds of one video -> (past, future, future_input)
+    windows, shapes (n*U, L, C) when ``collapse_user`` else (U, n, L, C)."""
+    lib = _lib.load()
+    _require_cuda(per_video_db)
+    src = _f32c(per_video_db)
+    U, S, Cc = src.shape
+    n = lib.fov_window_count(S, running_length, stride, int(purelly_testing))
+    if n <= 0:
+        raise _lib.FovError("reshape2second_stacks: %d seconds give no complete window of 2 x %d" % (S, running_length))
+    shape = (n * U, running_length, Cc) if collapse_user else (U, n, running_length, Cc)
+    past, fut, fut_in = (torch.empty(shape, device=src.device) for _ in range(3))
+    _lib.check(lib.fov_window_stacks(U, S, Cc, running_length, stride, int(purelly_testing), int(collapse_user),
+                                     ptr(src), ptr(past), ptr(fut), ptr(fut_in), _stream()), "fov_window_stacks")
+    return past, fut, fut_in
+
+
+def get_whole_span(x):
+    """mycode/others_LSTM_span_whole.py:403-419 on the device: (N, L, ...) -> (N, 2L, ...), row i = [x[i]; x[i+1]],
+    last row zero (unshuffled data only, as the reference asserts)."""
+    lib = _lib.load()
+    _require_cuda(x)
+    x = _f32c(x)
+    N = x.shape[0]
+    half = x[0].numel()
+    out = torch.empty((N, 2 * x.shape[1]) + tuple(x.shape[2:]), device=x.device)
+    _lib.check(lib.fov_whole_span(N, half, ptr(x), ptr(out), _stream()), "fov_whole_span")
+    return out
+
+
+def one_hot_heatmaps(frames, bin_size=10):
+    """(..., F, 3) xyz frames -> (..., 360/bin, 180/bin, F) one-hot FoV-centre maps, frames as channels
+    (mycode/dataIO.py:77-82, mycode/utility.py:533-556, mycode/data_generator_for_heatmap.py:32,65-67)."""
+    lib = _lib.load()
+    _require_cuda(frames)
+    frames = _f32c(frames)
+    lead, Fr = frames.shape[:-2], frames.shape[-2]
+    rows = 1
+    for d in lead:
+        rows *= d
+    out = torch.empty(*lead, 360 // bin_size, 180 // bin_size, Fr, device=frames.device)
+    _lib.check(lib.fov_onehot_heatmaps(rows, Fr, bin_size, ptr(frames), ptr(out), _stream()), "fov_onehot_heatmaps")
+    return out

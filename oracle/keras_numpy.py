@@ -226,14 +226,19 @@ def gaussian_resample(mu, var, noise, mode="sqrt_floor"):
     return mu[:, None, :] + std[:, None, :] * noise
 
 
-def reshape2second_stacks(per_video_db, collapse_user=False, stride=10, running_length=10):
-    """mycode/utility.py:264-305 (purelly_testing=False): sliding windows of
-    ``running_length`` seconds with stride ``stride``; future = windows shifted by
-    running_length//stride; decoder input = [last past second, future[:-1]]."""
+def reshape2second_stacks(per_video_db, collapse_user=False, stride=10, running_length=10,
+                          purelly_testing=False):
+    """mycode/utility.py:264-305: sliding windows of ``running_length`` seconds with
+    stride ``stride``; future = windows shifted by running_length//stride; decoder
+    input = [last past second, future[:-1]]; ``purelly_testing`` appends
+    running_length//stride zero seconds first (:274-277)."""
     L = running_length
     n_tok = per_video_db.shape[-1]
     assert per_video_db.shape[1] >= 2 * L
     shift = L // stride
+    if purelly_testing:
+        per_video_db = np.concatenate(
+            (per_video_db, np.zeros((per_video_db.shape[0], shift, per_video_db.shape[2]))), axis=1)
     nrows = (per_video_db.shape[1] - L) // stride + 1
     idx = stride * np.arange(nrows)[:, None] + np.arange(L)
     win = per_video_db[:, idx, :].transpose(1, 0, 2, 3)        # (nrows, users, L, tok)
@@ -246,6 +251,43 @@ def reshape2second_stacks(per_video_db, collapse_user=False, stride=10, running_
                 fut_in.reshape(-1, L, n_tok))
     return (past.transpose(1, 0, 2, 3), fut.transpose(1, 0, 2, 3),
             fut_in.transpose(1, 0, 2, 3))
+
+
+def get_whole_span(x):
+    """mycode/others_LSTM_span_whole.py:403-419: (N,L,...) -> (N,2L,...), row i =
+    [x[i]; x[i+1]]; the last row stays zero."""
+    out = np.zeros((x.shape[0], 2 * x.shape[1]) + x.shape[2:], x.dtype)
+    out[:-1] = np.concatenate((x[:-1], x[1:]), axis=1)
+    return out
+
+
+def xyz2thetaphi(x, y, z):
+    """mycode/dataIO.py:77-82: theta in [-pi,pi), phi in [0,pi)."""
+    theta = np.mod(np.arctan2(y, x), 2 * np.pi) - np.pi
+    phi = np.mod(np.arctan2(z, np.sqrt(x ** 2 + y ** 2)) + np.pi / 2, np.pi)
+    return theta, phi
+
+
+def theta_phi_index(frames, bin_size=10):
+    """mycode/utility.py:520-539: (...,F,3) xyz -> integer (theta_index, phi_index)."""
+    theta, phi = xyz2thetaphi(frames[..., 0], frames[..., 1], frames[..., 2])
+    ti = np.floor((theta + np.pi) / np.pi * 180 / bin_size)
+    ti[ti == 360 / bin_size] -= 1
+    pj = np.floor(phi / np.pi * 180 / bin_size)
+    pj[pj == 180 / bin_size] -= 1
+    return ti.astype(np.int64), pj.astype(np.int64)
+
+
+def one_hot_heatmaps(frames, bin_size=10):
+    """_create_one_hot (mycode/utility.py:546-556) of the indices above, then frames
+    as channels (mycode/data_generator_for_heatmap.py:32,65-67):
+    (N,T,F,3) -> (N,T,360/bin,180/bin,F)."""
+    ti, pj = theta_phi_index(frames, bin_size)
+    N, T, Fr = ti.shape
+    one_hot = np.zeros((N, T, Fr, 360 // bin_size, 180 // bin_size))
+    n, t, f = np.meshgrid(np.arange(N), np.arange(T), np.arange(Fr), indexing="ij")
+    one_hot[n, t, f, ti, pj] = 1
+    return one_hot.transpose(0, 1, 3, 4, 2)
 
 
 # --------------------------------------------------------------------------- #

@@ -12,7 +12,12 @@ repo: only the outputs are stored (``reference_numpy_golden.npz``).
 
 Functions executed: ``get_gt_target_xyz`` (utility.py:483-500),
 ``get_gt_target_xyz_oth`` (:505-517), ``reshape2second_stacks`` (:264-305),
-``generate_fake_batch_numpy`` (:73-80).
+``generate_fake_batch_numpy`` (:73-80), ``_create_one_hot`` (:546-556, its Python-2
+float shape ``(360/bin_size)`` is cast to int by an ``np.zeros`` shim),
+``xyz2thetaphi`` (dataIO.py:77-82), ``get_whole_span``
+(others_LSTM_span_whole.py:403-419) and the index statements of the nested
+``_theta_phi_index_for_onehot`` (utility.py:520-539; its two ``pickle.dump`` lines
+are dropped and ``return theta_index, phi_index`` is appended).
 """
 import ast
 import os
@@ -35,6 +40,45 @@ def load_reference_functions():
         if isinstance(node, ast.FunctionDef) and node.name in WANT:
             code = compile(ast.Module([node], type_ignores=[]), REF, "exec")
             exec(code, ns)
+    return ns
+
+
+class _NpShim:
+    """numpy with ``zeros`` accepting the Python-2 style float shapes of _create_one_hot."""
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+    @staticmethod
+    def zeros(shape, *a, **k):
+        return np.zeros(tuple(int(v) for v in shape) if isinstance(shape, tuple) else shape, *a, **k)
+
+
+def load_heatmap_functions():
+    """_create_one_hot + the nested _theta_phi_index_for_onehot (utility.py), xyz2thetaphi (dataIO.py),
+    get_whole_span (others_LSTM_span_whole.py), all executed from the reference's own source."""
+    ns = {"np": _NpShim()}
+    dio = ast.parse(open("/root/reference/mycode/dataIO.py").read())
+    for node in dio.body:
+        if isinstance(node, ast.FunctionDef) and node.name == "xyz2thetaphi":
+            exec(compile(ast.Module([node], type_ignores=[]), "dataIO.py", "exec"), ns)
+    tree = ast.parse(open(REF).read())
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == "_create_one_hot":
+            exec(compile(ast.Module([node], type_ignores=[]), REF, "exec"), ns)
+        if isinstance(node, ast.FunctionDef) and node.name == "_save_theta_phi_index":
+            inner = [n for n in node.body if isinstance(n, ast.FunctionDef)][0]
+            body = [st for st in inner.body
+                    if not (isinstance(st, ast.Expr) and isinstance(st.value, ast.Call) and
+                            "pickle" in ast.unparse(st.value.func))]
+            ret = ast.parse("return theta_index, phi_index").body[0]
+            inner.body = body + [ret]
+            ast.fix_missing_locations(inner)
+            exec(compile(ast.Module([inner], type_ignores=[]), REF, "exec"), ns)
+    span = ast.parse(open("/root/reference/mycode/others_LSTM_span_whole.py").read())
+    for node in span.body:
+        if isinstance(node, ast.FunctionDef) and node.name == "get_whole_span":
+            exec(compile(ast.Module([node], type_ignores=[]), "others_LSTM_span_whole.py", "exec"), ns)
     return ns
 
 
@@ -68,6 +112,32 @@ def main():
     np.random.seed(7)
     noise = np.array([np.random.normal(0.0, 1.0, 30) for _ in range(6)])
     out["fake_mu"], out["fake_var"], out["fake_noise"], out["fake_out"] = mu, var, noise, samp
+    # ---- added after the cases above (their random draws stay what they were) ----
+    vid90 = rng.uniform(-1, 1, (2, 27, 90))
+    out["stack90_in"] = vid90
+    for stride, testing in ((10, True), (1, True), (5, False)):
+        for collapse in (True, False):
+            a, b, c = ns["reshape2second_stacks"](vid90.copy(), collapse_user=collapse, stride=stride,
+                                                  purelly_testing=testing)
+            tag = "stack90_s%d_t%d_c%d" % (stride, int(testing), int(collapse))
+            out[tag + "_past"], out[tag + "_fut"], out[tag + "_futin"] = a, b, c
+    hs = load_heatmap_functions()
+    hs["cfg"] = types.SimpleNamespace(shuffle_data=False)
+    hs["num_user"] = 5
+    oth = rng.uniform(-1, 1, (7, 10, 4, 6))                       # (N, 10, num_user-1, 6)
+    out["span_in"], out["span_out"] = oth, hs["get_whole_span"](oth.copy())
+    oth5 = rng.uniform(-1, 1, (3, 10, 4, 30, 3))
+    out["span5_in"], out["span5_out"] = oth5, hs["get_whole_span"](oth5.copy())
+    # unit vectors incl. the poles, the theta wrap and exact bin edges
+    v = rng.normal(size=(3, 4, 30, 3))
+    v /= np.linalg.norm(v, axis=-1, keepdims=True)
+    v[0, 0, :6] = [[0, 0, 1], [0, 0, -1], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0]]
+    v[0, 1, 0] = [-1.0, -1e-12, 0.0]
+    v[0, 1, 1] = [np.cos(np.deg2rad(40.0)), np.sin(np.deg2rad(40.0)), 0.0]
+    v = v.astype(np.float32).astype(np.float64)                   # the device sees float32 inputs
+    ti, pj = hs["_theta_phi_index_for_onehot"](v)
+    out["onehot_in"], out["onehot_theta"], out["onehot_phi"] = v, ti, pj
+    out["onehot_out"] = hs["_create_one_hot"](ti, pj).transpose(0, 1, 3, 4, 2)   # frames as channels
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_numpy_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items()})

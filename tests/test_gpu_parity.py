@@ -56,6 +56,89 @@ def test_featuriser_and_resampler_match_reference_golden(golden):
     np.testing.assert_allclose(out[:, :, 0], golden["fake_out"], atol=2e-6)
 
 
+# ------------------------------------------------------------------ sample builders (windows, spans, heatmaps)
+
+@pytest.mark.parametrize("stride,collapse", [(10, True), (10, False), (1, True), (1, False), (2, True), (2, False)])
+def test_window_stacks_match_reference_golden(golden, stride, collapse):
+    """reshape2second_stacks on the device is a pure gather: bit-exact against the reference's own output."""
+    _cuda()
+    from longterm360fov_b200 import ops
+    src = torch.tensor(golden["stack_in"], dtype=torch.float32, device="cuda")
+    got = ops.reshape2second_stacks(src, collapse_user=collapse, stride=stride)
+    tag = "stack_s%d_c%d" % (stride, int(collapse))
+    for g, name in zip(got, ("_past", "_fut", "_futin")):
+        assert np.array_equal(g.cpu().numpy(), golden[tag + name].astype(np.float32))
+
+
+@pytest.mark.parametrize("stride,testing", [(10, True), (1, True), (5, False)])
+@pytest.mark.parametrize("collapse", [True, False])
+def test_window_stacks_raw_frames_and_purely_testing(golden, stride, testing, collapse):
+    _cuda()
+    from longterm360fov_b200 import ops
+    src = torch.tensor(golden["stack90_in"], dtype=torch.float32, device="cuda")
+    got = ops.reshape2second_stacks(src, collapse_user=collapse, stride=stride, purelly_testing=testing)
+    tag = "stack90_s%d_t%d_c%d" % (stride, int(testing), int(collapse))
+    for g, name in zip(got, ("_past", "_fut", "_futin")):
+        assert np.array_equal(g.cpu().numpy(), golden[tag + name].astype(np.float32))
+    with pytest.raises(Exception):
+        ops.reshape2second_stacks(src[:, :19], stride=stride)             # < 2 x running_length seconds
+
+
+def test_window_stacks_large_video_against_oracle_and_properties():
+    """A full-size video (48 viewers x 600 s x 90): oracle equality, plus the properties the layout implies:
+    future of window i == past of window i + shift; future_input[:, 1:] == future[:, :-1]."""
+    _cuda()
+    from longterm360fov_b200 import ops
+    rng = np.random.default_rng(0)
+    vid = rng.uniform(-1, 1, (48, 600, 90)).astype(np.float32)
+    for stride, collapse in ((1, False), (10, True), (3, False)):       # C=90 rows are 8-byte aligned: float2 path
+        past, fut, fin = ops.reshape2second_stacks(torch.tensor(vid).cuda(), collapse_user=collapse, stride=stride)
+        a, b, c = kn.reshape2second_stacks(vid, collapse_user=collapse, stride=stride)
+        assert np.array_equal(past.cpu().numpy(), a) and np.array_equal(fut.cpu().numpy(), b)
+        assert np.array_equal(fin.cpu().numpy(), c)
+        if not collapse:
+            shift = 10 // stride
+            assert torch.equal(fut[:, :-shift], past[:, shift:])
+            assert torch.equal(fin[:, :, 1:], fut[:, :, :-1]) and torch.equal(fin[:, :, 0], past[:, :, -1])
+    odd = rng.uniform(-1, 1, (3, 25, 7)).astype(np.float32)              # odd row width: scalar path
+    got = ops.reshape2second_stacks(torch.tensor(odd).cuda(), stride=5)
+    for g, r in zip(got, kn.reshape2second_stacks(odd, stride=5)):
+        assert np.array_equal(g.cpu().numpy(), r)
+
+
+def test_whole_span_matches_reference_golden(golden):
+    _cuda()
+    from longterm360fov_b200 import ops
+    for key in ("span", "span5"):
+        x = torch.tensor(golden[key + "_in"], dtype=torch.float32, device="cuda")
+        got = ops.get_whole_span(x).cpu().numpy()
+        assert np.array_equal(got, golden[key + "_out"].astype(np.float32))
+    one = torch.rand(1, 10, 3, device="cuda")                               # single row: all zero
+    assert not ops.get_whole_span(one).any()
+    odd = torch.rand(5, 3, 7, device="cuda")                                # 21 floats per row: scalar path
+    assert np.array_equal(ops.get_whole_span(odd).cpu().numpy(), kn.get_whole_span(odd.cpu().numpy()))
+
+
+def test_one_hot_heatmaps_match_reference_golden(golden):
+    """Bin indices are integer work: bit-exact against the reference's theta/phi indices and one-hot tensor
+    (poles, the theta wrap and an exact bin edge included); at full size every frame lights exactly one cell."""
+    _cuda()
+    from longterm360fov_b200 import ops
+    x = torch.tensor(golden["onehot_in"], dtype=torch.float32, device="cuda")
+    got = ops.one_hot_heatmaps(x).cpu().numpy()
+    assert got.shape == golden["onehot_out"].shape
+    assert np.array_equal(got, golden["onehot_out"].astype(np.float32))
+    rng = np.random.default_rng(5)
+    v = rng.normal(size=(64, 10, 30, 3))
+    v = (v / np.linalg.norm(v, axis=-1, keepdims=True)).astype(np.float32)
+    big = ops.one_hot_heatmaps(torch.tensor(v).cuda())
+    assert big.shape == (64, 10, 36, 18, 30)
+    assert torch.equal(big.sum(dim=(2, 3)), torch.ones(64, 10, 30, device="cuda"))
+    assert np.array_equal(big.cpu().numpy(), kn.one_hot_heatmaps(v.astype(np.float64)).astype(np.float32))
+    coarse = ops.one_hot_heatmaps(torch.tensor(v[:2]).cuda(), bin_size=30)   # 12 x 6 grid
+    assert np.array_equal(coarse.cpu().numpy(), kn.one_hot_heatmaps(v[:2].astype(np.float64), 30).astype(np.float32))
+
+
 # ------------------------------------------------------------------ fc-LSTM
 
 @pytest.mark.parametrize("B", [1, 7, 33, 70])

@@ -30,6 +30,31 @@ def test_windowing_matches_reference_golden(golden, stride, collapse):
     assert np.array_equal(c, golden[tag + "_futin"])
 
 
+@pytest.mark.parametrize("stride,testing", [(10, True), (1, True), (5, False)])
+@pytest.mark.parametrize("collapse", [True, False])
+def test_windowing_purely_testing_and_raw_frames_match_reference_golden(golden, stride, testing, collapse):
+    a, b, c = kn.reshape2second_stacks(golden["stack90_in"], collapse_user=collapse, stride=stride,
+                                       purelly_testing=testing)
+    tag = "stack90_s%d_t%d_c%d" % (stride, int(testing), int(collapse))
+    assert np.array_equal(a, golden[tag + "_past"])
+    assert np.array_equal(b, golden[tag + "_fut"])
+    assert np.array_equal(c, golden[tag + "_futin"])
+
+
+def test_whole_span_matches_reference_golden(golden):
+    assert np.array_equal(kn.get_whole_span(golden["span_in"]), golden["span_out"])
+    assert np.array_equal(kn.get_whole_span(golden["span5_in"]), golden["span5_out"])
+    assert not golden["span_out"][-1].any()                     # "the last row is all zero!"
+
+
+def test_one_hot_heatmaps_match_reference_golden(golden):
+    ti, pj = kn.theta_phi_index(golden["onehot_in"])
+    assert np.array_equal(ti, golden["onehot_theta"]) and np.array_equal(pj, golden["onehot_phi"])
+    got = kn.one_hot_heatmaps(golden["onehot_in"])
+    assert np.array_equal(got, golden["onehot_out"])
+    assert got.sum() == golden["onehot_in"].shape[0] * golden["onehot_in"].shape[1] * 30   # one 1 per frame
+
+
 def test_resampler_matches_reference_golden(golden):
     mu, var, noise = golden["fake_mu"], golden["fake_var"], golden["fake_noise"]
     got = kn.gaussian_resample(mu[:, None], var[:, None], noise[:, :, None], "sqrt_floor")[..., 0]
