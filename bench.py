@@ -447,14 +447,22 @@ def run_ours(args):
         return
 
     # ---------------- end-to-end through the public API ----------------
+    # model.fit_generator(...) is the call the reference's scripts make (mycode/convlstm_heatmap.py:415-418; model.fit
+    # at mycode/others_LSTM_span_whole.py:778-785 runs the same loop): every step copies its inputs and targets from
+    # pinned HOST memory and reads its loss back; the copy of batch i+1 overlaps the kernels of step i.
     e2e_steps = max(3, min(args.steps, 10))
-    for i in range(2):
-        model.train_on_batch(*host_batches[i % 2])
+
+    def host_gen():
+        i = 0
+        while True:
+            yield host_batches[i % 2]
+            i += 1
+
+    model.fit_generator(host_gen(), steps_per_epoch=2, epochs=1)
     barrier()
     sampler.active = True
     e0.record()
-    for i in range(e2e_steps):
-        model.train_on_batch(*host_batches[i % 2])          # H2D of inputs+targets, step, D2H of the loss
+    model.fit_generator(host_gen(), steps_per_epoch=e2e_steps, epochs=1)   # per step: H2D, step, D2H of the loss
     e1.record()
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1)
@@ -508,7 +516,9 @@ def run_ours(args):
                    "l2": "no flush needed: per-step working set (saved activations ~%.1f GB) >> 126 MB L2; "
                          "two alternating input batches" % saved_gb},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+                "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                "api": "model.fit_generator(gen of pinned host batches): H2D of batch i+1 on a side stream under the "
+                       "kernels of step i, loss read back every step"},
         "gpu_launches": launches,
         "infer": {"value": infer_val, "unit": UNIT, "ms_per_step": ms_inf / args.steps},
         "final_loss": final_loss,

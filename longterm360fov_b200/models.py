@@ -320,6 +320,39 @@ class Model:
             t.record_stream(main)
         return float(self.train_step_device(xs, ys, ready).item())
 
+    def _prefetch(self, x, y):
+        """Host -> device copy of one batch on the side stream; returns (xs, ys, event, batch size)."""
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self._copy_stream):
+            xs = self._to_dev(self._as_list(x))
+            ys = self._to_dev(self._as_list(y))
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        for t in xs + ys:
+            t.record_stream(main)
+        return xs, ys, ready, len(xs[0])
+
+    def _train_batches(self, batches):
+        """Input pipeline of fit / fit_generator: while the kernels of step i run, the batch of step i+1 is assembled
+        on the host and copied on the side stream (the copy engines are idle during the step), and only then is the
+        loss of step i read back.  Every batch still crosses PCIe inside the loop; yields (batch size, loss)."""
+        it = iter(batches)
+        try:
+            cur = self._prefetch(*next(it))
+        except StopIteration:
+            return
+        while cur is not None:
+            xs, ys, ready, b = cur
+            torch.cuda.current_stream().wait_event(ready)
+            loss = self.train_step_device(xs, ys)              # asynchronous launches
+            try:
+                cur = self._prefetch(*next(it))
+            except StopIteration:
+                cur = None
+            yield b, float(loss.item())
+
     def test_on_batch(self, x, y):
         xs, ys = self._to_dev(self._as_list(x)), self._to_dev(self._as_list(y))
         with torch.no_grad():
@@ -383,10 +416,10 @@ class Model:
         for epoch in range(initial_epoch, epochs):
             idx = np.random.permutation(n) if shuffle else np.arange(n)
             tot = 0.0
-            for s in range(0, n, batch_size):
-                bi = idx[s:s + batch_size]
-                l = self.train_on_batch([a[bi] for a in xs], [a[bi] for a in ys])
-                tot += l * len(bi)
+            host = (([a[idx[s:s + batch_size]] for a in xs], [a[idx[s:s + batch_size]] for a in ys])
+                    for s in range(0, n, batch_size))
+            for b, l in self._train_batches(host):
+                tot += l * b
             logs = {"loss": tot / n}
             if vx is not None:
                 logs["val_loss"] = self.evaluate(vx, vy, batch_size)
@@ -414,10 +447,8 @@ class Model:
         self.stop_training = False
         for epoch in range(initial_epoch, epochs):
             tot, cnt = 0.0, 0
-            for _ in range(steps_per_epoch):
-                bx, by = next(generator)
-                b = len(self._as_list(bx)[0])
-                tot += b * self.train_on_batch(bx, by)
+            for b, l in self._train_batches(next(generator) for _ in range(steps_per_epoch)):
+                tot += b * l
                 cnt += b
             logs = {"loss": tot / max(cnt, 1)}
             if validation_data is not None:

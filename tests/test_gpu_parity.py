@@ -764,3 +764,30 @@ def test_fit_predict_surface_m1():
                          fov.EarlyStopping(monitor="val_loss", patience=10)])
     assert len(h.history["loss"]) == 6 and h.history["loss"][-1] < h.history["loss"][0]
     assert m.predict([enc, dec_in], batch_size=100).shape == (N, 10, 6)
+
+
+def test_fit_input_pipeline_matches_train_on_batch():
+    """fit / fit_generator prefetch batch i+1 on a side stream while step i runs: same losses and weights as
+    the serial train_on_batch loop on the same batches."""
+    fov = _cuda()
+    from longterm360fov_b200 import data
+    e, d, t, _ = data.make_m1_batch(96, seed=3)
+    w = kn.init_fov_seq2seq(seed=5)
+    a = fov.fov_seq2seq(weights=w).compile("Adam", "mean_squared_error")
+    b = fov.fov_seq2seq(weights=w).compile("Adam", "mean_squared_error")
+    serial = [a.train_on_batch([e[s:s + 32], d[s:s + 32]], t[s:s + 32]) for s in range(0, 96, 32)]
+
+    def gen():
+        while True:
+            for s in range(0, 96, 32):
+                yield [e[s:s + 32], d[s:s + 32]], t[s:s + 32]
+
+    h = b.fit_generator(gen(), steps_per_epoch=3, epochs=1)
+    assert abs(h.history["loss"][0] - float(np.mean(serial))) < 1e-6
+    for k in a.weight_order:
+        assert torch.equal(a.params[k], b.params[k]), k
+    c = fov.fov_seq2seq(weights=w).compile("Adam", "mean_squared_error")
+    h2 = c.fit([e, d], t, batch_size=32, epochs=1, shuffle=False)
+    assert abs(h2.history["loss"][0] - float(np.mean(serial))) < 1e-6
+    for k in a.weight_order:
+        assert torch.equal(a.params[k], c.params[k]), k
