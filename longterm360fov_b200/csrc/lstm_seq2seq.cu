@@ -10,10 +10,15 @@
 // Replaces the Keras LSTM/Dense calls cited in include/fov360.h.
 #include "fov_common.cuh"
 #include "fov_internal.h"
+#include <stdlib.h>
 
 // diagnostics / A-B testing: -1 = never use the tensor-core forward, 0 = choose, 1 = whenever the shape allows
 static int g_lstm_tc_mode = 0;
 extern "C" void fov_debug_lstm_tc(int mode) { g_lstm_tc_mode = mode; }
+// A/B switch, default off: with 70-float [h|x] rows the tensor-core weight gradient takes its unaligned gather path and
+// the config-2 step is 1 % slower than with the SIMT kernels (11.07 vs 10.96 ms at B=4096, measured)
+static int g_lstm_wgrad_tc = getenv("FOV_LSTM_WGRAD_TC") ? atoi(getenv("FOV_LSTM_WGRAD_TC")) : 0;
+extern "C" void fov_debug_lstm_wgrad_tc(int on) { g_lstm_wgrad_tc = on; }
 
 namespace {
 
@@ -486,6 +491,9 @@ extern "C" int fov_lstm_seq2seq_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
     fov_conv_cfg c{};
     c.N = (int)rows; c.H = 1; c.W = 1; c.Cin = K; c.Cout = N; c.kh = 1; c.kw = 1; c.dil_h = 1; c.dil_w = 1;
     c.x_img_stride = lda; c.x_pix_stride = (int)lda; c.y_img_stride = N; c.y_pix_stride = N;
+    // tensor-core weight gradient for the wide products ([h|x]^T dZ, N = 4H); the 6-column head stays on the SIMT kernel
+    if (cfg->math != FOV_MATH_FP32 && g_lstm_tc_mode >= 0 && g_lstm_wgrad_tc && gw && N % 4 == 0)
+      return fov_conv2d_bwd_weight_tc(&c, A, dZ, gw, gb, cfg->math, stream);
     return fov_conv2d_bwd_weight(&c, A, dZ, gw, gb, stream);
   };
   if (cfg->T_enc > 0) {

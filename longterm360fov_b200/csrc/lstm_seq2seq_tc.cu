@@ -119,7 +119,7 @@ __device__ __forceinline__ void pin8(float (&v)[8]) {
   asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
 }
 
-template <int NS, int NG, int REC, int OD>
+template <int NS, int NG, int REC, int OD, bool TRAIN>
 __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid_constant__ LstmTcParams P) {
   constexpr int NW = kRows * NG;           // threads: one per sequence
   constexpr uint32_t kWbOff = NS * kBTerm;                 // x-part weights (all terms in one tile, 32-byte chunks)
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
     for (int pi = 0; pi < P.nph; ++pi) {
       const TcPhase& ph = P.ph[pi];
       const int in_dim = ph.in_dim, T = ph.T, K = kH + in_dim;
-      const bool save = P.training != 0;
+      const bool save = TRAIN;                            // inference instantiations carry no saved-tensor stores
       const int xh_vec = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);
       const int Kn = (pi + 1 < P.nph) ? kH + P.ph[pi + 1].in_dim : K;      // xh row width of the next phase
       const int xhn_vec = (Kn % 4 == 0) ? 4 : ((Kn % 2 == 0) ? 2 : 1);
@@ -480,12 +480,12 @@ size_t tc_smem_bytes() {
   return (size_t)(NS + 1) * kBTerm + (size_t)NG * (NS + 1) * kATerm + sizeof(LstmTcBook<OD>) + 1024;
 }
 
-template <int NS, int NG, int REC, int OD>
-int launch_tc(const LstmTcParams& P, cudaStream_t st) {
+template <int NS, int NG, int REC, int OD, bool TRAIN>
+int launch_tc_t(const LstmTcParams& P, cudaStream_t st) {
   const size_t smem = tc_smem_bytes<NS, NG, OD>();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_tc_fwd_kernel<NS, NG, REC, OD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(lstm_tc_fwd_kernel<NS, NG, REC, OD, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) {
       fov_set_error("fov_lstm (tensor-core): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -495,9 +495,14 @@ int launch_tc(const LstmTcParams& P, cudaStream_t st) {
   }
   const int per_cta = kRows * NG;
   const int grid = (P.B + per_cta - 1) / per_cta;
-  lstm_tc_fwd_kernel<NS, NG, REC, OD><<<grid, kRows * NG, smem, st>>>(P);
+  lstm_tc_fwd_kernel<NS, NG, REC, OD, TRAIN><<<grid, kRows * NG, smem, st>>>(P);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
+}
+
+template <int NS, int NG, int REC, int OD>
+int launch_tc(const LstmTcParams& P, cudaStream_t st) {
+  return P.training ? launch_tc_t<NS, NG, REC, OD, true>(P, st) : launch_tc_t<NS, NG, REC, OD, false>(P, st);
 }
 
 template <int NS, int NG>

@@ -784,10 +784,10 @@ def test_fit_input_pipeline_matches_train_on_batch():
 
     h = b.fit_generator(gen(), steps_per_epoch=3, epochs=1)
     assert abs(h.history["loss"][0] - float(np.mean(serial))) < 1e-6
-    for k in a.weight_order:
-        assert torch.equal(a.params[k], b.params[k]), k
+    for k in a.weight_order:                                   # weight gradients reduce with atomics: order may differ
+        assert torch.allclose(a.params[k], b.params[k], rtol=0, atol=1e-6), k
     c = fov.fov_seq2seq(weights=w).compile("Adam", "mean_squared_error")
     h2 = c.fit([e, d], t, batch_size=32, epochs=1, shuffle=False)
     assert abs(h2.history["loss"][0] - float(np.mean(serial))) < 1e-6
     for k in a.weight_order:
-        assert torch.equal(a.params[k], c.params[k]), k
+        assert torch.allclose(a.params[k], c.params[k], rtol=0, atol=1e-6), k
