@@ -73,7 +73,8 @@ typedef struct {
 } fov_lstm_weights;
 
 typedef struct {                 /* per LSTM, all (B,T,...) row-major */
-  float *xh;                     /* (B,T,H+in): [h_{t-1} | x_t], A operand of the weight-grad GEMM */
+  float *xh;                     /* (B,T,XS): [h_{t-1} | x_t | 0], XS = (H+in+3)/4*4 (rows padded to 16 bytes so the
+                                    tensor-core weight-gradient GEMM reads them with aligned vector loads) */
   float *gates;                  /* (B,T,4H): activated i,f,g,o */
   float *c;                      /* (B,T,H) */
   float *hseq;                   /* (B,T,H)  (also the return_sequences output) */
@@ -102,7 +103,10 @@ typedef struct {
   float *g_enc_kernel, *g_enc_recurrent, *g_enc_bias;
   float *g_dec_kernel, *g_dec_recurrent, *g_dec_bias;
   float *g_head_kernel, *g_head_bias;
+  float *ws;                     /* optional workspace of fov_lstm_bwd_ws_floats() floats: with it (and cfg.math != 0)
+                                    each LSTM's [dU; dW; db] is ONE tcgen05 launch over the padded xh rows */
 } fov_lstm_grads;
+size_t fov_lstm_bwd_ws_floats(const fov_lstm_cfg* cfg);
 
 int fov_lstm_seq2seq_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w,
                          const fov_lstm_io* io, const fov_lstm_grads* g, void* stream);

@@ -46,7 +46,7 @@ class LstmGrads(C.Structure):
     _fields_ = [(n, c_float_p) for n in (
         "dy", "dhseq_enc", "y", "dz_enc", "dz_dec", "dpre",
         "g_enc_kernel", "g_enc_recurrent", "g_enc_bias",
-        "g_dec_kernel", "g_dec_recurrent", "g_dec_bias", "g_head_kernel", "g_head_bias")]
+        "g_dec_kernel", "g_dec_recurrent", "g_dec_bias", "g_head_kernel", "g_head_bias", "ws")]
 
 
 class ConvCfg(C.Structure):
@@ -92,6 +92,7 @@ SYMBOLS = {
     "fov_lstm_seq2seq_fwd": (_I, [C.POINTER(LstmCfg), C.POINTER(LstmWeights), C.POINTER(LstmIO), _P]),
     "fov_lstm_seq2seq_bwd": (_I, [C.POINTER(LstmCfg), C.POINTER(LstmWeights), C.POINTER(LstmIO),
                                   C.POINTER(LstmGrads), _P]),
+    "fov_lstm_bwd_ws_floats": (C.c_size_t, [C.POINTER(LstmCfg)]),
     "fov_conv2d_fwd": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P]),
     "fov_conv2d_bwd_data": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P]),
     "fov_conv2d_bwd_weight": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P]),

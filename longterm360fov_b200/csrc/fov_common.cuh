@@ -74,6 +74,9 @@ __device__ __forceinline__ void fov_cp_async_wait_all() {
   asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
+// row width of the saved [h_{t-1} | x_t | 0] tensor of an fc-LSTM (include/fov360.h fov_lstm_saved.xh)
+__host__ __device__ inline int fov_lstm_xh_stride(int H, int in_dim) { return (H + in_dim + 3) / 4 * 4; }
+
 static inline int fov_num_sms() {
   static int n = 0;
   if (n == 0) {

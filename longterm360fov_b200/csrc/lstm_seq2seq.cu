@@ -15,9 +15,10 @@
 // diagnostics / A-B testing: -1 = never use the tensor-core forward, 0 = choose, 1 = whenever the shape allows
 static int g_lstm_tc_mode = 0;
 extern "C" void fov_debug_lstm_tc(int mode) { g_lstm_tc_mode = mode; }
-// A/B switch, default off: with 70-float [h|x] rows the tensor-core weight gradient takes its unaligned gather path and
-// the config-2 step is 1 % slower than with the SIMT kernels (11.07 vs 10.96 ms at B=4096, measured)
-static int g_lstm_wgrad_tc = getenv("FOV_LSTM_WGRAD_TC") ? atoi(getenv("FOV_LSTM_WGRAD_TC")) : 0;
+// A/B switch for the tensor-core LSTM weight gradient (needs fov_lstm_grads.ws).  History: on unpadded 70-float [h|x]
+// rows it took the unaligned gather path of wgrad_tc.cu and lost to the SIMT kernels (11.07 vs 10.96 ms per config-2
+// step), hence the rows padded to a multiple of 4 floats and the single aligned launch per LSTM.
+static int g_lstm_wgrad_tc = getenv("FOV_LSTM_WGRAD_TC") ? atoi(getenv("FOV_LSTM_WGRAD_TC")) : 1;
 extern "C" void fov_debug_lstm_wgrad_tc(int on) { g_lstm_wgrad_tc = on; }
 
 namespace {
@@ -83,9 +84,10 @@ __device__ __forceinline__ void lstm_fwd_phase(const PhaseDesc& ph, float* Wsm, 
       }
     }
     if (training && ph.sv.xh) {
-      for (int idx = tid; idx < BT * K; idx += kNT) {
-        int s = idx / K, k = idx - s * K;
-        if (s < nvalid) ph.sv.xh[((size_t)(b0 + s) * T + t) * K + k] = cur[k * BTS + s];
+      const int XS = fov_lstm_xh_stride(kH, in_dim);          // rows padded with zeros to a multiple of 4 floats
+      for (int idx = tid; idx < BT * XS; idx += kNT) {
+        int s = idx / XS, k = idx - s * XS;
+        if (s < nvalid) ph.sv.xh[((size_t)(b0 + s) * T + t) * XS + k] = k < K ? cur[k * BTS + s] : 0.0f;
       }
     }
     float acc[4][SPT];
@@ -382,6 +384,18 @@ __global__ void __launch_bounds__(kNT) lstm_seq2seq_bwd_kernel(const __grid_cons
   }
 }
 
+// g_recurrent (H,4H) += ws rows [0,H); g_kernel (in,4H) += ws rows [H,H+in)   (ws = [h | x | 0]^T dZ, row-major, 4H wide)
+__global__ void __launch_bounds__(256) lstm_wgrad_scatter_kernel(const float* __restrict__ ws, float* __restrict__ g_recurrent,
+                                                                  float* __restrict__ g_kernel, int in_dim) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= (kH + in_dim) * kG) return;
+  const float4 v = *reinterpret_cast<const float4*>(ws + i);
+  float* dst = i < kH * kG ? g_recurrent + i : g_kernel + (i - kH * kG);
+  float4 o = *reinterpret_cast<float4*>(dst);
+  o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+  *reinterpret_cast<float4*>(dst) = o;
+}
+
 size_t fwd_smem_bytes(const fov_lstm_cfg& cfg, int spt) {
   const int bts = 4 * spt + 4;
   const int in_e = cfg.T_enc > 0 ? cfg.in_enc : 0, in_d = cfg.T_dec > 0 ? cfg.in_dec : 0;
@@ -418,6 +432,14 @@ int launch(K kernel, const LstmKParams& P, int grid, size_t smem, cudaStream_t s
 }
 
 }  // namespace
+
+extern "C" size_t fov_lstm_bwd_ws_floats(const fov_lstm_cfg* cfg) {
+  if (!cfg) return 0;
+  size_t n = 0;
+  if (cfg->T_enc > 0) n += (size_t)fov_lstm_xh_stride(kH, cfg->in_enc) * kG;
+  if (cfg->T_dec > 0) n += (size_t)fov_lstm_xh_stride(kH, cfg->in_dec) * kG;
+  return n;
+}
 
 extern "C" int fov_lstm_seq2seq_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w,
                                     const fov_lstm_io* io, void* stream) {
@@ -486,29 +508,50 @@ extern "C" int fov_lstm_seq2seq_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
 
   // time-batched weight gradients: [dU; dW] = [h_{t-1} | x_t]^T dZ over all (b,t) rows
   auto wgrad = [&](const float* A, long long lda, int K, const float* dZ, int N, long long rows,
-                   float* gw, float* gb) -> int {
+                   float* gw, float* gb, bool tc) -> int {
     if (!gw && !gb) return FOV_OK;
     fov_conv_cfg c{};
     c.N = (int)rows; c.H = 1; c.W = 1; c.Cin = K; c.Cout = N; c.kh = 1; c.kw = 1; c.dil_h = 1; c.dil_w = 1;
     c.x_img_stride = lda; c.x_pix_stride = (int)lda; c.y_img_stride = N; c.y_pix_stride = N;
-    // tensor-core weight gradient for the wide products ([h|x]^T dZ, N = 4H); the 6-column head stays on the SIMT kernel
-    if (cfg->math != FOV_MATH_FP32 && g_lstm_tc_mode >= 0 && g_lstm_wgrad_tc && gw && N % 4 == 0)
-      return fov_conv2d_bwd_weight_tc(&c, A, dZ, gw, gb, cfg->math, stream);
+    if (tc) return fov_conv2d_bwd_weight_tc(&c, A, dZ, gw, gb, cfg->math, stream);
     return fov_conv2d_bwd_weight(&c, A, dZ, gw, gb, stream);
   };
+  // One LSTM: with a workspace and a tensor-core math mode, ONE tcgen05 launch computes the whole padded product
+  // [h | x | 0]^T dZ (aligned rows: the fast path of wgrad_tc.cu) and the bias gradient, and a small kernel adds its
+  // row blocks to the two weight-gradient tensors; otherwise two SIMT products + a column sum.
+  auto lstm_wgrads = [&](const fov_lstm_saved& sv, int in_dim, int T, const float* dz, float* g_kernel,
+                         float* g_recurrent, float* g_bias, float* wsp) -> int {
+    const long long rows = (long long)cfg->B * T;
+    const int XS = fov_lstm_xh_stride(kH, in_dim);
+    if (wsp && cfg->math != FOV_MATH_FP32 && g_lstm_wgrad_tc && g_kernel && g_recurrent) {
+      cudaError_t e = cudaMemsetAsync(wsp, 0, sizeof(float) * (size_t)XS * kG, st);
+      if (e != cudaSuccess) { fov_set_error("fov_lstm_seq2seq_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e)); return FOV_ERR_CUDA; }
+      int r = wgrad(sv.xh, XS, XS, dz, kG, rows, wsp, g_bias, true);
+      if (r) return r;
+      const int n = (kH + in_dim) * kG;
+      lstm_wgrad_scatter_kernel<<<(n / 4 + 255) / 256, 256, 0, st>>>(wsp, g_recurrent, g_kernel, in_dim);
+      FOV_CUDA_LAUNCH_CHECK();
+      return FOV_OK;
+    }
+    int r = wgrad(sv.xh, XS, kH, dz, kG, rows, g_recurrent, g_bias, false);
+    if (r) return r;
+    return wgrad(sv.xh + kH, XS, in_dim, dz, kG, rows, g_kernel, nullptr, false);
+  };
+  float* wsp = g->ws;
   if (cfg->T_enc > 0) {
-    const long long rows = (long long)cfg->B * cfg->T_enc;
-    const int K = kH + cfg->in_enc;
-    if ((rc = wgrad(io->enc.xh, K, kH, g->dz_enc, kG, rows, g->g_enc_recurrent, g->g_enc_bias))) return rc;
-    if ((rc = wgrad(io->enc.xh + kH, K, cfg->in_enc, g->dz_enc, kG, rows, g->g_enc_kernel, nullptr))) return rc;
+    if ((rc = lstm_wgrads(io->enc, cfg->in_enc, cfg->T_enc, g->dz_enc, g->g_enc_kernel, g->g_enc_recurrent,
+                          g->g_enc_bias, wsp)))
+      return rc;
+    if (wsp) wsp += (size_t)fov_lstm_xh_stride(kH, cfg->in_enc) * kG;
   }
   if (cfg->T_dec > 0) {
-    const long long rows = (long long)cfg->B * cfg->T_dec;
-    const int K = kH + cfg->in_dec;
-    if ((rc = wgrad(io->dec.xh, K, kH, g->dz_dec, kG, rows, g->g_dec_recurrent, g->g_dec_bias))) return rc;
-    if ((rc = wgrad(io->dec.xh + kH, K, cfg->in_dec, g->dz_dec, kG, rows, g->g_dec_kernel, nullptr))) return rc;
-    if (has_head)
-      if ((rc = wgrad(io->dec.hseq, kH, kH, g->dpre, cfg->out_dim, rows, g->g_head_kernel, g->g_head_bias))) return rc;
+    if ((rc = lstm_wgrads(io->dec, cfg->in_dec, cfg->T_dec, g->dz_dec, g->g_dec_kernel, g->g_dec_recurrent,
+                          g->g_dec_bias, wsp)))
+      return rc;
+    if (has_head) {
+      const long long rows = (long long)cfg->B * cfg->T_dec;
+      if ((rc = wgrad(io->dec.hseq, kH, kH, g->dpre, cfg->out_dim, rows, g->g_head_kernel, g->g_head_bias, false))) return rc;
+    }
   }
   return FOV_OK;
 }

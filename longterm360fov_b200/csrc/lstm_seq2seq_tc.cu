@@ -229,11 +229,11 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
     int step = 0;
     for (int pi = 0; pi < P.nph; ++pi) {
       const TcPhase& ph = P.ph[pi];
-      const int in_dim = ph.in_dim, T = ph.T, K = kH + in_dim;
+      const int in_dim = ph.in_dim, T = ph.T, K = fov_lstm_xh_stride(kH, in_dim);   // padded [h | x | 0] row width
       const bool save = TRAIN;                            // inference instantiations carry no saved-tensor stores
-      const int xh_vec = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);
-      const int Kn = (pi + 1 < P.nph) ? kH + P.ph[pi + 1].in_dim : K;      // xh row width of the next phase
-      const int xhn_vec = (Kn % 4 == 0) ? 4 : ((Kn % 2 == 0) ? 2 : 1);
+      const int xh_vec = 4;
+      const int Kn = (pi + 1 < P.nph) ? fov_lstm_xh_stride(kH, P.ph[pi + 1].in_dim) : K;   // of the next phase
+      const int xhn_vec = 4;
       // every MMA of the previous phase has completed once all workers got here (each group waited for its last commit)
       tc_fence_before();
       bar_workers(NW);
@@ -308,8 +308,8 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
         if (save && valid && ph.sv.xh) {
           float* xr = ph.sv.xh + (size_t)b * T * K + kH;
 #pragma unroll
-          for (int k = 0; k < kXK; ++k)
-            if (k < in_dim) xr[k] = xn[k];
+          for (int k = 0; k < kXK + 3; ++k)
+            if (kH + k < K) xr[k] = k < kXK ? xn[k < kXK ? k : 0] : 0.0f;     // xn is zero beyond in_dim: the row pad
         }
       }
       fence_proxy_async_smem();
@@ -440,8 +440,8 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
           if (save && valid && ph.sv.xh) {
             float* xr = ph.sv.xh + (rowt + 1) * K + kH;
 #pragma unroll
-            for (int k = 0; k < kXK; ++k)
-              if (k < in_dim) xr[k] = xn[k];
+            for (int k = 0; k < kXK + 3; ++k)
+              if (kH + k < K) xr[k] = k < kXK ? xn[k < kXK ? k : 0] : 0.0f;
           }
           fence_proxy_async_smem();
           bar_group(g);

@@ -85,10 +85,10 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
         enc_hseq = torch.empty(B, T_enc, H, device=dev) if opts.get("need_enc_hseq", True) else None
         saved = {}
         if training:
-            saved["enc_xh"] = torch.empty(B, T_enc, H + in_enc, device=dev)
+            saved["enc_xh"] = torch.empty(B, T_enc, (H + in_enc + 3) // 4 * 4, device=dev)   # [h | x | 0] rows
             saved["enc_gates"] = torch.empty(B, T_enc, 4 * H, device=dev)
             saved["enc_c"] = torch.empty(B, T_enc, H, device=dev)
-            saved["dec_xh"] = torch.empty(B, T_dec, H + in_dec, device=dev)
+            saved["dec_xh"] = torch.empty(B, T_dec, (H + in_dec + 3) // 4 * 4, device=dev)
             saved["dec_gates"] = torch.empty(B, T_dec, 4 * H, device=dev)
             saved["dec_c"] = torch.empty(B, T_dec, H, device=dev)
             saved["dec_hseq"] = torch.empty(B, T_dec, H, device=dev)
@@ -119,6 +119,7 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
         dz_enc = torch.empty(cfg.B, cfg.T_enc, 4 * cfg.H, device=dev)
         dz_dec = torch.empty(cfg.B, cfg.T_dec, 4 * cfg.H, device=dev)
         dpre = torch.empty_like(y)
+        ws = torch.empty(int(lib.fov_lstm_bwd_ws_floats(C.byref(cfg))), device=dev)
         w = _lib.LstmWeights(ptr(We), ptr(Ue), ptr(be), ptr(Wd), ptr(Ud), ptr(bd), ptr(Wo), ptr(bo))
         io = _lib.LstmIO(ptr(x_enc), ptr(x_dec), ptr(extra), None, None, ptr(y), None, None,
                          _lib.LstmSaved(ptr(sv["enc_xh"]), ptr(sv["enc_gates"]), ptr(sv["enc_c"]),
@@ -128,7 +129,7 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
         g = _lib.LstmGrads(ptr(dy), ptr(dhseq_enc), ptr(y), ptr(dz_enc), ptr(dz_dec), ptr(dpre),
                            ptr(s["enc_kernel"]), ptr(s["enc_recurrent"]), ptr(s["enc_bias"]),
                            ptr(s["dec_kernel"]), ptr(s["dec_recurrent"]), ptr(s["dec_bias"]),
-                           ptr(s["head_kernel"]), ptr(s["head_bias"]))
+                           ptr(s["head_kernel"]), ptr(s["head_bias"]), ptr(ws))
         _lib.check(lib.fov_lstm_seq2seq_bwd(C.byref(cfg), C.byref(w), C.byref(io), C.byref(g), _stream()),
                    "fov_lstm_seq2seq_bwd")
         d_extra = dpre if ctx.has_extra else None
