@@ -272,6 +272,25 @@ __global__ void __launch_bounds__(256) colsum_kernel(long long M, int C, int HW,
   }
 }
 
+// Narrow dense matrices (C <= 32 columns, rows contiguous): the flat array is walked with a stride that is a multiple of
+// C, so a thread always sees the same column; all 256 threads of a CTA carry data whatever C is.
+__global__ void __launch_bounds__(256) colsum_narrow_kernel(long long total, int C, const float* __restrict__ dy,
+                                                            float* __restrict__ gb) {
+  __shared__ float part[32];
+  if (threadIdx.x < 32) part[threadIdx.x] = 0.0f;
+  __syncthreads();
+  const long long nthr = (long long)gridDim.x * blockDim.x;
+  const long long step = nthr / C * C;                 // <= nthr: the threads e0 < step cover every element once
+  const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float s = 0.0f;
+  if (e0 < step) {
+    for (long long e = e0; e < total; e += step) s += __ldg(dy + e);
+    atomicAdd(&part[(int)(e0 % C)], s);
+  }
+  __syncthreads();
+  if (threadIdx.x < C) atomicAdd(&gb[threadIdx.x], part[threadIdx.x]);
+}
+
 // wt[(kh-1-i, kw-1-j)][co][ci] = w[(i,j)][ci][co]
 __global__ void flip_transpose_kernel(int taps_h, int taps_w, int Cin, int Cout, const float* __restrict__ w,
                                       float* __restrict__ wt) {
@@ -403,7 +422,14 @@ extern "C" int fov_conv2d_bwd_weight(const fov_conv_cfg* cfg, const float* x, co
     conv_wgrad_kernel<<<grid, kThreads, 0, st>>>(k, x, dy, gw, per);
     FOV_CUDA_LAUNCH_CHECK();
   }
-  if (gbias) {
+  if (gbias && k.Cout <= 32 && k.y_pix_stride == k.Cout && k.y_img_stride == (long long)HW * k.Cout) {
+    const long long total = k.M * k.Cout;
+    long long blocks = (total + 256 * 16 - 1) / (256 * 16);
+    if (blocks > 2 * fov_num_sms()) blocks = 2 * fov_num_sms();
+    if (blocks < 1) blocks = 1;
+    colsum_narrow_kernel<<<(unsigned)blocks, 256, 0, st>>>(total, k.Cout, dy, gbias);
+    FOV_CUDA_LAUNCH_CHECK();
+  } else if (gbias) {
     long long blocks = (k.M + 1023) / 1024;
     if (blocks > 2 * fov_num_sms()) blocks = 2 * fov_num_sms();
     if (blocks < 1) blocks = 1;
