@@ -289,6 +289,12 @@ int fov_whole_span(long long N, long long half, const float* x, float* out, void
  * Angles are evaluated in float64 so the bin indices equal NumPy's. */
 int fov_onehot_heatmaps(long long rows, int frames, int bin_size, const float* xyz, float* out, void* stream);
 
+/* FoV hit rate (evaluation metric, mycode/baseline_knn_mean.py:48-93,123-168): pred / gt (rows,2) = (theta, phi)
+ * centres in radians, spans in radians (the scripts use 120 x 120 degrees); out[i] = overlap of the two boxes over the
+ * ground-truth box area after the +-pi wrap fix of boundary_cases. */
+int fov_hit_rate(long long rows, const float* pred, const float* gt, float span_theta, float span_phi,
+                 float gt_span_theta, float gt_span_phi, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,6 +108,30 @@ __global__ void __launch_bounds__(256) onehot_heatmap_kernel(long long rows, int
   }
 }
 
+// FoV hit rate of one (predicted, ground-truth) centre pair: overlap of the two (theta, phi) boxes over the ground-truth
+// box area, after the +-pi wrap fix of boundary_cases (mycode/baseline_knn_mean.py:48-93).  float64 like the reference.
+__global__ void __launch_bounds__(256) hit_rate_kernel(long long rows, const float* __restrict__ pred,
+                                                        const float* __restrict__ gt, double span_t, double span_p,
+                                                        double gspan_t, double gspan_p, float* __restrict__ out) {
+  const double kPi = 3.141592653589793;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+    double ct = (double)pred[2 * i], cp = (double)pred[2 * i + 1];
+    double gtt = (double)gt[2 * i], gtp = (double)gt[2 * i + 1];
+    if (gtt > 2 / 3.0 * kPi && ct < -2 / 3.0 * kPi) ct += 2 * kPi;
+    if (gtt < -2 / 3.0 * kPi && ct > 2 / 3.0 * kPi) gtt += 2 * kPi;
+    const double b0 = ct - span_t / 2, b1 = cp - span_p / 2, b2 = ct + span_t / 2, b3 = cp + span_p / 2;
+    const double q0 = gtt - gspan_t / 2, q1 = gtp - gspan_p / 2, q2 = gtt + gspan_t / 2, q3 = gtp + gspan_p / 2;
+    const double area = (q2 - q0) * (q3 - q1);
+    double ov = 0.0;
+    const double iw = fmin(b2, q2) - fmax(b0, q0);
+    if (iw > 0) {
+      const double ih = fmin(b3, q3) - fmax(b1, q1);
+      if (ih > 0) ov = iw * ih / area;
+    }
+    out[i] = (float)ov;
+  }
+}
+
 int grid_for(long long work_items, int block) {
   long long g = (work_items + block - 1) / block;
   const long long cap = (long long)fov_num_sms() * 16;
@@ -172,6 +196,16 @@ extern "C" int fov_onehot_heatmaps(long long rows, int frames, int bin_size, con
   const int nth = 360 / bin_size, nph = 180 / bin_size;
   onehot_heatmap_kernel<<<(unsigned)rows, 256, frames * sizeof(int), (cudaStream_t)stream>>>(rows, frames, nth, nph,
                                                                                            (double)bin_size, xyz, out);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
+
+extern "C" int fov_hit_rate(long long rows, const float* pred, const float* gt, float span_theta, float span_phi,
+                            float gt_span_theta, float gt_span_phi, float* out, void* stream) {
+  FOV_CHECK_ARG(rows > 0 && pred && gt && out, "bad arguments");
+  FOV_CHECK_ARG(gt_span_theta > 0 && gt_span_phi > 0, "ground-truth span must be positive");
+  hit_rate_kernel<<<grid_for(rows, 256), 256, 0, (cudaStream_t)stream>>>(rows, pred, gt, (double)span_theta, (double)span_phi,
+                                                                        (double)gt_span_theta, (double)gt_span_phi, out);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }

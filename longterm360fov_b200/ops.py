@@ -684,3 +684,17 @@ def one_hot_heatmaps(frames, bin_size=10):
     out = torch.empty(*lead, 360 // bin_size, 180 // bin_size, Fr, device=frames.device)
     _lib.check(lib.fov_onehot_heatmaps(rows, Fr, bin_size, ptr(frames), ptr(out), _stream()), "fov_onehot_heatmaps")
     return out
+
+
+def hit_rate(pred_theta_phi, gt_theta_phi, a=1.0, span_deg=120.0):
+    """FoV hit rate per (theta, phi) centre pair (mycode/baseline_knn_mean.py:48-93,123-168): (..., 2) radians ->
+    (...,); the predicted box is ``a`` x 120 degrees wide, the ground-truth box 120 degrees."""
+    import math
+    lib = _lib.load()
+    _require_cuda(pred_theta_phi, gt_theta_phi)
+    p, g = _f32c(pred_theta_phi), _f32c(gt_theta_phi)
+    out = torch.empty(p.shape[:-1], device=p.device)
+    sp = a * span_deg / 180.0 * math.pi
+    gs = span_deg / 180.0 * math.pi
+    _lib.check(lib.fov_hit_rate(out.numel(), ptr(p), ptr(g), sp, sp, gs, gs, ptr(out), _stream()), "fov_hit_rate")
+    return out

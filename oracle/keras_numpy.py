@@ -290,6 +290,23 @@ def one_hot_heatmaps(frames, bin_size=10):
     return one_hot.transpose(0, 1, 3, 4, 2)
 
 
+def hit_rate(pred, gt, a=1.0, span_deg=120.0):
+    """mycode/baseline_knn_mean.py:48-93 (boundary_cases, get_iou_or_hitrate,
+    bbox_overlaps_hit_rate) and :131-132 (spans), vectorised: (...,2) (theta, phi)
+    centres -> box overlap over the ground-truth box area."""
+    ct, cp = np.array(pred[..., 0], np.float64), np.array(pred[..., 1], np.float64)
+    gt_t, gt_p = np.array(gt[..., 0], np.float64), np.array(gt[..., 1], np.float64)
+    c1 = (gt_t > 2 / 3.0 * np.pi) & (ct < -2 / 3.0 * np.pi)
+    ct = np.where(c1, ct + 2 * np.pi, ct)
+    c2 = (gt_t < -2 / 3.0 * np.pi) & (ct > 2 / 3.0 * np.pi)
+    gt_t = np.where(c2, gt_t + 2 * np.pi, gt_t)
+    s = a * span_deg / 180.0 * np.pi
+    g = span_deg / 180.0 * np.pi
+    iw = np.minimum(ct + s / 2, gt_t + g / 2) - np.maximum(ct - s / 2, gt_t - g / 2)
+    ih = np.minimum(cp + s / 2, gt_p + g / 2) - np.maximum(cp - s / 2, gt_p - g / 2)
+    return np.where((iw > 0) & (ih > 0), iw * ih / (g * g), 0.0)
+
+
 # --------------------------------------------------------------------------- #
 # losses
 # --------------------------------------------------------------------------- #

@@ -138,6 +138,29 @@ def main():
     ti, pj = hs["_theta_phi_index_for_onehot"](v)
     out["onehot_in"], out["onehot_theta"], out["onehot_phi"] = v, ti, pj
     out["onehot_out"] = hs["_create_one_hot"](ti, pj).transpose(0, 1, 3, 4, 2)   # frames as channels
+    # hit rate: boundary_cases + get_iou_or_hitrate + bbox_overlaps_hit_rate (baseline_knn_mean.py:48-93), frame mode
+    # of _eval_for_seq2seq (:157-160), spans of :131-132
+    kn = {"np": np}
+    ksrc = "".join(l for l in open("/root/reference/mycode/baseline_knn_mean.py") if not l.startswith("%"))   # IPython magics
+    ktree = ast.parse(ksrc)
+    for node in ktree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("get_iou_or_hitrate", "bbox_overlaps_hit_rate",
+                                                               "boundary_cases"):
+            exec(compile(ast.Module([node], type_ignores=[]), "baseline_knn_mean.py", "exec"), kn)
+    n = 400
+    gt_c = np.stack([rng.uniform(-np.pi, np.pi, n), rng.uniform(0, np.pi, n)])            # (2, n): theta, phi
+    pr_c = gt_c + rng.normal(size=(2, n)) * np.array([[0.9], [0.5]])
+    pr_c[0] = np.mod(pr_c[0] + np.pi, 2 * np.pi) - np.pi                                 # wraps across +-pi
+    pr_c[:, :4] = gt_c[:, :4]                                                             # exact hits
+    gt_c = gt_c.astype(np.float32).astype(np.float64)
+    pr_c = pr_c.astype(np.float32).astype(np.float64)
+    out["hit_pred"], out["hit_gt"] = pr_c.T.copy(), gt_c.T.copy()
+    for a in (1.0, 0.75):
+        span = np.array([a * 120, a * 120]) / 180.0 * np.pi
+        gt_span = np.array([120, 120]) / 180.0 * np.pi
+        g2, c2 = kn["boundary_cases"](gt_c.copy(), pr_c.copy())
+        res = [kn["get_iou_or_hitrate"](c2[:, i], span, g2[:, i], gt_span)[0] for i in range(n)]
+        out["hit_out_a%d" % int(a * 100)] = np.array(res, np.float64)
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_numpy_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items()})

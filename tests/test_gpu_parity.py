@@ -139,6 +139,25 @@ def test_one_hot_heatmaps_match_reference_golden(golden):
     assert np.array_equal(coarse.cpu().numpy(), kn.one_hot_heatmaps(v[:2].astype(np.float64), 30).astype(np.float32))
 
 
+def test_hit_rate_matches_reference_golden(golden):
+    """Evaluation metric (baseline_knn_mean.py:48-93): floating point, evaluated in float64 on the device and
+    stored as float32 -> tolerance 1e-6 against the reference's own output, wrap-around cases included."""
+    _cuda()
+    from longterm360fov_b200 import ops
+    p = torch.tensor(golden["hit_pred"], dtype=torch.float32, device="cuda")
+    g = torch.tensor(golden["hit_gt"], dtype=torch.float32, device="cuda")
+    for a in (1.0, 0.75):
+        got = ops.hit_rate(p, g, a=a).cpu().numpy()
+        np.testing.assert_allclose(got, golden["hit_out_a%d" % int(a * 100)], rtol=0, atol=1e-6)
+    rng = np.random.default_rng(2)
+    big_p = rng.uniform(-3.1, 3.1, (512, 10, 30, 2)).astype(np.float32)
+    big_g = rng.uniform(-3.1, 3.1, (512, 10, 30, 2)).astype(np.float32)
+    big_p[..., 1] = np.abs(big_p[..., 1]); big_g[..., 1] = np.abs(big_g[..., 1])
+    got = ops.hit_rate(torch.tensor(big_p).cuda(), torch.tensor(big_g).cuda()).cpu().numpy()
+    assert got.shape == (512, 10, 30) and got.min() >= 0.0 and got.max() <= 1.0
+    np.testing.assert_allclose(got, kn.hit_rate(big_p, big_g), rtol=0, atol=1e-6)
+
+
 # ------------------------------------------------------------------ fc-LSTM
 
 @pytest.mark.parametrize("B", [1, 7, 33, 70])

@@ -55,6 +55,12 @@ def test_one_hot_heatmaps_match_reference_golden(golden):
     assert got.sum() == golden["onehot_in"].shape[0] * golden["onehot_in"].shape[1] * 30   # one 1 per frame
 
 
+def test_hit_rate_matches_reference_golden(golden):
+    for a in (1.0, 0.75):
+        got = kn.hit_rate(golden["hit_pred"], golden["hit_gt"], a=a)
+        np.testing.assert_allclose(got, golden["hit_out_a%d" % int(a * 100)], rtol=0, atol=1e-14)
+
+
 def test_resampler_matches_reference_golden(golden):
     mu, var, noise = golden["fake_mu"], golden["fake_var"], golden["fake_noise"]
     got = kn.gaussian_resample(mu[:, None], var[:, None], noise[:, :, None], "sqrt_floor")[..., 0]
