@@ -450,7 +450,7 @@ def run_ours(args):
     # model.fit_generator(...) is the call the reference's scripts make (mycode/convlstm_heatmap.py:415-418; model.fit
     # at mycode/others_LSTM_span_whole.py:778-785 runs the same loop): every step copies its inputs and targets from
     # pinned HOST memory and reads its loss back; the copy of batch i+1 overlaps the kernels of step i.
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 50))
 
     def host_gen():
         i = 0

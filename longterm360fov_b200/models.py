@@ -321,37 +321,46 @@ class Model:
         return float(self.train_step_device(xs, ys, ready).item())
 
     def _prefetch(self, x, y):
-        """Host -> device copy of one batch on the side stream; returns (xs, ys, event, batch size)."""
+        """Host -> device copy of one batch on the side stream; returns (xs, ys, (inputs event, targets event), batch size)."""
         main = torch.cuda.current_stream()
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         with torch.cuda.stream(self._copy_stream):
             xs = self._to_dev(self._as_list(x))
-            ys = self._to_dev(self._as_list(y))
-            ready = torch.cuda.Event()
-            ready.record(self._copy_stream)
+            x_ready = torch.cuda.Event()
+            x_ready.record(self._copy_stream)
+            ys = self._to_dev(self._as_list(y))                # only the loss needs them: may land during the forward
+            y_ready = torch.cuda.Event()
+            y_ready.record(self._copy_stream)
         for t in xs + ys:
             t.record_stream(main)
-        return xs, ys, ready, len(xs[0])
+        return xs, ys, (x_ready, y_ready), len(xs[0])
 
     def _train_batches(self, batches):
         """Input pipeline of fit / fit_generator: while the kernels of step i run, the batch of step i+1 is assembled
-        on the host and copied on the side stream (the copy engines are idle during the step), and only then is the
-        loss of step i read back.  Every batch still crosses PCIe inside the loop; yields (batch size, loss)."""
+        on the host and copied on the side stream (the copy engines are idle during the step); the loss of a step is
+        read back once the next step has been enqueued.  Every batch still crosses PCIe inside the loop and every
+        loss is read; yields (batch size, loss) in step order."""
         it = iter(batches)
         try:
             cur = self._prefetch(*next(it))
         except StopIteration:
             return
+        pending = None                                         # (batch size, loss tensor) of the step before
         while cur is not None:
-            xs, ys, ready, b = cur
-            torch.cuda.current_stream().wait_event(ready)
-            loss = self.train_step_device(xs, ys)              # asynchronous launches
+            xs, ys, (x_ready, y_ready), b = cur
+            torch.cuda.current_stream().wait_event(x_ready)
+            loss = self.train_step_device(xs, ys, y_ready)     # asynchronous launches
             try:
                 cur = self._prefetch(*next(it))
             except StopIteration:
                 cur = None
-            yield b, float(loss.item())
+            # the loss of step i-1 is read while step i runs: the host never drains the GPU between steps
+            if pending is not None:
+                yield pending[0], float(pending[1].item())
+            pending = (b, loss)
+        if pending is not None:
+            yield pending[0], float(pending[1].item())
 
     def test_on_batch(self, x, y):
         xs, ys = self._to_dev(self._as_list(x)), self._to_dev(self._as_list(y))
