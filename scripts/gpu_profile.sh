@@ -23,6 +23,6 @@ cap() {  # name regex skip count
 }
 # one timed step (the 4th) of: the three persistent / fused ConvLSTM kernels per layer, the dense GEMMs, the fc-LSTM
 cap convlstm 'tc_wgrad_rows|convlstm_seq' ${CL_SKIP:-27} ${CL_N:-9}
-cap conv 'tc_conv_kernel|tc_wgrad_kernel' ${CV_SKIP:-36} ${CV_N:-12}
-cap lstm 'lstm_' ${LS_SKIP:-6} 2
+[ -n "$ONLY_CONVLSTM" ] || cap conv 'tc_conv_kernel|tc_wgrad_kernel' ${CV_SKIP:-36} ${CV_N:-12}
+[ -n "$ONLY_CONVLSTM" ] || cap lstm 'lstm_' ${LS_SKIP:-6} 2
 du -sh $OUT
