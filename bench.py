@@ -101,7 +101,8 @@ def _time_cuda(fn, reps=20, warm=3):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed
 # `ncu --set full` capture (profiles/), keyed by per-GPU batch; None when no capture exists for it.
 NCU_TRAFFIC_BYTES = {2048: 1040990000,    # 33.29 MB read + 1007.70 MB written
-                     4096: 2128110000}    # profiles/r01_ncu_full_m3_b4096_bf16x2.md row 0: 66.13 MB read + 2061.98 MB written
+                     4096: 2128110000,    # profiles/r01_ncu_full_m3_b4096_bf16x2.md row 0: 66.13 MB read + 2061.98 MB written
+                     8880: 4674160000}    # profiles/r01_ncu_full_m3_b8880_bf16x2.md row 0: 143.02 MB read + 4531.14 MB written
 
 
 def kernel_rooflines(lib, dev, B, compute, peaks, seq_per_s_per_gpu):
