@@ -220,19 +220,23 @@ def other_workloads(dev, peaks, compute):
     # ---- config 5: convlstm_seq2seq heatmap form, one heatmap = one predicted (36,18,30) second ----
     Bh = 32
     m4 = fov.convlstm_seq2seq(seed=2, device=dev).compile("RMSprop", "mean_squared_error")
-    m4.set_compute(compute)
     x, y = data.make_m4_batch(Bh, seed=7)
     xs, ys = m4._to_dev(x), m4._to_dev(y)
-    ms_t = _time_cuda(lambda: m4.train_step_device(xs, ys), reps=3, warm=2)
-    with torch.no_grad():
-        ms_i = _time_cuda(lambda: m4._forward(xs, False), reps=3, warm=1)
     flop_fwd = 10 * 381.5e6 + 10 * (381.5e6 + 18.9e9)         # encoder + decoder steps + heads
-    res["convlstm_seq2seq_heatmap"] = {
-        "batch": Bh, "unit": "heatmaps/s", "train": Bh * 10 / (ms_t * 1e-3), "infer": Bh * 10 / (ms_i * 1e-3),
-        "train_ms_per_step": ms_t, "infer_ms_per_step": ms_i,
-        "train_algorithmic_tflops": 3 * flop_fwd * Bh / (ms_t * 1e-3) / 1e12,
-        "infer_algorithmic_tflops": flop_fwd * Bh / (ms_i * 1e-3) / 1e12,
-        "tensor_peak_tflops": peaks["bf16"], "compute": compute}
+    # the default arithmetic (fp32-grade two-term split) and the plain bf16 tensor-core mode BASELINE.json's config 5
+    # names ("bf16 tensor-core gate convolutions"; forward tolerance 3e-2 max-abs, tests/test_gpu_parity.py)
+    for mode in dict.fromkeys([compute, "bf16"]):
+        m4.set_compute(mode)
+        ms_t = _time_cuda(lambda: m4.train_step_device(xs, ys), reps=3, warm=2)
+        with torch.no_grad():
+            ms_i = _time_cuda(lambda: m4._forward(xs, False), reps=3, warm=1)
+        entry = {
+            "batch": Bh, "unit": "heatmaps/s", "train": Bh * 10 / (ms_t * 1e-3), "infer": Bh * 10 / (ms_i * 1e-3),
+            "train_ms_per_step": ms_t, "infer_ms_per_step": ms_i,
+            "train_algorithmic_tflops": 3 * flop_fwd * Bh / (ms_t * 1e-3) / 1e12,
+            "infer_algorithmic_tflops": flop_fwd * Bh / (ms_i * 1e-3) / 1e12,
+            "tensor_peak_tflops": peaks["bf16"], "compute": mode}
+        res["convlstm_seq2seq_heatmap" if mode == compute else "convlstm_seq2seq_heatmap_" + mode] = entry
     del m4, xs, ys
     torch.cuda.empty_cache()
 

@@ -56,6 +56,7 @@ struct LstmTcBook {
   float4 bias4[kH];                        // (b_i, b_f, b_c, b_o) of a hidden unit
   float Wo_s[kH * OD];                     // head kernel, rows padded to OD columns
   float bo_s[OD];
+  float ypart[2 * kRows * OD];             // WPG = 8: head partial sums of the threads that own units 32..63
   uint64_t tmem_full[2];
   uint32_t tmem_ptr;
 };
@@ -65,7 +66,7 @@ struct LstmTcBook {
 __device__ unsigned long long g_lstm_tc_timeline[8];
 
 __device__ __forceinline__ void bar_workers(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
-__device__ __forceinline__ void bar_group(int g) { asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory"); }
+__device__ __forceinline__ void bar_group(int g, int n) { asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "r"(n) : "memory"); }
 
 // tanh(x) = 1 - 2 / (1 + 2^(x * 2 log2 e)): FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA (abs error ~1e-7)
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -119,9 +120,16 @@ __device__ __forceinline__ void pin8(float (&v)[8]) {
   asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
 }
 
-template <int NS, int NG, int REC, int OD, bool TRAIN>
-__global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid_constant__ LstmTcParams P) {
-  constexpr int NW = kRows * NG;           // threads: one per sequence
+// WPG = warps per 128-sequence group: 4 (a thread owns the 64 hidden units of its sequence) or 8 (the two warps of a
+// TMEM lane quarter own 32 units each: twice the warps per scheduler to hide the MUFU / tcgen05.ld latencies, half the
+// cell state per thread; the head partial sums of the upper half travel through shared memory)
+template <int NS, int NG, int REC, int OD, bool TRAIN, int WPG>
+__global__ void __launch_bounds__(32 * WPG * NG, 1) lstm_tc_fwd_kernel(const __grid_constant__ LstmTcParams P) {
+  constexpr int NW = 32 * WPG * NG;        // threads
+  constexpr int GT = 32 * WPG;             // threads per group
+  constexpr int UPT = kH / (WPG / 4);      // hidden units per thread
+  constexpr int NPASS = UPT / 8;
+  constexpr bool PF = WPG == 4;            // double-buffered accumulator reads (register budget allows it at WPG = 4)
   constexpr uint32_t kWbOff = NS * kBTerm;                 // x-part weights (all terms in one tile, 32-byte chunks)
   constexpr uint32_t kActOff = kWbOff + kBTerm;
   constexpr uint32_t kGrpBytes = (NS + 1) * kATerm;        // h terms, then the x tile (terms as 32-byte chunks)
@@ -155,7 +163,9 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
 
   {
     // ---------------- thread = one sequence (accumulator row) ----------------
-    const int g = warp >> 2, q = warp & 3, r = q * 32 + lane;
+    const int g = warp / WPG, wg = warp % WPG, q = wg & 3, half = wg >> 2, r = q * 32 + lane;
+    const int u0 = half * UPT;               // my first hidden unit
+    const bool lead = half == 0;             // the thread of the row that handles x, the head tail and y
     const long long b = ((long long)blockIdx.x * NG + g) * kRows + r;
     const bool valid = b < P.B;
     uint8_t* hA = smem + kActOff + (uint32_t)g * kGrpBytes;
@@ -163,6 +173,7 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
     const uint32_t rowoff = (uint32_t)r * 128u, rsw = (uint32_t)(r & 7);
     const uint32_t t_row = tmem_d + (uint32_t)(g * kG) + ((uint32_t)(q * 32) << 16);
     const bool dbg = P.dbg && blockIdx.x == 0 && tid == 0;
+    const bool issuer = r == 0 && lead;
     long long tw = 0, ta = 0, tb = 0, tm = 0;
     const long long t_begin = clock64();
     const uint32_t idesc = idesc_bf16_f32(kRows, kG, 0, 0);
@@ -222,9 +233,9 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
       }
     };
 
-    float c[kH];
+    float c[UPT];
 #pragma unroll
-    for (int u = 0; u < kH; ++u) c[u] = 0.0f;
+    for (int u = 0; u < UPT; ++u) c[u] = 0.0f;
 
     int step = 0;
     for (int pi = 0; pi < P.nph; ++pi) {
@@ -286,20 +297,20 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
         const float* c0 = (pi == 0 && !ph.zero_init && valid) ? P.c0 : nullptr;
         float* xh0 = (save && valid && ph.sv.xh) ? ph.sv.xh + (size_t)b * T * K : nullptr;
 #pragma unroll
-        for (int p16 = 0; p16 < 4; ++p16) {
+        for (int p16 = 0; p16 < UPT / 16; ++p16) {
           float hv[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            hv[j] = h0 ? __ldg(&h0[(size_t)b * kH + p16 * 16 + j]) : 0.0f;
-            c[p16 * 16 + j] = c0 ? __ldg(&c0[(size_t)b * kH + p16 * 16 + j]) : 0.0f;
+            hv[j] = h0 ? __ldg(&h0[(size_t)b * kH + u0 + p16 * 16 + j]) : 0.0f;
+            c[p16 * 16 + j] = c0 ? __ldg(&c0[(size_t)b * kH + u0 + p16 * 16 + j]) : 0.0f;
           }
-          h_store8(p16 * 2, hv);
-          h_store8(p16 * 2 + 1, hv + 8);
-          if (xh0) store16(xh0 + p16 * 16, hv, xh_vec);
+          h_store8((u0 >> 3) + p16 * 2, hv);
+          h_store8((u0 >> 3) + p16 * 2 + 1, hv + 8);
+          if (xh0) store16(xh0 + u0 + p16 * 16, hv, xh_vec);
         }
       }
       // ---- x_0 ----
-      {
+      if (lead) {
         float xn[kXK];
 #pragma unroll
         for (int k = 0; k < kXK; ++k)
@@ -315,7 +326,7 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
       fence_proxy_async_smem();
       tc_fence_before();
       bar_workers(NW);
-      if (r == 0) issue_mmas();
+      if (issuer) issue_mmas();
 
       const bool next_phase_carries = (pi + 1 < P.nph) && !P.ph[pi + 1].zero_init;
       for (int t = 0; t < T; ++t) {
@@ -323,7 +334,7 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
         float xn[kXK];
 #pragma unroll
         for (int k = 0; k < kXK; ++k) xn[k] = 0.0f;
-        if (!ph.ar && more) {
+        if (!ph.ar && more && lead) {
 #pragma unroll
           for (int k = 0; k < kXK; ++k)
             xn[k] = (valid && k < in_dim) ? __ldg(&ph.x[((size_t)b * ph.x_T + t + 1) * in_dim + k]) : 0.0f;
@@ -351,25 +362,37 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
         float yacc[OD];
 #pragma unroll
         for (int d = 0; d < OD; ++d) yacc[d] = 0.0f;
-        // 8 hidden units per pass; the accumulator columns of pass p+1 are in flight (tcgen05.ld) during the math of p
-        float gt[2][4][8];
+        // 8 hidden units per pass; at WPG = 4 the accumulator columns of pass p+1 are in flight (tcgen05.ld) during the
+        // math of pass p
+        float gt[PF ? 2 : 1][4][8];
+        const uint32_t t_col = t_row + (uint32_t)u0;
+        if (PF) {
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) tmem_ld8(t_row + gi * kH, gt[0][gi]);
-        tmem_ld_wait();
+          for (int gi = 0; gi < 4; ++gi) tmem_ld8(t_col + gi * kH, gt[0][gi]);
+          tmem_ld_wait();
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) pin8(gt[0][gi]);
+          for (int gi = 0; gi < 4; ++gi) pin8(gt[0][gi]);
+        }
 #pragma unroll
-        for (int p8 = 0; p8 < 8; ++p8) {
-          float (&ga)[4][8] = gt[p8 & 1];
-          if (p8 + 1 < 8) {
+        for (int p8 = 0; p8 < NPASS; ++p8) {
+          float (&ga)[4][8] = gt[PF ? (p8 & 1) : 0];
+          if (PF) {
+            if (p8 + 1 < NPASS) {
 #pragma unroll
-            for (int gi = 0; gi < 4; ++gi) tmem_ld8(t_row + gi * kH + (p8 + 1) * 8, gt[(p8 + 1) & 1][gi]);
+              for (int gi = 0; gi < 4; ++gi) tmem_ld8(t_col + gi * kH + (p8 + 1) * 8, gt[PF ? ((p8 + 1) & 1) : 0][gi]);
+            }
+          } else {
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) tmem_ld8(t_col + gi * kH + p8 * 8, ga[gi]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) pin8(ga[gi]);
           }
           float hn[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int u = p8 * 8 + j;
-            const float4 bb = bk->bias4[u];
+            const float4 bb = bk->bias4[u0 + u];
             float ai, af, ao;
             if (REC == FOV_REC_HARD_SIGMOID) {
               ai = __saturatef(fmaf(0.2f, ga[0][j], bb.x));
@@ -386,11 +409,11 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
             hn[j] = ao * tanh5(cn);
             ga[0][j] = ai; ga[1][j] = af; ga[2][j] = ag; ga[3][j] = ao;
           }
-          h_store8(p8, hn);
+          h_store8((u0 >> 3) + p8, hn);
           if (ph.has_head) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4* wr = reinterpret_cast<const float4*>(&bk->Wo_s[(p8 * 8 + j) * OD]);
+              const float4* wr = reinterpret_cast<const float4*>(&bk->Wo_s[(u0 + p8 * 8 + j) * OD]);
 #pragma unroll
               for (int d4 = 0; d4 < OD / 4; ++d4) {
                 const float4 w4 = wr[d4];
@@ -403,51 +426,72 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
           }
           if (gates_p) {
 #pragma unroll
-            for (int gi = 0; gi < 4; ++gi) store8(gates_p + gi * kH + p8 * 8, ga[gi], 4);
+            for (int gi = 0; gi < 4; ++gi) store8(gates_p + gi * kH + u0 + p8 * 8, ga[gi], 4);
           }
           if (c_p) {
             float cv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) cv[j] = c[p8 * 8 + j];
-            store8(c_p + p8 * 8, cv, 4);
+            store8(c_p + u0 + p8 * 8, cv, 4);
           }
-          if (hseq_p) store8(hseq_p + p8 * 8, hn, 4);
-          if (xh_next) store8(xh_next + p8 * 8, hn, xh_next_vec);
-          if (hT_p) store8(hT_p + p8 * 8, hn, 4);
-          if (p8 + 1 < 8) {
+          if (hseq_p) store8(hseq_p + u0 + p8 * 8, hn, 4);
+          if (xh_next) store8(xh_next + u0 + p8 * 8, hn, xh_next_vec);
+          if (hT_p) store8(hT_p + u0 + p8 * 8, hn, 4);
+          if (PF && p8 + 1 < NPASS) {
             tmem_ld_wait();
 #pragma unroll
-            for (int gi = 0; gi < 4; ++gi) pin8(gt[(p8 + 1) & 1][gi]);
+            for (int gi = 0; gi < 4; ++gi) pin8(gt[PF ? ((p8 + 1) & 1) : 0][gi]);
           }
         }
         tc_fence_before();                 // my tcgen05.ld of this accumulator are complete before the next MMAs
         if (dbg) { k2 = clock64(); ta += k2 - k1; }
 
         if (ph.has_head) {
-          const size_t o = rowt * (size_t)P.out_dim;
+          if (WPG == 8) {
+            // the thread that owns units 32..63 of the row hands its partial head sums to the lead thread
+            float* yp = &bk->ypart[(g * kRows + r) * OD];
+            if (!lead) {
 #pragma unroll
-          for (int d = 0; d < OD; ++d) {
-            float sum = yacc[d] + bk->bo_s[d];
-            const bool live = d < P.out_dim;
-            if (live && valid && ph.extra) sum += __ldg(&ph.extra[o + d]);
-            const float yv = head_act_fn(P.head_act, sum);
-            if (live && valid) ph.y[o + d] = yv;
-            if (ph.ar && d < kXK) xn[d] = live ? yv : 0.0f;
+              for (int d4 = 0; d4 < OD / 4; ++d4)
+                reinterpret_cast<float4*>(yp)[d4] = make_float4(yacc[d4 * 4], yacc[d4 * 4 + 1], yacc[d4 * 4 + 2], yacc[d4 * 4 + 3]);
+            }
+            bar_group(g, GT);
+            if (lead) {
+#pragma unroll
+              for (int d4 = 0; d4 < OD / 4; ++d4) {
+                const float4 v = reinterpret_cast<const float4*>(yp)[d4];
+                yacc[d4 * 4] += v.x; yacc[d4 * 4 + 1] += v.y; yacc[d4 * 4 + 2] += v.z; yacc[d4 * 4 + 3] += v.w;
+              }
+            }
+          }
+          if (lead) {
+            const size_t o = rowt * (size_t)P.out_dim;
+#pragma unroll
+            for (int d = 0; d < OD; ++d) {
+              float sum = yacc[d] + bk->bo_s[d];
+              const bool live = d < P.out_dim;
+              if (live && valid && ph.extra) sum += __ldg(&ph.extra[o + d]);
+              const float yv = head_act_fn(P.head_act, sum);
+              if (live && valid) ph.y[o + d] = yv;
+              if (ph.ar && d < kXK) xn[d] = live ? yv : 0.0f;
+            }
           }
         }
         if (more) {
-          x_store(xn);
-          if (save && valid && ph.sv.xh) {
-            float* xr = ph.sv.xh + (rowt + 1) * K + kH;
+          if (lead) {
+            x_store(xn);
+            if (save && valid && ph.sv.xh) {
+              float* xr = ph.sv.xh + (rowt + 1) * K + kH;
 #pragma unroll
-            for (int k = 0; k < kXK + 3; ++k)
-              if (kH + k < K) xr[k] = k < kXK ? xn[k < kXK ? k : 0] : 0.0f;
+              for (int k = 0; k < kXK + 3; ++k)
+                if (kH + k < K) xr[k] = k < kXK ? xn[k < kXK ? k : 0] : 0.0f;
+            }
           }
           fence_proxy_async_smem();
-          bar_group(g);
+          bar_group(g, GT);
           long long k3 = 0;
           if (dbg) k3 = clock64();
-          if (r == 0) issue_mmas();
+          if (issuer) issue_mmas();
           if (dbg) tm += clock64() - k3;
         }
         ++step;
@@ -456,11 +500,11 @@ __global__ void __launch_bounds__(kRows * NG, 1) lstm_tc_fwd_kernel(const __grid
     }
     if (valid && P.cT) {
 #pragma unroll
-      for (int p16 = 0; p16 < 4; ++p16) {
-        float cv[16];
+      for (int p8 = 0; p8 < NPASS; ++p8) {
+        float cv[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) cv[j] = c[p16 * 16 + j];
-        store16(P.cT + (size_t)b * kH + p16 * 16, cv, 4);
+        for (int j = 0; j < 8; ++j) cv[j] = c[p8 * 8 + j];
+        store8(P.cT + (size_t)b * kH + u0 + p8 * 8, cv, 4);
       }
     }
     if (dbg) {
@@ -480,12 +524,12 @@ size_t tc_smem_bytes() {
   return (size_t)(NS + 1) * kBTerm + (size_t)NG * (NS + 1) * kATerm + sizeof(LstmTcBook<OD>) + 1024;
 }
 
-template <int NS, int NG, int REC, int OD, bool TRAIN>
-int launch_tc_t(const LstmTcParams& P, cudaStream_t st) {
+template <int NS, int NG, int REC, int OD, bool TRAIN, int WPG>
+int launch_tc_w(const LstmTcParams& P, cudaStream_t st) {
   const size_t smem = tc_smem_bytes<NS, NG, OD>();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_tc_fwd_kernel<NS, NG, REC, OD, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(lstm_tc_fwd_kernel<NS, NG, REC, OD, TRAIN, WPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) {
       fov_set_error("fov_lstm (tensor-core): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -495,9 +539,21 @@ int launch_tc_t(const LstmTcParams& P, cudaStream_t st) {
   }
   const int per_cta = kRows * NG;
   const int grid = (P.B + per_cta - 1) / per_cta;
-  lstm_tc_fwd_kernel<NS, NG, REC, OD, TRAIN><<<grid, kRows * NG, smem, st>>>(P);
+  lstm_tc_fwd_kernel<NS, NG, REC, OD, TRAIN, WPG><<<grid, 32 * WPG * NG, smem, st>>>(P);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
+}
+
+int g_lstm_tc_wpg = 8;                       // diagnostics: 4 = one thread per sequence everywhere
+
+template <int NS, int NG, int REC, int OD, bool TRAIN>
+int launch_tc_t(const LstmTcParams& P, cudaStream_t st) {
+  // 8 warps per group when a CTA runs ONE group (batches below 128 x 148 sequences, default two-term arithmetic): the
+  // step is then a serial MMA -> epilogue chain and the extra warps shorten it (B=4096 AR decode: 0.091 vs 0.112 ms).
+  // With two groups per CTA 16 warps get 128 registers each, spill, and lose 5 % to the 4-warp form (measured).
+  if (NS == 2 && NG == 1 && g_lstm_tc_wpg == 8)
+    return launch_tc_w<NS, NG, REC, OD, TRAIN, (NS == 2 && NG == 1 ? 8 : 4)>(P, st);
+  return launch_tc_w<NS, NG, REC, OD, TRAIN, 4>(P, st);
 }
 
 template <int NS, int NG, int REC, int OD>
@@ -518,6 +574,7 @@ int g_lstm_tc_dbg = 0;
 }  // namespace
 
 extern "C" void fov_debug_lstm_tc_enable(int on) { g_lstm_tc_dbg = on; }
+extern "C" void fov_debug_lstm_tc_wpg(int wpg) { g_lstm_tc_wpg = wpg; }
 extern "C" int fov_debug_lstm_tc_read(unsigned long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_lstm_tc_timeline, sizeof(unsigned long long) * 8);
 }

@@ -63,8 +63,9 @@ def timing():
         m2 = fov.fov_seq2seq_mu_var(seed=3, device=dev)
         enc = torch.randn(Bi, 10, 6, device=dev) * 0.3
         last = enc[:, -1:, :].contiguous()
-        for mode, name in ((1, "tc"), (-1, "fp32")):
-            lib.fov_debug_lstm_tc(mode)
+        for mode, name in ((1, "tc"), (2, "tc_wpg4"), (-1, "fp32")):
+            lib.fov_debug_lstm_tc(1 if mode == 2 else mode)
+            lib.fov_debug_lstm_tc_wpg(4 if mode == 2 else 8)
             with torch.no_grad():
                 for _ in range(3):
                     m2._forward([enc, last], False, teacher_forcing=False, steps=10)
