@@ -13,7 +13,7 @@
 #include <stdlib.h>
 
 // diagnostics / A-B testing: -1 = never use the tensor-core forward, 0 = choose, 1 = whenever the shape allows
-static int g_lstm_tc_mode = 0;
+static int g_lstm_tc_mode = getenv("FOV_LSTM_TC") ? atoi(getenv("FOV_LSTM_TC")) : 0;
 extern "C" void fov_debug_lstm_tc(int mode) { g_lstm_tc_mode = mode; }
 // A/B switch for the tensor-core LSTM weight gradient (needs fov_lstm_grads.ws).  History: on unpadded 70-float [h|x]
 // rows it took the unaligned gather path of wgrad_tc.cu and lost to the SIMT kernels (11.07 vs 10.96 ms per config-2
