@@ -283,17 +283,18 @@ def other_workloads(dev, peaks, compute):
 
     # ---- sample builders: windows of a full-size video, one-hot heatmaps; HBM-bound ----
     from longterm360fov_b200 import ops as _o
-    vid = torch.rand(48, 600, 90, device=dev) * 2 - 1
+    SEC, NHM = 3000, 16384                                    # outputs of 1.5 GB / 1.3 GB: well beyond the 126 MB L2
+    vid = torch.rand(48, SEC, 90, device=dev) * 2 - 1
     ms = _time_cuda(lambda: _o.reshape2second_stacks(vid, collapse_user=False, stride=1), reps=10, warm=3)
-    nwin = 600 - 10 + 1 - 10
+    nwin = SEC - 10 + 1 - 10
     wbytes = 3 * nwin * 48 * 10 * 90 * 4                      # three window tensors written; the source stays in L2
-    fr = torch.nn.functional.normalize(torch.randn(4096, 30, 3, device=dev), dim=-1)
+    fr = torch.nn.functional.normalize(torch.randn(NHM, 30, 3, device=dev), dim=-1)
     ms_h = _time_cuda(lambda: _o.one_hot_heatmaps(fr), reps=10, warm=3)
-    hbytes = 4096 * 36 * 18 * 30 * 4
+    hbytes = NHM * 36 * 18 * 30 * 4
     res["sample_builders"] = {
-        "window_stacks": {"shape": "48 viewers x 600 s x 90, stride 1", "windows_per_s": nwin * 48 / (ms * 1e-3),
+        "window_stacks": {"shape": "48 viewers x %d s x 90, stride 1" % SEC, "windows_per_s": nwin * 48 / (ms * 1e-3),
                           "ms": ms, "hbm_gbs": wbytes / (ms * 1e-3) / 1e9, "frac_of_copy_peak": wbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-        "one_hot_heatmaps": {"shape": "4096 seconds x 30 frames -> (36,18,30)", "heatmaps_per_s": 4096 / (ms_h * 1e-3),
+        "one_hot_heatmaps": {"shape": "%d seconds x 30 frames -> (36,18,30)" % NHM, "heatmaps_per_s": NHM / (ms_h * 1e-3),
                              "ms": ms_h, "hbm_gbs": hbytes / (ms_h * 1e-3) / 1e9,
                              "frac_of_copy_peak": hbytes / (ms_h * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
     del vid, fr
