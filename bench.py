@@ -264,6 +264,20 @@ def other_workloads(dev, peaks, compute):
                 "Dense+tanh head and re-feed in the epilogue) unless compute=fp32; bound by the gate algebra "
                 "(MUFU/issue), not by HBM or the tensor pipe"}
 
+    # ---- config 3's model, training at a batch that fills the machine with 128-sequence tiles: tcgen05 forward (saved
+    #      tensors written) + tcgen05 BPTT + one tensor-core weight-gradient launch per LSTM ----
+    Bl = 148 * 256
+    for tf in (True, False):
+        m2t = fov.fov_seq2seq_mu_var(seed=3, device=dev, teacher_forcing=tf).compile("Adam", "mean_squared_error")
+        m2t.set_compute(compute)
+        e_ = torch.randn(Bl, 10, 6, device=dev) * 0.3
+        d_ = torch.randn(Bl, 10 if tf else 1, 6, device=dev) * 0.3
+        t_ = torch.randn(Bl, 10, 6, device=dev) * 0.3
+        ms = _time_cuda(lambda: m2t.train_step_device([e_, d_], [t_]), reps=10, warm=3)
+        res["fov_seq2seq_mu_var_train_" + ("teacher_forced" if tf else "autoregressive")] = {
+            "batch": Bl, "unit": "sequences/s", "value": Bl / (ms * 1e-3), "ms_per_step": ms, "compute": compute}
+        del m2t
+
     # ---- config 2 at the reference's own batch size (32): launch-bound, eager vs CUDA-graph replay ----
     Bs = 32
     px, py = data.make_m3_batch(Bs, NUM_USER, seed=11)

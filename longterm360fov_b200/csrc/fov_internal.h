@@ -38,6 +38,10 @@ int fov_conv_bwd_data_preflipped(const fov_conv_cfg* fwd_cfg, const float* dy, c
 // Persistent fc-LSTM forward on tensor cores (lstm_seq2seq_tc.cu); same contract as fov_lstm_seq2seq_fwd
 bool lstm_tc_supported(const fov_lstm_cfg* cfg);
 int lstm_tc_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w, const fov_lstm_io* io, cudaStream_t st);
+// Persistent fc-LSTM BPTT on tensor cores: writes dz_enc / dz_dec / dpre like the fp32 kernel (no weight gradients)
+bool lstm_tc_bwd_supported(const fov_lstm_cfg* cfg);
+int lstm_tc_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w, const fov_lstm_io* io, const fov_lstm_grads* g,
+                cudaStream_t st);
 
 // ---- tensor-core (tcgen05) implicit-GEMM convolution family (conv_tc.cu) -------------------
 // One K segment of the implicit-GEMM A operand: an NHWC activation tensor convolved with its

@@ -20,6 +20,8 @@ extern "C" void fov_debug_lstm_tc(int mode) { g_lstm_tc_mode = mode; }
 // step), hence the rows padded to a multiple of 4 floats and the single aligned launch per LSTM.
 static int g_lstm_wgrad_tc = getenv("FOV_LSTM_WGRAD_TC") ? atoi(getenv("FOV_LSTM_WGRAD_TC")) : 1;
 extern "C" void fov_debug_lstm_wgrad_tc(int on) { g_lstm_wgrad_tc = on; }
+static int g_lstm_bptt_tc = getenv("FOV_LSTM_BPTT_TC") ? atoi(getenv("FOV_LSTM_BPTT_TC")) : 1;   // A/B switch
+extern "C" void fov_debug_lstm_bptt_tc(int on) { g_lstm_bptt_tc = on; }
 
 namespace {
 
@@ -500,7 +502,12 @@ extern "C" int fov_lstm_seq2seq_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
   const int bt = 4 * spt, grid = (cfg->B + bt - 1) / bt;
   const size_t smem = bwd_smem_bytes(spt);
   const bool hsb = cfg->rec_act == FOV_REC_HARD_SIGMOID;
-  if (spt == 4)
+  // tensor-core BPTT (lstm_seq2seq_tc.cu): 128-sequence tiles, dh_rec = dZ x U^T on tcgen05.  One 4-warp CTA per SM:
+  // it pays once every SM has a tile (mu/var model train step, B=37888: 2.66 vs 3.59 ms; B=8880, 70 CTAs: equal)
+  if (cfg->math != FOV_MATH_FP32 && g_lstm_tc_mode >= 0 && g_lstm_bptt_tc && lstm_tc_bwd_supported(cfg) &&
+      (g_lstm_tc_mode > 0 || cfg->B >= 128 * fov_num_sms()))
+    rc = lstm_tc_bwd(&P.cfg, w, io, g, st);
+  else if (spt == 4)
     rc = hsb ? launch(lstm_seq2seq_bwd_kernel<4, FOV_REC_HARD_SIGMOID>, P, grid, smem, st)
              : launch(lstm_seq2seq_bwd_kernel<4, FOV_REC_SIGMOID>, P, grid, smem, st);
   else

@@ -579,6 +579,350 @@ extern "C" int fov_debug_lstm_tc_read(unsigned long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_lstm_tc_timeline, sizeof(unsigned long long) * 8);
 }
 
+// =====================================================================================================================
+// Persistent fc-LSTM BPTT on tensor cores: ONE launch walks the decoder steps T_dec-1..0 and then the encoder steps.
+//   * thread = one sequence (accumulator row); dc of its 64 hidden units lives in registers for the whole sequence;
+//   * per step the thread turns the saved gates / cell states of its row into the gate pre-activation gradients dZ_t
+//     (written to HBM for the time-batched weight gradients, and as bf16 terms into the swizzled A-operand rows);
+//   * one tcgen05.mma chain  [dh_rec_{t-1} | dx_t] = dZ_t x [U | W]^T  (K = 4H = 256; the Keras layouts (H,4H) / (in,4H)
+//     ARE the K-major B operand, rows = N); dh_rec is read back from TMEM by the next (earlier) step, dx_t - only needed
+//     when decoding autoregressively - re-enters through the Dense head chain dy_{t-1} += dx_t.
+// Same contract as the fp32 kernel of lstm_seq2seq.cu (saved tensors in, dz / dpre out).
+// =====================================================================================================================
+namespace {
+
+struct BwdTcPhase {
+  const float *Uk, *Wk;                    // recurrent (H,4H); kernel (in,4H), read in autoregressive mode only
+  int in_dim, T;
+  int ar, has_head, zero_carry;            // zero_carry: the phase starts from dh = dc = 0
+  const float *dy, *y, *dhseq;             // (B,T,out) x2; optional (B,T,H)
+  float *dpre, *dz;                        // (B,T,out); (B,T,4H)
+  const float *gates, *c;                  // saved activated gates (B,T,4H), cell states (B,T,H)
+  const float* c_init;                     // c_{-1}: base pointer + per-sequence stride, or NULL (zeros)
+  long long c_init_stride;
+};
+struct LstmTcBwdParams {
+  BwdTcPhase ph[2];
+  int nph, B, out_dim, head_act;
+  const float* Wo;
+};
+template <int OD>
+struct LstmTcBwdBook {
+  float Wo_s[kH * OD];
+  uint64_t tmem_full;
+  uint32_t tmem_ptr;
+};
+
+template <int REC>
+__device__ __forceinline__ float rec_grad(float a) {
+  if (REC == FOV_REC_HARD_SIGMOID) return (a > 0.0f && a < 1.0f) ? 0.2f : 0.0f;
+  return a * (1.0f - a);
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+template <int NS, int REC, int OD, bool AR>
+__global__ void __launch_bounds__(kRows, 1) lstm_tc_bwd_kernel(const __grid_constant__ LstmTcBwdParams P) {
+  constexpr int NB = AR ? kH + kXK : kH;                 // B rows = accumulator columns: dh_rec (+ dx)
+  constexpr uint32_t kBTile = NB * 128;                  // one 64-wide k tile of one term of [U | W]^T
+  constexpr uint32_t kAOff = NS * 4 * kBTile;
+  using Book = LstmTcBwdBook<OD>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  Book* bk = reinterpret_cast<Book*>(smem + kAOff + NS * 4 * kATerm);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(smem_u32(&bk->tmem_full), 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&bk->tmem_ptr), 128);
+    tmem_relinquish();
+  }
+  for (int idx = tid; idx < kH * OD; idx += kRows) {
+    const int u = idx / OD, d = idx - u * OD;
+    bk->Wo_s[idx] = (P.out_dim > 0 && d < P.out_dim) ? __ldg(&P.Wo[u * P.out_dim + d]) : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = bk->tmem_ptr;
+
+  const int r = tid;
+  const long long b = (long long)blockIdx.x * kRows + r;
+  const bool valid = b < P.B;
+  const uint32_t rowoff = (uint32_t)r * 128u, rsw = (uint32_t)(r & 7);
+  const uint32_t t_row = tmem_d + ((uint32_t)(warp * 32) << 16);
+  const uint32_t idesc = idesc_bf16_f32(kRows, NB, 0, 0);
+
+  float dc[kH];
+#pragma unroll
+  for (int u = 0; u < kH; ++u) dc[u] = 0.0f;
+  bool pending = false, acc_valid = false;
+  uint32_t waits = 0;
+
+  for (int pi = 0; pi < P.nph; ++pi) {
+    const BwdTcPhase& ph = P.ph[pi];
+    const int T = ph.T;
+    if (pending) {                                       // the weights may only change once the last MMA has read them
+      mbar_wait(smem_u32(&bk->tmem_full), waits & 1u);
+      ++waits; pending = false; acc_valid = true;
+    }
+    if (ph.zero_carry) {
+      acc_valid = false;
+#pragma unroll
+      for (int u = 0; u < kH; ++u) dc[u] = 0.0f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ---- [U | W]^T: row n of the Keras tensor = B-operand row n, 256 k values = four 64-wide swizzled tiles ----
+    for (int item = tid; item < NB * 4; item += kRows) {
+      const int n = item >> 2, kt = item & 3;
+      const float* src = nullptr;
+      if (n < kH) src = ph.Uk + (size_t)n * kG + kt * 64;
+      else if (AR && ph.ar && n - kH < ph.in_dim) src = ph.Wk + (size_t)(n - kH) * kG + kt * 64;
+      const uint32_t nsw = (uint32_t)(n & 7), noff = (uint32_t)n * 128u;
+#pragma unroll 2
+      for (int c8 = 0; c8 < 8; ++c8) {
+        float v[8];
+        if (src) load8(src + c8 * 8, v);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+        }
+        uint2 lo[NS], hi[NS];
+        split4<NS>(make_float4(v[0], v[1], v[2], v[3]), lo);
+        split4<NS>(make_float4(v[4], v[5], v[6], v[7]), hi);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          *reinterpret_cast<uint4*>(smem + (uint32_t)(s * 4 + kt) * kBTile + noff + ((((uint32_t)c8) ^ nsw) << 4)) =
+              make_uint4(lo[s].x, lo[s].y, hi[s].x, hi[s].y);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    const bool next_carries = (pi + 1 < P.nph) && !P.ph[pi + 1].zero_carry;
+    for (int t = T - 1; t >= 0; --t) {
+      if (pending) {
+        mbar_wait(smem_u32(&bk->tmem_full), waits & 1u);
+        ++waits; pending = false; acc_valid = true;
+      }
+      __syncwarp();
+      tc_fence_after();
+      const size_t rowt = (size_t)b * T + t;
+
+      // ---- Dense head: dpre = (dy + dx_{t+1}) * act'(y) ----
+      float dpre[OD];
+#pragma unroll
+      for (int d = 0; d < OD; ++d) dpre[d] = 0.0f;
+      if (ph.has_head) {
+        float dxv[kXK];
+#pragma unroll
+        for (int d = 0; d < kXK; ++d) dxv[d] = 0.0f;
+        if (AR && ph.ar && acc_valid && t < T - 1) {
+          tmem_ld16(t_row + kH, dxv);
+          tmem_ld_wait();
+        }
+        const size_t o = rowt * (size_t)P.out_dim;
+#pragma unroll
+        for (int d = 0; d < OD; ++d) {
+          const bool live = valid && d < P.out_dim;
+          float gy = live ? __ldg(&ph.dy[o + d]) : 0.0f;
+          if (d < kXK) gy += dxv[d];
+          const float yv = live ? __ldg(&ph.y[o + d]) : 0.0f;
+          const float dp = live ? gy * fov_act_grad(P.head_act, yv) : 0.0f;
+          dpre[d] = dp;
+          if (live) ph.dpre[o + d] = dp;
+        }
+      }
+
+      const float* g_row = ph.gates + rowt * kG;
+      const float* c_row = ph.c + rowt * kH;
+      const float* cp_row = t > 0 ? c_row - kH : (ph.c_init ? ph.c_init + (size_t)b * ph.c_init_stride : nullptr);
+      const float* dhs_row = ph.dhseq ? ph.dhseq + rowt * kH : nullptr;
+      float* dz_row = ph.dz + rowt * kG;
+      // the row's saved tensors of the NEXT (earlier) step -> L2 while this step computes: with four warps per SM the
+      // eight load / compute passes of a step would otherwise each expose a full DRAM round trip
+      if (valid && t > 0) {
+        const char* pg = reinterpret_cast<const char*>(g_row - kG);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(pg + i * 128));
+        if (t > 1) {
+          const char* pc = reinterpret_cast<const char*>(c_row - 2 * kH);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pc));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + 128));
+        }
+        if (dhs_row) {
+          const char* pd = reinterpret_cast<const char*>(dhs_row - kH);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pd));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + 128));
+        }
+      }
+#pragma unroll
+      for (int p8 = 0; p8 < 8; ++p8) {
+        float acc8[8], gi8[8], gf8[8], gg8[8], go8[8], ct8[8], cp8[8], dhs8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc8[j] = 0.0f; gi8[j] = 0.0f; gf8[j] = 0.0f; gg8[j] = 0.0f; go8[j] = 0.0f;
+                                       ct8[j] = 0.0f; cp8[j] = 0.0f; dhs8[j] = 0.0f; }
+        if (acc_valid) tmem_ld8(t_row + p8 * 8, acc8);
+        if (valid) {
+          load8(g_row + p8 * 8, gi8); load8(g_row + kH + p8 * 8, gf8);
+          load8(g_row + 2 * kH + p8 * 8, gg8); load8(g_row + 3 * kH + p8 * 8, go8);
+          load8(c_row + p8 * 8, ct8);
+          if (cp_row) load8(cp_row + p8 * 8, cp8);
+          if (dhs_row) load8(dhs_row + p8 * 8, dhs8);
+        }
+        if (acc_valid) {
+          tmem_ld_wait();
+          pin8(acc8);
+        }
+        float dz[4][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int u = p8 * 8 + j;
+          float dh = acc8[j] + dhs8[j];
+          if (ph.has_head) {
+            const float4* wr = reinterpret_cast<const float4*>(&bk->Wo_s[u * OD]);
+#pragma unroll
+            for (int d4 = 0; d4 < OD / 4; ++d4) {
+              const float4 w4 = wr[d4];
+              dh = fmaf(dpre[d4 * 4], w4.x, dh); dh = fmaf(dpre[d4 * 4 + 1], w4.y, dh);
+              dh = fmaf(dpre[d4 * 4 + 2], w4.z, dh); dh = fmaf(dpre[d4 * 4 + 3], w4.w, dh);
+            }
+          }
+          const float tc_ = tanh5(ct8[j]);
+          const float dog = dh * tc_;
+          const float dct = fmaf(dh * go8[j], 1.0f - tc_ * tc_, dc[u]);
+          dc[u] = valid ? dct * gf8[j] : 0.0f;
+          dz[0][j] = dct * gg8[j] * rec_grad<REC>(gi8[j]);
+          dz[1][j] = dct * cp8[j] * rec_grad<REC>(gf8[j]);
+          dz[2][j] = dct * gi8[j] * (1.0f - gg8[j] * gg8[j]);
+          dz[3][j] = dog * rec_grad<REC>(go8[j]);
+        }
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          if (valid) store8(dz_row + gi * kH + p8 * 8, dz[gi], 4);
+          uint2 lo[NS], hi[NS];
+          split4<NS>(make_float4(dz[gi][0], dz[gi][1], dz[gi][2], dz[gi][3]), lo);
+          split4<NS>(make_float4(dz[gi][4], dz[gi][5], dz[gi][6], dz[gi][7]), hi);
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+            *reinterpret_cast<uint4*>(smem + kAOff + (uint32_t)(s * 4 + gi) * kATerm + rowoff + ((((uint32_t)p8) ^ rsw) << 4)) =
+                make_uint4(lo[s].x, lo[s].y, hi[s].x, hi[s].y);
+        }
+      }
+      tc_fence_before();
+      acc_valid = false;
+      const bool need_mma = t > 0 || next_carries;
+      if (need_mma) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          uint32_t acc = 0;
+#pragma unroll
+          for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+#pragma unroll
+              for (int sum = NS - 1; sum >= 0; --sum) {
+#pragma unroll
+                for (int sa = 0; sa <= sum; ++sa) {
+                  const int sb = sum - sa;
+                  umma_bf16(tmem_d, desc_at(kDescHi128, base + kAOff + (uint32_t)(sa * 4 + kt) * kATerm + k4 * 32),
+                            desc_at(kDescHi128, base + (uint32_t)(sb * 4 + kt) * kBTile + k4 * 32), idesc, acc);
+                  acc = 1;
+                }
+              }
+            }
+          }
+          umma_commit(smem_u32(&bk->tmem_full));
+        }
+        pending = true;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 128);
+}
+
+template <int NS, int REC, int OD, bool AR>
+int launch_tc_bwd(const LstmTcBwdParams& P, cudaStream_t st) {
+  constexpr int NB = AR ? kH + kXK : kH;
+  const size_t smem = (size_t)NS * 4 * NB * 128 + (size_t)NS * 4 * kATerm + sizeof(LstmTcBwdBook<OD>) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_tc_bwd_kernel<NS, REC, OD, AR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) {
+      fov_set_error("fov_lstm BPTT (tensor-core): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return FOV_ERR_CUDA;
+    }
+    configured = true;
+  }
+  lstm_tc_bwd_kernel<NS, REC, OD, AR><<<(P.B + kRows - 1) / kRows, kRows, smem, st>>>(P);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
+template <int NS, int REC>
+int launch_tc_bwd_oa(const LstmTcBwdParams& P, bool ar, cudaStream_t st) {
+  if (P.out_dim <= 8) return ar ? launch_tc_bwd<NS, REC, 8, true>(P, st) : launch_tc_bwd<NS, REC, 8, false>(P, st);
+  return ar ? launch_tc_bwd<NS, REC, 16, true>(P, st) : launch_tc_bwd<NS, REC, 16, false>(P, st);
+}
+
+}  // namespace
+
+// teacher-forced phases never read the input kernel, so any input width works; autoregressive decoding needs in_dec <= 16
+bool lstm_tc_bwd_supported(const fov_lstm_cfg* cfg) {
+  if (cfg->H != kH || (cfg->math != FOV_MATH_BF16 && cfg->math != FOV_MATH_BF16X2)) return false;
+  if (cfg->out_dim > 16) return false;
+  if (cfg->T_dec > 0 && !cfg->teacher_forcing && cfg->in_dec > kXK) return false;
+  return true;
+}
+
+int lstm_tc_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w, const fov_lstm_io* io, const fov_lstm_grads* g,
+                cudaStream_t st) {
+  LstmTcBwdParams P{};
+  P.B = cfg->B; P.out_dim = cfg->T_dec > 0 ? cfg->out_dim : 0; P.head_act = cfg->head_act; P.Wo = w->head_kernel;
+  const bool ar = cfg->T_dec > 0 && cfg->teacher_forcing == 0;
+  int n = 0;
+  if (cfg->T_dec > 0) {
+    BwdTcPhase& ph = P.ph[n++];
+    ph.Uk = w->dec_recurrent; ph.Wk = w->dec_kernel; ph.in_dim = cfg->in_dec; ph.T = cfg->T_dec;
+    ph.ar = ar; ph.has_head = P.out_dim > 0; ph.zero_carry = 1;
+    ph.dy = g->dy; ph.y = g->y; ph.dhseq = nullptr; ph.dpre = g->dpre; ph.dz = g->dz_dec;
+    ph.gates = io->dec.gates; ph.c = io->dec.c;
+    if (cfg->dec_zero_init) { ph.c_init = nullptr; ph.c_init_stride = 0; }
+    else if (cfg->T_enc > 0) { ph.c_init = io->enc.c + (size_t)(cfg->T_enc - 1) * kH; ph.c_init_stride = (long long)cfg->T_enc * kH; }
+    else { ph.c_init = io->c0; ph.c_init_stride = kH; }
+  }
+  if (cfg->T_enc > 0) {
+    BwdTcPhase& ph = P.ph[n++];
+    ph.Uk = w->enc_recurrent; ph.Wk = w->enc_kernel; ph.in_dim = cfg->in_enc; ph.T = cfg->T_enc;
+    ph.ar = 0; ph.has_head = 0; ph.zero_carry = (n == 1 || cfg->dec_zero_init) ? 1 : 0;
+    ph.dy = nullptr; ph.y = nullptr; ph.dhseq = g->dhseq_enc; ph.dpre = nullptr; ph.dz = g->dz_enc;
+    ph.gates = io->enc.gates; ph.c = io->enc.c; ph.c_init = io->c0; ph.c_init_stride = kH;
+  }
+  P.nph = n;
+  auto a16 = [](const void* q) { return (uintptr_t)q % 16 == 0; };
+  FOV_CHECK_ARG(a16(io->enc.gates) && a16(io->enc.c) && a16(io->dec.gates) && a16(io->dec.c) && a16(g->dz_enc) &&
+                    a16(g->dz_dec) && a16(g->dhseq_enc) && a16(io->c0) && a16(w->enc_recurrent) && a16(w->dec_recurrent) &&
+                    a16(w->dec_kernel),
+                "tensor-core fc-LSTM BPTT needs 16-byte aligned tensors");
+  const bool hs = cfg->rec_act == FOV_REC_HARD_SIGMOID;
+  if (cfg->math == FOV_MATH_BF16)
+    return hs ? launch_tc_bwd_oa<1, FOV_REC_HARD_SIGMOID>(P, ar, st) : launch_tc_bwd_oa<1, FOV_REC_SIGMOID>(P, ar, st);
+  return hs ? launch_tc_bwd_oa<2, FOV_REC_HARD_SIGMOID>(P, ar, st) : launch_tc_bwd_oa<2, FOV_REC_SIGMOID>(P, ar, st);
+}
+
 bool lstm_tc_supported(const fov_lstm_cfg* cfg) {
   if (cfg->H != kH || cfg->math < FOV_MATH_BF16 || cfg->math > FOV_MATH_BF16X3) return false;
   if (cfg->T_enc > 0 && cfg->in_enc > kXK) return false;

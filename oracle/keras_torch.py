@@ -256,7 +256,8 @@ def loss_and_grads(forward, w, inputs, targets, loss_fns, loss_weights=None):
     for o, y, fn, lw in zip(outs, targets, loss_fns, loss_weights):
         total = total + lw * fn(y, o)
     total.backward()
-    grads = {k: v.grad.detach().clone() for k, v in w.items()}
+    # a weight the loss does not depend on (e.g. the encoder under decoder_no_init_state) has a zero gradient
+    grads = {k: (v.grad.detach().clone() if v.grad is not None else torch.zeros_like(v)) for k, v in w.items()}
     return total.detach(), [o.detach() for o in outs], grads
 
 

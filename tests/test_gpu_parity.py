@@ -323,6 +323,44 @@ def test_lstm_tensor_core_forward_feeds_bptt(tf, B, force_lstm_tc):
         _grad_close(m.grads[k].cpu().numpy(), g_ref[k].numpy(), k)
 
 
+@pytest.mark.parametrize("tf,in_enc,B,kw", [(True, 90, 37, {}), (False, 90, 140, {}), (False, 6, 300, {"recurrent_activation": "sigmoid"}),
+                                            (True, 6, 129, {"decoder_no_init_state": True})])
+def test_lstm_tensor_core_bptt(tf, in_enc, B, kw, force_lstm_tc):
+    """Persistent BPTT on tcgen05 (dh_rec = dZ x U^T, the autoregressive dx chain through extra accumulator columns):
+    loss and every gradient against the float64 oracle; a 90-wide encoder input keeps the forward on the fp32 kernel
+    (teacher-forced phases never read the input kernel in the backward pass), sigmoid gates and the zero-state decoder
+    ablation included."""
+    fov = _cuda()
+    rng = np.random.default_rng(13)
+    w = _perturb(kn.init_fov_seq2seq(seed=4, num_encoder_tokens=in_enc), 5, 0.1)
+    enc = rng.uniform(-1, 1, (B, 10, in_enc)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 10 if tf else 1, 6)).astype(np.float32)
+    tgt = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    m = fov.fov_seq2seq(num_encoder_tokens=in_enc, teacher_forcing=tf, weights=w, **kw).compile("Adam", "mean_squared_error")
+    xs, ys = m._to_dev([enc, dec]), m._to_dev([tgt])
+    m.gflat.zero_()
+    loss = m._loss(m._forward(xs, True), ys)
+    loss.backward()
+    okw = {{"recurrent_activation": "ra"}.get(k, k): v for k, v in kw.items()}
+    l_ref, _, g_ref = kt.loss_and_grads(lambda ww, a, b: kt.fov_seq2seq_forward(ww, a, b, teacher_forcing=tf, **okw),
+                                        kt.to_torch(w),
+                                        [torch.tensor(enc, dtype=torch.float64), torch.tensor(dec, dtype=torch.float64)],
+                                        [torch.tensor(tgt, dtype=torch.float64)], [kt.mse])
+    assert abs(loss.item() - l_ref.item()) < 1e-5
+    for k in m.weight_order:
+        _grad_close(m.grads[k].cpu().numpy(), g_ref[k].numpy(), k)
+    # the fp32 BPTT kernel on the same saved tensors gives the same gradients
+    tc_grads = {k: m.grads[k].clone() for k in m.weight_order}
+    force_lstm_tc.fov_debug_lstm_bptt_tc(0)
+    try:
+        m.gflat.zero_()
+        m._loss(m._forward(xs, True), ys).backward()
+    finally:
+        force_lstm_tc.fov_debug_lstm_bptt_tc(1)
+    for k in m.weight_order:
+        _grad_close(tc_grads[k].cpu().numpy(), m.grads[k].cpu().numpy(), k, rtol=1e-3)
+
+
 def test_m3_with_tensor_core_target_lstm(force_lstm_tc):
     """Config 2's graph with the target fc-LSTM on tensor cores (additive head term from the others branch,
     encoder h sequence read by the reconstruction head): forward + gradients against the oracle."""
