@@ -7,11 +7,14 @@ the timed CPU baseline.
 
 Parity status
 -------------
-* Featuriser / windowing (``get_gt_target_xyz``, ``get_gt_target_xyz_oth``,
-  ``reshape2second_stacks``, ``generate_fake_batch_numpy``) are PINNED: the
-  golden vectors in ``tests/golden/reference_numpy_golden.npz`` were produced by
-  executing the reference's own function bodies from
-  ``/root/reference/mycode/utility.py`` (see ``tests/golden/make_reference_golden.py``).
+* Featuriser / windowing / sample builders / evaluation metric (``get_gt_target_xyz``,
+  ``get_gt_target_xyz_oth``, ``reshape2second_stacks`` incl. ``purelly_testing``,
+  ``generate_fake_batch_numpy``, ``get_whole_span``, ``xyz2thetaphi`` + the one-hot
+  index / ``_create_one_hot`` path, the FoV hit rate) are PINNED: the golden vectors in
+  ``tests/golden/reference_numpy_golden.npz`` were produced by executing the
+  reference's own function bodies from ``/root/reference/mycode/{utility,dataIO,
+  others_LSTM_span_whole,baseline_knn_mean}.py`` (see
+  ``tests/golden/make_reference_golden.py``).
 * The layer numerics (LSTM, ConvLSTM2D, Dense, Conv, losses, optimisers) live in
   un-vendored, un-pinned Keras 2.2.x / TensorFlow 1.x which cannot be installed
   here, and the reference ships no tests or golden vectors for them:

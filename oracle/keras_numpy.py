@@ -3,9 +3,9 @@ hot path, and of the four canonical model graphs (SURVEY.md section 8a').
 
 TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Parity status of this
 file: **parity unpinned** for the Keras layer numerics (Keras/TF1 is not
-installable here and the reference holds no golden vectors); the featuriser
-functions are pinned against the reference's own code via
-``tests/golden/reference_numpy_golden.npz``.
+installable here and the reference holds no golden vectors); the featuriser,
+windowing, whole-span, one-hot heatmap and hit-rate functions are pinned against
+the reference's own code via ``tests/golden/reference_numpy_golden.npz``.
 
 Every function cites the reference call site it follows (paths relative to
 ``/root/reference``).  Weight layouts are Keras': LSTM ``kernel (in,4H)``,
