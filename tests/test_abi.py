@@ -55,6 +55,29 @@ def test_struct_layouts_match_the_c_header(tmp_path):
             assert int(out["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
 
 
+def test_host_side_entry_points_need_no_gpu():
+    """Pure host functions of the C ABI and argument validation (every error path returns before any CUDA call)."""
+    from longterm360fov_b200 import _lib
+    from oracle import keras_numpy as kn
+    lib = _lib.load()
+    for S in (20, 21, 27, 33, 600):
+        for stride in (1, 2, 3, 5, 10):
+            for testing in (False, True):
+                vid = np.zeros((1, S, 2))
+                n_ref = kn.reshape2second_stacks(vid, collapse_user=True, stride=stride, purelly_testing=testing)[0].shape[0]
+                assert lib.fov_window_count(S, 10, stride, int(testing)) == n_ref, (S, stride, testing)
+    assert lib.fov_window_count(19, 10, 1, 0) == 0                       # fewer than 2 x running_length seconds
+    cfg = _lib.LstmCfg(64, 10, 10, 90, 6, 64, 6, 1, 1, 0, 0, 1, 2)
+    assert lib.fov_lstm_bwd_ws_floats(ctypes.byref(cfg)) == (156 + 72) * 256    # [h|x|0] rows padded to 4 floats
+    one = ctypes.c_void_p(16)                                            # never dereferenced: validation fails first
+    assert lib.fov_window_stacks(3, 19, 6, 10, 1, 0, 1, one, one, one, one, None) == -1
+    assert b"running_length" in lib.fov_last_error()
+    assert lib.fov_window_stacks(3, 30, 6, 10, 20, 0, 1, one, one, one, one, None) == -1   # stride > running_length
+    assert lib.fov_onehot_heatmaps(4, 30, 7, one, one, None) == -1       # 7 does not divide 180
+    assert lib.fov_hit_rate(0, one, one, 1.0, 1.0, 1.0, 1.0, one, None) == -1
+    assert lib.fov_whole_span(0, 8, one, one, None) == -1
+
+
 def test_models_fail_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
