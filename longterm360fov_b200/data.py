@@ -45,11 +45,12 @@ def mean_var(frames):
 
 
 def one_hot_heatmaps(frames, bin_size=10):
-    """(N,T,30,3) xyz -> (N,T,36,18,30): one one-hot FoV-centre map per frame, the 30
-    frames of a second stacked as channels (mycode/data_generator_for_heatmap.py:32,65-67)."""
-    x, y, z = frames[..., 0], frames[..., 1], frames[..., 2]
-    theta = np.arctan2(x, z)                       # yaw in (-pi, pi]
-    phi = np.arccos(np.clip(y, -1, 1))             # polar angle in [0, pi]
+    """(N,T,30,3) xyz -> (N,T,36,18,30): one one-hot FoV-centre map per frame, the 30 frames of a second stacked as
+    channels (mycode/data_generator_for_heatmap.py:32,65-67).  Host-side twin of ``ops.one_hot_heatmaps`` with the
+    reference's angles (mycode/dataIO.py:77-82) and binning (mycode/utility.py:533-539)."""
+    x, y, z = (np.asarray(frames[..., i], np.float64) for i in range(3))
+    theta = np.mod(np.arctan2(y, x), 2 * np.pi) - np.pi
+    phi = np.mod(np.arctan2(z, np.sqrt(x ** 2 + y ** 2)) + np.pi / 2, np.pi)
     ti = np.floor((theta + np.pi) / np.pi * 180 / bin_size).astype(np.int64)
     ti[ti == 360 // bin_size] -= 1
     pi_ = np.floor(phi / np.pi * 180 / bin_size).astype(np.int64)
