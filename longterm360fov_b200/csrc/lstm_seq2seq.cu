@@ -459,10 +459,10 @@ extern "C" int fov_lstm_seq2seq_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
   P.cfg = *cfg; P.w = *w; P.io = *io;
   if (P.cfg.T_dec == 0) P.cfg.out_dim = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  // tensor-core forward (lstm_seq2seq_tc.cu): 128-sequence tiles; below ~32 tiles the 16-sequence fp32 CTAs win
-  // (measured on B200, AR decode: B=4096 0.104 ms vs 0.136 ms fp32; B=75776 0.29 ms vs 1.47 ms).  In training mode the
-  // row-per-thread stores of the saved tensors need every SM busy to pay off (B=4096: 347 us vs 170 us fp32 under ncu).
-  const int tc_min_B = cfg->training ? 128 * fov_num_sms() : 4096;
+  // tensor-core forward (lstm_seq2seq_tc.cu): 128-sequence tiles.  Measured on B200, AR decode of the mu/var model:
+  // B=512..2048 0.088 ms vs 0.096 ms fp32 (both latency bound), B=3072 0.088 vs 0.133, B=75776 0.29 vs 1.47 ms.  In
+  // training mode the row-per-thread stores of the saved tensors need every SM busy to pay off (B=8880: equal).
+  const int tc_min_B = cfg->training ? 128 * fov_num_sms() : 512;
   if (cfg->math != FOV_MATH_FP32 && g_lstm_tc_mode >= 0 && lstm_tc_supported(cfg) &&
       (g_lstm_tc_mode > 0 || cfg->B >= tc_min_B))
     return lstm_tc_fwd(&P.cfg, w, io, st);
