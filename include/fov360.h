@@ -11,7 +11,8 @@
  * Conventions
  *   - every pointer is a DEVICE pointer to contiguous float32 unless stated,
  *     16-byte aligned; the caller owns all buffers (inputs, outputs, saved
- *     activations, workspaces); the library allocates nothing and keeps no state.
+ *     activations, workspaces); the library allocates nothing and keeps no state except the
+ *     NCCL communicator of fov_dp_init and the diagnostic switches of include/fov_debug.h.
  *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it.
  *   - weight layouts are Keras': LSTM kernel (in,4H) / recurrent_kernel (H,4H) /
  *     bias (4H), gate blocks i,f,c,o; ConvLSTM2D kernel (kh,kw,Cin,4F) /
@@ -193,7 +194,6 @@ typedef struct {
   const float *x;
   const float *kernel, *recurrent, *bias;
   const float *h0, *c0;          /* optional (B,H,W,F) dense */
-  const float *drop_masks;       /* optional (4,B,H,W,Cin), already scaled by 1/(1-p) */
   float *hseq;                   /* strided output */
   float *gates;                  /* (B,T,H,W,4F): pre-activations then activated gates (saved) */
   float *cseq;                   /* (B,T,H,W,F) */
@@ -241,11 +241,13 @@ int fov_cce_fwd_bwd(long long rows, int C, const float* p, const float* t, float
 
 /* Keras-form Adam / RMSprop over one flat parameter buffer
  * ('Adam' mycode/FoV_seq2seq.py:103; 'RMSprop' mycode/convlstm_seq2seq.py:287).
- * grad_scale multiplies g first (1/world_size after an allreduce-sum). */
+ * g is first multiplied by grad_scale and, when grad_div is not NULL, divided by the DEVICE scalar
+ * *grad_div (the summed sample count of a count-weighted data-parallel allreduce: no host sync). */
 int fov_adam_step(long long n, float* p, const float* g, float* m, float* v, int t, float lr,
-                  float beta1, float beta2, float eps, float grad_scale, void* stream);
+                  float beta1, float beta2, float eps, float grad_scale, const float* grad_div,
+                  void* stream);
 int fov_rmsprop_step(long long n, float* p, const float* g, float* a, float lr, float rho,
-                     float eps, float grad_scale, void* stream);
+                     float eps, float grad_scale, const float* grad_div, void* stream);
 
 /* Per-second mean / population variance featuriser (mycode/utility.py:483-517):
  * frames (rows,30,3) interleaved xyz -> (rows,6) = [mx,my,mz,vx,vy,vz]. */
@@ -255,6 +257,17 @@ int fov_mean_var_xyz(long long rows, const float* frames, float* out, void* stre
  *  convlstm_seq2seq.py:51-58 mode 2).  muvar (rows,6), noise (rows,30,3) -> (rows,30,3) */
 int fov_gauss_resample(long long rows, int mode, const float* muvar, const float* noise,
                        float* out, void* stream);
+/* Gradient of the re-sampler w.r.t. (mu, var) - K.random_normal(mean=mu, stddev=...) is differentiable in
+ * its mean and stddev, so training graphs with cfg.sample_and_refeed back-propagate through the draw
+ * (mycode/convlstm_seq2seq.py:259-272): dmuvar (rows,6) = [sum_f dout, sum_f dout*noise * d sd/d var]. */
+int fov_gauss_resample_bwd(long long rows, int mode, const float* muvar, const float* noise,
+                           const float* dout, float* dmuvar, void* stream);
+/* Philox4x32-10 counter-based generator (the generator behind K.random_normal): element i of the stream is
+ * word i%4 of philox(counter = offset + i/4, key = seed).  words (n) raw 32-bit outputs and/or normal (n)
+ * Box-Muller N(0,1) draws; either may be NULL.  Results depend on (seed, offset) only - a rank draws the
+ * rows it owns with offset = first_row * 90 / 4 and gets the numbers a single process would. */
+int fov_philox_normal(long long n, unsigned long long seed, unsigned long long offset,
+                      unsigned int* words, float* normal, void* stream);
 
 /* ConvLSTM2D input dropout (keras ConvLSTM2D(dropout=0.3), mycode/others_LSTM_span_whole.py:89,
  * mycode/convlstm_seq2seq.py:100-126): one mask per gate, shape (B,H,W,Cin), constant over time, applied to the
@@ -294,6 +307,23 @@ int fov_onehot_heatmaps(long long rows, int frames, int bin_size, const float* x
  * ground-truth box area after the +-pi wrap fix of boundary_cases. */
 int fov_hit_rate(long long rows, const float* pred, const float* gt, float span_theta, float span_phi,
                  float gt_span_theta, float gt_span_phi, float* out, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Data-parallel training (the reference is single-process): one process per GPU, one NCCL
+ * communicator per process, one summed allreduce of the flat fp32 gradient bucket per step over NVLink.
+ * The communicator handle is the only state the library keeps.  Rank 0 calls fov_dp_get_unique_id, the
+ * caller ships the fov_dp_unique_id_bytes() bytes to every rank (any transport), every rank calls fov_dp_init.
+ * libnccl.so.2 is bound at run time; without it these calls return FOV_ERR_UNSUPPORTED.
+ * ------------------------------------------------------------------------- */
+int fov_dp_unique_id_bytes(void);
+int fov_dp_get_unique_id(void* id_out);
+int fov_dp_init(const void* unique_id, int rank, int world);
+int fov_dp_world(void);
+int fov_dp_rank(void);
+/* in-place sum over all ranks / copy from root, asynchronous on `stream` */
+int fov_dp_allreduce(float* flat, size_t n, void* stream);
+int fov_dp_broadcast(float* flat, size_t n, int root, void* stream);
+int fov_dp_destroy(void);
 
 #ifdef __cplusplus
 }

@@ -69,7 +69,7 @@ class ConvLstmCfg(C.Structure):
 
 class ConvLstmIO(C.Structure):
     _fields_ = [(n, c_float_p) for n in (
-        "x", "kernel", "recurrent", "bias", "h0", "c0", "drop_masks", "hseq", "gates", "cseq",
+        "x", "kernel", "recurrent", "bias", "h0", "c0", "hseq", "gates", "cseq",
         "hT", "cT", "ws")]
 
 
@@ -110,10 +110,20 @@ SYMBOLS = {
     "fov_mse_fwd_bwd": (_I, [_LL, _P, _P, _F, _P, _P, _P]),
     "fov_gauss_nll_fwd_bwd": (_I, [_I, _I, _I, _P, _P, _F, _P, _P, _P]),
     "fov_cce_fwd_bwd": (_I, [_LL, _I, _P, _P, _F, _P, _P, _P]),
-    "fov_adam_step": (_I, [_LL, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _P]),
-    "fov_rmsprop_step": (_I, [_LL, _P, _P, _P, _F, _F, _F, _F, _P]),
+    "fov_adam_step": (_I, [_LL, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _P, _P]),
+    "fov_rmsprop_step": (_I, [_LL, _P, _P, _P, _F, _F, _F, _F, _P, _P]),
     "fov_mean_var_xyz": (_I, [_LL, _P, _P, _P]),
     "fov_gauss_resample": (_I, [_LL, _I, _P, _P, _P, _P]),
+    "fov_gauss_resample_bwd": (_I, [_LL, _I, _P, _P, _P, _P, _P]),
+    "fov_philox_normal": (_I, [_LL, C.c_ulonglong, C.c_ulonglong, _P, _P, _P]),
+    "fov_dp_unique_id_bytes": (_I, []),
+    "fov_dp_get_unique_id": (_I, [_P]),
+    "fov_dp_init": (_I, [_P, _I, _I]),
+    "fov_dp_world": (_I, []),
+    "fov_dp_rank": (_I, []),
+    "fov_dp_allreduce": (_I, [_P, C.c_size_t, _P]),
+    "fov_dp_broadcast": (_I, [_P, C.c_size_t, _I, _P]),
+    "fov_dp_destroy": (_I, []),
     "fov_dropout_expand": (_I, [_I, _I, _I, _I, _P, _LL, _LL, _I, _P, _P, _P]),
     "fov_dropout_reduce": (_I, [_I, _I, _I, _I, _P, _P, _P, _LL, _LL, _I, _I, _P]),
     "fov_gate_kernel_expand": (_I, [_I, _I, _I, _P, _P, _P]),

@@ -11,13 +11,13 @@ pids=()
 for src in "$HERE"/*.cu; do
   obj="$HERE/build/$(basename "${src%.cu}").o"
   objs+=("$obj")
-  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/fov_common.cuh" -nt "$obj" || "$HERE/fov_internal.h" -nt "$obj" || "$HERE/tc_common.cuh" -nt "$obj" || "$HERE/../../include/fov360.h" -nt "$obj" ]]; then
+  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/fov_common.cuh" -nt "$obj" || "$HERE/fov_internal.h" -nt "$obj" || "$HERE/tc_common.cuh" -nt "$obj" || "$HERE/../../include/fov360.h" -nt "$obj" || "$HERE/../../include/fov_debug.h" -nt "$obj" ]]; then
     ( "$NVCC" "${FLAGS[@]}" -c "$src" -o "$obj" > "$obj.log" 2>&1 || { cat "$obj.log"; exit 1; } ) &
     pids+=($!)
   fi
 done
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
-"$NVCC" -shared -o "$OUT/libfov360.so" "${objs[@]}" -lcudart
+"$NVCC" -shared -o "$OUT/libfov360.so" "${objs[@]}" -lcudart -ldl
 echo "built $OUT/libfov360.so"
 # stand-alone bring-up harness for the tensor-core kernels (tests/cuda/tc_selftest.cu)
 SELF="$HERE/../../tests/cuda/tc_selftest.cu"

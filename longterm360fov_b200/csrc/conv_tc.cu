@@ -770,15 +770,15 @@ int pick_vec(const TcSeg& g) {
 
 template <int NS, int EPI>
 int launch_conv(const DevParams& dp, const Plan& pl, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static FovPerDevice configured;
+  if (!configured.done()) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<NS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(227 * 1024));
     if (e != cudaSuccess) {
       fov_set_error("tc_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return FOV_ERR_CUDA;
     }
-    configured = true;
+    configured.mark();
   }
   const long long m_tiles = (pl.total_pos + BLOCK_M - 1) / BLOCK_M;
   if (m_tiles * pl.n_tiles >= (1LL << 31)) { fov_set_error("tc_conv: grid too large"); return FOV_ERR_ARG; }

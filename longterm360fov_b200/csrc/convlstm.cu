@@ -130,7 +130,6 @@ extern "C" size_t fov_convlstm_fwd_ws_bytes(const fov_convlstm_cfg* cfg) {
 
 static int convlstm_fwd_tc(const fov_convlstm_cfg* cfg, const fov_convlstm_io* io, cudaStream_t st) {
   FOV_CHECK_ARG(io->ws != nullptr, "math != 0 needs io->ws (fov_convlstm_fwd_ws_bytes)");
-  FOV_CHECK_ARG(!io->drop_masks, "dropout masks are applied by the caller in this build");
   const Geo g = geo(cfg);
   const int F = cfg->F;
   TcConv k = step_conv(cfg, io, g);
@@ -170,7 +169,8 @@ extern "C" int fov_convlstm_fwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
   const int F = cfg->F;
 
   // ---- input projection for every timestep ----
-  if (!io->drop_masks) {
+  // (input dropout is expressed by the caller as a widened input: fov_dropout_expand / fov_gate_kernel_expand)
+  {
     fov_conv_cfg k = input_conv_cfg(cfg);
     if (cfg->x_b_stride == (long long)cfg->T * cfg->x_t_stride || cfg->T == 1) {
       k.N = cfg->B * cfg->T; k.x_img_stride = cfg->T == 1 ? cfg->x_b_stride : cfg->x_t_stride;
@@ -182,13 +182,6 @@ extern "C" int fov_convlstm_fwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
         if ((rc = fov_conv2d_fwd(&k, io->x + t * cfg->x_t_stride, io->kernel, io->bias,
                                  io->gates + t * g.z_t, stream))) return rc;
     }
-  } else {
-    // training-time input dropout: one mask per gate, constant over time
-    // (keras ConvLSTM2D(dropout=...), mycode/others_LSTM_span_whole.py:89).  The gate
-    // blocks of the kernel are NOT contiguous ([K][4F] rows), so each gate uses a
-    // compacted copy of its weight columns placed after the masked input in ws.
-    fov_set_error("fov_convlstm_fwd: dropout masks are applied by the caller in this build");
-    return FOV_ERR_UNSUPPORTED;
   }
 
   // ---- recurrence ----

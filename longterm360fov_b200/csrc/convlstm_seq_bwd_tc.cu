@@ -459,15 +459,15 @@ int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT, BwdP
 
 template <int NS, int F, int DXN>
 int launch_bwd(const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static FovPerDevice configured;
+  if (!configured.done()) {
     cudaError_t e = cudaFuncSetAttribute(convlstm_seq_bwd_kernel<NS, F, DXN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) {
       fov_set_error("convlstm_seq_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return FOV_ERR_CUDA;
     }
-    configured = true;
+    configured.mark();
   }
   convlstm_seq_bwd_kernel<NS, F, DXN><<<grid, kBThr, pl.smem_bytes, st>>>(p);
   FOV_CUDA_LAUNCH_CHECK();

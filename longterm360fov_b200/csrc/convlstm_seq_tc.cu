@@ -516,15 +516,15 @@ int seq_plan(const fov_convlstm_cfg* c, const TcConv& step, SeqPlan* out) {
 
 template <int NS, int F, int NG, int WPG>
 int launch_seq(const SeqParams& p, const SeqPlan& pl, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static FovPerDevice configured;
+  if (!configured.done()) {
     cudaError_t e = cudaFuncSetAttribute(convlstm_seq_fwd_kernel<NS, F, NG, WPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) {
       fov_set_error("convlstm_seq: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return FOV_ERR_CUDA;
     }
-    configured = true;
+    configured.mark();
   }
   convlstm_seq_fwd_kernel<NS, F, NG, WPG><<<grid, 32 * (WPG * NG + 2), pl.smem_bytes, st>>>(p);
   FOV_CUDA_LAUNCH_CHECK();

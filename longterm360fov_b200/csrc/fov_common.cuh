@@ -77,13 +77,33 @@ __device__ __forceinline__ void fov_cp_async_wait_all() {
 // row width of the saved [h_{t-1} | x_t | 0] tensor of an fc-LSTM (include/fov360.h fov_lstm_saved.xh)
 __host__ __device__ inline int fov_lstm_xh_stride(int H, int in_dim) { return (H + in_dim + 3) / 4 * 4; }
 
-static inline int fov_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+// Per-device one-time setup flag (kernel attributes are per device: a second GPU in the same process needs its own
+// cudaFuncSetAttribute call).  Racing first calls from two host threads repeat the idempotent setup, nothing more.
+struct FovPerDevice {
+  static constexpr int kMaxDev = 64;
+  bool flag[kMaxDev] = {};
+  static int cur() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
   }
-  return n;
+  bool done() const {
+    const int d = cur();
+    return d >= 0 && d < kMaxDev && flag[d];
+  }
+  void mark() {
+    const int d = cur();
+    if (d >= 0 && d < kMaxDev) flag[d] = true;
+  }
+};
+
+static inline int fov_num_sms() {
+  static int n[FovPerDevice::kMaxDev] = {};
+  const int dev = FovPerDevice::cur();
+  if (dev < 0 || dev >= FovPerDevice::kMaxDev) return 148;
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
+  }
+  return n[dev];
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "../../include/fov360.h"
+#include "../../include/fov_debug.h"
 
 struct GatesFwdArgs {
   long long npix;   // B*H*W

@@ -10,17 +10,19 @@
 // Replaces the Keras LSTM/Dense calls cited in include/fov360.h.
 #include "fov_common.cuh"
 #include "fov_internal.h"
-#include <stdlib.h>
 
 // diagnostics / A-B testing: -1 = never use the tensor-core forward, 0 = choose, 1 = whenever the shape allows
-static int g_lstm_tc_mode = getenv("FOV_LSTM_TC") ? atoi(getenv("FOV_LSTM_TC")) : 0;
+static int g_lstm_tc_mode = 0;
 extern "C" void fov_debug_lstm_tc(int mode) { g_lstm_tc_mode = mode; }
+// time-batched input projection in front of the tensor-core forward: -1 never, 0 choose (inputs wider than 16), 1 always
+static int g_lstm_xproj_mode = 0;
+extern "C" void fov_debug_lstm_xproj(int mode) { g_lstm_xproj_mode = mode; }
 // A/B switch for the tensor-core LSTM weight gradient (needs fov_lstm_grads.ws).  History: on unpadded 70-float [h|x]
 // rows it took the unaligned gather path of wgrad_tc.cu and lost to the SIMT kernels (11.07 vs 10.96 ms per config-2
 // step), hence the rows padded to a multiple of 4 floats and the single aligned launch per LSTM.
-static int g_lstm_wgrad_tc = getenv("FOV_LSTM_WGRAD_TC") ? atoi(getenv("FOV_LSTM_WGRAD_TC")) : 1;
+static int g_lstm_wgrad_tc = 1;
 extern "C" void fov_debug_lstm_wgrad_tc(int on) { g_lstm_wgrad_tc = on; }
-static int g_lstm_bptt_tc = getenv("FOV_LSTM_BPTT_TC") ? atoi(getenv("FOV_LSTM_BPTT_TC")) : 1;   // A/B switch
+static int g_lstm_bptt_tc = 1;   // A/B switch
 extern "C" void fov_debug_lstm_bptt_tc(int on) { g_lstm_bptt_tc = on; }
 
 namespace {

@@ -527,15 +527,15 @@ size_t tc_smem_bytes() {
 template <int NS, int NG, int REC, int OD, bool TRAIN, int WPG>
 int launch_tc_w(const LstmTcParams& P, cudaStream_t st) {
   const size_t smem = tc_smem_bytes<NS, NG, OD>();
-  static bool configured = false;
-  if (!configured) {
+  static FovPerDevice configured;
+  if (!configured.done()) {
     cudaError_t e = cudaFuncSetAttribute(lstm_tc_fwd_kernel<NS, NG, REC, OD, TRAIN, WPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) {
       fov_set_error("fov_lstm (tensor-core): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return FOV_ERR_CUDA;
     }
-    configured = true;
+    configured.mark();
   }
   const int per_cta = kRows * NG;
   const int grid = (P.B + per_cta - 1) / per_cta;
@@ -858,15 +858,15 @@ template <int NS, int REC, int OD, bool AR>
 int launch_tc_bwd(const LstmTcBwdParams& P, cudaStream_t st) {
   constexpr int NB = AR ? kH + kXK : kH;
   const size_t smem = (size_t)NS * 4 * NB * 128 + (size_t)NS * 4 * kATerm + sizeof(LstmTcBwdBook<OD>) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static FovPerDevice configured;
+  if (!configured.done()) {
     cudaError_t e = cudaFuncSetAttribute(lstm_tc_bwd_kernel<NS, REC, OD, AR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) {
       fov_set_error("fov_lstm BPTT (tensor-core): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return FOV_ERR_CUDA;
     }
-    configured = true;
+    configured.mark();
   }
   lstm_tc_bwd_kernel<NS, REC, OD, AR><<<(P.B + kRows - 1) / kRows, kRows, smem, st>>>(P);
   FOV_CUDA_LAUNCH_CHECK();

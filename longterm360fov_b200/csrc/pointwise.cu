@@ -211,7 +211,9 @@ __global__ void __launch_bounds__(256) cce_kernel(long long rows, int C, const f
 
 __global__ void __launch_bounds__(256) adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, float lr_t,
-                                                   float b1, float b2, float eps, float gs) {
+                                                   float b1, float b2, float eps, float gs,
+                                                   const float* __restrict__ gdiv) {
+  if (gdiv) gs = gs / __ldg(gdiv);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gs;
@@ -224,7 +226,9 @@ __global__ void __launch_bounds__(256) adam_kernel(long long n, float* __restric
 
 __global__ void __launch_bounds__(256) rmsprop_kernel(long long n, float* __restrict__ p,
                                                       const float* __restrict__ g, float* __restrict__ a,
-                                                      float lr, float rho, float eps, float gs) {
+                                                      float lr, float rho, float eps, float gs,
+                                                      const float* __restrict__ gdiv) {
+  if (gdiv) gs = gs / __ldg(gdiv);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gs;
@@ -265,6 +269,71 @@ __global__ void gauss_resample_kernel(long long rows, int mode, const float* __r
     else if (mode == 1) sd = sqrtf(var);
     else sd = var;
     out[i] = fmaf(sd, noise[i], mu);
+  }
+}
+
+// d(mu,var) of out = mu + sd(var) * noise: one thread per (row, axis), 30 frames each
+__global__ void gauss_resample_bwd_kernel(long long rows, int mode, const float* __restrict__ muvar,
+                                          const float* __restrict__ noise, const float* __restrict__ dout,
+                                          float* __restrict__ dmuvar) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * 3;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / 3;
+    const int a = (int)(i - r * 3);
+    const float* d = dout + r * 90 + a;
+    const float* z = noise + r * 90 + a;
+    float dm = 0.0f, ds = 0.0f;
+    for (int f = 0; f < 30; ++f) { dm += d[3 * f]; ds = fmaf(d[3 * f], z[3 * f], ds); }
+    const float var = muvar[r * 6 + 3 + a];
+    float dv;
+    if (mode == 0) dv = var < 0.0f ? 0.0f : ds * 0.5f * rsqrtf(var);        // floored branch is constant
+    else if (mode == 1) dv = ds * 0.5f * rsqrtf(var);
+    else dv = ds;
+    dmuvar[r * 6 + a] = dm;
+    dmuvar[r * 6 + 3 + a] = dv;
+  }
+}
+
+// Philox4x32-10 (Salmon et al. 2011; the generator TF's K.random_normal uses, mycode/convlstm_seq2seq.py:57):
+// counter = (idx_lo, idx_hi, 0, 0), key = (seed_lo, seed_hi); element 4*idx + j of the stream is word j.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// raw words (bit-exact against the oracle's integer restatement) and Box-Muller normals:
+// u1 = (w0 + 1) * 2^-32 in (0,1], u2 = w1 * 2^-32; z0 = sqrt(-2 ln u1) cos(2 pi u2), z1 = ... sin(...)
+__global__ void philox_kernel(long long n, unsigned long long seed, unsigned long long offset,
+                              uint32_t* __restrict__ words, float* __restrict__ normal) {
+  const long long nblk = (n + 3) / 4;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long ctr = offset + (unsigned long long)b;
+    const uint4 w = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+    float z[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u1 = ((float)ww[2 * h] + 1.0f) * 2.3283064365386963e-10f;
+      const float u2 = (float)ww[2 * h + 1] * 2.3283064365386963e-10f;
+      const float rad = sqrtf(-2.0f * logf(fminf(u1, 1.0f)));
+      float sn, cs;
+      sincospif(2.0f * u2, &sn, &cs);
+      z[2 * h] = rad * cs; z[2 * h + 1] = rad * sn;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = 4 * b + j;
+      if (i < n) {
+        if (words) words[i] = ww[j];
+        if (normal) normal[i] = z[j];
+      }
+    }
   }
 }
 
@@ -330,18 +399,20 @@ extern "C" int fov_cce_fwd_bwd(long long rows, int C, const float* p, const floa
 }
 
 extern "C" int fov_adam_step(long long n, float* p, const float* g, float* m, float* v, int t, float lr,
-                             float beta1, float beta2, float eps, float grad_scale, void* stream) {
+                             float beta1, float beta2, float eps, float grad_scale, const float* grad_div,
+                             void* stream) {
   FOV_CHECK_ARG(n > 0 && p && g && m && v && t >= 1, "bad args");
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t));
-  adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, p, g, m, v, (float)lr_t, beta1, beta2, eps, grad_scale);
+  adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, p, g, m, v, (float)lr_t, beta1, beta2, eps, grad_scale,
+                                                          grad_div);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
 
 extern "C" int fov_rmsprop_step(long long n, float* p, const float* g, float* a, float lr, float rho, float eps,
-                                float grad_scale, void* stream) {
+                                float grad_scale, const float* grad_div, void* stream) {
   FOV_CHECK_ARG(n > 0 && p && g && a, "bad args");
-  rmsprop_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, p, g, a, lr, rho, eps, grad_scale);
+  rmsprop_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, p, g, a, lr, rho, eps, grad_scale, grad_div);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
@@ -360,7 +431,21 @@ extern "C" int fov_gauss_resample(long long rows, int mode, const float* muvar, 
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
+extern "C" int fov_gauss_resample_bwd(long long rows, int mode, const float* muvar, const float* noise,
+                                      const float* dout, float* dmuvar, void* stream) {
+  FOV_CHECK_ARG(rows > 0 && mode >= 0 && mode <= 2 && muvar && noise && dout && dmuvar, "bad args");
+  gauss_resample_bwd_kernel<<<grid_for(rows * 3), 256, 0, (cudaStream_t)stream>>>(rows, mode, muvar, noise, dout, dmuvar);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
 
+extern "C" int fov_philox_normal(long long n, unsigned long long seed, unsigned long long offset, unsigned int* words,
+                                 float* normal, void* stream) {
+  FOV_CHECK_ARG(n > 0 && (words || normal), "bad args");
+  philox_kernel<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(n, seed, offset, words, normal);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // ConvLSTM2D input dropout as a widened input (include/fov360.h): expand / reduce helpers

@@ -458,14 +458,14 @@ int plan(const TcWgradRows& c, WrParams* out, size_t* smem_bytes) {
 
 template <int NS>
 int launch(const WrParams& p, int grid, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static FovPerDevice configured;
+  if (!configured.done()) {
     cudaError_t e = cudaFuncSetAttribute(tc_wgrad_rows_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       fov_set_error("tc_wgrad_rows: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return FOV_ERR_CUDA;
     }
-    configured = true;
+    configured.mark();
   }
   tc_wgrad_rows_kernel<NS><<<grid, kThr, smem, st>>>(p);
   FOV_CUDA_LAUNCH_CHECK();

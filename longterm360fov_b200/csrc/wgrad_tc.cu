@@ -373,14 +373,14 @@ int vec_of(const void* ptr, long long a, long long b, long long c, long long d) 
 
 template <int NS, bool FAST, int PIX, int MT>
 int launch(const WgParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static FovPerDevice configured;
+  if (!configured.done()) {
     cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<NS, FAST, PIX, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       fov_set_error("tc_wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return FOV_ERR_CUDA;
     }
-    configured = true;
+    configured.mark();
   }
   tc_wgrad_kernel<NS, FAST, PIX, MT><<<grid, kThr, smem, st>>>(p);
   FOV_CUDA_LAUNCH_CHECK();

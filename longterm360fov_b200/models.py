@@ -50,10 +50,10 @@ class Adam:
     def init(self, n, device):
         self.state = (torch.zeros(n, device=device), torch.zeros(n, device=device))
 
-    def step(self, p, g, grad_scale=1.0):
+    def step(self, p, g, grad_scale=1.0, grad_div=None):
         self.iterations += 1
         ops.adam_step(p, g, self.state[0], self.state[1], self.iterations, self.lr, self.beta_1,
-                      self.beta_2, self.epsilon, grad_scale)
+                      self.beta_2, self.epsilon, grad_scale, grad_div)
 
 
 class RMSprop:
@@ -67,9 +67,9 @@ class RMSprop:
     def init(self, n, device):
         self.state = (torch.zeros(n, device=device),)
 
-    def step(self, p, g, grad_scale=1.0):
+    def step(self, p, g, grad_scale=1.0, grad_div=None):
         self.iterations += 1
-        ops.rmsprop_step(p, g, self.state[0], self.lr, self.rho, self.epsilon, grad_scale)
+        ops.rmsprop_step(p, g, self.state[0], self.lr, self.rho, self.epsilon, grad_scale, grad_div)
 
 
 def _make_optimizer(opt):
@@ -95,8 +95,9 @@ class _GraphedStep:
     the step at the reference's batch sizes (32-64).  The optimiser step stays outside (its step count and learning
     rate are host-side arguments) and so does the gradient allreduce."""
 
-    def __init__(self, model, xs, ys):
+    def __init__(self, model, xs, ys, seed=None):
         self.model = model
+        self.seed = seed
         self.sx = [torch.empty_like(t) for t in xs]
         self.sy = [torch.empty_like(t) for t in ys]
         self._load(xs, ys)
@@ -120,7 +121,7 @@ class _GraphedStep:
         ops.set_math(m.compute)
         outs = m._forward(self.sx, True)
         total = m._loss(outs, self.sy)
-        total.backward()
+        total.backward(self.seed)
         return total.detach()
 
     def run(self, xs, ys):
@@ -149,6 +150,9 @@ class Model:
         for k, shp in sizes:
             self._offsets[k] = (off, shp)
             off += (int(np.prod(shp)) + 63) // 64 * 64
+        # + 64 reserved floats: the last element of the gradient bucket carries the sample count of a
+        # data-parallel step through the allreduce (parallel.allreduce_gradients)
+        off += 64
         self.n_flat = off
         self.flat = torch.zeros(off, device=self.device)
         self.gflat = torch.zeros(off, device=self.device)
@@ -162,8 +166,9 @@ class Model:
         self.loss_kinds = None
         self.loss_weights = None
         self.stop_training = False
-        self.process_group = None
+        self.comm = None
         self.world_size = 1
+        self._seeds = {}
         self.running_length = 10
         # arithmetic of the conv / dense / ConvLSTM kernels (ops.set_math): tensor cores with 2 bf16
         # terms per operand by default (fp32-grade results); "fp32" selects the CUDA-core kernels
@@ -238,14 +243,17 @@ class Model:
         self.loss_weights = [1.0] * len(kinds) if loss_weights is None else [float(w) for w in loss_weights]
         return self
 
-    def distribute(self, process_group=None):
-        """Data-parallel training: batch sharded by rank by the caller, one summed
-        allreduce of the flat gradient bucket per step (NCCL over NVLink on GPUs)."""
-        import torch.distributed as dist
-        self.process_group = process_group if process_group is not None else dist.group.WORLD
-        self.world_size = dist.get_world_size(self.process_group)
-        # identical start: broadcast rank 0's parameters
-        dist.broadcast(self.flat, src=0, group=self.process_group)
+    def distribute(self, comm=None):
+        """Data-parallel training: batch sharded by rank by the caller, one count-weighted summed allreduce of
+        the flat gradient bucket per step.  ``comm``: a parallel.FovComm / parallel.TorchComm; default = the C
+        ABI's own NCCL communicator (fov_dp_init ... over NVLink), bootstrapped through the initialised
+        torch.distributed default group."""
+        if comm is None:
+            import torch.distributed as dist
+            comm = parallel.FovComm(dist.get_rank(), dist.get_world_size())
+        self.comm = comm
+        self.world_size = comm.world
+        comm.broadcast(self.flat, 0)        # identical start: rank 0's parameters
         return self
 
     # ------------------------------------------------------------------ #
@@ -282,13 +290,19 @@ class Model:
         (no host sync).  DP: gradients are sum-allreduced and scaled by 1/world.
         ``targets_ready``: optional CUDA event after which ``ys`` may be read (their H2D copy
         runs on a side stream while the forward pass computes)."""
+        n_local = int(xs[0].shape[0])
+        seed = None
+        if self.world_size > 1:       # gradients weighted by the local sample count (parallel.py)
+            seed = self._seeds.get(n_local)
+            if seed is None:
+                seed = self._seeds[n_local] = torch.full((1,), float(n_local), device=self.device)
         if self._use_graphs:
             if targets_ready is not None:
                 torch.cuda.current_stream().wait_event(targets_ready)
-            key = (self.compute,) + tuple(tuple(t.shape) for t in list(xs) + list(ys))
+            key = (self.compute, self.world_size > 1) + tuple(tuple(t.shape) for t in list(xs) + list(ys))
             step = self._graphs.get(key)
             if step is None:
-                step = self._graphs[key] = _GraphedStep(self, xs, ys)
+                step = self._graphs[key] = _GraphedStep(self, xs, ys, seed)
             total = step.run(xs, ys)
         else:
             self.gflat.zero_()
@@ -297,12 +311,12 @@ class Model:
             if targets_ready is not None:
                 torch.cuda.current_stream().wait_event(targets_ready)
             total = self._loss(outs, ys)
-            total.backward()
-        scale = 1.0
+            total.backward(seed)
+        div = None
         if self.world_size > 1:
-            scale = parallel.allreduce_gradients(self.gflat, self.process_group)
+            div = parallel.allreduce_gradients(self.gflat, self.comm, n_local)
         with torch.no_grad():
-            self.optimizer.step(self.flat, self.gflat, scale)
+            self.optimizer.step(self.flat, self.gflat, 1.0, div)
         return total.detach() if not self._use_graphs else total.clone()
 
     def train_on_batch(self, x, y):
@@ -698,7 +712,8 @@ def others_lstm_span_whole(latent_dim=64, num_user=34, kernel_size=5, max_encode
 
 class ConvLSTMSeq2Seq(Model):
     def __init__(self, weights, head_kind="conv2d", max_decoder_seq_length=10, dilation_rate=1,
-                 recurrent_activation="hard_sigmoid", dropout=0.0, device=None):
+                 recurrent_activation="hard_sigmoid", dropout=0.0, device=None, sample_and_refeed=False,
+                 resample_mode="var_as_std", sample_seed=0):
         order = ["%s_convlstm%d/%s" % (s, l, n) for s in ("enc", "dec") for l in range(3)
                  for n in ("kernel", "recurrent_kernel", "bias")]
         if head_kind in ("conv2d", "conv1d"):
@@ -712,6 +727,28 @@ class ConvLSTMSeq2Seq(Model):
         self.dilation = (dilation_rate, dilation_rate)
         self.rec_act = recurrent_activation
         self.dropout = float(dropout)
+        # cfg.sample_and_refeed (mycode/convlstm_seq2seq.py:259-272): the Dense head's (mu, var) is re-sampled into
+        # fps frames per axis which become the next decoder input.  The graph passes var as the stddev (:57,
+        # 'var_as_std'); decode_sequence_fov_sampling uses the NumPy twin (utility.py:73-80, 'sqrt_floor').
+        self.sample_and_refeed = bool(sample_and_refeed)
+        if self.sample_and_refeed and head_kind != "dense":
+            raise ValueError("sample_and_refeed needs the mean/var Dense head (cfg.predict_mean_var)")
+        self.resample_mode = resample_mode
+        self.sample_seed = int(sample_seed)
+        self.noise_fn = None          # optional callable (step, B) -> (B,fps,3) N(0,1) tensor: explicit noise (parity runs)
+        self._draws = 0
+
+    def _noise(self, step, B, fps):
+        """Standard-normal draws of one decoder step: the caller's explicit noise, else the in-kernel Philox stream
+        keyed by (sample_seed; draw counter, data-parallel rank) - independent of the batch split."""
+        if self.noise_fn is not None:
+            z = self.noise_fn(step, B)
+            z = z if isinstance(z, torch.Tensor) else torch.as_tensor(np.asarray(z, dtype=np.float32))
+            return z.to(self.device, torch.float32).reshape(B, fps, 3)
+        rank = self.comm.rank if self.comm is not None else 0
+        off = (self._draws << 40) + (rank << 32)
+        self._draws += 1
+        return ops.philox_normal((B, fps, 3), self.sample_seed, off, self.device)
 
     def _stack(self, side, x, states, training):
         p, g = self.params, self.grads
@@ -725,14 +762,14 @@ class ConvLSTMSeq2Seq(Model):
                                         [x.shape[4]] + [w[1].shape[2] for w in wl[:-1]])
         return ops.convlstm_stack(x, wl, states, sl, self.dilation, self.rec_act, training, dropout_masks=masks)
 
-    def _forward(self, inputs, training):
+    def _forward(self, inputs, training, resample_mode=None):
         enc_in, dec_in = inputs
         p = self.params
         B = enc_in.shape[0]
         _, states = self._stack("enc", enc_in, None, training)
         x = dec_in[:, 0:1]
         outs = []
-        for _ in range(self.T_dec):
+        for step in range(self.T_dec):
             cat, states = self._stack("dec", x, states, training)
             d = cat[:, 0]                                              # (B,H,W,56)
             if self.head_kind == "conv2d":
@@ -754,20 +791,49 @@ class ConvLSTMSeq2Seq(Model):
             else:
                 y = ops.dense(d[:, 0].reshape(B, -1), p["head_dense/kernel"], p["head_dense/bias"], None,
                               self._sinks("head_dense/kernel", "head_dense/bias"), training)
-                x = y.view(B, 1, 1, 1, -1)
+                if self.sample_and_refeed:
+                    fps = enc_in.shape[3]
+                    fr = ops.gauss_resample(y, self._noise(step, B, fps), resample_mode or self.resample_mode)
+                    x = fr.view(B, 1, 1, fps, 3)
+                else:
+                    x = y.view(B, 1, 1, 1, -1)
             outs.append(y)
         return [torch.stack(outs, dim=1)]
+
+    def decode_sequence_fov_sampling(self, input_seq, last_location=None):
+        """mycode/convlstm_seq2seq.py:479-502: encoder once, then max_decoder_seq_length decoder steps, each
+        re-sampling fps frames from the predicted (mu, var) with the NumPy rule (negative variances floored to 1e-3,
+        std = sqrt(var)) as the next input.  One batched pass; returns (B, steps, 6)."""
+        if not self.sample_and_refeed:
+            raise ValueError("built without sample_and_refeed")
+        xs = self._to_dev([input_seq])[0]
+        last = xs[:, -1:].contiguous() if last_location is None else self._to_dev([last_location])[0]
+        with torch.no_grad():
+            ops.set_math(self.compute)
+            y = self._forward([xs, last], False, resample_mode="sqrt_floor")[0]
+        return y.cpu().numpy()
 
 
 def convlstm_seq2seq(latent_dim=16, kernel_size=5, dilation_rate=1, use_one_hot=True, input_mean_var=False,
                      predict_mean_var=False, max_decoder_seq_length=10, fps=30, head=(512, 1024, None),
-                     recurrent_activation="hard_sigmoid", dropout=0.0, weights=None, seed=1, device=None):
+                     recurrent_activation="hard_sigmoid", dropout=0.0, weights=None, seed=1, device=None,
+                     sample_and_refeed=None, sample_seed=0):
     """Builder for M4 (mycode/convlstm_seq2seq.py:32-45,73-287).
     heatmap form (``use_one_hot=True``): ``[encoder_inputs (B,10,36,18,fps), decoder_inputs
     (B,1,36,18,fps)]`` -> ``(B,10,36,18,fps)``, heads Conv2D 56->512->1024->fps + channel softmax.
-    trajectory form: ``(B,10,1,fps,3)`` images with the Conv1D(k=7) head, or, with
-    ``input_mean_var`` and ``predict_mean_var``, ``(B,10,1,1,6)`` images with a Dense(6) head."""
+    trajectory form: ``(B,10,1,fps,3)`` images with the Conv1D(k=7) head; with ``predict_mean_var`` a Dense(6)
+    mean/var head whose output is either fed back as a ``(B,1,1,1,6)`` image (``input_mean_var``) or - raw xyz
+    inputs - re-sampled into fps frames per axis (``sample_and_refeed``, cfg defaults of mycode/config.py:69-75;
+    mycode/convlstm_seq2seq.py:259-272).  Raw inputs with a mean/var head NEED the re-sampling step (6 != 3
+    channels), so it defaults to on there."""
     filters = (latent_dim * 2, latent_dim, latent_dim // 2)
+    if sample_and_refeed is None:
+        sample_and_refeed = bool(predict_mean_var and not input_mean_var and not use_one_hot)
+    if predict_mean_var and not use_one_hot and not input_mean_var and not sample_and_refeed:
+        raise ValueError("predict_mean_var on raw xyz inputs feeds a 6-wide output into 3-channel ConvLSTMs: "
+                         "enable sample_and_refeed (as the reference's cfg does) or input_mean_var")
+    if sample_and_refeed and (use_one_hot or not predict_mean_var or input_mean_var):
+        raise ValueError("sample_and_refeed applies to the raw-xyz trajectory form with predict_mean_var")
     if use_one_hot:
         kind, in_ch, hd = "conv2d", fps, (head[0], head[1], fps)
     elif predict_mean_var:
@@ -778,4 +844,5 @@ def convlstm_seq2seq(latent_dim=16, kernel_size=5, dilation_rate=1, use_one_hot=
         flat_dim = sum(filters) * (1 if input_mean_var else fps)
         weights = _init_weights("init_convlstm_seq2seq", seed=seed, in_ch=in_ch, filters=filters,
                                 kernel_size=kernel_size, head=hd, head_kind=kind, flat_dim=flat_dim)
-    return ConvLSTMSeq2Seq(weights, kind, max_decoder_seq_length, dilation_rate, recurrent_activation, dropout, device)
+    return ConvLSTMSeq2Seq(weights, kind, max_decoder_seq_length, dilation_rate, recurrent_activation, dropout, device,
+                           sample_and_refeed=sample_and_refeed, sample_seed=sample_seed)

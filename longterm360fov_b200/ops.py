@@ -33,6 +33,13 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _expect(cond, msg, *args):
+    """Host-side operand checks: the C ABI gets raw pointers, so a shape that disagrees with the weights would be
+    a silent out-of-bounds read of the flat parameter bucket, not an error."""
+    if not cond:
+        raise _lib.FovError(msg % args if args else msg)
+
+
 # arithmetic used by the conv / dense / ConvLSTM Functions built from now on (see _lib.MATH);
 # each Function records the mode of its forward for its backward.
 _MATH = [_lib.MATH["bf16x2"]]
@@ -68,11 +75,32 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
         lib = _lib.load()
         _require_cuda(x_enc, x_dec, We)
         x_enc, x_dec, extra = _f32c(x_enc), _f32c(x_dec), _f32c(extra)
+        _expect(x_enc.dim() == 3 and x_dec.dim() == 3, "LSTMSeq2SeqFn: x_enc / x_dec must be (B,T,in)")
         B, T_enc, in_enc = x_enc.shape
         in_dec = x_dec.shape[2]
         H = Ue.shape[0]
         out_dim = Wo.shape[1]
         T_dec = opts["T_dec"]
+        _expect(x_dec.shape[0] == B, "LSTMSeq2SeqFn: x_dec has %d sequences, x_enc %d", x_dec.shape[0], B)
+        _expect(tuple(We.shape) == (in_enc, 4 * H) and tuple(Ue.shape) == (H, 4 * H) and be.numel() == 4 * H,
+                "LSTMSeq2SeqFn: encoder weights %s/%s/%s do not fit input width %d, H=%d", tuple(We.shape),
+                tuple(Ue.shape), tuple(be.shape), in_enc, H)
+        _expect(tuple(Wd.shape) == (in_dec, 4 * H) and tuple(Ud.shape) == (H, 4 * H) and bd.numel() == 4 * H,
+                "LSTMSeq2SeqFn: decoder weights %s/%s/%s do not fit input width %d, H=%d", tuple(Wd.shape),
+                tuple(Ud.shape), tuple(bd.shape), in_dec, H)
+        _expect(Wo.shape[0] == H and bo.numel() == out_dim, "LSTMSeq2SeqFn: head weights %s/%s do not fit H=%d",
+                tuple(Wo.shape), tuple(bo.shape), H)
+        if opts["teacher_forcing"]:
+            _expect(x_dec.shape[1] == T_dec, "LSTMSeq2SeqFn: teacher forcing needs x_dec (B,%d,in), got %s", T_dec,
+                    tuple(x_dec.shape))
+        else:
+            _expect(x_dec.shape[1] == 1, "LSTMSeq2SeqFn: autoregressive decoding takes x_dec (B,1,in), got %s",
+                    tuple(x_dec.shape))
+            _expect(out_dim == in_dec, "LSTMSeq2SeqFn: re-feeding needs head width %d == decoder input width %d",
+                    out_dim, in_dec)
+        if extra is not None:
+            _expect(tuple(extra.shape) == (B, T_dec, out_dim), "LSTMSeq2SeqFn: extra must be (B,T_dec,out), got %s",
+                    tuple(extra.shape))
         training = bool(opts.get("training", False))
         dev = x_enc.device
         cfg = _lib.LstmCfg(B, T_enc, T_dec, in_enc, in_dec, H, out_dim,
@@ -196,8 +224,11 @@ class Conv2DFn(torch.autograd.Function):
         lib = _lib.load()
         _require_cuda(x, kernel)
         x = _f32c(x)
+        _expect(x.dim() == 4 and kernel.dim() == 4, "Conv2DFn: x must be (N,H,W,Cin) and kernel (kh,kw,Cin,Cout)")
         N, H, W, Cin = x.shape
-        kh, kw, _, Cout = kernel.shape
+        kh, kw, kc, Cout = kernel.shape
+        _expect(kc == Cin, "Conv2DFn: kernel expects %d input channels, x has %d", kc, Cin)
+        _expect(bias is None or bias.numel() == Cout, "Conv2DFn: bias does not have Cout=%d elements", Cout)
         dil = opts.get("dilation", (1, 1))
         act = opts.get("activation")
         y = torch.empty(N, H, W, Cout, device=x.device)
@@ -291,9 +322,13 @@ class DualDenseFn(torch.autograd.Function):
         lib = _lib.load()
         _require_cuda(x, W1, W2)
         x = _f32c(x)
+        _expect(x.dim() == 3, "DualDenseFn: x must be (B,T,C)")
         B, T, Cin = x.shape
         t0 = int(opts["t0"])
         C1, C2 = W1.shape[-1], W2.shape[-1]
+        _expect(W1.shape[-2] == Cin and W2.shape[-2] == Cin, "DualDenseFn: kernels expect %d / %d inputs, x has %d",
+                W1.shape[-2], W2.shape[-2], Cin)
+        _expect(b1.numel() == C1 and b2.numel() == C2 and 0 <= t0 < T, "DualDenseFn: bias / t0 mismatch")
         math = opts.get("math", _MATH[0])
         full, part = DualDenseFn._cfgs(B, T, t0, Cin, C1, C2)
         y1 = torch.empty(B, T, C1, device=x.device)
@@ -384,8 +419,24 @@ class ConvLSTMStackFn(torch.autograd.Function):
         L = opts["layers"]
         weights = [flat[3 * l:3 * l + 3] for l in range(L)]
         states = [tuple(_f32c(s) for s in flat[3 * L + 2 * l:3 * L + 2 * l + 2]) for l in range(L)]
+        _expect(x.dim() == 5, "ConvLSTMStackFn: x must be (B,T,H,W,C)")
         B, T, H, W, Cin0 = x.shape
         Fs = [w[1].shape[2] for w in weights]
+        cprev = Cin0
+        for l, (K, R, b) in enumerate(weights):
+            F = Fs[l]
+            _expect(K.dim() == 4 and R.dim() == 4 and K.shape[:2] == R.shape[:2],
+                    "ConvLSTMStackFn: layer %d kernel / recurrent kernel shapes %s / %s", l, tuple(K.shape), tuple(R.shape))
+            _expect(K.shape[2] == cprev, "ConvLSTMStackFn: layer %d kernel expects %d input channels, gets %d", l,
+                    K.shape[2], cprev)
+            _expect(K.shape[3] == 4 * F and R.shape[3] == 4 * F and b.numel() == 4 * F,
+                    "ConvLSTMStackFn: layer %d gate width is not 4F = %d", l, 4 * F)
+            for s_ in states[l]:
+                _expect(s_ is None or tuple(s_.shape) == (B, H, W, F),
+                        "ConvLSTMStackFn: layer %d initial state must be (B,H,W,F) = %s, got %s", l, (B, H, W, F),
+                        None if s_ is None else tuple(s_.shape))
+            _expect((states[l][0] is None) == (states[l][1] is None), "ConvLSTMStackFn: give both h0 and c0 or neither")
+            cprev = F
         Fsum = sum(Fs)
         dev = x.device
         dil = opts.get("dilation", (1, 1))
@@ -432,7 +483,7 @@ class ConvLSTMStackFn(torch.autograd.Function):
             cT = torch.empty(B, H, W, F, device=dev)
             h0, c0 = states[l]
             hptr = cat.data_ptr() + 4 * off
-            io = _lib.ConvLstmIO(lx_ptr, ptr(lK), ptr(R), ptr(b), ptr(h0), ptr(c0), None, hptr,
+            io = _lib.ConvLstmIO(lx_ptr, ptr(lK), ptr(R), ptr(b), ptr(h0), ptr(c0), hptr,
                                  ptr(gates), ptr(cseq), ptr(hT), ptr(cT), ptr(fws))
             _lib.check(lib.fov_convlstm_fwd(C.byref(cfg), C.byref(io), st), "fov_convlstm_fwd")
             outs += [hT, cT]
@@ -483,7 +534,7 @@ class ConvLSTMStackFn(torch.autograd.Function):
                 dxp, acc = dcat.data_ptr() + 4 * cfgs[l - 1][3], 1
             gk, gr_, gb = ctx.sinks[l]
             if mask is None:
-                io = _lib.ConvLstmIO(xptr, ptr(K), ptr(R), ptr(b), ptr(h0), ptr(c0), None, hptr,
+                io = _lib.ConvLstmIO(xptr, ptr(K), ptr(R), ptr(b), ptr(h0), ptr(c0), hptr,
                                      ptr(gates), ptr(cseq), None, None, None)
                 g = _lib.ConvLstmGrads(dcat.data_ptr() + 4 * off, ptr(dhT), ptr(dcT), dxp, ptr(dh0), ptr(dc0),
                                        ptr(gk), ptr(gr_), ptr(gb), ptr(ws), acc)
@@ -493,7 +544,7 @@ class ConvLSTMStackFn(torch.autograd.Function):
                 xb_, xt_, xpix_, cin_ = xgeo
                 gk4 = torch.zeros_like(K4)
                 dx4 = torch.empty_like(x4) if dxp else None
-                io = _lib.ConvLstmIO(ptr(x4), ptr(K4), ptr(R), ptr(b), ptr(h0), ptr(c0), None, hptr,
+                io = _lib.ConvLstmIO(ptr(x4), ptr(K4), ptr(R), ptr(b), ptr(h0), ptr(c0), hptr,
                                      ptr(gates), ptr(cseq), None, None, None)
                 g = _lib.ConvLstmGrads(dcat.data_ptr() + 4 * off, ptr(dhT), ptr(dcT), ptr(dx4), ptr(dh0), ptr(dc0),
                                        ptr(gk4), ptr(gr_), ptr(gb), ptr(ws), 0)
@@ -582,9 +633,13 @@ class LossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dl):
-        # the loss weight is already folded into dy by the kernel; the objective is the plain
-        # sum of these losses (Keras compile(loss=[...], loss_weights=[...])), so dl == 1.
-        return None, None, ctx.dy, None, None
+        # the loss weight is already folded into dy by the kernel; dl is whatever the caller did with the loss tensor
+        # afterwards (1 for the plain sum of Keras compile(loss=[...]), the shard weight of a data-parallel step,
+        # a micro-batch average, ...): one scalar multiply of the small (B,T,out) gradient.
+        dy = ctx.dy
+        if dy is not None:
+            dy = dy * dl.reshape(())
+        return None, None, dy, None, None
 
 
 def loss(kind, y_true, y_pred, weight=1.0, running_length=10):
@@ -596,18 +651,19 @@ def loss(kind, y_true, y_pred, weight=1.0, running_length=10):
 # --------------------------------------------------------------------------- #
 
 
-def adam_step(p, g, m, v, t, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, grad_scale=1.0):
+def adam_step(p, g, m, v, t, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, grad_scale=1.0, grad_div=None):
+    """grad_div: optional 1-element device tensor; g is divided by it inside the kernel (no host sync)."""
     lib = _lib.load()
     _require_cuda(p, g, m, v)
     _lib.check(lib.fov_adam_step(p.numel(), ptr(p), ptr(g), ptr(m), ptr(v), int(t), lr, beta1, beta2, eps,
-                                 grad_scale, _stream()), "fov_adam_step")
+                                 grad_scale, ptr(grad_div), _stream()), "fov_adam_step")
 
 
-def rmsprop_step(p, g, a, lr=1e-3, rho=0.9, eps=1e-7, grad_scale=1.0):
+def rmsprop_step(p, g, a, lr=1e-3, rho=0.9, eps=1e-7, grad_scale=1.0, grad_div=None):
     lib = _lib.load()
     _require_cuda(p, g, a)
-    _lib.check(lib.fov_rmsprop_step(p.numel(), ptr(p), ptr(g), ptr(a), lr, rho, eps, grad_scale, _stream()),
-               "fov_rmsprop_step")
+    _lib.check(lib.fov_rmsprop_step(p.numel(), ptr(p), ptr(g), ptr(a), lr, rho, eps, grad_scale, ptr(grad_div),
+                                    _stream()), "fov_rmsprop_step")
 
 
 def mean_var_xyz(frames):
@@ -624,16 +680,57 @@ def mean_var_xyz(frames):
     return out
 
 
+RESAMPLE_MODES = {"sqrt_floor": 0, "sqrt": 1, "var_as_std": 2}
+
+
+class GaussResampleFn(torch.autograd.Function):
+    """frames = mu + sd(var) * noise, differentiable in (mu, var) like K.random_normal(mean=mu, stddev=...)
+    (mycode/convlstm_seq2seq.py:51-60,259-272; mycode/others_LSTM_span_whole.py:64-71,302-315)."""
+
+    @staticmethod
+    def forward(ctx, mode, muvar, noise):
+        lib = _lib.load()
+        _require_cuda(muvar, noise)
+        muvar, noise = _f32c(muvar), _f32c(noise)
+        rows = muvar.numel() // 6
+        _expect(muvar.shape[-1] == 6 and noise.numel() == rows * 90,
+                "gauss_resample: muvar (rows,6) and noise (rows,30,3) disagree: %s vs %s", tuple(muvar.shape),
+                tuple(noise.shape))
+        out = torch.empty_like(noise)
+        _lib.check(lib.fov_gauss_resample(rows, mode, ptr(muvar), ptr(noise), ptr(out), _stream()),
+                   "fov_gauss_resample")
+        ctx.mode, ctx.rows = mode, rows
+        ctx.save_for_backward(muvar, noise)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        muvar, noise = ctx.saved_tensors
+        dmuvar = torch.empty_like(muvar)
+        _lib.check(lib.fov_gauss_resample_bwd(ctx.rows, ctx.mode, ptr(muvar), ptr(noise), ptr(_f32c(dout)), ptr(dmuvar),
+                                              _stream()), "fov_gauss_resample_bwd")
+        return None, dmuvar, None
+
+
 def gauss_resample(muvar, noise, mode="sqrt_floor"):
-    """(rows,6) mean/var + (rows,30,3) N(0,1) noise -> (rows,30,3) frames."""
+    """(rows,6) mean/var + (rows,30,3) N(0,1) noise -> (rows,30,3) frames; gradients flow to muvar."""
+    return GaussResampleFn.apply(RESAMPLE_MODES[mode], muvar, noise)
+
+
+def philox_normal(shape, seed, offset=0, device=None, return_words=False):
+    """N(0,1) draws from the in-kernel Philox4x32-10 stream (fov_philox_normal): element i is word i%4 of
+    philox(counter = offset + i//4, key = seed), Box-Muller on word pairs.  Depends on (seed, offset) only."""
     lib = _lib.load()
-    _require_cuda(muvar, noise)
-    muvar, noise = _f32c(muvar), _f32c(noise)
-    out = torch.empty_like(noise)
-    m = {"sqrt_floor": 0, "sqrt": 1, "var_as_std": 2}[mode]
-    _lib.check(lib.fov_gauss_resample(muvar.shape[0], m, ptr(muvar), ptr(noise), ptr(out), _stream()),
-               "fov_gauss_resample")
-    return out
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    n = 1
+    for d in shape:
+        n *= int(d)
+    out = torch.empty(shape, device=device)
+    words = torch.empty(n, dtype=torch.int32, device=device) if return_words else None
+    _lib.check(lib.fov_philox_normal(n, int(seed) & (2 ** 64 - 1), int(offset), ptr(words), ptr(out), _stream()),
+               "fov_philox_normal")
+    return (out, words) if return_words else out
 
 
 # --------------------------------------------------------------------------- #

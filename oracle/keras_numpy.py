@@ -554,8 +554,43 @@ def init_convlstm_seq2seq(seed=1, in_ch=30, filters=(32, 16, 8), kernel_size=5,
     return w
 
 
+def philox4x32_10(counter, seed):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11 - the counter-based generator behind TF's
+    random_normal, which K.random_normal at mycode/convlstm_seq2seq.py:57 calls): counter (n,) uint64 ->
+    (n,4) uint32 words with counter words (lo, hi, 0, 0) and key (seed lo, seed hi).  Integer restatement the
+    CUDA kernel fov_philox_normal is compared with bit for bit."""
+    c = np.zeros((len(counter), 4), np.uint64)
+    counter = np.asarray(counter, np.uint64)
+    c[:, 0] = counter & np.uint64(0xFFFFFFFF)
+    c[:, 1] = counter >> np.uint64(32)
+    k0 = np.uint64(seed & 0xFFFFFFFF)
+    k1 = np.uint64((seed >> 32) & 0xFFFFFFFF)
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c[:, 0]
+        p1 = M1 * c[:, 2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c = np.stack([hi1 ^ c[:, 1] ^ k0, lo1, hi0 ^ c[:, 3] ^ k1, lo0], axis=1)
+        k0 = (k0 + np.uint64(0x9E3779B9)) & MASK
+        k1 = (k1 + np.uint64(0xBB67AE85)) & MASK
+    return c.astype(np.uint32)
+
+
+def philox_normal(n, seed, offset=0):
+    """n N(0,1) draws of the stream fov_philox_normal defines: element i = word i%4 of counter offset + i//4,
+    Box-Muller on word pairs: u1 = (w0+1) 2^-32, u2 = w1 2^-32, (z0, z1) = sqrt(-2 ln u1) (cos, sin)(2 pi u2).
+    Returns (words uint32 (n,), normals float64 (n,))."""
+    nblk = (n + 3) // 4
+    w = philox4x32_10(np.arange(nblk, dtype=np.uint64) + np.uint64(offset), seed)
+    u1 = (w[:, 0::2].astype(np.float64) + 1.0) * 2.0 ** -32
+    u2 = w[:, 1::2].astype(np.float64) * 2.0 ** -32
+    rad = np.sqrt(-2.0 * np.log(u1))
+    z = np.stack([rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)], axis=-1)   # (nblk, 2 pairs, 2)
+    return w.reshape(-1)[:n], z.reshape(-1)[:n]
+
+
 def convlstm_seq2seq_forward(w, enc_in, dec_in, head_kind="conv2d", steps=10, dilation=(1, 1),
-                             recurrent_activation="hard_sigmoid"):
+                             recurrent_activation="hard_sigmoid", noise=None, resample_mode="var_as_std"):
     """M4 forward (mycode/convlstm_seq2seq.py:100-126,146-165,209-281).
     heatmap form: enc_in (B,10,36,18,30), dec_in (B,1,36,18,30) -> (B,10,36,18,30);
     trajectory forms: enc_in (B,10,1,30,3), dec_in (B,1,1,30,3) ->
@@ -594,6 +629,9 @@ def convlstm_seq2seq_forward(w, enc_in, dec_in, head_kind="conv2d", steps=10, di
             x = y
         else:
             y = dense(d[:, 0].reshape(B, -1), w["head_dense/kernel"], w["head_dense/bias"])
-            x = y[:, None, None, :]
+            if noise is not None:     # cfg.sample_and_refeed (mycode/convlstm_seq2seq.py:259-272)
+                x = gaussian_resample(y[:, :3], y[:, 3:], noise[len(outs)], resample_mode)[:, None]
+            else:
+                x = y[:, None, None, :]
         outs.append(y)
     return np.stack(outs, axis=1)

@@ -201,8 +201,25 @@ def others_lstm_span_whole_forward(w, enc_in, oth_in, dec_in, ra="hard_sigmoid")
     return [torch.stack(outs, 1), r_oth, r_tar]
 
 
+def gaussian_resample(muvar, noise, mode="var_as_std"):
+    """(B,6) [mu | var] + (B,30,3) N(0,1) noise -> (B,30,3); differentiable in muvar like K.random_normal(mean, stddev)
+    (mycode/convlstm_seq2seq.py:51-60; others_LSTM_span_whole.py:64-71; utility.py:73-80)."""
+    mu, var = muvar[:, :3], muvar[:, 3:]
+    if mode == "sqrt_floor":
+        std = torch.sqrt(torch.where(var < 0, torch.full_like(var, 1e-3), var))
+    elif mode == "sqrt":
+        std = torch.sqrt(var)
+    elif mode == "var_as_std":
+        std = var
+    else:
+        raise ValueError(mode)
+    return mu[:, None, :] + std[:, None, :] * noise
+
+
 def convlstm_seq2seq_forward(w, enc_in, dec_in, head_kind="conv2d", steps=10, dilation=(1, 1),
-                             ra="hard_sigmoid"):
+                             ra="hard_sigmoid", noise=None, resample_mode="var_as_std"):
+    """noise (steps,B,30,3): cfg.sample_and_refeed - the dense head's (mu,var) is re-sampled into 30 frames that
+    become the next decoder input (mycode/convlstm_seq2seq.py:259-272)."""
     B = enc_in.shape[0]
     _, states = convlstm_stack(w, enc_in, "enc_convlstm", dilation=dilation, ra=ra)
     x = dec_in[:, 0]
@@ -232,7 +249,10 @@ def convlstm_seq2seq_forward(w, enc_in, dec_in, head_kind="conv2d", steps=10, di
             x = y
         else:
             y = dense(d[:, 0].reshape(B, -1), w["head_dense/kernel"], w["head_dense/bias"])
-            x = y[:, None, None, :]
+            if noise is not None:
+                x = gaussian_resample(y, noise[len(outs)], resample_mode)[:, None]     # (B,1,30,3)
+            else:
+                x = y[:, None, None, :]
         outs.append(y)
     return torch.stack(outs, 1)
 

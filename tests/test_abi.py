@@ -10,10 +10,16 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "fov360.h")).read()
+def _declared_symbols(header="fov360.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(fov_[a-z0-9_]+)\s*\(", src)))
+
+
+def _exported_symbols(path):
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", path], check=True, capture_output=True, text=True).stdout
+    return sorted({l.split()[-1] for l in out.splitlines() if l.split() and l.split()[-1].startswith("fov_")})
 
 
 def test_library_builds_and_exports_every_declared_symbol():
@@ -28,6 +34,17 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert name in _lib.SYMBOLS, "ctypes binding missing for %s" % name
     assert set(_lib.SYMBOLS) == set(declared)
     assert _lib.load().fov_version() >= 100
+    # nothing undeclared leaves the library: every exported fov_* symbol is in fov360.h (the boundary) or in
+    # fov_debug.h (diagnostic switches, not on the product path)
+    debug = _declared_symbols("fov_debug.h")
+    assert all(n.startswith("fov_debug_") for n in debug)
+    exported = _exported_symbols(_lib.LIB_PATH)
+    assert set(exported) == set(declared) | set(debug), sorted(set(exported) ^ (set(declared) | set(debug)))
+    # the data-parallel entry points exist and validate their arguments without a GPU or NCCL
+    lib = _lib.load()
+    assert lib.fov_dp_unique_id_bytes() == 128 and lib.fov_dp_world() == 1 and lib.fov_dp_rank() == 0
+    assert lib.fov_dp_init(None, 0, 1) == -1 and lib.fov_dp_destroy() == 0
+    assert lib.fov_dp_allreduce(ctypes.c_void_p(16), 4, None) == -1 and b"fov_dp_init" in lib.fov_last_error()
 
 
 def test_struct_layouts_match_the_c_header(tmp_path):

@@ -1,6 +1,6 @@
 """world_size-2 gloo test (CPU) of the data-parallel host logic: contiguous batch sharding,
-one summed allreduce of the flat gradient bucket, 1/world scaling, identical optimiser step on
-every rank == the single-process full-batch step.  The per-shard gradients come from the CPU
+one count-weighted summed allreduce of the flat gradient bucket (unequal shards: 9 samples over 2 ranks), identical
+optimiser step on every rank == the single-process full-batch step.  The per-shard gradients come from the CPU
 oracle (the CUDA path cannot run here); the code under test is longterm360fov_b200.parallel."""
 import os
 import socket
@@ -25,7 +25,7 @@ def _free_port():
 
 def _data():
     rng = np.random.default_rng(0)
-    enc = rng.uniform(-1, 1, (8, 10, 6)); dec = rng.uniform(-1, 1, (8, 10, 6)); tgt = rng.uniform(-1, 1, (8, 10, 6))
+    enc = rng.uniform(-1, 1, (9, 10, 6)); dec = rng.uniform(-1, 1, (9, 10, 6)); tgt = rng.uniform(-1, 1, (9, 10, 6))
     return enc, dec, tgt
 
 
@@ -41,20 +41,25 @@ def _worker(rank, world, port, out_q):
     order = sorted(w)
     enc, dec, tgt = parallel.shard_batch(list(_data()), rank, world)
     opt = kt.KerasAdam(w)
+    comm = parallel.TorchComm()
+    assert (comm.rank, comm.world) == (rank, world)
+    n_local = len(enc)                                       # 5 on rank 0, 4 on rank 1
     losses = []
     for _ in range(3):
         loss, _, grads = kt.loss_and_grads(kt.fov_seq2seq_forward, w, [torch.tensor(enc), torch.tensor(dec)],
                                            [torch.tensor(tgt)], [kt.mse])
-        bucket = _flat(grads, order)
-        scale = parallel.allreduce_gradients(bucket)
-        bucket *= scale
+        # the model back-propagates with seed n_local (gradients x local count) into a bucket with a reserved tail
+        bucket = torch.cat([_flat(grads, order) * n_local, torch.zeros(64, dtype=torch.float64)])
+        div = parallel.allreduce_gradients(bucket, comm, n_local)
+        assert float(div) == 9.0
+        bucket = bucket / div
         off = 0
         g2 = {}
         for k in order:
             n = w[k].numel()
             g2[k] = bucket[off:off + n].view_as(w[k]); off += n
         opt.step(g2)
-        losses.append(float(loss))
+        losses.append(float(loss) * n_local / 9.0)
     out_q.put((rank, _flat({k: v.detach() for k, v in w.items()}, order).numpy(), losses))
     dist.destroy_process_group()
 
@@ -85,7 +90,7 @@ def test_dp2_equals_full_batch_step():
     ref = _flat({k: v.detach() for k, v in w.items()}, order).numpy()
     np.testing.assert_allclose(res[0][1], res[1][1], atol=0)            # ranks stay identical
     np.testing.assert_allclose(res[0][1], ref, atol=1e-12)              # == full-batch training
-    np.testing.assert_allclose(np.mean([res[0][2], res[1][2]], axis=0), full_losses, atol=1e-12)
+    np.testing.assert_allclose(np.sum([res[0][2], res[1][2]], axis=0), full_losses, atol=1e-12)
 
 
 def test_shard_bounds_cover_and_partition():

@@ -243,3 +243,34 @@ def test_m3_gradients_finite_difference():
             wm = {k: v.copy() for k, v in w.items()}; wm[name][idx] -= eps
             fd = (total(wp) - total(wm)) / (2 * eps)
             assert abs(fd - grads[name][idx].item()) < 1e-6 + 1e-4 * abs(fd), (name, idx, fd, grads[name][idx].item())
+
+
+def test_philox_restatement_matches_random123_known_answers():
+    """Philox4x32-10 known-answer vectors of the Random123 distribution (kat_vectors: counter, key -> output):
+    the pin for oracle.keras_numpy.philox4x32_10, which the CUDA stream fov_philox_normal must equal bit for bit."""
+    w = kn.philox4x32_10(np.array([0], np.uint64), 0)[0]
+    assert [int(v) for v in w] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    words, z = kn.philox_normal(200000, seed=99)
+    assert words.dtype == np.uint32 and abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
+    # offset addressing: block k of the stream is counter k
+    w2, _ = kn.philox_normal(8, seed=99, offset=5)
+    assert np.array_equal(w2, words[20:28])
+
+
+def test_resample_modes_and_torch_twin_agree():
+    rng = np.random.default_rng(0)
+    muvar = rng.uniform(0.05, 1, (7, 6)); noise = rng.normal(size=(7, 30, 3))
+    muvar[2, 4] = -0.3
+    for mode in ("sqrt_floor", "var_as_std"):
+        a = kn.gaussian_resample(muvar[:, :3], muvar[:, 3:], noise, mode)
+        b = kt.gaussian_resample(torch.tensor(muvar), torch.tensor(noise), mode).numpy()
+        np.testing.assert_allclose(a, b, atol=1e-12)
+    assert np.isnan(kn.gaussian_resample(muvar[:, :3], muvar[:, 3:], noise, "sqrt")[2, :, 1]).all()   # sqrt(negative), as written
+    # M4 with sampling: NumPy and torch restatements agree
+    w = kn.init_convlstm_seq2seq(seed=5, in_ch=3, filters=(4, 2, 2), kernel_size=3, head=None, head_kind="dense", flat_dim=8 * 30)
+    enc = rng.uniform(-1, 1, (2, 3, 1, 30, 3)); dec = enc[:, -1:]
+    nz = rng.normal(size=(3, 2, 30, 3))
+    a = kn.convlstm_seq2seq_forward({k: v.astype(np.float64) for k, v in w.items()}, enc, dec, head_kind="dense", steps=3, noise=nz)
+    b = kt.convlstm_seq2seq_forward(kt.to_torch(w), torch.tensor(enc), torch.tensor(dec), head_kind="dense", steps=3,
+                                    noise=torch.tensor(nz)).numpy()
+    np.testing.assert_allclose(a, b, atol=1e-10)
