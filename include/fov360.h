@@ -64,7 +64,8 @@ typedef struct {
   int dec_zero_init;  /* 1: decoder starts from a zero state (FoV_seq2seq_no_teac_forc.py:29) */
   int training;       /* 1: write the saved-activation buffers */
   int math;           /* FOV_MATH_* (declared below): 0 = fp32 CUDA-core kernel; 1..3 = the forward runs on tensor
-                         cores (tcgen05, that many bf16 terms per operand) when in_enc, in_dec <= 16 */
+                         cores (tcgen05, that many bf16 terms per operand): inputs up to 16 features ride in the
+                         per-step GEMM, wider ones (FoV_seq2seq's 90) go through the time-batched projection (io.ws) */
 } fov_lstm_cfg;
 
 typedef struct {
@@ -89,7 +90,13 @@ typedef struct {
   float *y;                      /* (B,T_dec,out) */
   float *hT, *cT;                /* optional final state (B,H) */
   fov_lstm_saved enc, dec;       /* any pointer may be NULL when training == 0 */
+  float *ws;                     /* optional workspace of fov_lstm_fwd_ws_bytes() bytes: holds the time-batched input
+                                    projection x_t . W of every step (one TMA-fed tcgen05 GEMM per phase) that lets
+                                    inputs wider than 16 features run the tensor-core recurrence */
 } fov_lstm_io;
+
+/* bytes of fov_lstm_io.ws this configuration can use (0: none needed) */
+size_t fov_lstm_fwd_ws_bytes(const fov_lstm_cfg* cfg);
 
 int fov_lstm_seq2seq_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w,
                          const fov_lstm_io* io, void* stream);

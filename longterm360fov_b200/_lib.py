@@ -39,7 +39,7 @@ class LstmSaved(C.Structure):
 
 class LstmIO(C.Structure):
     _fields_ = [(n, c_float_p) for n in ("x_enc", "x_dec", "extra", "h0", "c0", "y", "hT", "cT")] + \
-               [("enc", LstmSaved), ("dec", LstmSaved)]
+               [("enc", LstmSaved), ("dec", LstmSaved), ("ws", c_float_p)]
 
 
 class LstmGrads(C.Structure):
@@ -93,6 +93,7 @@ SYMBOLS = {
     "fov_lstm_seq2seq_bwd": (_I, [C.POINTER(LstmCfg), C.POINTER(LstmWeights), C.POINTER(LstmIO),
                                   C.POINTER(LstmGrads), _P]),
     "fov_lstm_bwd_ws_floats": (C.c_size_t, [C.POINTER(LstmCfg)]),
+    "fov_lstm_fwd_ws_bytes": (C.c_size_t, [C.POINTER(LstmCfg)]),
     "fov_conv2d_fwd": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P]),
     "fov_conv2d_bwd_data": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P]),
     "fov_conv2d_bwd_weight": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P]),

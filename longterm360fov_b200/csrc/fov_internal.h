@@ -39,6 +39,13 @@ int fov_conv_bwd_data_preflipped(const fov_conv_cfg* fwd_cfg, const float* dy, c
 // Persistent fc-LSTM forward on tensor cores (lstm_seq2seq_tc.cu); same contract as fov_lstm_seq2seq_fwd
 bool lstm_tc_supported(const fov_lstm_cfg* cfg);
 int lstm_tc_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w, const fov_lstm_io* io, cudaStream_t st);
+size_t lstm_tc_fwd_ws_floats(const fov_lstm_cfg* cfg);
+// Time-batched input projection P = x . W on tensor cores, fed by TMA (xproj_tc.cu); P is the tiled workspace the
+// tensor-core forward reads, xh (optional) receives the x part of the saved [h | x | 0] rows
+size_t lstm_xproj_ws_floats(int B, int T);
+bool lstm_xproj_supported(int B, int T, int in, int math, const float* x);
+int lstm_xproj_run(int B, int T, int in, int math, const float* x, const float* W, float* P, float* xh, int K_xh,
+                   cudaStream_t st);
 // Persistent fc-LSTM BPTT on tensor cores: writes dz_enc / dz_dec / dpre like the fp32 kernel (no weight gradients)
 bool lstm_tc_bwd_supported(const fov_lstm_cfg* cfg);
 int lstm_tc_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w, const fov_lstm_io* io, const fov_lstm_grads* g,

@@ -15,7 +15,7 @@
 static int g_lstm_tc_mode = 0;
 extern "C" void fov_debug_lstm_tc(int mode) { g_lstm_tc_mode = mode; }
 // time-batched input projection in front of the tensor-core forward: -1 never, 0 choose (inputs wider than 16), 1 always
-static int g_lstm_xproj_mode = 0;
+int g_lstm_xproj_mode = 0;
 extern "C" void fov_debug_lstm_xproj(int mode) { g_lstm_xproj_mode = mode; }
 // A/B switch for the tensor-core LSTM weight gradient (needs fov_lstm_grads.ws).  History: on unpadded 70-float [h|x]
 // rows it took the unaligned gather path of wgrad_tc.cu and lost to the SIMT kernels (11.07 vs 10.96 ms per config-2
@@ -445,6 +445,11 @@ extern "C" size_t fov_lstm_bwd_ws_floats(const fov_lstm_cfg* cfg) {
   return n;
 }
 
+extern "C" size_t fov_lstm_fwd_ws_bytes(const fov_lstm_cfg* cfg) {
+  if (!cfg || check_cfg(cfg) || cfg->math == FOV_MATH_FP32 || g_lstm_tc_mode < 0) return 0;
+  return lstm_tc_fwd_ws_floats(cfg) * sizeof(float);
+}
+
 extern "C" int fov_lstm_seq2seq_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w,
                                     const fov_lstm_io* io, void* stream) {
   int rc = check_cfg(cfg);
@@ -464,9 +469,11 @@ extern "C" int fov_lstm_seq2seq_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
   // tensor-core forward (lstm_seq2seq_tc.cu): 128-sequence tiles.  Measured on B200, AR decode of the mu/var model:
   // B=512..2048 0.088 ms vs 0.096 ms fp32 (both latency bound), B=3072 0.088 vs 0.133, B=75776 0.29 vs 1.47 ms.  In
   // training mode the row-per-thread stores of the saved tensors need every SM busy to pay off (B=8880: equal).
-  const int tc_min_B = cfg->training ? 128 * fov_num_sms() : 512;
+  const bool wide = (cfg->T_enc > 0 && cfg->in_enc > 16) || (cfg->T_dec > 0 && cfg->in_dec > 16);
+  const int tc_min_B = (cfg->training && !wide) ? 128 * fov_num_sms() : 512;
   if (cfg->math != FOV_MATH_FP32 && g_lstm_tc_mode >= 0 && lstm_tc_supported(cfg) &&
-      (g_lstm_tc_mode > 0 || cfg->B >= tc_min_B))
+      (g_lstm_tc_mode > 0 || cfg->B >= tc_min_B) &&
+      (!wide || (io->ws != nullptr && (uintptr_t)io->x_enc % 16 == 0 && (uintptr_t)io->x_dec % 16 == 0)))
     return lstm_tc_fwd(&P.cfg, w, io, st);
   // 64 sequences per CTA when the operand tile fits, else 32
   // ... and 16 when even 32-sequence tiles would leave SMs idle (the recurrence is latency bound: smaller tiles =

@@ -40,6 +40,9 @@ struct TcPhase {
   const float* extra;                      // optional (B,T,out)
   float* y;                                // (B,T,out)
   fov_lstm_saved sv;
+  // time-batched input projection x_t . W of every step of the phase (xproj_tc.cu), tiled [b/128][t][col/4][b%128][4];
+  // when set, the per-step GEMM is the K = 64 recurrent part only and the epilogue adds the projection (any in_dim)
+  const float* xproj;
 };
 
 struct LstmTcParams {
@@ -123,7 +126,7 @@ __device__ __forceinline__ void pin8(float (&v)[8]) {
 // WPG = warps per 128-sequence group: 4 (a thread owns the 64 hidden units of its sequence) or 8 (the two warps of a
 // TMEM lane quarter own 32 units each: twice the warps per scheduler to hide the MUFU / tcgen05.ld latencies, half the
 // cell state per thread; the head partial sums of the upper half travel through shared memory)
-template <int NS, int NG, int REC, int OD, bool TRAIN, int WPG>
+template <int NS, int NG, int REC, int OD, bool TRAIN, int WPG, bool XP>
 __global__ void __launch_bounds__(32 * WPG * NG, 1) lstm_tc_fwd_kernel(const __grid_constant__ LstmTcParams P) {
   constexpr int NW = 32 * WPG * NG;        // threads
   constexpr int GT = 32 * WPG;             // threads per group
@@ -178,19 +181,21 @@ __global__ void __launch_bounds__(32 * WPG * NG, 1) lstm_tc_fwd_kernel(const __g
     const long long t_begin = clock64();
     const uint32_t idesc = idesc_bf16_f32(kRows, kG, 0, 0);
     // D[128 x 256] = [x_t | h_{t-1}] x [W ; U] for my group: called by ONE thread after the group barrier
-    auto issue_mmas = [&]() {
+    auto issue_mmas = [&](bool use_x) {
       tc_fence_after();
       const uint32_t hA_s = base + kActOff + (uint32_t)g * kGrpBytes, xA_s = hA_s + NS * kATerm;
       const uint32_t d = tmem_d + (uint32_t)(g * kG);
       uint32_t acc = 0;
-      // x part: one k16 step, the terms are 32-byte chunks of the same tile
+      // x part: one k16 step, the terms are 32-byte chunks of the same tile (skipped when the projection is time-batched)
+      if (use_x) {
 #pragma unroll
-      for (int sum = NS - 1; sum >= 0; --sum) {
+        for (int sum = NS - 1; sum >= 0; --sum) {
 #pragma unroll
-        for (int sa = 0; sa <= sum; ++sa) {
-          const int sb = sum - sa;
-          umma_bf16(d, desc_at(kDescHi128, xA_s + sa * 32), desc_at(kDescHi128, base + kWbOff + sb * 32), idesc, acc);
-          acc = 1;
+          for (int sa = 0; sa <= sum; ++sa) {
+            const int sb = sum - sa;
+            umma_bf16(d, desc_at(kDescHi128, xA_s + sa * 32), desc_at(kDescHi128, base + kWbOff + sb * 32), idesc, acc);
+            acc = 1;
+          }
         }
       }
       // h part: four k16 steps
@@ -202,7 +207,8 @@ __global__ void __launch_bounds__(32 * WPG * NG, 1) lstm_tc_fwd_kernel(const __g
           for (int sa = 0; sa <= sum; ++sa) {
             const int sb = sum - sa;
             umma_bf16(d, desc_at(kDescHi128, hA_s + sa * kATerm + k4 * 32),
-                      desc_at(kDescHi128, base + sb * kBTerm + k4 * 32), idesc, 1u);
+                      desc_at(kDescHi128, base + sb * kBTerm + k4 * 32), idesc, acc);
+            acc = 1;
           }
         }
       }
@@ -240,6 +246,7 @@ __global__ void __launch_bounds__(32 * WPG * NG, 1) lstm_tc_fwd_kernel(const __g
     int step = 0;
     for (int pi = 0; pi < P.nph; ++pi) {
       const TcPhase& ph = P.ph[pi];
+      const bool xp = XP && ph.xproj != nullptr;          // input projection precomputed for every step of this phase
       const int in_dim = ph.in_dim, T = ph.T, K = fov_lstm_xh_stride(kH, in_dim);   // padded [h | x | 0] row width
       const bool save = TRAIN;                            // inference instantiations carry no saved-tensor stores
       const int xh_vec = 4;
@@ -266,6 +273,7 @@ __global__ void __launch_bounds__(32 * WPG * NG, 1) lstm_tc_fwd_kernel(const __g
         }
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
+          if (xp) break;
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -310,7 +318,7 @@ __global__ void __launch_bounds__(32 * WPG * NG, 1) lstm_tc_fwd_kernel(const __g
         }
       }
       // ---- x_0 ----
-      if (lead) {
+      if (lead && !xp) {
         float xn[kXK];
 #pragma unroll
         for (int k = 0; k < kXK; ++k)
@@ -326,7 +334,9 @@ __global__ void __launch_bounds__(32 * WPG * NG, 1) lstm_tc_fwd_kernel(const __g
       fence_proxy_async_smem();
       tc_fence_before();
       bar_workers(NW);
-      if (issuer) issue_mmas();
+      if (issuer) issue_mmas(!xp);
+      // my row of the tiled projection workspace: column group cg of step t at Pr + (t * 64 + cg) * 512 floats
+      const float* Pr = xp ? ph.xproj + (((size_t)(b >> 7) * T) * 64 * 128 + (size_t)(b & 127)) * 4 : nullptr;
 
       const bool next_phase_carries = (pi + 1 < P.nph) && !P.ph[pi + 1].zero_init;
       for (int t = 0; t < T; ++t) {
@@ -334,11 +344,22 @@ __global__ void __launch_bounds__(32 * WPG * NG, 1) lstm_tc_fwd_kernel(const __g
         float xn[kXK];
 #pragma unroll
         for (int k = 0; k < kXK; ++k) xn[k] = 0.0f;
-        if (!ph.ar && more && lead) {
+        if (!ph.ar && more && lead && !xp) {
 #pragma unroll
           for (int k = 0; k < kXK; ++k)
             xn[k] = (valid && k < in_dim) ? __ldg(&ph.x[((size_t)b * ph.x_T + t + 1) * in_dim + k]) : 0.0f;
         }
+        // projection of this step, first pass: in flight while waiting for the accumulator
+        float4 pq[XP ? 2 : 1][8];
+        auto p_load = [&](int p8, float4 (&dst)[8]) {
+          const float* src = Pr + ((size_t)t * 64 + (u0 >> 2) + p8 * 2) * 512;
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi) {
+            dst[gi * 2] = __ldg(reinterpret_cast<const float4*>(src + (size_t)gi * 16 * 512));
+            dst[gi * 2 + 1] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(gi * 16 + 1) * 512));
+          }
+        };
+        if (XP && xp) p_load(0, pq[0]);
         const size_t rowt = (size_t)b * T + t;
         float* gates_p = (save && valid && ph.sv.gates) ? ph.sv.gates + rowt * kG : nullptr;
         float* c_p = (save && valid && ph.sv.c) ? ph.sv.c + rowt * kH : nullptr;
@@ -387,6 +408,16 @@ __global__ void __launch_bounds__(32 * WPG * NG, 1) lstm_tc_fwd_kernel(const __g
             tmem_ld_wait();
 #pragma unroll
             for (int gi = 0; gi < 4; ++gi) pin8(ga[gi]);
+          }
+          if (XP && xp) {
+            if (p8 + 1 < NPASS) p_load(p8 + 1, pq[XP ? ((p8 + 1) & 1) : 0]);
+            const float4 (&pp)[8] = pq[XP ? (p8 & 1) : 0];
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) {
+              ga[gi][0] += pp[gi * 2].x; ga[gi][1] += pp[gi * 2].y; ga[gi][2] += pp[gi * 2].z; ga[gi][3] += pp[gi * 2].w;
+              ga[gi][4] += pp[gi * 2 + 1].x; ga[gi][5] += pp[gi * 2 + 1].y; ga[gi][6] += pp[gi * 2 + 1].z;
+              ga[gi][7] += pp[gi * 2 + 1].w;
+            }
           }
           float hn[8];
 #pragma unroll
@@ -478,7 +509,7 @@ __global__ void __launch_bounds__(32 * WPG * NG, 1) lstm_tc_fwd_kernel(const __g
           }
         }
         if (more) {
-          if (lead) {
+          if (lead && !xp) {
             x_store(xn);
             if (save && valid && ph.sv.xh) {
               float* xr = ph.sv.xh + (rowt + 1) * K + kH;
@@ -491,7 +522,7 @@ __global__ void __launch_bounds__(32 * WPG * NG, 1) lstm_tc_fwd_kernel(const __g
           bar_group(g, GT);
           long long k3 = 0;
           if (dbg) k3 = clock64();
-          if (issuer) issue_mmas();
+          if (issuer) issue_mmas(!xp);
           if (dbg) tm += clock64() - k3;
         }
         ++step;
@@ -524,12 +555,12 @@ size_t tc_smem_bytes() {
   return (size_t)(NS + 1) * kBTerm + (size_t)NG * (NS + 1) * kATerm + sizeof(LstmTcBook<OD>) + 1024;
 }
 
-template <int NS, int NG, int REC, int OD, bool TRAIN, int WPG>
+template <int NS, int NG, int REC, int OD, bool TRAIN, int WPG, bool XP = false>
 int launch_tc_w(const LstmTcParams& P, cudaStream_t st) {
   const size_t smem = tc_smem_bytes<NS, NG, OD>();
   static FovPerDevice configured;
   if (!configured.done()) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_tc_fwd_kernel<NS, NG, REC, OD, TRAIN, WPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(lstm_tc_fwd_kernel<NS, NG, REC, OD, TRAIN, WPG, XP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) {
       fov_set_error("fov_lstm (tensor-core): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -539,7 +570,7 @@ int launch_tc_w(const LstmTcParams& P, cudaStream_t st) {
   }
   const int per_cta = kRows * NG;
   const int grid = (P.B + per_cta - 1) / per_cta;
-  lstm_tc_fwd_kernel<NS, NG, REC, OD, TRAIN, WPG><<<grid, 32 * WPG * NG, smem, st>>>(P);
+  lstm_tc_fwd_kernel<NS, NG, REC, OD, TRAIN, WPG, XP><<<grid, 32 * WPG * NG, smem, st>>>(P);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
@@ -548,6 +579,10 @@ int g_lstm_tc_wpg = 8;                       // diagnostics: 4 = one thread per 
 
 template <int NS, int NG, int REC, int OD, bool TRAIN>
 int launch_tc_t(const LstmTcParams& P, cudaStream_t st) {
+  // a phase with a time-batched input projection: ONE group of 8 warps per CTA (32 hidden units per thread leave the
+  // registers for the projection prefetch; without the x operand / x weights the CTA needs ~100 KB of shared memory)
+  if (NG == 1 && (P.ph[0].xproj || (P.nph > 1 && P.ph[1].xproj)))
+    return launch_tc_w<NS, NG, REC, OD, TRAIN, (NG == 1 ? 8 : 4), (NG == 1)>(P, st);
   // 8 warps per group when a CTA runs ONE group (batches below 128 x 148 sequences, default two-term arithmetic): the
   // step is then a serial MMA -> epilogue chain and the extra warps shorten it (B=4096 AR decode: 0.091 vs 0.112 ms).
   // With two groups per CTA 16 warps get 128 registers each, spill, and lose 5 % to the 4-warp form (measured).
@@ -923,12 +958,34 @@ int lstm_tc_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w, const fov_ls
   return hs ? launch_tc_bwd_oa<2, FOV_REC_HARD_SIGMOID>(P, ar, st) : launch_tc_bwd_oa<2, FOV_REC_SIGMOID>(P, ar, st);
 }
 
+extern int g_lstm_xproj_mode;    // lstm_seq2seq.cu (fov_debug_lstm_xproj): -1 never, 0 inputs wider than 16, 1 whenever allowed
+
+namespace {
+// a phase takes the time-batched projection when its inputs are known in advance (not autoregressive), the shape fits
+// the TMA view and either the input is wider than the fused x operand (16) or the debug switch asks for it
+bool phase_wants_xproj(const fov_lstm_cfg* cfg, bool dec) {
+  const int in = dec ? cfg->in_dec : cfg->in_enc, T = dec ? cfg->T_dec : cfg->T_enc;
+  if (T <= 0 || g_lstm_xproj_mode < 0 || (dec && !cfg->teacher_forcing)) return false;
+  if (in <= kXK && g_lstm_xproj_mode == 0) return false;
+  return lstm_xproj_supported(cfg->B, T, in, cfg->math, nullptr);
+}
+}  // namespace
+
 bool lstm_tc_supported(const fov_lstm_cfg* cfg) {
   if (cfg->H != kH || cfg->math < FOV_MATH_BF16 || cfg->math > FOV_MATH_BF16X3) return false;
-  if (cfg->T_enc > 0 && cfg->in_enc > kXK) return false;
-  if (cfg->T_dec > 0 && cfg->in_dec > kXK) return false;
+  if (cfg->T_enc > 0 && cfg->in_enc > kXK && !phase_wants_xproj(cfg, false)) return false;
+  if (cfg->T_dec > 0 && cfg->in_dec > kXK && !phase_wants_xproj(cfg, true)) return false;
   if (cfg->out_dim > 16) return false;
   return true;
+}
+
+// floats of fov_lstm_io.ws the tensor-core forward wants for this configuration (0: none)
+size_t lstm_tc_fwd_ws_floats(const fov_lstm_cfg* cfg) {
+  if (!lstm_tc_supported(cfg)) return 0;
+  size_t n = 0;
+  if (phase_wants_xproj(cfg, false)) n += lstm_xproj_ws_floats(cfg->B, cfg->T_enc);
+  if (phase_wants_xproj(cfg, true)) n += lstm_xproj_ws_floats(cfg->B, cfg->T_dec);
+  return n;
 }
 
 int lstm_tc_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w, const fov_lstm_io* io, cudaStream_t st) {
@@ -942,6 +999,7 @@ int lstm_tc_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w, const fov_ls
     ph.Wk = w->enc_kernel; ph.Uk = w->enc_recurrent; ph.bk = w->enc_bias;
     ph.x = io->x_enc; ph.in_dim = cfg->in_enc; ph.T = cfg->T_enc; ph.x_T = cfg->T_enc;
     ph.ar = 0; ph.has_head = 0; ph.zero_init = 0; ph.extra = nullptr; ph.y = nullptr; ph.sv = io->enc;
+    ph.xproj = nullptr;
   }
   if (cfg->T_dec > 0) {
     TcPhase& ph = P.ph[n++];
@@ -950,14 +1008,39 @@ int lstm_tc_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w, const fov_ls
     ph.ar = cfg->teacher_forcing == 0; ph.x_T = ph.ar ? 1 : cfg->T_dec;
     ph.has_head = P.out_dim > 0; ph.zero_init = cfg->dec_zero_init ? 1 : 0;
     ph.extra = io->extra; ph.y = io->y; ph.sv = io->dec;
+    ph.xproj = nullptr;
   }
   P.nph = n;
+  // ---- time-batched input projections (xproj_tc.cu): P = x . W for every step of a phase, one TMA-fed launch each ----
+  bool any_xp = false;
+  {
+    float* wsp = io->ws;
+    for (int i = 0; i < n; ++i) {
+      TcPhase& ph = P.ph[i];
+      const bool dec = cfg->T_enc > 0 ? i == 1 : true;
+      const bool want = phase_wants_xproj(cfg, dec) && wsp != nullptr && (uintptr_t)ph.x % 16 == 0;
+      if (!want) {
+        if (ph.in_dim > kXK) {
+          fov_set_error("fov_lstm (tensor-core): a %d-wide input needs the time-batched projection: pass fov_lstm_io.ws "
+                        "(fov_lstm_fwd_ws_bytes) and a 16-byte aligned input", ph.in_dim);
+          return FOV_ERR_ARG;
+        }
+        continue;
+      }
+      float* xh = (cfg->training && ph.sv.xh) ? ph.sv.xh : nullptr;
+      int rc = lstm_xproj_run(cfg->B, ph.T, ph.in_dim, cfg->math, ph.x, ph.Wk, wsp, xh, fov_lstm_xh_stride(kH, ph.in_dim), st);
+      if (rc) return rc;
+      ph.xproj = wsp;
+      wsp += lstm_xproj_ws_floats(cfg->B, ph.T);
+      any_xp = true;
+    }
+  }
   auto a16 = [](const void* q) { return (uintptr_t)q % 16 == 0; };
   FOV_CHECK_ARG(a16(io->enc.gates) && a16(io->enc.c) && a16(io->enc.hseq) && a16(io->dec.gates) && a16(io->dec.c) &&
                     a16(io->dec.hseq) && a16(io->enc.xh) && a16(io->dec.xh) && a16(io->hT) && a16(io->cT),
                 "tensor-core fc-LSTM needs 16-byte aligned state / saved tensors");
   // two groups per CTA (MMA / epilogue overlap) once there are enough sequences to fill the SMs with one group each
-  const bool two = cfg->math <= FOV_MATH_BF16X2 && cfg->B > kRows * fov_num_sms();
+  const bool two = !any_xp && cfg->math <= FOV_MATH_BF16X2 && cfg->B > kRows * fov_num_sms();
   switch (cfg->math) {
     case FOV_MATH_BF16: return two ? launch_tc_ro<1, 2>(P, cfg->rec_act, st) : launch_tc_ro<1, 1>(P, cfg->rec_act, st);
     case FOV_MATH_BF16X2: return two ? launch_tc_ro<2, 2>(P, cfg->rec_act, st) : launch_tc_ro<2, 1>(P, cfg->rec_act, st);

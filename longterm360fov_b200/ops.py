@@ -120,11 +120,14 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
             saved["dec_gates"] = torch.empty(B, T_dec, 4 * H, device=dev)
             saved["dec_c"] = torch.empty(B, T_dec, H, device=dev)
             saved["dec_hseq"] = torch.empty(B, T_dec, H, device=dev)
+        # workspace of the time-batched input projection (inputs wider than 16 features on the tensor-core path)
+        nws = lib.fov_lstm_fwd_ws_bytes(C.byref(cfg))
+        ws = _ws(nws, dev) if nws else None
         io = _lib.LstmIO(ptr(x_enc), ptr(x_dec), ptr(extra), None, None, ptr(y), None, None,
                          _lib.LstmSaved(ptr(saved.get("enc_xh")), ptr(saved.get("enc_gates")),
                                         ptr(saved.get("enc_c")), ptr(enc_hseq)),
                          _lib.LstmSaved(ptr(saved.get("dec_xh")), ptr(saved.get("dec_gates")),
-                                        ptr(saved.get("dec_c")), ptr(saved.get("dec_hseq"))))
+                                        ptr(saved.get("dec_c")), ptr(saved.get("dec_hseq"))), ptr(ws))
         _lib.check(lib.fov_lstm_seq2seq_fwd(C.byref(cfg), C.byref(w), C.byref(io), _stream()),
                    "fov_lstm_seq2seq_fwd")
         if training:
@@ -153,7 +156,7 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
                          _lib.LstmSaved(ptr(sv["enc_xh"]), ptr(sv["enc_gates"]), ptr(sv["enc_c"]),
                                         ptr(enc_hseq)),
                          _lib.LstmSaved(ptr(sv["dec_xh"]), ptr(sv["dec_gates"]), ptr(sv["dec_c"]),
-                                        ptr(sv["dec_hseq"])))
+                                        ptr(sv["dec_hseq"])), None)
         g = _lib.LstmGrads(ptr(dy), ptr(dhseq_enc), ptr(y), ptr(dz_enc), ptr(dz_dec), ptr(dpre),
                            ptr(s["enc_kernel"]), ptr(s["enc_recurrent"]), ptr(s["enc_bias"]),
                            ptr(s["dec_kernel"]), ptr(s["dec_recurrent"]), ptr(s["dec_bias"]),
@@ -175,8 +178,10 @@ def lstm_states(x_enc, We, Ue, be, rec_act="hard_sigmoid", h0=None, c0=None):
     w = _lib.LstmWeights(ptr(We), ptr(Ue), ptr(be), None, None, None, None, None)
     hT = torch.empty(B, H, device=x_enc.device)
     cT = torch.empty(B, H, device=x_enc.device)
+    nws = lib.fov_lstm_fwd_ws_bytes(C.byref(cfg))
+    ws = _ws(nws, x_enc.device) if nws else None
     io = _lib.LstmIO(ptr(x_enc), None, None, ptr(_f32c(h0)), ptr(_f32c(c0)), None, ptr(hT), ptr(cT),
-                     _lib.LstmSaved(), _lib.LstmSaved())
+                     _lib.LstmSaved(), _lib.LstmSaved(), ptr(ws))
     _lib.check(lib.fov_lstm_seq2seq_fwd(C.byref(cfg), C.byref(w), C.byref(io), _stream()), "lstm_states")
     return hT, cT
 
@@ -199,7 +204,7 @@ def lstm_decode_steps(x_dec, h0, c0, Wd, Ud, bd, Wo, bo, T_dec, teacher_forcing,
     hT = torch.empty(B, H, device=dev)
     cT = torch.empty(B, H, device=dev)
     io = _lib.LstmIO(None, ptr(x_dec), ptr(_f32c(extra)), ptr(_f32c(h0)), ptr(_f32c(c0)), ptr(y), ptr(hT),
-                     ptr(cT), _lib.LstmSaved(), _lib.LstmSaved())
+                     ptr(cT), _lib.LstmSaved(), _lib.LstmSaved(), None)
     _lib.check(lib.fov_lstm_seq2seq_fwd(C.byref(cfg), C.byref(w), C.byref(io), _stream()), "lstm_decode_steps")
     return y, hT, cT
 

@@ -380,3 +380,102 @@ def test_optimiser_device_divisor():
                 ops.rmsprop_step(pa, g * 37.0, sa[0], grad_div=div)
                 ops.rmsprop_step(pb, g, sb[0])
         assert torch.allclose(pa, pb, rtol=0, atol=2e-6), kind
+
+
+# ------------------------------------------------------------------ time-batched input projection (TMA-fed tcgen05 GEMM)
+
+@pytest.fixture
+def lstm_switches():
+    """fov_debug_lstm_tc / fov_debug_lstm_xproj (include/fov_debug.h), restored afterwards."""
+    from longterm360fov_b200 import _lib
+    lib = _lib.load()
+    yield lib
+    lib.fov_debug_lstm_tc(0)
+    lib.fov_debug_lstm_xproj(0)
+
+
+@pytest.mark.parametrize("B", [1, 130, 700])
+@pytest.mark.parametrize("tf", [True, False])
+def test_lstm_xproj_wide_encoder_forward(B, tf, lstm_switches):
+    """FoV_seq2seq's 90-wide raw encoder input (mycode/FoV_seq2seq.py:82-86) on tensor cores: ONE TMA-fed GEMM
+    computes x_t . W for all 10 encoder steps, the persistent recurrent kernel adds it in its gate epilogue.
+    Two launches in total; against the float64 oracle and the fp32 kernel; ragged batches (B = 1, 130, 700)."""
+    fov = _cuda()
+    lib = lstm_switches
+    rng = np.random.default_rng(B + 3)
+    w = _perturb(kn.init_fov_seq2seq(seed=2, num_encoder_tokens=90), 3)
+    enc = rng.uniform(-1, 1, (B, 10, 90)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 10 if tf else 1, 6)).astype(np.float32)
+    ref = kn.fov_seq2seq_forward({k: v.astype(np.float64) for k, v in w.items()}, enc.astype(np.float64),
+                                 dec.astype(np.float64), teacher_forcing=tf)
+    m = fov.fov_seq2seq(teacher_forcing=tf, weights=w)
+    lib.fov_debug_lstm_tc(1 if B < 512 else 0)                 # from 512 sequences the dispatcher picks it itself
+    n0 = lib.fov_launch_count()
+    got = m.predict([enc, dec], batch_size=B)
+    assert lib.fov_launch_count() == n0 + 2                    # projection GEMM + ONE persistent recurrence
+    assert np.abs(got - ref).max() < 2e-5
+    lib.fov_debug_lstm_tc(-1)
+    fp32 = m.predict([enc, dec], batch_size=B)
+    assert np.abs(got - fp32).max() < 2e-5
+    lib.fov_debug_lstm_tc(1)
+    m.set_compute("bf16")
+    assert np.abs(m.predict([enc, dec], batch_size=B) - ref).max() < BF16_ATOL
+    m.set_compute("bf16x3")
+    assert np.abs(m.predict([enc, dec], batch_size=B) - ref).max() < 2e-5
+    # encoder_model alone (T_dec = 0) takes the same path
+    m.set_compute("bf16x2")
+    h, c = m.encoder_model.predict(enc)
+    lib.fov_debug_lstm_tc(-1)
+    h0, c0 = m.encoder_model.predict(enc)
+    assert np.abs(h - h0).max() < 2e-5 and np.abs(c - c0).max() < 2e-5
+
+
+def test_lstm_xproj_forced_on_narrow_inputs(lstm_switches):
+    """fov_debug_lstm_xproj(1): every teacher-forced phase goes through the time-batched projection, also the 6-wide
+    ones that normally ride in the per-step GEMM: encoder AND decoder projected (3 launches), same results."""
+    fov = _cuda()
+    lib = lstm_switches
+    rng = np.random.default_rng(8)
+    B = 333
+    w = _perturb(kn.init_fov_seq2seq(seed=2, num_encoder_tokens=6), 3)
+    enc = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    ref = kn.fov_seq2seq_forward({k: v.astype(np.float64) for k, v in w.items()}, enc.astype(np.float64),
+                                 dec.astype(np.float64), teacher_forcing=True)
+    m = fov.fov_seq2seq_mu_var(teacher_forcing=True, weights=w)
+    lib.fov_debug_lstm_tc(1)
+    lib.fov_debug_lstm_xproj(1)
+    n0 = lib.fov_launch_count()
+    got = m.predict([enc, dec], batch_size=B)
+    assert lib.fov_launch_count() == n0 + 3
+    assert np.abs(got - ref).max() < 2e-5
+    lib.fov_debug_lstm_xproj(-1)
+    n0 = lib.fov_launch_count()
+    fused = m.predict([enc, dec], batch_size=B)
+    assert lib.fov_launch_count() == n0 + 1
+    assert np.abs(got - fused).max() < 2e-5
+
+
+@pytest.mark.parametrize("tf,B", [(True, 640), (False, 150)])
+def test_m1_training_through_xproj(tf, B, lstm_switches):
+    """Training: the projection kernel also writes the x part of the saved [h | x | 0] rows; loss and every
+    gradient of FoV_seq2seq against the float64 oracle."""
+    fov = _cuda()
+    lib = lstm_switches
+    rng = np.random.default_rng(13)
+    w = _perturb(kn.init_fov_seq2seq(seed=4, num_encoder_tokens=90), 5, 0.05)
+    enc = rng.uniform(-1, 1, (B, 10, 90)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 10 if tf else 1, 6)).astype(np.float32)
+    tgt = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    m = fov.fov_seq2seq(teacher_forcing=tf, weights=w).compile("Adam", "mean_squared_error")
+    if B < 512:
+        lib.fov_debug_lstm_tc(1)
+    xs, ys = m._to_dev([enc, dec]), m._to_dev([tgt])
+    m.gflat.zero_()
+    loss = m._loss(m._forward(xs, True), ys)
+    loss.backward()
+    l_ref, _, g_ref = kt.loss_and_grads(lambda ww, a, b: kt.fov_seq2seq_forward(ww, a, b, teacher_forcing=tf),
+                                        kt.to_torch(w), [t64(enc), t64(dec)], [t64(tgt)], [kt.mse])
+    assert abs(loss.item() - l_ref.item()) < 1e-5
+    for k in m.weight_order:
+        _grad_close(m.grads[k].cpu().numpy(), g_ref[k].numpy(), k)
