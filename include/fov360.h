@@ -176,6 +176,13 @@ int fov_conv2d_bwd_data_tc(const fov_conv_cfg* cfg, const float* dy, const float
 /* gw += x^T (*) dy ; gbias += colsum(dy): pixel reduction on tensor cores, split across CTAs */
 int fov_conv2d_bwd_weight_tc(const fov_conv_cfg* cfg, const float* x, const float* dy, float* gw,
                              float* gbias, int math, void* stream);
+/* Same with a caller-owned workspace of fov_conv_wgrad_ws_bytes() bytes (0: this shape does not use one): wide
+ * k x k convolutions (the 56 -> 512 -> 1024 -> 30 heads of mycode/convlstm_seq2seq.py:175-181) then convert both
+ * operands ONCE into bf16 term planes in a zero-padded frame and run a TMA-fed (cp.async.bulk.tensor) tcgen05
+ * GEMM over them; other shapes fall through to fov_conv2d_bwd_weight_tc. */
+size_t fov_conv_wgrad_ws_bytes(const fov_conv_cfg* cfg, int math);
+int fov_conv2d_bwd_weight_tc_ws(const fov_conv_cfg* cfg, const float* x, const float* dy, float* gw,
+                                float* gbias, void* ws, int math, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * ConvLSTM2D layer over a whole sequence (return_sequences=True, return_state).

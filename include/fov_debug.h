@@ -36,6 +36,8 @@ void fov_debug_seq_bwd_nostack(int on);
 /* worker warps per image group of the persistent ConvLSTM / fc-LSTM forward (0 = default) */
 void fov_debug_seq_wpg(int wpg);
 void fov_debug_lstm_tc_wpg(int wpg);
+/* TMA-fed weight gradient of wide k x k convolutions (default 1) or the general gather kernel (0) */
+void fov_debug_wgrad_planes(int enable);
 /* general weight gradient: force the 128-wide M tile / the narrow path (bring-up) */
 void fov_debug_wgrad_single_m(int on);
 void fov_debug_wgrad_narrow(int on);

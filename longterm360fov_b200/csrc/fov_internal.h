@@ -131,6 +131,9 @@ struct TcWgrad {
   float* gbias;    // may be NULL
 };
 int tc_wgrad_run(const TcWgrad& c, cudaStream_t st);
+// TMA-fed form for wide k x k convolutions (wgrad_planes_tc.cu): both operands converted once into bf16 planes
+size_t tc_wgrad_planes_ws_bytes(const TcWgrad& c);
+int tc_wgrad_planes_run(const TcWgrad& c, void* ws, cudaStream_t st);
 
 // Fused ConvLSTM weight gradient (wgrad_rows_tc.cu): gK, gR and gb of a layer in one launch, taps as descriptor
 // offsets (no gather).  dZ is the dense (B,T,HW,Cout) gate-gradient buffer; segment s pairs image (b, t + t_shift)

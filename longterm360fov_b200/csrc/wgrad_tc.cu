@@ -476,6 +476,37 @@ int tc_wgrad_run(const TcWgrad& c, cudaStream_t st) {
   return launch<3, false, 64, 1>(p, grid, smem, st);
 }
 
+namespace {
+TcWgrad wgrad_from_cfg(const fov_conv_cfg* cfg, const float* x, const float* dy, float* gw, float* gbias, int math) {
+  TcWgrad c{};
+  c.x = x; c.x_outer = cfg->x_img_stride; c.x_inner = 0; c.x_pix_stride = cfg->x_pix_stride; c.Cin = cfg->Cin;
+  c.kh = cfg->kh; c.kw = cfg->kw; c.dil_h = cfg->dil_h; c.dil_w = cfg->dil_w; c.pad_h = cfg->pad_h; c.pad_w = cfg->pad_w;
+  c.dy = dy; c.dy_outer = cfg->y_img_stride; c.dy_inner = 0; c.dy_pix_stride = cfg->y_pix_stride; c.Cout = cfg->Cout;
+  c.N_img = cfg->N; c.T_inner = 1; c.H = cfg->H; c.W = cfg->W;
+  c.math = math; c.gw = gw; c.gbias = gbias;
+  return c;
+}
+}  // namespace
+
+extern "C" size_t fov_conv_wgrad_ws_bytes(const fov_conv_cfg* cfg, int math) {
+  if (!cfg || math < 1 || math > 3 || cfg->N <= 0 || cfg->H <= 0 || cfg->W <= 0 || cfg->Cin <= 0 || cfg->Cout <= 0) return 0;
+  float dummy = 0.0f;
+  return tc_wgrad_planes_ws_bytes(wgrad_from_cfg(cfg, &dummy, &dummy, &dummy, nullptr, math));
+}
+
+// with a workspace of fov_conv_wgrad_ws_bytes() bytes: wide k x k convolutions take the TMA-fed kernel of
+// wgrad_planes_tc.cu (operands converted once into bf16 planes); everything else is fov_conv2d_bwd_weight_tc
+extern "C" int fov_conv2d_bwd_weight_tc_ws(const fov_conv_cfg* cfg, const float* x, const float* dy, float* gw,
+                                           float* gbias, void* ws, int math, void* stream) {
+  FOV_CHECK_ARG(cfg != nullptr, "cfg is NULL");
+  if (ws && gw && x && dy && fov_conv_wgrad_ws_bytes(cfg, math) > 0) {
+    int rc = tc_wgrad_planes_run(wgrad_from_cfg(cfg, x, dy, gw, gbias, math), ws, (cudaStream_t)stream);
+    if (rc || !gbias || (cfg->Cout + 63) / 64 * 64 <= 2048) return rc;
+    return fov_conv2d_bwd_weight(cfg, x, dy, nullptr, gbias, stream);      // very wide dY: separate column-sum kernel
+  }
+  return fov_conv2d_bwd_weight_tc(cfg, x, dy, gw, gbias, math, stream);
+}
+
 extern "C" int fov_conv2d_bwd_weight_tc(const fov_conv_cfg* cfg, const float* x, const float* dy, float* gw,
                                         float* gbias, int math, void* stream) {
   FOV_CHECK_ARG(cfg != nullptr, "cfg is NULL");

@@ -275,8 +275,10 @@ class Conv2DFn(torch.autograd.Function):
             _lib.check(lib.fov_conv2d_bwd_weight(C.byref(cfg), ptr(x), ptr(dpre), ptr(gw), ptr(gb), st),
                        "fov_conv2d_bwd_weight")
         else:
-            _lib.check(lib.fov_conv2d_bwd_weight_tc(C.byref(cfg), ptr(x), ptr(dpre), ptr(gw), ptr(gb), math, st),
-                       "fov_conv2d_bwd_weight_tc")
+            nws = lib.fov_conv_wgrad_ws_bytes(C.byref(cfg), math)       # > 0: wide k x k conv, TMA-fed plane kernel
+            wws = _ws(nws, x.device) if nws else None
+            _lib.check(lib.fov_conv2d_bwd_weight_tc_ws(C.byref(cfg), ptr(x), ptr(dpre), ptr(gw), ptr(gb), ptr(wws), math,
+                                                       st), "fov_conv2d_bwd_weight_tc_ws")
         dx = None
         if ctx.need_dx:
             dx = torch.empty_like(x)

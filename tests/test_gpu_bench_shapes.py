@@ -479,3 +479,59 @@ def test_m1_training_through_xproj(tf, B, lstm_switches):
     assert abs(loss.item() - l_ref.item()) < 1e-5
     for k in m.weight_order:
         _grad_close(m.grads[k].cpu().numpy(), g_ref[k].numpy(), k)
+
+
+# ------------------------------------------------------------------ TMA-fed weight gradient of wide k x k convolutions
+
+PLANE_CASES = [
+    # N,H,W,Cin,Cout,kh,kw
+    (8, 36, 18, 56, 160, 5, 5),       # head conv 0 shape family: Cin padded to 64, a ragged last output-channel block
+    (8, 36, 18, 64, 30, 5, 5),        # head conv 2: 30 output channels (one 64-wide dY group, duplicated lanes ignored)
+    (7, 30, 22, 96, 64, 3, 3),        # 3x3: three taps per kernel row in one MMA
+    (6, 30, 24, 32, 72, 2, 4),        # even kernel: asymmetric TF 'same' padding
+    (7, 36, 18, 128, 256, 5, 5),      # two x channel groups, two output blocks, several pixel splits (the 512 -> 1024 family)
+]
+
+
+@pytest.mark.parametrize("mode", ["bf16x2", "bf16x3", "bf16"])
+@pytest.mark.parametrize("case", PLANE_CASES)
+def test_conv_weight_gradient_tma_planes(case, mode):
+    """fov_conv2d_bwd_weight_tc_ws on shapes that take wgrad_planes_tc.cu (operands converted once into bf16 planes in
+    a zero-padded frame, tiles by cp.async.bulk.tensor, taps of a kernel row as overlapping N groups): gw and gb against
+    the float64 oracle, and against the general gather kernel; gw is ACCUMULATED (+=) as the ABI promises."""
+    fov = _cuda()
+    import ctypes as C
+    from longterm360fov_b200 import ops, _lib
+    lib = _lib.load()
+    ops.set_math(mode)
+    N, H, W, Cin, Cout, kh, kw = case
+    rng = np.random.default_rng(Cin * 7 + Cout)
+    x = rng.normal(size=(N, H, W, Cin)).astype(np.float32)
+    k = (rng.normal(size=(kh, kw, Cin, Cout)) / np.sqrt(kh * kw * Cin)).astype(np.float32)
+    b = rng.normal(size=Cout).astype(np.float32) * 0.1
+    gy = rng.normal(size=(N, H, W, Cout)).astype(np.float32)
+    cfg = ops._conv_cfg(N, H, W, Cin, Cout, kh, kw, (1, 1), None, 0.0, H * W * Cin, Cin, H * W * Cout, Cout)
+    assert lib.fov_conv_wgrad_ws_bytes(C.byref(cfg), _lib.MATH[mode]) > 0, "case must take the plane kernel"
+    xt = torch.tensor(x, device="cuda", requires_grad=True)
+    kt_ = torch.tensor(k, device="cuda", requires_grad=True)
+    bt = torch.tensor(b, device="cuda", requires_grad=True)
+    gw0 = torch.tensor(rng.normal(size=k.shape).astype(np.float32), device="cuda")
+    gw, gb = gw0.clone(), torch.zeros_like(bt)
+    y = ops.conv2d(xt, kt_, bt, None, (1, 1), (gw, gb), True)
+    y.backward(torch.tensor(gy, device="cuda"))
+    x64 = torch.tensor(x, dtype=torch.float64)
+    k64 = torch.tensor(k, dtype=torch.float64, requires_grad=True)
+    b64 = torch.tensor(b, dtype=torch.float64, requires_grad=True)
+    kt.conv2d(x64, k64, b64, None, (1, 1)).backward(torch.tensor(gy, dtype=torch.float64))
+    rtol = 2e-2 if mode == "bf16" else 2e-4
+    _grad_close((gw - gw0).cpu().numpy(), k64.grad.numpy(), "dw", rtol=rtol)
+    _grad_close(gb.cpu().numpy(), b64.grad.numpy(), "db", rtol=1e-4)
+    # the general kernel on the same operands
+    lib.fov_debug_wgrad_planes(0)
+    try:
+        assert lib.fov_conv_wgrad_ws_bytes(C.byref(cfg), _lib.MATH[mode]) == 0
+        gw2, gb2 = torch.zeros_like(kt_), torch.zeros_like(bt)
+        ops.conv2d(xt, kt_, bt, None, (1, 1), (gw2, gb2), True).backward(torch.tensor(gy, device="cuda"))
+    finally:
+        lib.fov_debug_wgrad_planes(1)
+    _grad_close((gw - gw0).cpu().numpy(), gw2.cpu().numpy(), "dw vs gather kernel", rtol=rtol)
