@@ -173,6 +173,14 @@ int fov_conv2d_fwd_tc(const fov_conv_cfg* cfg, const float* x, const float* w, c
                       float* y, void* ws, int math, void* stream);
 int fov_conv2d_bwd_data_tc(const fov_conv_cfg* cfg, const float* dy, const float* w, float* dx,
                            void* ws, int math, void* stream);
+/* The same two calls with the weight repack hoisted out: fov_conv_tc_pack fills ws (fov_conv_tc_ws_bytes bytes) for
+ * the forward (bwd_data = 0) or the backward-data (1) convolution of cfg; the *_packed calls only read it.  For callers
+ * that run one layer many times between weight updates (the 10 decoder steps of mycode/convlstm_seq2seq.py:211-238). */
+int fov_conv_tc_pack(const fov_conv_cfg* cfg, const float* w, void* ws, int math, int bwd_data, void* stream);
+int fov_conv2d_fwd_tc_packed(const fov_conv_cfg* cfg, const float* x, const float* bias, float* y,
+                             const void* ws, int math, void* stream);
+int fov_conv2d_bwd_data_tc_packed(const fov_conv_cfg* cfg, const float* dy, float* dx, const void* ws,
+                                  int math, void* stream);
 /* gw += x^T (*) dy ; gbias += colsum(dy): pixel reduction on tensor cores, split across CTAs */
 int fov_conv2d_bwd_weight_tc(const fov_conv_cfg* cfg, const float* x, const float* dy, float* gw,
                              float* gbias, int math, void* stream);

@@ -36,6 +36,9 @@ void fov_debug_seq_bwd_nostack(int on);
 /* worker warps per image group of the persistent ConvLSTM / fc-LSTM forward (0 = default) */
 void fov_debug_seq_wpg(int wpg);
 void fov_debug_lstm_tc_wpg(int wpg);
+/* wide single-term (bf16) convolutions with two 128-row accumulator tiles per CTA: 0 never, 1 when the grid still
+ * fills the machine (default), 2 whenever the tile fits */
+void fov_debug_conv_mt2(int mode);
 /* TMA-fed weight gradient of wide k x k convolutions (default 1) or the general gather kernel (0) */
 void fov_debug_wgrad_planes(int enable);
 /* general weight gradient: force the 128-wide M tile / the narrow path (bring-up) */

@@ -100,6 +100,9 @@ SYMBOLS = {
     "fov_conv_tc_ws_bytes": (C.c_size_t, [C.POINTER(ConvCfg), _I, _I]),
     "fov_conv2d_fwd_tc": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P, _I, _P]),
     "fov_conv2d_bwd_data_tc": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _I, _P]),
+    "fov_conv_tc_pack": (_I, [C.POINTER(ConvCfg), _P, _P, _I, _I, _P]),
+    "fov_conv2d_fwd_tc_packed": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _I, _P]),
+    "fov_conv2d_bwd_data_tc_packed": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _I, _P]),
     "fov_conv2d_bwd_weight_tc": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _I, _P]),
     "fov_conv_wgrad_ws_bytes": (C.c_size_t, [C.POINTER(ConvCfg), _I]),
     "fov_conv2d_bwd_weight_tc_ws": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P, _I, _P]),

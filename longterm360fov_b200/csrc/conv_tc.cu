@@ -41,7 +41,8 @@ constexpr int kProducers = 256;
 constexpr int kEpiWarps = 8;                   // warps 0-7: producers, then epilogue (warp w: TMEM lanes 32*(w&3)..)
 constexpr int kThreads = 320;                  // + weight-copy warp (8) + MMA warp (9)
 constexpr int kMaxBStages = 4;
-constexpr int kMaxRegionRows = 384;            // 128 D rows + halo
+constexpr int kMaxRegionRows = 384;            // 128 (or 2 x 128) D rows + halo
+constexpr int kMaxMT = 2;                      // M tiles (128 frame positions each) per CTA
 constexpr int kMaxTaps = 64;
 constexpr int CONV_RS = 36;                    // conv epilogue staging row stride (floats)
 enum { O_OUT = 0, O_H = 1, O_GATES = 2, O_CPREV = 3, O_DENSE = 4 };
@@ -57,7 +58,7 @@ struct DevSeg {
 
 struct DevParams {
   DevSeg seg[2];
-  int nseg, mode_b, dbg, n_tiles, pipe;
+  int nseg, mode_b, dbg, n_tiles, pipe, MT;
   int H, W, Hp, Wp, PLh, PLw, HpWp, T_inner, N_img, total_pos;
   int K_total, KB, Cout, BLOCK_N, b_stages, tmem_cols, b_off, b_stage_bytes, data_bytes;
   const uint8_t* wpk;
@@ -79,8 +80,8 @@ struct DevParams {
 // shared-memory bookkeeping placed after the data area (activation regions, weight ring / staging)
 struct Book {
   int rp[2][kMaxRegionRows];            // per region row: element offset of that position's pixel, -1 = zero row
-  int off_o[5][BLOCK_M];                // epilogue element offsets of the D rows (image + pixel), see O_*
-  int valid[BLOCK_M];                   // D row is a real pixel
+  int off_o[5][kMaxMT * BLOCK_M];       // epilogue element offsets of the D rows (image + pixel), see O_*
+  int valid[kMaxMT * BLOCK_M];          // D row is a real pixel
   float bias_s[256];                    // LSTM epilogue: the 4F gate biases
   int tapshift[2][kMaxTaps];            // row offset of every tap relative to the region start
   uint64_t b_full[kMaxBStages], b_empty[kMaxBStages], a_full[2], a_empty[2], tmem_full;
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
   // stage come from L2 after the first touch (backward-data of the wide dense layers has 15 n tiles per M tile)
   const int m_tile = (int)(blockIdx.x / (unsigned)p.n_tiles);
   const int n_tile = (int)(blockIdx.x - (unsigned)m_tile * (unsigned)p.n_tiles);
-  const int L0 = m_tile * BLOCK_M;              // first frame position of this tile
+  const int MT = p.MT;                          // 128-row accumulator tiles of this CTA (2: wide layers, weights read once per 256 rows)
+  const int L0 = m_tile * BLOCK_M * MT;         // first frame position of this tile
   const int n0 = n_tile * p.BLOCK_N;
   const int S = p.b_stages;
   const uint32_t b_tile_bytes = (uint32_t)p.BLOCK_N * 128u;
@@ -123,8 +125,8 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
   }
 
   // ---------------- setup: frame position -> pixel tables ----------------
-  if (tid < BLOCK_M) {
-    const int L = L0 + tid;
+  for (int dr = tid; dr < BLOCK_M * MT; dr += kThreads) {
+    const int L = L0 + dr;
     int ok = 0;
     if (L < p.total_pos) {
       const int n = L / p.HpWp, rem = L - n * p.HpWp;
@@ -134,17 +136,17 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
         ok = 1;
         const int pix = y * p.W + x;
         if (EPI == TC_EPI_CONV) {
-          bk->off_o[O_OUT][tid] = (int)(img_off(n, p.T_inner, p.y_outer, p.y_inner) + (long long)pix * p.y_pix_stride);
+          bk->off_o[O_OUT][dr] = (int)(img_off(n, p.T_inner, p.y_outer, p.y_inner) + (long long)pix * p.y_pix_stride);
         } else {
-          bk->off_o[O_OUT][tid] = (int)(img_off(n, p.T_inner, p.c_outer, p.c_inner) + (long long)pix * p.F);
-          bk->off_o[O_H][tid] = (int)(img_off(n, p.T_inner, p.h_outer, p.h_inner) + (long long)pix * p.h_pix_stride);
-          bk->off_o[O_GATES][tid] = (int)(img_off(n, p.T_inner, p.g_outer, p.g_inner) + (long long)pix * 4 * p.F);
-          bk->off_o[O_CPREV][tid] = (int)(img_off(n, p.T_inner, p.cp_outer, p.cp_inner) + (long long)pix * p.F);
-          bk->off_o[O_DENSE][tid] = (n * p.H * p.W + pix) * p.F;
+          bk->off_o[O_OUT][dr] = (int)(img_off(n, p.T_inner, p.c_outer, p.c_inner) + (long long)pix * p.F);
+          bk->off_o[O_H][dr] = (int)(img_off(n, p.T_inner, p.h_outer, p.h_inner) + (long long)pix * p.h_pix_stride);
+          bk->off_o[O_GATES][dr] = (int)(img_off(n, p.T_inner, p.g_outer, p.g_inner) + (long long)pix * 4 * p.F);
+          bk->off_o[O_CPREV][dr] = (int)(img_off(n, p.T_inner, p.cp_outer, p.cp_inner) + (long long)pix * p.F);
+          bk->off_o[O_DENSE][dr] = (n * p.H * p.W + pix) * p.F;
         }
       }
     }
-    bk->valid[tid] = ok;
+    bk->valid[dr] = ok;
   }
   for (int s = 0; s < p.nseg; ++s) {
     const DevSeg& sg = p.seg[s];
@@ -333,14 +335,17 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
       const uint32_t idesc = idesc_bf16_f32(BLOCK_M, p.BLOCK_N, 0, 0);
       uint32_t first = 1;
       // one 16-wide K step: A = staged region of (seg, buffer) shifted by the tap, B = weight ring slot
+      const uint32_t mt_rows = (uint32_t)BLOCK_M * (uint32_t)p.seg[0].row_bytes;     // second accumulator tile: 128 rows further
       auto kstep = [&](uint32_t a_hi, uint32_t a_addr, uint32_t a_term, uint32_t b_addr) {
 #pragma unroll
         for (int sum = NS - 1; sum >= 0; --sum) {     // smallest cross terms first, hi*hi last
 #pragma unroll
           for (int sa = 0; sa <= sum; ++sa) {
             const int sb = sum - sa;
-            umma_bf16(tmem_d, desc_at(a_hi, a_addr + sa * a_term), desc_at(kDescHi128, b_addr + sb * b_tile_bytes), idesc,
-                      first ^ 1u);
+            const uint64_t bd = desc_at(kDescHi128, b_addr + sb * b_tile_bytes);
+            umma_bf16(tmem_d, desc_at(a_hi, a_addr + sa * a_term), bd, idesc, first ^ 1u);
+            if (MT == 2)
+              umma_bf16(tmem_d + (uint32_t)p.BLOCK_N, desc_at(a_hi, a_addr + sa * a_term + mt_rows), bd, idesc, first ^ 1u);
             first = 0;
           }
         }
@@ -397,14 +402,15 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
   // all MMAs have completed when tmem_full fires, so the data area is free: the staging rows alias it.
   if (warp < kEpiWarps) {
     const int q = warp & 3, half = warp >> 2;
-    const int r0 = q * 32;
-    const uint32_t t_row = tmem_d + ((uint32_t)r0 << 16);
     float* stg = reinterpret_cast<float*>(smem) + warp * (32 * CONV_RS);     // 32 rows x 32 floats (+4 pad)
 
     if (EPI == TC_EPI_CONV) {
       mbar_wait(smem_u32(&bk->tmem_full), 0);
       tc_fence_after();
       if (dbg) g_tc_timeline[m_tile * 8 + 3] = clock64();
+      for (int mt = 0; mt < MT; ++mt) {
+      const int r0 = mt * BLOCK_M + q * 32;
+      const uint32_t t_row = tmem_d + (uint32_t)(mt * p.BLOCK_N) + ((uint32_t)(q * 32) << 16);
       for (int c0 = half * 32; c0 < p.BLOCK_N; c0 += 64) {
         float v[32];
         tmem_ld16(t_row + c0, v);
@@ -473,7 +479,10 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const DevParams p)
         }
         __syncwarp();
       }
+      }
     } else {
+      const int r0 = q * 32;
+      const uint32_t t_row = tmem_d + ((uint32_t)r0 << 16);
       // Fused ConvLSTM step.  Accumulator columns: [i | f | c~ | o], each F wide, processed 8 channels per
       // pass; the two warps of a lane quarter take alternate passes.  Row-per-thread values go through the
       // staging rows two 8-wide segments at a time and leave as coalesced float4 row segments.
@@ -657,7 +666,7 @@ struct SegPlan {
 };
 struct Plan {
   SegPlan sp[2];
-  int PLh, PLw, Hp, Wp, mode_b;
+  int PLh, PLw, Hp, Wp, mode_b, MT;
   int K_total, KB, BLOCK_N, n_tiles, NS, b_stages, b_stage_bytes, b_off, tmem_cols, data_bytes;
   long long total_pos;
   size_t smem_bytes, ws_bytes;
@@ -665,7 +674,26 @@ struct Plan {
 
 int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
+int make_plan_mt(const TcConv& c, Plan* pl, int MT);
+
+// Wide single-term convolutions (the 512 / 1024-channel heads in bf16 mode) stream their weights from L2 at
+// 64 B / cycle / SM at the tensor peak - above what L2 delivers to 148 SMs at once (~43 B / cycle / SM).  Two 128-row
+// accumulator tiles per CTA (256 frame positions, 2 x BLOCK_N TMEM columns) read every weight tile once per 256 rows.
 int make_plan(const TcConv& c, Plan* pl) {
+  if (c.epi == TC_EPI_CONV && c.nseg == 1 && c.math == 1 && c.seg[0].Cin > 64 && c.Cout >= 128 && c.no_mt2 <= 0) {
+    Plan p2;
+    if (make_plan_mt(c, &p2, 2) == FOV_OK &&
+        (c.no_mt2 < 0 || p2.total_pos >= 2LL * BLOCK_M * 2 * fov_num_sms() / p2.n_tiles)) {
+      *pl = p2;
+      return FOV_OK;
+    }
+    fov_set_error("");
+  }
+  return make_plan_mt(c, pl, 1);
+}
+
+int make_plan_mt(const TcConv& c, Plan* pl, int MT) {
+  pl->MT = MT;
   FOV_CHECK_ARG(c.nseg == 1 || c.nseg == 2, "nseg must be 1 or 2");
   FOV_CHECK_ARG(c.math >= 1 && c.math <= 3, "math must be 1..3 bf16 terms");
   FOV_CHECK_ARG(c.N_img > 0 && c.H > 0 && c.W > 0 && c.Cout > 0 && c.T_inner > 0, "bad shape");
@@ -699,7 +727,7 @@ int make_plan(const TcConv& c, Plan* pl) {
     k += sp.taps * sp.Cin_p;
     sp.minshift = -(g.pad_h * pl->Wp + g.pad_w);
     const int maxshift = ((g.kh - 1) * g.dil_h - g.pad_h) * pl->Wp + ((g.kw - 1) * g.dil_w - g.pad_w);
-    sp.R = (BLOCK_M + maxshift - sp.minshift + 7) / 8 * 8;
+    sp.R = (BLOCK_M * MT + maxshift - sp.minshift + 7) / 8 * 8;
     FOV_CHECK_ARG(sp.R <= kMaxRegionRows, "convolution halo too large for the shifted-tap kernel");
     sp.nbuf = sp.nch > 1 ? 2 : 1;
     any_multi |= sp.nch > 1;
@@ -747,7 +775,8 @@ int make_plan(const TcConv& c, Plan* pl) {
   }
   // several CTAs per SM hide the load latency of short K loops: do not take more ring slots than needed
   if (pl->KB <= 6 && pl->b_stages > 2) pl->b_stages = 2;
-  pl->tmem_cols = (int)tmem_cols_for(pl->BLOCK_N);
+  FOV_CHECK_ARG(MT * pl->BLOCK_N <= 512, "accumulator tiles exceed tensor memory");
+  pl->tmem_cols = (int)tmem_cols_for(MT * pl->BLOCK_N);
   pl->b_off = region_bytes;
   pl->data_bytes = region_bytes + pl->b_stages * pl->b_stage_bytes;
   if (pl->data_bytes < staging) pl->data_bytes = staging;
@@ -780,7 +809,7 @@ int launch_conv(const DevParams& dp, const Plan& pl, cudaStream_t st) {
     }
     configured.mark();
   }
-  const long long m_tiles = (pl.total_pos + BLOCK_M - 1) / BLOCK_M;
+  const long long m_tiles = (pl.total_pos + BLOCK_M * pl.MT - 1) / (BLOCK_M * pl.MT);
   if (m_tiles * pl.n_tiles >= (1LL << 31)) { fov_set_error("tc_conv: grid too large"); return FOV_ERR_ARG; }
   dim3 grid((unsigned)(m_tiles * pl.n_tiles));
   tc_conv_kernel<NS, EPI><<<grid, kThreads, pl.smem_bytes, st>>>(dp);
@@ -791,6 +820,10 @@ int launch_conv(const DevParams& dp, const Plan& pl, cudaStream_t st) {
 }  // namespace
 
 static int g_tc_debug = 0;
+static int g_conv_no_mt2 = 0;
+// diagnostics / A-B: two accumulator tiles per CTA in the wide single-term convolutions: 0 = never, 1 = when the grid
+// still fills the machine (default), 2 = whenever the tile fits (small test shapes)
+extern "C" void fov_debug_conv_mt2(int mode) { g_conv_no_mt2 = mode == 0 ? 1 : (mode == 2 ? -1 : 0); }
 // diagnostics (not part of include/fov360.h): per-CTA phase timestamps of the next conv launches
 extern "C" void fov_debug_timeline_enable(int on) { g_tc_debug = on; }
 extern "C" int fov_debug_timeline_read(unsigned long long* out, int n_words) {
@@ -863,7 +896,7 @@ int tc_conv_run(const TcConv& c, cudaStream_t st) {
   if (!c.prepacked && (rc = tc_conv_pack(c, st))) return rc;
 
   DevParams dp{};
-  dp.nseg = c.nseg; dp.mode_b = pl.mode_b; dp.dbg = g_tc_debug; dp.n_tiles = pl.n_tiles;
+  dp.nseg = c.nseg; dp.mode_b = pl.mode_b; dp.dbg = g_tc_debug; dp.n_tiles = pl.n_tiles; dp.MT = pl.MT;
   for (int s = 0; s < c.nseg; ++s) {
     const TcSeg& g = c.seg[s];
     const SegPlan& sp = pl.sp[s];
@@ -946,6 +979,7 @@ int conv_from_cfg(const fov_conv_cfg* cfg, int math, TcConv* c) {
   c->N_img = cfg->N; c->T_inner = 1; c->H = cfg->H; c->W = cfg->W;
   c->math = math;
   c->epi = TC_EPI_CONV;
+  c->no_mt2 = g_conv_no_mt2;
   return FOV_OK;
 }
 void fwd_seg(const fov_conv_cfg* cfg, TcConv* c) {
@@ -983,6 +1017,47 @@ extern "C" int fov_conv2d_fwd_tc(const fov_conv_cfg* cfg, const float* x, const 
   c.ws = ws;
   c.bias = bias; c.y = y; c.y_outer = cfg->y_img_stride; c.y_inner = 0; c.y_pix_stride = cfg->y_pix_stride;
   c.act = cfg->act; c.beta = cfg->beta;
+  return tc_conv_run(c, (cudaStream_t)stream);
+}
+
+// Weights packed once, reused by several calls (the 10 decoder steps of convlstm_seq2seq run the same three head
+// convolutions: mycode/convlstm_seq2seq.py:211-238): fov_conv_tc_pack fills ws, the *_packed calls read it.
+extern "C" int fov_conv_tc_pack(const fov_conv_cfg* cfg, const float* w, void* ws, int math, int bwd_data, void* stream) {
+  TcConv c;
+  int rc = conv_from_cfg(cfg, math, &c);
+  if (rc) return rc;
+  FOV_CHECK_ARG(w && ws, "NULL pointer");
+  if (bwd_data) bwd_seg(cfg, &c); else fwd_seg(cfg, &c);
+  c.seg[0].w = w;
+  c.ws = ws;
+  return tc_conv_pack(c, (cudaStream_t)stream);
+}
+
+extern "C" int fov_conv2d_fwd_tc_packed(const fov_conv_cfg* cfg, const float* x, const float* bias, float* y,
+                                        const void* ws, int math, void* stream) {
+  TcConv c;
+  int rc = conv_from_cfg(cfg, math, &c);
+  if (rc) return rc;
+  FOV_CHECK_ARG(x && y && ws, "NULL pointer");
+  fwd_seg(cfg, &c);
+  c.seg[0].x = x;
+  c.ws = const_cast<void*>(ws); c.prepacked = 1;
+  c.bias = bias; c.y = y; c.y_outer = cfg->y_img_stride; c.y_inner = 0; c.y_pix_stride = cfg->y_pix_stride;
+  c.act = cfg->act; c.beta = cfg->beta;
+  return tc_conv_run(c, (cudaStream_t)stream);
+}
+
+extern "C" int fov_conv2d_bwd_data_tc_packed(const fov_conv_cfg* cfg, const float* dy, float* dx, const void* ws,
+                                             int math, void* stream) {
+  TcConv c;
+  int rc = conv_from_cfg(cfg, math, &c);
+  if (rc) return rc;
+  FOV_CHECK_ARG(dy && dx && ws, "NULL pointer");
+  bwd_seg(cfg, &c);
+  c.seg[0].x = dy;
+  c.ws = const_cast<void*>(ws); c.prepacked = 1;
+  c.bias = nullptr; c.y = dx; c.y_outer = cfg->x_img_stride; c.y_inner = 0; c.y_pix_stride = cfg->x_pix_stride;
+  c.act = FOV_ACT_LINEAR; c.beta = cfg->beta;
   return tc_conv_run(c, (cudaStream_t)stream);
 }
 

@@ -72,6 +72,7 @@ struct TcConv {
   int math;                         // bf16 terms per operand: 1 (bf16), 2 (3 MMAs), 3 (6 MMAs, ~fp32)
   void* ws;                         // packed-weight workspace, tc_conv_ws_bytes() bytes
   int prepacked;                    // 1: ws already holds the packed weights of this exact problem
+  int no_mt2;                       // two accumulator tiles per CTA: 1 never, 0 auto, -1 whenever it fits (fov_debug_conv_mt2)
   // TC_EPI_CONV epilogue: y = act(acc + bias + beta*y)
   int epi;
   const float* bias;

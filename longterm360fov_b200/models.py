@@ -769,6 +769,7 @@ class ConvLSTMSeq2Seq(Model):
         _, states = self._stack("enc", enc_in, None, training)
         x = dec_in[:, 0:1]
         outs = []
+        packs = {}          # packed head weights, valid for this pass (forward + its backward): packed once, used T_dec times
         for step in range(self.T_dec):
             cat, states = self._stack("dec", x, states, training)
             d = cat[:, 0]                                              # (B,H,W,56)
@@ -776,7 +777,7 @@ class ConvLSTMSeq2Seq(Model):
                 y = d
                 for l in range(3):
                     y = ops.conv2d(y, p["head_conv%d/kernel" % l], p["head_conv%d/bias" % l], "relu", (1, 1),
-                                   self._sinks("head_conv%d/kernel" % l, "head_conv%d/bias" % l), training)
+                                   self._sinks("head_conv%d/kernel" % l, "head_conv%d/bias" % l), training, packs)
                 y = ops.SoftmaxFn.apply(y)
                 x = y.unsqueeze(1)
             elif self.head_kind == "conv1d":

@@ -243,11 +243,12 @@ class Conv2DFn(torch.autograd.Function):
             _lib.check(lib.fov_conv2d_fwd(C.byref(cfg), ptr(x), ptr(kernel), ptr(bias), ptr(y), _stream()),
                        "fov_conv2d_fwd")
         else:
-            ws = _ws(lib.fov_conv_tc_ws_bytes(C.byref(cfg), math, 0), x.device)
-            _lib.check(lib.fov_conv2d_fwd_tc(C.byref(cfg), ptr(x), ptr(kernel), ptr(bias), ptr(y), ptr(ws),
-                                             math, _stream()), "fov_conv2d_fwd_tc")
+            ws = _packed_weights(lib, opts.get("pack_cache"), cfg, kernel, math, 0)
+            _lib.check(lib.fov_conv2d_fwd_tc_packed(C.byref(cfg), ptr(x), ptr(bias), ptr(y), ptr(ws), math, _stream()),
+                       "fov_conv2d_fwd_tc_packed")
         if opts.get("training", False):
             ctx.math = math
+            ctx.pack_cache = opts.get("pack_cache")
             ctx.cfg, ctx.sinks, ctx.act = cfg, sinks, act
             ctx.need_dx = ctx.needs_input_grad[2]
             ctx.save_for_backward(x, kernel, y)
@@ -288,15 +289,32 @@ class Conv2DFn(torch.autograd.Function):
                 _lib.check(lib.fov_conv2d_bwd_data(C.byref(cfg), ptr(dpre), ptr(kernel), ptr(dx), ptr(ws), st),
                            "fov_conv2d_bwd_data")
             else:
-                ws = _ws(lib.fov_conv_tc_ws_bytes(C.byref(cfg), math, 1), x.device)
-                _lib.check(lib.fov_conv2d_bwd_data_tc(C.byref(cfg), ptr(dpre), ptr(kernel), ptr(dx), ptr(ws),
-                                                      math, st), "fov_conv2d_bwd_data_tc")
+                ws = _packed_weights(lib, ctx.pack_cache, cfg, kernel, math, 1)
+                _lib.check(lib.fov_conv2d_bwd_data_tc_packed(C.byref(cfg), ptr(dpre), ptr(dx), ptr(ws), math, st),
+                           "fov_conv2d_bwd_data_tc_packed")
         return None, None, dx, None, None
 
 
-def conv2d(x, kernel, bias, activation=None, dilation=(1, 1), sinks=None, training=False):
-    return Conv2DFn.apply({"activation": activation, "dilation": dilation, "training": training},
-                          sinks, x, kernel, bias)
+def _packed_weights(lib, cache, cfg, kernel, math, bwd_data):
+    """bf16-term image of a layer's weights for the tensor-core conv kernels (fov_conv_tc_pack).  ``cache``: optional
+    dict owned by the caller and valid while the weights do not change (one forward + backward pass): layers that run
+    several times per pass - the head convolutions of the 10 decoder steps - are packed once."""
+    key = None
+    if cache is not None:
+        key = (kernel.data_ptr(), tuple(kernel.shape), int(math), int(bwd_data), cfg.H, cfg.W, cfg.N)
+        ws = cache.get(key)
+        if ws is not None:
+            return ws
+    ws = _ws(lib.fov_conv_tc_ws_bytes(C.byref(cfg), math, bwd_data), kernel.device)
+    _lib.check(lib.fov_conv_tc_pack(C.byref(cfg), ptr(kernel), ptr(ws), math, bwd_data, _stream()), "fov_conv_tc_pack")
+    if key is not None:
+        cache[key] = ws
+    return ws
+
+
+def conv2d(x, kernel, bias, activation=None, dilation=(1, 1), sinks=None, training=False, pack_cache=None):
+    return Conv2DFn.apply({"activation": activation, "dilation": dilation, "training": training,
+                           "pack_cache": pack_cache}, sinks, x, kernel, bias)
 
 
 def dense(x, kernel, bias, activation=None, sinks=None, training=False):

@@ -535,3 +535,44 @@ def test_conv_weight_gradient_tma_planes(case, mode):
     finally:
         lib.fov_debug_wgrad_planes(1)
     _grad_close((gw - gw0).cpu().numpy(), gw2.cpu().numpy(), "dw vs gather kernel", rtol=rtol)
+
+
+# ------------------------------------------------------------------ 256-row CTA tiles of the wide bf16 convolutions
+
+@pytest.mark.parametrize("case", [(6, 36, 18, 128, 256, 5, 5), (5, 30, 20, 192, 160, 3, 3), (700, 1, 1, 256, 128, 1, 1)])
+def test_conv_two_accumulator_tiles_per_cta(case):
+    """fov_debug_conv_mt2(2): the single-term (bf16) convolution with two 128-row accumulator tiles per CTA (weights read
+    from L2 once per 256 frame positions) - forward and backward-data bit-identical to the one-tile form (same MMA
+    order per accumulator), and inside the stated bf16 tolerance of the float64 oracle."""
+    fov = _cuda()
+    from longterm360fov_b200 import ops, _lib
+    lib = _lib.load()
+    ops.set_math("bf16")
+    N, H, W, Cin, Cout, kh, kw = case
+    rng = np.random.default_rng(Cin + Cout)
+    x = rng.normal(size=(N, H, W, Cin)).astype(np.float32)
+    k = (rng.normal(size=(kh, kw, Cin, Cout)) / np.sqrt(kh * kw * Cin)).astype(np.float32)
+    b = rng.normal(size=Cout).astype(np.float32) * 0.1
+    gy = rng.normal(size=(N, H, W, Cout)).astype(np.float32)
+
+    def run(mode):
+        lib.fov_debug_conv_mt2(mode)
+        try:
+            xt = torch.tensor(x, device="cuda", requires_grad=True)
+            kt_ = torch.tensor(k, device="cuda", requires_grad=True)
+            bt = torch.tensor(b, device="cuda", requires_grad=True)
+            gw, gb = torch.zeros_like(kt_), torch.zeros_like(bt)
+            y = ops.conv2d(xt, kt_, bt, None, (1, 1), (gw, gb), True)      # linear: no relu mask flips at bf16 precision
+            y.backward(torch.tensor(gy, device="cuda"))
+            return y.detach().cpu().numpy(), xt.grad.cpu().numpy()
+        finally:
+            lib.fov_debug_conv_mt2(1)
+
+    y2, dx2 = run(2)
+    y1, dx1 = run(0)
+    assert np.array_equal(y2, y1) and np.array_equal(dx2, dx1)
+    x64 = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    yr = kt.conv2d(x64, t64(k), t64(b), None, (1, 1))
+    yr.backward(t64(gy))
+    assert np.abs(y2 - yr.detach().numpy()).max() < BF16_ATOL
+    _grad_close(dx2, x64.grad.numpy(), "dx", rtol=2e-2)
