@@ -318,6 +318,12 @@ int fov_window_stacks(int U, int S, int C, int L, int stride, int purely_testing
 /* get_whole_span (mycode/others_LSTM_span_whole.py:403-419): x (N, half) rows (half = L * everything after the
  * time axis) -> out (N, 2*half): out[i] = [x[i] ; x[i+1]], the last row is all zero. */
 int fov_whole_span(long long N, long long half, const float* x, float* out, void* stream);
+/* get_data's target / others split (mycode/utility.py:389-430) applied to the windows of one video: every viewer is the
+ * target once; for target t the others are viewers idx[t*K .. t*K+K) (the remaining viewers, padded with duplicates or
+ * truncated to K = num_user - 1 by the caller's index list).  src (U, n, row) -> out (K, N_total, row) with
+ * out[j][base_rows + t*n + w] = src[idx[t*K+j]][w]; out_j_stride = N_total * row floats.  idx is a DEVICE int32 array. */
+int fov_pick_user_gather(int T, int K, int n, long long row, const int* idx, const float* src, float* out,
+                         long long out_j_stride, long long base_rows, void* stream);
 /* One-hot FoV-centre heatmaps: xyz (rows, frames, 3) -> out (rows, 360/bin, 180/bin, frames), one 1 per frame at
  * (theta bin, phi bin) with theta, phi of mycode/dataIO.py:77-82 and the binning of mycode/utility.py:533-539,
  * _create_one_hot :546-556; frames stacked as channels as mycode/data_generator_for_heatmap.py:32,65-67 feeds them.

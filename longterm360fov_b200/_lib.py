@@ -137,6 +137,7 @@ SYMBOLS = {
     "fov_window_count": (_I, [_I, _I, _I, _I]),
     "fov_window_stacks": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "fov_whole_span": (_I, [_LL, _LL, _P, _P, _P]),
+    "fov_pick_user_gather": (_I, [_I, _I, _I, _LL, _P, _P, _P, _LL, _LL, _P]),
     "fov_onehot_heatmaps": (_I, [_LL, _I, _I, _P, _P, _P]),
     "fov_hit_rate": (_I, [_LL, _P, _P, _F, _F, _F, _F, _P, _P]),
 }

@@ -188,6 +188,45 @@ extern "C" int fov_whole_span(long long N, long long half, const float* x, float
   return FOV_OK;
 }
 
+// get_data's target / others split (mycode/utility.py:389-430) on windowed tensors: every viewer of a video is the target
+// once; for target t the others are the viewers idx[t][0..K) (the rest of the video, padded with duplicates or truncated
+// to num_user - 1).  src (U, n, row) windows of one video; out[j][base + t*n + w][:] = src[idx[t*K + j]][w][:].
+template <typename V>
+__global__ void __launch_bounds__(256) pick_user_gather_kernel(int n, long long rowv, int K, const int* __restrict__ idx,
+                                                               const V* __restrict__ src, V* __restrict__ out,
+                                                               long long out_j_stride_v, long long base_rows,
+                                                               long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i % rowv;
+    long long r = i / rowv;
+    const int w = (int)(r % n); r /= n;
+    const int j = (int)(r % K);
+    const long long t = r / K;
+    const int u = __ldg(&idx[t * K + j]);
+    out[(long long)j * out_j_stride_v + (base_rows + t * n + w) * rowv + e] = __ldg(&src[((long long)u * n + w) * rowv + e]);
+  }
+}
+
+extern "C" int fov_pick_user_gather(int T, int K, int n, long long row, const int* idx, const float* src, float* out,
+                                    long long out_j_stride, long long base_rows, void* stream) {
+  FOV_CHECK_ARG(T > 0 && K > 0 && n > 0 && row > 0 && idx && src && out && out_j_stride >= 0 && base_rows >= 0,
+                "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  auto a16 = [](const void* p) { return (uintptr_t)p % 16 == 0; };
+  if (row % 4 == 0 && out_j_stride % 4 == 0 && a16(src) && a16(out)) {
+    const long long total = (long long)T * K * n * (row / 4);
+    pick_user_gather_kernel<float4><<<grid_for(total, 256), 256, 0, st>>>(
+        n, row / 4, K, idx, reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(out), out_j_stride / 4,
+        base_rows, total);
+  } else {
+    const long long total = (long long)T * K * n * row;
+    pick_user_gather_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(n, row, K, idx, src, out, out_j_stride, base_rows,
+                                                                          total);
+  }
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
+
 extern "C" int fov_onehot_heatmaps(long long rows, int frames, int bin_size, const float* xyz, float* out, void* stream) {
   FOV_CHECK_ARG(rows > 0 && rows < (1LL << 31) && frames > 0 && frames <= 4096, "bad shape");
   FOV_CHECK_ARG(bin_size > 0 && 360 % bin_size == 0 && 180 % bin_size == 0, "bin_size must divide 180");

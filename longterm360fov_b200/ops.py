@@ -793,6 +793,56 @@ def get_whole_span(x):
     return out
 
 
+def get_data(datadb, pick_user=False, num_user=48, draw=None, running_length=10, stride=10, fps=30, device=None):
+    """mycode/utility.py:359-446 on the device (cfg.cut_data_head / cfg.time_shift at their defaults).  ``datadb``:
+    {video: {'x','y','z': (viewers, frames) array or tensor}}.  Each video is windowed ONCE for all its viewers
+    (fov_window_stacks); the target / others split with duplicate padding or truncation to num_user - 1 is a gather
+    over the viewer axis of those windows (fov_pick_user_gather), written straight into the final tensors.
+    ``draw(n)`` supplies the duplicate indices (default np.random.randint, as the reference draws them).
+    Returns (past, future, future_input) (N,10,90), plus the others' three (num_user-1, N, 10, 90) when pick_user."""
+    import numpy as np
+    lib = _lib.load()
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    draw = draw or (lambda n: int(np.random.randint(n)))
+    K = num_user - 1
+    vids = []
+    for vid in datadb.keys():
+        d = datadb[vid]
+        xyz = torch.stack([torch.as_tensor(np.asarray(d[c]) if not isinstance(d[c], torch.Tensor) else d[c])
+                           .to(device=device, dtype=torch.float32) for c in "xyz"], dim=-1)      # (U, frames, 3)
+        U, S = xyz.shape[0], xyz.shape[1] // fps
+        if S < 2 * running_length:
+            continue                                                # 'video only has %d seconds. skip...'
+        per = xyz[:, :S * fps].reshape(U, S, 3 * fps)
+        vids.append((per, U))
+    if not vids:
+        raise _lib.FovError("get_data: no video has %d seconds" % (2 * running_length))
+    if not pick_user:
+        parts = [reshape2second_stacks(per, True, stride, running_length) for per, _ in vids]
+        return tuple(torch.cat([p[k] for p in parts], dim=0) for k in range(3))
+    wins = [reshape2second_stacks(per, False, stride, running_length) for per, _ in vids]     # (U, n, L, C) x 3
+    n_total = sum(w[0].shape[0] * w[0].shape[1] for w in wins)
+    L, Cc = wins[0][0].shape[2], wins[0][0].shape[3]
+    row = L * Cc
+    tar = [torch.cat([w[k].reshape(-1, L, Cc) for w in wins], dim=0) for k in range(3)]       # target t = viewer t, in order
+    oth = [torch.empty(K, n_total, L, Cc, device=device) for _ in range(3)]
+    base = 0
+    for (per, U), w in zip(vids, wins):
+        n = w[0].shape[1]
+        idx = []
+        for t in range(U):
+            lst = [u for u in range(U) if u != t]
+            while len(lst) < K:
+                lst.append(lst[draw(len(lst))])
+            idx += lst[:K]
+        idx_t = torch.tensor(idx, dtype=torch.int32, device=device)
+        for k in range(3):
+            _lib.check(lib.fov_pick_user_gather(U, K, n, row, ptr(idx_t), ptr(w[k]), ptr(oth[k]), n_total * row, base,
+                                                _stream()), "fov_pick_user_gather")
+        base += U * n
+    return tuple(tar) + tuple(oth)
+
+
 def one_hot_heatmaps(frames, bin_size=10):
     """(..., F, 3) xyz frames -> (..., 360/bin, 180/bin, F) one-hot FoV-centre maps, frames as channels
     (mycode/dataIO.py:77-82, mycode/utility.py:533-556, mycode/data_generator_for_heatmap.py:32,65-67)."""

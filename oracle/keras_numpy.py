@@ -253,6 +253,48 @@ def reshape2second_stacks(per_video_db, collapse_user=False, stride=10, running_
             fut_in.transpose(1, 0, 2, 3))
 
 
+def others_index_list(n_viewers, target, num_user, draw):
+    """Viewer indices of the 'others' of one target (mycode/utility.py:404-416): the video's other viewers in order;
+    fewer than num_user - 1 -> padded with duplicates drawn one at a time from the CURRENT (already padded) list,
+    ``draw(len)`` standing for np.random.randint(len); more -> truncated."""
+    lst = [u for u in range(n_viewers) if u != target]
+    K = num_user - 1
+    while len(lst) < K:
+        lst.append(lst[draw(len(lst))])
+    return lst[:K]
+
+
+def get_data(datadb, pick_user=False, num_user=48, draw=None, running_length=10, stride=10, fps=FPS):
+    """mycode/utility.py:359-446 (cfg.cut_data_head False, cfg.time_shift False).  datadb: {video: {'x','y','z':
+    (viewers, frames)}}.  pick_user False: every (viewer, window) of every video, windows collapsed over viewers ->
+    (past, future, future_input), each (N, 10, 90).  pick_user True: every viewer is the target once; returns the
+    target's three tensors (N,10,90) and the others' three (num_user-1, N, 10, 90).  Videos shorter than 2 x
+    running_length seconds are skipped.  ``draw(n)`` supplies the duplicate-padding indices (np.random.randint)."""
+    draw = draw or (lambda n: int(np.random.randint(n)))
+    tar, oth = [[], [], []], [[], [], []]
+    for vid in datadb.keys():
+        d = datadb[vid]
+        per = np.stack((d["x"], d["y"], d["z"]), axis=-1)
+        per = per[:, :per.shape[1] // fps * fps, :]
+        per = per.reshape(per.shape[0], per.shape[1] // fps, 3 * fps)
+        if per.shape[1] < 2 * running_length:
+            continue
+        if not pick_user:
+            for k, a in enumerate(reshape2second_stacks(per, True, stride, running_length)):
+                tar[k].append(a)
+            continue
+        for t in range(per.shape[0]):
+            idx = others_index_list(per.shape[0], t, num_user, draw)
+            for k, a in enumerate(reshape2second_stacks(per[t:t + 1], True, stride, running_length)):
+                tar[k].append(a)
+            for k, a in enumerate(reshape2second_stacks(per[idx], False, stride, running_length)):
+                oth[k].append(a)
+    out = [np.concatenate(a, axis=0) for a in tar]
+    if pick_user:
+        out += [np.concatenate(a, axis=1) for a in oth]
+    return tuple(out)
+
+
 def get_whole_span(x):
     """mycode/others_LSTM_span_whole.py:403-419: (N,L,...) -> (N,2L,...), row i =
     [x[i]; x[i+1]]; the last row stays zero."""

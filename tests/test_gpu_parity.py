@@ -848,3 +848,21 @@ def test_fit_input_pipeline_matches_train_on_batch():
     assert abs(h2.history["loss"][0] - float(np.mean(serial))) < 1e-6
     for k in a.weight_order:
         assert torch.allclose(a.params[k], c.params[k], rtol=0, atol=1e-6), k
+
+
+def test_get_data_matches_reference_golden():
+    """ops.get_data (device windows + fov_pick_user_gather) against the reference's own get_data outputs
+    (utility.py:359-446): pure gathers -> bit-exact in float32; both modes, duplicate padding and truncation."""
+    _cuda()
+    import os
+    from longterm360fov_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_get_data_golden.npz"))
+    datadb = {k: {c: g["in_%s_%s" % (k, c)] for c in "xyz"} for k in ("v0", "v1", "v2")}
+    for a, name in zip(ops.get_data(datadb, pick_user=False), ("all_past", "all_fut", "all_futin")):
+        assert np.array_equal(a.cpu().numpy(), g[name].astype(np.float32))
+    for num_user in (4, 6):
+        dups = list(g["u%d_dups" % num_user])
+        out = ops.get_data(datadb, pick_user=True, num_user=num_user, draw=lambda n: int(dups.pop(0)))
+        assert not dups
+        for a, name in zip(out, ("tar_past", "tar_fut", "tar_futin", "oth_past", "oth_fut", "oth_futin")):
+            assert np.array_equal(a.cpu().numpy(), g["u%d_%s" % (num_user, name)].astype(np.float32)), name

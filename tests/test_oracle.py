@@ -274,3 +274,19 @@ def test_resample_modes_and_torch_twin_agree():
     b = kt.convlstm_seq2seq_forward(kt.to_torch(w), torch.tensor(enc), torch.tensor(dec), head_kind="dense", steps=3,
                                     noise=torch.tensor(nz)).numpy()
     np.testing.assert_allclose(a, b, atol=1e-10)
+
+
+def test_get_data_restatement_matches_reference_golden():
+    """oracle get_data (target / others split, duplicate padding, truncation, short-video skip) against the outputs of
+    the reference's own get_data (tests/golden/make_get_data_golden.py), bit for bit."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_get_data_golden.npz"))
+    datadb = {k: {c: g["in_%s_%s" % (k, c)] for c in "xyz"} for k in ("v0", "v1", "v2")}
+    for a, name in zip(kn.get_data(datadb, pick_user=False), ("all_past", "all_fut", "all_futin")):
+        assert np.array_equal(a, g[name])
+    for num_user in (4, 6):
+        dups = list(g["u%d_dups" % num_user])
+        out = kn.get_data(datadb, pick_user=True, num_user=num_user, draw=lambda n: int(dups.pop(0)))
+        assert not dups
+        for a, name in zip(out, ("tar_past", "tar_fut", "tar_futin", "oth_past", "oth_fut", "oth_futin")):
+            assert np.array_equal(a, g["u%d_%s" % (num_user, name)]), name
