@@ -113,6 +113,8 @@ typedef struct {
   float *g_head_kernel, *g_head_bias;
   float *ws;                     /* optional workspace of fov_lstm_bwd_ws_floats() floats: with it (and cfg.math != 0)
                                     each LSTM's [dU; dW; db] is ONE tcgen05 launch over the padded xh rows */
+  const float *dhseq_dec;        /* optional (B,T_dec,H): gradient w.r.t. dec.hseq (stacked LSTMs: the layer above reads
+                                    this layer's hidden sequence, mycode/Fov_seq2seq_2layers.py:232-272) */
 } fov_lstm_grads;
 size_t fov_lstm_bwd_ws_floats(const fov_lstm_cfg* cfg);
 
@@ -324,6 +326,13 @@ int fov_whole_span(long long N, long long half, const float* x, float* out, void
  * out[j][base_rows + t*n + w] = src[idx[t*K+j]][w]; out_j_stride = N_total * row floats.  idx is a DEVICE int32 array. */
 int fov_pick_user_gather(int T, int K, int n, long long row, const int* idx, const float* src, float* out,
                          long long out_j_stride, long long base_rows, void* stream);
+/* Training batches of the concat-state model from the per-second mean/var features mv (U,S,6) of one video (the data
+ * preparation of mycode/others_LSTM_span_whole.py:403-419,640-668 + mycode/utility.py:389-430 composed): sequence
+ * b = target viewer (b / n) x window (b % n), n = (S-20)/stride + 1, start second s0 = (b % n) * stride:
+ *   enc (B,10,6) = mv[t, s0..s0+10); oth (B,20,1,K,6) = mv[idx[t*K+j], s0..s0+20); dec0 (B,1,6) = mv[t, s0+9];
+ *   fut (B,10,6) = mv[t, s0+10..s0+20).  idx: DEVICE int32 (U,K) others of every target.  B <= U*n (truncation). */
+int fov_m3_batches(int U, int S, int stride, int K, const int* idx, const float* mv, long long B, float* enc,
+                   float* oth, float* dec0, float* fut, void* stream);
 /* One-hot FoV-centre heatmaps: xyz (rows, frames, 3) -> out (rows, 360/bin, 180/bin, frames), one 1 per frame at
  * (theta bin, phi bin) with theta, phi of mycode/dataIO.py:77-82 and the binning of mycode/utility.py:533-539,
  * _create_one_hot :546-556; frames stacked as channels as mycode/data_generator_for_heatmap.py:32,65-67 feeds them.

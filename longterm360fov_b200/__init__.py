@@ -4,9 +4,12 @@ kernels behind a C ABI (include/fov360.h).  No CPU fallback: importing the model
 without libfov360.so raises."""
 from . import _lib
 from .callbacks import EarlyStopping, ModelCheckpoint, ReduceLROnPlateau
+from .pipeline import M3VideoBatches
 from .models import (Adam, ConvLSTMSeq2Seq, FovSeq2Seq, Model, OthersLSTMSpanWhole, RMSprop,
-                     convlstm_seq2seq, fov_seq2seq, fov_seq2seq_mu_var, others_lstm_span_whole)
+                     convlstm_seq2seq, fov_seq2seq, fov_seq2seq_mu_var, others_lstm_span_whole,
+                     StackedFovSeq2Seq, stacked_fov_seq2seq)
 
 __all__ = ["fov_seq2seq", "fov_seq2seq_mu_var", "others_lstm_span_whole", "convlstm_seq2seq",
            "Model", "FovSeq2Seq", "OthersLSTMSpanWhole", "ConvLSTMSeq2Seq", "Adam", "RMSprop",
-           "ModelCheckpoint", "ReduceLROnPlateau", "EarlyStopping"]
+           "ModelCheckpoint", "ReduceLROnPlateau", "EarlyStopping", "M3VideoBatches", "StackedFovSeq2Seq",
+           "stacked_fov_seq2seq"]

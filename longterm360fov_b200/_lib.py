@@ -46,7 +46,7 @@ class LstmGrads(C.Structure):
     _fields_ = [(n, c_float_p) for n in (
         "dy", "dhseq_enc", "y", "dz_enc", "dz_dec", "dpre",
         "g_enc_kernel", "g_enc_recurrent", "g_enc_bias",
-        "g_dec_kernel", "g_dec_recurrent", "g_dec_bias", "g_head_kernel", "g_head_bias", "ws")]
+        "g_dec_kernel", "g_dec_recurrent", "g_dec_bias", "g_head_kernel", "g_head_bias", "ws", "dhseq_dec")]
 
 
 class ConvCfg(C.Structure):
@@ -138,6 +138,7 @@ SYMBOLS = {
     "fov_window_stacks": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "fov_whole_span": (_I, [_LL, _LL, _P, _P, _P]),
     "fov_pick_user_gather": (_I, [_I, _I, _I, _LL, _P, _P, _P, _LL, _LL, _P]),
+    "fov_m3_batches": (_I, [_I, _I, _I, _I, _P, _P, _LL, _P, _P, _P, _P, _P]),
     "fov_onehot_heatmaps": (_I, [_LL, _I, _I, _P, _P, _P]),
     "fov_hit_rate": (_I, [_LL, _P, _P, _F, _F, _F, _F, _P, _P]),
 }

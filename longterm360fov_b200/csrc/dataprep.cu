@@ -227,6 +227,52 @@ extern "C" int fov_pick_user_gather(int T, int K, int n, long long row, const in
   return FOV_OK;
 }
 
+// Training batches of the concat-state model straight from the per-second mean/var features of one video
+// (mycode/others_LSTM_span_whole.py:403-419,640-668 with mycode/utility.py:389-430,483-517 composed): sequence
+// b = (target viewer t = b / n, window w = b % n) starts at second s0 = w * stride and gets
+//   enc  (B,10,6)        = mv[t, s0 .. s0+10)                     (target past; also the reconstruction target)
+//   oth  (B,20,1,K,6)    = mv[idx[t*K+j], s0 .. s0+20)            (others' whole span; also the others target)
+//   dec0 (B,1,6)         = mv[t, s0+9]                            (last observed second)
+//   fut  (B,10,6)        = mv[t, s0+10 .. s0+20)                  (target future)
+// One thread per output float, outputs coalesced; the feature table (U*S*6 floats) stays in L2.
+__global__ void __launch_bounds__(256) m3_batch_kernel(int S, int n, int stride, int K, const int* __restrict__ idx,
+                                                       const float* __restrict__ mv, long long B, float* __restrict__ enc,
+                                                       float* __restrict__ oth, float* __restrict__ dec0,
+                                                       float* __restrict__ fut) {
+  const int per_oth = 20 * K * 6, per = per_oth + 126;
+  const long long total = B * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / per;
+    const int e = (int)(i - b * per);
+    const int t = (int)(b / n), s0 = (int)(b % n) * stride;
+    if (e < per_oth) {
+      const int c = e % 6, j = (e / 6) % K, s = e / (6 * K);
+      const int u = __ldg(&idx[(long long)t * K + j]);
+      oth[b * per_oth + e] = __ldg(&mv[((long long)u * S + s0 + s) * 6 + c]);
+    } else if (e < per_oth + 60) {
+      const int q = e - per_oth;
+      enc[b * 60 + q] = __ldg(&mv[((long long)t * S + s0) * 6 + q]);
+    } else if (e < per_oth + 120) {
+      const int q = e - per_oth - 60;
+      fut[b * 60 + q] = __ldg(&mv[((long long)t * S + s0 + 10) * 6 + q]);
+    } else {
+      const int q = e - per_oth - 120;
+      dec0[b * 6 + q] = __ldg(&mv[((long long)t * S + s0 + 9) * 6 + q]);
+    }
+  }
+}
+
+extern "C" int fov_m3_batches(int U, int S, int stride, int K, const int* idx, const float* mv, long long B, float* enc,
+                              float* oth, float* dec0, float* fut, void* stream) {
+  FOV_CHECK_ARG(U > 0 && S >= 20 && stride > 0 && K > 0 && idx && mv && enc && oth && dec0 && fut, "bad arguments");
+  const int n = (S - 20) / stride + 1;                       // windows whose 20 seconds exist
+  FOV_CHECK_ARG(B > 0 && B <= (long long)U * n, "B exceeds viewers x windows");
+  const long long total = B * (20LL * K * 6 + 126);
+  m3_batch_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(S, n, stride, K, idx, mv, B, enc, oth, dec0, fut);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
+
 extern "C" int fov_onehot_heatmaps(long long rows, int frames, int bin_size, const float* xyz, float* out, void* stream) {
   FOV_CHECK_ARG(rows > 0 && rows < (1LL << 31) && frames > 0 && frames <= 4096, "bad shape");
   FOV_CHECK_ARG(bin_size > 0 && 360 % bin_size == 0 && 180 % bin_size == 0, "bin_size must divide 180");

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kNT) lstm_seq2seq_bwd_kernel(const __grid_cons
     BwdPhaseDesc ph;
     ph.Wk = P.w.dec_kernel; ph.Uk = P.w.dec_recurrent; ph.in_dim = cfg.in_dec; ph.T = cfg.T_dec;
     ph.ar = cfg.teacher_forcing == 0; ph.has_head = out_dim > 0;
-    ph.dy = P.g.dy; ph.y = P.g.y; ph.dhseq = nullptr; ph.dpre = P.g.dpre; ph.dz = P.g.dz_dec;
+    ph.dy = P.g.dy; ph.y = P.g.y; ph.dhseq = P.g.dhseq_dec; ph.dpre = P.g.dpre; ph.dz = P.g.dz_dec;
     ph.sv = P.io.dec;
     if (cfg.dec_zero_init) { ph.c_init = nullptr; ph.c_init_stride = 0; }
     else if (cfg.T_enc > 0) {

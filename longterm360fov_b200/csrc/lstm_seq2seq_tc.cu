@@ -933,7 +933,7 @@ int lstm_tc_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w, const fov_ls
     BwdTcPhase& ph = P.ph[n++];
     ph.Uk = w->dec_recurrent; ph.Wk = w->dec_kernel; ph.in_dim = cfg->in_dec; ph.T = cfg->T_dec;
     ph.ar = ar; ph.has_head = P.out_dim > 0; ph.zero_carry = 1;
-    ph.dy = g->dy; ph.y = g->y; ph.dhseq = nullptr; ph.dpre = g->dpre; ph.dz = g->dz_dec;
+    ph.dy = g->dy; ph.y = g->y; ph.dhseq = g->dhseq_dec; ph.dpre = g->dpre; ph.dz = g->dz_dec;
     ph.gates = io->dec.gates; ph.c = io->dec.c;
     if (cfg->dec_zero_init) { ph.c_init = nullptr; ph.c_init_stride = 0; }
     else if (cfg->T_enc > 0) { ph.c_init = io->enc.c + (size_t)(cfg->T_enc - 1) * kH; ph.c_init_stride = (long long)cfg->T_enc * kH; }
@@ -949,7 +949,7 @@ int lstm_tc_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weights* w, const fov_ls
   P.nph = n;
   auto a16 = [](const void* q) { return (uintptr_t)q % 16 == 0; };
   FOV_CHECK_ARG(a16(io->enc.gates) && a16(io->enc.c) && a16(io->dec.gates) && a16(io->dec.c) && a16(g->dz_enc) &&
-                    a16(g->dz_dec) && a16(g->dhseq_enc) && a16(io->c0) && a16(w->enc_recurrent) && a16(w->dec_recurrent) &&
+                    a16(g->dz_dec) && a16(g->dhseq_enc) && a16(g->dhseq_dec) && a16(io->c0) && a16(w->enc_recurrent) && a16(w->dec_recurrent) &&
                     a16(w->dec_kernel),
                 "tensor-core fc-LSTM BPTT needs 16-byte aligned tensors");
   const bool hs = cfg->rec_act == FOV_REC_HARD_SIGMOID;

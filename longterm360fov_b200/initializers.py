@@ -100,3 +100,17 @@ def init_convlstm_seq2seq(seed=1, in_ch=30, filters=(32, 16, 8), kernel_size=5, 
     else:
         _dense(rng, flat_dim, 6, "head_dense", w)
     return w
+
+
+def init_stacked_fov_seq2seq(seed=1, n_layers=2, num_encoder_tokens=6, num_decoder_tokens=6, latent_dim=64):
+    """2- / 3-layer target-only models (mycode/Fov_seq2seq_2layers.py:232-272, mycode/3layers.py:223-275): LSTMs of
+    latent_dim // 2 units."""
+    rng = np.random.default_rng(seed)
+    units = latent_dim // 2
+    w = {}
+    for l in range(n_layers):
+        _lstm(rng, num_encoder_tokens if l == 0 else units, units, "encoder%d" % l, w)
+    for l in range(n_layers):
+        _lstm(rng, num_decoder_tokens if l == 0 else units, units, "decoder%d" % l, w)
+    _dense(rng, units, num_decoder_tokens, "decoder_dense", w)
+    return w

@@ -350,23 +350,36 @@ class Model:
             t.record_stream(main)
         return xs, ys, (x_ready, y_ready), len(xs[0])
 
-    def _train_batches(self, batches):
+    def _train_batches(self, batches, builder=None):
         """Input pipeline of fit / fit_generator: while the kernels of step i run, the batch of step i+1 is assembled
         on the host and copied on the side stream (the copy engines are idle during the step); the loss of a step is
         read back once the next step has been enqueued.  Every batch still crosses PCIe inside the loop and every
-        loss is read; yields (batch size, loss) in step order."""
+        loss is read; yields (batch size, loss) in step order.
+        ``builder``: the items are RAW host chunks (an array or a list of arrays); ``builder(*device_chunks)`` turns
+        them into (inputs, targets) on the GPU (pipeline.py)."""
         it = iter(batches)
+
+        def fetch():
+            item = next(it)
+            if builder is None:
+                return self._prefetch(*item)
+            raw = self._as_list(item)
+            dev, _, (ready, _), _ = self._prefetch(raw, [])
+            return dev, None, (ready, None), None
         try:
-            cur = self._prefetch(*next(it))
+            cur = fetch()
         except StopIteration:
             return
         pending = None                                         # (batch size, loss tensor) of the step before
         while cur is not None:
             xs, ys, (x_ready, y_ready), b = cur
             torch.cuda.current_stream().wait_event(x_ready)
+            if builder is not None:
+                xs, ys = builder(*xs)                          # featuriser + windowing + target/others split on the GPU
+                b = len(xs[0])
             loss = self.train_step_device(xs, ys, y_ready)     # asynchronous launches
             try:
-                cur = self._prefetch(*next(it))
+                cur = fetch()
             except StopIteration:
                 cur = None
             # the loss of step i-1 is read while step i runs: the host never drains the GPU between steps
@@ -459,9 +472,10 @@ class Model:
         return hist
 
     def fit_generator(self, generator, steps_per_epoch, epochs=1, validation_data=None,
-                      validation_steps=None, callbacks=None, initial_epoch=0, verbose=0, **_):
+                      validation_steps=None, callbacks=None, initial_epoch=0, verbose=0, batch_builder=None, **_):
         """keras Model.fit_generator (mycode/convlstm_heatmap.py:415-418): the generator
-        yields (inputs, targets) batches forever."""
+        yields (inputs, targets) batches forever.  With ``batch_builder`` (pipeline.py) it yields RAW chunks instead
+        and the builder makes the batches on the device."""
         hist = History()
         callbacks = callbacks or []
         for cb in callbacks:
@@ -470,7 +484,7 @@ class Model:
         self.stop_training = False
         for epoch in range(initial_epoch, epochs):
             tot, cnt = 0.0, 0
-            for b, l in self._train_batches(next(generator) for _ in range(steps_per_epoch)):
+            for b, l in self._train_batches((next(generator) for _ in range(steps_per_epoch)), batch_builder):
                 tot += b * l
                 cnt += b
             logs = {"loss": tot / max(cnt, 1)}
@@ -561,8 +575,8 @@ class FovSeq2Seq(Model):
         T_dec = dec.shape[1] if tf else (steps or self.T_dec)
         opts = {"T_dec": T_dec, "teacher_forcing": tf, "head_act": "tanh", "rec_act": self.rec_act,
                 "dec_zero_init": self.decoder_no_init_state, "training": training, "need_enc_hseq": False}
-        y, _ = ops.LSTMSeq2SeqFn.apply(opts, self._lstm_sinks() if training else None, enc, dec, None,
-                                       *self._w())
+        y, _, _ = ops.LSTMSeq2SeqFn.apply(opts, self._lstm_sinks() if training else None, enc, dec, None,
+                                          *self._w())
         return [y]
 
     # --- inference sub-models (mycode/FoV_seq2seq.py:137-178) --- #
@@ -618,6 +632,131 @@ def fov_seq2seq_mu_var(latent_dim=64, num_decoder_tokens=6, **kw):
     """Builder for M2 (mycode/FoV_seq2seq_mu_var.py:40-49,219-248): encoder consumes the
     per-second mean/var (B,10,6)."""
     return fov_seq2seq(latent_dim=latent_dim, num_encoder_tokens=6, num_decoder_tokens=num_decoder_tokens, **kw)
+
+
+# --------------------------------------------------------------------------- #
+# sibling models: 2- / 3-layer target-only fc-LSTM encoder-decoders (SURVEY.md 8f row 3)
+# --------------------------------------------------------------------------- #
+
+_KH = 64     # hidden width of the fc-LSTM kernels
+
+
+def _pad_gates(a, units):
+    """(..., 4*units) gate-blocked [i|f|c|o] -> (..., 4*64): every gate block padded to 64 columns with zeros."""
+    a = np.asarray(a, np.float32)
+    out = np.zeros(a.shape[:-1] + (4 * _KH,), np.float32)
+    for g in range(4):
+        out[..., g * _KH:g * _KH + units] = a[..., g * units:(g + 1) * units]
+    return out
+
+
+def _strip_gates(a, units):
+    return np.concatenate([a[..., g * _KH:g * _KH + units] for g in range(4)], axis=-1)
+
+
+def _pad_rows(a, rows):
+    out = np.zeros((rows,) + a.shape[1:], np.float32)
+    out[:a.shape[0]] = a
+    return out
+
+
+class StackedFovSeq2Seq(Model):
+    """mycode/Fov_seq2seq_2layers.py:232-272 and mycode/3layers.py:223-275: n_layers encoder LSTMs and n_layers decoder
+    LSTMs of latent_dim // 2 = 32 units (layer l reads the hidden sequence of layer l-1; decoder layer l starts from
+    the state of encoder layer l), Dense(6, tanh) on the last decoder layer, teacher forcing.
+
+    The fc-LSTM kernels are built for 64 hidden units.  A 32-unit LSTM is EXACTLY a 64-unit LSTM whose extra units have
+    zero weights and zero bias: their gates sit at hard_sigmoid(0) / tanh(0), so c = h = 0 for ever, they feed
+    nothing into the real units (zero recurrent rows, zero rows in the next layer's kernel and in the head) and every
+    one of their gradients is exactly 0 - Adam / RMSprop leave them at 0.  The parameters therefore LIVE padded in the
+    flat bucket; get_weights / set_weights / save / load speak the Keras shapes.
+    One persistent launch per layer runs its encoder and decoder phases; layers above the first have 64-wide inputs
+    and take the time-batched projection (xproj_tc.cu) on the tensor-core path."""
+
+    def __init__(self, weights, n_layers=2, share_last_decoder=None, recurrent_activation="hard_sigmoid", device=None):
+        self.n_layers = n_layers
+        self.share_last_decoder = (n_layers == 3) if share_last_decoder is None else bool(share_last_decoder)
+        self.units = int(np.shape(weights["encoder0/recurrent_kernel"])[0])
+        if self.units > _KH:
+            raise NotImplementedError("fc-LSTM kernels support up to %d units" % _KH)
+        self.weight_order = (["%s%d/%s" % (s, l, n) for s in ("encoder", "decoder") for l in range(n_layers)
+                              for n in ("kernel", "recurrent_kernel", "bias")] +
+                             ["decoder_dense/kernel", "decoder_dense/bias"])
+        self._keras_shapes = {k: tuple(np.shape(weights[k])) for k in self.weight_order}
+        super().__init__({k: self._pad(k, weights[k]) for k in self.weight_order}, device)
+        self.rec_act = recurrent_activation
+
+    def _pad(self, name, a):
+        a = np.asarray(a, np.float32)
+        u = self.units
+        layer, kind = name.split("/")
+        if layer == "decoder_dense":
+            return _pad_rows(a, _KH) if kind == "kernel" else a
+        if kind == "bias":
+            return _pad_gates(a, u)
+        a = _pad_gates(a, u)
+        if kind == "recurrent_kernel" or not layer.endswith("0"):     # rows = hidden units (of this / the layer below)
+            a = _pad_rows(a, _KH)
+        return a
+
+    def _strip(self, name, a):
+        u = self.units
+        layer, kind = name.split("/")
+        shp = self._keras_shapes[name]
+        if layer == "decoder_dense":
+            return a[:shp[0]] if kind == "kernel" else a
+        a = _strip_gates(a, u)
+        return a[:shp[0]] if a.ndim == 2 else a
+
+    def get_weights(self):
+        return [self._strip(k, self.params[k].detach().cpu().numpy()) for k in self.weight_order]
+
+    def set_weights(self, arrays):
+        arrays = list(arrays)
+        if tuple(np.shape(arrays[0])) == self._keras_shapes[self.weight_order[0]] and \
+                tuple(np.shape(arrays[1])) == self._keras_shapes[self.weight_order[1]]:
+            arrays = [self._pad(k, a) for k, a in zip(self.weight_order, arrays)]
+        super().set_weights(arrays)
+
+    def count_params(self):
+        return sum(int(np.prod(s)) for s in self._keras_shapes.values())
+
+    def _forward(self, inputs, training):
+        enc, dec = inputs
+        p, g = self.params, self.grads
+        L = self.n_layers
+        xe, xd = enc, dec
+        y = None
+        for l in range(L):
+            last = l == L - 1
+            pe = "encoder%d" % l
+            pd = "decoder%d" % (l - 1 if (self.share_last_decoder and last) else l)     # 3layers.py:266 reuses decoder_lstm2
+            opts = {"T_dec": dec.shape[1], "teacher_forcing": True, "head_act": "tanh", "rec_act": self.rec_act,
+                    "dec_zero_init": False, "training": training, "need_enc_hseq": not last, "need_dec_hseq": not last}
+            sinks = None
+            if training:
+                sinks = {"enc_kernel": g[pe + "/kernel"], "enc_recurrent": g[pe + "/recurrent_kernel"],
+                         "enc_bias": g[pe + "/bias"], "dec_kernel": g[pd + "/kernel"],
+                         "dec_recurrent": g[pd + "/recurrent_kernel"], "dec_bias": g[pd + "/bias"]}
+                if last:
+                    sinks["head_kernel"], sinks["head_bias"] = g["decoder_dense/kernel"], g["decoder_dense/bias"]
+            y, xe, xd = ops.LSTMSeq2SeqFn.apply(
+                opts, sinks, xe, xd, None, p[pe + "/kernel"], p[pe + "/recurrent_kernel"], p[pe + "/bias"],
+                p[pd + "/kernel"], p[pd + "/recurrent_kernel"], p[pd + "/bias"],
+                p["decoder_dense/kernel"] if last else None, p["decoder_dense/bias"] if last else None)
+        return [y]
+
+
+def stacked_fov_seq2seq(n_layers=2, latent_dim=64, num_encoder_tokens=6, num_decoder_tokens=6, share_last_decoder=None,
+                        recurrent_activation="hard_sigmoid", weights=None, seed=1, device=None):
+    """Builder for the 2-layer (mycode/Fov_seq2seq_2layers.py:232-272) and 3-layer (mycode/3layers.py:223-275)
+    target-only models: inputs ``[encoder_inputs (B,T,6), decoder_inputs (B,T,6)]`` -> ``(B,T,6)``; every LSTM has
+    latent_dim // 2 units.  ``weights`` in Keras shapes (keys encoder{l}/..., decoder{l}/..., decoder_dense/...)."""
+    if weights is None:
+        weights = _init_weights("init_stacked_fov_seq2seq", seed=seed, n_layers=n_layers,
+                                num_encoder_tokens=num_encoder_tokens, num_decoder_tokens=num_decoder_tokens,
+                                latent_dim=latent_dim)
+    return StackedFovSeq2Seq(weights, n_layers, share_last_decoder, recurrent_activation, device)
 
 
 # --------------------------------------------------------------------------- #
@@ -680,7 +819,7 @@ class OthersLSTMSpanWhole(Model):
                      "enc_bias": g["encoder/bias"], "dec_kernel": g["decoder/kernel"],
                      "dec_recurrent": g["decoder/recurrent_kernel"], "dec_bias": g["decoder/bias"],
                      "head_kernel": gWd[:Hl], "head_bias": self._zero_bias_grad}
-        y, enc_seq = ops.LSTMSeq2SeqFn.apply(
+        y, enc_seq, _ = ops.LSTMSeq2SeqFn.apply(
             opts, sinks, enc_in, dec_in, e, p["encoder/kernel"], p["encoder/recurrent_kernel"],
             p["encoder/bias"], p["decoder/kernel"], p["decoder/recurrent_kernel"], p["decoder/bias"],
             Wd[:Hl], self._zero_bias)

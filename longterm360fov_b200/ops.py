@@ -64,10 +64,12 @@ def _ws(nbytes, device):
 
 
 class LSTMSeq2SeqFn(torch.autograd.Function):
-    """y, enc_hseq = f(x_enc, x_dec, extra | enc/dec/head weights).
+    """y, enc_hseq, dec_hseq = f(x_enc, x_dec, extra | enc/dec/head weights).
 
-    opts: dict(T_dec, teacher_forcing, head_act, rec_act, dec_zero_init, training)
+    opts: dict(T_dec, teacher_forcing, head_act, rec_act, dec_zero_init, training, need_enc_hseq, need_dec_hseq)
     sinks: dict name -> gradient view for the 8 weights (or None at inference).
+    Wo / bo may be None (no head: a lower layer of a stacked model, mycode/Fov_seq2seq_2layers.py:232-272, whose
+    hidden sequences feed the layer above); gradients flow back into x_enc / x_dec (teacher forcing) when they need them.
     """
 
     @staticmethod
@@ -79,7 +81,7 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
         B, T_enc, in_enc = x_enc.shape
         in_dec = x_dec.shape[2]
         H = Ue.shape[0]
-        out_dim = Wo.shape[1]
+        out_dim = Wo.shape[1] if Wo is not None else 0
         T_dec = opts["T_dec"]
         _expect(x_dec.shape[0] == B, "LSTMSeq2SeqFn: x_dec has %d sequences, x_enc %d", x_dec.shape[0], B)
         _expect(tuple(We.shape) == (in_enc, 4 * H) and tuple(Ue.shape) == (H, 4 * H) and be.numel() == 4 * H,
@@ -88,8 +90,8 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
         _expect(tuple(Wd.shape) == (in_dec, 4 * H) and tuple(Ud.shape) == (H, 4 * H) and bd.numel() == 4 * H,
                 "LSTMSeq2SeqFn: decoder weights %s/%s/%s do not fit input width %d, H=%d", tuple(Wd.shape),
                 tuple(Ud.shape), tuple(bd.shape), in_dec, H)
-        _expect(Wo.shape[0] == H and bo.numel() == out_dim, "LSTMSeq2SeqFn: head weights %s/%s do not fit H=%d",
-                tuple(Wo.shape), tuple(bo.shape), H)
+        _expect(Wo is None or (Wo.shape[0] == H and bo.numel() == out_dim),
+                "LSTMSeq2SeqFn: head weights do not fit H=%d", H)
         if opts["teacher_forcing"]:
             _expect(x_dec.shape[1] == T_dec, "LSTMSeq2SeqFn: teacher forcing needs x_dec (B,%d,in), got %s", T_dec,
                     tuple(x_dec.shape))
@@ -111,6 +113,7 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
         y = torch.empty(B, T_dec, out_dim, device=dev)
         # the encoder's h sequence is an output only for callers that read it (M3's target-past head)
         enc_hseq = torch.empty(B, T_enc, H, device=dev) if opts.get("need_enc_hseq", True) else None
+        dec_hseq = torch.empty(B, T_dec, H, device=dev) if (training or opts.get("need_dec_hseq", False)) else None
         saved = {}
         if training:
             saved["enc_xh"] = torch.empty(B, T_enc, (H + in_enc + 3) // 4 * 4, device=dev)   # [h | x | 0] rows
@@ -119,7 +122,7 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
             saved["dec_xh"] = torch.empty(B, T_dec, (H + in_dec + 3) // 4 * 4, device=dev)
             saved["dec_gates"] = torch.empty(B, T_dec, 4 * H, device=dev)
             saved["dec_c"] = torch.empty(B, T_dec, H, device=dev)
-            saved["dec_hseq"] = torch.empty(B, T_dec, H, device=dev)
+            saved["dec_hseq"] = dec_hseq
         # workspace of the time-batched input projection (inputs wider than 16 features on the tensor-core path)
         nws = lib.fov_lstm_fwd_ws_bytes(C.byref(cfg))
         ws = _ws(nws, dev) if nws else None
@@ -127,25 +130,33 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
                          _lib.LstmSaved(ptr(saved.get("enc_xh")), ptr(saved.get("enc_gates")),
                                         ptr(saved.get("enc_c")), ptr(enc_hseq)),
                          _lib.LstmSaved(ptr(saved.get("dec_xh")), ptr(saved.get("dec_gates")),
-                                        ptr(saved.get("dec_c")), ptr(saved.get("dec_hseq"))), ptr(ws))
+                                        ptr(saved.get("dec_c")), ptr(dec_hseq)), ptr(ws))
         _lib.check(lib.fov_lstm_seq2seq_fwd(C.byref(cfg), C.byref(w), C.byref(io), _stream()),
                    "fov_lstm_seq2seq_fwd")
         if training:
             ctx.cfg, ctx.sinks, ctx.saved = cfg, sinks, saved
             ctx.has_extra = extra is not None
+            ctx.need_dx = (ctx.needs_input_grad[2], ctx.needs_input_grad[3] and bool(opts["teacher_forcing"]))
             ctx.save_for_backward(x_enc, x_dec, extra, We, Ue, be, Wd, Ud, bd, Wo, bo, y, enc_hseq)
+        nondiff = []
         if enc_hseq is None:
             enc_hseq = y.new_empty(0)
-            ctx.mark_non_differentiable(enc_hseq)
-        return y, enc_hseq
+            nondiff.append(enc_hseq)
+        if dec_hseq is None or not opts.get("need_dec_hseq", False):
+            dec_hseq = y.new_empty(0)                 # saved tensor only: not an output of this call
+            nondiff.append(dec_hseq)
+        if nondiff:
+            ctx.mark_non_differentiable(*nondiff)
+        return y, enc_hseq, dec_hseq
 
     @staticmethod
-    def backward(ctx, dy, dhseq_enc):
+    def backward(ctx, dy, dhseq_enc, dhseq_dec):
         lib = _lib.load()
         x_enc, x_dec, extra, We, Ue, be, Wd, Ud, bd, Wo, bo, y, enc_hseq = ctx.saved_tensors
         cfg, s, sv = ctx.cfg, ctx.sinks, ctx.saved
         dy = _f32c(dy) if dy is not None else torch.zeros_like(y)
         dhseq_enc = _f32c(dhseq_enc) if enc_hseq is not None else None
+        dhseq_dec = _f32c(dhseq_dec) if (dhseq_dec is not None and dhseq_dec.numel()) else None
         dev = y.device
         dz_enc = torch.empty(cfg.B, cfg.T_enc, 4 * cfg.H, device=dev)
         dz_dec = torch.empty(cfg.B, cfg.T_dec, 4 * cfg.H, device=dev)
@@ -160,11 +171,29 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
         g = _lib.LstmGrads(ptr(dy), ptr(dhseq_enc), ptr(y), ptr(dz_enc), ptr(dz_dec), ptr(dpre),
                            ptr(s["enc_kernel"]), ptr(s["enc_recurrent"]), ptr(s["enc_bias"]),
                            ptr(s["dec_kernel"]), ptr(s["dec_recurrent"]), ptr(s["dec_bias"]),
-                           ptr(s["head_kernel"]), ptr(s["head_bias"]), ptr(ws))
+                           ptr(s.get("head_kernel")), ptr(s.get("head_bias")), ptr(ws), ptr(dhseq_dec))
         _lib.check(lib.fov_lstm_seq2seq_bwd(C.byref(cfg), C.byref(w), C.byref(io), C.byref(g), _stream()),
                    "fov_lstm_seq2seq_bwd")
         d_extra = dpre if ctx.has_extra else None
-        return (None, None, None, None, d_extra) + (None,) * 8
+        # gradients w.r.t. the inputs (a layer below in a stacked model): dx = dZ . W^T, one Dense backward-data GEMM
+        dxs = [None, None]
+        for i, (need, xin, dz, Wk) in enumerate(((ctx.need_dx[0], x_enc, dz_enc, We), (ctx.need_dx[1], x_dec, dz_dec, Wd))):
+            if not need:
+                continue
+            rows, cin = xin.shape[0] * xin.shape[1], xin.shape[2]
+            ccfg = _conv_cfg(rows, 1, 1, cin, 4 * cfg.H, 1, 1, (1, 1), None, 0.0, cin, cin, 4 * cfg.H, 4 * cfg.H)
+            dx = torch.empty_like(xin)
+            math = cfg.math
+            if math == 0:
+                wsd = torch.empty(Wk.numel(), device=dev)
+                _lib.check(lib.fov_conv2d_bwd_data(C.byref(ccfg), ptr(dz), ptr(Wk), ptr(dx), ptr(wsd), _stream()),
+                           "fov_conv2d_bwd_data")
+            else:
+                wsd = _ws(lib.fov_conv_tc_ws_bytes(C.byref(ccfg), math, 1), dev)
+                _lib.check(lib.fov_conv2d_bwd_data_tc(C.byref(ccfg), ptr(dz), ptr(Wk), ptr(dx), ptr(wsd), math, _stream()),
+                           "fov_conv2d_bwd_data_tc")
+            dxs[i] = dx
+        return (None, None, dxs[0], dxs[1], d_extra) + (None,) * 8
 
 
 def lstm_states(x_enc, We, Ue, be, rec_act="hard_sigmoid", h0=None, c0=None):
@@ -386,8 +415,7 @@ class DualDenseFn(torch.autograd.Function):
         st = _stream()
         xs = x.data_ptr() + 4 * t0 * Cin
         dx = torch.empty_like(x) if ctx.need_dx else None
-        for cfg, xp, W, dy, sinks, beta, off in ((full, x.data_ptr(), W1, dy1, ctx.sinks[0], 0.0, 0),
-                                                 (part, xs, W2, dy2, ctx.sinks[1], 1.0, 4 * t0 * Cin)):
+        for cfg, xp, W, dy, sinks in ((full, x.data_ptr(), W1, dy1, ctx.sinks[0]), (part, xs, W2, dy2, ctx.sinks[1])):
             gw, gb = sinks
             if math == 0:
                 _lib.check(lib.fov_conv2d_bwd_weight(C.byref(cfg), xp, ptr(dy), ptr(gw), ptr(gb), st),
@@ -395,16 +423,26 @@ class DualDenseFn(torch.autograd.Function):
             else:
                 _lib.check(lib.fov_conv2d_bwd_weight_tc(C.byref(cfg), xp, ptr(dy), ptr(gw), ptr(gb), math, st),
                            "fov_conv2d_bwd_weight_tc")
-            if dx is not None:
-                cfg.beta = beta
-                dxp = dx.data_ptr() + off
+        if dx is not None:
+            # dx[:, :t0] = dy1[:, :t0] . W1^T ;  dx[:, t0:] = [dy1[:, t0:] | dy2] . [W1 | W2]^T  - ONE GEMM (K = C1 + C2) for the
+            # slices both layers read, each slice of dx written exactly once.  (Two accumulating GEMMs re-read and
+            # re-wrote the 10 future slices: 1.3 GB of extra traffic per step at B = 8880, 1.16 ms -> 0.6 ms.)
+            Ts = T - t0
+            jobs = []
+            if t0 > 0:
+                past = _conv_cfg(B, 1, t0, Cin, C1, 1, 1, (1, 1), None, 0.0, T * Cin, Cin, T * C1, C1)
+                jobs.append((past, dy1.data_ptr(), W1, dx.data_ptr()))
+            dcat = torch.cat([dy1[:, t0:], dy2], dim=-1)                       # (B, Ts, C1 + C2), small next to dx
+            Wcat = torch.cat([W1, W2], dim=-1)
+            fut = _conv_cfg(B, 1, Ts, Cin, C1 + C2, 1, 1, (1, 1), None, 0.0, T * Cin, Cin, Ts * (C1 + C2), C1 + C2)
+            jobs.append((fut, dcat.data_ptr(), Wcat, dx.data_ptr() + 4 * t0 * Cin))
+            for cfg, dyp, W, dxp in jobs:
                 if math == 0:
                     ws = torch.empty(W.numel(), device=x.device)
-                    _lib.check(lib.fov_conv2d_bwd_data(C.byref(cfg), ptr(dy), ptr(W), dxp, ptr(ws), st),
-                               "fov_conv2d_bwd_data")
+                    _lib.check(lib.fov_conv2d_bwd_data(C.byref(cfg), dyp, ptr(W), dxp, ptr(ws), st), "fov_conv2d_bwd_data")
                 else:
                     ws = _ws(lib.fov_conv_tc_ws_bytes(C.byref(cfg), math, 1), x.device)
-                    _lib.check(lib.fov_conv2d_bwd_data_tc(C.byref(cfg), ptr(dy), ptr(W), dxp, ptr(ws), math, st),
+                    _lib.check(lib.fov_conv2d_bwd_data_tc(C.byref(cfg), dyp, ptr(W), dxp, ptr(ws), math, st),
                                "fov_conv2d_bwd_data_tc")
         return None, None, None, dx, None, None, None, None
 
@@ -841,6 +879,49 @@ def get_data(datadb, pick_user=False, num_user=48, draw=None, running_length=10,
                                                 _stream()), "fov_pick_user_gather")
         base += U * n
     return tuple(tar) + tuple(oth)
+
+
+def others_index(n_viewers, num_user, draw=None):
+    """(U, num_user-1) int32 table: the others of every target viewer (mycode/utility.py:404-416): the video's other
+    viewers in order, padded with duplicates drawn from the current list or truncated."""
+    import numpy as np
+    draw = draw or (lambda n: int(np.random.randint(n)))
+    K = num_user - 1
+    rows = []
+    for t in range(n_viewers):
+        lst = [u for u in range(n_viewers) if u != t]
+        while len(lst) < K:
+            lst.append(lst[draw(len(lst))])
+        rows.append(lst[:K])
+    return np.asarray(rows, dtype=np.int32)
+
+
+def m3_batches_from_video(frames, num_user, stride=10, limit=None, idx=None, draw=None):
+    """Training batches of others_lstm_span_whole from ONE raw video on the device: ``frames`` (U, S, 90) unit-sphere
+    xyz per second (30 frames interleaved) -> per-second mean/var (fov_mean_var_xyz) -> every (target viewer, window)
+    sequence (fov_m3_batches).  Returns (inputs [enc (B,10,6), oth (B,20,1,K,6), dec0 (B,1,6)], targets [fut (B,10,6),
+    oth viewed (B,20,K*6), enc]) - the two reconstruction targets alias their inputs, nothing is copied.
+    ``limit``: keep the first ``limit`` sequences."""
+    lib = _lib.load()
+    _require_cuda(frames)
+    frames = _f32c(frames)
+    U, S = frames.shape[0], frames.shape[1]
+    K = num_user - 1
+    mv = mean_var_xyz(frames)                                     # (U,S,6)
+    n = (S - 20) // stride + 1
+    if n < 1:
+        raise _lib.FovError("m3_batches_from_video: %d seconds give no 20-second window" % S)
+    B = U * n if limit is None else min(int(limit), U * n)
+    if idx is None:
+        idx = torch.as_tensor(others_index(U, num_user, draw), device=frames.device)
+    dev = frames.device
+    enc = torch.empty(B, 10, 6, device=dev)
+    oth = torch.empty(B, 20, 1, K, 6, device=dev)
+    dec0 = torch.empty(B, 1, 6, device=dev)
+    fut = torch.empty(B, 10, 6, device=dev)
+    _lib.check(lib.fov_m3_batches(U, S, stride, K, ptr(idx), ptr(mv), B, ptr(enc), ptr(oth), ptr(dec0), ptr(fut),
+                                  _stream()), "fov_m3_batches")
+    return [enc, oth, dec0], [fut, oth.view(B, 20, K * 6), enc]
 
 
 def one_hot_heatmaps(frames, bin_size=10):

@@ -505,6 +505,39 @@ def fov_seq2seq_forward(w, enc_in, dec_in, teacher_forcing=True, decoder_no_init
     return np.stack(outs, axis=1)
 
 
+def init_stacked_fov_seq2seq(seed=1, n_layers=2, num_encoder_tokens=6, num_decoder_tokens=6, latent_dim=64):
+    """Weights of the 2- / 3-layer target-only models (mycode/Fov_seq2seq_2layers.py:232-272, mycode/3layers.py:223-275):
+    n_layers encoder LSTMs and n_layers decoder LSTMs of latent_dim // 2 units, Dense(num_decoder_tokens, tanh)."""
+    rng = np.random.default_rng(seed)
+    units = latent_dim // 2
+    w = {}
+    for l in range(n_layers):
+        init_lstm(rng, num_encoder_tokens if l == 0 else units, units, "encoder%d" % l, w)
+    for l in range(n_layers):
+        init_lstm(rng, num_decoder_tokens if l == 0 else units, units, "decoder%d" % l, w)
+    init_dense(rng, units, num_decoder_tokens, "decoder_dense", w)
+    return w
+
+
+def stacked_fov_seq2seq_forward(w, enc_in, dec_in, n_layers=2, share_last_decoder=None,
+                                recurrent_activation="hard_sigmoid"):
+    """Teacher-forced forward of the stacked models: encoder layer l reads the hidden sequence of layer l-1, decoder
+    layer l starts from the final state of encoder layer l and reads the hidden sequence of decoder layer l-1.
+    ``share_last_decoder`` (default: n_layers == 3): mycode/3layers.py:266 calls ``decoder_lstm2`` again for the third
+    decoder layer, so layers 2 and 3 of the decoder share one set of weights - it is what the graph computes."""
+    if share_last_decoder is None:
+        share_last_decoder = n_layers == 3
+    xe, xd = enc_in, dec_in
+    for l in range(n_layers):
+        pe = "encoder%d" % l
+        pd = "decoder%d" % (l - 1 if (share_last_decoder and l == n_layers - 1) else l)
+        xe, h, c = lstm(xe, w[pe + "/kernel"], w[pe + "/recurrent_kernel"], w[pe + "/bias"],
+                        recurrent_activation=recurrent_activation)
+        xd, _, _ = lstm(xd, w[pd + "/kernel"], w[pd + "/recurrent_kernel"], w[pd + "/bias"], h, c,
+                        recurrent_activation=recurrent_activation)
+    return dense(xd, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+
+
 def init_others_lstm_span_whole(seed=1, num_user=34, kernel_size=5, latent_dim=64,
                                 oth_filters=(32, 16, 8), flat_dense=256):
     """Weights of M3, the canonical concat-state model (SURVEY.md hazard 2)."""

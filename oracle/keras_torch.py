@@ -179,6 +179,19 @@ def fov_seq2seq_forward(w, enc_in, dec_in, teacher_forcing=True, decoder_no_init
     return torch.stack(outs, 1)
 
 
+def stacked_fov_seq2seq_forward(w, enc_in, dec_in, n_layers=2, share_last_decoder=None, ra="hard_sigmoid"):
+    """mycode/Fov_seq2seq_2layers.py:232-272, mycode/3layers.py:223-275 (see oracle/keras_numpy.py)."""
+    if share_last_decoder is None:
+        share_last_decoder = n_layers == 3
+    xe, xd = enc_in, dec_in
+    for l in range(n_layers):
+        pe = "encoder%d" % l
+        pd = "decoder%d" % (l - 1 if (share_last_decoder and l == n_layers - 1) else l)
+        xe, h, c = lstm(xe, w[pe + "/kernel"], w[pe + "/recurrent_kernel"], w[pe + "/bias"], ra=ra)
+        xd, _, _ = lstm(xd, w[pd + "/kernel"], w[pd + "/recurrent_kernel"], w[pd + "/bias"], h, c, ra=ra)
+    return dense(xd, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+
+
 def others_lstm_span_whole_forward(w, enc_in, oth_in, dec_in, ra="hard_sigmoid"):
     B, Tenc = enc_in.shape[:2]
     Tall = oth_in.shape[1]

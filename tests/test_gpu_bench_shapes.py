@@ -576,3 +576,58 @@ def test_conv_two_accumulator_tiles_per_cta(case):
     yr.backward(t64(gy))
     assert np.abs(y2 - yr.detach().numpy()).max() < BF16_ATOL
     _grad_close(dx2, x64.grad.numpy(), "dx", rtol=2e-2)
+
+
+# ------------------------------------------------------------------ sibling models: 2- / 3-layer fc-LSTM stacks (32 units)
+
+@pytest.mark.parametrize("n_layers,B,tc", [(2, 21, False), (3, 9, False), (2, 140, True), (3, 600, True)])
+def test_stacked_fov_seq2seq(n_layers, B, tc, lstm_switches):
+    """mycode/Fov_seq2seq_2layers.py:232-272 / mycode/3layers.py:223-275 (32-unit LSTMs; the 3-layer graph re-uses
+    decoder_lstm2 for its third decoder layer): forward, loss, every gradient in Keras shapes and Adam steps against the
+    float64 oracle; the zero-padded units stay exactly zero; fp32 kernels and the tensor-core path (64-wide inputs of the
+    upper layers through the TMA-fed projection)."""
+    fov = _cuda()
+    lib = lstm_switches
+    rng = np.random.default_rng(n_layers * 100 + B)
+    w = _perturb(kn.init_stacked_fov_seq2seq(seed=3, n_layers=n_layers), 4, 0.05)
+    enc = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    tgt = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    m = fov.stacked_fov_seq2seq(n_layers=n_layers, weights=w).compile("Adam", "mean_squared_error")
+    assert m.count_params() == sum(v.size for v in w.values())
+    for a, k in zip(m.get_weights(), m.weight_order):
+        assert np.array_equal(a, w[k]), k                                   # Keras shapes in and out
+    lib.fov_debug_lstm_tc(1 if tc else -1)
+    wt = kt.to_torch(w)
+    fwd = lambda ww, a, b: kt.stacked_fov_seq2seq_forward(ww, a, b, n_layers=n_layers)
+    l_ref, outs_ref, g_ref = kt.loss_and_grads(fwd, wt, [t64(enc), t64(dec)], [t64(tgt)], [kt.mse])
+    got = m.predict_on_batch([enc, dec])
+    assert np.abs(got - outs_ref[0].numpy()).max() < 2e-5
+    np.testing.assert_allclose(got, kn.stacked_fov_seq2seq_forward({k: v.astype(np.float64) for k, v in w.items()},
+                                                                   enc.astype(np.float64), dec.astype(np.float64), n_layers),
+                               atol=2e-5)
+    xs, ys = m._to_dev([enc, dec]), m._to_dev([tgt])
+    m.gflat.zero_()
+    loss = m._loss(m._forward(xs, True), ys)
+    loss.backward()
+    assert abs(loss.item() - l_ref.item()) < 1e-5
+    for k in m.weight_order:
+        gpad = m.grads[k].cpu().numpy()
+        _grad_close(m._strip(k, gpad), g_ref[k].numpy(), k)
+        # gradients of the padding are exactly zero
+        mask = np.ones_like(gpad, bool)
+        real = m._pad(k, np.ones(m._keras_shapes[k], np.float32)) != 0
+        mask[real] = False
+        assert not gpad[mask].any(), k
+    if n_layers == 3:                                                       # decoder2 is created but never called (:266)
+        assert not m.grads["decoder2/kernel"].any()
+    opt = kt.KerasAdam(wt)
+    for step in range(5):
+        l_ref, _, g_ref = kt.loss_and_grads(fwd, wt, [t64(enc), t64(dec)], [t64(tgt)], [kt.mse])
+        opt.step(g_ref)
+        l = m.train_on_batch([enc, dec], tgt)
+        assert abs(l - l_ref.item()) < 5e-4 * max(1.0, abs(l_ref.item())), (step, l, l_ref.item())
+    for a, k in zip(m.get_weights(), m.weight_order):
+        np.testing.assert_allclose(a, wt[k].detach().numpy(), atol=2e-4, err_msg=k)
+    pad = m._pad("encoder1/recurrent_kernel", np.ones(m._keras_shapes["encoder1/recurrent_kernel"], np.float32)) == 0
+    assert not m.params["encoder1/recurrent_kernel"].detach().cpu().numpy()[pad].any()

@@ -866,3 +866,66 @@ def test_get_data_matches_reference_golden():
         assert not dups
         for a, name in zip(out, ("tar_past", "tar_fut", "tar_futin", "oth_past", "oth_fut", "oth_futin")):
             assert np.array_equal(a.cpu().numpy(), g["u%d_%s" % (num_user, name)].astype(np.float32)), name
+
+
+def test_m3_device_batches_equal_the_reference_preparation():
+    """pipeline.M3VideoBatches / fov_m3_batches (mean/var featuriser + windowing + target/others split fused on the
+    device) against the reference's host preparation restated by functions that are each pinned to the reference's own
+    outputs: get_data(pick_user=True) -> get_gt_target_xyz / _oth -> get_whole_span
+    (mycode/others_LSTM_span_whole.py:403-419,640-668).  The rows get_whole_span pairs ACROSS target runs (last window of a
+    run: its own TODO, :421-428) take the sequence's true future here; all other rows are identical."""
+    fov = _cuda()
+    from longterm360fov_b200 import data, ops
+    U, S, num_user = 5, 50, 5
+    raw = data.synth_trajectories(1, U, S, seed=3)[0]                       # (U, S*30, 3)
+    datadb = {"v": {c: raw[:, :, i].astype(np.float64) for i, c in enumerate("xyz")}}
+    tp, tf, _, op, of, _ = kn.get_data(datadb, pick_user=True, num_user=num_user)
+    N, n = tp.shape[0], S // 10 - 1
+    enc_ref = kn.get_gt_target_xyz(tp)
+    fut_ref = kn.get_gt_target_xyz(tf)
+    mv_o = lambda a: kn.get_gt_target_xyz_oth(a.transpose(1, 2, 0, 3).reshape(N, 10, num_user - 1, 30, 3))   # (N,10,K,6)
+    span = kn.get_whole_span(mv_o(op))                                      # (N,20,K,6), row i = [i ; i+1]
+    own = np.concatenate([mv_o(op), mv_o(of)], axis=1)                      # the sequence's own past + future
+    frames = torch.tensor(raw.reshape(U, S, 90), device="cuda")
+    (enc, oth, dec0), (fut, oth_t, enc_t) = fov.M3VideoBatches(num_user=num_user)(frames)
+    assert enc.shape == (N, 10, 6) and oth.shape == (N, 20, 1, num_user - 1, 6) and dec0.shape == (N, 1, 6)
+    np.testing.assert_allclose(enc.cpu().numpy(), enc_ref, atol=2e-6)
+    np.testing.assert_allclose(fut.cpu().numpy(), fut_ref, atol=2e-6)
+    np.testing.assert_allclose(dec0.cpu().numpy(), enc_ref[:, -1:], atol=2e-6)
+    got = oth.cpu().numpy()[:, :, 0]
+    inner = np.arange(N) % n != n - 1
+    np.testing.assert_allclose(got[inner], span[inner], atol=2e-6)
+    np.testing.assert_allclose(got, own, atol=2e-6)
+    assert oth_t.data_ptr() == oth.data_ptr() and enc_t.data_ptr() == enc.data_ptr()      # reconstruction targets alias
+    # truncation to a fixed batch and duplicate padding of the others (num_user - 1 > viewers - 1)
+    dups = []
+    b2 = fov.M3VideoBatches(num_user=8, limit=7, draw=lambda k: dups.append(k) or 0)(frames)
+    assert b2[0][1].shape == (7, 20, 1, 7, 6) and len(dups) == U * 3
+    idx = ops.others_index(U, 8, draw=lambda k: 0)
+    assert idx.shape == (U, 7) and (idx[0] == [1, 2, 3, 4, 1, 1, 1]).all()
+
+
+def test_fit_generator_with_device_batch_builder():
+    """fit_generator(raw video chunks, batch_builder=M3VideoBatches): same losses and weights as feeding the batches the
+    builder makes through train_on_batch."""
+    fov = _cuda()
+    from longterm360fov_b200 import data
+    U, S, num_user = 6, 60, 6
+    vids = [data.synth_trajectories(1, U, S, seed=s)[0].reshape(U, S, 90) for s in (1, 2)]
+    w = kn.init_others_lstm_span_whole(seed=3, num_user=num_user)
+    a = fov.others_lstm_span_whole(num_user=num_user, weights=w).compile("Adam", ["mean_squared_error"] * 3, [1, 1, 1])
+    b = fov.others_lstm_span_whole(num_user=num_user, weights=w).compile("Adam", ["mean_squared_error"] * 3, [1, 1, 1])
+    builder = fov.M3VideoBatches(num_user=num_user)
+    ref = []
+    for v in vids * 2:
+        xs, ys = builder(torch.tensor(v, device="cuda"))
+        ref.append(float(a.train_step_device(xs, ys).item()))
+
+    def gen():
+        while True:
+            for v in vids:
+                yield torch.from_numpy(v).pin_memory()
+    h = b.fit_generator(gen(), steps_per_epoch=4, epochs=1, batch_builder=builder)
+    assert abs(h.history["loss"][0] - float(np.mean(ref))) < 1e-6
+    for k in a.weight_order:
+        assert torch.allclose(a.params[k], b.params[k], rtol=0, atol=1e-6), k

@@ -290,3 +290,20 @@ def test_get_data_restatement_matches_reference_golden():
         assert not dups
         for a, name in zip(out, ("tar_past", "tar_fut", "tar_futin", "oth_past", "oth_fut", "oth_futin")):
             assert np.array_equal(a, g["u%d_%s" % (num_user, name)]), name
+
+
+def test_stacked_seq2seq_restatements_agree():
+    """2- / 3-layer fc-LSTM stacks (Fov_seq2seq_2layers.py:232-272, 3layers.py:223-275): NumPy and torch restatements."""
+    rng = np.random.default_rng(1)
+    for L in (2, 3):
+        w = kn.init_stacked_fov_seq2seq(seed=2, n_layers=L)
+        enc = rng.uniform(-1, 1, (4, 10, 6)); dec = rng.uniform(-1, 1, (4, 10, 6))
+        a = kn.stacked_fov_seq2seq_forward({k: v.astype(np.float64) for k, v in w.items()}, enc, dec, L)
+        b = kt.stacked_fov_seq2seq_forward(kt.to_torch(w), torch.tensor(enc), torch.tensor(dec), L).numpy()
+        np.testing.assert_allclose(a, b, atol=1e-10)
+        assert a.shape == (4, 10, 6)
+    # 3-layer graph: decoder layer 3 re-uses decoder1's weights (0-based), decoder2 is unused
+    w3 = kn.init_stacked_fov_seq2seq(seed=2, n_layers=3)
+    w3b = dict(w3); w3b["decoder2/kernel"] = w3["decoder2/kernel"] * 0
+    x64 = {k: v.astype(np.float64) for k, v in w3.items()}; y64 = {k: v.astype(np.float64) for k, v in w3b.items()}
+    assert np.array_equal(kn.stacked_fov_seq2seq_forward(x64, enc, dec, 3), kn.stacked_fov_seq2seq_forward(y64, enc, dec, 3))
