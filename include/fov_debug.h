@@ -31,6 +31,9 @@ void fov_debug_lstm_xproj(int mode);
 void fov_debug_convlstm_persistent(int enable);
 void fov_debug_convlstm_persistent_bwd(int enable);
 void fov_debug_wgrad_rows(int enable);
+/* ConvLSTM weight gradient accumulated inside the persistent BPTT kernel (1) or by the separate fused launch (0, the
+ * default: measured faster, see convlstm_seq_bwd_tc.cu) */
+void fov_debug_seq_bwd_wgrad(int enable);
 /* persistent BPTT without the stacked-N operand layout (bring-up) */
 void fov_debug_seq_bwd_nostack(int on);
 /* worker warps per image group of the persistent ConvLSTM / fc-LSTM forward (0 = default) */

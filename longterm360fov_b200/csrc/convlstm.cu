@@ -259,8 +259,11 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
       if (gr->dx && tc_convlstm_seq_bwd_supported(cfg, rT, &kT)) { seq = true; dx_fused = true; }
       else if (tc_convlstm_seq_bwd_supported(cfg, rT, nullptr)) seq = true;
     }
+    bool wg_fused = false;
     if (seq) {
+      wg_fused = tc_convlstm_seq_bwd_fuses_wgrad(cfg, io, gr, rT, dx_fused ? &kT : nullptr);
       if ((rc = tc_convlstm_seq_bwd(cfg, io, gr, rT, dx_fused ? &kT : nullptr, st))) return rc;
+      if (wg_fused) return FOV_OK;               // dZ never left the SM; gK / gR / gb are done
     } else {
       if ((rc = tc_conv_pack(rT, st))) return rc;
       rT.prepacked = 1;

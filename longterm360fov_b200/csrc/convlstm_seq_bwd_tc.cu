@@ -50,17 +50,27 @@ struct BwdParams {
   float* dx; long long x_b, x_t; int x_pix, Cin, Cp, Fp, dx_accumulate;
   const uint8_t* wpk2;                           // packed K^T (same k order), NULL: no dx
   uint32_t kb1_bytes, kb2_bytes;                 // bytes of one (k-block, term) tile of R^T / K^T
+  // fused weight gradient (template WG): gK / gR accumulate in TMEM over the whole sequence,
+  //   D[n][(tap, c)] += sum_pos dZ_t[pos][n] * [x_t | h_{t-1}][pos + tap][c]
+  // with the dZ operand rows that are already in shared memory as the MN-major A operand; x_t / h_{t-1} rows are staged
+  // next to them (MN-major B, the kw taps = overlapping N groups, LBO = one row: wgrad_rows_tc.cu)
+  const float* xin; long long xi_b, xi_t; int xi_pix, xi_cin;   // layer input (B,T,HW,Cin), strided
+  const float* hin; long long hi_b, hi_t; int hi_pix;           // hidden sequence (B,T,HW,F), strided: h_{t-1} = hin[t-1]
+  float *gK, *gR, *gB;
+  uint32_t x_off, h_off, wtab_off, x_term, h_term, x_desc_hi, h_desc_hi;
+  int x_cw, wg_col0, write_dz;
 };
 
 struct BwdBook {
-  uint64_t w_full, a_full, tmem_full;
+  uint64_t w_full, a_full, tmem_full, wg_done;
   uint32_t tmem_ptr;
 };
 
 __device__ unsigned long long g_bwd_timeline[8];
 
 // DXN: accumulator columns of the fused input gradient each worker thread reads back (0: no fused dx)
-template <int NS, int F, int DXN>
+// WG: the layer's weight gradient rides in this kernel (one CTA per SM variants only: it needs its own TMEM columns)
+template <int NS, int F, int DXN, bool WG>
 __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_kernel(const BwdParams p) {
   constexpr int N4F = 4 * F;
   constexpr int LPR = F / 4;                       // float4 per row of an F-channel tensor
@@ -79,6 +89,7 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
     mbar_init(smem_u32(&bk->w_full), 1);
     mbar_init(smem_u32(&bk->a_full), kWorkers);
     mbar_init(smem_u32(&bk->tmem_full), 1);
+    mbar_init(smem_u32(&bk->wg_done), 1);
     fence_mbar_init();
     // Every MMA of a timestep's chain, fully resolved once (A/B descriptor low words, instruction descriptor,
     // accumulate flag): the issue loop is one 16-byte table read + one tcgen05.mma.  A lone thread computing
@@ -117,6 +128,11 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
   // dZ rows of pad positions stay zero for the whole sequence
   for (uint32_t i = (uint32_t)tid * 16u; i < (uint32_t)p.nch * p.chunk_bytes; i += (uint32_t)kBThr * 16u)
     *reinterpret_cast<uint4*>(smem + p.act_off + i) = make_uint4(0u, 0u, 0u, 0u);
+  if (WG) {                                       // x / h operand tiles: pad rows and unused channel slots stay zero
+    const uint32_t nb = NS * (p.x_term + p.h_term);
+    for (uint32_t i = (uint32_t)tid * 16u; i < nb; i += (uint32_t)kBThr * 16u)
+      *reinterpret_cast<uint4*>(smem + p.x_off + i) = make_uint4(0u, 0u, 0u, 0u);
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -153,6 +169,62 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
       }
       so[j] = (uint32_t)(m - p.minshift) * (uint32_t)p.row_bytes;      // my row of the dZ operand region
     }
+    // fused weight gradient: my (row, column group) items of the x_t / h_{t-1} operand tiles - 128 rows x 8 groups
+    // (float2 of x, float4 of h) over 256 threads = 4 rows per thread, one column group
+    constexpr int XH = WG ? 4 : 1;
+    int off_xi[XH], off_hi[XH];
+    uint32_t sx[XH], sh[XH];
+    float2 vx[XH];
+    float4 vhh[XH];
+    if (WG) {
+      // bias gradient for free: channel x_cw - 1 of the x tile is a constant 1 on every real pixel row (written once,
+      // the per-step stores only touch channels < Cin), so accumulator column (centre tap, x_cw - 1) = sum_pos dZ[pos][n]
+      if (tid < kRows && tid < npos) {
+        const int m = tid;
+        const int bi = m / p.HpWp, rem = m - bi * p.HpWp;
+        const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
+        const int y = yp - p.PLh, x = xp - p.PLw;
+        if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && b0 + bi < p.B) {
+          const uint32_t a = (uint32_t)(m - p.minshift) * (uint32_t)(p.x_cw * 2) + (uint32_t)(p.x_cw - 1) * 2u;
+          const uint32_t xm = p.x_cw * 2 == 128 ? 7u : (p.x_cw * 2 == 64 ? 3u : 1u);
+          *reinterpret_cast<uint16_t*>(smem + p.x_off + (a ^ (((a >> 7) & xm) << 4))) = 0x3F80u;     // bf16 1.0, term 0
+        }
+      }
+      const int cgp = tid & 7;
+#pragma unroll
+      for (int j = 0; j < XH; ++j) {
+        const int m = (tid >> 3) + j * 32;
+        off_xi[j] = off_hi[j] = -1;
+        if (m < npos) {
+          const int bi = m / p.HpWp, rem = m - bi * p.HpWp;
+          const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
+          const int y = yp - p.PLh, x = xp - p.PLw;
+          const int b = b0 + bi;
+          if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && b < p.B) {
+            const int pix = y * p.W + x;
+            if (cgp * 2 < p.xi_cin) off_xi[j] = (int)((long long)b * p.xi_b + (long long)pix * p.xi_pix) + cgp * 2;
+            if (cgp * 4 < F) off_hi[j] = (int)((long long)b * p.hi_b + (long long)pix * p.hi_pix) + cgp * 4;
+          }
+        }
+        const uint32_t r = (uint32_t)(m - p.minshift);
+        const uint32_t ax = r * (uint32_t)(p.x_cw * 2) + (uint32_t)cgp * 4u;     // float2 -> 2 bf16 = 4 bytes
+        const uint32_t xm = p.x_cw * 2 == 128 ? 7u : (p.x_cw * 2 == 64 ? 3u : 1u);
+        sx[j] = ax ^ (((ax >> 7) & xm) << 4);
+        const uint32_t ah = r * (uint32_t)(F * 2) + (uint32_t)cgp * 8u;           // float4 -> 4 bf16 = 8 bytes
+        const uint32_t hm = F * 2 == 128 ? 7u : (F * 2 == 64 ? 3u : 1u);
+        sh[j] = ah ^ (((ah >> 7) & hm) << 4);
+      }
+    }
+    auto load_xh = [&](int t) {
+#pragma unroll
+      for (int j = 0; j < XH; ++j) {
+        vx[j] = make_float2(0.f, 0.f);
+        vhh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (off_xi[j] >= 0) vx[j] = __ldg(reinterpret_cast<const float2*>(p.xin + (long long)t * p.xi_t + off_xi[j]));
+        if (off_hi[j] >= 0 && t > 0)
+          vhh[j] = __ldg(reinterpret_cast<const float4*>(p.hin + (long long)(t - 1) * p.hi_t + off_hi[j]));
+      }
+    };
     float4 dc[NIT];
 #pragma unroll
     for (int j = 0; j < NIT; ++j) {
@@ -218,7 +290,7 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
       }
     };
     const bool dbg = (p.dbg & 1) && blockIdx.x == 0 && tid == 0;
-    long long tw = 0, tcmp = 0, k0 = 0, k1 = 0;
+    long long tw = 0, tcmp = 0, k0 = 0, k1 = 0, twg = 0, tepi = 0;
     const long long t_begin = clock64();
 
     float4 vg[NIT][4], vc[NIT], vp[NIT], vh[NIT];
@@ -243,6 +315,7 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
     };
 #pragma unroll
     for (int j = 0; j < NIT; ++j) load_item(p.T - 1, j);
+    if (WG) load_xh(p.T - 1);
     for (int t = p.T - 1; t >= 0; --t) {
       // ---- dh_rec of this step: dhT at the last step, else the accumulator of the GEMM issued at step t+1 ----
       float4 dr[NIT];
@@ -318,10 +391,22 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
         }
         dc[j] = make_float4(dcv[0], dcv[1], dcv[2], dcv[3]);
 #pragma unroll
+        for (int gi = 0; gi < 4; ++gi) vg[j][gi] = make_float4(dz[gi][0], dz[gi][1], dz[gi][2], dz[gi][3]);
+      }
+      // the weight-gradient MMAs of step t+1 still read the operand rows: they ran under the gate algebra above
+      if (WG && t < p.T - 1) {
+        const long long w0 = dbg ? clock64() : 0;
+        mbar_wait(smem_u32(&bk->wg_done), (uint32_t)(p.T - 2 - t) & 1u);
+        if (dbg) twg += clock64() - w0;
+      }
+#pragma unroll
+      for (int j = 0; j < NIT; ++j) {
+        const bool ok = off_g[j] >= 0;
+#pragma unroll
         for (int gi = 0; gi < 4; ++gi) {
-          const float4 z4 = make_float4(dz[gi][0], dz[gi][1], dz[gi][2], dz[gi][3]);
+          const float4 z4 = vg[j][gi];
           if (!ok) continue;
-          *reinterpret_cast<float4*>(gz + off_g[j] + gi * F) = z4;
+          if (!WG || p.write_dz) *reinterpret_cast<float4*>(gz + off_g[j] + gi * F) = z4;
           // bf16 terms into the operand rows: channel gi*F + ch of chunk (channel / 64)
           const int zc = gi * F + ch;
           const uint32_t a0 = so[j] + (uint32_t)(zc & 63) * 2u;
@@ -333,13 +418,34 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
           for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(dstc + s * p.term_bytes + sw) = pk[s];
         }
       }
-      if (t > 0 || p.wpk2) {
+      if (WG) {                                    // x_t / h_{t-1} rows of the weight-gradient B operand
+#pragma unroll
+        for (int j = 0; j < XH; ++j) {
+          if (off_xi[j] >= 0) {
+            float r0 = vx[j].x, r1 = vx[j].y;
+#pragma unroll
+            for (int s_ = 0; s_ < NS; ++s_) {
+              const uint32_t pk = pack_bf16x2(r0, r1);
+              *reinterpret_cast<uint32_t*>(smem + p.x_off + s_ * p.x_term + sx[j]) = pk;
+              r0 -= __uint_as_float(pk << 16); r1 -= __uint_as_float(pk & 0xffff0000u);
+            }
+          }
+          if (off_hi[j] >= 0) {
+            uint2 pk[NS];
+            split4<NS>(vhh[j], pk);
+#pragma unroll
+            for (int s_ = 0; s_ < NS; ++s_) *reinterpret_cast<uint2*>(smem + p.h_off + s_ * p.h_term + sh[j]) = pk[s_];
+          }
+        }
+      }
+      if (t > 0 || p.wpk2 || WG) {
         fence_proxy_async_smem();
         mbar_arrive(smem_u32(&bk->a_full));
       }
       if (t > 0) {                                 // in flight while the GEMM of this step runs
 #pragma unroll
         for (int j = 0; j < NIT; ++j) load_item(t - 1, j);
+        if (WG) load_xh(t - 1);
       }
       if (DXN > 0 && t < p.T - 1) dx_store(t + 1);
       if (t == 0 && p.dc0) {
@@ -354,7 +460,39 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
       tc_fence_after();
       if (DXN > 0) { dx_read(); dx_store(0); }
     }
-    if (dbg) { g_bwd_timeline[0] = tw; g_bwd_timeline[1] = tcmp; g_bwd_timeline[2] = clock64() - t_begin; }
+    if (WG) {
+      // ---- partial gK / gR / gb of this CTA -> global (lanes = consecutive n: coalesced red.global.add) ----
+      const long long e0 = dbg ? clock64() : 0;
+      mbar_wait(smem_u32(&bk->wg_done), (uint32_t)(p.T - 1) & 1u);
+      tc_fence_after();
+      const int n = q * 32 + lane;
+      const int kw = p.kw;
+      const int xcols = kw * p.x_cw, hcols = kw * F;
+      for (int c0 = half * 8; c0 < xcols + hcols; c0 += 16) {
+        float v[8];
+        tmem_ld8(t_row + (uint32_t)(p.wg_col0 + c0), v);
+        tmem_ld_wait();
+        if (n < N4F) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            if (c < xcols) {
+              const int tap = c / p.x_cw, ci = c - tap * p.x_cw;
+              if (ci < p.xi_cin) atomicAdd(p.gK + ((size_t)tap * p.xi_cin + ci) * N4F + n, v[j]);
+              else if (ci == p.x_cw - 1 && tap == p.pad_w && p.gB) atomicAdd(p.gB + n, v[j]);      // the ones channel
+            } else {
+              const int ch_ = c - xcols, tap = ch_ / F, cf = ch_ - tap * F;
+              atomicAdd(p.gR + ((size_t)tap * F + cf) * N4F + n, v[j]);
+            }
+          }
+        }
+      }
+      if (dbg) tepi = clock64() - e0;
+    }
+    if (dbg) {
+      g_bwd_timeline[0] = tw; g_bwd_timeline[1] = tcmp; g_bwd_timeline[2] = clock64() - t_begin;
+      g_bwd_timeline[3] = twg; g_bwd_timeline[6] = tepi;
+    }
   } else if (warp == kBWWarp) {
     // ---------------- weights, once: B tile of a (k-block, term) = [Fp rows of R^T | Cp rows of K^T] x 128 B ----
     // Copied in 16-row (2048-byte) pieces, one piece per lane and round: larger pieces into the interleaved layout
@@ -379,13 +517,44 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
       mbar_wait(smem_u32(&bk->w_full), 0);
       const bool dbg = (p.dbg & 1) && blockIdx.x == 0;
       long long mw = 0, mi = 0;
-      const int t_last = p.wpk2 ? 0 : 1;
+      // fused weight gradient: the MMAs of one step, resolved once: A = dZ rows (MN-major, M = 4F channels, K = 16
+      // positions), B = x / h rows with the kw taps as overlapping N groups
+      int nwg = 0;
+      uint4* wtab = reinterpret_cast<uint4*>(smem + p.wtab_off);
+      if (WG) {
+        const uint32_t a_lbo = p.nch > 1 ? p.chunk_bytes : 0u;
+        const int nk16 = (p.G * p.HpWp + 15) / 16;                 // K steps that hold positions of this group
+        for (int k16 = 0; k16 < nk16; ++k16)
+          for (int sum = NS - 1; sum >= 0; --sum)
+            for (int sa = 0; sa <= sum; ++sa) {
+              const int sb = sum - sa;
+              const uint64_t ad = smem_desc_sw128(base + p.act_off + (uint32_t)sa * p.term_bytes +
+                                                      (uint32_t)(-p.minshift + k16 * 16) * 128u, a_lbo, 1024);
+              const uint32_t xrow = (uint32_t)(p.x_cw * 2), hrow = (uint32_t)(F * 2);
+              const uint64_t bx = desc_at_lbo(p.x_desc_hi, base + p.x_off + (uint32_t)sb * p.x_term + (uint32_t)(k16 * 16) * xrow, xrow);
+              const uint64_t bh = desc_at_lbo(p.h_desc_hi, base + p.h_off + (uint32_t)sb * p.h_term + (uint32_t)(k16 * 16) * hrow, hrow);
+              wtab[nwg++] = make_uint4((uint32_t)ad, (uint32_t)bx, idesc_bf16_f32(kRows, p.kw * p.x_cw, 1, 1), (uint32_t)p.wg_col0);
+              wtab[nwg++] = make_uint4((uint32_t)ad, (uint32_t)bh, idesc_bf16_f32(kRows, p.kw * F, 1, 1),
+                                       (uint32_t)(p.wg_col0 + p.kw * p.x_cw) | 0x80000000u);
+            }
+      }
+      const uint32_t a_hi_wg = (uint32_t)(smem_desc_sw128(0, 0, 1024) >> 32);
+      const int t_last = (p.wpk2 || WG) ? 0 : 1;
       for (int t = p.T - 1; t >= t_last; --t) {
         const long long q0 = clock64();
         mbar_wait(smem_u32(&bk->a_full), (uint32_t)(p.T - 1 - t) & 1u);
         tc_fence_after();
         const long long q1 = clock64();
         mw += q1 - q0;
+        if (WG && t == 0 && !p.wpk2) {             // no dh_rec / dx chain at the first timestep: weight gradient only
+          for (int i = 0; i < nwg; ++i) {
+            const uint4 m = wtab[i];
+            umma_bf16(tmem_d + (m.w & 0x7fffffffu), ((uint64_t)a_hi_wg << 32) | m.x,
+                      ((uint64_t)((m.w >> 31) ? p.h_desc_hi : p.x_desc_hi) << 32) | m.y, m.z, (t == p.T - 1 && i < 2) ? 0u : 1u);
+          }
+          umma_commit(smem_u32(&bk->wg_done));
+          continue;
+        }
         // stacked terms: the bf16 terms of a weight tile are adjacent in shared memory, so ONE MMA with
         // N = (NS - sa) * BLOCK_N multiplies A term sa by the B terms 0 .. NS-1-sa (NS MMAs per k step instead of
         // NS (NS + 1) / 2; product (sa, sb) lands in accumulator columns [sb * BLOCK_N, +BLOCK_N), summed at read-back)
@@ -395,6 +564,14 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
           umma_bf16(tmem_d, ((uint64_t)p.desc_hi << 32) | m.x, ((uint64_t)kDescHi128 << 32) | m.y, m.z, m.w);
         }
         umma_commit(smem_u32(&bk->tmem_full));
+        if (WG) {                                  // after the chain: these run while the workers do the next step's gate algebra
+          for (int i = 0; i < nwg; ++i) {
+            const uint4 m = wtab[i];
+            umma_bf16(tmem_d + (m.w & 0x7fffffffu), ((uint64_t)a_hi_wg << 32) | m.x,
+                      ((uint64_t)((m.w >> 31) ? p.h_desc_hi : p.x_desc_hi) << 32) | m.y, m.z, (t == p.T - 1 && i < 2) ? 0u : 1u);
+          }
+          umma_commit(smem_u32(&bk->wg_done));
+        }
         mi += clock64() - q1;
       }
       if (dbg) { g_bwd_timeline[4] = mw; g_bwd_timeline[5] = mi; }
@@ -408,12 +585,14 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
 struct BwdPlan {
   TcStepPlan sp, sp2;
   int G, Fp, Cp, fuse_dx, stack;
+  int wg, x_cw;                                  // fused weight gradient
+  uint32_t x_off, h_off, wtab_off, x_term, h_term, wg_col0;
   size_t w_bytes;
   uint32_t chunk_bytes, act_off, dh_off, mma_off, data_bytes, tmem_cols;
   size_t smem_bytes;
 };
 
-int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT, BwdPlan* out) {
+int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT, BwdPlan* out, bool want_wg = false) {
   BwdPlan pl{};
   int rc = tc_conv_step_plan(rT, &pl.sp);
   if (rc) return rc;
@@ -449,6 +628,31 @@ int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT, BwdP
   FOV_CHECK_ARG(pl.smem_bytes <= 227 * 1024, "persistent BPTT: weights + operands exceed shared memory");
   pl.stack = (sp.NS > 1 && sp.NS * (pl.Fp + pl.Cp) <= 256) ? 1 : 0;
   pl.tmem_cols = tmem_cols_for((pl.stack ? sp.NS : 1) * (pl.Fp + pl.Cp));
+  // Fused weight gradient: only the one-CTA-per-SM variant (F = 32: its accumulators need kw * (x_cw + F) more TMEM
+  // columns, which two resident CTAs cannot both have), 1 x kw kernels, no fused dx, an even input width <= 16.
+  pl.wg = 0;
+  if (want_wg && !kT && F == 32 && c->kh == 1 && c->dil_w == 1 && c->Cin <= 14 && c->Cin % 2 == 0 &&
+      c->x_pix_stride % 2 == 0 && c->x_b_stride % 2 == 0 && c->x_t_stride % 2 == 0) {
+    pl.x_cw = 16;
+    const uint32_t base_cols = (uint32_t)((pl.stack ? sp.NS : 1) * (pl.Fp + pl.Cp));
+    const uint32_t cols = base_cols + (uint32_t)(c->kw * (pl.x_cw + F));
+    const uint32_t R = (uint32_t)sg.R;
+    pl.x_term = (R * (uint32_t)(pl.x_cw * 2) + 1023u) / 1024u * 1024u;
+    pl.h_term = (R * (uint32_t)(F * 2) + 1023u) / 1024u * 1024u;
+    pl.x_off = pl.data_bytes;
+    pl.h_off = pl.x_off + (uint32_t)sp.NS * pl.x_term;
+    pl.wtab_off = pl.h_off + (uint32_t)sp.NS * pl.h_term;
+    const uint32_t nent = (uint32_t)(((pl.G * sp.Hp * sp.Wp + 15) / 16) * (sp.NS * (sp.NS + 1) / 2) * 2);
+    const uint32_t data2 = (pl.wtab_off + nent * 16u + 1023u) / 1024u * 1024u;
+    if (cols <= 512 && c->kw * (pl.x_cw + F) <= 448 && c->kw * pl.x_cw <= 256 && c->kw * F <= 256 &&
+        data2 + sizeof(BwdBook) + 1024 <= 227 * 1024) {
+      pl.wg = 1;
+      pl.wg_col0 = base_cols;
+      pl.tmem_cols = tmem_cols_for((int)cols);
+      pl.data_bytes = data2;
+      pl.smem_bytes = pl.data_bytes + sizeof(BwdBook) + 1024;
+    }
+  }
   FOV_CHECK_ARG(!pl.fuse_dx || (long long)c->B * c->x_b_stride < (1LL << 31), "input too large for 32-bit offsets");
   const long long HW = (long long)c->H * c->W;
   FOV_CHECK_ARG((long long)c->B * c->T * HW * 4 * F < (1LL << 31) && (long long)c->B * c->h_b_stride < (1LL << 31),
@@ -457,11 +661,11 @@ int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT, BwdP
   return FOV_OK;
 }
 
-template <int NS, int F, int DXN>
+template <int NS, int F, int DXN, bool WG = false>
 int launch_bwd(const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t st) {
   static FovPerDevice configured;
   if (!configured.done()) {
-    cudaError_t e = cudaFuncSetAttribute(convlstm_seq_bwd_kernel<NS, F, DXN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(convlstm_seq_bwd_kernel<NS, F, DXN, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) {
       fov_set_error("convlstm_seq_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -469,7 +673,7 @@ int launch_bwd(const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t st)
     }
     configured.mark();
   }
-  convlstm_seq_bwd_kernel<NS, F, DXN><<<grid, kBThr, pl.smem_bytes, st>>>(p);
+  convlstm_seq_bwd_kernel<NS, F, DXN, WG><<<grid, kBThr, pl.smem_bytes, st>>>(p);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
@@ -484,6 +688,7 @@ int launch_bwd_dx(const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t 
 }
 template <int NS>
 int launch_bwd_f(int F, const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t st) {
+  if (pl.wg) return launch_bwd<NS, 32, 0, true>(p, pl, grid, st);
   switch (F) {
     case 8: return launch_bwd_dx<NS, 8>(p, pl, grid, st);
     case 16: return launch_bwd_dx<NS, 16>(p, pl, grid, st);
@@ -494,7 +699,14 @@ int launch_bwd_f(int F, const BwdParams& p, const BwdPlan& pl, int grid, cudaStr
 
 }  // namespace
 
-static int g_bwd_disable = 0, g_bwd_dbg = 0, g_bwd_nostack = 0;
+// Weight gradient inside the persistent BPTT kernel (template WG): OFF by default.  Measured on B200 (M3 layer 0,
+// B = 8880, bf16x2, scripts/bptt_timeline.py): fused 5.28 ms vs 3.10 ms BPTT + 1.81 ms separate weight-gradient launch =
+// 4.91 ms.  dZ stays on chip (3.0 GB of writes and 3.5 GB of reads less per step), but the 42 extra MN-major MMAs per
+// timestep share the shared-memory port with the workers' transposes and operand stores, whose phase grows from 12.5 k to
+// 20 k cycles per step (the workers, not the MMA thread, are the critical path of this kernel).  Kept behind the switch,
+// parity-tested (tests/test_gpu_bench_shapes.py), as the starting point for a version with the operands in TMEM.
+static int g_bwd_disable = 0, g_bwd_dbg = 0, g_bwd_nostack = 0, g_bwd_no_wg = 1;
+extern "C" void fov_debug_seq_bwd_wgrad(int enable) { g_bwd_no_wg = !enable; }
 extern "C" void fov_debug_seq_bwd_nostack(int on) { g_bwd_nostack = on; }
 extern "C" void fov_debug_convlstm_persistent_bwd(int enable) { g_bwd_disable = !enable; }
 extern "C" void fov_debug_seq_bwd_enable(int on) { g_bwd_dbg = on; }
@@ -510,13 +722,27 @@ bool tc_convlstm_seq_bwd_supported(const fov_convlstm_cfg* c, const TcConv& rT, 
   return ok;
 }
 
+// does the persistent BPTT of this layer also produce its weight gradients (g_kernel / g_recurrent / g_bias)?
+bool tc_convlstm_seq_bwd_fuses_wgrad(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const fov_convlstm_grads* gr,
+                                     const TcConv& rT, const TcConv* kT) {
+  // not with a fused dx (TMEM columns), not when an unfused dx convolution still needs dZ in HBM, not with an initial state
+  if (g_bwd_disable || g_bwd_no_wg || kT || gr->dx || io->h0 || !gr->g_kernel || !gr->g_recurrent) return false;
+  if ((uintptr_t)io->x % 8 != 0 || (uintptr_t)io->hseq % 16 != 0) return false;
+  BwdPlan pl;
+  const bool ok = bwd_plan(c, rT, kT, &pl, true) == FOV_OK && pl.wg;
+  fov_set_error("");
+  return ok;
+}
+
 // rT: the recurrent backward-data convolution of this layer (convlstm.cu rec_bwd_conv) with ws = its packed-weight
 // workspace.  Runs the whole reverse time loop: gates (in: activated gates, out: dZ), optional dc0.  dh0 is not
-// produced (callers that need it use the per-timestep path).
+// produced (callers that need it use the per-timestep path).  When tc_convlstm_seq_bwd_fuses_wgrad() the weight
+// gradients are accumulated too and dZ is not written to HBM (nothing reads it afterwards).
 int tc_convlstm_seq_bwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const fov_convlstm_grads* gr,
                         const TcConv& rT, const TcConv* kT, cudaStream_t st) {
+  const bool want_wg = tc_convlstm_seq_bwd_fuses_wgrad(c, io, gr, rT, kT);
   BwdPlan pl;
-  int rc = bwd_plan(c, rT, kT, &pl);
+  int rc = bwd_plan(c, rT, kT, &pl, want_wg);
   if (rc) return rc;
   if ((rc = tc_conv_pack(rT, st))) return rc;
   if (kT && (rc = tc_conv_pack(*kT, st))) return rc;
@@ -543,6 +769,19 @@ int tc_convlstm_seq_bwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, co
   }
   p.chunk_bytes = pl.chunk_bytes; p.act_off = pl.act_off; p.dh_off = pl.dh_off; p.mma_off = pl.mma_off; p.data_bytes = pl.data_bytes;
   p.tmem_cols = pl.tmem_cols;
+  if (pl.wg) {
+    p.xin = io->x; p.xi_b = c->x_b_stride; p.xi_t = c->x_t_stride; p.xi_pix = c->x_pix_stride; p.xi_cin = c->Cin;
+    p.hin = io->hseq; p.hi_b = c->h_b_stride; p.hi_t = c->h_t_stride; p.hi_pix = c->h_pix_stride;
+    p.gK = gr->g_kernel; p.gR = gr->g_recurrent; p.gB = gr->g_bias;
+    p.x_off = pl.x_off; p.h_off = pl.h_off; p.wtab_off = pl.wtab_off; p.x_term = pl.x_term; p.h_term = pl.h_term;
+    p.x_cw = pl.x_cw; p.wg_col0 = (int)pl.wg_col0; p.write_dz = 0;
+    auto mn_hi = [](int row_bytes) {           // MN-major descriptor high word: SBO = 8 rows, version 1, swizzle = row width
+      const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+      return ((uint32_t)(8 * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+    };
+    p.x_desc_hi = mn_hi(pl.x_cw * 2); p.h_desc_hi = mn_hi(F * 2);
+    FOV_CHECK_ARG((long long)c->B * c->x_b_stride < (1LL << 31), "input too large for 32-bit offsets");
+  }
   p.wpk = reinterpret_cast<const uint8_t*>(((uintptr_t)rT.ws + 255) & ~(uintptr_t)255);
   p.gates = io->gates; p.z_t = (long long)HW * 4 * F; p.z_b = p.z_t * c->T;
   p.cseq = io->cseq; p.c_t = (long long)HW * F; p.c_b = p.c_t * c->T;

@@ -118,6 +118,9 @@ int tc_convlstm_seq_fwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, co
 bool tc_convlstm_seq_bwd_supported(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT);
 int tc_convlstm_seq_bwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const fov_convlstm_grads* gr,
                         const TcConv& rT, const TcConv* kT, cudaStream_t st);
+// true: that launch also accumulates g_kernel / g_recurrent / g_bias (no separate weight-gradient launch, dZ stays on chip)
+bool tc_convlstm_seq_bwd_fuses_wgrad(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const fov_convlstm_grads* gr,
+                                     const TcConv& rT, const TcConv* kT);
 
 // Tensor-core weight gradient: gw[(tap*Cin+ci)*Cout+n] += sum_pixels x(pixel+tap, ci) * dy(pixel, n),
 // gbias[n] += sum_pixels dy(pixel, n).  Both operands are read in their natural NHWC layout and

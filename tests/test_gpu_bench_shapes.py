@@ -631,3 +631,51 @@ def test_stacked_fov_seq2seq(n_layers, B, tc, lstm_switches):
         np.testing.assert_allclose(a, wt[k].detach().numpy(), atol=2e-4, err_msg=k)
     pad = m._pad("encoder1/recurrent_kernel", np.ones(m._keras_shapes["encoder1/recurrent_kernel"], np.float32)) == 0
     assert not m.params["encoder1/recurrent_kernel"].detach().cpu().numpy()[pad].any()
+
+
+# ------------------------------------------------------------------ ConvLSTM weight gradient inside the persistent BPTT
+
+@pytest.mark.parametrize("B,T", [(1, 1), (4, 20), (131, 7), (7, 2)])
+@pytest.mark.parametrize("mode", ["bf16x2", "bf16x3", "bf16"])
+def test_convlstm_bptt_fused_weight_gradient(B, T, mode):
+    """Layer 0 of the others branch (Cin = 6, F = 32, kernel (1,5)): gK, gR and gb accumulated in TMEM inside the
+    persistent BPTT kernel (dZ never leaves the SM; the bias gradient rides on a constant-1 input channel) against the
+    separate fused weight-gradient launch on the same saved tensors, and against the float64 oracle.  One launch fewer.
+    (Opt-in through fov_debug_seq_bwd_wgrad(1): measured slower than the two-launch form on B200.)"""
+    fov = _cuda()
+    from longterm360fov_b200 import ops, _lib
+    lib = _lib.load()
+    ops.set_math(mode)
+    rng = np.random.default_rng(B * 31 + T)
+    H, W, Cin, F = 1, 33, 6, 32
+    x = rng.normal(size=(B, T, H, W, Cin)).astype(np.float32)
+    w = ((rng.normal(size=(1, 5, Cin, 4 * F)) * 0.3).astype(np.float32),
+         (rng.normal(size=(1, 5, F, 4 * F)) * 0.3).astype(np.float32), (rng.normal(size=4 * F) * 0.1).astype(np.float32))
+    gcat = rng.normal(size=(B, T, H, W, F)).astype(np.float32)
+
+    def run(fused):
+        lib.fov_debug_seq_bwd_wgrad(int(fused))
+        try:
+            xt = torch.tensor(x, device="cuda")                        # no gradient w.r.t. the input: the model's case
+            wt = [tuple(torch.tensor(a, device="cuda", requires_grad=True) for a in w)]
+            sinks = [tuple(torch.zeros_like(a) for a in wt[0])]
+            n0 = lib.fov_launch_count()
+            cat, _ = ops.convlstm_stack(xt, wt, None, sinks, (1, 1), "hard_sigmoid", True)
+            (cat * torch.tensor(gcat, device="cuda")).sum().backward()
+            torch.cuda.synchronize()
+            return [g.cpu().numpy() for g in sinks[0]], int(lib.fov_launch_count() - n0)
+        finally:
+            lib.fov_debug_seq_bwd_wgrad(0)              # the default: separate launch (measured faster)
+
+    g1, n1 = run(True)
+    g0, n0 = run(False)
+    # three bf16 terms per operand do not leave room for the extra operand tiles: that mode keeps the separate launch
+    assert n1 == (n0 if mode == "bf16x3" else n0 - 1), (n1, n0)
+    d64 = lambda a, rg=True: torch.tensor(a, dtype=torch.float64, requires_grad=rg)
+    w64 = {"L0/kernel": d64(w[0]), "L0/recurrent_kernel": d64(w[1]), "L0/bias": d64(w[2])}
+    catr, _ = kt.convlstm_stack(w64, d64(x, False), "L", None, (1, 1), n_layers=1)
+    (catr * d64(gcat, False)).sum().backward()
+    rt = 0.1 if mode == "bf16" else 2e-3
+    for j, n in enumerate(("kernel", "recurrent_kernel", "bias")):
+        _grad_close(g1[j], g0[j], "fused vs separate L0/%s" % n, rtol=2e-2 if mode == "bf16" else 2e-4)
+        _grad_close(g1[j], w64["L0/%s" % n].grad.numpy(), "L0/%s" % n, rtol=rt)
