@@ -27,6 +27,7 @@ extern "C" void fov_debug_lstm_bptt_tc(int on) { g_lstm_bptt_tc = on; }
 
 namespace {
 
+constexpr int kTcTrainMinB = 6144;   // sequences from which the tensor-core training path (forward + BPTT) wins
 constexpr int kH = 64;     // latent_dim
 constexpr int kG = 256;    // 4H
 constexpr int kNT = 256;   // threads per CTA
@@ -468,9 +469,11 @@ extern "C" int fov_lstm_seq2seq_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
   cudaStream_t st = (cudaStream_t)stream;
   // tensor-core forward (lstm_seq2seq_tc.cu): 128-sequence tiles.  Measured on B200, AR decode of the mu/var model:
   // B=512..2048 0.088 ms vs 0.096 ms fp32 (both latency bound), B=3072 0.088 vs 0.133, B=75776 0.29 vs 1.47 ms.  In
-  // training mode the row-per-thread stores of the saved tensors need every SM busy to pay off (B=8880: equal).
+  // training mode the thread-per-row saved tensors travel as 256-bit stores / loads (one full sector per lane); whole
+  // train step of the mu/var model, tensor-core forward + BPTT vs fp32 kernels (scripts/lstm_train_threshold.py):
+  // B=4096 0.88 vs 0.64 ms, B=8192 0.98 vs 1.17, B=16384 1.12 vs 1.91, B=37888 2.04 vs 3.60.
   const bool wide = (cfg->T_enc > 0 && cfg->in_enc > 16) || (cfg->T_dec > 0 && cfg->in_dec > 16);
-  const int tc_min_B = (cfg->training && !wide) ? 128 * fov_num_sms() : 512;
+  const int tc_min_B = (cfg->training && !wide) ? kTcTrainMinB : 512;
   if (cfg->math != FOV_MATH_FP32 && g_lstm_tc_mode >= 0 && lstm_tc_supported(cfg) &&
       (g_lstm_tc_mode > 0 || cfg->B >= tc_min_B) &&
       (!wide || (io->ws != nullptr && (uintptr_t)io->x_enc % 16 == 0 && (uintptr_t)io->x_dec % 16 == 0)))
@@ -511,10 +514,10 @@ extern "C" int fov_lstm_seq2seq_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
   const int bt = 4 * spt, grid = (cfg->B + bt - 1) / bt;
   const size_t smem = bwd_smem_bytes(spt);
   const bool hsb = cfg->rec_act == FOV_REC_HARD_SIGMOID;
-  // tensor-core BPTT (lstm_seq2seq_tc.cu): 128-sequence tiles, dh_rec = dZ x U^T on tcgen05.  One 4-warp CTA per SM:
-  // it pays once every SM has a tile (mu/var model train step, B=37888: 2.66 vs 3.59 ms; B=8880, 70 CTAs: equal)
+  // tensor-core BPTT (lstm_seq2seq_tc.cu): 128-sequence tiles, dh_rec = dZ x U^T on tcgen05, saved tensors by 256-bit
+  // loads (crossover with the fp32 kernel near 6 k sequences, see the forward dispatch above)
   if (cfg->math != FOV_MATH_FP32 && g_lstm_tc_mode >= 0 && g_lstm_bptt_tc && lstm_tc_bwd_supported(cfg) &&
-      (g_lstm_tc_mode > 0 || cfg->B >= 128 * fov_num_sms()))
+      (g_lstm_tc_mode > 0 || cfg->B >= kTcTrainMinB))
     rc = lstm_tc_bwd(&P.cfg, w, io, g, st);
   else if (spt == 4)
     rc = hsb ? launch(lstm_seq2seq_bwd_kernel<4, FOV_REC_HARD_SIGMOID>, P, grid, smem, st)

@@ -105,10 +105,21 @@ __device__ __forceinline__ void store16(float* dst, const float (&v)[16], int ve
   }
 }
 
+// one thread = one row here, so a warp's store touches 32 different rows: a 256-bit store (sm_100: STG.E.256) fills a whole
+// 32-byte sector per lane where two 128-bit stores write two half sectors
+__device__ __forceinline__ void st_global_v8(float* dst, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void store8(float* dst, const float (&v)[8], int vec) {
   if (vec == 4) {
-    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    if ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+      st_global_v8(dst, v);
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
   } else if (vec == 2) {
 #pragma unroll
     for (int j = 0; j < 8; j += 2) *reinterpret_cast<float2*>(dst + j) = make_float2(v[j], v[j + 1]);
@@ -653,9 +664,16 @@ __device__ __forceinline__ float rec_grad(float a) {
   if (REC == FOV_REC_HARD_SIGMOID) return (a > 0.0f && a < 1.0f) ? 0.2f : 0.0f;
   return a * (1.0f - a);
 }
+// 8 consecutive floats of the thread's own row: one 256-bit load (LDG.E.256, a full 32-byte sector) when aligned
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  if ((reinterpret_cast<uintptr_t>(p) & 31u) == 0) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+  } else {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
 }
 
 template <int NS, int REC, int OD, bool AR>
