@@ -197,41 +197,56 @@ def kernel_rooflines(lib, dev, B, compute, peaks, seq_per_s_per_gpu, step_ms):
     del x0, dcat
     # ---- the dense layers on the flattened concat buffer: Dense(198) on 20 slices, Dense(256) on 10 ----
     flat = hseq.view(B, T, 1848)
-    for name, key, rows, cout, view in (("Dense 1848->198 (reconstruction head, 20 slices)", "dense198", B * 20, 198, None),
-                                        ("Dense 1848->256 (concat-state fusion, 10 future slices)", "dense256", B * 10, 256, 10)):
-        wd = torch.randn(1, 1, 1848, cout, device=dev) * 0.02
-        bd = torch.zeros(cout, device=dev)
-        y = torch.empty(rows, cout, device=dev)
-        dx = torch.empty(B, T, 1848, device=dev)
-        gw, gbv = torch.zeros_like(wd), torch.zeros_like(bd)
-        if view is None:
-            dcfg = _lib.ConvCfg(rows, 1, 1, 1848, cout, 1, 1, 1, 1, 0, 0, 1848, 1848, cout, cout, 0, 0.0)
-            xp = flat.data_ptr()
-            dxp = dx.data_ptr()
-        else:   # the strided future view, read in place
-            dcfg = _lib.ConvCfg(B, 1, view, 1848, cout, 1, 1, 1, 1, 0, 0, T * 1848, 1848, view * cout, cout, 0, 0.0)
-            xp = flat.data_ptr() + 4 * (T - view) * 1848
-            dxp = dx.data_ptr() + 4 * (T - view) * 1848
-        flop = 2.0 * rows * 1848 * cout
+    dx = torch.empty(B, T, 1848, device=dev)
+
+    def gemm_calls(cfg, xp, dyp, w, bias, yp, dxp, gw, gb):
+        """forward / backward-data / weight-gradient closures of one dense layer through the C ABI"""
         if math == 0:
-            wsd = torch.empty(1848 * cout, device=dev)
-            f_fwd = lambda: _lib.check(lib.fov_conv2d_fwd(C.byref(dcfg), xp, wd.data_ptr(), bd.data_ptr(), y.data_ptr(), st))
-            f_bd = lambda: _lib.check(lib.fov_conv2d_bwd_data(C.byref(dcfg), y.data_ptr(), wd.data_ptr(), dxp, wsd.data_ptr(), st))
-            f_bw = lambda: _lib.check(lib.fov_conv2d_bwd_weight(C.byref(dcfg), xp, y.data_ptr(), gw.data_ptr(), gbv.data_ptr(), st))
-        else:
-            ws1 = torch.empty(int(lib.fov_conv_tc_ws_bytes(C.byref(dcfg), math, 0)) + 256, dtype=torch.uint8, device=dev)
-            ws2 = torch.empty(int(lib.fov_conv_tc_ws_bytes(C.byref(dcfg), math, 1)) + 256, dtype=torch.uint8, device=dev)
-            f_fwd = lambda: _lib.check(lib.fov_conv2d_fwd_tc(C.byref(dcfg), xp, wd.data_ptr(), bd.data_ptr(), y.data_ptr(),
-                                                             ws1.data_ptr(), math, st))
-            f_bd = lambda: _lib.check(lib.fov_conv2d_bwd_data_tc(C.byref(dcfg), y.data_ptr(), wd.data_ptr(), dxp,
-                                                                 ws2.data_ptr(), math, st))
-            f_bw = lambda: _lib.check(lib.fov_conv2d_bwd_weight_tc(C.byref(dcfg), xp, y.data_ptr(), gw.data_ptr(),
-                                                                   gbv.data_ptr(), math, st))
-        io_b = rows * (1848 + cout) * 4
-        entry(name + ": forward", key + "_fwd", _time_cuda(f_fwd, reps=10, warm=2), io_b, flop)
-        entry(name + ": backward-data", key + "_bwd_data", _time_cuda(f_bd, reps=10, warm=2), io_b, flop)
-        entry(name + ": weight gradient", key + "_wgrad", _time_cuda(f_bw, reps=10, warm=2), io_b, flop)
-        del wd, y, dx
+            wsd = torch.empty(w.numel(), device=dev)
+            return (lambda: _lib.check(lib.fov_conv2d_fwd(C.byref(cfg), xp, w.data_ptr(), bias.data_ptr(), yp, st)),
+                    lambda: _lib.check(lib.fov_conv2d_bwd_data(C.byref(cfg), dyp, w.data_ptr(), dxp, wsd.data_ptr(), st)),
+                    lambda: _lib.check(lib.fov_conv2d_bwd_weight(C.byref(cfg), xp, dyp, gw.data_ptr(), gb.data_ptr(), st)))
+        ws1 = torch.empty(int(lib.fov_conv_tc_ws_bytes(C.byref(cfg), math, 0)) + 256, dtype=torch.uint8, device=dev)
+        ws2 = torch.empty(int(lib.fov_conv_tc_ws_bytes(C.byref(cfg), math, 1)) + 256, dtype=torch.uint8, device=dev)
+        return (lambda: _lib.check(lib.fov_conv2d_fwd_tc(C.byref(cfg), xp, w.data_ptr(), bias.data_ptr(), yp, ws1.data_ptr(), math, st)),
+                lambda: _lib.check(lib.fov_conv2d_bwd_data_tc(C.byref(cfg), dyp, w.data_ptr(), dxp, ws2.data_ptr(), math, st)),
+                lambda: _lib.check(lib.fov_conv2d_bwd_weight_tc(C.byref(cfg), xp, dyp, gw.data_ptr(), gb.data_ptr(), math, st)))
+
+    Tf = 10
+    w198 = torch.randn(1, 1, 1848, 198, device=dev) * 0.02
+    w256 = torch.randn(1, 1, 1848, 256, device=dev) * 0.02
+    wcat = torch.cat([w198, w256], dim=-1)
+    b198, b256, bcat = torch.zeros(198, device=dev), torch.zeros(256, device=dev), torch.zeros(454, device=dev)
+    y198 = torch.empty(B * T, 198, device=dev)
+    y256 = torch.empty(B * Tf, 256, device=dev)
+    ycat = torch.empty(B * Tf, 454, device=dev)
+    g198, g256 = torch.zeros_like(w198), torch.zeros_like(w256)
+    gb198, gb256 = torch.zeros_like(b198), torch.zeros_like(b256)
+    fut_off = 4 * (T - Tf) * 1848
+    c_full = _lib.ConvCfg(B * T, 1, 1, 1848, 198, 1, 1, 1, 1, 0, 0, 1848, 1848, 198, 198, 0, 0.0)
+    c_fut = _lib.ConvCfg(B, 1, Tf, 1848, 256, 1, 1, 1, 1, 0, 0, T * 1848, 1848, Tf * 256, 256, 0, 0.0)
+    c_past = _lib.ConvCfg(B, 1, T - Tf, 1848, 198, 1, 1, 1, 1, 0, 0, T * 1848, 1848, T * 198, 198, 0, 0.0)
+    c_cat = _lib.ConvCfg(B, 1, Tf, 1848, 454, 1, 1, 1, 1, 0, 0, T * 1848, 1848, Tf * 454, 454, 0, 0.0)
+    f198 = gemm_calls(c_full, flat.data_ptr(), y198.data_ptr(), w198, b198, y198.data_ptr(), dx.data_ptr(), g198, gb198)
+    f256 = gemm_calls(c_fut, flat.data_ptr() + fut_off, y256.data_ptr(), w256, b256, y256.data_ptr(), dx.data_ptr() + fut_off,
+                      g256, gb256)
+    fpast = gemm_calls(c_past, flat.data_ptr(), y198.data_ptr(), w198, b198, y198.data_ptr(), dx.data_ptr(), g198, gb198)
+    fcat = gemm_calls(c_cat, flat.data_ptr() + fut_off, ycat.data_ptr(), wcat, bcat, ycat.data_ptr(), dx.data_ptr() + fut_off,
+                      g198, gb198)
+    r20, r10 = B * T, B * Tf
+    io = lambda rows, cout: rows * (1848 + cout) * 4
+    fl = lambda rows, cout: 2.0 * rows * 1848 * cout
+    entry("Dense 1848->198 (reconstruction head, 20 slices): forward", "dense198_fwd", _time_cuda(f198[0], reps=10, warm=2),
+          io(r20, 198), fl(r20, 198))
+    entry("Dense 1848->256 (concat-state fusion, 10 future slices): forward", "dense256_fwd",
+          _time_cuda(f256[0], reps=10, warm=2), io(r10, 256), fl(r10, 256))
+    entry("Dense backward-data, 10 past slices: dx = dy198 . W198^T", "dense_bwd_data_past",
+          _time_cuda(fpast[1], reps=10, warm=2), io(r10, 198), fl(r10, 198))
+    entry("Dense backward-data, 10 future slices, both layers in ONE GEMM: dx = [dy198 | dy256] . [W198 | W256]^T",
+          "dense_bwd_data_future_fused", _time_cuda(fcat[1], reps=10, warm=2), io(r10, 454), fl(r10, 454))
+    entry("Dense 1848->198: weight gradient", "dense198_wgrad", _time_cuda(f198[2], reps=10, warm=2), io(r20, 198), fl(r20, 198))
+    entry("Dense 1848->256: weight gradient", "dense256_wgrad", _time_cuda(f256[2], reps=10, warm=2), io(r10, 256), fl(r10, 256))
+    del w198, w256, wcat, y198, y256, ycat, dx
     del hseq
     out.sort(key=lambda e: -e["ms"])
     dom = out[0]

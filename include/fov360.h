@@ -212,6 +212,9 @@ typedef struct {
   int math;                      /* FOV_MATH_*: 0 = fp32 CUDA-core kernels; 1..3 = tcgen05 kernels with that
                                     many bf16 terms per operand (the step becomes ONE fused launch:
                                     [x taps | h taps] x [K;R] GEMM + gate algebra + cell update) */
+  int ws_prepacked;              /* 1: io.ws still holds this layer's packed weights from an earlier fov_convlstm_fwd
+                                    call with the same weights and shapes (the 10 one-step decoder calls of
+                                    mycode/convlstm_seq2seq.py:211-220): the repack launch is skipped */
 } fov_convlstm_cfg;
 
 typedef struct {

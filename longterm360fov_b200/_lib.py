@@ -64,7 +64,7 @@ class ConvLstmCfg(C.Structure):
                 ("dil_w", C.c_int), ("rec_act", C.c_int),
                 ("x_b_stride", C.c_longlong), ("x_t_stride", C.c_longlong), ("x_pix_stride", C.c_int),
                 ("h_b_stride", C.c_longlong), ("h_t_stride", C.c_longlong), ("h_pix_stride", C.c_int),
-                ("training", C.c_int), ("math", C.c_int)]
+                ("training", C.c_int), ("math", C.c_int), ("ws_prepacked", C.c_int)]
 
 
 class ConvLstmIO(C.Structure):

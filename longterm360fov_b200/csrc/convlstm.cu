@@ -137,7 +137,7 @@ static int convlstm_fwd_tc(const fov_convlstm_cfg* cfg, const fov_convlstm_io* i
   // whole images per MMA tile: one persistent launch runs every timestep (convlstm_seq_tc.cu)
   if (tc_convlstm_seq_supported(cfg, k)) return tc_convlstm_seq_fwd(cfg, io, k, st);
   for (int t = 0; t < cfg->T; ++t) {
-    k.prepacked = t > 0;
+    k.prepacked = t > 0 || cfg->ws_prepacked;
     k.seg[0].x = io->x + t * cfg->x_t_stride;
     if (t == 0) {
       k.seg[1].x = io->h0; k.seg[1].img_outer = g.hw_f; k.seg[1].pix_stride = F;

@@ -570,7 +570,7 @@ int tc_convlstm_seq_fwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, co
   SeqPlan pl;
   int rc = seq_plan(c, step, &pl);
   if (rc) return rc;
-  if ((rc = tc_conv_pack(step, st))) return rc;
+  if (!c->ws_prepacked && (rc = tc_conv_pack(step, st))) return rc;
   const TcStepPlan& sp = pl.sp;
   SeqParams p{};
   for (int s = 0; s < 2; ++s) {

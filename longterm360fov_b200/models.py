@@ -889,7 +889,7 @@ class ConvLSTMSeq2Seq(Model):
         self._draws += 1
         return ops.philox_normal((B, fps, 3), self.sample_seed, off, self.device)
 
-    def _stack(self, side, x, states, training):
+    def _stack(self, side, x, states, training, packs=None):
         p, g = self.params, self.grads
         wl = [(p["%s_convlstm%d/kernel" % (side, l)], p["%s_convlstm%d/recurrent_kernel" % (side, l)],
                p["%s_convlstm%d/bias" % (side, l)]) for l in range(3)]
@@ -899,7 +899,8 @@ class ConvLSTMSeq2Seq(Model):
         if training and self.dropout:       # a fresh set of masks per layer call, as Keras draws them
             masks = self._dropout_masks(self.dropout, x.shape[0], x.shape[2], x.shape[3],
                                         [x.shape[4]] + [w[1].shape[2] for w in wl[:-1]])
-        return ops.convlstm_stack(x, wl, states, sl, self.dilation, self.rec_act, training, dropout_masks=masks)
+        return ops.convlstm_stack(x, wl, states, sl, self.dilation, self.rec_act, training, dropout_masks=masks,
+                                  pack_cache=packs)
 
     def _forward(self, inputs, training, resample_mode=None):
         enc_in, dec_in = inputs
@@ -910,7 +911,7 @@ class ConvLSTMSeq2Seq(Model):
         outs = []
         packs = {}          # packed head weights, valid for this pass (forward + its backward): packed once, used T_dec times
         for step in range(self.T_dec):
-            cat, states = self._stack("dec", x, states, training)
+            cat, states = self._stack("dec", x, states, training, packs)
             d = cat[:, 0]                                              # (B,H,W,56)
             if self.head_kind == "conv2d":
                 y = d

@@ -536,11 +536,23 @@ class ConvLSTMStackFn(torch.autograd.Function):
                 lx_ptr, lx_b, lx_t, lx_pix, lcin, lK = cur_ptr, cur_b, cur_t, cur_pix, cin, K
             drop.append((mask, x4, K4))
             cfg = _lib.ConvLstmCfg(B, T, H, W, lcin, F, kh, kw, dil[0], dil[1], rec,
-                                   lx_b, lx_t, lx_pix, T * HW * Fsum, HW * Fsum, Fsum, int(training), math)
+                                   lx_b, lx_t, lx_pix, T * HW * Fsum, HW * Fsum, Fsum, int(training), math, 0)
             # saved gates exist only for BPTT; the fused tensor-core step never materialises them otherwise
             fws_bytes = lib.fov_convlstm_fwd_ws_bytes(C.byref(cfg))     # > 0: the fused tensor-core step runs
             gates = torch.empty((B, T, H, W, 4 * F) if (training or fws_bytes == 0) else (1,), device=dev)
-            fws = _ws(fws_bytes, dev) if fws_bytes else None
+            fws = None
+            if fws_bytes:
+                # packed gate weights: shared by the calls of one pass when the caller hands in a cache (the one-step
+                # decoder calls of convlstm_seq2seq run the same three layers 10 times)
+                pcache = opts.get("pack_cache")
+                pkey = (lK.data_ptr(), R.data_ptr(), tuple(lK.shape), math, B, H, W) if (pcache is not None and mask is None) else None
+                fws = pcache.get(pkey) if pkey is not None else None
+                if fws is not None:
+                    cfg.ws_prepacked = 1
+                else:
+                    fws = _ws(fws_bytes, dev)
+                    if pkey is not None:
+                        pcache[pkey] = fws
             cseq = torch.empty(B, T, H, W, F, device=dev)
             hT = torch.empty(B, H, W, F, device=dev)
             cT = torch.empty(B, H, W, F, device=dev)
@@ -622,7 +634,7 @@ class ConvLSTMStackFn(torch.autograd.Function):
 
 
 def convlstm_stack(x, weights, states=None, sinks=None, dilation=(1, 1), rec_act="hard_sigmoid",
-                   training=False, dropout_masks=None):
+                   training=False, dropout_masks=None, pack_cache=None):
     """weights: [(K,R,b)]*L ; states: [(h0,c0)]*L or None; dropout_masks: per layer None or a
     (4,B,H,W,Cin_l) tensor of keep-masks already scaled by 1/(1-rate) (training only).
     Returns (concat_seq, [(hT,cT)]*L)."""
@@ -633,7 +645,8 @@ def convlstm_stack(x, weights, states=None, sinks=None, dilation=(1, 1), rec_act
     for l in range(L):
         flat += list(states[l]) if states is not None else [None, None]
     out = ConvLSTMStackFn.apply({"layers": L, "dilation": dilation, "rec_act": rec_act,
-                                 "training": training, "dropout_masks": dropout_masks}, sinks, x, *flat)
+                                 "training": training, "dropout_masks": dropout_masks, "pack_cache": pack_cache},
+                                sinks, x, *flat)
     return out[0], [(out[1 + 2 * l], out[2 + 2 * l]) for l in range(L)]
 
 
