@@ -342,6 +342,22 @@ int fov_m3_batches(int U, int S, int stride, int K, const int* idx, const float*
  * Angles are evaluated in float64 so the bin indices equal NumPy's. */
 int fov_onehot_heatmaps(long long rows, int frames, int bin_size, const float* xyz, float* out, void* stream);
 
+/* Gaussian-FoV / head-direction tiles (mycode/data_generator_gaussian_FoV.py): the per-second heat maps of the
+ * reference's Gaussian-FoV data generator, from frame centres.
+ * fov_theta_phi_frames: xyz (frames,3) -> phi_theta (frames,2) float64 = [phi/pi, (theta+pi)/2/pi] (:21-55 on
+ *   xyz2thetaphi, mycode/dataIO.py:77-82).
+ * fov_gaussian_fov_tiles: phi_theta (maps*frames, 2) float64 centres in [0,1] -> out (maps, 18, 36, frames) float32;
+ *   kind 0 = crop_FoV_from_equirect / get_gaussian_FoV (:57-127), kind 1 = blur_head_direction_equirect /
+ *   get_head_direction (:163-232); every 10th row / column of the 180 x 360 map of each frame, divided by the maximum
+ *   over the FULL-resolution maps of every frame of the call (as the reference normalises).  peak: one device float of
+ *   scratch that returns that maximum.  Frames of a map are its channels (:130-138, :235-243).
+ * fov_heatmap_sum: tiles (maps, cells, frames) -> out (maps, cells): frame channels summed per cell and each map scaled
+ *   to sum 1 (heatmap_sum + normalize_to_distribution, :246-261), float32 in NumPy's summation order. */
+int fov_theta_phi_frames(long long frames, const float* xyz, double* phi_theta, void* stream);
+int fov_gaussian_fov_tiles(long long maps, int frames, int kind, const double* phi_theta, float* out, float* peak,
+                           void* stream);
+int fov_heatmap_sum(long long maps, int cells, int frames, const float* tiles, float* out, void* stream);
+
 /* FoV hit rate (evaluation metric, mycode/baseline_knn_mean.py:48-93,123-168): pred / gt (rows,2) = (theta, phi)
  * centres in radians, spans in radians (the scripts use 120 x 120 degrees); out[i] = overlap of the two boxes over the
  * ground-truth box area after the +-pi wrap fix of boundary_cases. */

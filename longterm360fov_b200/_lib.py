@@ -141,6 +141,9 @@ SYMBOLS = {
     "fov_m3_batches": (_I, [_I, _I, _I, _I, _P, _P, _LL, _P, _P, _P, _P, _P]),
     "fov_onehot_heatmaps": (_I, [_LL, _I, _I, _P, _P, _P]),
     "fov_hit_rate": (_I, [_LL, _P, _P, _F, _F, _F, _F, _P, _P]),
+    "fov_theta_phi_frames": (_I, [_LL, _P, _P, _P]),
+    "fov_gaussian_fov_tiles": (_I, [_LL, _I, _I, _P, _P, _P, _P]),
+    "fov_heatmap_sum": (_I, [_LL, _I, _I, _P, _P, _P]),
 }
 
 _lib = None

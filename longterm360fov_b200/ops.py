@@ -952,6 +952,51 @@ def one_hot_heatmaps(frames, bin_size=10):
     return out
 
 
+def theta_phi_frames(frames):
+    """(..., F, 3) xyz frames -> (..., F, 2) float64 [phi / pi, (theta + pi) / 2 / pi], the frame-level label array of
+    mycode/data_generator_gaussian_FoV.py:21-55."""
+    lib = _lib.load()
+    _require_cuda(frames)
+    frames = _f32c(frames)
+    out = torch.empty(*frames.shape[:-1], 2, device=frames.device, dtype=torch.float64)
+    _lib.check(lib.fov_theta_phi_frames(out.numel() // 2, ptr(frames), ptr(out), _stream()), "fov_theta_phi_frames")
+    return out
+
+
+def gaussian_fov_tiles(phi_theta, kind="fov", fps=30, return_peak=False):
+    """Gaussian-FoV (``kind='fov'``: get_gaussianFoV_per_vid_per_target_giventhetaphi,
+    mycode/data_generator_gaussian_FoV.py:57-138) or head-direction (``kind='head'``: :163-243) tiles:
+    phi_theta (num_user, num_sec * fps, 2) float64 centres in [0, 1] -> (num_user, num_sec, 18, 36, fps) float32,
+    normalised by the maximum over every full-resolution frame of the call like the reference."""
+    lib = _lib.load()
+    _require_cuda(phi_theta)
+    _expect(phi_theta.dim() == 3 and phi_theta.shape[-1] == 2, "phi_theta must be (num_user, frames, 2), got %s",
+            tuple(phi_theta.shape))
+    _expect(kind in ("fov", "head"), "kind must be 'fov' or 'head', got %r", kind)
+    U, n = phi_theta.shape[0], phi_theta.shape[1] // fps
+    _expect(n > 0, "need at least one whole second of frames")
+    pt = phi_theta[:, :n * fps].to(torch.float64).contiguous()
+    out = torch.empty(U, n, 18, 36, fps, device=pt.device)
+    peak = torch.empty(1, device=pt.device)
+    _lib.check(lib.fov_gaussian_fov_tiles(U * n, fps, 0 if kind == "fov" else 1, ptr(pt), ptr(out), ptr(peak),
+                                          _stream()), "fov_gaussian_fov_tiles")
+    return (out, peak) if return_peak else out
+
+
+def heatmap_sum(tiles):
+    """heatmap_sum + normalize_to_distribution (mycode/data_generator_gaussian_FoV.py:246-261):
+    (..., 18, 36, F) -> (..., 18, 36, 1), frame channels summed, each map scaled to sum 1."""
+    lib = _lib.load()
+    _require_cuda(tiles)
+    tiles = _f32c(tiles)
+    _expect(tiles.dim() >= 3, "tiles must be (..., H, W, F)")
+    H, W, Fr = tiles.shape[-3:]
+    maps = tiles.numel() // (H * W * Fr)
+    out = torch.empty(*tiles.shape[:-1], 1, device=tiles.device)
+    _lib.check(lib.fov_heatmap_sum(maps, H * W, Fr, ptr(tiles), ptr(out), _stream()), "fov_heatmap_sum")
+    return out
+
+
 def hit_rate(pred_theta_phi, gt_theta_phi, a=1.0, span_deg=120.0):
     """FoV hit rate per (theta, phi) centre pair (mycode/baseline_knn_mean.py:48-93,123-168): (..., 2) radians ->
     (...,); the predicted box is ``a`` x 120 degrees wide, the ground-truth box 120 degrees."""

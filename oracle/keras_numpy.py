@@ -15,6 +15,8 @@ ConvLSTM2D ``kernel (kh,kw,Cin,4F)``, ``recurrent_kernel (kh,kw,F,4F)``; Dense
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 FPS = 30
@@ -330,6 +332,112 @@ def one_hot_heatmaps(frames, bin_size=10):
     n, t, f = np.meshgrid(np.arange(N), np.arange(T), np.arange(Fr), indexing="ij")
     one_hot[n, t, f, ti, pj] = 1
     return one_hot.transpose(0, 1, 3, 4, 2)
+
+
+def theta_phi_frames(xyz):
+    """get_theta_phi_array / get_theta_phi_array_per_user (mycode/data_generator_gaussian_FoV.py:21-55) for one
+    viewer: (..., F, 3) xyz frames -> (..., F, 2) = [phi / pi, (theta + pi) / 2 / pi], both in [0, 1]."""
+    theta, phi = xyz2thetaphi(xyz[..., 0], xyz[..., 1], xyz[..., 2])
+    return np.stack([phi / np.pi, (theta + np.pi) / 2 / np.pi], axis=-1)
+
+
+def _fov_rows(kind, xi, img_h):
+    """Image rows visited by the row loop: crop_FoV_from_equirect (:71-74, 90 rows from xi - 44, wrapping over the
+    poles) or blur_head_direction_equirect (:176-183, blur_h rows from max(int(xi - blur_h / 2), 0) + 1, no wrap).
+    Returns (rows that exist in the image, rowx of the LAST visited row - the sigma below is taken from it)."""
+    if kind == "fov":
+        row = int(xi - img_h / 4 + img_h)
+        n_it = 0
+        while n_it < img_h / 2:
+            n_it += 1
+        rows = [(row + 1 + i) % img_h for i in range(n_it)]
+    else:
+        blur_h = 5 / 18 * img_h
+        row = int(xi - blur_h / 2)
+        n_it = 0
+        while n_it < blur_h:
+            n_it += 1
+        if row <= 0:
+            row = 0
+        rows = [row + 1 + i for i in range(n_it)]
+    return rows, rows[-1] / float(img_h)
+
+
+def _fov_longitude(kind, row, img_h, img_w):
+    """Half width (columns) of the FoV at an image row (:77-80 / :186-189); float index of the Python-2 code -> int."""
+    rowx = row / float(img_h)
+    half_span = int(img_w / 6) if kind == "fov" else 0.5 * (5 / 36) * img_w
+    lon = int(half_span / (math.cos(math.pi * (abs(rowx - 0.5))) + 0.00001))
+    if kind == "fov":
+        if lon > img_w / 2 - 1:
+            lon = int(img_w / 2 - 1)
+    elif lon >= img_h - 1:
+        lon = img_h - 1
+    return lon
+
+
+def gaussian_fov_frames(phi_theta, kind="fov", img_h=180, img_w=360, full=False):
+    """get_gaussian_FoV (mycode/data_generator_gaussian_FoV.py:121-127 -> crop_FoV_from_equirect :57-118,
+    kind="fov") and get_head_direction (:226-232 -> blur_head_direction_equirect :163-224, kind="head") restated:
+    (n, 2) frame centres [phi, theta] in [0, 1] -> (n, 18, 36, 1) float32, every 10th row / column of the 180 x 360
+    map, normalised by the maximum of the FULL-resolution maps of all n frames.  A frame's map is the indicator of a
+    latitude-dependent column span around the centre (wrapping in theta) times exp(-d^2 / 2 * sigma^2) + its
+    wrapped copy; sigma comes from the last visited row (as written: the value multiplies, it does not divide)."""
+    phi_theta = np.asarray(phi_theta, np.float64).reshape(-1, 2)
+    n = phi_theta.shape[0]
+    shrink = img_h / 256
+    Y, X = np.meshgrid(np.arange(img_h, dtype=np.float64), np.arange(img_w, dtype=np.float64), indexing="ij")
+    maps = np.zeros((n, img_h, img_w), np.float32)
+    for k in range(n):
+        xi, zi = int(phi_theta[k, 0] * img_h), int(phi_theta[k, 1] * img_w)
+        rows, rowx = _fov_rows(kind, xi, img_h)
+        mask = np.zeros((img_h, img_w))
+        for row in rows:
+            if row >= img_h:
+                continue
+            lon = _fov_longitude(kind, row, img_h, img_w)
+            zlow, zhigh = zi - lon, zi + lon
+            if zlow < 0:
+                mask[row, zlow + img_w:img_w] = 1
+                zlow = 0
+            if zhigh > img_w:
+                mask[row, 0:zhigh % img_w] = 1
+                zhigh = img_w - 1
+            mask[row, zlow:zhigh] = 1
+        sigma = ((0.01 if kind == "fov" else 0.05) + 0.008 * (math.pi * (abs(rowx - 0.5)))) / shrink
+        G = np.exp(-((X - zi) ** 2 + (Y - xi) ** 2) / 2.0 * sigma ** 2)
+        zoo = zi
+        margin = int(img_w * 0.3)
+        if zi + margin > img_w:
+            zoo = zi - img_w
+        if zi - margin < 0:
+            zoo = zi + img_w
+        G1 = np.exp(-((X - zoo) ** 2 + (Y - xi) ** 2) / 2.0 * sigma ** 2)
+        if zoo == zi:
+            G1 = 0.00001 * G1
+        maps[k] = mask * (G + G1)
+    maps = maps / np.max(maps)
+    if full:
+        return maps
+    return maps[:, 0::10, 0::10, None]
+
+
+def gaussian_fov_per_video(phi_theta, kind="fov", fps=FPS):
+    """get_gaussianFoV_per_vid_per_target_giventhetaphi / get_headdirection_... (:130-138, :235-243):
+    (num_user, num_sec * fps, 2) -> (num_user, num_sec, 18, 36, fps), frames of a second as channels."""
+    U, n = phi_theta.shape[0], phi_theta.shape[1] // fps
+    t = gaussian_fov_frames(phi_theta[:, :n * fps].reshape(-1, 2), kind)
+    return t.reshape(U, n, fps, 18, 36).transpose(0, 1, 3, 4, 2)
+
+
+def heatmap_sum(heat_frame):
+    """heatmap_sum + normalize_to_distribution (mycode/data_generator_gaussian_FoV.py:246-261): sum the frame
+    channels of every second and scale each (18, 36) map to sum 1."""
+    s = np.sum(heat_frame, axis=-1)[..., np.newaxis]
+    flat = s.reshape((-1,) + s.shape[-3:])
+    for i in range(flat.shape[0]):
+        flat[i] = flat[i] / np.sum(flat[i])
+    return flat.reshape(s.shape)
 
 
 def hit_rate(pred, gt, a=1.0, span_deg=120.0):

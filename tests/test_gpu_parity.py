@@ -139,6 +139,41 @@ def test_one_hot_heatmaps_match_reference_golden(golden):
     assert np.array_equal(coarse.cpu().numpy(), kn.one_hot_heatmaps(v[:2].astype(np.float64), 30).astype(np.float32))
 
 
+def test_gaussian_fov_tiles_match_reference_golden():
+    """Gaussian-FoV / head-direction tiles (data_generator_gaussian_FoV.py:57-243) on the device against the outputs
+    of the reference's own functions.  The masks, the peak pixel and the summation order are integer / ordered work;
+    the pixel values go through exp() in float64 and ONE rounding to float32, so they may differ from NumPy's by the
+    last float32 bit where the two float64 exp() differ in their last bit: atol 1.2e-7 (one ulp at 1.0), zeros exact."""
+    _cuda()
+    import os
+    from longterm360fov_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_gaussian_fov_golden.npz"))
+    for kind in ("fov", "head"):
+        for tag, src in ((kind, "pt"), (kind + "_wrap", "pt_wrap")):
+            got, peak = ops.gaussian_fov_tiles(torch.tensor(g[src]).cuda(), kind, return_peak=True)
+            got = got.cpu().numpy()
+            ref = g[tag]
+            assert got.shape == ref.shape and got.dtype == np.float32
+            assert np.array_equal(got == 0, ref == 0), "painted region differs"
+            np.testing.assert_allclose(got, ref, rtol=0, atol=1.2e-7)
+            full = kn.gaussian_fov_frames(g[src].reshape(-1, 2), kind, full=True)        # already / max
+            assert abs(float(full.max()) - 1.0) == 0.0 and peak.item() > 0.0
+        tiles = torch.tensor(g[kind]).cuda()
+        assert np.array_equal(ops.heatmap_sum(tiles).cpu().numpy(), g[kind + "_sum"])       # NumPy's summation order
+    lab = ops.theta_phi_frames(torch.tensor(g["xyz"], dtype=torch.float32).cuda()).cpu().numpy()
+    np.testing.assert_allclose(lab.reshape(3, 60, 2), g["xyz_phi_theta"], rtol=0, atol=1e-15)
+    # a whole video: 8 viewers x 40 s; every map's peak pixel is <= 1, at least one frame reaches it, and the
+    # device agrees with the oracle restatement
+    rng = np.random.default_rng(11)
+    pt = np.stack([rng.uniform(0.05, 0.95, (8, 1200)), rng.uniform(0, 1, (8, 1200))], axis=-1)
+    for kind in ("fov", "head"):
+        got = ops.gaussian_fov_tiles(torch.tensor(pt).cuda(), kind).cpu().numpy()
+        assert got.shape == (8, 40, 18, 36, 30) and got.max() <= 1.0 and got.min() >= 0.0
+        ref = kn.gaussian_fov_per_video(pt[:2, :300], kind)     # the oracle paints 180 x 360 per frame: a slice only
+        sub, _ = ops.gaussian_fov_tiles(torch.tensor(pt[:2, :300]).cuda(), kind, return_peak=True)
+        np.testing.assert_allclose(sub.cpu().numpy(), ref, rtol=0, atol=1.2e-7)
+
+
 def test_hit_rate_matches_reference_golden(golden):
     """Evaluation metric (baseline_knn_mean.py:48-93): floating point, evaluated in float64 on the device and
     stored as float32 -> tolerance 1e-6 against the reference's own output, wrap-around cases included."""

@@ -55,6 +55,19 @@ def test_one_hot_heatmaps_match_reference_golden(golden):
     assert got.sum() == golden["onehot_in"].shape[0] * golden["onehot_in"].shape[1] * 30   # one 1 per frame
 
 
+def test_gaussian_fov_tiles_match_reference_golden():
+    """crop_FoV_from_equirect / blur_head_direction_equirect restated (data_generator_gaussian_FoV.py:57-243):
+    bit-exact against the outputs of the reference's own functions, incl. the poles, the theta seam and a call whose
+    frames all wrap (the normaliser is then a wrapped frame's own peak), and the per-second distribution maps."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_gaussian_fov_golden.npz"))
+    for kind in ("fov", "head"):
+        assert np.array_equal(kn.gaussian_fov_per_video(g["pt"], kind), g[kind])
+        assert np.array_equal(kn.gaussian_fov_per_video(g["pt_wrap"], kind), g[kind + "_wrap"])
+        assert np.array_equal(kn.heatmap_sum(g[kind].copy()), g[kind + "_sum"])
+    assert np.array_equal(kn.theta_phi_frames(g["xyz"]).reshape(3, 60, 2), g["xyz_phi_theta"])
+
+
 def test_hit_rate_matches_reference_golden(golden):
     for a in (1.0, 0.75):
         got = kn.hit_rate(golden["hit_pred"], golden["hit_gt"], a=a)
