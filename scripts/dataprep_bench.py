@@ -34,3 +34,12 @@ for rows in (16384, 4096):
 x = torch.rand(4096, 10, 33, 30, 3, device=dev)
 ms = t(lambda: ops.get_whole_span(x))
 print("whole span (4096,10,33,30,3): %.3f ms, %.0f GB/s moved" % (ms, 3 * x.numel() * 4 / 1e9 / ms * 1e3))
+# Gaussian-FoV / head-direction tiles of a whole video: 48 viewers x 200 s x 30 fps (compute-bound on float64 exp:
+# the peak pass evaluates every painted full-resolution pixel, the tile pass 648 per frame)
+pt = torch.rand(48, 6000, 2, device=dev, dtype=torch.float64)
+for kind in ("fov", "head"):
+    ms = t(lambda: ops.gaussian_fov_tiles(pt, kind), reps=3, warm=1)
+    print("gaussian tiles kind=%s 48x200 s: %.3f ms, %.2f M frames/s" % (kind, ms, 48 * 6000 / ms / 1e3))
+tiles = ops.gaussian_fov_tiles(pt, "fov")
+ms = t(lambda: ops.heatmap_sum(tiles))
+print("heatmap_sum (48,200,18,36,30): %.3f ms, %.0f GB/s read" % (ms, tiles.numel() * 4 / 1e9 / ms * 1e3))

@@ -40,8 +40,11 @@ for w in $WHAT; do
       launches m4_b32_bf16_train python scripts/profile_step.py m4 32 bf16 train 2
       launches m4_b32_bf16_infer python scripts/profile_step.py m4 32 bf16 infer 2
       # second step of the training run: head convs (fwd / bwd-data), TMA-fed weight gradients, general weight gradients
-      full m4_conv 'tc_conv_kernel<1, 0>' 150 12 python scripts/profile_step.py m4 32 bf16 train 2
+      full m4_conv 'tc_conv_kernel' 244 12 python scripts/profile_step.py m4 32 bf16 train 2
       full m4_wgrad_planes 'wgrad_planes|planes_kernel' 30 9 python scripts/profile_step.py m4 32 bf16 train 2
+      ;;
+    m4conv)
+      full m4_conv 'tc_conv_kernel' 244 12 python scripts/profile_step.py m4 32 bf16 train 2
       ;;
     m1)
       launches m1_b8192_bf16x2_train python scripts/profile_step.py m1 8192 bf16x2 train 3
