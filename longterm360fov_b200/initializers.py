@@ -114,3 +114,25 @@ def init_stacked_fov_seq2seq(seed=1, n_layers=2, num_encoder_tokens=6, num_decod
         _lstm(rng, num_decoder_tokens if l == 0 else units, units, "decoder%d" % l, w)
     _dense(rng, units, num_decoder_tokens, "decoder_dense", w)
     return w
+
+
+def init_given_others_seq2seq(seed=1, num_user=34, latent_dim=32, num_encoder_tokens=6, num_decoder_tokens=6,
+                              variant="mlp_mixing"):
+    """mycode/given_others_gt_mean_var_seq2seq.py:97-166: two encoder + two decoder LSTMs of latent_dim units,
+    Dense(6, tanh) and the variant's mixing layers."""
+    rng = np.random.default_rng(seed)
+    w = {}
+    for l in range(2):
+        _lstm(rng, num_encoder_tokens if l == 0 else latent_dim, latent_dim, "encoder%d" % l, w)
+    for l in range(2):
+        _lstm(rng, num_decoder_tokens if l == 0 else latent_dim, latent_dim, "decoder%d" % l, w)
+    oth = (num_user - 1) * 6
+    if variant == "others_mlp":
+        _dense(rng, oth, 256, "others_dense1", w)
+        _dense(rng, 256, latent_dim, "others_dense2", w)
+        _dense(rng, 2 * latent_dim, num_decoder_tokens, "decoder_dense", w)
+    else:
+        _dense(rng, latent_dim, num_decoder_tokens, "decoder_dense", w)
+        if variant == "mlp_mixing":
+            _dense(rng, oth + num_decoder_tokens, num_decoder_tokens, "mixing", w)
+    return w

@@ -759,6 +759,106 @@ def stacked_fov_seq2seq(n_layers=2, latent_dim=64, num_encoder_tokens=6, num_dec
     return StackedFovSeq2Seq(weights, n_layers, share_last_decoder, recurrent_activation, device)
 
 
+class GivenOthersSeq2Seq(Model):
+    """mycode/given_others_gt_mean_var_seq2seq.py:97-308: two-layer fc-LSTM encoder-decoder (32 units) that is
+    GIVEN the other viewers' ground-truth mean / variance of every future second and mixes them into its own
+    prediction; every step's output is the next decoder input (cfg.teacher_forcing = False) or the decoder is
+    teacher forced.  Variants (the script's flags): 'mlp_mixing' (default there: Dense(6, tanh) over [others ;
+    own Dense(6, tanh) prediction], :277-281), 'others_mlp' (Dense 256 -> 32 relu on the others slice, concatenated
+    with the decoder state before decoder_dense, :251-261), 'target_only' (:247-248).
+
+    An fc-LSTM cell is a ConvLSTM2D cell on a 1 x 1 image with 1 x 1 kernels, so the graph runs on the ConvLSTM
+    kernels that already carry states and their gradients across one-step calls (as M4's decoder does): the encoder
+    is one 2-layer stack call over the 10 past seconds, the re-fed decoder one 2-layer step call per future second.
+    LSTM weights live in their Keras shapes in the flat bucket and are handed over as (1,1,in,4H) views."""
+
+    n_inputs, n_outputs = 3, 1
+
+    def __init__(self, weights, variant="mlp_mixing", teacher_forcing=False, recurrent_activation="hard_sigmoid",
+                 device=None):
+        if variant not in ("mlp_mixing", "others_mlp", "target_only"):
+            raise ValueError("variant must be 'mlp_mixing', 'others_mlp' or 'target_only'")
+        self.variant = variant
+        self.teacher_forcing = bool(teacher_forcing)
+        order = ["%s%d/%s" % (s, l, n) for s in ("encoder", "decoder") for l in range(2)
+                 for n in ("kernel", "recurrent_kernel", "bias")]
+        if variant == "others_mlp":
+            order += ["others_dense1/kernel", "others_dense1/bias", "others_dense2/kernel", "others_dense2/bias"]
+        order += ["decoder_dense/kernel", "decoder_dense/bias"]
+        if variant == "mlp_mixing":
+            order += ["mixing/kernel", "mixing/bias"]
+        self.weight_order = order
+        super().__init__(weights, device)
+        self.rec_act = recurrent_activation
+        if variant == "target_only":
+            self.n_inputs = 2
+
+    def _cells(self, side, src):
+        out = []
+        for l in range(2):
+            K, R, b = (src["%s%d/%s" % (side, l, n)] for n in ("kernel", "recurrent_kernel", "bias"))
+            out.append((K.view(1, 1, K.shape[0], K.shape[1]), R.view(1, 1, R.shape[0], R.shape[1]), b))
+        return out
+
+    def _stack(self, side, x, states, training):
+        B, T = x.shape[0], x.shape[1]
+        return ops.convlstm_stack(x.reshape(B, T, 1, 1, x.shape[-1]), self._cells(side, self.params), states,
+                                  self._cells(side, self.grads) if training else None, (1, 1), self.rec_act, training)
+
+    def _head(self, s2, oth_t, training):
+        p = self.params
+        d = lambda name, x, act: ops.dense(x, p[name + "/kernel"], p[name + "/bias"], act,
+                                           self._sinks(name + "/kernel", name + "/bias"), training)
+        if self.variant == "target_only":
+            return d("decoder_dense", s2, "tanh")
+        flat = oth_t.reshape(oth_t.shape[0], -1)
+        if self.variant == "others_mlp":
+            o = d("others_dense2", d("others_dense1", flat, "relu"), "relu")
+            return d("decoder_dense", torch.cat([o, s2], dim=-1), "tanh")
+        pred = d("decoder_dense", s2, "tanh")
+        return d("mixing", torch.cat([flat, pred], dim=-1), "tanh")
+
+    def _forward(self, inputs, training):
+        if self.variant == "target_only":
+            enc, dec = inputs
+            oth = None
+            T = dec.shape[1] if self.teacher_forcing else self.running_length
+        else:
+            enc, oth, dec = inputs
+            T = oth.shape[1]
+        B, H = enc.shape[0], self.params["encoder0/recurrent_kernel"].shape[0]
+        _, states = self._stack("encoder", enc, None, training)
+        outs = []
+        if self.teacher_forcing:
+            cat, _ = self._stack("decoder", dec, states, training)
+            d2 = cat[:, :, 0, 0, H:]                                  # hidden sequence of the second decoder layer
+            for t in range(T):
+                outs.append(self._head(d2[:, t].contiguous(), None if oth is None else oth[:, t], training))
+        else:
+            x = dec[:, 0:1]
+            for t in range(T):
+                cat, states = self._stack("decoder", x, states, training)
+                y = self._head(cat[:, 0, 0, 0, H:].contiguous(), None if oth is None else oth[:, t], training)
+                outs.append(y)
+                x = y.unsqueeze(1)
+        return [torch.stack(outs, dim=1)]
+
+
+def given_others_gt_mean_var_seq2seq(latent_dim=32, num_user=34, num_encoder_tokens=6, num_decoder_tokens=6,
+                                     variant="mlp_mixing", teacher_forcing=False, target_user_only=False,
+                                     recurrent_activation="hard_sigmoid", weights=None, seed=1, device=None):
+    """Builder for mycode/given_others_gt_mean_var_seq2seq.py:97-308 (cfg.input_mean_var, cfg.predict_mean_var):
+    inputs ``[encoder_inputs (B,10,6), others_fut_inputs (B,10,num_user-1,6), decoder_inputs (B,1,6)]`` (``(B,10,6)``
+    decoder inputs when teacher forced; no others input with ``target_user_only``) -> ``(B,10,6)``."""
+    if target_user_only:
+        variant = "target_only"
+    if weights is None:
+        weights = _init_weights("init_given_others_seq2seq", seed=seed, num_user=num_user, latent_dim=latent_dim,
+                                num_encoder_tokens=num_encoder_tokens, num_decoder_tokens=num_decoder_tokens,
+                                variant=variant)
+    return GivenOthersSeq2Seq(weights, variant, teacher_forcing, recurrent_activation, device)
+
+
 # --------------------------------------------------------------------------- #
 # M3: concat-state model with others' whole-span ConvLSTM
 # --------------------------------------------------------------------------- #

@@ -646,6 +646,69 @@ def stacked_fov_seq2seq_forward(w, enc_in, dec_in, n_layers=2, share_last_decode
     return dense(xd, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
 
 
+def init_given_others_seq2seq(seed=1, num_user=34, latent_dim=32, num_encoder_tokens=6, num_decoder_tokens=6,
+                              variant="mlp_mixing"):
+    """Weights of mycode/given_others_gt_mean_var_seq2seq.py:97-166: two encoder and two decoder LSTMs of latent_dim
+    (32) units, Dense(6, tanh), and per variant: 'mlp_mixing' (the script's default) a Dense(6, tanh) over
+    [others' mean/var of the step (num_user-1, 6) ; decoder prediction (6)]; 'others_mlp' Dense(256, relu) ->
+    Dense(latent_dim, relu) on the others slice, whose output is concatenated with the decoder state before
+    decoder_dense; 'target_only' nothing else."""
+    rng = np.random.default_rng(seed)
+    w = {}
+    for l in range(2):
+        init_lstm(rng, num_encoder_tokens if l == 0 else latent_dim, latent_dim, "encoder%d" % l, w)
+    for l in range(2):
+        init_lstm(rng, num_decoder_tokens if l == 0 else latent_dim, latent_dim, "decoder%d" % l, w)
+    oth = (num_user - 1) * 6
+    if variant == "others_mlp":
+        init_dense(rng, oth, 256, "others_dense1", w)
+        init_dense(rng, 256, latent_dim, "others_dense2", w)
+        init_dense(rng, 2 * latent_dim, num_decoder_tokens, "decoder_dense", w)
+    else:
+        init_dense(rng, latent_dim, num_decoder_tokens, "decoder_dense", w)
+        if variant == "mlp_mixing":
+            init_dense(rng, oth + num_decoder_tokens, num_decoder_tokens, "mixing", w)
+    return w
+
+
+def given_others_seq2seq_forward(w, enc_in, oth_in, dec_in, variant="mlp_mixing", teacher_forcing=False,
+                                 recurrent_activation="hard_sigmoid"):
+    """mycode/given_others_gt_mean_var_seq2seq.py:97-308 with cfg.input_mean_var / predict_mean_var: 2-layer fc-LSTM
+    encoder-decoder; every step's output is re-fed as the next decoder input unless teacher_forcing
+    (cfg.teacher_forcing, default False).  enc_in (B,10,6), oth_in (B,T,num_user-1,6) others' ground-truth mean/var
+    of the future seconds, dec_in (B,1,6) (or (B,T,6) teacher-forced) -> (B,T,6)."""
+    ra = recurrent_activation
+    B, T = oth_in.shape[0], oth_in.shape[1]
+    L = lambda n: (w[n + "/kernel"], w[n + "/recurrent_kernel"], w[n + "/bias"])
+    e1, h1, c1 = lstm(enc_in, *L("encoder0"), recurrent_activation=ra)
+    _, h2, c2 = lstm(e1, *L("encoder1"), recurrent_activation=ra)
+    if teacher_forcing:
+        d1, _, _ = lstm(dec_in, *L("decoder0"), h1, c1, recurrent_activation=ra)
+        d2, _, _ = lstm(d1, *L("decoder1"), h2, c2, recurrent_activation=ra)
+    x = dec_in[:, 0]
+    outs = []
+    for t in range(T):
+        if teacher_forcing:
+            s2 = d2[:, t]
+        else:
+            h1, c1 = lstm_step(x, h1, c1, *L("decoder0"), recurrent_activation=ra)
+            h2, c2 = lstm_step(h1, h2, c2, *L("decoder1"), recurrent_activation=ra)
+            s2 = h2
+        flat = oth_in[:, t].reshape(B, -1)
+        if variant == "target_only":
+            y = dense(s2, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+        elif variant == "others_mlp":
+            o = dense(flat, w["others_dense1/kernel"], w["others_dense1/bias"], "relu")
+            o = dense(o, w["others_dense2/kernel"], w["others_dense2/bias"], "relu")
+            y = dense(np.concatenate([o, s2], axis=-1), w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+        else:
+            pred = dense(s2, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+            y = dense(np.concatenate([flat, pred], axis=-1), w["mixing/kernel"], w["mixing/bias"], "tanh")
+        outs.append(y)
+        x = y
+    return np.stack(outs, axis=1)
+
+
 def init_others_lstm_span_whole(seed=1, num_user=34, kernel_size=5, latent_dim=64,
                                 oth_filters=(32, 16, 8), flat_dense=256):
     """Weights of M3, the canonical concat-state model (SURVEY.md hazard 2)."""

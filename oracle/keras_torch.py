@@ -192,6 +192,40 @@ def stacked_fov_seq2seq_forward(w, enc_in, dec_in, n_layers=2, share_last_decode
     return dense(xd, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
 
 
+def given_others_seq2seq_forward(w, enc_in, oth_in, dec_in, variant="mlp_mixing", teacher_forcing=False,
+                                 ra="hard_sigmoid"):
+    """mycode/given_others_gt_mean_var_seq2seq.py:97-308 (see oracle/keras_numpy.py)."""
+    B, T = oth_in.shape[0], oth_in.shape[1]
+    L = lambda n: (w[n + "/kernel"], w[n + "/recurrent_kernel"], w[n + "/bias"])
+    e1, h1, c1 = lstm(enc_in, *L("encoder0"), ra=ra)
+    _, h2, c2 = lstm(e1, *L("encoder1"), ra=ra)
+    if teacher_forcing:
+        d1, _, _ = lstm(dec_in, *L("decoder0"), h1, c1, ra=ra)
+        d2, _, _ = lstm(d1, *L("decoder1"), h2, c2, ra=ra)
+    x = dec_in[:, 0]
+    outs = []
+    for t in range(T):
+        if teacher_forcing:
+            s2 = d2[:, t]
+        else:
+            h1, c1 = lstm_step(x, h1, c1, *L("decoder0"), ra=ra)
+            h2, c2 = lstm_step(h1, h2, c2, *L("decoder1"), ra=ra)
+            s2 = h2
+        flat = oth_in[:, t].reshape(B, -1)
+        if variant == "target_only":
+            y = dense(s2, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+        elif variant == "others_mlp":
+            o = dense(flat, w["others_dense1/kernel"], w["others_dense1/bias"], "relu")
+            o = dense(o, w["others_dense2/kernel"], w["others_dense2/bias"], "relu")
+            y = dense(torch.cat([o, s2], dim=-1), w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+        else:
+            pred = dense(s2, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+            y = dense(torch.cat([flat, pred], dim=-1), w["mixing/kernel"], w["mixing/bias"], "tanh")
+        outs.append(y)
+        x = y
+    return torch.stack(outs, dim=1)
+
+
 def others_lstm_span_whole_forward(w, enc_in, oth_in, dec_in, ra="hard_sigmoid"):
     B, Tenc = enc_in.shape[:2]
     Tall = oth_in.shape[1]

@@ -633,6 +633,60 @@ def test_stacked_fov_seq2seq(n_layers, B, tc, lstm_switches):
     assert not m.params["encoder1/recurrent_kernel"].detach().cpu().numpy()[pad].any()
 
 
+# ------------------------------------------------------------------ sibling model: 2-layer fc-LSTM given others' mean / var
+
+@pytest.mark.parametrize("variant,tf", [("mlp_mixing", False), ("mlp_mixing", True), ("others_mlp", False),
+                                        ("target_only", False), ("others_mlp", True)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16x2"])
+def test_given_others_mean_var_seq2seq(variant, tf, mode):
+    """mycode/given_others_gt_mean_var_seq2seq.py:97-308: two-layer 32-unit fc-LSTM encoder-decoder whose every output
+    is re-fed (or teacher forced), mixing the others' ground-truth mean / var through an MLP: forward (north-star bar
+    1e-4), loss, every gradient and 5 Adam steps against the float64 oracle."""
+    fov = _cuda()
+    B = 37
+    rng = np.random.default_rng(len(variant) * 2 + int(tf))
+    w = _perturb(kn.init_given_others_seq2seq(seed=5, variant=variant), 6, 0.05)
+    enc = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    oth = rng.uniform(-1, 1, (B, 10, 33, 6)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 10 if tf else 1, 6)).astype(np.float32)
+    tgt = rng.uniform(-1, 1, (B, 10, 6)).astype(np.float32)
+    m = fov.given_others_gt_mean_var_seq2seq(variant=variant, teacher_forcing=tf, weights=w)
+    m.set_compute(mode).compile("Adam", "mean_squared_error")
+    assert m.count_params() == sum(v.size for v in w.values())
+    x = [enc, dec] if variant == "target_only" else [enc, oth, dec]
+    wt = kt.to_torch(w)
+    if variant == "target_only":
+        fwd = lambda ww, a, c: kt.given_others_seq2seq_forward(ww, a, t64(oth), c, variant, tf)
+    else:
+        fwd = lambda ww, a, b, c: kt.given_others_seq2seq_forward(ww, a, b, c, variant, tf)
+    l_ref, outs_ref, g_ref = kt.loss_and_grads(fwd, wt, [t64(a) for a in x], [t64(tgt)], [kt.mse])
+    got = m.predict_on_batch(x)
+    assert got.shape == (B, 10, 6)
+    assert np.abs(got - outs_ref[0].numpy()).max() < FWD_ATOL
+    ref_np = kn.given_others_seq2seq_forward({k: v.astype(np.float64) for k, v in w.items()}, enc.astype(np.float64),
+                                             oth.astype(np.float64), dec.astype(np.float64), variant, tf)
+    assert np.abs(got - ref_np).max() < FWD_ATOL
+    xs, ys = m._to_dev(x), m._to_dev([tgt])
+    m.gflat.zero_()
+    loss = m._loss(m._forward(xs, True), ys)
+    loss.backward()
+    assert abs(loss.item() - l_ref.item()) < 1e-4
+    for k in m.weight_order:
+        _grad_close(m.grads[k].cpu().numpy(), g_ref[k].numpy(), k)
+    opt = kt.KerasAdam(wt)
+    for step in range(5):
+        l_ref, _, g_ref = kt.loss_and_grads(fwd, wt, [t64(a) for a in x], [t64(tgt)], [kt.mse])
+        opt.step(g_ref)
+        l = m.train_on_batch(x, tgt)
+        assert abs(l - l_ref.item()) < 5e-4 * max(1.0, abs(l_ref.item())), (step, l, l_ref.item())
+    # Adam divides by sqrt(v): an element whose gradient sits at rounding-noise level (behind a relu that is almost
+    # always off) moves by up to lr per step in a direction the noise decides, so a handful of such elements may
+    # differ by a few lr after 5 steps; everything else agrees to 3e-4
+    for a, k in zip(m.get_weights(), m.weight_order):
+        err = np.abs(a - wt[k].detach().numpy())
+        assert (err > 3e-4).mean() < 1e-3 and err.max() < 2.5e-3, (k, err.max(), (err > 3e-4).sum())
+
+
 # ------------------------------------------------------------------ ConvLSTM weight gradient inside the persistent BPTT
 
 @pytest.mark.parametrize("B,T", [(1, 1), (4, 20), (131, 7), (7, 2)])
