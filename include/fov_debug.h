@@ -38,6 +38,13 @@ void fov_debug_seq_bwd_wgrad(int enable);
 void fov_debug_seq_bwd_nostack(int on);
 /* worker warps per image group of the persistent ConvLSTM / fc-LSTM forward (0 = default) */
 void fov_debug_seq_wpg(int wpg);
+/* persistent ConvLSTM kernels at small batches: 1 (default) = as few images per CTA as still fills the SMs, one group
+ * per CTA; 0 = always full 128-row groups */
+void fov_debug_seq_spread(int on);
+/* fp32 fc-LSTM kernels at small batches: 1 (default) = 4 / 8 sequences per CTA while the batch leaves SMs idle */
+void fov_debug_lstm_small_tiles(int on);
+/* fused ConvLSTM weight gradient: 1 = one tile per CTA even with few tiles (default 0: at least 4 tiles per CTA) */
+void fov_debug_wgrad_rows_full_grid(int on);
 void fov_debug_lstm_tc_wpg(int wpg);
 /* wide single-term (bf16) convolutions with two 128-row accumulator tiles per CTA: 0 never, 1 when the grid still
  * fills the machine (default), 2 whenever the tile fits */

@@ -21,6 +21,8 @@
 #include "fov_internal.h"
 #include "tc_common.cuh"
 
+extern int g_fov_seq_no_spread;      // convlstm_seq_tc.cu
+
 namespace {
 
 using namespace tc;
@@ -617,6 +619,10 @@ int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT, BwdP
   FOV_CHECK_ARG(F == 8 || F == 16 || F == 32 || F == 64, "F must be 8/16/32/64");
   pl.G = kRows / (sp.Hp * sp.Wp);
   FOV_CHECK_ARG(pl.G >= 1, "image larger than one MMA tile");
+  if (!g_fov_seq_no_spread) {        // small batches: as few images per CTA as still fills the machine (see convlstm_seq_tc.cu)
+    const int g_fill = (c->B + fov_num_sms() - 1) / fov_num_sms();
+    if (g_fill < pl.G) pl.G = g_fill < 1 ? 1 : g_fill;
+  }
   FOV_CHECK_ARG(sp.K_total / 16 <= kMaxSteps && (sp.K_total / 16) * (sp.NS * (sp.NS + 1) / 2) <= kMaxMmas, "too many k steps");
   FOV_CHECK_ARG(kRows * (F / 4) / kWorkers <= kMaxItems, "too many channels");
   pl.chunk_bytes = (uint32_t)sp.NS * (uint32_t)sg.term_bytes;

@@ -21,6 +21,9 @@
 #include "tc_common.cuh"
 #include <type_traits>
 
+// diagnostics / A-B (fov_debug_seq_spread): 1 = keep full image groups at small batches; shared with convlstm_seq_bwd_tc.cu
+int g_fov_seq_no_spread = 0;
+
 namespace {
 
 using namespace tc;
@@ -471,6 +474,15 @@ int seq_plan(const fov_convlstm_cfg* c, const TcConv& step, SeqPlan* out) {
   FOV_CHECK_ARG(F == 8 || F == 16 || F == 32 || F == 64, "F must be 8/16/32/64");
   pl.G = kRows / (sp.Hp * sp.Wp);
   FOV_CHECK_ARG(pl.G >= 1, "image larger than one MMA tile");
+  // Small batches (the reference trains at 32 / 64): the recurrence is latency bound and most SMs idle, so spread the
+  // images - as few per group as still fills the machine, one group per CTA.  An MMA step costs the same for 1 or 3
+  // images (M = 128 either way) but the gate algebra and the copies of a step shrink with the group.
+  const int sms = fov_num_sms();
+  if (!g_fov_seq_no_spread) {
+    const int g_fill = (c->B + sms - 1) / sms;
+    if (g_fill < pl.G) pl.G = g_fill < 1 ? 1 : g_fill;
+  }
+  const bool spread = !g_fov_seq_no_spread && (c->B + pl.G - 1) / pl.G <= sms;
   const int x_items = sp.seg[0].R * (1 << sp.seg[0].lpr_log2);
   FOV_CHECK_ARG(x_items <= kXI * kRows, "input frame too wide to prefetch");
   FOV_CHECK_ARG(sp.seg[0].taps <= kSeqMaxTaps && sp.seg[1].taps <= kSeqMaxTaps && sp.K_total / 16 <= kSeqMaxSteps,
@@ -492,7 +504,8 @@ int seq_plan(const fov_convlstm_cfg* c, const TcConv& step, SeqPlan* out) {
       const size_t grp = pl.grp_bytes + wpg * tile;                      // operands + the staging tiles of the group
       const size_t one = pl.act_off + grp + book, two = one + grp;
       int ng = 0;
-      if (2 * (one + 1024) <= 228 * 1024) ng = 1;                        // two CTAs per SM overlap each other
+      if (spread && one <= kUsable) ng = 1;                              // every group gets an SM of its own
+      else if (2 * (one + 1024) <= 228 * 1024) ng = 1;                   // two CTAs per SM overlap each other
       else if (two <= kUsable && 2 * 6 * F <= 512) ng = 2;               // one CTA per SM, two groups inside
       else if (round == 1 && one <= kUsable) ng = 1;
       if (!ng) continue;
@@ -550,6 +563,7 @@ int launch_seq_f(int F, const SeqParams& p, const SeqPlan& pl, int grid, cudaStr
 
 static int g_seq_disable = 0, g_seq_dbg = 0;
 extern "C" void fov_debug_seq_wpg(int wpg) { g_seq_wpg = wpg; }
+extern "C" void fov_debug_seq_spread(int on) { g_fov_seq_no_spread = !on; }
 extern "C" void fov_debug_seq_enable(int on) { g_seq_dbg = on; }
 extern "C" int fov_debug_seq_read(unsigned long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_seq_timeline, sizeof(unsigned long long) * 16);

@@ -14,6 +14,9 @@
 // diagnostics / A-B testing: -1 = never use the tensor-core forward, 0 = choose, 1 = whenever the shape allows
 static int g_lstm_tc_mode = 0;
 extern "C" void fov_debug_lstm_tc(int mode) { g_lstm_tc_mode = mode; }
+// diagnostics / A-B: 0 = never use the 4 / 8-sequence tiles of the fp32 kernels at small batches
+static int g_lstm_no_small = 0;
+extern "C" void fov_debug_lstm_small_tiles(int on) { g_lstm_no_small = !on; }
 // time-batched input projection in front of the tensor-core forward: -1 never, 0 choose (inputs wider than 16), 1 always
 int g_lstm_xproj_mode = 0;
 extern "C" void fov_debug_lstm_xproj(int mode) { g_lstm_xproj_mode = mode; }
@@ -102,10 +105,15 @@ __device__ __forceinline__ void lstm_fwd_phase(const PhaseDesc& ph, float* Wsm, 
     for (int k = 0; k < K; ++k) {
       const float4 w = *reinterpret_cast<const float4*>(&Wsm[k * kG + u * 4]);
       float a[SPT];
+      if constexpr (SPT % 4 == 0) {
 #pragma unroll
-      for (int q = 0; q < SPT / 4; ++q) {
-        float4 v = *reinterpret_cast<const float4*>(&cur[k * BTS + s0 + q * 4]);
-        a[q * 4 + 0] = v.x; a[q * 4 + 1] = v.y; a[q * 4 + 2] = v.z; a[q * 4 + 3] = v.w;
+        for (int q = 0; q < SPT / 4; ++q) {
+          float4 v = *reinterpret_cast<const float4*>(&cur[k * BTS + s0 + q * 4]);
+          a[q * 4 + 0] = v.x; a[q * 4 + 1] = v.y; a[q * 4 + 2] = v.z; a[q * 4 + 3] = v.w;
+        }
+      } else {                                   // small-batch tiles (1 / 2 sequences per thread)
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) a[i] = cur[k * BTS + s0 + i];
       }
 #pragma unroll
       for (int i = 0; i < SPT; ++i) {
@@ -317,13 +325,18 @@ __device__ __forceinline__ void lstm_bwd_phase(const BwdPhaseDesc& ph, float* UT
 #pragma unroll 4
     for (int j = 0; j < kG; ++j) {
       const float w = UT[j * kH + u];
+      if constexpr (SPT % 4 == 0) {
 #pragma unroll
-      for (int q = 0; q < SPT / 4; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(&dzs[j * BTS + s0 + q * 4]);
-        dhr[q * 4 + 0] = fmaf(w, v.x, dhr[q * 4 + 0]);
-        dhr[q * 4 + 1] = fmaf(w, v.y, dhr[q * 4 + 1]);
-        dhr[q * 4 + 2] = fmaf(w, v.z, dhr[q * 4 + 2]);
-        dhr[q * 4 + 3] = fmaf(w, v.w, dhr[q * 4 + 3]);
+        for (int q = 0; q < SPT / 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(&dzs[j * BTS + s0 + q * 4]);
+          dhr[q * 4 + 0] = fmaf(w, v.x, dhr[q * 4 + 0]);
+          dhr[q * 4 + 1] = fmaf(w, v.y, dhr[q * 4 + 1]);
+          dhr[q * 4 + 2] = fmaf(w, v.z, dhr[q * 4 + 2]);
+          dhr[q * 4 + 3] = fmaf(w, v.w, dhr[q * 4 + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) dhr[i] = fmaf(w, dzs[j * BTS + s0 + i], dhr[i]);
       }
     }
     if (ph.ar && t > 0) {
@@ -484,9 +497,19 @@ extern "C" int fov_lstm_seq2seq_fwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
   int spt = 16;
   if (fwd_smem_bytes(P.cfg, 16) > 200 * 1024 || cfg->B <= 32 * fov_num_sms()) spt = 8;
   if (cfg->B <= 48 * fov_num_sms()) spt = 4;
+  // small batches (the reference trains at 32 / 64): 8 / 4 sequences per CTA, one CTA per SM - the per-step chain of a
+  // thread shrinks with its sequences and the idle SMs take the rest
+  if (cfg->B <= 8 * fov_num_sms() && !g_lstm_no_small) spt = 2;
+  if (cfg->B <= 4 * fov_num_sms() && !g_lstm_no_small) spt = 1;
   const int bt = 4 * spt, grid = (cfg->B + bt - 1) / bt;
   const size_t smem = fwd_smem_bytes(P.cfg, spt);
   const bool hs = cfg->rec_act == FOV_REC_HARD_SIGMOID;
+  if (spt == 1)
+    return hs ? launch(lstm_seq2seq_fwd_kernel<1, FOV_REC_HARD_SIGMOID>, P, grid, smem, st)
+              : launch(lstm_seq2seq_fwd_kernel<1, FOV_REC_SIGMOID>, P, grid, smem, st);
+  if (spt == 2)
+    return hs ? launch(lstm_seq2seq_fwd_kernel<2, FOV_REC_HARD_SIGMOID>, P, grid, smem, st)
+              : launch(lstm_seq2seq_fwd_kernel<2, FOV_REC_SIGMOID>, P, grid, smem, st);
   if (spt == 4)
     return hs ? launch(lstm_seq2seq_fwd_kernel<4, FOV_REC_HARD_SIGMOID>, P, grid, smem, st)
               : launch(lstm_seq2seq_fwd_kernel<4, FOV_REC_SIGMOID>, P, grid, smem, st);
@@ -510,7 +533,9 @@ extern "C" int fov_lstm_seq2seq_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
   P.cfg = *cfg; P.w = *w; P.io = *io; P.g = *g;
   if (P.cfg.T_dec == 0) P.cfg.out_dim = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int spt = cfg->B <= 48 * fov_num_sms() ? 4 : 8;
+  int spt = cfg->B <= 48 * fov_num_sms() ? 4 : 8;
+  if (cfg->B <= 8 * fov_num_sms() && !g_lstm_no_small) spt = 2;      // small batches: see the forward dispatch
+  if (cfg->B <= 4 * fov_num_sms() && !g_lstm_no_small) spt = 1;
   const int bt = 4 * spt, grid = (cfg->B + bt - 1) / bt;
   const size_t smem = bwd_smem_bytes(spt);
   const bool hsb = cfg->rec_act == FOV_REC_HARD_SIGMOID;
@@ -519,6 +544,12 @@ extern "C" int fov_lstm_seq2seq_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
   if (cfg->math != FOV_MATH_FP32 && g_lstm_tc_mode >= 0 && g_lstm_bptt_tc && lstm_tc_bwd_supported(cfg) &&
       (g_lstm_tc_mode > 0 || cfg->B >= kTcTrainMinB))
     rc = lstm_tc_bwd(&P.cfg, w, io, g, st);
+  else if (spt == 1)
+    rc = hsb ? launch(lstm_seq2seq_bwd_kernel<1, FOV_REC_HARD_SIGMOID>, P, grid, smem, st)
+             : launch(lstm_seq2seq_bwd_kernel<1, FOV_REC_SIGMOID>, P, grid, smem, st);
+  else if (spt == 2)
+    rc = hsb ? launch(lstm_seq2seq_bwd_kernel<2, FOV_REC_HARD_SIGMOID>, P, grid, smem, st)
+             : launch(lstm_seq2seq_bwd_kernel<2, FOV_REC_SIGMOID>, P, grid, smem, st);
   else if (spt == 4)
     rc = hsb ? launch(lstm_seq2seq_bwd_kernel<4, FOV_REC_HARD_SIGMOID>, P, grid, smem, st)
              : launch(lstm_seq2seq_bwd_kernel<4, FOV_REC_SIGMOID>, P, grid, smem, st);

@@ -474,7 +474,9 @@ int launch(const WrParams& p, int grid, size_t smem, cudaStream_t st) {
 
 }  // namespace
 
-static int g_wr_disable = 0, g_wr_dbg = 0;
+static int g_wr_disable = 0, g_wr_dbg = 0, g_wr_full_grid = 0;
+// diagnostics / A-B: 1 = one tile per CTA even when there are few tiles
+extern "C" void fov_debug_wgrad_rows_full_grid(int on) { g_wr_full_grid = on; }
 extern "C" void fov_debug_wgrad_rows_timeline(int on) { g_wr_dbg = on; }
 extern "C" int fov_debug_wgrad_rows_read(unsigned long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_wr_timeline, sizeof(unsigned long long) * 8);
@@ -497,6 +499,11 @@ int tc_wgrad_rows_run(const TcWgradRows& c, cudaStream_t st) {
   if (rc) return rc;
   p.dbg = g_wr_dbg;
   int grid = p.ntiles < 2 * fov_num_sms() ? p.ntiles : 2 * fov_num_sms();
+  // every CTA ends with a red.global.add of its whole accumulator (4F x taps*(Cx+F) floats onto the same addresses):
+  // with few tiles (small batches) give each CTA at least kMinTiles of them - fewer, longer CTAs beat 296 contending
+  // epilogues (B=32: 94 us per layer with one tile per CTA)
+  constexpr int kMinTiles = 4;
+  if (!g_wr_full_grid && p.ntiles < kMinTiles * grid) grid = (p.ntiles + kMinTiles - 1) / kMinTiles;
   if (grid < 1) grid = 1;
   switch (c.math) {
     case 1: return launch<1>(p, grid, smem, st);

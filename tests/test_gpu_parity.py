@@ -195,7 +195,7 @@ def test_hit_rate_matches_reference_golden(golden):
 
 # ------------------------------------------------------------------ fc-LSTM
 
-@pytest.mark.parametrize("B", [1, 7, 33, 70])
+@pytest.mark.parametrize("B", [1, 7, 33, 70, 700, 1300])
 @pytest.mark.parametrize("tf,in_enc", [(True, 90), (False, 90), (False, 6), (True, 6)])
 def test_lstm_seq2seq_forward(B, tf, in_enc):
     fov = _cuda()
@@ -249,7 +249,7 @@ def test_encoder_decoder_submodels_match_host_loop():
     assert np.abs(one - ref).max() < 2e-5
 
 
-@pytest.mark.parametrize("tf,in_enc,B", [(True, 90, 37), (False, 90, 9), (False, 6, 64), (True, 6, 3)])
+@pytest.mark.parametrize("tf,in_enc,B", [(True, 90, 37), (False, 90, 9), (False, 6, 64), (True, 6, 3), (False, 6, 650), (True, 90, 1250)])
 def test_lstm_seq2seq_gradients(tf, in_enc, B):
     fov = _cuda()
     rng = np.random.default_rng(11)
