@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfov360.so")
 ACT = {None: 0, "linear": 0, "tanh": 1, "relu": 2}
 # arithmetic of the convolution / dense / ConvLSTM family (include/fov360.h FOV_MATH_*):
 # fp32 = CUDA-core kernels; bf16 / bf16x2 / bf16x3 = tcgen05 kernels with 1 / 2 / 3 bf16 terms per
-# operand and fp32 accumulation in tensor memory (bf16x2 is fp32-grade: ~1e-5 max-abs error)
+# operand and fp32 accumulation in tensor memory (bf16x2: ~16 mantissa bits, ~1e-5 max-abs forward error, inside the 1e-4 bar; bf16x3 is the fp32-grade mode)
 MATH = {"fp32": 0, "bf16": 1, "bf16x2": 2, "bf16x3": 3}
 REC = {"hard_sigmoid": 0, "sigmoid": 1}
 

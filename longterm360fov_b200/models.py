@@ -171,7 +171,7 @@ class Model:
         self._seeds = {}
         self.running_length = 10
         # arithmetic of the conv / dense / ConvLSTM kernels (ops.set_math): tensor cores with 2 bf16
-        # terms per operand by default (fp32-grade results); "fp32" selects the CUDA-core kernels
+        # terms per operand by default (~16 mantissa bits, forward error ~1e-5); "fp32" selects the CUDA-core kernels
         self.compute = os.environ.get("FOV_COMPUTE", "bf16x2")
         self._graphs, self._use_graphs = {}, False
 

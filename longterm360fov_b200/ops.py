@@ -46,7 +46,7 @@ _MATH = [_lib.MATH["bf16x2"]]
 
 
 def set_math(mode):
-    """mode: 'fp32' (CUDA cores), 'bf16', 'bf16x2' (default, fp32-grade on tensor cores), 'bf16x3'."""
+    """mode: 'fp32' (CUDA cores), 'bf16', 'bf16x2' (default: 2 bf16 terms per operand, ~16 mantissa bits), 'bf16x3' (3 terms, fp32-grade)."""
     _MATH[0] = _lib.MATH[mode] if isinstance(mode, str) else int(mode)
 
 
