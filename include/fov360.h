@@ -158,6 +158,15 @@ int fov_act_bwd(int act, long long rows, int cols, const float* y, long long y_s
                 const float* dy, long long dy_stride, float* dpre, long long dpre_stride,
                 void* stream);
 
+/* Tap-stacked narrow convolutions (Cout <= 32, e.g. the 1024 -> 30 head of mycode/convlstm_seq2seq.py:179-181): the
+ * caller runs the kh x 1 convolution with Cout' = kw*Cp stacked output columns (tx, c) on fov_conv2d_fwd_tc and folds
+ * the kw column taps here: y[r,w,c] = act(bias[c] + sum_tx yp[r, w+tx-pad_w, tx*Cp+c]); rows = N*H image rows.
+ * fov_tapstack_expand is the transpose for the backward pass: dyp[r,w,tx*Cp+c] = dpre[r, w-tx+pad_w, c] (else 0). */
+int fov_tapstack_reduce(long long rows, int W, int kw, int pad_w, int Cp, int Cout, const float* yp, const float* bias,
+                        int act, float* y, void* stream);
+int fov_tapstack_expand(long long rows, int W, int kw, int pad_w, int Cp, int Cout, const float* dpre, float* dyp,
+                        void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Tensor-core (tcgen05 / TMEM) forms of the convolution family.
  * Same operands and semantics as fov_conv2d_fwd / _bwd_data / _bwd_weight; the

@@ -107,6 +107,8 @@ SYMBOLS = {
     "fov_conv_wgrad_ws_bytes": (C.c_size_t, [C.POINTER(ConvCfg), _I]),
     "fov_conv2d_bwd_weight_tc_ws": (_I, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P, _I, _P]),
     "fov_act_bwd": (_I, [_I, _LL, _I, _P, _LL, _P, _LL, _P, _LL, _P]),
+    "fov_tapstack_reduce": (_I, [_LL, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
+    "fov_tapstack_expand": (_I, [_LL, _I, _I, _I, _I, _I, _P, _P, _P]),
     "fov_convlstm_fwd": (_I, [C.POINTER(ConvLstmCfg), C.POINTER(ConvLstmIO), _P]),
     "fov_convlstm_fwd_ws_bytes": (C.c_size_t, [C.POINTER(ConvLstmCfg)]),
     "fov_convlstm_bwd_ws_floats": (C.c_size_t, [C.POINTER(ConvLstmCfg)]),

@@ -453,3 +453,68 @@ extern "C" int fov_act_bwd(int act, long long rows, int cols, const float* y, lo
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Tap-stacked narrow convolutions (the 1024 -> 30 head of convlstm_seq2seq, mycode/convlstm_seq2seq.py:179-181, and
+// the 1024 -> 3 Conv1D head, :187-189).  With Cout <= 32 a kh x kw convolution issues kh*kw tcgen05.mma of N = 32 per
+// k-step, each at the ~45-cycle floor of a small-N MMA.  The host instead runs the kh x 1 convolution
+//   Y'[n,h,w,(tx,c)] = sum_{ty,ci} x[n,h+ty-ph,w,ci] * K[ty,tx,ci,c]          (Cout' = kw*Cp columns: kw x fewer MMAs)
+// on the same shifted-tap kernel and these two kernels fold / unfold the kw column taps:
+//   y[n,h,w,c] = act(b[c] + sum_tx Y'[n,h,w+tx-pw,(tx,c)])            dY'[n,h,w',(tx,c)] = dpre[n,h,w'-tx+pw,c]
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) tapstack_reduce_kernel(long long rows, int W, int kw, int pad_w, int Cp, int Cout,
+                                                              const float* __restrict__ yp, const float* __restrict__ bias,
+                                                              int act, float* __restrict__ y) {
+  const long long total = rows * W * Cout;
+  const int CW = kw * Cp;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % Cout);
+    const long long pw = e / Cout;
+    const int w = (int)(pw % W);
+    const long long r = pw / W;
+    float acc = bias ? __ldg(&bias[c]) : 0.0f;
+    for (int tx = 0; tx < kw; ++tx) {
+      const int ws = w + tx - pad_w;
+      if (ws >= 0 && ws < W) acc += __ldg(&yp[(r * W + ws) * CW + tx * Cp + c]);
+    }
+    y[e] = fov_act(act, acc);
+  }
+}
+__global__ void __launch_bounds__(256) tapstack_expand_kernel(long long rows, int W, int kw, int pad_w, int Cp, int Cout,
+                                                              const float* __restrict__ dpre, float* __restrict__ dyp) {
+  const int CW = kw * Cp;
+  const long long total = rows * W * CW;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(e % CW);
+    const long long pw = e / CW;
+    const int w = (int)(pw % W);
+    const long long r = pw / W;
+    const int tx = col / Cp, c = col - tx * Cp;
+    const int wd = w - tx + pad_w;
+    float v = 0.0f;
+    if (c < Cout && wd >= 0 && wd < W) v = __ldg(&dpre[(r * W + wd) * Cout + c]);
+    dyp[e] = v;
+  }
+}
+}  // namespace
+
+extern "C" int fov_tapstack_reduce(long long rows, int W, int kw, int pad_w, int Cp, int Cout, const float* yp,
+                                   const float* bias, int act, float* y, void* stream) {
+  FOV_CHECK_ARG(rows > 0 && W > 0 && kw > 0 && pad_w >= 0 && pad_w < kw && Cp >= Cout && Cout > 0 && yp && y, "bad args");
+  long long blocks = (rows * W * Cout + 255) / 256;
+  if (blocks > 8LL * fov_num_sms()) blocks = 8LL * fov_num_sms();
+  tapstack_reduce_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(rows, W, kw, pad_w, Cp, Cout, yp, bias, act, y);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}
+
+extern "C" int fov_tapstack_expand(long long rows, int W, int kw, int pad_w, int Cp, int Cout, const float* dpre,
+                                   float* dyp, void* stream) {
+  FOV_CHECK_ARG(rows > 0 && W > 0 && kw > 0 && pad_w >= 0 && pad_w < kw && Cp >= Cout && Cout > 0 && dpre && dyp, "bad args");
+  long long blocks = (rows * W * kw * Cp + 255) / 256;
+  if (blocks > 8LL * fov_num_sms()) blocks = 8LL * fov_num_sms();
+  tapstack_expand_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(rows, W, kw, pad_w, Cp, Cout, dpre, dyp);
+  FOV_CUDA_LAUNCH_CHECK();
+  return FOV_OK;
+}

@@ -341,9 +341,109 @@ def _packed_weights(lib, cache, cfg, kernel, math, bwd_data):
     return ws
 
 
+class TapStackConvFn(torch.autograd.Function):
+    """Narrow convolution (Cout <= 32 over >= 128 input channels: the 1024 -> 30 Conv2D head of
+    mycode/convlstm_seq2seq.py:179-181, the 1024 -> 3 Conv1D head of :187-189) on the tensor-core conv kernels with
+    the kw column taps STACKED along the output channels: a kh x kw convolution with N = 32 issues kh*kw small
+    tcgen05.mma per k-step, each at the ~45-cycle floor of a narrow MMA; the kh x 1 convolution onto kw*Cp stacked
+    columns (tx, c) issues kw x fewer, kw x wider ones, and fov_tapstack_reduce folds the taps
+    (y[n,h,w,c] = act(b[c] + sum_tx Y'[n,h,w+tx-pw,(tx,c)])).  Backward: the transpose unfold, then the ordinary
+    backward-data / weight-gradient kernels on the stacked problem; the stacked weight gradient is folded back into the
+    Keras-layout sink.  Same operands, semantics and sinks as Conv2DFn."""
+
+    @staticmethod
+    def stacked_kernel(kernel, Cp, cache):
+        """(kh,kw,Cin,Cout) -> (kh,1,Cin,kw*Cp), columns (tx, c), zero columns for c >= Cout; cached per pass."""
+        key = ("tapstack", kernel.data_ptr(), tuple(kernel.shape), Cp)
+        if cache is not None and key in cache:
+            return cache[key]
+        kh, kw, Cin, Cout = kernel.shape
+        ks = torch.zeros(kh, 1, Cin, kw * Cp, device=kernel.device)
+        ks.view(kh, Cin, kw, Cp)[..., :Cout] = kernel.detach().permute(0, 2, 1, 3)
+        if cache is not None:
+            cache[key] = ks
+        return ks
+
+    @staticmethod
+    def forward(ctx, opts, sinks, x, kernel, bias):
+        lib = _lib.load()
+        _require_cuda(x, kernel)
+        x = _f32c(x)
+        N, H, W, Cin = x.shape
+        kh, kw, kc, Cout = kernel.shape
+        _expect(kc == Cin, "TapStackConvFn: kernel expects %d input channels, x has %d", kc, Cin)
+        _expect(bias is None or bias.numel() == Cout, "TapStackConvFn: bias does not have Cout=%d elements", Cout)
+        act, math, cache = opts.get("activation"), opts.get("math", _MATH[0]), opts.get("pack_cache")
+        Cp = (Cout + 15) // 16 * 16
+        CW = kw * Cp
+        ks = TapStackConvFn.stacked_kernel(kernel, Cp, cache)
+        cfg = _conv_cfg(N, H, W, Cin, CW, kh, 1, (1, 1), None, 0.0, H * W * Cin, Cin, H * W * CW, CW)
+        yp = torch.empty(N, H, W, CW, device=x.device)
+        ws = _packed_weights(lib, cache, cfg, ks, math, 0)
+        _lib.check(lib.fov_conv2d_fwd_tc_packed(C.byref(cfg), ptr(x), None, ptr(yp), ptr(ws), math, _stream()),
+                   "fov_conv2d_fwd_tc_packed")
+        y = torch.empty(N, H, W, Cout, device=x.device)
+        pad_w = (kw - 1) // 2
+        _lib.check(lib.fov_tapstack_reduce(N * H, W, kw, pad_w, Cp, Cout, ptr(yp), ptr(bias), ACT[act], ptr(y), _stream()),
+                   "fov_tapstack_reduce")
+        if opts.get("training", False):
+            ctx.cfg, ctx.sinks, ctx.act, ctx.math, ctx.cache = cfg, sinks, act, math, cache
+            ctx.geom = (N, H, W, Cin, kh, kw, Cout, Cp, pad_w)
+            ctx.need_dx = ctx.needs_input_grad[2]
+            ctx.save_for_backward(x, kernel, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, kernel, y = ctx.saved_tensors
+        N, H, W, Cin, kh, kw, Cout, Cp, pad_w = ctx.geom
+        cfg, math, st = ctx.cfg, ctx.math, _stream()
+        dy = _f32c(dy)
+        if ctx.act not in (None, "linear"):
+            dpre = torch.empty_like(y)
+            _lib.check(lib.fov_act_bwd(ACT[ctx.act], N * H * W, Cout, ptr(y), Cout, ptr(dy), Cout, ptr(dpre), Cout, st),
+                       "fov_act_bwd")
+        else:
+            dpre = dy
+        CW = kw * Cp
+        dyp = torch.empty(N, H, W, CW, device=x.device)
+        _lib.check(lib.fov_tapstack_expand(N * H, W, kw, pad_w, Cp, Cout, ptr(dpre), ptr(dyp), st), "fov_tapstack_expand")
+        gw, gb = ctx.sinks
+        gws = torch.zeros(kh, 1, Cin, CW, device=x.device)
+        gbs = torch.zeros(CW, device=x.device) if gb is not None else None
+        nws = lib.fov_conv_wgrad_ws_bytes(C.byref(cfg), math)
+        wws = _ws(nws, x.device) if nws else None
+        _lib.check(lib.fov_conv2d_bwd_weight_tc_ws(C.byref(cfg), ptr(x), ptr(dyp), ptr(gws), ptr(gbs), ptr(wws), math, st),
+                   "fov_conv2d_bwd_weight_tc_ws")
+        gw.view(kh, kw, Cin, Cout).add_(gws.view(kh, Cin, kw, Cp)[..., :Cout].permute(0, 2, 1, 3))
+        if gb is not None:                  # the centre tap's columns are dpre itself (shift 0): their sums are the bias gradient
+            gb += gbs[pad_w * Cp:pad_w * Cp + Cout]
+        dx = None
+        if ctx.need_dx:
+            dx = torch.empty_like(x)
+            ks = TapStackConvFn.stacked_kernel(kernel, Cp, ctx.cache)
+            ws = _packed_weights(lib, ctx.cache, cfg, ks, math, 1)
+            _lib.check(lib.fov_conv2d_bwd_data_tc_packed(C.byref(cfg), ptr(dyp), ptr(dx), ptr(ws), math, st),
+                       "fov_conv2d_bwd_data_tc_packed")
+        return None, None, dx, None, None
+
+
+_TAPSTACK = [True]          # A/B switch (set_tapstack)
+
+
+def set_tapstack(on):
+    """Diagnostics: route narrow wide-input convolutions through TapStackConvFn (default) or the plain kernel."""
+    _TAPSTACK[0] = bool(on)
+
+
 def conv2d(x, kernel, bias, activation=None, dilation=(1, 1), sinks=None, training=False, pack_cache=None):
-    return Conv2DFn.apply({"activation": activation, "dilation": dilation, "training": training,
-                           "pack_cache": pack_cache}, sinks, x, kernel, bias)
+    opts = {"activation": activation, "dilation": dilation, "training": training, "pack_cache": pack_cache}
+    kh, kw, Cin, Cout = kernel.shape
+    if (_TAPSTACK[0] and _MATH[0] != 0 and tuple(dilation) == (1, 1) and kw >= 3 and Cout <= 32 and Cin >= 128 and
+            kw * ((Cout + 15) // 16 * 16) <= 256):
+        return TapStackConvFn.apply(opts, sinks, x, kernel, bias)
+    return Conv2DFn.apply(opts, sinks, x, kernel, bias)
 
 
 def dense(x, kernel, bias, activation=None, sinks=None, training=False):
@@ -455,8 +555,7 @@ def dual_dense(x, W1, b1, W2, b2, t0, sinks1=None, sinks2=None, training=False):
 
 def conv1d(x, kernel, bias, activation=None, sinks=None, training=False):
     """keras Conv1D(padding='same'): x (B,L,Cin), kernel (k,Cin,Cout)."""
-    y = Conv2DFn.apply({"activation": activation, "training": training}, sinks, x.unsqueeze(1),
-                       kernel.unsqueeze(0), bias)
+    y = conv2d(x.unsqueeze(1), kernel.unsqueeze(0), bias, activation, (1, 1), sinks, training)
     return y.squeeze(1)
 
 
