@@ -7,9 +7,11 @@ from .callbacks import EarlyStopping, ModelCheckpoint, ReduceLROnPlateau
 from .pipeline import M3VideoBatches
 from .models import (Adam, ConvLSTMSeq2Seq, FovSeq2Seq, Model, OthersLSTMSpanWhole, RMSprop,
                      convlstm_seq2seq, fov_seq2seq, fov_seq2seq_mu_var, others_lstm_span_whole,
-                     StackedFovSeq2Seq, stacked_fov_seq2seq, GivenOthersSeq2Seq, given_others_gt_mean_var_seq2seq)
+                     StackedFovSeq2Seq, stacked_fov_seq2seq, GivenOthersSeq2Seq, given_others_gt_mean_var_seq2seq,
+                     OthersConvLSTMTarget, others_convlstm_target)
 
 __all__ = ["fov_seq2seq", "fov_seq2seq_mu_var", "others_lstm_span_whole", "convlstm_seq2seq",
            "Model", "FovSeq2Seq", "OthersLSTMSpanWhole", "ConvLSTMSeq2Seq", "Adam", "RMSprop",
            "ModelCheckpoint", "ReduceLROnPlateau", "EarlyStopping", "M3VideoBatches", "StackedFovSeq2Seq",
-           "stacked_fov_seq2seq", "GivenOthersSeq2Seq", "given_others_gt_mean_var_seq2seq"]
+           "stacked_fov_seq2seq", "GivenOthersSeq2Seq", "given_others_gt_mean_var_seq2seq",
+           "OthersConvLSTMTarget", "others_convlstm_target"]

@@ -136,3 +136,25 @@ def init_given_others_seq2seq(seed=1, num_user=34, latent_dim=32, num_encoder_to
         if variant == "mlp_mixing":
             _dense(rng, oth + num_decoder_tokens, num_decoder_tokens, "mixing", w)
     return w
+
+
+def init_others_convlstm_target(seed=1, num_user=34, kernel_size=5, oth_filters=(32, 16, 8), tar_filters=(8, 4, 2)):
+    """All-ConvLSTM form of mycode/others_LSTM_span_whole.py (use_fclstm_tar=False, :133-199), raw xyz layout."""
+    rng = np.random.default_rng(seed)
+    w = {}
+    cin = (num_user - 1) * 3
+    for l, f in enumerate(oth_filters):
+        _convlstm(rng, 1, kernel_size, cin, f, "oth_convlstm%d" % l, w)
+        cin = f
+    cin = 3
+    for l, f in enumerate(tar_filters):
+        _convlstm(rng, 1, kernel_size, cin, f, "tar_enc_convlstm%d" % l, w)
+        cin = f
+    cin = 3 + sum(oth_filters)
+    for l, f in enumerate(tar_filters):
+        _convlstm(rng, 1, kernel_size, cin, f, "tar_dec_convlstm%d" % l, w)
+        cin = f
+    _dense(rng, sum(oth_filters), (num_user - 1) * 3, "oth_recon_dense", w)
+    _dense(rng, sum(tar_filters), 3, "encoder_dense", w)
+    _dense(rng, sum(tar_filters), 3, "decoder_dense", w)
+    return w

@@ -944,6 +944,73 @@ def others_lstm_span_whole(latent_dim=64, num_user=34, kernel_size=5, max_encode
                                recurrent_activation, dropout, device)
 
 
+class OthersConvLSTMTarget(Model):
+    """The all-ConvLSTM form of mycode/others_LSTM_span_whole.py (use_fclstm_tar = False, :133-199,273-317) in the raw
+    xyz layout (cfg.input_mean_var = cfg.predict_mean_var = False, the defaults of mycode/config.py:69-75): the
+    target viewer's past runs through its own ConvLSTM2D stack (latent_dim_target = 8 / 4 / 2 filters, kernel (1,5)),
+    and every future second a three-layer one-step decoder stack - seeded by the encoder states - reads the channel
+    concat [last output (fps,3) ; others' ConvLSTM state of that second (fps,56)] (:273-275); Dense(3) on the
+    concatenated decoder states is the output and the next input (:296,317).  Aux heads as in M3:
+    Dense((num_user-1)*3) on the others' state of all 20 seconds, Dense(3,tanh) on the target's past state.
+    (As shipped the script stops at a NameError, SURVEY.md hazard 1; this is the graph it describes.)
+    Runs on the same kernels as M3 / M4: the persistent ConvLSTM kernels for the two 10 / 20-step stacks, one-step calls
+    with carried states for the decoder (filters 4 and 2 take the fp32 CUDA-core ConvLSTM kernels)."""
+
+    n_inputs, n_outputs = 3, 3
+    weight_order = (
+        ["%s_convlstm%d/%s" % (s, l, n) for s in ("oth", "tar_enc", "tar_dec") for l in range(3)
+         for n in ("kernel", "recurrent_kernel", "bias")] +
+        ["oth_recon_dense/kernel", "oth_recon_dense/bias", "encoder_dense/kernel", "encoder_dense/bias",
+         "decoder_dense/kernel", "decoder_dense/bias"])
+
+    def __init__(self, weights, max_encoder_seq_length=10, recurrent_activation="hard_sigmoid", device=None):
+        super().__init__(weights, device)
+        self.T_enc = max_encoder_seq_length
+        self.rec_act = recurrent_activation
+
+    def _stack(self, prefix, x, states, training):
+        p, g = self.params, self.grads
+        names = ("kernel", "recurrent_kernel", "bias")
+        wl = [tuple(p["%s_convlstm%d/%s" % (prefix, l, n)] for n in names) for l in range(3)]
+        sl = [tuple(g["%s_convlstm%d/%s" % (prefix, l, n)] for n in names) for l in range(3)] if training else None
+        return ops.convlstm_stack(x, wl, states, sl, rec_act=self.rec_act, training=training)
+
+    def _dense(self, name, x, act, training):
+        p = self.params
+        return ops.dense(x, p[name + "/kernel"], p[name + "/bias"], act,
+                         self._sinks(name + "/kernel", name + "/bias"), training)
+
+    def _forward(self, inputs, training):
+        enc_in, oth_in, dec_in = inputs
+        Tdec = oth_in.shape[1] - self.T_enc
+        oth_seq, _ = self._stack("oth", oth_in, None, training)
+        r_oth = self._dense("oth_recon_dense", oth_seq, None, training)
+        pst, states = self._stack("tar_enc", enc_in, None, training)
+        r_tar = self._dense("encoder_dense", pst, "tanh", training)
+        x = dec_in
+        outs = []
+        for t in range(Tdec):
+            cat_in = torch.cat([x, oth_seq[:, self.T_enc + t:self.T_enc + t + 1]], dim=-1)
+            dstate, states = self._stack("tar_dec", cat_in, states, training)
+            y = self._dense("decoder_dense", dstate, None, training)
+            outs.append(y)
+            x = y
+        return [torch.cat(outs, dim=1), r_oth, r_tar]
+
+
+def others_convlstm_target(num_user=34, kernel_size=5, max_encoder_seq_length=10, oth_filters=(32, 16, 8),
+                           tar_filters=(8, 4, 2), recurrent_activation="hard_sigmoid", weights=None, seed=1,
+                           device=None):
+    """Builder for the all-ConvLSTM form of mycode/others_LSTM_span_whole.py (use_fclstm_tar=False): inputs
+    ``[encoder_inputs (B,10,1,fps,3), encoder_inputs_oth (B,20,1,fps,(num_user-1)*3), decoder_inputs (B,1,1,fps,3)]`` ->
+    ``[decoder_outputs (B,10,1,fps,3), decoder_outputs_oth (B,20,1,fps,(num_user-1)*3), encoder_reconstruct_tar
+    (B,10,1,fps,3)]``."""
+    if weights is None:
+        weights = _init_weights("init_others_convlstm_target", seed=seed, num_user=num_user, kernel_size=kernel_size,
+                                oth_filters=oth_filters, tar_filters=tar_filters)
+    return OthersConvLSTMTarget(weights, max_encoder_seq_length, recurrent_activation, device)
+
+
 # --------------------------------------------------------------------------- #
 # M4: ConvLSTM encoder-decoder (heatmap / trajectory forms)
 # --------------------------------------------------------------------------- #

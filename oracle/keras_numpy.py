@@ -771,6 +771,56 @@ def others_lstm_span_whole_forward(w, enc_in, oth_in, dec_in, recurrent_activati
     return [np.stack(outs, axis=1), r_oth, r_tar]
 
 
+def init_others_convlstm_target(seed=1, num_user=34, kernel_size=5, oth_filters=(32, 16, 8), tar_filters=(8, 4, 2)):
+    """Weights of the all-ConvLSTM form of mycode/others_LSTM_span_whole.py (use_fclstm_tar=False, :133-199, raw xyz
+    layout: cfg.input_mean_var = cfg.predict_mean_var = False, the defaults of mycode/config.py:69-75): others' stack
+    on (1,fps,(num_user-1)*3) images, a target encoder stack and a target decoder stack of latent_dim_target = 8 / 4 / 2
+    filters (the decoder reads [its own last output ; others' state of that second], 3 + 56 channels), Dense((num_user-1)*3)
+    on the others' state, Dense(3,tanh) on the target's past state, Dense(3) on the decoder state."""
+    rng = np.random.default_rng(seed)
+    w = {}
+    cin = (num_user - 1) * 3
+    for l, f in enumerate(oth_filters):
+        init_convlstm(rng, 1, kernel_size, cin, f, "oth_convlstm%d" % l, w)
+        cin = f
+    cin = 3
+    for l, f in enumerate(tar_filters):
+        init_convlstm(rng, 1, kernel_size, cin, f, "tar_enc_convlstm%d" % l, w)
+        cin = f
+    cin = 3 + sum(oth_filters)
+    for l, f in enumerate(tar_filters):
+        init_convlstm(rng, 1, kernel_size, cin, f, "tar_dec_convlstm%d" % l, w)
+        cin = f
+    init_dense(rng, sum(oth_filters), (num_user - 1) * 3, "oth_recon_dense", w)
+    init_dense(rng, sum(tar_filters), 3, "encoder_dense", w)
+    init_dense(rng, sum(tar_filters), 3, "decoder_dense", w)
+    return w
+
+
+def others_convlstm_target_forward(w, enc_in, oth_in, dec_in, recurrent_activation="hard_sigmoid"):
+    """mycode/others_LSTM_span_whole.py:80-102,133-199,226-349 with use_fclstm_tar=False in the raw layout:
+    enc_in (B,10,1,fps,3), oth_in (B,20,1,fps,(U-1)*3), dec_in (B,1,1,fps,3) ->
+    [decoder_outputs (B,10,1,fps,3), decoder_outputs_oth (B,20,1,fps,(U-1)*3), encoder_reconstruct_tar (B,10,1,fps,3)].
+    Per future second: decoder input = channel concat [last output ; others' state] (:273-275), three one-step
+    ConvLSTMs seeded by the encoder states, Dense(3) on their concatenated states (:296), output re-fed (:317)."""
+    ra = recurrent_activation
+    Tenc = enc_in.shape[1]
+    Tdec = oth_in.shape[1] - Tenc
+    oth_seq, _ = others_convlstm_stack(w, oth_in, recurrent_activation=ra)
+    r_oth = dense(oth_seq, w["oth_recon_dense/kernel"], w["oth_recon_dense/bias"])
+    pst, states = others_convlstm_stack(w, enc_in, "tar_enc_convlstm", recurrent_activation=ra)
+    r_tar = dense(pst, w["encoder_dense/kernel"], w["encoder_dense/bias"], "tanh")
+    x = dec_in
+    outs = []
+    for t in range(Tdec):
+        cat_in = np.concatenate([x, oth_seq[:, Tenc + t:Tenc + t + 1]], axis=-1)
+        dstate, states = others_convlstm_stack(w, cat_in, "tar_dec_convlstm", h0c0=states, recurrent_activation=ra)
+        y = dense(dstate, w["decoder_dense/kernel"], w["decoder_dense/bias"])
+        outs.append(y)
+        x = y
+    return [np.concatenate(outs, axis=1), r_oth, r_tar]
+
+
 def init_convlstm_seq2seq(seed=1, in_ch=30, filters=(32, 16, 8), kernel_size=5,
                           head=(512, 1024, 30), head_kind="conv2d", head_kernel=None,
                           flat_dim=None):

@@ -248,6 +248,25 @@ def others_lstm_span_whole_forward(w, enc_in, oth_in, dec_in, ra="hard_sigmoid")
     return [torch.stack(outs, 1), r_oth, r_tar]
 
 
+def others_convlstm_target_forward(w, enc_in, oth_in, dec_in, ra="hard_sigmoid"):
+    """All-ConvLSTM form of mycode/others_LSTM_span_whole.py (see oracle/keras_numpy.py)."""
+    Tenc = enc_in.shape[1]
+    Tdec = oth_in.shape[1] - Tenc
+    oth_seq, _ = convlstm_stack(w, oth_in, "oth_convlstm", ra=ra)
+    r_oth = dense(oth_seq, w["oth_recon_dense/kernel"], w["oth_recon_dense/bias"])
+    pst, states = convlstm_stack(w, enc_in, "tar_enc_convlstm", ra=ra)
+    r_tar = dense(pst, w["encoder_dense/kernel"], w["encoder_dense/bias"], "tanh")
+    x = dec_in
+    outs = []
+    for t in range(Tdec):
+        cat_in = torch.cat([x, oth_seq[:, Tenc + t:Tenc + t + 1]], dim=-1)
+        dstate, states = convlstm_stack(w, cat_in, "tar_dec_convlstm", h0c0=states, ra=ra)
+        y = dense(dstate, w["decoder_dense/kernel"], w["decoder_dense/bias"])
+        outs.append(y)
+        x = y
+    return [torch.cat(outs, dim=1), r_oth, r_tar]
+
+
 def gaussian_resample(muvar, noise, mode="var_as_std"):
     """(B,6) [mu | var] + (B,30,3) N(0,1) noise -> (B,30,3); differentiable in muvar like K.random_normal(mean, stddev)
     (mycode/convlstm_seq2seq.py:51-60; others_LSTM_span_whole.py:64-71; utility.py:73-80)."""

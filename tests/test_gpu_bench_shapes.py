@@ -687,6 +687,52 @@ def test_given_others_mean_var_seq2seq(variant, tf, mode):
         assert (err > 3e-4).mean() < 1e-3 and err.max() < 2.5e-3, (k, err.max(), (err > 3e-4).sum())
 
 
+# ------------------------------------------------------------------ sibling model: all-ConvLSTM target (decoder-input concat)
+
+@pytest.mark.parametrize("num_user,B", [(6, 5), (34, 3)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16x2"])
+def test_others_convlstm_target(num_user, B, mode):
+    """mycode/others_LSTM_span_whole.py with use_fclstm_tar=False (:133-199,273-317), raw xyz layout: target encoder
+    and one-step decoder ConvLSTM stacks of 8 / 4 / 2 filters, decoder input = [last output ; others' state], three
+    outputs and 3 x MSE: forward (1e-4), loss, every gradient and 4 Adam steps against the float64 oracle."""
+    fov = _cuda()
+    rng = np.random.default_rng(num_user + B)
+    w = _perturb(kn.init_others_convlstm_target(seed=7, num_user=num_user), 8, 0.05)
+    C = (num_user - 1) * 3
+    enc = rng.uniform(-1, 1, (B, 10, 1, 30, 3)).astype(np.float32)
+    oth = rng.uniform(-1, 1, (B, 20, 1, 30, C)).astype(np.float32)
+    dec = rng.uniform(-1, 1, (B, 1, 1, 30, 3)).astype(np.float32)
+    tg = [rng.uniform(-1, 1, (B, 10, 1, 30, 3)).astype(np.float32), rng.uniform(-1, 1, (B, 20, 1, 30, C)).astype(np.float32),
+          rng.uniform(-1, 1, (B, 10, 1, 30, 3)).astype(np.float32)]
+    m = fov.others_convlstm_target(num_user=num_user, weights=w)
+    m.set_compute(mode).compile("Adam", ["mean_squared_error"] * 3, [1, 1, 1])
+    assert m.count_params() == sum(v.size for v in w.values())
+    x = [enc, oth, dec]
+    wt = kt.to_torch(w)
+    l_ref, outs_ref, g_ref = kt.loss_and_grads(kt.others_convlstm_target_forward, wt, [t64(a) for a in x],
+                                               [t64(a) for a in tg], [kt.mse] * 3)
+    got = m.predict_on_batch(x)
+    ref_np = kn.others_convlstm_target_forward({k: v.astype(np.float64) for k, v in w.items()},
+                                               *[a.astype(np.float64) for a in x])
+    for a, b, c in zip(got, outs_ref, ref_np):
+        assert a.shape == tuple(b.shape)
+        assert np.abs(a - b.numpy()).max() < FWD_ATOL and np.abs(a - c).max() < FWD_ATOL
+    xs, ys = m._to_dev(x), m._to_dev(tg)
+    m.gflat.zero_()
+    loss = m._loss(m._forward(xs, True), ys)
+    loss.backward()
+    assert abs(loss.item() - l_ref.item()) < 1e-4
+    for k in m.weight_order:
+        _grad_close(m.grads[k].cpu().numpy(), g_ref[k].numpy(), k)
+    opt = kt.KerasAdam(wt)
+    for step in range(4):
+        l_ref, _, g_ref = kt.loss_and_grads(kt.others_convlstm_target_forward, wt, [t64(a) for a in x],
+                                            [t64(a) for a in tg], [kt.mse] * 3)
+        opt.step(g_ref)
+        l = m.train_on_batch(x, tg)
+        assert abs(l - l_ref.item()) < 5e-4 * max(1.0, abs(l_ref.item())), (step, l, l_ref.item())
+
+
 # ------------------------------------------------------------------ ConvLSTM weight gradient inside the persistent BPTT
 
 @pytest.mark.parametrize("B,T", [(1, 1), (4, 20), (131, 7), (7, 2)])

@@ -320,3 +320,34 @@ def test_stacked_seq2seq_restatements_agree():
     w3b = dict(w3); w3b["decoder2/kernel"] = w3["decoder2/kernel"] * 0
     x64 = {k: v.astype(np.float64) for k, v in w3.items()}; y64 = {k: v.astype(np.float64) for k, v in w3b.items()}
     assert np.array_equal(kn.stacked_fov_seq2seq_forward(x64, enc, dec, 3), kn.stacked_fov_seq2seq_forward(y64, enc, dec, 3))
+
+
+def test_given_others_and_convlstm_target_restatements_agree():
+    """given_others_gt_mean_var_seq2seq.py:97-308 (three variants, re-fed and teacher forced) and the all-ConvLSTM
+    form of others_LSTM_span_whole.py (:133-199,273-317): NumPy and torch restatements agree; known structure checks
+    (target_only ignores the others; the re-fed decoder really consumes its own output)."""
+    rng = np.random.default_rng(3)
+    enc = rng.uniform(-1, 1, (3, 10, 6)); oth = rng.uniform(-1, 1, (3, 10, 33, 6))
+    for variant in ("mlp_mixing", "others_mlp", "target_only"):
+        w = kn.init_given_others_seq2seq(seed=4, variant=variant)
+        w64 = {k: v.astype(np.float64) for k, v in w.items()}
+        for tf in (False, True):
+            dec = rng.uniform(-1, 1, (3, 10 if tf else 1, 6))
+            a = kn.given_others_seq2seq_forward(w64, enc, oth, dec, variant, tf)
+            b = kt.given_others_seq2seq_forward(kt.to_torch(w), torch.tensor(enc), torch.tensor(oth), torch.tensor(dec),
+                                                variant, tf).numpy()
+            np.testing.assert_allclose(a, b, atol=1e-10)
+            assert a.shape == (3, 10, 6) and np.abs(a).max() <= 1.0          # tanh outputs
+            other = kn.given_others_seq2seq_forward(w64, enc, oth * 0.5, dec, variant, tf)
+            assert np.array_equal(a, other) == (variant == "target_only")
+        dec2 = dec[:, :1] + 0.1
+        c = kn.given_others_seq2seq_forward(w64, enc, oth, dec2, variant, False)
+        d = kn.given_others_seq2seq_forward(w64, enc, oth, dec[:, :1], variant, False)
+        assert np.abs(c[:, -1] - d[:, -1]).max() > 0                          # the seed propagates through all 10 re-fed steps
+    w = kn.init_others_convlstm_target(seed=5, num_user=5)
+    x = [rng.uniform(-1, 1, (2, 10, 1, 30, 3)), rng.uniform(-1, 1, (2, 20, 1, 30, 12)), rng.uniform(-1, 1, (2, 1, 1, 30, 3))]
+    a = kn.others_convlstm_target_forward({k: v.astype(np.float64) for k, v in w.items()}, *x)
+    b = kt.others_convlstm_target_forward(kt.to_torch(w), *[torch.tensor(t) for t in x])
+    for u, v in zip(a, b):
+        np.testing.assert_allclose(u, v.numpy(), atol=1e-10)
+    assert [u.shape for u in a] == [(2, 10, 1, 30, 3), (2, 20, 1, 30, 12), (2, 10, 1, 30, 3)]
