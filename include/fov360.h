@@ -115,6 +115,9 @@ typedef struct {
                                     each LSTM's [dU; dW; db] is ONE tcgen05 launch over the padded xh rows */
   const float *dhseq_dec;        /* optional (B,T_dec,H): gradient w.r.t. dec.hseq (stacked LSTMs: the layer above reads
                                     this layer's hidden sequence, mycode/Fov_seq2seq_2layers.py:232-272) */
+  void *wgrad_stream;            /* optional cudaStream_t: the weight-gradient launches (nothing on the backward chain reads
+                                    them) go to this stream after an event on `stream`; the caller joins it before it
+                                    reads the gradients and keeps dz / saved tensors / ws alive until then.  NULL: `stream` */
 } fov_lstm_grads;
 size_t fov_lstm_bwd_ws_floats(const fov_lstm_cfg* cfg);
 
@@ -249,6 +252,8 @@ typedef struct {
   float *ws;                     /* workspace floats: see fov_convlstm_bwd_ws_floats */
   int dx_accumulate;             /* 0: dx overwritten; 1: dx += (stacked layers add into the
                                     gradient of the layer below) */
+  void *wgrad_stream;            /* optional cudaStream_t for the weight-gradient launches of the tensor-core path (see
+                                    fov_lstm_grads.wgrad_stream).  NULL: `stream` */
 } fov_convlstm_grads;
 
 size_t fov_convlstm_bwd_ws_floats(const fov_convlstm_cfg* cfg);

@@ -46,7 +46,8 @@ class LstmGrads(C.Structure):
     _fields_ = [(n, c_float_p) for n in (
         "dy", "dhseq_enc", "y", "dz_enc", "dz_dec", "dpre",
         "g_enc_kernel", "g_enc_recurrent", "g_enc_bias",
-        "g_dec_kernel", "g_dec_recurrent", "g_dec_bias", "g_head_kernel", "g_head_bias", "ws", "dhseq_dec")]
+        "g_dec_kernel", "g_dec_recurrent", "g_dec_bias", "g_head_kernel", "g_head_bias", "ws", "dhseq_dec")] + \
+               [("wgrad_stream", C.c_void_p)]
 
 
 class ConvCfg(C.Structure):
@@ -76,7 +77,7 @@ class ConvLstmIO(C.Structure):
 class ConvLstmGrads(C.Structure):
     _fields_ = [(n, c_float_p) for n in ("dhseq", "dhT", "dcT", "dx", "dh0", "dc0",
                                          "g_kernel", "g_recurrent", "g_bias", "ws")] + \
-               [("dx_accumulate", C.c_int)]
+               [("dx_accumulate", C.c_int), ("wgrad_stream", C.c_void_p)]
 
 
 # every symbol include/fov360.h declares: name -> (restype, argtypes)

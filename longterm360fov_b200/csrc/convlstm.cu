@@ -306,6 +306,14 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
       kT.seg[0].x = io->gates; kT.y = gr->dx; kT.beta = gr->dx_accumulate ? 1.0f : 0.0f;
       if ((rc = tc_conv_run(kT, st))) return rc;
     }
+    // the weight gradients feed only the optimiser: on request they leave the backward chain for a side stream
+    if (gr->wgrad_stream && (cudaStream_t)gr->wgrad_stream != st) {
+      if (fov_fork_stream(st, (cudaStream_t)gr->wgrad_stream)) {
+        fov_set_error("fov_convlstm_bwd: could not fork the weight-gradient stream");
+        return FOV_ERR_CUDA;
+      }
+      st = (cudaStream_t)gr->wgrad_stream;
+    }
     // fused weight gradient (gK, gR, gb in one launch, no gather) when the taps fit the TMEM columns
     if (gr->g_kernel && gr->g_recurrent) {
       TcWgradRows wr{};

@@ -107,3 +107,14 @@ static inline int fov_num_sms() {
   }
   return n[dev];
 }
+
+// Fork helper for launches that nothing downstream on `main` reads (weight gradients): `side` waits for everything
+// enqueued on `main` so far.  Graph-capture safe (event record / wait is how a captured fork is expressed).
+static inline int fov_fork_stream(cudaStream_t main, cudaStream_t side) {
+  cudaEvent_t ev;
+  if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return -1;
+  int rc = 0;
+  if (cudaEventRecord(ev, main) != cudaSuccess || cudaStreamWaitEvent(side, ev, 0) != cudaSuccess) rc = -1;
+  cudaEventDestroy(ev);          // released once the recorded work has completed
+  return rc;
+}

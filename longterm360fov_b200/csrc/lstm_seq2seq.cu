@@ -589,6 +589,15 @@ extern "C" int fov_lstm_seq2seq_bwd(const fov_lstm_cfg* cfg, const fov_lstm_weig
     if (r) return r;
     return wgrad(sv.xh + kH, XS, in_dim, dz, kG, rows, g_kernel, nullptr, false);
   };
+  // the weight gradients feed only the optimiser: on request they leave the backward chain for a side stream
+  if (g->wgrad_stream && (cudaStream_t)g->wgrad_stream != st) {
+    if (fov_fork_stream(st, (cudaStream_t)g->wgrad_stream)) {
+      fov_set_error("fov_lstm_seq2seq_bwd: could not fork the weight-gradient stream");
+      return FOV_ERR_CUDA;
+    }
+    st = (cudaStream_t)g->wgrad_stream;
+    stream = g->wgrad_stream;
+  }
   float* wsp = g->ws;
   if (cfg->T_enc > 0) {
     if ((rc = lstm_wgrads(io->enc, cfg->in_enc, cfg->T_enc, g->dz_enc, g->g_enc_kernel, g->g_enc_recurrent,

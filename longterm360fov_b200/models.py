@@ -122,6 +122,7 @@ class _GraphedStep:
         outs = m._forward(self.sx, True)
         total = m._loss(outs, self.sy)
         total.backward(self.seed)
+        ops.join_wgrad_stream()
         return total.detach()
 
     def run(self, xs, ys):
@@ -174,6 +175,11 @@ class Model:
         # terms per operand by default (~16 mantissa bits, forward error ~1e-5); "fp32" selects the CUDA-core kernels
         self.compute = os.environ.get("FOV_COMPUTE", "bf16x2")
         self._graphs, self._use_graphs = {}, False
+        # weight gradients on a side stream (ops._WgFork): None = for batches up to wgrad_side_stream_max_batch (where
+        # the step is a latency-bound chain and most SMs idle), True / False = always / never
+        self.wgrad_side_stream = None
+        self.wgrad_side_stream_min_eager_batch = 384
+        self.wgrad_side_stream_max_batch = 2560
 
     def enable_cuda_graphs(self, on=True):
         """Replay the training step from a CUDA graph (captured per input-shape set on first use).  Worth it when the
@@ -296,10 +302,26 @@ class Model:
             seed = self._seeds.get(n_local)
             if seed is None:
                 seed = self._seeds[n_local] = torch.full((1,), float(n_local), device=self.device)
+        # small batches: the weight-gradient launches leave the backward chain for a side stream (ops.set_wgrad_side_stream)
+        side = self.wgrad_side_stream
+        if side is None:
+            # measured on B200 (scripts/small_batch_ab.py, config 2): replayed from a CUDA graph the fork always pays
+            # (B=32 1.36 -> 1.17 ms, B=1110 3.92 -> 3.56 ms); launched eagerly its host cost (events, stream switches,
+            # allocator bookkeeping) outweighs it below ~400 sequences (B=256 2.10 -> 2.82 ms, B=512 2.64 -> 2.14 ms);
+            # above ~2.5 k sequences the kernels fill the GPU and the gain fades (B=8880 +2 %) - left off there
+            lo = 0 if self._use_graphs else self.wgrad_side_stream_min_eager_batch
+            side = lo <= n_local <= self.wgrad_side_stream_max_batch
+        ops.set_wgrad_side_stream(side)
+        try:
+            return self._train_step_device(xs, ys, targets_ready, n_local, seed, bool(side))
+        finally:
+            ops.set_wgrad_side_stream(False)
+
+    def _train_step_device(self, xs, ys, targets_ready, n_local, seed, side):
         if self._use_graphs:
             if targets_ready is not None:
                 torch.cuda.current_stream().wait_event(targets_ready)
-            key = (self.compute, self.world_size > 1) + tuple(tuple(t.shape) for t in list(xs) + list(ys))
+            key = (self.compute, self.world_size > 1, side) + tuple(tuple(t.shape) for t in list(xs) + list(ys))
             step = self._graphs.get(key)
             if step is None:
                 step = self._graphs[key] = _GraphedStep(self, xs, ys, seed)
@@ -312,6 +334,7 @@ class Model:
                 torch.cuda.current_stream().wait_event(targets_ready)
             total = self._loss(outs, ys)
             total.backward(seed)
+            ops.join_wgrad_stream()
         div = None
         if self.world_size > 1:
             div = parallel.allreduce_gradients(self.gflat, self.comm, n_local)

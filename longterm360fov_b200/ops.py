@@ -59,6 +59,72 @@ def _ws(nbytes, device):
 
 
 # --------------------------------------------------------------------------- #
+# weight gradients on a side stream
+# --------------------------------------------------------------------------- #
+# Nothing on the backward chain reads a weight gradient: only the optimiser does.  At small batches (the reference
+# trains at 32 / 64) the step is a chain of dependent launches that leaves most SMs idle, so the weight-gradient
+# launches can leave that chain: they fork onto a side stream after the kernel that produced their operands and the
+# caller joins the stream before the optimiser step (join_wgrad_stream).  Tensors they read are registered with the
+# caching allocator (record_stream), so nothing is recycled under them.  Graph-capture safe (event fork / join).
+_WG = {"on": False, "streams": {}, "used": False}
+
+
+def set_wgrad_side_stream(on):
+    _WG["on"] = bool(on)
+
+
+def _wg_stream():
+    """The side stream of the current device, or None when the feature is off."""
+    if not _WG["on"]:
+        return None
+    dev = torch.cuda.current_device()
+    st = _WG["streams"].get(dev)
+    if st is None:
+        st = _WG["streams"][dev] = torch.cuda.Stream(device=dev)
+    _WG["used"] = True
+    return st
+
+
+def _wg_keep(side, *tensors):
+    for t in tensors:
+        if t is not None and t.is_cuda:
+            t.record_stream(side)
+
+
+class _WgFork:
+    """``with _WgFork(x, dy) as side:`` - inside, the current stream is the side stream (forked after everything
+    enqueued so far) when the feature is on, else nothing changes."""
+
+    def __init__(self, *reads):
+        self.reads = reads
+        self.side = _wg_stream()
+        self.ctx = None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            _wg_keep(self.side, *self.reads)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self.side
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def join_wgrad_stream():
+    """The current stream waits for the side-stream weight gradients of this pass (call before the optimiser)."""
+    if _WG["used"]:
+        cur = torch.cuda.current_stream()
+        for st in _WG["streams"].values():
+            if st.device == cur.device:
+                cur.wait_stream(st)
+        _WG["used"] = False
+
+
+# --------------------------------------------------------------------------- #
 # persistent fc-LSTM encoder-decoder
 # --------------------------------------------------------------------------- #
 
@@ -168,10 +234,14 @@ class LSTMSeq2SeqFn(torch.autograd.Function):
                                         ptr(enc_hseq)),
                          _lib.LstmSaved(ptr(sv["dec_xh"]), ptr(sv["dec_gates"]), ptr(sv["dec_c"]),
                                         ptr(sv["dec_hseq"])), None)
+        side = _wg_stream()
+        if side is not None:     # the weight-gradient GEMMs read these after this node has returned
+            _wg_keep(side, dz_enc, dz_dec, dpre, ws, sv["enc_xh"], sv["dec_xh"], sv["dec_hseq"])
         g = _lib.LstmGrads(ptr(dy), ptr(dhseq_enc), ptr(y), ptr(dz_enc), ptr(dz_dec), ptr(dpre),
                            ptr(s["enc_kernel"]), ptr(s["enc_recurrent"]), ptr(s["enc_bias"]),
                            ptr(s["dec_kernel"]), ptr(s["dec_recurrent"]), ptr(s["dec_bias"]),
-                           ptr(s.get("head_kernel")), ptr(s.get("head_bias")), ptr(ws), ptr(dhseq_dec))
+                           ptr(s.get("head_kernel")), ptr(s.get("head_bias")), ptr(ws), ptr(dhseq_dec),
+                           side.cuda_stream if side is not None else None)
         _lib.check(lib.fov_lstm_seq2seq_bwd(C.byref(cfg), C.byref(w), C.byref(io), C.byref(g), _stream()),
                    "fov_lstm_seq2seq_bwd")
         d_extra = dpre if ctx.has_extra else None
@@ -301,14 +371,16 @@ class Conv2DFn(torch.autograd.Function):
         cfg.act = 0
         gw, gb = ctx.sinks
         math = ctx.math
-        if math == 0:
-            _lib.check(lib.fov_conv2d_bwd_weight(C.byref(cfg), ptr(x), ptr(dpre), ptr(gw), ptr(gb), st),
-                       "fov_conv2d_bwd_weight")
-        else:
-            nws = lib.fov_conv_wgrad_ws_bytes(C.byref(cfg), math)       # > 0: wide k x k conv, TMA-fed plane kernel
-            wws = _ws(nws, x.device) if nws else None
-            _lib.check(lib.fov_conv2d_bwd_weight_tc_ws(C.byref(cfg), ptr(x), ptr(dpre), ptr(gw), ptr(gb), ptr(wws), math,
-                                                       st), "fov_conv2d_bwd_weight_tc_ws")
+        with _WgFork(x, dpre):
+            wst = _stream()
+            if math == 0:
+                _lib.check(lib.fov_conv2d_bwd_weight(C.byref(cfg), ptr(x), ptr(dpre), ptr(gw), ptr(gb), wst),
+                           "fov_conv2d_bwd_weight")
+            else:
+                nws = lib.fov_conv_wgrad_ws_bytes(C.byref(cfg), math)   # > 0: wide k x k conv, TMA-fed plane kernel
+                wws = _ws(nws, x.device) if nws else None
+                _lib.check(lib.fov_conv2d_bwd_weight_tc_ws(C.byref(cfg), ptr(x), ptr(dpre), ptr(gw), ptr(gb), ptr(wws),
+                                                           math, wst), "fov_conv2d_bwd_weight_tc_ws")
         dx = None
         if ctx.need_dx:
             dx = torch.empty_like(x)
@@ -515,14 +587,16 @@ class DualDenseFn(torch.autograd.Function):
         st = _stream()
         xs = x.data_ptr() + 4 * t0 * Cin
         dx = torch.empty_like(x) if ctx.need_dx else None
-        for cfg, xp, W, dy, sinks in ((full, x.data_ptr(), W1, dy1, ctx.sinks[0]), (part, xs, W2, dy2, ctx.sinks[1])):
-            gw, gb = sinks
-            if math == 0:
-                _lib.check(lib.fov_conv2d_bwd_weight(C.byref(cfg), xp, ptr(dy), ptr(gw), ptr(gb), st),
-                           "fov_conv2d_bwd_weight")
-            else:
-                _lib.check(lib.fov_conv2d_bwd_weight_tc(C.byref(cfg), xp, ptr(dy), ptr(gw), ptr(gb), math, st),
-                           "fov_conv2d_bwd_weight_tc")
+        with _WgFork(x, dy1, dy2):
+            wst = _stream()
+            for cfg, xp, W, dy, sinks in ((full, x.data_ptr(), W1, dy1, ctx.sinks[0]), (part, xs, W2, dy2, ctx.sinks[1])):
+                gw, gb = sinks
+                if math == 0:
+                    _lib.check(lib.fov_conv2d_bwd_weight(C.byref(cfg), xp, ptr(dy), ptr(gw), ptr(gb), wst),
+                               "fov_conv2d_bwd_weight")
+                else:
+                    _lib.check(lib.fov_conv2d_bwd_weight_tc(C.byref(cfg), xp, ptr(dy), ptr(gw), ptr(gb), math, wst),
+                               "fov_conv2d_bwd_weight_tc")
         if dx is not None:
             # dx[:, :t0] = dy1[:, :t0] . W1^T ;  dx[:, t0:] = [dy1[:, t0:] | dy2] . [W1 | W2]^T  - ONE GEMM (K = C1 + C2) for the
             # slices both layers read, each slice of dx written exactly once.  (Two accumulating GEMMs re-read and
@@ -710,8 +784,12 @@ class ConvLSTMStackFn(torch.autograd.Function):
             if mask is None:
                 io = _lib.ConvLstmIO(xptr, ptr(K), ptr(R), ptr(b), ptr(h0), ptr(c0), hptr,
                                      ptr(gates), ptr(cseq), None, None, None)
+                side = _wg_stream()
+                if side is not None:     # the layer's weight gradient reads these after this node has returned
+                    _wg_keep(side, gates, cat, x, h0)
                 g = _lib.ConvLstmGrads(dcat.data_ptr() + 4 * off, ptr(dhT), ptr(dcT), dxp, ptr(dh0), ptr(dc0),
-                                       ptr(gk), ptr(gr_), ptr(gb), ptr(ws), acc)
+                                       ptr(gk), ptr(gr_), ptr(gb), ptr(ws), acc,
+                                       side.cuda_stream if side is not None else None)
                 _lib.check(lib.fov_convlstm_bwd(C.byref(cfg), C.byref(io), C.byref(g), st), "fov_convlstm_bwd")
             else:
                 # widened-input form: gradients w.r.t. x4 / K4, folded back through the masks / the gate blocks
@@ -721,7 +799,7 @@ class ConvLSTMStackFn(torch.autograd.Function):
                 io = _lib.ConvLstmIO(ptr(x4), ptr(K4), ptr(R), ptr(b), ptr(h0), ptr(c0), hptr,
                                      ptr(gates), ptr(cseq), None, None, None)
                 g = _lib.ConvLstmGrads(dcat.data_ptr() + 4 * off, ptr(dhT), ptr(dcT), ptr(dx4), ptr(dh0), ptr(dc0),
-                                       ptr(gk4), ptr(gr_), ptr(gb), ptr(ws), 0)
+                                       ptr(gk4), ptr(gr_), ptr(gb), ptr(ws), 0, None)
                 _lib.check(lib.fov_convlstm_bwd(C.byref(cfg), C.byref(io), C.byref(g), st), "fov_convlstm_bwd")
                 _lib.check(lib.fov_gate_kernel_reduce(K.shape[0] * K.shape[1], cin_, F, ptr(gk4), ptr(gk), st),
                            "fov_gate_kernel_reduce")

@@ -733,6 +733,46 @@ def test_others_convlstm_target(num_user, B, mode):
         assert abs(l - l_ref.item()) < 5e-4 * max(1.0, abs(l_ref.item())), (step, l, l_ref.item())
 
 
+# ------------------------------------------------------------------ weight gradients on a side stream
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_weight_gradients_on_side_stream_match(graphs):
+    """Model.wgrad_side_stream: the weight-gradient launches fork onto a side stream after the kernel that produced
+    their operands and are joined before the optimiser step.  Same batches, same start: 6 Adam steps of config 2 with
+    the fork forced on and forced off end in the same weights and losses (the gradients are sums of red.global.add
+    partials either way, so equality is to rounding, 1e-5), eagerly and replayed from a CUDA graph; the 2-layer re-fed
+    sibling model (one-step ConvLSTM cells with carried states, dense heads) likewise."""
+    fov = _cuda()
+    from longterm360fov_b200 import data
+    x, y = data.make_m3_batch(24, 34, seed=3)
+    res = []
+    for side in (False, True):
+        m = fov.others_lstm_span_whole(num_user=34, seed=2).compile("Adam", ["mean_squared_error"] * 3, [1, 1, 1])
+        m.wgrad_side_stream = side
+        if graphs:
+            m.enable_cuda_graphs()
+        losses = [m.train_on_batch(x, y) for _ in range(6)]
+        res.append((losses, m.get_weights()))
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-5)
+    for a, b, k in zip(res[0][1], res[1][1], m.weight_order):
+        np.testing.assert_allclose(a, b, atol=1e-5, err_msg=k)
+    rng = np.random.default_rng(4)
+    xs = [rng.uniform(-1, 1, (19, 10, 6)).astype(np.float32), rng.uniform(-1, 1, (19, 10, 33, 6)).astype(np.float32),
+          rng.uniform(-1, 1, (19, 1, 6)).astype(np.float32)]
+    tg = rng.uniform(-1, 1, (19, 10, 6)).astype(np.float32)
+    res = []
+    for side in (False, True):
+        m = fov.given_others_gt_mean_var_seq2seq(seed=3).compile("Adam", "mean_squared_error")
+        m.wgrad_side_stream = side
+        if graphs:
+            m.enable_cuda_graphs()
+        losses = [m.train_on_batch(xs, tg) for _ in range(4)]
+        res.append((losses, m.get_weights()))
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-5)
+    for a, b, k in zip(res[0][1], res[1][1], m.weight_order):
+        np.testing.assert_allclose(a, b, atol=1e-5, err_msg=k)
+
+
 # ------------------------------------------------------------------ ConvLSTM weight gradient inside the persistent BPTT
 
 @pytest.mark.parametrize("B,T", [(1, 1), (4, 20), (131, 7), (7, 2)])
