@@ -381,15 +381,24 @@ def other_workloads(dev, peaks, compute):
     del vid, fr
 
     # ---- config 1 model (FoV_seq2seq, teacher forcing) training on the GPU ----
-    Bt = 8192
     m1 = fov.fov_seq2seq(seed=4, device=dev).compile("Adam", "mean_squared_error")
     e, d, t, _ = data.make_m1_batch(512, seed=9)
-    rep = Bt // 512
-    xs = m1._to_dev([np.tile(e, (rep, 1, 1)), np.tile(d, (rep, 1, 1))])
-    ys = m1._to_dev([np.tile(t, (rep, 1, 1))])
-    ms = _time_cuda(lambda: m1.train_step_device(xs, ys), reps=10, warm=3)
-    res["fov_seq2seq_teacher_forced_train"] = {"batch": Bt, "unit": "sequences/s", "value": Bt / (ms * 1e-3),
-                                               "ms_per_step": ms}
+    cfg1 = {"unit": "sequences/s", "io_bytes_per_seq": 4320,
+            "note": "SURVEY.md 8(d) config 1 is HBM-classified on 4 080 + 240 B of input / target per sequence; the "
+                    "train step also writes and re-reads ~41 KB of saved tensors per sequence"}
+    for Bt in (8192, 65536):               # SURVEY.md 8(d) lists B = 32 (reference), 4 096 and 65 536 for this config
+        rep = Bt // 512
+        xs = m1._to_dev([np.tile(e, (rep, 1, 1)), np.tile(d, (rep, 1, 1))])
+        ys = m1._to_dev([np.tile(t, (rep, 1, 1))])
+        ms = _time_cuda(lambda: m1.train_step_device(xs, ys), reps=10, warm=3)
+        val = Bt / (ms * 1e-3)
+        cfg1["batch_%d" % Bt] = {"value": val, "ms_per_step": ms,
+                                 "io_frac_of_hbm_peak": val * 4320 / 1e9 / peaks["hbm_gbs"],
+                                 "algorithmic_tflops": val * 3.46e6 / 1e12}
+        if Bt == 8192:
+            cfg1.update(batch=Bt, value=val, ms_per_step=ms)
+        del xs, ys
+    res["fov_seq2seq_teacher_forced_train"] = cfg1
     return res
 
 

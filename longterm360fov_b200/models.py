@@ -177,6 +177,7 @@ class Model:
         self._graphs, self._use_graphs = {}, False
         # weight gradients on a side stream (ops._WgFork): None = for batches up to wgrad_side_stream_max_batch (where
         # the step is a latency-bound chain and most SMs idle), True / False = always / never
+        self.loss_readback_depth = 2      # fit / fit_generator read the loss of a step this many steps late
         self.wgrad_side_stream = None
         self.wgrad_side_stream_min_eager_batch = 384
         self.wgrad_side_stream_max_batch = 2560
@@ -393,7 +394,8 @@ class Model:
             cur = fetch()
         except StopIteration:
             return
-        pending = None                                         # (batch size, loss tensor) of the step before
+        pending = collections.deque()                          # (batch size, loss tensor) of the steps in flight
+        depth = max(1, int(self.loss_readback_depth))
         while cur is not None:
             xs, ys, (x_ready, y_ready), b = cur
             torch.cuda.current_stream().wait_event(x_ready)
@@ -405,12 +407,16 @@ class Model:
                 cur = fetch()
             except StopIteration:
                 cur = None
-            # the loss of step i-1 is read while step i runs: the host never drains the GPU between steps
-            if pending is not None:
-                yield pending[0], float(pending[1].item())
-            pending = (b, loss)
-        if pending is not None:
-            yield pending[0], float(pending[1].item())
+            # the loss of step i-depth is read while the steps after it run: the host never drains the GPU between
+            # steps, and with depth > 1 a launch-latency spike on the host (8 ranks sharing the host's cores and the
+            # driver) is absorbed by the queued steps instead of opening a bubble
+            pending.append((b, loss))
+            while len(pending) > depth:
+                pb, pl = pending.popleft()
+                yield pb, float(pl.item())
+        while pending:
+            pb, pl = pending.popleft()
+            yield pb, float(pl.item())
 
     def test_on_batch(self, x, y):
         xs, ys = self._to_dev(self._as_list(x)), self._to_dev(self._as_list(y))
