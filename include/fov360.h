@@ -227,6 +227,9 @@ typedef struct {
   int ws_prepacked;              /* 1: io.ws still holds this layer's packed weights from an earlier fov_convlstm_fwd
                                     call with the same weights and shapes (the 10 one-step decoder calls of
                                     mycode/convlstm_seq2seq.py:211-220): the repack launch is skipped */
+  int wave_layers;               /* layer wavefront: number of stacked layers that will run concurrently (0 / 1: this
+                                    layer has the GPU to itself).  The persistent kernels size their image groups so
+                                    that the CTAs of all wave_layers layers fit on the SMs at once */
 } fov_convlstm_cfg;
 
 typedef struct {
@@ -238,9 +241,20 @@ typedef struct {
   float *cseq;                   /* (B,T,H,W,F) */
   float *hT, *cT;                /* optional dense (B,H,W,F) */
   float *ws;                     /* workspace of fov_convlstm_fwd_ws_bytes() bytes (math != 0) */
+  /* Layer wavefront of stacked ConvLSTMs at small batches (optional, persistent tensor-core kernels only, see
+   * fov_convlstm_wave_groups): the layers of a stack are launched on DIFFERENT streams and run concurrently; layer l
+   * raises wave_set[group*T + t] once h_t of the group's images is in global memory and layer l+1 waits for
+   * wave_wait[group*T + t] before it reads x_t.  int32 device arrays of fov_convlstm_wave_groups() * T zeros.  The
+   * caller guarantees that all the stack's CTAs can be resident at once (sum of the groups <= number of SMs). */
+  const int *wave_wait;
+  int *wave_set;
 } fov_convlstm_io;
 
 size_t fov_convlstm_fwd_ws_bytes(const fov_convlstm_cfg* cfg);
+/* image groups (= CTAs) of the persistent forward (backward = 0) / BPTT (backward = 1, with a fused input gradient when
+ * with_dx) kernel for this configuration, 0 when the configuration does not take a persistent kernel with one group per
+ * CTA (then the wavefront flags are not available).  The group of image b is b / (ceil(B / groups)). */
+int fov_convlstm_wave_groups(const fov_convlstm_cfg* cfg, int backward, int with_dx);
 int fov_convlstm_fwd(const fov_convlstm_cfg* cfg, const fov_convlstm_io* io, void* stream);
 
 typedef struct {
@@ -254,6 +268,11 @@ typedef struct {
                                     gradient of the layer below) */
   void *wgrad_stream;            /* optional cudaStream_t for the weight-gradient launches of the tensor-core path (see
                                     fov_lstm_grads.wgrad_stream).  NULL: `stream` */
+  /* layer wavefront of the backward pass (see fov_convlstm_io.wave_wait): this layer's BPTT waits for wave_wait[group*T+t]
+   * before it reads dhseq[t] (the layer above is still adding its dx into it) and raises wave_set[group*T+t] once its
+   * own fused dx_t is in global memory.  wave_set needs the fused input gradient (dx != NULL on the persistent path). */
+  const int *wave_wait;
+  int *wave_set;
 } fov_convlstm_grads;
 
 size_t fov_convlstm_bwd_ws_floats(const fov_convlstm_cfg* cfg);

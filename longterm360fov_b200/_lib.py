@@ -65,19 +65,20 @@ class ConvLstmCfg(C.Structure):
                 ("dil_w", C.c_int), ("rec_act", C.c_int),
                 ("x_b_stride", C.c_longlong), ("x_t_stride", C.c_longlong), ("x_pix_stride", C.c_int),
                 ("h_b_stride", C.c_longlong), ("h_t_stride", C.c_longlong), ("h_pix_stride", C.c_int),
-                ("training", C.c_int), ("math", C.c_int), ("ws_prepacked", C.c_int)]
+                ("training", C.c_int), ("math", C.c_int), ("ws_prepacked", C.c_int), ("wave_layers", C.c_int)]
 
 
 class ConvLstmIO(C.Structure):
     _fields_ = [(n, c_float_p) for n in (
         "x", "kernel", "recurrent", "bias", "h0", "c0", "hseq", "gates", "cseq",
-        "hT", "cT", "ws")]
+        "hT", "cT", "ws")] + [("wave_wait", C.c_void_p), ("wave_set", C.c_void_p)]
 
 
 class ConvLstmGrads(C.Structure):
     _fields_ = [(n, c_float_p) for n in ("dhseq", "dhT", "dcT", "dx", "dh0", "dc0",
                                          "g_kernel", "g_recurrent", "g_bias", "ws")] + \
-               [("dx_accumulate", C.c_int), ("wgrad_stream", C.c_void_p)]
+               [("dx_accumulate", C.c_int), ("wgrad_stream", C.c_void_p), ("wave_wait", C.c_void_p),
+                ("wave_set", C.c_void_p)]
 
 
 # every symbol include/fov360.h declares: name -> (restype, argtypes)
@@ -112,6 +113,7 @@ SYMBOLS = {
     "fov_tapstack_expand": (_I, [_LL, _I, _I, _I, _I, _I, _P, _P, _P]),
     "fov_convlstm_fwd": (_I, [C.POINTER(ConvLstmCfg), C.POINTER(ConvLstmIO), _P]),
     "fov_convlstm_fwd_ws_bytes": (C.c_size_t, [C.POINTER(ConvLstmCfg)]),
+    "fov_convlstm_wave_groups": (_I, [_P, _I, _I]),
     "fov_convlstm_bwd_ws_floats": (C.c_size_t, [C.POINTER(ConvLstmCfg)]),
     "fov_convlstm_bwd": (_I, [C.POINTER(ConvLstmCfg), C.POINTER(ConvLstmIO), C.POINTER(ConvLstmGrads), _P]),
     "fov_softmax_fwd": (_I, [_LL, _I, _P, _P, _P]),

@@ -128,6 +128,16 @@ extern "C" size_t fov_convlstm_fwd_ws_bytes(const fov_convlstm_cfg* cfg) {
   return tc_conv_ws_bytes(step_conv(cfg, &io, geo(cfg)));
 }
 
+extern "C" int fov_convlstm_wave_groups(const fov_convlstm_cfg* cfg, int backward, int with_dx) {
+  if (!cfg || check(cfg) || !tc_step_ok(cfg)) { fov_set_error(""); return 0; }
+  const Geo g = geo(cfg);
+  fov_convlstm_io io{};
+  if (!backward) return tc_convlstm_seq_wave_groups(cfg, step_conv(cfg, &io, g));
+  TcConv rT = rec_bwd_conv(cfg, nullptr, g);
+  TcConv kT = in_bwd_conv(cfg, nullptr, g);
+  return tc_convlstm_seq_bwd_wave_groups(cfg, rT, with_dx ? &kT : nullptr);
+}
+
 static int convlstm_fwd_tc(const fov_convlstm_cfg* cfg, const fov_convlstm_io* io, cudaStream_t st) {
   FOV_CHECK_ARG(io->ws != nullptr, "math != 0 needs io->ws (fov_convlstm_fwd_ws_bytes)");
   const Geo g = geo(cfg);
@@ -136,6 +146,7 @@ static int convlstm_fwd_tc(const fov_convlstm_cfg* cfg, const fov_convlstm_io* i
   k.ws = io->ws;
   // whole images per MMA tile: one persistent launch runs every timestep (convlstm_seq_tc.cu)
   if (tc_convlstm_seq_supported(cfg, k)) return tc_convlstm_seq_fwd(cfg, io, k, st);
+  FOV_CHECK_ARG(!io->wave_wait && !io->wave_set, "wavefront flags need the persistent kernel (fov_convlstm_wave_groups)");
   for (int t = 0; t < cfg->T; ++t) {
     k.prepacked = t > 0 || cfg->ws_prepacked;
     k.seg[0].x = io->x + t * cfg->x_t_stride;
@@ -165,6 +176,7 @@ extern "C" int fov_convlstm_fwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
                 "NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (tc_step_ok(cfg)) return convlstm_fwd_tc(cfg, io, st);
+  FOV_CHECK_ARG(!io->wave_wait && !io->wave_set, "wavefront flags need the persistent kernel (fov_convlstm_wave_groups)");
   const Geo g = geo(cfg);
   const int F = cfg->F;
 
@@ -260,6 +272,8 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
       else if (tc_convlstm_seq_bwd_supported(cfg, rT, nullptr)) seq = true;
     }
     bool wg_fused = false;
+    FOV_CHECK_ARG(seq || (!gr->wave_wait && !gr->wave_set), "wavefront flags need the persistent BPTT kernel");
+    FOV_CHECK_ARG(!gr->wave_set || dx_fused, "wavefront: wave_set needs the fused input gradient");
     if (seq) {
       wg_fused = tc_convlstm_seq_bwd_fuses_wgrad(cfg, io, gr, rT, dx_fused ? &kT : nullptr);
       if ((rc = tc_convlstm_seq_bwd(cfg, io, gr, rT, dx_fused ? &kT : nullptr, st))) return rc;
@@ -269,6 +283,7 @@ extern "C" int fov_convlstm_bwd(const fov_convlstm_cfg* cfg, const fov_convlstm_
       rT.prepacked = 1;
     }
   } else {
+    FOV_CHECK_ARG(!gr->wave_wait && !gr->wave_set, "wavefront flags need the persistent BPTT kernel");
     if ((rc = fov_conv_flip_weights(&r, io->recurrent, Rt, st))) return rc;
   }
 

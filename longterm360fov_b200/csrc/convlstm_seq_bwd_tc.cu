@@ -61,6 +61,11 @@ struct BwdParams {
   float *gK, *gR, *gB;
   uint32_t x_off, h_off, wtab_off, x_term, h_term, x_desc_hi, h_desc_hi;
   int x_cw, wg_col0, write_dz;
+  // layer wavefront (optional): [image group][T] flags.  wait_flags: dhseq[t] is being completed by the BPTT of the
+  // layer above (its fused dx) while this kernel runs - wait for its flag, read it through L2; set_flags: raise the flag
+  // of step t once this kernel's dx_t has been added into dx
+  const int* wait_flags;
+  int* set_flags;
 };
 
 struct BwdBook {
@@ -72,7 +77,9 @@ __device__ unsigned long long g_bwd_timeline[8];
 
 // DXN: accumulator columns of the fused input gradient each worker thread reads back (0: no fused dx)
 // WG: the layer's weight gradient rides in this kernel (one CTA per SM variants only: it needs its own TMEM columns)
-template <int NS, int F, int DXN, bool WG>
+// WAVE: layer-wavefront instantiation (per-step flags from / to the neighbouring layers' BPTT kernels); a template
+// parameter so that the large-batch instantiations do not carry the flag code
+template <int NS, int F, int DXN, bool WG, bool WAVE = false>
 __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_kernel(const BwdParams p) {
   constexpr int N4F = 4 * F;
   constexpr int LPR = F / 4;                       // float4 per row of an F-channel tensor
@@ -288,7 +295,12 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
             *reinterpret_cast<float4*>(g) = v;
           }
         }
+        if (WAVE && p.set_flags && ph == 1) __threadfence();                  // my dx_t stores are device-visible
         asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
+      }
+      if (WAVE && p.set_flags && tid == 0) {
+        __threadfence();
+        *reinterpret_cast<volatile int*>(p.set_flags + (long long)blockIdx.x * p.T + t) = 1;
       }
     };
     const bool dbg = (p.dbg & 1) && blockIdx.x == 0 && tid == 0;
@@ -298,6 +310,7 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
     float4 vg[NIT][4], vc[NIT], vp[NIT], vh[NIT];
     // saved tensors of item j at step t -> registers
     auto load_item = [&](int t, int j) {
+      if (WAVE && p.wait_flags && j == 0) wave_wait(p.wait_flags + (long long)blockIdx.x * p.T + t);   // dhseq[t] is complete
       const float* gt = p.gates + (long long)t * p.z_t;
       const float* ct = p.cseq + (long long)t * p.c_t;
       {
@@ -312,7 +325,10 @@ __global__ void __launch_bounds__(kBThr, (F <= 16) ? 2 : 1) convlstm_seq_bwd_ker
           else if (p.c0) vp[j] = __ldg(reinterpret_cast<const float4*>(p.c0 + off_d[j]));
         }
         vh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && p.dhseq) vh[j] = __ldg(reinterpret_cast<const float4*>(p.dhseq + (long long)t * p.dh_t + off_h[j]));
+        if (ok && p.dhseq) {
+          const float4* src = reinterpret_cast<const float4*>(p.dhseq + (long long)t * p.dh_t + off_h[j]);
+          vh[j] = (WAVE && p.wait_flags) ? __ldcg(src) : __ldg(src);
+        }
       }
     };
 #pragma unroll
@@ -620,7 +636,8 @@ int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT, BwdP
   pl.G = kRows / (sp.Hp * sp.Wp);
   FOV_CHECK_ARG(pl.G >= 1, "image larger than one MMA tile");
   if (!g_fov_seq_no_spread) {        // small batches: as few images per CTA as still fills the machine (see convlstm_seq_tc.cu)
-    const int g_fill = (c->B + fov_num_sms() - 1) / fov_num_sms();
+    const int sms = fov_num_sms() / (c->wave_layers > 1 ? c->wave_layers : 1);  // layer wavefront: the stack shares the SMs
+    const int g_fill = (c->B + sms - 1) / sms;
     if (g_fill < pl.G) pl.G = g_fill < 1 ? 1 : g_fill;
   }
   FOV_CHECK_ARG(sp.K_total / 16 <= kMaxSteps && (sp.K_total / 16) * (sp.NS * (sp.NS + 1) / 2) <= kMaxMmas, "too many k steps");
@@ -667,11 +684,11 @@ int bwd_plan(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT, BwdP
   return FOV_OK;
 }
 
-template <int NS, int F, int DXN, bool WG = false>
+template <int NS, int F, int DXN, bool WG = false, bool WAVE = false>
 int launch_bwd(const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t st) {
   static FovPerDevice configured;
   if (!configured.done()) {
-    cudaError_t e = cudaFuncSetAttribute(convlstm_seq_bwd_kernel<NS, F, DXN, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(convlstm_seq_bwd_kernel<NS, F, DXN, WG, WAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) {
       fov_set_error("convlstm_seq_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -679,12 +696,20 @@ int launch_bwd(const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t st)
     }
     configured.mark();
   }
-  convlstm_seq_bwd_kernel<NS, F, DXN, WG><<<grid, kBThr, pl.smem_bytes, st>>>(p);
+  convlstm_seq_bwd_kernel<NS, F, DXN, WG, WAVE><<<grid, kBThr, pl.smem_bytes, st>>>(p);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
 template <int NS, int F>
 int launch_bwd_dx(const BwdParams& p, const BwdPlan& pl, int grid, cudaStream_t st) {
+  if (p.wait_flags || p.set_flags) {      // layer wavefront
+    switch (p.wpk2 ? p.Cin / 2 : 0) {
+      case 0: return launch_bwd<NS, F, 0, false, true>(p, pl, grid, st);
+      case 8: return launch_bwd<NS, F, 8, false, true>(p, pl, grid, st);
+      case 16: return launch_bwd<NS, F, 16, false, true>(p, pl, grid, st);
+      default: fov_set_error("persistent BPTT: unsupported fused dx width"); return FOV_ERR_UNSUPPORTED;
+    }
+  }
   switch (p.wpk2 ? p.Cin / 2 : 0) {
     case 0: return launch_bwd<NS, F, 0>(p, pl, grid, st);
     case 8: return launch_bwd<NS, F, 8>(p, pl, grid, st);
@@ -744,6 +769,15 @@ bool tc_convlstm_seq_bwd_fuses_wgrad(const fov_convlstm_cfg* c, const fov_convls
 // workspace.  Runs the whole reverse time loop: gates (in: activated gates, out: dZ), optional dc0.  dh0 is not
 // produced (callers that need it use the per-timestep path).  When tc_convlstm_seq_bwd_fuses_wgrad() the weight
 // gradients are accumulated too and dZ is not written to HBM (nothing reads it afterwards).
+// image groups (= CTAs) of the persistent BPTT kernel, 0 when the configuration does not take it
+int tc_convlstm_seq_bwd_wave_groups(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT) {
+  if (!tc_convlstm_seq_bwd_supported(c, rT, kT)) return 0;
+  BwdPlan pl;
+  const bool ok = bwd_plan(c, rT, kT, &pl, false) == FOV_OK;
+  fov_set_error("");
+  return ok ? (c->B + pl.G - 1) / pl.G : 0;
+}
+
 int tc_convlstm_seq_bwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const fov_convlstm_grads* gr,
                         const TcConv& rT, const TcConv* kT, cudaStream_t st) {
   const bool want_wg = tc_convlstm_seq_bwd_fuses_wgrad(c, io, gr, rT, kT);
@@ -794,6 +828,9 @@ int tc_convlstm_seq_bwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, co
   p.c0 = io->c0;
   p.dhseq = gr->dhseq; p.dh_b = c->h_b_stride; p.dh_t = c->h_t_stride; p.dh_pix = c->h_pix_stride;
   p.dhT = gr->dhT; p.dcT = gr->dcT; p.dc0 = gr->dc0;
+  p.wait_flags = gr->wave_wait; p.set_flags = gr->wave_set;
+  FOV_CHECK_ARG(!gr->wave_set || kT, "wavefront: wave_set needs the fused input gradient");
+  FOV_CHECK_ARG(!(gr->wave_wait || gr->wave_set) || !pl.wg, "wavefront flags are not available with the in-kernel weight gradient");
   auto a16 = [](const void* q) { return (uintptr_t)q % 16 == 0; };
   FOV_CHECK_ARG(a16(io->gates) && a16(io->cseq) && a16(io->c0) && a16(gr->dhseq) && a16(gr->dhT) && a16(gr->dcT) &&
                     a16(gr->dc0) && c->h_pix_stride % 4 == 0 && c->h_b_stride % 4 == 0 && c->h_t_stride % 4 == 0,

@@ -53,6 +53,10 @@ struct SeqParams {
   float* gates; long long z_b, z_t;       // (B,T,HW,4F) activated gates (training only)
   float* cseq; long long c_b, c_t;        // (B,T,HW,F)
   float *hT, *cT;                // optional dense (B,HW,F)
+  // layer wavefront (optional): [image group][T] flags.  wait_flags: x_t is being written by the layer below while this
+  // kernel runs - wait for its flag, read it through L2; set_flags: raise the flag once h_t is in global memory
+  const int* wait_flags;
+  int* set_flags;
 };
 
 constexpr int kStgStride = 36;   // floats per row of a warp's 32 x 32 staging tile (144 B: conflict-free float4 rows)
@@ -65,6 +69,7 @@ struct SeqBook {
   float bias_s[256];             // [pass][gate][8]: the 32 biases a pass needs are contiguous
   uint64_t w_full, a_full[2], tmem_full[2];
   uint32_t tmem_ptr;
+  int wave_cnt[2];               // arrivals of a group's worker threads at the current step's flag
 };
 
 // diagnostics: cycles CTA 0 spent per phase (fov_debug_seq_read): [0] worker wait tmem_full, [1] phase A, [2] phase B,
@@ -73,7 +78,9 @@ __device__ unsigned long long g_seq_timeline[16];   // [8..12]: phase A split: t
 
 // WPG = worker warps per image group: 4 (one thread per accumulator row does all F channels) or 8 (the two warps of
 // a TMEM lane quarter split the channel passes and the copy-out chunks: twice the threads for the gate algebra)
-template <int NS, int F, int NG, int WPG>
+// WAVE: layer-wavefront instantiation (per-step flags to / from the neighbouring layers' kernels; one group per CTA).  A
+// template parameter, not a run-time test: the flag code costs the large-batch instantiations registers and ~3 %.
+template <int NS, int F, int NG, int WPG, bool WAVE = false>
 __global__ void __launch_bounds__(32 * (WPG * NG + 2), NG == 1 ? 2 : 1) convlstm_seq_fwd_kernel(const SeqParams p) {
   constexpr int kWWarp = WPG * NG, kMmaWarp = WPG * NG + 1, kThr = 32 * (WPG * NG + 2);
   constexpr int N4F = 4 * F;
@@ -99,6 +106,7 @@ __global__ void __launch_bounds__(32 * (WPG * NG + 2), NG == 1 ? 2 : 1) convlstm
     }
   }
   if (tid < N4F) bk->bias_s[((tid & (F - 1)) >> 3) * 32 + (tid / F) * 8 + (tid & 7)] = __ldg(&p.bias[tid]);
+  if (tid < 2) bk->wave_cnt[tid] = 0;
   if (warp == kMmaWarp && lane == 0) {
     mbar_init(smem_u32(&bk->w_full), 1);
     for (int g = 0; g < NG; ++g) {
@@ -171,8 +179,10 @@ __global__ void __launch_bounds__(32 * (WPG * NG + 2), NG == 1 ? 2 : 1) convlstm
         }
       }
     }
+    const int wgrp = blockIdx.x * NG + g;            // my image group: index of its wavefront flags
     auto x_load = [&](int t, float4 (&xv)[XI]) {
       const float* xt = p.x + (long long)t * p.x_t;
+      if (WAVE && p.wait_flags) wave_wait(p.wait_flags + (long long)wgrp * p.T + t);     // the layer below has stored x_t
 #pragma unroll
       for (int j = 0; j < XI; ++j) {
         xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -180,7 +190,7 @@ __global__ void __launch_bounds__(32 * (WPG * NG + 2), NG == 1 ? 2 : 1) convlstm
           const int ch = ((gtd + j * GT) & (lpr - 1)) * 4;
           int nv = sx.Cin - ch;
           nv = nv > 4 ? 4 : nv;
-          xv[j] = ldg_vec4(xt + goff[j], nv, p.x_vec);
+          xv[j] = (WAVE && p.wait_flags) ? ldcg_vec4(xt + goff[j], nv, p.x_vec) : ldg_vec4(xt + goff[j], nv, p.x_vec);
         }
       }
     };
@@ -376,6 +386,7 @@ __global__ void __launch_bounds__(32 * (WPG * NG + 2), NG == 1 ? 2 : 1) convlstm
           ++k;
         }
       }
+      if (WAVE && p.set_flags) wave_publish_arrive(&bk->wave_cnt[g], GT, p.set_flags + (long long)wgrp * p.T + t);
       if (dbg) { c3k = clock64(); tb += c3k - c2k; }
       if (t + 1 < p.T) {
         x_store(xv);
@@ -477,7 +488,7 @@ int seq_plan(const fov_convlstm_cfg* c, const TcConv& step, SeqPlan* out) {
   // Small batches (the reference trains at 32 / 64): the recurrence is latency bound and most SMs idle, so spread the
   // images - as few per group as still fills the machine, one group per CTA.  An MMA step costs the same for 1 or 3
   // images (M = 128 either way) but the gate algebra and the copies of a step shrink with the group.
-  const int sms = fov_num_sms();
+  const int sms = fov_num_sms() / (c->wave_layers > 1 ? c->wave_layers : 1);    // layer wavefront: the stack shares the SMs
   if (!g_fov_seq_no_spread) {
     const int g_fill = (c->B + sms - 1) / sms;
     if (g_fill < pl.G) pl.G = g_fill < 1 ? 1 : g_fill;
@@ -527,11 +538,11 @@ int seq_plan(const fov_convlstm_cfg* c, const TcConv& step, SeqPlan* out) {
   return FOV_OK;
 }
 
-template <int NS, int F, int NG, int WPG>
+template <int NS, int F, int NG, int WPG, bool WAVE = false>
 int launch_seq(const SeqParams& p, const SeqPlan& pl, int grid, cudaStream_t st) {
   static FovPerDevice configured;
   if (!configured.done()) {
-    cudaError_t e = cudaFuncSetAttribute(convlstm_seq_fwd_kernel<NS, F, NG, WPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(convlstm_seq_fwd_kernel<NS, F, NG, WPG, WAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) {
       fov_set_error("convlstm_seq: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -539,13 +550,15 @@ int launch_seq(const SeqParams& p, const SeqPlan& pl, int grid, cudaStream_t st)
     }
     configured.mark();
   }
-  convlstm_seq_fwd_kernel<NS, F, NG, WPG><<<grid, 32 * (WPG * NG + 2), pl.smem_bytes, st>>>(p);
+  convlstm_seq_fwd_kernel<NS, F, NG, WPG, WAVE><<<grid, 32 * (WPG * NG + 2), pl.smem_bytes, st>>>(p);
   FOV_CUDA_LAUNCH_CHECK();
   return FOV_OK;
 }
 
 template <int NS, int F>
 int launch_seq_ng(const SeqParams& p, const SeqPlan& pl, int grid, cudaStream_t st) {
+  if (p.wait_flags || p.set_flags)        // layer wavefront: one group per CTA (checked by the caller)
+    return pl.WPG == 8 ? launch_seq<NS, F, 1, 8, true>(p, pl, grid, st) : launch_seq<NS, F, 1, 4, true>(p, pl, grid, st);
   if (pl.WPG == 8) return pl.NG == 2 ? launch_seq<NS, F, 2, 8>(p, pl, grid, st) : launch_seq<NS, F, 1, 8>(p, pl, grid, st);
   return pl.NG == 2 ? launch_seq<NS, F, 2, 4>(p, pl, grid, st) : launch_seq<NS, F, 1, 4>(p, pl, grid, st);
 }
@@ -577,6 +590,16 @@ bool tc_convlstm_seq_supported(const fov_convlstm_cfg* c, const TcConv& step) {
   const bool ok = seq_plan(c, step, &pl) == FOV_OK;
   fov_set_error("");
   return ok;
+}
+
+// image groups (= CTAs) of the persistent forward when it runs one group per CTA, else 0 (fov_convlstm_wave_groups)
+int tc_convlstm_seq_wave_groups(const fov_convlstm_cfg* c, const TcConv& step) {
+  if (g_seq_disable) return 0;
+  SeqPlan pl;
+  const bool ok = seq_plan(c, step, &pl) == FOV_OK;
+  fov_set_error("");
+  if (!ok || pl.NG != 1) return 0;
+  return (c->B + pl.G - 1) / pl.G;
 }
 
 // step: the fused two-segment step GEMM of this layer (convlstm.cu step_conv) with ws = the packed-weight workspace
@@ -613,6 +636,8 @@ int tc_convlstm_seq_fwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, co
   p.gates = io->gates; p.z_t = (long long)HW * 4 * F; p.z_b = p.z_t * c->T;
   p.cseq = io->cseq; p.c_t = (long long)HW * F; p.c_b = p.c_t * c->T;
   p.hT = io->hT; p.cT = io->cT;
+  p.wait_flags = io->wave_wait; p.set_flags = io->wave_set;
+  FOV_CHECK_ARG(!(io->wave_wait || io->wave_set) || pl.NG == 1, "wavefront flags need one image group per CTA");
   auto a16 = [](const void* q) { return (uintptr_t)q % 16 == 0; };
   FOV_CHECK_ARG(a16(io->hseq) && a16(io->gates) && a16(io->cseq) && a16(io->hT) && a16(io->cT) && a16(io->h0) &&
                     a16(io->c0) && c->h_pix_stride % 4 == 0 && c->h_b_stride % 4 == 0 && c->h_t_stride % 4 == 0,

@@ -116,6 +116,8 @@ int tc_convlstm_seq_fwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, co
 // kT (optional): the input backward-data convolution; when it shares the k order of rT its result dx rides in the
 // same MMAs (extra accumulator columns) and the separate time-batched dx launch is not needed.
 bool tc_convlstm_seq_bwd_supported(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT);
+int tc_convlstm_seq_bwd_wave_groups(const fov_convlstm_cfg* c, const TcConv& rT, const TcConv* kT);
+int tc_convlstm_seq_wave_groups(const fov_convlstm_cfg* c, const TcConv& step);
 int tc_convlstm_seq_bwd(const fov_convlstm_cfg* c, const fov_convlstm_io* io, const fov_convlstm_grads* gr,
                         const TcConv& rT, const TcConv* kT, cudaStream_t st);
 // true: that launch also accumulates g_kernel / g_recurrent / g_bias (no separate weight-gradient launch, dZ stays on chip)

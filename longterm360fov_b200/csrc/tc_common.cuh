@@ -205,6 +205,46 @@ __device__ __forceinline__ float4 ldg_vec4(const float* __restrict__ p, int nval
   return v;
 }
 
+// the same gather through L2 only (ld.global.cg): for tensors another kernel is writing WHILE this one runs (layer
+// wavefront of the persistent ConvLSTM kernels) - __ldg / L1-cached loads may return a stale line there
+__device__ __forceinline__ float4 ldcg_vec4(const float* p, int nvalid, int vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec == 4) {
+    v = __ldcg(reinterpret_cast<const float4*>(p));
+  } else if (vec == 2) {
+    if (nvalid >= 2) { const float2 a = __ldcg(reinterpret_cast<const float2*>(p)); v.x = a.x; v.y = a.y; }
+    if (nvalid >= 4) { const float2 b = __ldcg(reinterpret_cast<const float2*>(p + 2)); v.z = b.x; v.w = b.y; }
+  } else {
+    if (nvalid > 0) v.x = __ldcg(p);
+    if (nvalid > 1) v.y = __ldcg(p + 1);
+    if (nvalid > 2) v.z = __ldcg(p + 2);
+    if (nvalid > 3) v.w = __ldcg(p + 3);
+  }
+  return v;
+}
+
+// ---- layer wavefront: per (image group, timestep) flags in global memory between two concurrently running kernels ----
+// producer: every thread that stored data calls wave_publish_arrive (its stores are device-visible before it counts in);
+// the last of `n` arrivals raises the flag.  consumer: wave_wait spins (bounded: a broken co-residency assumption ends
+// in a trap, not in a hang), then reads the data with ldcg loads.
+__device__ __forceinline__ void wave_publish_arrive(int* smem_counter, int n, int* flag) {
+  __threadfence();
+  if (atomicAdd_block(smem_counter, 1) == n - 1) {
+    *smem_counter = 0;                 // the next step's arrivals are ordered behind this one by the kernel's own barriers
+    __threadfence();
+    *reinterpret_cast<volatile int*>(flag) = 1;
+  }
+}
+__device__ __forceinline__ void wave_wait(const int* flag) {
+  const volatile int* f = reinterpret_cast<const volatile int*>(flag);
+  unsigned spins = 0;
+  while (*f == 0) {
+    __nanosleep(40);
+    if (++spins > (1u << 23)) __trap();          // ~0.5 s: the producer kernel never ran beside this one
+  }
+  __threadfence();
+}
+
 // ---- shared by the shifted-tap kernels -------------------------------------------------------
 // exp-based activations for the fused epilogue (abs error ~1e-7, far inside the bf16-split budget)
 __device__ __forceinline__ float fast_tanh(float x) {

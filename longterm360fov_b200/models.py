@@ -14,8 +14,10 @@ else changes.  Graph topologies follow SURVEY.md section 8a':
 from __future__ import annotations
 
 import collections
+import gc
 import math
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -96,7 +98,10 @@ class _GraphedStep:
     rate are host-side arguments) and so does the gradient allreduce."""
 
     def __init__(self, model, xs, ys, seed=None):
-        self.model = model
+        # weak: model -> _graphs -> step -> model would be a cycle, and a model (with its graphs' private memory pools)
+        # that only the cyclic collector can free may be freed in the middle of ANOTHER model's capture - a cudaFree
+        # there invalidates the capture
+        self._model = weakref.ref(model)
         self.seed = seed
         self.sx = [torch.empty_like(t) for t in xs]
         self.sy = [torch.empty_like(t) for t in ys]
@@ -107,9 +112,14 @@ class _GraphedStep:
             for _ in range(2):
                 self._fwd_bwd()
         torch.cuda.current_stream().wait_stream(side)
+        gc.collect()                                      # nothing left for the collector to free during the capture
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._fwd_bwd()
+
+    @property
+    def model(self):
+        return self._model()
 
     def _load(self, xs, ys):
         for dst, src in zip(self.sx + self.sy, list(xs) + list(ys)):
@@ -178,6 +188,7 @@ class Model:
         # weight gradients on a side stream (ops._WgFork): None = for batches up to wgrad_side_stream_max_batch (where
         # the step is a latency-bound chain and most SMs idle), True / False = always / never
         self.loss_readback_depth = 2      # fit / fit_generator read the loss of a step this many steps late
+        self.layer_wavefront = None       # training steps: None = with CUDA graphs only, True / False = always / never
         self.wgrad_side_stream = None
         self.wgrad_side_stream_min_eager_batch = 384
         self.wgrad_side_stream_max_batch = 2560
@@ -313,10 +324,15 @@ class Model:
             lo = 0 if self._use_graphs else self.wgrad_side_stream_min_eager_batch
             side = lo <= n_local <= self.wgrad_side_stream_max_batch
         ops.set_wgrad_side_stream(side)
+        # layer wavefront of stacked ConvLSTMs (ops._wave_groups: batches whose whole stack fits on the SMs at once):
+        # replayed from a graph B=32 1.19 -> 0.94 ms; launched eagerly a training step of that size is bound by the host,
+        # and the extra stream bookkeeping costs more than the overlap returns (1.49 -> 1.89 ms) - graphs only
+        ops.set_layer_wavefront(self._use_graphs if self.layer_wavefront is None else self.layer_wavefront)
         try:
             return self._train_step_device(xs, ys, targets_ready, n_local, seed, bool(side))
         finally:
             ops.set_wgrad_side_stream(False)
+            ops.set_layer_wavefront(True)
 
     def _train_step_device(self, xs, ys, targets_ready, n_local, seed, side):
         if self._use_graphs:

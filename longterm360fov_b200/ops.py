@@ -125,6 +125,50 @@ def join_wgrad_stream():
 
 
 # --------------------------------------------------------------------------- #
+# layer wavefront of stacked ConvLSTMs at small batches
+# --------------------------------------------------------------------------- #
+# At the reference's batch sizes the three stacked recurrences (20 dependent steps each, ~8 us per step) run back to
+# back on a few SMs.  When every CTA of the whole stack fits on the GPU at once, the layers are launched on separate
+# streams instead and run CONCURRENTLY: layer l publishes a flag per (image group, timestep) once h_t is in global memory,
+# layer l+1 waits for it before it reads x_t (fov_convlstm_io.wave_set / wave_wait); the BPTT kernels do the same in the
+# other direction through the fused input gradient (fov_convlstm_grads.wave_set / wave_wait).
+_WAVE = {"on": True, "streams": {}}
+
+
+def set_layer_wavefront(on):
+    _WAVE["on"] = bool(on)
+
+
+def _wave_streams(n):
+    dev = torch.cuda.current_device()
+    sts = _WAVE["streams"].setdefault(dev, [])
+    while len(sts) < n:
+        sts.append(torch.cuda.Stream(device=dev))
+    return sts[:n]
+
+
+def _wave_groups(lib, cfgs, backward, with_dx):
+    """Image groups per layer when EVERY layer of the stack takes a persistent one-group-per-CTA kernel with the same
+    grouping and all their CTAs can be resident at once; else 0."""
+    if not _WAVE["on"] or len(cfgs) < 2 or cfgs[0].T < 2:
+        return 0
+    g0 = 0
+    for l, cfg in enumerate(cfgs):
+        cfg.wave_layers = len(cfgs)               # group size such that the whole stack fits on the SMs
+        g = lib.fov_convlstm_wave_groups(C.byref(cfg), int(backward), int(with_dx[l]))
+        if g <= 0 or (l and g != g0):
+            g0 = 0
+            break
+        g0 = g
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    if g0 and g0 * len(cfgs) <= sms:
+        return g0
+    for cfg in cfgs:
+        cfg.wave_layers = 0
+    return 0
+
+
+# --------------------------------------------------------------------------- #
 # persistent fc-LSTM encoder-decoder
 # --------------------------------------------------------------------------- #
 
@@ -688,6 +732,23 @@ class ConvLSTMStackFn(torch.autograd.Function):
         cur_ptr = ptr(x)
         masks = opts.get("dropout_masks") or [None] * L
         drop = []
+        # layer wavefront (small batches, no dropout): every layer on its own stream, per-step flags between them
+        wave_g, wflags, wstreams, main_s = 0, None, None, torch.cuda.current_stream()
+        wave_keep = []
+        if not (training and any(m is not None for m in masks)):
+            probe, c_ = [], Cin0
+            for l in range(L):
+                K_ = weights[l][0]
+                probe.append(_lib.ConvLstmCfg(B, T, H, W, c_, Fs[l], K_.shape[0], K_.shape[1], dil[0], dil[1], rec,
+                                              (T * HW * Cin0) if l == 0 else T * HW * Fsum, (HW * Cin0) if l == 0 else HW * Fsum,
+                                              Cin0 if l == 0 else Fsum, T * HW * Fsum, HW * Fsum, Fsum, int(training), math, 0))
+                c_ = Fs[l]
+            wave_g = _wave_groups(lib, probe, False, [False] * L)
+            if wave_g:
+                wflags = torch.zeros(max(L - 1, 1), wave_g, T, dtype=torch.int32, device=dev)
+                wstreams = [main_s] + _wave_streams(L - 1)
+                for s_ in wstreams[1:]:
+                    s_.wait_stream(main_s)
         for l in range(L):
             K, R, b = weights[l]
             kh, kw = K.shape[0], K.shape[1]
@@ -709,7 +770,8 @@ class ConvLSTMStackFn(torch.autograd.Function):
                 lx_ptr, lx_b, lx_t, lx_pix, lcin, lK = cur_ptr, cur_b, cur_t, cur_pix, cin, K
             drop.append((mask, x4, K4))
             cfg = _lib.ConvLstmCfg(B, T, H, W, lcin, F, kh, kw, dil[0], dil[1], rec,
-                                   lx_b, lx_t, lx_pix, T * HW * Fsum, HW * Fsum, Fsum, int(training), math, 0)
+                                   lx_b, lx_t, lx_pix, T * HW * Fsum, HW * Fsum, Fsum, int(training), math, 0,
+                                   L if wave_g else 0)
             # saved gates exist only for BPTT; the fused tensor-core step never materialises them otherwise
             fws_bytes = lib.fov_convlstm_fwd_ws_bytes(C.byref(cfg))     # > 0: the fused tensor-core step runs
             gates = torch.empty((B, T, H, W, 4 * F) if (training or fws_bytes == 0) else (1,), device=dev)
@@ -731,14 +793,24 @@ class ConvLSTMStackFn(torch.autograd.Function):
             cT = torch.empty(B, H, W, F, device=dev)
             h0, c0 = states[l]
             hptr = cat.data_ptr() + 4 * off
+            w_wait = wflags[l - 1].data_ptr() if (wave_g and l > 0) else None
+            w_set = wflags[l].data_ptr() if (wave_g and l < L - 1) else None
+            # wavefront: this layer runs on its own stream while the loop goes on - its workspace must outlive the loop
+            # iteration (a block freed here could be handed to the next layer's allocation on the main stream)
+            wave_keep.append(fws)
             io = _lib.ConvLstmIO(lx_ptr, ptr(lK), ptr(R), ptr(b), ptr(h0), ptr(c0), hptr,
-                                 ptr(gates), ptr(cseq), ptr(hT), ptr(cT), ptr(fws))
-            _lib.check(lib.fov_convlstm_fwd(C.byref(cfg), C.byref(io), st), "fov_convlstm_fwd")
+                                 ptr(gates), ptr(cseq), ptr(hT), ptr(cT), ptr(fws), w_wait, w_set)
+            _lib.check(lib.fov_convlstm_fwd(C.byref(cfg), C.byref(io), wstreams[l].cuda_stream if wave_g else st),
+                       "fov_convlstm_fwd")
             outs += [hT, cT]
             saved.append((gates, cseq))
             cfgs.append((cfg, cur_ptr, hptr, off, F, (cur_b, cur_t, cur_pix, cin)))
             cur_ptr, cur_b, cur_t, cur_pix, cin = hptr, T * HW * Fsum, HW * Fsum, Fsum, F
             off += F
+        if wave_g:
+            for s_ in wstreams[1:]:
+                main_s.wait_stream(s_)
+        del wave_keep
         if training:
             ctx.sinks, ctx.cfgs, ctx.L, ctx.drop = sinks, cfgs, L, drop
             ctx.x_needs_grad = ctx.needs_input_grad[2]
@@ -763,6 +835,16 @@ class ConvLSTMStackFn(torch.autograd.Function):
         dcat = torch.zeros_like(cat) if dcat is None else dcat.contiguous()
         dx0 = torch.empty_like(x) if ctx.x_needs_grad else None
         dstate_out = [None] * (2 * L)
+        # layer wavefront of the BPTT kernels: layer l waits per step for the fused dx of layer l+1
+        wave_g, wflags, wstreams, main_s = 0, None, None, torch.cuda.current_stream()
+        wave_keep = []          # per-layer temporaries stay alive until the layers' streams have been joined
+        if all(d[0] is None for d in ctx.drop) and not any(ctx.state_needs_grad[l] and per[l][3] is not None for l in range(L)):
+            wave_g = _wave_groups(lib, [c[0] for c in cfgs], True, [l > 0 or ctx.x_needs_grad for l in range(L)])
+            if wave_g:
+                wflags = torch.zeros(max(L - 1, 1), wave_g, cfgs[0][0].T, dtype=torch.int32, device=dev)
+                wstreams = [main_s] + _wave_streams(L - 1)
+                for s_ in wstreams[1:]:
+                    s_.wait_stream(main_s)
         for l in reversed(range(L)):
             cfg, _xptr, _hptr, off, F, xgeo = cfgs[l]
             K, R, b, h0, c0, gates, cseq = per[l]
@@ -772,6 +854,7 @@ class ConvLSTMStackFn(torch.autograd.Function):
             dhT, dcT = _f32c(dstates[2 * l]), _f32c(dstates[2 * l + 1])
             nws = lib.fov_convlstm_bwd_ws_floats(C.byref(cfg))
             ws = torch.empty(nws, device=dev)
+            wave_keep += [ws, dhT, dcT]
             dh0 = dc0 = None
             if ctx.state_needs_grad[l] and h0 is not None:
                 dh0 = torch.empty_like(h0)
@@ -787,10 +870,14 @@ class ConvLSTMStackFn(torch.autograd.Function):
                 side = _wg_stream()
                 if side is not None:     # the layer's weight gradient reads these after this node has returned
                     _wg_keep(side, gates, cat, x, h0)
+                # producer of layer l's dhseq = layer l+1 (flags[l]); this layer publishes into flags[l-1]
+                w_wait = wflags[l].data_ptr() if (wave_g and l < L - 1) else None
+                w_set = wflags[l - 1].data_ptr() if (wave_g and l > 0) else None
                 g = _lib.ConvLstmGrads(dcat.data_ptr() + 4 * off, ptr(dhT), ptr(dcT), dxp, ptr(dh0), ptr(dc0),
                                        ptr(gk), ptr(gr_), ptr(gb), ptr(ws), acc,
-                                       side.cuda_stream if side is not None else None)
-                _lib.check(lib.fov_convlstm_bwd(C.byref(cfg), C.byref(io), C.byref(g), st), "fov_convlstm_bwd")
+                                       side.cuda_stream if side is not None else None, w_wait, w_set)
+                _lib.check(lib.fov_convlstm_bwd(C.byref(cfg), C.byref(io), C.byref(g),
+                                                wstreams[l].cuda_stream if wave_g else st), "fov_convlstm_bwd")
             else:
                 # widened-input form: gradients w.r.t. x4 / K4, folded back through the masks / the gate blocks
                 xb_, xt_, xpix_, cin_ = xgeo
@@ -799,7 +886,7 @@ class ConvLSTMStackFn(torch.autograd.Function):
                 io = _lib.ConvLstmIO(ptr(x4), ptr(K4), ptr(R), ptr(b), ptr(h0), ptr(c0), hptr,
                                      ptr(gates), ptr(cseq), None, None, None)
                 g = _lib.ConvLstmGrads(dcat.data_ptr() + 4 * off, ptr(dhT), ptr(dcT), ptr(dx4), ptr(dh0), ptr(dc0),
-                                       ptr(gk4), ptr(gr_), ptr(gb), ptr(ws), 0, None)
+                                       ptr(gk4), ptr(gr_), ptr(gb), ptr(ws), 0, None, None, None)
                 _lib.check(lib.fov_convlstm_bwd(C.byref(cfg), C.byref(io), C.byref(g), st), "fov_convlstm_bwd")
                 _lib.check(lib.fov_gate_kernel_reduce(K.shape[0] * K.shape[1], cin_, F, ptr(gk4), ptr(gk), st),
                            "fov_gate_kernel_reduce")
@@ -807,6 +894,10 @@ class ConvLSTMStackFn(torch.autograd.Function):
                     _lib.check(lib.fov_dropout_reduce(cfg.B, cfg.T, cfg.H * cfg.W, cin_, ptr(dx4), ptr(mask), dxp,
                                                       xb_, xt_, xpix_, acc, st), "fov_dropout_reduce")
             dstate_out[2 * l], dstate_out[2 * l + 1] = dh0, dc0
+        if wave_g:
+            for s_ in wstreams[1:]:
+                main_s.wait_stream(s_)
+        del wave_keep
         return (None, None, dx0) + (None,) * (3 * L) + tuple(dstate_out)
 
 

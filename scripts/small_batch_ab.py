@@ -31,21 +31,24 @@ def step_ms(m, xs, ys, reps=30):
     return e0.elapsed_time(e1) / reps
 
 
+from longterm360fov_b200 import ops
+
 for B in Bs:
     x, y = data.make_m3_batch(B, 34, seed=0)
     row = []
-    for spread, side in ((0, False), (1, False), (1, True)):
+    for spread, side, wave in ((0, False, False), (1, False, False), (1, True, False), (1, True, True)):
         lib.fov_debug_seq_spread(spread)
         lib.fov_debug_lstm_small_tiles(spread)
         lib.fov_debug_wgrad_rows_full_grid(1 - spread)
+        ops.set_layer_wavefront(wave)
         for graphs in (False, True):
             m = fov.others_lstm_span_whole(num_user=34, seed=1).compile("Adam", ["mean_squared_error"] * 3, [1, 1, 1])
             m.wgrad_side_stream = side
+            m.layer_wavefront = wave
             if graphs:
                 m.enable_cuda_graphs()
             xs, ys = m._to_dev(x), m._to_dev(y)
             row.append(step_ms(m, xs, ys))
-    print("B=%5d  large-batch shapes: eager %.3f ms, graph %.3f ms | small-batch shapes: eager %.3f, graph %.3f | + weight "
-          "gradients on a side stream: eager %.3f, graph %.3f  (%.0f -> %.0f -> %.0f seq/s)"
-          % (B, row[0], row[1], row[2], row[3], row[4], row[5], B / min(row[0], row[1]) * 1e3,
-             B / min(row[2], row[3]) * 1e3, B / min(row[4], row[5]) * 1e3))
+    print("B=%5d  eager / graph ms:  large-batch shapes %.3f / %.3f | small-batch shapes %.3f / %.3f | + weight gradients "
+          "on a side stream %.3f / %.3f | + layer wavefront %.3f / %.3f   (best: %.0f -> %.0f -> %.0f -> %.0f seq/s)"
+          % ((B,) + tuple(row) + tuple(B / min(row[2 * i], row[2 * i + 1]) * 1e3 for i in range(4))))

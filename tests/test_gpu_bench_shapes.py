@@ -773,6 +773,40 @@ def test_weight_gradients_on_side_stream_match(graphs):
         np.testing.assert_allclose(a, b, atol=1e-5, err_msg=k)
 
 
+# ------------------------------------------------------------------ layer wavefront of stacked ConvLSTMs
+
+@pytest.mark.parametrize("B", [3, 40, 64, 147, 150])
+def test_layer_wavefront_matches_sequential_layers(B):
+    """ops.set_layer_wavefront: at batches whose whole ConvLSTM stack fits on the SMs at once (B <= 147 for three
+    layers) the layers run concurrently on separate streams, handing timesteps over through per-(group, step) flags,
+    forward and BPTT.  Each image's arithmetic is unchanged, so the forward is BIT-identical to the layer-after-layer
+    run; 4 Adam steps (eager and from a CUDA graph) end in the same losses and weights to rounding (weight gradients
+    are red.global.add sums either way).  B = 150 does not qualify and must silently take the sequential path."""
+    fov = _cuda()
+    from longterm360fov_b200 import data, ops
+    x, y = data.make_m3_batch(B, 34, seed=B)
+    outs = []
+    for wave in (False, True):
+        ops.set_layer_wavefront(wave)
+        m = fov.others_lstm_span_whole(num_user=34, seed=2)
+        outs.append(m.predict_on_batch(x))
+    ops.set_layer_wavefront(True)
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    res = []
+    for wave, graphs in ((False, False), (True, False), (True, True)):
+        m = fov.others_lstm_span_whole(num_user=34, seed=2).compile("Adam", ["mean_squared_error"] * 3, [1, 1, 1])
+        m.layer_wavefront = wave
+        if graphs:
+            m.enable_cuda_graphs()
+        losses = [m.train_on_batch(x, y) for _ in range(4)]
+        res.append((losses, m.get_weights()))
+    for other in res[1:]:
+        np.testing.assert_allclose(res[0][0], other[0], rtol=1e-5)
+        for a, b, k in zip(res[0][1], other[1], m.weight_order):
+            np.testing.assert_allclose(a, b, atol=1e-5, err_msg=k)
+
+
 # ------------------------------------------------------------------ ConvLSTM weight gradient inside the persistent BPTT
 
 @pytest.mark.parametrize("B,T", [(1, 1), (4, 20), (131, 7), (7, 2)])
