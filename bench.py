@@ -359,8 +359,9 @@ def other_workloads(dev, peaks, compute):
         del ms3
     res["others_lstm_span_whole_train_batch32"] = dict(small, batch=Bs, unit="sequences/s",
                                                        note="the reference's batch size; latency bound (3 x 20 dependent recurrence steps forward and "
-                                                            "backward): small-batch launch shapes (one image per CTA, 4-sequence fc-LSTM tiles), "
-                                                            "model.enable_cuda_graphs() replays forward + BPTT from one graph")
+                                                            "backward): small-batch launch shapes (one image per CTA, 4-sequence fc-LSTM tiles); "
+                                                            "model.enable_cuda_graphs() replays forward + BPTT from one graph, in which the three ConvLSTM "
+                                                            "layers run as a wavefront and the weight gradients on a side stream")
 
     # ---- sample builders: windows of a full-size video, one-hot heatmaps; HBM-bound ----
     from longterm360fov_b200 import ops as _o
