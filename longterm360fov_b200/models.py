@@ -185,13 +185,12 @@ class Model:
         # terms per operand by default (~16 mantissa bits, forward error ~1e-5); "fp32" selects the CUDA-core kernels
         self.compute = os.environ.get("FOV_COMPUTE", "bf16x2")
         self._graphs, self._use_graphs = {}, False
-        # weight gradients on a side stream (ops._WgFork): None = for batches up to wgrad_side_stream_max_batch (where
-        # the step is a latency-bound chain and most SMs idle), True / False = always / never
+        # weight gradients on a side stream (ops._WgFork): None = always when the step is replayed from a CUDA graph,
+        # eagerly from wgrad_side_stream_min_eager_batch sequences; True / False = always / never
         self.loss_readback_depth = 2      # fit / fit_generator read the loss of a step this many steps late
         self.layer_wavefront = None       # training steps: None = with CUDA graphs only, True / False = always / never
         self.wgrad_side_stream = None
         self.wgrad_side_stream_min_eager_batch = 384
-        self.wgrad_side_stream_max_batch = 2560
 
     def enable_cuda_graphs(self, on=True):
         """Replay the training step from a CUDA graph (captured per input-shape set on first use).  Worth it when the
@@ -317,12 +316,12 @@ class Model:
         # small batches: the weight-gradient launches leave the backward chain for a side stream (ops.set_wgrad_side_stream)
         side = self.wgrad_side_stream
         if side is None:
-            # measured on B200 (scripts/small_batch_ab.py, config 2): replayed from a CUDA graph the fork always pays
-            # (B=32 1.36 -> 1.17 ms, B=1110 3.92 -> 3.56 ms); launched eagerly its host cost (events, stream switches,
-            # allocator bookkeeping) outweighs it below ~400 sequences (B=256 2.10 -> 2.82 ms, B=512 2.64 -> 2.14 ms);
-            # above ~2.5 k sequences the kernels fill the GPU and the gain fades (B=8880 +2 %) - left off there
+            # measured on B200 (scripts/small_batch_ab.py, scripts/m3_side_stream_ab.py, config 2): replayed from a CUDA
+            # graph the fork always pays (B=32 1.36 -> 1.17 ms, B=1110 3.92 -> 3.56 ms); launched eagerly its host cost
+            # (events, stream switches) outweighs it below ~400 sequences (B=256 2.10 -> 2.82 ms, B=512 2.64 -> 2.14 ms);
+            # at large batches the overlap still returns 1-4 % (B=2220 6.04 -> 5.83, B=8880 20.25 -> 19.97 ms)
             lo = 0 if self._use_graphs else self.wgrad_side_stream_min_eager_batch
-            side = lo <= n_local <= self.wgrad_side_stream_max_batch
+            side = n_local >= lo
         ops.set_wgrad_side_stream(side)
         # layer wavefront of stacked ConvLSTMs (ops._wave_groups: batches whose whole stack fits on the SMs at once):
         # replayed from a graph B=32 1.19 -> 0.94 ms; launched eagerly a training step of that size is bound by the host,
@@ -1088,6 +1087,9 @@ class ConvLSTMSeq2Seq(Model):
         self.sample_seed = int(sample_seed)
         self.noise_fn = None          # optional callable (step, B) -> (B,fps,3) N(0,1) tensor: explicit noise (parity runs)
         self._draws = 0
+        # the heads' weight gradients (42 % of the backward time) overlap the backward-data convolutions of the next
+        # decoder step: measured 35.8 -> 33.6 ms per training step at B=32 (scripts/m4_side_stream_ab.py)
+        self.wgrad_side_stream = True
 
     def _noise(self, step, B, fps):
         """Standard-normal draws of one decoder step: the caller's explicit noise, else the in-kernel Philox stream

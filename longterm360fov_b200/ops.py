@@ -64,13 +64,16 @@ def _ws(nbytes, device):
 # Nothing on the backward chain reads a weight gradient: only the optimiser does.  At small batches (the reference
 # trains at 32 / 64) the step is a chain of dependent launches that leaves most SMs idle, so the weight-gradient
 # launches can leave that chain: they fork onto a side stream after the kernel that produced their operands and the
-# caller joins the stream before the optimiser step (join_wgrad_stream).  Tensors they read are registered with the
-# caching allocator (record_stream), so nothing is recycled under them.  Graph-capture safe (event fork / join).
-_WG = {"on": False, "streams": {}, "used": False}
+# caller joins the stream before the optimiser step (join_wgrad_stream).  Tensors they read are held in a keep-list
+# until that join (so nothing is recycled under them; record_stream would defer their release to an allocator event
+# poll and make the pool churn at multi-GB batches).  Graph-capture safe (event fork / join).
+_WG = {"on": False, "streams": {}, "used": False, "keep": []}
 
 
 def set_wgrad_side_stream(on):
     _WG["on"] = bool(on)
+    if not on and (_WG["used"] or _WG["keep"]):      # a pass that ended without its join (an exception on the way)
+        join_wgrad_stream()
 
 
 def _wg_stream():
@@ -86,9 +89,7 @@ def _wg_stream():
 
 
 def _wg_keep(side, *tensors):
-    for t in tensors:
-        if t is not None and t.is_cuda:
-            t.record_stream(side)
+    _WG["keep"].extend(t for t in tensors if t is not None)
 
 
 class _WgFork:
@@ -122,6 +123,7 @@ def join_wgrad_stream():
             if st.device == cur.device:
                 cur.wait_stream(st)
         _WG["used"] = False
+    _WG["keep"].clear()
 
 
 # --------------------------------------------------------------------------- #
@@ -526,15 +528,16 @@ class TapStackConvFn(torch.autograd.Function):
         dyp = torch.empty(N, H, W, CW, device=x.device)
         _lib.check(lib.fov_tapstack_expand(N * H, W, kw, pad_w, Cp, Cout, ptr(dpre), ptr(dyp), st), "fov_tapstack_expand")
         gw, gb = ctx.sinks
-        gws = torch.zeros(kh, 1, Cin, CW, device=x.device)
-        gbs = torch.zeros(CW, device=x.device) if gb is not None else None
-        nws = lib.fov_conv_wgrad_ws_bytes(C.byref(cfg), math)
-        wws = _ws(nws, x.device) if nws else None
-        _lib.check(lib.fov_conv2d_bwd_weight_tc_ws(C.byref(cfg), ptr(x), ptr(dyp), ptr(gws), ptr(gbs), ptr(wws), math, st),
-                   "fov_conv2d_bwd_weight_tc_ws")
-        gw.view(kh, kw, Cin, Cout).add_(gws.view(kh, Cin, kw, Cp)[..., :Cout].permute(0, 2, 1, 3))
-        if gb is not None:                  # the centre tap's columns are dpre itself (shift 0): their sums are the bias gradient
-            gb += gbs[pad_w * Cp:pad_w * Cp + Cout]
+        with _WgFork(x, dyp):               # off the backward chain when the side stream is on (ops._WgFork)
+            gws = torch.zeros(kh, 1, Cin, CW, device=x.device)
+            gbs = torch.zeros(CW, device=x.device) if gb is not None else None
+            nws = lib.fov_conv_wgrad_ws_bytes(C.byref(cfg), math)
+            wws = _ws(nws, x.device) if nws else None
+            _lib.check(lib.fov_conv2d_bwd_weight_tc_ws(C.byref(cfg), ptr(x), ptr(dyp), ptr(gws), ptr(gbs), ptr(wws), math,
+                                                       _stream()), "fov_conv2d_bwd_weight_tc_ws")
+            gw.view(kh, kw, Cin, Cout).add_(gws.view(kh, Cin, kw, Cp)[..., :Cout].permute(0, 2, 1, 3))
+            if gb is not None:              # the centre tap's columns are dpre itself (shift 0): their sums are the bias gradient
+                gb += gbs[pad_w * Cp:pad_w * Cp + Cout]
         dx = None
         if ctx.need_dx:
             dx = torch.empty_like(x)
