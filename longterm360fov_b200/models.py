@@ -187,7 +187,8 @@ class Model:
         self._graphs, self._use_graphs = {}, False
         # weight gradients on a side stream (ops._WgFork): None = always when the step is replayed from a CUDA graph,
         # eagerly from wgrad_side_stream_min_eager_batch sequences; True / False = always / never
-        self.loss_readback_depth = 2      # fit / fit_generator read the loss of a step this many steps late
+        # fit / fit_generator read the loss of a step this many steps late (FOV_READBACK_DEPTH overrides)
+        self.loss_readback_depth = int(os.environ.get("FOV_READBACK_DEPTH", "2"))
         self.layer_wavefront = None       # training steps: None = with CUDA graphs only, True / False = always / never
         self.wgrad_side_stream = None
         self.wgrad_side_stream_min_eager_batch = 384
@@ -409,8 +410,31 @@ class Model:
             cur = fetch()
         except StopIteration:
             return
-        pending = collections.deque()                          # (batch size, loss tensor) of the steps in flight
+        pending = collections.deque()                          # (batch size, pinned host scalar, copy-done event)
         depth = max(1, int(self.loss_readback_depth))
+        # The loss goes back to the host on its OWN stream, behind an event recorded right after the step that produced
+        # it.  (`loss.item()` would enqueue its copy at the tail of the compute stream and block the host until every
+        # step launched so far has finished: the host could then never run ahead of the GPU, and with several ranks
+        # the per-step gaps drift apart and the gradient allreduce waits for the slowest.)
+        if getattr(self, "_readback_stream", None) is None:
+            self._readback_stream = torch.cuda.Stream(device=self.device)
+            self._readback_ring = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(8)]
+            self._readback_i = 0
+        rb = self._readback_stream
+
+        def read_back(loss):
+            ev = torch.cuda.Event()
+            ev.record()
+            host = self._readback_ring[self._readback_i % len(self._readback_ring)]
+            self._readback_i += 1
+            with torch.cuda.stream(rb):
+                rb.wait_event(ev)
+                host.copy_(loss.reshape(1), non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(rb)
+            loss.record_stream(rb)
+            return host, done
+        depth = min(depth, len(self._readback_ring) - 2)
         while cur is not None:
             xs, ys, (x_ready, y_ready), b = cur
             torch.cuda.current_stream().wait_event(x_ready)
@@ -425,13 +449,15 @@ class Model:
             # the loss of step i-depth is read while the steps after it run: the host never drains the GPU between
             # steps, and with depth > 1 a launch-latency spike on the host (8 ranks sharing the host's cores and the
             # driver) is absorbed by the queued steps instead of opening a bubble
-            pending.append((b, loss))
+            pending.append((b,) + read_back(loss))
             while len(pending) > depth:
-                pb, pl = pending.popleft()
-                yield pb, float(pl.item())
+                pb, ph, pd = pending.popleft()
+                pd.synchronize()
+                yield pb, float(ph)
         while pending:
-            pb, pl = pending.popleft()
-            yield pb, float(pl.item())
+            pb, ph, pd = pending.popleft()
+            pd.synchronize()
+            yield pb, float(ph)
 
     def test_on_batch(self, x, y):
         xs, ys = self._to_dev(self._as_list(x)), self._to_dev(self._as_list(y))
