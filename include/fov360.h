@@ -255,6 +255,9 @@ size_t fov_convlstm_fwd_ws_bytes(const fov_convlstm_cfg* cfg);
  * with_dx) kernel for this configuration, 0 when the configuration does not take a persistent kernel with one group per
  * CTA (then the wavefront flags are not available).  The group of image b is b / (ceil(B / groups)). */
 int fov_convlstm_wave_groups(const fov_convlstm_cfg* cfg, int backward, int with_dx);
+/* 1 when fov_convlstm_fwd runs this configuration as ONE persistent launch over all timesteps (whole images per MMA
+ * tile), 0 when it launches per timestep (then a caller may interleave the layers of a stack at launch level) */
+int fov_convlstm_fwd_persistent(const fov_convlstm_cfg* cfg);
 int fov_convlstm_fwd(const fov_convlstm_cfg* cfg, const fov_convlstm_io* io, void* stream);
 
 typedef struct {

@@ -114,6 +114,7 @@ SYMBOLS = {
     "fov_convlstm_fwd": (_I, [C.POINTER(ConvLstmCfg), C.POINTER(ConvLstmIO), _P]),
     "fov_convlstm_fwd_ws_bytes": (C.c_size_t, [C.POINTER(ConvLstmCfg)]),
     "fov_convlstm_wave_groups": (_I, [_P, _I, _I]),
+    "fov_convlstm_fwd_persistent": (_I, [_P]),
     "fov_convlstm_bwd_ws_floats": (C.c_size_t, [C.POINTER(ConvLstmCfg)]),
     "fov_convlstm_bwd": (_I, [C.POINTER(ConvLstmCfg), C.POINTER(ConvLstmIO), C.POINTER(ConvLstmGrads), _P]),
     "fov_softmax_fwd": (_I, [_LL, _I, _P, _P, _P]),

@@ -128,6 +128,12 @@ extern "C" size_t fov_convlstm_fwd_ws_bytes(const fov_convlstm_cfg* cfg) {
   return tc_conv_ws_bytes(step_conv(cfg, &io, geo(cfg)));
 }
 
+extern "C" int fov_convlstm_fwd_persistent(const fov_convlstm_cfg* cfg) {
+  if (!cfg || check(cfg) || !tc_step_ok(cfg)) { fov_set_error(""); return 0; }
+  fov_convlstm_io io{};
+  return tc_convlstm_seq_supported(cfg, step_conv(cfg, &io, geo(cfg))) ? 1 : 0;
+}
+
 extern "C" int fov_convlstm_wave_groups(const fov_convlstm_cfg* cfg, int backward, int with_dx) {
   if (!cfg || check(cfg) || !tc_step_ok(cfg)) { fov_set_error(""); return 0; }
   const Geo g = geo(cfg);

@@ -752,6 +752,13 @@ class ConvLSTMStackFn(torch.autograd.Function):
                 wstreams = [main_s] + _wave_streams(L - 1)
                 for s_ in wstreams[1:]:
                     s_.wait_stream(main_s)
+        if (not training and not wave_g and _WAVE["on"] and L >= 2 and T >= 2 and math != 0
+                and all(lib.fov_convlstm_fwd_ws_bytes(C.byref(c_)) > 0 and not lib.fov_convlstm_fwd_persistent(C.byref(c_))
+                        for c_ in probe)):
+            # inference on images larger than one MMA tile (config 5's 36 x 18 heat maps): every (layer, timestep) is its
+            # own launch, so the layers can run as a wavefront at LAUNCH level - layer l step t next to layer l+1 step
+            # t-1 - on one stream per layer with an event per (layer, step): (T + L - 1) launch slots instead of T * L
+            return ConvLSTMStackFn._forward_step_wavefront(lib, opts, x, weights, states, probe, Fs, math)
         for l in range(L):
             K, R, b = weights[l]
             kh, kw = K.shape[0], K.shape[1]
@@ -822,6 +829,59 @@ class ConvLSTMStackFn(torch.autograd.Function):
             for l in range(L):
                 tensors += list(weights[l]) + list(states[l]) + list(saved[l])
             ctx.save_for_backward(*tensors)
+        return (cat,) + tuple(outs)
+
+    @staticmethod
+    def _forward_step_wavefront(lib, opts, x, weights, states, probe, Fs, math):
+        B, T, H, W, Cin0 = x.shape
+        L, HW, Fsum, dev = len(weights), H * W, sum(Fs), x.device
+        cat = torch.empty(B, T, H, W, Fsum, device=dev)
+        main_s = torch.cuda.current_stream()
+        streams = [main_s] + _wave_streams(L - 1)
+        for s_ in streams[1:]:
+            s_.wait_stream(main_s)
+        pcache = opts.get("pack_cache")
+        lay, off, cin = [], 0, Cin0
+        for l in range(L):
+            K, R, b = weights[l]
+            F = Fs[l]
+            c1 = probe[l]
+            cfg = _lib.ConvLstmCfg(B, 1, H, W, cin, F, K.shape[0], K.shape[1], c1.dil_h, c1.dil_w, c1.rec_act,
+                                   c1.x_b_stride, c1.x_t_stride, c1.x_pix_stride, T * HW * Fsum, HW * Fsum, Fsum, 0, math, 0, 0)
+            fws_bytes = lib.fov_convlstm_fwd_ws_bytes(C.byref(cfg))
+            pkey = (K.data_ptr(), R.data_ptr(), tuple(K.shape), math, B, H, W) if pcache is not None else None
+            fws = pcache.get(pkey) if pkey is not None else None
+            packed = fws is not None
+            if fws is None:
+                fws = _ws(fws_bytes, dev)
+                if pkey is not None:
+                    pcache[pkey] = fws
+            x_base = x.data_ptr() if l == 0 else cat.data_ptr() + 4 * (off - Fs[l - 1])
+            lay.append(dict(cfg=cfg, K=K, R=R, b=b, fws=fws, packed=packed, x_base=x_base, x_t=4 * c1.x_t_stride,
+                            h_base=cat.data_ptr() + 4 * off, h_t=4 * HW * Fsum,
+                            st=[(torch.empty(B, H, W, F, device=dev), torch.empty(B, H, W, F, device=dev)) for _ in range(2)],
+                            cseq=torch.empty(B, 1, H, W, F, device=dev), gates=torch.empty(1, device=dev),
+                            h=states[l][0], c=states[l][1]))
+            off += F
+            cin = F
+        ev = [[torch.cuda.Event() for _ in range(T)] for _ in range(L)]
+        for t in range(T):
+            for l, d in enumerate(lay):
+                s_ = streams[l]
+                if l > 0:
+                    s_.wait_event(ev[l - 1][t])
+                d["cfg"].ws_prepacked = 1 if (d["packed"] or t > 0) else 0
+                hT, cT = d["st"][t & 1]
+                io = _lib.ConvLstmIO(d["x_base"] + t * d["x_t"], ptr(d["K"]), ptr(d["R"]), ptr(d["b"]), ptr(d["h"]), ptr(d["c"]),
+                                     d["h_base"] + t * d["h_t"], ptr(d["gates"]), ptr(d["cseq"]), ptr(hT), ptr(cT), ptr(d["fws"]))
+                _lib.check(lib.fov_convlstm_fwd(C.byref(d["cfg"]), C.byref(io), s_.cuda_stream), "fov_convlstm_fwd")
+                ev[l][t].record(s_)
+                d["h"], d["c"] = hT, cT
+        for s_ in streams[1:]:
+            main_s.wait_stream(s_)
+        outs = []
+        for d in lay:
+            outs += [d["h"], d["c"]]
         return (cat,) + tuple(outs)
 
     @staticmethod

@@ -807,6 +807,48 @@ def test_layer_wavefront_matches_sequential_layers(B):
             np.testing.assert_allclose(a, b, atol=1e-5, err_msg=k)
 
 
+@pytest.mark.parametrize("shape", [(3, 12, 6), (2, 36, 18)])
+@pytest.mark.parametrize("mode", ["bf16", "bf16x2"])
+def test_step_wavefront_inference_matches(shape, mode):
+    """Images larger than one MMA tile run one launch per (layer, timestep); at inference the layers of a stack are
+    interleaved at launch level (layer l step t next to layer l+1 step t-1, one stream per layer, one event per launch).
+    Same kernels, same operands: the outputs are bit-identical to the layer-after-layer order, on the bare stack op
+    (with initial states) and through the config-5 model."""
+    fov = _cuda()
+    from longterm360fov_b200 import ops
+    B, H, W = shape
+    rng = np.random.default_rng(B + H)
+    dev = torch.device("cuda")
+    ops.set_math(mode)
+    w = kn.init_convlstm_seq2seq(seed=3, in_ch=30, filters=(32, 16, 8), kernel_size=5, head=(24, 40, 30), head_kind="conv2d")
+    wl = [tuple(torch.tensor(w["enc_convlstm%d/%s" % (l, n)], device=dev) for n in ("kernel", "recurrent_kernel", "bias"))
+          for l in range(3)]
+    x = torch.tensor(rng.uniform(0, 1, (B, 7, H, W, 30)).astype(np.float32), device=dev)
+    st0 = [(torch.tensor(rng.normal(size=(B, H, W, f)).astype(np.float32) * 0.3, device=dev),
+            torch.tensor(rng.normal(size=(B, H, W, f)).astype(np.float32) * 0.3, device=dev)) for f in (32, 16, 8)]
+    res = []
+    for wave in (False, True):
+        ops.set_layer_wavefront(wave)
+        with torch.no_grad():
+            cat, states = ops.convlstm_stack(x, wl, st0, None, training=False)
+            cat2, states2 = ops.convlstm_stack(x, wl, None, None, training=False, pack_cache={})
+        res.append([cat, cat2] + [t for s_ in states + states2 for t in s_])
+    ops.set_layer_wavefront(True)
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+    if (H, W) == (36, 18):
+        enc = rng.uniform(0, 1, (B, 10, H, W, 30)).astype(np.float32)
+        dec = rng.uniform(0, 1, (B, 1, H, W, 30)).astype(np.float32)
+        outs = []
+        for wave in (False, True):
+            ops.set_layer_wavefront(wave)
+            m = fov.convlstm_seq2seq(weights=w, head=(24, 40, None))
+            m.set_compute(mode)
+            outs.append(m.predict_on_batch([enc, dec]))
+        ops.set_layer_wavefront(True)
+        assert np.array_equal(outs[0], outs[1])
+
+
 # ------------------------------------------------------------------ ConvLSTM weight gradient inside the persistent BPTT
 
 @pytest.mark.parametrize("B,T", [(1, 1), (4, 20), (131, 7), (7, 2)])
