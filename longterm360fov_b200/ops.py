@@ -8,6 +8,7 @@ Functions return ``None`` for weight inputs.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -71,7 +72,7 @@ _WG = {"on": False, "streams": {}, "used": False, "keep": []}
 
 
 def set_wgrad_side_stream(on):
-    _WG["on"] = bool(on)
+    _WG["on"] = bool(on) and os.environ.get("FOV_NO_WGRAD_STREAM", "0") in ("", "0")     # FOV_NO_WGRAD_STREAM=1: never
     if not on and (_WG["used"] or _WG["keep"]):      # a pass that ended without its join (an exception on the way)
         join_wgrad_stream()
 
@@ -134,11 +135,11 @@ def join_wgrad_stream():
 # streams instead and run CONCURRENTLY: layer l publishes a flag per (image group, timestep) once h_t is in global memory,
 # layer l+1 waits for it before it reads x_t (fov_convlstm_io.wave_set / wave_wait); the BPTT kernels do the same in the
 # other direction through the fused input gradient (fov_convlstm_grads.wave_set / wave_wait).
-_WAVE = {"on": True, "streams": {}}
+_WAVE = {"on": os.environ.get("FOV_NO_WAVEFRONT", "0") in ("", "0"), "streams": {}}      # FOV_NO_WAVEFRONT=1: never
 
 
 def set_layer_wavefront(on):
-    _WAVE["on"] = bool(on)
+    _WAVE["on"] = bool(on) and os.environ.get("FOV_NO_WAVEFRONT", "0") in ("", "0")
 
 
 def _wave_streams(n):
