@@ -22,7 +22,15 @@ import weakref
 import numpy as np
 import torch
 
-from . import _lib, ops, parallel
+from . import _lib, h5lite, ops, parallel
+
+_H5_EXT = (".h5", ".hdf5")
+
+
+def _is_hdf5(path):
+    with open(path, "rb") as fh:
+        return fh.read(8) == h5lite.SIG
+
 
 def _init_weights(kind, **kw):
     """Keras-default initialisers (glorot_uniform / orthogonal / forget-bias 1).
@@ -227,19 +235,68 @@ class Model:
     def get_weights_dict(self):
         return {k: v for k, v in zip(self.weight_order, self.get_weights())}
 
+    def _keras_layers(self):
+        """[(layer, [(layer/weight:0, array), ...]), ...]: ``weight_order`` grouped the way Keras' saving.py stores a
+        model (one group per layer, weights in ``layer.weights`` order, TensorFlow-style ``:0`` names)."""
+        layers = collections.OrderedDict()
+        for k, a in self.get_weights_dict().items():
+            layers.setdefault(k.split("/", 1)[0], []).append((k + ":0", a))
+        return list(layers.items())
+
     def save_weights(self, path):
-        """Keras-layout weights as .npz keyed by layer/weight name (h5py is unavailable)."""
+        """Keras-layout weights.  ``*.h5`` / ``*.hdf5``: an HDF5 file in Keras 2.2's ``save_weights`` layout
+        (``layer_names`` / ``weight_names`` attributes, one group per layer; the names the reference's checkpoints
+        use, mycode/FoV_seq2seq.py:108) written by ``h5lite``; anything else: ``.npz`` keyed by layer / weight name."""
+        if path.endswith(_H5_EXT):
+            h5lite.write_keras_weights(path, self._keras_layers())
+            return
         if not path.endswith(".npz"):
             path = path + ".npz"
         np.savez(path, **{k.replace("/", "__"): v for k, v in self.get_weights_dict().items()})
 
     save = save_weights
 
-    def load_weights(self, path):
+    def load_weights(self, path, layer_map=None):
+        """``.npz`` written by ``save_weights``, or an HDF5 checkpoint (``model.save_weights`` / ``model.save`` /
+        ``ModelCheckpoint`` of Keras 2.2, or this class's own ``.h5``).  HDF5 layers are matched BY NAME when the file
+        holds this model's layer names (or ``layer_map = {file layer name: this model's layer name}`` names them);
+        otherwise - a checkpoint of the reference, whose layers carry Keras' auto names (``lstm_1``, ``dense_2``) - by
+        ORDER, as Keras' own ``load_weights`` does: the file's layers that hold weights against this model's layers
+        in ``weight_order``, every shape checked; a mismatch raises with both lists."""
+        if path.endswith(_H5_EXT) or (os.path.exists(path) and _is_hdf5(path)):
+            self.set_weights(self._match_keras_layers(h5lite.read_keras_weights(path), layer_map))
+            return
         if not path.endswith(".npz") and not os.path.exists(path):
             path = path + ".npz"
         z = np.load(path)
         self.set_weights([z[k.replace("/", "__")] for k in self.weight_order])
+
+    def _match_keras_layers(self, file_layers, layer_map=None):
+        mine = self._keras_layers()
+        file_layers = [(n, ws) for n, ws in file_layers if ws]
+        if layer_map:
+            file_layers = [(layer_map.get(n, n), ws) for n, ws in file_layers]
+        by_name = dict(file_layers)
+        if all(l in by_name for l, _ in mine):
+            pairs = [(l, ws, by_name[l]) for l, ws in mine]
+        elif len(file_layers) == len(mine):
+            pairs = [(l, ws, fws) for (l, ws), (_, fws) in zip(mine, file_layers)]
+        else:
+            raise ValueError("checkpoint holds %d layers with weights %s, the model %d %s; pass layer_map" % (
+                len(file_layers), [n for n, _ in file_layers], len(mine), [l for l, _ in mine]))
+        out = {}
+        for l, ws, fws in pairs:
+            if len(ws) != len(fws):
+                raise ValueError("layer %s: %d weights in the model, %d in the checkpoint" % (l, len(ws), len(fws)))
+            short = {n.split("/")[-1].split(":")[0]: a for n, a in fws}
+            for i, (k, a) in enumerate(ws):
+                w = k.split("/", 1)[1].split(":")[0]
+                src = short[w] if w in short and len(short) == len(fws) else fws[i][1]
+                if tuple(np.shape(src)) != tuple(np.shape(a)):
+                    raise ValueError("layer %s weight %s: shape %s in the checkpoint, %s in the model" % (
+                        l, w, np.shape(src), np.shape(a)))
+                out[k.split(":")[0]] = np.asarray(src, np.float32)
+        return [out[k] for k in self.weight_order]
 
     def count_params(self):
         return sum(int(np.prod(s)) for _, s in self._offsets.values())

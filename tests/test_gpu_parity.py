@@ -3,6 +3,8 @@ compared with the CPU oracle on the same seeded inputs.  Forward bar is the nort
 1e-4 max-abs, for the fp32 CUDA-core kernels ("fp32") and for the tcgen05 kernels with two
 bf16 terms per operand ("bf16x2", the default); the single-term "bf16" tensor-core mode is
 held to the stated bf16 tolerance BF16_ATOL."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -860,6 +862,40 @@ def test_fit_predict_surface_m1():
                          fov.EarlyStopping(monitor="val_loss", patience=10)])
     assert len(h.history["loss"]) == 6 and h.history["loss"][-1] < h.history["loss"][0]
     assert m.predict([enc, dec_in], batch_size=100).shape == (N, 10, 6)
+
+
+def test_h5_checkpoints_round_trip(tmp_path):
+    """ModelCheckpoint('...{epoch:02d}-{val_loss:.4f}.h5') as the reference writes it (mycode/FoV_seq2seq.py:108),
+    then load_weights of that HDF5 file into fresh models (by name; the stacked model's padded 32-unit LSTMs go
+    through their Keras shapes): predictions identical."""
+    fov = _cuda()
+    from longterm360fov_b200 import h5lite
+    rng = np.random.default_rng(52)
+    N = 64
+    enc = rng.uniform(-1, 1, (N, 10, 90)).astype(np.float32)
+    fut = np.tanh(enc[:, :, :6] * 0.5).astype(np.float32)
+    dec_in = np.concatenate([enc[:, -1:, :6], fut[:, :-1]], axis=1)
+    m = fov.fov_seq2seq(seed=3).compile(optimizer="Adam", loss="mean_squared_error")
+    tag = str(tmp_path / "fov_s2s_withTfor_epoch{epoch:02d}-{val_loss:.4f}.h5")
+    m.fit([enc, dec_in], fut, batch_size=32, epochs=2, validation_split=0.25,
+          callbacks=[fov.ModelCheckpoint(tag, monitor="val_loss", save_best_only=False)])
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 2 and files[1].startswith("fov_s2s_withTfor_epoch02-") and files[1].endswith(".h5")
+    layers = h5lite.read_keras_weights(str(tmp_path / files[1]))
+    assert [n for n, _ in layers] == ["encoder", "decoder", "decoder_dense"]
+    assert layers[0][1][0][0] == "encoder/kernel:0" and layers[0][1][0][1].shape == (90, 256)
+    m2 = fov.fov_seq2seq(seed=9)
+    assert np.abs(m2.predict([enc, dec_in]) - m.predict([enc, dec_in])).max() > 1e-3
+    m2.load_weights(str(tmp_path / files[1]))
+    np.testing.assert_array_equal(m2.predict([enc, dec_in]), m.predict([enc, dec_in]))
+    s = fov.stacked_fov_seq2seq(n_layers=3, seed=4)
+    p = str(tmp_path / "fov_s2s_tanh_3layers.h5")
+    s.save(p)
+    assert dict(h5lite.read_keras_weights(p))["encoder1"][0][1].shape == (32, 128)
+    s2 = fov.stacked_fov_seq2seq(n_layers=3, seed=5)
+    s2.load_weights(p)
+    x = [enc[:, :, :6], dec_in]
+    np.testing.assert_array_equal(s2.predict(x), s.predict(x))
 
 
 def test_fit_input_pipeline_matches_train_on_batch():
