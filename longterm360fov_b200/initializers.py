@@ -127,7 +127,16 @@ def init_given_others_seq2seq(seed=1, num_user=34, latent_dim=32, num_encoder_to
     for l in range(2):
         _lstm(rng, num_decoder_tokens if l == 0 else latent_dim, latent_dim, "decoder%d" % l, w)
     oth = (num_user - 1) * 6
-    if variant == "others_mlp":
+    if variant == "others_lstm":
+        for l in range(2):
+            for d in ("fwd", "bwd"):
+                _lstm(rng, oth if l == 0 else 2 * latent_dim, latent_dim, "others_bilstm%d_%s" % (l, d), w)
+        _dense(rng, 3 * latent_dim, num_decoder_tokens, "decoder_dense", w)
+    elif variant == "conv_mixing":
+        _dense(rng, latent_dim, num_decoder_tokens, "decoder_dense", w)
+        for l, (ci, co) in enumerate([(num_user, 8), (8, 8), (8, 1)]):
+            _conv(rng, (1, 3, ci, co), "mixing_conv%d" % l, w)
+    elif variant == "others_mlp":
         _dense(rng, oth, 256, "others_dense1", w)
         _dense(rng, 256, latent_dim, "others_dense2", w)
         _dense(rng, 2 * latent_dim, num_decoder_tokens, "decoder_dense", w)

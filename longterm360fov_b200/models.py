@@ -881,17 +881,22 @@ class GivenOthersSeq2Seq(Model):
 
     def __init__(self, weights, variant="mlp_mixing", teacher_forcing=False, recurrent_activation="hard_sigmoid",
                  device=None):
-        if variant not in ("mlp_mixing", "others_mlp", "target_only"):
-            raise ValueError("variant must be 'mlp_mixing', 'others_mlp' or 'target_only'")
+        if variant not in ("mlp_mixing", "others_mlp", "others_lstm", "conv_mixing", "target_only"):
+            raise ValueError("variant must be 'mlp_mixing', 'conv_mixing', 'others_mlp', 'others_lstm' or 'target_only'")
         self.variant = variant
         self.teacher_forcing = bool(teacher_forcing)
         order = ["%s%d/%s" % (s, l, n) for s in ("encoder", "decoder") for l in range(2)
                  for n in ("kernel", "recurrent_kernel", "bias")]
         if variant == "others_mlp":
             order += ["others_dense1/kernel", "others_dense1/bias", "others_dense2/kernel", "others_dense2/bias"]
+        if variant == "others_lstm":
+            order += ["others_bilstm%d_%s/%s" % (l, d, n) for l in range(2) for d in ("fwd", "bwd")
+                      for n in ("kernel", "recurrent_kernel", "bias")]
         order += ["decoder_dense/kernel", "decoder_dense/bias"]
         if variant == "mlp_mixing":
             order += ["mixing/kernel", "mixing/bias"]
+        if variant == "conv_mixing":
+            order += ["mixing_conv%d/%s" % (l, n) for l in range(3) for n in ("kernel", "bias")]
         self.weight_order = order
         super().__init__(weights, device)
         self.rec_act = recurrent_activation
@@ -910,12 +915,45 @@ class GivenOthersSeq2Seq(Model):
         return ops.convlstm_stack(x.reshape(B, T, 1, 1, x.shape[-1]), self._cells(side, self.params), states,
                                   self._cells(side, self.grads) if training else None, (1, 1), self.rec_act, training)
 
+    def _one_cell(self, name, x, state, training):
+        """One fc-LSTM over (B,T,C) as a 1 x 1 ConvLSTM cell -> ((B,T,H), (hT, cT))."""
+        cell = lambda src: [tuple(t.view(1, 1, *t.shape) if t.dim() == 2 else t
+                                  for t in (src[name + "/" + n] for n in ("kernel", "recurrent_kernel", "bias")))]
+        B, T = x.shape[0], x.shape[1]
+        seq, st = ops.convlstm_stack(x.reshape(B, T, 1, 1, x.shape[-1]), cell(self.params),
+                                     None if state is None else [state], cell(self.grads) if training else None,
+                                     (1, 1), self.rec_act, training)
+        return seq[:, :, 0, 0, :], st[0]
+
+    def _others_bilstm(self, oth, training):
+        """Two stacked Bidirectional(LSTM, merge_mode='concat') over the others' future
+        (mycode/given_others_gt_mean_var_seq2seq.py:151-158): the backward LSTM reads the time-reversed sequence and its
+        output is reversed back before the concat; the second pair starts from the first pair's final states (the
+        script hands Keras the [seq, h, c, h, c] list of the first layer, which Bidirectional.__call__ splits into
+        input + initial_state)."""
+        y, st = oth.reshape(oth.shape[0], oth.shape[1], -1), {"fwd": None, "bwd": None}
+        for l in range(2):
+            f, sf = self._one_cell("others_bilstm%d_fwd" % l, y, st["fwd"], training)
+            b, sb = self._one_cell("others_bilstm%d_bwd" % l, torch.flip(y, dims=[1]).contiguous(), st["bwd"], training)
+            y, st = torch.cat([f, torch.flip(b, dims=[1])], dim=-1), {"fwd": sf, "bwd": sb}
+        return y
+
     def _head(self, s2, oth_t, training):
         p = self.params
         d = lambda name, x, act: ops.dense(x, p[name + "/kernel"], p[name + "/bias"], act,
                                            self._sinks(name + "/kernel", name + "/bias"), training)
         if self.variant == "target_only":
             return d("decoder_dense", s2, "tanh")
+        if self.variant == "others_lstm":                             # oth_t: the bi-LSTM output of this step (B,2H)
+            return d("decoder_dense", torch.cat([oth_t, s2], dim=-1), "tanh")
+        if self.variant == "conv_mixing":                             # (:190-199,289-295) image (1, 6, num_user)
+            pred = d("decoder_dense", s2, "tanh")
+            img = torch.cat([oth_t, pred.unsqueeze(1)], dim=1).permute(0, 2, 1).unsqueeze(1).contiguous()
+            for l in range(3):
+                n = "mixing_conv%d" % l
+                img = ops.conv2d(img, p[n + "/kernel"], p[n + "/bias"], "relu", (1, 1),
+                                 self._sinks(n + "/kernel", n + "/bias"), training)
+            return img[:, 0, :, 0]
         flat = oth_t.reshape(oth_t.shape[0], -1)
         if self.variant == "others_mlp":
             o = d("others_dense2", d("others_dense1", flat, "relu"), "relu")
@@ -933,12 +971,17 @@ class GivenOthersSeq2Seq(Model):
             T = oth.shape[1]
         B, H = enc.shape[0], self.params["encoder0/recurrent_kernel"].shape[0]
         _, states = self._stack("encoder", enc, None, training)
+        if self.variant == "others_lstm":
+            oth = self._others_bilstm(oth, training)
         outs = []
         if self.teacher_forcing:
             cat, _ = self._stack("decoder", dec, states, training)
             d2 = cat[:, :, 0, 0, H:]                                  # hidden sequence of the second decoder layer
             for t in range(T):
-                outs.append(self._head(d2[:, t].contiguous(), None if oth is None else oth[:, t], training))
+                # the script's others_lstm branch reads get_dim1_layer(decoder2_outputs): the FIRST decoder step for
+                # every output step when teacher forced (:238); kept as written
+                td = 0 if self.variant == "others_lstm" else t
+                outs.append(self._head(d2[:, td].contiguous(), None if oth is None else oth[:, t], training))
         else:
             x = dec[:, 0:1]
             for t in range(T):
@@ -954,7 +997,9 @@ def given_others_gt_mean_var_seq2seq(latent_dim=32, num_user=34, num_encoder_tok
                                      recurrent_activation="hard_sigmoid", weights=None, seed=1, device=None):
     """Builder for mycode/given_others_gt_mean_var_seq2seq.py:97-308 (cfg.input_mean_var, cfg.predict_mean_var):
     inputs ``[encoder_inputs (B,10,6), others_fut_inputs (B,10,num_user-1,6), decoder_inputs (B,1,6)]`` (``(B,10,6)``
-    decoder inputs when teacher forced; no others input with ``target_user_only``) -> ``(B,10,6)``."""
+    decoder inputs when teacher forced; no others input with ``target_user_only``) -> ``(B,10,6)``.  ``variant``:
+    'mlp_mixing' (the script's flags), 'conv_mixing' (:190-199), 'others_mlp' (:146-149), 'others_lstm' (two stacked
+    Bidirectional LSTMs over the others' future, :151-158), 'target_only'."""
     if target_user_only:
         variant = "target_only"
     if weights is None:

@@ -652,7 +652,10 @@ def init_given_others_seq2seq(seed=1, num_user=34, latent_dim=32, num_encoder_to
     (32) units, Dense(6, tanh), and per variant: 'mlp_mixing' (the script's default) a Dense(6, tanh) over
     [others' mean/var of the step (num_user-1, 6) ; decoder prediction (6)]; 'others_mlp' Dense(256, relu) ->
     Dense(latent_dim, relu) on the others slice, whose output is concatenated with the decoder state before
-    decoder_dense; 'target_only' nothing else."""
+    decoder_dense; 'others_lstm' (:151-158, the branch the script's own flags select under model_others) two stacked
+    Bidirectional(LSTM(latent_dim), merge_mode='concat') over the others' future, decoder_dense on
+    [bi-LSTM output (2*latent_dim) ; decoder state]; 'conv_mixing' (:190-199) Conv2D(8,(1,3)) -> Conv2D(8,(1,3)) ->
+    Conv2D(1,(1,3)), all relu, over the (1, 6, num_user) image of [others ; prediction]; 'target_only' nothing else."""
     rng = np.random.default_rng(seed)
     w = {}
     for l in range(2):
@@ -660,7 +663,16 @@ def init_given_others_seq2seq(seed=1, num_user=34, latent_dim=32, num_encoder_to
     for l in range(2):
         init_lstm(rng, num_decoder_tokens if l == 0 else latent_dim, latent_dim, "decoder%d" % l, w)
     oth = (num_user - 1) * 6
-    if variant == "others_mlp":
+    if variant == "others_lstm":
+        for l in range(2):
+            for d in ("fwd", "bwd"):
+                init_lstm(rng, oth if l == 0 else 2 * latent_dim, latent_dim, "others_bilstm%d_%s" % (l, d), w)
+        init_dense(rng, 3 * latent_dim, num_decoder_tokens, "decoder_dense", w)
+    elif variant == "conv_mixing":
+        init_dense(rng, latent_dim, num_decoder_tokens, "decoder_dense", w)
+        for l, (ci, co) in enumerate([(num_user, 8), (8, 8), (8, 1)]):
+            init_conv(rng, (1, 3, ci, co), "mixing_conv%d" % l, w)
+    elif variant == "others_mlp":
         init_dense(rng, oth, 256, "others_dense1", w)
         init_dense(rng, 256, latent_dim, "others_dense2", w)
         init_dense(rng, 2 * latent_dim, num_decoder_tokens, "decoder_dense", w)
@@ -676,12 +688,25 @@ def given_others_seq2seq_forward(w, enc_in, oth_in, dec_in, variant="mlp_mixing"
     """mycode/given_others_gt_mean_var_seq2seq.py:97-308 with cfg.input_mean_var / predict_mean_var: 2-layer fc-LSTM
     encoder-decoder; every step's output is re-fed as the next decoder input unless teacher_forcing
     (cfg.teacher_forcing, default False).  enc_in (B,10,6), oth_in (B,T,num_user-1,6) others' ground-truth mean/var
-    of the future seconds, dec_in (B,1,6) (or (B,T,6) teacher-forced) -> (B,T,6)."""
+    of the future seconds, dec_in (B,1,6) (or (B,T,6) teacher-forced) -> (B,T,6).
+
+    'others_lstm': Keras' Bidirectional runs the backward LSTM on the time-reversed input and reverses its output
+    sequence back before the concat; called with return_state=True it returns [seq, fwd_h, fwd_c, bwd_h, bwd_c], and
+    the script passes that LIST to the second Bidirectional (:154-155), which Keras reads as input + initial_state:
+    the second pair starts from the first pair's final states.  In the teacher-forced graph the script takes
+    get_dim1_layer(decoder2_outputs) = the decoder's FIRST step for every output step (:238); restated as written."""
     ra = recurrent_activation
     B, T = oth_in.shape[0], oth_in.shape[1]
     L = lambda n: (w[n + "/kernel"], w[n + "/recurrent_kernel"], w[n + "/bias"])
     e1, h1, c1 = lstm(enc_in, *L("encoder0"), recurrent_activation=ra)
     _, h2, c2 = lstm(e1, *L("encoder1"), recurrent_activation=ra)
+    if variant == "others_lstm":
+        y, st = oth_in.reshape(B, T, -1), {"fwd": (None, None), "bwd": (None, None)}
+        for l in range(2):
+            f, fh, fc = lstm(y, *L("others_bilstm%d_fwd" % l), *st["fwd"], recurrent_activation=ra)
+            b, bh, bc = lstm(y[:, ::-1], *L("others_bilstm%d_bwd" % l), *st["bwd"], recurrent_activation=ra)
+            y, st = np.concatenate([f, b[:, ::-1]], axis=-1), {"fwd": (fh, fc), "bwd": (bh, bc)}
+        oth_seq = y
     if teacher_forcing:
         d1, _, _ = lstm(dec_in, *L("decoder0"), h1, c1, recurrent_activation=ra)
         d2, _, _ = lstm(d1, *L("decoder1"), h2, c2, recurrent_activation=ra)
@@ -697,6 +722,16 @@ def given_others_seq2seq_forward(w, enc_in, oth_in, dec_in, variant="mlp_mixing"
         flat = oth_in[:, t].reshape(B, -1)
         if variant == "target_only":
             y = dense(s2, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+        elif variant == "others_lstm":
+            s = d2[:, 0] if teacher_forcing else s2
+            y = dense(np.concatenate([oth_seq[:, t], s], axis=-1), w["decoder_dense/kernel"], w["decoder_dense/bias"],
+                      "tanh")
+        elif variant == "conv_mixing":
+            pred = dense(s2, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+            img = np.concatenate([oth_in[:, t], pred[:, None]], axis=1).transpose(0, 2, 1)[:, None]   # (B,1,6,num_user)
+            for l in range(3):
+                img = conv2d(img, w["mixing_conv%d/kernel" % l], w["mixing_conv%d/bias" % l], "relu")
+            y = img[:, 0, :, 0]
         elif variant == "others_mlp":
             o = dense(flat, w["others_dense1/kernel"], w["others_dense1/bias"], "relu")
             o = dense(o, w["others_dense2/kernel"], w["others_dense2/bias"], "relu")

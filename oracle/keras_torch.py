@@ -199,6 +199,13 @@ def given_others_seq2seq_forward(w, enc_in, oth_in, dec_in, variant="mlp_mixing"
     L = lambda n: (w[n + "/kernel"], w[n + "/recurrent_kernel"], w[n + "/bias"])
     e1, h1, c1 = lstm(enc_in, *L("encoder0"), ra=ra)
     _, h2, c2 = lstm(e1, *L("encoder1"), ra=ra)
+    if variant == "others_lstm":
+        y, st = oth_in.reshape(B, T, -1), {"fwd": (None, None), "bwd": (None, None)}
+        for l in range(2):
+            f, fh, fc = lstm(y, *L("others_bilstm%d_fwd" % l), *st["fwd"], ra=ra)
+            b, bh, bc = lstm(torch.flip(y, dims=[1]), *L("others_bilstm%d_bwd" % l), *st["bwd"], ra=ra)
+            y, st = torch.cat([f, torch.flip(b, dims=[1])], dim=-1), {"fwd": (fh, fc), "bwd": (bh, bc)}
+        oth_seq = y
     if teacher_forcing:
         d1, _, _ = lstm(dec_in, *L("decoder0"), h1, c1, ra=ra)
         d2, _, _ = lstm(d1, *L("decoder1"), h2, c2, ra=ra)
@@ -214,6 +221,15 @@ def given_others_seq2seq_forward(w, enc_in, oth_in, dec_in, variant="mlp_mixing"
         flat = oth_in[:, t].reshape(B, -1)
         if variant == "target_only":
             y = dense(s2, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+        elif variant == "others_lstm":
+            s = d2[:, 0] if teacher_forcing else s2
+            y = dense(torch.cat([oth_seq[:, t], s], dim=-1), w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+        elif variant == "conv_mixing":
+            pred = dense(s2, w["decoder_dense/kernel"], w["decoder_dense/bias"], "tanh")
+            img = torch.cat([oth_in[:, t], pred[:, None]], dim=1).permute(0, 2, 1)[:, None]
+            for l in range(3):
+                img = conv2d(img, w["mixing_conv%d/kernel" % l], w["mixing_conv%d/bias" % l], "relu")
+            y = img[:, 0, :, 0]
         elif variant == "others_mlp":
             o = dense(flat, w["others_dense1/kernel"], w["others_dense1/bias"], "relu")
             o = dense(o, w["others_dense2/kernel"], w["others_dense2/bias"], "relu")

@@ -636,7 +636,8 @@ def test_stacked_fov_seq2seq(n_layers, B, tc, lstm_switches):
 # ------------------------------------------------------------------ sibling model: 2-layer fc-LSTM given others' mean / var
 
 @pytest.mark.parametrize("variant,tf", [("mlp_mixing", False), ("mlp_mixing", True), ("others_mlp", False),
-                                        ("target_only", False), ("others_mlp", True)])
+                                        ("target_only", False), ("others_mlp", True), ("others_lstm", False),
+                                        ("others_lstm", True), ("conv_mixing", False)])
 @pytest.mark.parametrize("mode", ["fp32", "bf16x2"])
 def test_given_others_mean_var_seq2seq(variant, tf, mode):
     """mycode/given_others_gt_mean_var_seq2seq.py:97-308: two-layer 32-unit fc-LSTM encoder-decoder whose every output

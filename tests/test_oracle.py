@@ -328,7 +328,7 @@ def test_given_others_and_convlstm_target_restatements_agree():
     (target_only ignores the others; the re-fed decoder really consumes its own output)."""
     rng = np.random.default_rng(3)
     enc = rng.uniform(-1, 1, (3, 10, 6)); oth = rng.uniform(-1, 1, (3, 10, 33, 6))
-    for variant in ("mlp_mixing", "others_mlp", "target_only"):
+    for variant in ("mlp_mixing", "others_mlp", "target_only", "others_lstm", "conv_mixing"):
         w = kn.init_given_others_seq2seq(seed=4, variant=variant)
         w64 = {k: v.astype(np.float64) for k, v in w.items()}
         for tf in (False, True):
@@ -338,6 +338,8 @@ def test_given_others_and_convlstm_target_restatements_agree():
                                                 variant, tf).numpy()
             np.testing.assert_allclose(a, b, atol=1e-10)
             assert a.shape == (3, 10, 6) and np.abs(a).max() <= 1.0          # tanh outputs
+            if variant == "conv_mixing":
+                assert a.min() >= 0.0                                        # the last mixing Conv2D is relu (:196-199)
             other = kn.given_others_seq2seq_forward(w64, enc, oth * 0.5, dec, variant, tf)
             assert np.array_equal(a, other) == (variant == "target_only")
         dec2 = dec[:, :1] + 0.1
@@ -351,3 +353,50 @@ def test_given_others_and_convlstm_target_restatements_agree():
     for u, v in zip(a, b):
         np.testing.assert_allclose(u, v.numpy(), atol=1e-10)
     assert [u.shape for u in a] == [(2, 10, 1, 30, 3), (2, 20, 1, 30, 12), (2, 10, 1, 30, 3)]
+
+
+def test_given_others_bilstm_structure():
+    """others_lstm variant (given_others_gt_mean_var_seq2seq.py:151-158,236-241): the stacked Bidirectional LSTMs see
+    the whole future of the others (step 0's output depends on the others' LAST second through the backward LSTM);
+    the second pair starts from the first pair's final states (zeroing layer 0's recurrent kernels changes those
+    states and so the result, even with layer 1's input sequence held fixed is not needed: checked directly against a
+    hand-rolled Keras-semantics loop); the teacher-forced graph reads the decoder's first step throughout."""
+    rng = np.random.default_rng(9)
+    B, T, U, H = 2, 10, 5, 32
+    w = {k: v.astype(np.float64) for k, v in kn.init_given_others_seq2seq(seed=2, num_user=U + 1, variant="others_lstm").items()}
+    assert w["others_bilstm0_fwd/kernel"].shape == (U * 6, 4 * H) and w["others_bilstm1_bwd/kernel"].shape == (2 * H, 4 * H)
+    assert w["decoder_dense/kernel"].shape == (3 * H, 6)
+    enc = rng.uniform(-1, 1, (B, 10, 6)); oth = rng.uniform(-1, 1, (B, T, U, 6)); dec = rng.uniform(-1, 1, (B, 1, 6))
+    a = kn.given_others_seq2seq_forward(w, enc, oth, dec, "others_lstm", False)
+    oth2 = oth.copy(); oth2[:, -1] += 0.3
+    b = kn.given_others_seq2seq_forward(w, enc, oth2, dec, "others_lstm", False)
+    assert np.abs(a[:, 0] - b[:, 0]).max() > 1e-6
+    # hand-rolled: per-step loops in Keras order, explicit reversal, explicit state hand-over
+    L = lambda n: (w[n + "/kernel"], w[n + "/recurrent_kernel"], w[n + "/bias"])
+    x = oth.reshape(B, T, -1)
+    def run(xs, name, h, c):
+        out = []
+        for t in range(xs.shape[1]):
+            h, c = kn.lstm_step(xs[:, t], h, c, *L(name))
+            out.append(h)
+        return np.stack(out, 1), h, c
+    z = np.zeros((B, H))
+    f0, fh, fc = run(x, "others_bilstm0_fwd", z, z)
+    b0, bh, bc = run(x[:, ::-1], "others_bilstm0_bwd", z, z)
+    y0 = np.concatenate([f0, b0[:, ::-1]], -1)
+    f1, _, _ = run(y0, "others_bilstm1_fwd", fh, fc)
+    b1, _, _ = run(y0[:, ::-1], "others_bilstm1_bwd", bh, bc)
+    y1 = np.concatenate([f1, b1[:, ::-1]], -1)
+    e1, h1, c1 = kn.lstm(enc, *L("encoder0")); _, h2, c2 = kn.lstm(e1, *L("encoder1"))
+    xin, outs = dec[:, 0], []
+    for t in range(T):
+        h1, c1 = kn.lstm_step(xin, h1, c1, *L("decoder0"))
+        h2, c2 = kn.lstm_step(h1, h2, c2, *L("decoder1"))
+        xin = np.tanh(np.concatenate([y1[:, t], h2], -1) @ w["decoder_dense/kernel"] + w["decoder_dense/bias"])
+        outs.append(xin)
+    np.testing.assert_allclose(a, np.stack(outs, 1), atol=1e-12)
+    # teacher forced: only the decoder's first step reaches the outputs
+    dec_tf = rng.uniform(-1, 1, (B, T, 6)); dec_tf2 = dec_tf.copy(); dec_tf2[:, 1:] += 0.5
+    c = kn.given_others_seq2seq_forward(w, enc, oth, dec_tf, "others_lstm", True)
+    d = kn.given_others_seq2seq_forward(w, enc, oth, dec_tf2, "others_lstm", True)
+    assert np.array_equal(c, d)
