@@ -560,7 +560,7 @@ def _dtype_msg(dt):
     if dt.kind == "b":
         return struct.pack("<BBBBIHH", 0x10, 0, 0, 0, 1, 0, 8)
     if dt.kind == "S":
-        return struct.pack("<BBBBI", 0x13, 0x00, 0, 0, max(dt.itemsize, 1))     # null-terminated ASCII, as h5py's 'S'
+        return struct.pack("<BBBBI", 0x13, 0x01, 0, 0, max(dt.itemsize, 1))     # null-padded ASCII, as h5py's 'S'
     raise H5Error("cannot store dtype %s" % dt)
 
 
