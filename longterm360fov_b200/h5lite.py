@@ -246,7 +246,7 @@ class Dataset(_Object):
         self.dtype = self._type.dtype if not self._type.vlen_str else np.dtype(object)
 
     def __array__(self, dtype=None, copy=None):
-        a = self[()]
+        a = np.asarray(self._read())                                 # a scalar dataset decodes to a NumPy scalar
         return a.astype(dtype) if dtype is not None else a
 
     def __getitem__(self, key):
@@ -910,16 +910,57 @@ def read_keras_weights(path):
         return out
 
 
+def _put_keras_layers(g, layers):
+    g.attrs["layer_names"] = np.array([l.encode("utf8") for l, _ in layers]) if layers else np.zeros((0,), "S1")
+    for lname, ws in layers:
+        lg = g.require_group(lname)
+        lg.attrs["weight_names"] = (np.array([n.encode("utf8") for n, _ in ws]) if ws else np.zeros((0,), "S1"))
+        for wn, arr in ws:
+            lg.create_dataset(wn, data=np.asarray(arr))
+
+
 def write_keras_weights(path, layers, keras_version="2.2.4", backend="tensorflow"):
     """``layers``: [(layer_name, [(weight_name, array), ...]), ...] -> a file Keras' ``load_weights`` layout describes:
     root attributes ``layer_names`` / ``backend`` / ``keras_version``, one group per layer with ``weight_names`` and
     one dataset per weight at ``/<layer>/<weight_name>`` (weight names carry their own ``layer/`` prefix)."""
     with Writer(path) as w:
-        w.attrs["layer_names"] = np.array([l.encode("utf8") for l, _ in layers]) if layers else np.zeros((0,), "S1")
+        _put_keras_layers(w, layers)
         w.attrs["backend"] = backend
         w.attrs["keras_version"] = keras_version
-        for lname, ws in layers:
-            g = w.require_group(lname)
-            g.attrs["weight_names"] = (np.array([n.encode("utf8") for n, _ in ws]) if ws else np.zeros((0,), "S1"))
-            for wn, arr in ws:
-                g.create_dataset(wn, data=np.asarray(arr))
+
+
+def write_keras_model(path, layers, optimizer_weights=None, training_config=None, model_config=None,
+                      keras_version="2.2.4", backend="tensorflow"):
+    """Keras 2.2 ``model.save`` layout (``saving._serialize_model``): the layers under ``/model_weights``, the
+    optimizer's ``[(name, array), ...]`` under ``/optimizer_weights`` (attribute ``weight_names``), ``model_config`` /
+    ``training_config`` JSON strings as root attributes."""
+    import json
+    with Writer(path) as w:
+        w.attrs["keras_version"] = keras_version
+        w.attrs["backend"] = backend
+        w.attrs["model_config"] = json.dumps(model_config or {})
+        if training_config is not None:
+            w.attrs["training_config"] = json.dumps(training_config)
+        mg = w.create_group("model_weights")
+        _put_keras_layers(mg, layers)
+        mg.attrs["backend"] = backend
+        mg.attrs["keras_version"] = keras_version
+        if optimizer_weights:
+            og = w.create_group("optimizer_weights")
+            og.attrs["weight_names"] = np.array([n.encode("utf8") for n, _ in optimizer_weights])
+            for n, a in optimizer_weights:
+                og.create_dataset(n, data=np.asarray(a))
+
+
+def read_keras_optimizer(path):
+    """(training_config dict or None, [(name, array), ...]) of a ``model.save`` file; ([], None) parts when absent."""
+    import json
+    with File(path) as f:
+        cfg = f.attrs.get("training_config")
+        if cfg is not None:
+            cfg = json.loads(cfg.decode("utf8") if isinstance(cfg, bytes) else cfg)
+        og = f.get("optimizer_weights")
+        ws = []
+        if og is not None:
+            ws = [(n, np.array(og[n])) for n in _attr_list(og.attrs, "weight_names")]
+        return cfg, ws

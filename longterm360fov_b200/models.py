@@ -56,6 +56,7 @@ class Adam:
         self.lr, self.beta_1, self.beta_2, self.epsilon = lr, beta_1, beta_2, epsilon
         self.iterations = 0
         self.state = None
+        self.slots = ("m", "v")
 
     def init(self, n, device):
         self.state = (torch.zeros(n, device=device), torch.zeros(n, device=device))
@@ -73,6 +74,7 @@ class RMSprop:
         self.lr, self.rho, self.epsilon = lr, rho, epsilon
         self.iterations = 0
         self.state = None
+        self.slots = ("accumulator",)
 
     def init(self, n, device):
         self.state = (torch.zeros(n, device=device),)
@@ -254,7 +256,56 @@ class Model:
             path = path + ".npz"
         np.savez(path, **{k.replace("/", "__"): v for k, v in self.get_weights_dict().items()})
 
-    save = save_weights
+    def save(self, path):
+        """Keras ``model.save`` (mycode/FoV_seq2seq_mu_var.py:256): for ``*.h5`` the weights under ``/model_weights`` plus -
+        once compiled - the optimiser's iteration count and moment buffers under ``/optimizer_weights`` and the
+        ``training_config`` attribute, so that ``load_weights`` + ``load_optimizer_weights`` resume a run exactly;
+        other paths: ``save_weights``."""
+        if not path.endswith(_H5_EXT):
+            return self.save_weights(path)
+        opt_w, cfg = None, None
+        if self.optimizer is not None and self.optimizer.state is not None:
+            o = self.optimizer
+            name = type(o).__name__
+            opt_w = [("%s/iterations:0" % name, np.asarray(o.iterations, np.int64))]
+            for slot, flat in zip(o.slots, o.state):
+                host = flat.detach().cpu().numpy()
+                for k in self.weight_order:
+                    off, shp = self._offsets[k]
+                    opt_w.append(("training/%s/%s/%s:0" % (name, k, slot), host[off:off + int(np.prod(shp))].reshape(shp)))
+            conf = {k: float(getattr(o, k)) for k in ("lr", "beta_1", "beta_2", "rho", "epsilon") if hasattr(o, k)}
+            cfg = {"optimizer_config": {"class_name": name, "config": conf}, "loss": list(self.loss_kinds or []),
+                   "loss_weights": [float(x) for x in (self.loss_weights or [])], "metrics": [],
+                   "sample_weight_mode": None}
+        h5lite.write_keras_model(path, self._keras_layers(), opt_w, cfg,
+                                 {"class_name": type(self).__name__, "config": {"weight_order": list(self.weight_order)}})
+
+    def load_optimizer_weights(self, path):
+        """Restore the optimiser state a ``save('x.h5')`` of the same architecture wrote (iterations + moment buffers);
+        the model must be compiled with the same optimiser class.  Returns the file's ``training_config``."""
+        cfg, ws = h5lite.read_keras_optimizer(path)
+        o = self.optimizer
+        if o is None or o.state is None:
+            raise ValueError("compile() the model before load_optimizer_weights")
+        name = type(o).__name__
+        d = dict(ws)
+        if "%s/iterations:0" % name not in d:
+            raise ValueError("%s holds no %s state (optimizer_weights: %s)" % (path, name, [n for n, _ in ws][:3]))
+        for slot, flat in zip(o.slots, o.state):
+            host = np.zeros(self.n_flat, np.float32)
+            for k in self.weight_order:
+                off, shp = self._offsets[k]
+                a = d["training/%s/%s/%s:0" % (name, k, slot)]
+                if tuple(a.shape) != tuple(shp):
+                    raise ValueError("optimizer slot %s of %s: shape %s, expected %s" % (slot, k, a.shape, shp))
+                host[off:off + a.size] = a.ravel()
+            flat.copy_(torch.from_numpy(host).to(flat.device))
+        o.iterations = int(d["%s/iterations:0" % name])
+        if cfg:
+            for k, v in cfg.get("optimizer_config", {}).get("config", {}).items():
+                if hasattr(o, k):
+                    setattr(o, k, v)
+        return cfg
 
     def load_weights(self, path, layer_map=None):
         """``.npz`` written by ``save_weights``, or an HDF5 checkpoint (``model.save_weights`` / ``model.save`` /

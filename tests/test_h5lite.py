@@ -204,3 +204,63 @@ def test_model_h5_weights_from_a_keras_named_checkpoint(tmp_path):
     h5.write_keras_weights(p3, bad)
     with pytest.raises(ValueError, match="shape"):
         _FakeModel(6).load_weights(p3)
+
+
+def test_model_save_with_optimizer_state(tmp_path):
+    """model.save('x.h5') in Keras' model.save layout (model_weights / optimizer_weights / training_config) and
+    load_weights + load_optimizer_weights restore everything (host logic; torch CPU tensors stand in for the bucket)."""
+    import torch
+    from longterm360fov_b200.models import Model, Adam, RMSprop
+
+    class Fake(_FakeModel):
+        save, load_optimizer_weights = Model.save, Model.load_optimizer_weights
+        loss_kinds, loss_weights = ["mse"], [1.0]
+
+        def __init__(self, seed, opt):
+            super().__init__(seed)
+            self._offsets, off = {}, 0
+            for k, shp in zip(self.weight_order, self.shapes):
+                self._offsets[k] = (off, shp)
+                off += (int(np.prod(shp)) + 63) // 64 * 64
+            self.n_flat = off + 64
+            self.optimizer = opt
+            opt.init(self.n_flat, "cpu")
+
+    a = Fake(0, Adam(lr=2e-3))
+    g = torch.Generator().manual_seed(1)
+    for t in a.optimizer.state:
+        t.copy_(torch.rand(a.n_flat, generator=g))
+    a.optimizer.iterations = 17
+    p = str(tmp_path / "fov_s2s_tanh.h5")
+    a.save(p)
+    f = h5.File(p)
+    assert sorted(f.keys()) == ["model_weights", "optimizer_weights"]
+    names = [n.decode() for n in f["optimizer_weights"].attrs["weight_names"]]
+    assert names[0] == "Adam/iterations:0" and names[1] == "training/Adam/encoder/kernel/m:0" and len(names) == 17
+    assert f["optimizer_weights/training/Adam/decoder_dense/bias/v:0"].shape == (6,)
+    import json
+    cfg = json.loads(f.attrs["training_config"].decode())
+    assert cfg["optimizer_config"]["class_name"] == "Adam" and abs(cfg["optimizer_config"]["config"]["lr"] - 2e-3) < 1e-12
+    b = Fake(1, Adam())
+    b.load_weights(p)
+    b.load_optimizer_weights(p)
+    assert b.optimizer.iterations == 17 and abs(b.optimizer.lr - 2e-3) < 1e-12
+    for k in a.weight_order:
+        off, shp = a._offsets[k]
+        n = int(np.prod(shp))
+        for x, y in zip(a.optimizer.state, b.optimizer.state):
+            assert torch.equal(x[off:off + n], y[off:off + n])
+    for x, y in zip(a.w, b.w):
+        np.testing.assert_array_equal(x, y)
+    with pytest.raises(ValueError, match="RMSprop"):
+        Fake(2, RMSprop()).load_optimizer_weights(p)
+    # an uncompiled model's save holds weights only and still loads
+    c = _FakeModel(3)
+    c.optimizer = None
+    c.save = Model.save.__get__(c)
+    p2 = str(tmp_path / "w_only.h5")
+    c.save(p2)
+    assert h5.File(p2).keys() == ["model_weights"] and h5.read_keras_optimizer(p2) == (None, [])
+    d = _FakeModel(4)
+    d.load_weights(p2)
+    np.testing.assert_array_equal(d.w[0], c.w[0])
