@@ -87,3 +87,29 @@ def make_m4_batch(n, seed=0):
     tr = synth_trajectories(n, 1, 20, seed)[:, 0].reshape(n, 20, FPS, 3)
     hm = one_hot_heatmaps(tr)
     return [hm[:, :10], hm[:, 9:10]], [hm[:, 10:]]
+
+
+def clip_xyz(per_video):
+    """mycode/dataIO.py:16-26: clamp every video's 'x' / 'y' / 'z' arrays to [-1, 1] in place (the dataset pickles hold
+    unit vectors with rounding spill); returns the same dict."""
+    for v in per_video.values():
+        for axis in ("x", "y", "z"):
+            np.clip(v[axis], -1, 1, out=v[axis])
+    return per_video
+
+
+def rand_sample_ind(total_num_samples, num_testing_sample, batch_size, validation_ratio=0.1, rng=None):
+    """mycode/utility.py:575-586: indices of a random subset of the first ``total - num_testing`` samples whose size
+    makes both the training part and the ``validation_ratio`` part a whole number of batches (Keras' ``fit`` then never
+    sees a ragged last batch).  ``rng``: a ``random.Random`` (default: the ``random`` module, as the reference)."""
+    import random
+    n = total_num_samples - num_testing_sample
+    val_batches = int(n / batch_size * validation_ratio)
+    n_train = int((1 - validation_ratio) / validation_ratio * val_batches * batch_size)
+    n_val = int(val_batches * batch_size)
+    return (rng or random).sample(range(n), n_train + n_val)
+
+
+def rand_sample(data, sample_ind):
+    """mycode/utility.py:589-591: the chosen samples in ascending index order."""
+    return np.asarray(data)[np.sort(np.asarray(sample_ind, dtype=np.int64))]

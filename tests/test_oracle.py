@@ -1,6 +1,8 @@
 """CPU tests of the oracle itself: pinned against the reference's own NumPy
 functions (golden vectors), the two restatements against each other, torch.nn.LSTM
 as an independent gate-algebra check, known-answer cases and finite differences."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -400,3 +402,29 @@ def test_given_others_bilstm_structure():
     c = kn.given_others_seq2seq_forward(w, enc, oth, dec_tf, "others_lstm", True)
     d = kn.given_others_seq2seq_forward(w, enc, oth, dec_tf2, "others_lstm", True)
     assert np.array_equal(c, d)
+
+
+def test_host_utils_match_reference_golden():
+    """data.rand_sample_ind / rand_sample (mycode/utility.py:575-591) and clip_xyz (mycode/dataIO.py:16-26) against
+    outputs of the reference's own functions (tests/golden/make_host_utils_golden.py), same ``random`` seeds."""
+    import random
+    from longterm360fov_b200 import data
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_host_utils_golden.npz"))
+    for i, (tot, ntest, bs, vr) in enumerate(g["cases"]):
+        tot, ntest, bs = int(tot), int(ntest), int(bs)
+        random.seed(100 + i)
+        ind = data.rand_sample_ind(tot, ntest, bs, validation_ratio=float(vr))
+        assert np.array_equal(np.array(ind), g["ind%d" % i])
+        assert np.array_equal(np.array(data.rand_sample_ind(tot, ntest, bs, float(vr), rng=random.Random(100 + i))), g["ind%d" % i])
+        n_val = int((tot - ntest) / bs * float(vr)) * bs
+        assert n_val % bs == 0 and len(set(ind)) == len(ind) and max(ind) < tot - ntest   # whole validation batches
+        src = np.random.default_rng(i).standard_normal((tot - ntest, 3)).astype(np.float32)
+        assert np.array_equal(data.rand_sample(src, ind), g["picked%d" % i])
+    keys = [(k, a) for k in ("v0", 3) for a in "xyz"]
+    vids = {}
+    for (k, a), arr in zip(keys, g["clip_in"]):
+        vids.setdefault(k, {})[a] = arr.copy()
+    out = data.clip_xyz(vids)
+    assert out is vids
+    for (k, a), want in zip(keys, g["clip_out"]):
+        assert np.array_equal(out[k][a], want)
