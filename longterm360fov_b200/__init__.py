@@ -5,7 +5,7 @@ without libfov360.so raises."""
 from . import _lib, h5lite
 from .h5lite import load_h5, save2hdf5
 from .callbacks import EarlyStopping, ModelCheckpoint, ReduceLROnPlateau
-from .pipeline import M3VideoBatches
+from .pipeline import M3VideoBatches, M4HeatmapBatches
 from .models import (Adam, ConvLSTMSeq2Seq, FovSeq2Seq, Model, OthersLSTMSpanWhole, RMSprop,
                      convlstm_seq2seq, fov_seq2seq, fov_seq2seq_mu_var, others_lstm_span_whole,
                      StackedFovSeq2Seq, stacked_fov_seq2seq, GivenOthersSeq2Seq, given_others_gt_mean_var_seq2seq,
@@ -13,6 +13,6 @@ from .models import (Adam, ConvLSTMSeq2Seq, FovSeq2Seq, Model, OthersLSTMSpanWho
 
 __all__ = ["fov_seq2seq", "fov_seq2seq_mu_var", "others_lstm_span_whole", "convlstm_seq2seq",
            "Model", "FovSeq2Seq", "OthersLSTMSpanWhole", "ConvLSTMSeq2Seq", "Adam", "RMSprop",
-           "ModelCheckpoint", "ReduceLROnPlateau", "EarlyStopping", "M3VideoBatches", "StackedFovSeq2Seq",
+           "ModelCheckpoint", "ReduceLROnPlateau", "EarlyStopping", "M3VideoBatches", "M4HeatmapBatches", "StackedFovSeq2Seq",
            "stacked_fov_seq2seq", "GivenOthersSeq2Seq", "given_others_gt_mean_var_seq2seq",
            "OthersConvLSTMTarget", "others_convlstm_target", "h5lite", "load_h5", "save2hdf5"]

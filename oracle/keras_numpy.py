@@ -966,3 +966,31 @@ def convlstm_seq2seq_forward(w, enc_in, dec_in, head_kind="conv2d", steps=10, di
                 x = y[:, None, None, :]
         outs.append(y)
     return np.stack(outs, axis=1)
+
+
+def heatmap_batches_per_video(xyz, stride=10, running_length=10, bin_size=10):
+    """The heatmap ConvLSTM's samples of ONE video, in the order mycode/data_generator_for_heatmap.py:103-216 yields
+    them (target viewers outermost, windows in time order): per viewer the seconds of one-hot FoV-centre maps
+    (:142-146) are cut into (past, future) windows by reshape2second_stacks(collapse_user=True) (:95), and
+    _prepare_data (:17-75, cfg.input_mean_var = cfg.predict_mean_var = False) turns them into
+    encoder input (N,10,36,18,30), decoder input = the last observed second (N,1,36,18,30) and target (N,10,36,18,30)
+    (frames as channels: the transpose (0,1,4,3,2) of the stored (fps,18,36) stacks).
+    xyz: (U, S, fps, 3) unit vectors -> (enc, dec0, target), N = U * windows.
+
+    The shipped generator cannot run against the shipped utility.py (it hands 5-D stacks to the 3-D-only
+    reshape2second_stacks, :94-95, and _reshape_others_data transposes six axes of a 4-D array, :23), so there is no
+    reference output to record: this follows the statements on the target viewer's tensors, with the per-second stack
+    flattened for the windowing; its two building blocks (one_hot_heatmaps, reshape2second_stacks) are pinned to the
+    reference's own functions by golden vectors."""
+    U, S = xyz.shape[:2]
+    heat = one_hot_heatmaps(xyz, bin_size)                                   # (U,S,36,18,F)
+    flat = heat.reshape(U, S, -1)
+    enc, tgt = [], []
+    for u in range(U):
+        past, fut, _ = reshape2second_stacks(flat[u:u + 1], collapse_user=True, stride=stride,
+                                             running_length=running_length)
+        enc.append(past)
+        tgt.append(fut)
+    shp = (-1, running_length) + heat.shape[2:]
+    enc, tgt = np.concatenate(enc).reshape(shp), np.concatenate(tgt).reshape(shp)
+    return enc, enc[:, -1:], tgt

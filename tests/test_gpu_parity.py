@@ -1036,3 +1036,32 @@ def test_fit_generator_with_device_batch_builder():
     assert abs(h.history["loss"][0] - float(np.mean(ref))) < 1e-6
     for k in a.weight_order:
         assert torch.allclose(a.params[k], b.params[k], rtol=0, atol=1e-6), k
+
+
+def test_heatmap_batch_builder_on_device():
+    """pipeline.M4HeatmapBatches (raw xyz seconds -> one-hot maps -> windows on the GPU) equals the oracle restatement
+    of data_generator_for_heatmap.py:17-101 bit for bit, and drives fit_generator of the heatmap ConvLSTM."""
+    fov = _cuda()
+    from longterm360fov_b200 import data
+    U, S, stride = 3, 27, 5
+    raw = data.synth_trajectories(1, n_viewers=U, seconds=S, seed=11)[0].reshape(U, S, 90)
+    enc, dec, tgt = kn.heatmap_batches_per_video(raw.reshape(U, S, 30, 3).astype(np.float64), stride=stride)
+    builder = fov.M4HeatmapBatches(stride=stride)
+    (e, d), (t,) = builder(torch.tensor(raw, device="cuda"))
+    assert np.array_equal(e.cpu().numpy(), enc) and np.array_equal(t.cpu().numpy(), tgt)
+    assert np.array_equal(d.cpu().numpy(), dec)
+    lim = fov.M4HeatmapBatches(stride=stride, limit=4)
+    (e4, d4), (t4,) = lim(torch.tensor(raw, device="cuda"))
+    assert e4.shape[0] == 4 and torch.equal(e4, e[:4]) and torch.equal(t4, t[:4]) and torch.equal(d4, d[:4])
+    w = kn.init_convlstm_seq2seq(seed=5, in_ch=30, filters=(4, 3, 2), kernel_size=3, head=(6, 7, 30))
+    from longterm360fov_b200.models import ConvLSTMSeq2Seq
+    a = ConvLSTMSeq2Seq(w, head_kind="conv2d").compile("RMSprop", "mean_squared_error")
+    b = ConvLSTMSeq2Seq(w, head_kind="conv2d").compile("RMSprop", "mean_squared_error")
+    xs, ys = lim(torch.tensor(raw, device="cuda"))
+    ref = [float(a.train_step_device(xs, ys).item()) for _ in range(2)]
+
+    def gen():
+        while True:
+            yield torch.from_numpy(raw).pin_memory()
+    h = b.fit_generator(gen(), steps_per_epoch=2, epochs=1, batch_builder=lim)
+    assert abs(h.history["loss"][0] - float(np.mean(ref))) < 1e-5 * max(1.0, abs(np.mean(ref)))

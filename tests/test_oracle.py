@@ -428,3 +428,22 @@ def test_host_utils_match_reference_golden():
     assert out is vids
     for (k, a), want in zip(keys, g["clip_out"]):
         assert np.array_equal(out[k][a], want)
+
+
+def test_heatmap_batches_per_video_structure():
+    """kn.heatmap_batches_per_video (data_generator_for_heatmap.py:17-101 on the target viewer's tensors): sample
+    (viewer u, window i) holds the one-hot maps of seconds i*stride .. +9 (past) and +10 .. +19 (future), viewers
+    outermost; the decoder input is the last observed second; every frame-channel of every map holds exactly one 1."""
+    from longterm360fov_b200 import data
+    U, S, stride = 3, 27, 5
+    xyz = data.synth_trajectories(1, n_viewers=U, seconds=S, seed=11)[0].reshape(U, S, 30, 3).astype(np.float64)
+    enc, dec, tgt = kn.heatmap_batches_per_video(xyz, stride=stride)
+    n = (S - 20) // stride + 1
+    assert enc.shape == (U * n, 10, 36, 18, 30) and dec.shape == (U * n, 1, 36, 18, 30) and tgt.shape == enc.shape
+    heat = kn.one_hot_heatmaps(xyz)
+    for u in range(U):
+        for i in range(n):
+            assert np.array_equal(enc[u * n + i], heat[u, i * stride:i * stride + 10])
+            assert np.array_equal(tgt[u * n + i], heat[u, i * stride + 10:i * stride + 20])
+    assert np.array_equal(dec[:, 0], enc[:, -1])
+    assert np.array_equal(enc.sum(axis=(2, 3)), np.ones((U * n, 10, 30)))
