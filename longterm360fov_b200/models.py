@@ -141,8 +141,7 @@ class _GraphedStep:
         ops.set_math(m.compute)
         outs = m._forward(self.sx, True)
         total = m._loss(outs, self.sy)
-        total.backward(self.seed)
-        ops.join_wgrad_stream()
+        m._backward(total, self.seed)
         return total.detach()
 
     def run(self, xs, ys):
@@ -411,6 +410,20 @@ class Model:
             total = l if total is None else total + l
         return total
 
+    def _backward(self, total, seed=None):
+        """BPTT of the summed losses with a unit gradient (the fused loss gradients pass through untouched,
+        ops.set_unit_loss_grad), the side-stream weight gradients joined, then - data parallel - the small flat gradient
+        bucket scaled by the rank's sample count ``seed`` (a (1,) device tensor): the same numbers as back-propagating
+        with that seed, without a pass over the (B,T,out) loss gradients."""
+        ops.set_unit_loss_grad(True)
+        try:
+            total.backward()
+        finally:
+            ops.set_unit_loss_grad(False)
+        ops.join_wgrad_stream()
+        if seed is not None:
+            self.gflat.mul_(seed)
+
     def train_step_device(self, xs, ys, targets_ready=None):
         """One optimiser step on device tensors; returns the loss as a device tensor
         (no host sync).  DP: gradients are sum-allreduced and scaled by 1/world.
@@ -458,8 +471,7 @@ class Model:
             if targets_ready is not None:
                 torch.cuda.current_stream().wait_event(targets_ready)
             total = self._loss(outs, ys)
-            total.backward(seed)
-            ops.join_wgrad_stream()
+            self._backward(total, seed)
         div = None
         if self.world_size > 1:
             div = parallel.allreduce_gradients(self.gflat, self.comm, n_local)

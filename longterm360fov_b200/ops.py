@@ -1011,6 +1011,18 @@ class SoftmaxFn(torch.autograd.Function):
         return dx
 
 
+_UNIT_LOSS_GRAD = [False]
+
+
+def set_unit_loss_grad(on):
+    """The caller promises that the loss tensors are back-propagated with gradient exactly 1 (Model's own train step:
+    ``total = sum(losses); total.backward()``): LossFn.backward then returns the fused gradient as it is instead of
+    multiplying the whole (B,T,out) tensor by the incoming scalar (140 MB for config 2's reconstruction head at
+    B = 8880, ~0.1 ms per step for a multiplication by 1.0).  Off by default: any other use of the loss tensor
+    (scaling, averaging over micro-batches, a weighted data-parallel seed) keeps the multiply."""
+    _UNIT_LOSS_GRAD[0] = bool(on)
+
+
 class LossFn(torch.autograd.Function):
     """kind in {'mse','nll','cce'}: returns a 1-element loss tensor; gradient fused."""
 
@@ -1045,7 +1057,7 @@ class LossFn(torch.autograd.Function):
         # afterwards (1 for the plain sum of Keras compile(loss=[...]), the shard weight of a data-parallel step,
         # a micro-batch average, ...): one scalar multiply of the small (B,T,out) gradient.
         dy = ctx.dy
-        if dy is not None:
+        if dy is not None and not _UNIT_LOSS_GRAD[0]:
             dy = dy * dl.reshape(())
         return None, None, dy, None, None
 

@@ -100,8 +100,8 @@ class FovComm:
 
 def allreduce_gradients(flat_grads, comm, local_count):
     """Count-weighted gradient allreduce.  ``flat_grads``: the flat bucket whose LAST element is the reserved
-    count slot and whose gradients were back-propagated with seed ``local_count`` (i.e. are already multiplied
-    by the rank's sample count).  After the call the bucket holds the sums and ``flat_grads[-1]`` the global
+    count slot and whose gradients are already multiplied by the rank's sample count (Model._backward scales the
+    bucket after BPTT).  After the call the bucket holds the sums and ``flat_grads[-1]`` the global
     sample count the optimiser divides by (ops.adam_step(..., grad_div=flat_grads[-1:]))."""
     flat_grads[-1] = float(local_count)
     comm.allreduce_sum(flat_grads)

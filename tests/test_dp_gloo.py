@@ -48,7 +48,7 @@ def _worker(rank, world, port, out_q):
     for _ in range(3):
         loss, _, grads = kt.loss_and_grads(kt.fov_seq2seq_forward, w, [torch.tensor(enc), torch.tensor(dec)],
                                            [torch.tensor(tgt)], [kt.mse])
-        # the model back-propagates with seed n_local (gradients x local count) into a bucket with a reserved tail
+        # the model scales its gradient bucket by n_local after BPTT (Model._backward); the bucket has a reserved tail
         bucket = torch.cat([_flat(grads, order) * n_local, torch.zeros(64, dtype=torch.float64)])
         div = parallel.allreduce_gradients(bucket, comm, n_local)
         assert float(div) == 9.0

@@ -1065,3 +1065,39 @@ def test_heatmap_batch_builder_on_device():
             yield torch.from_numpy(raw).pin_memory()
     h = b.fit_generator(gen(), steps_per_epoch=2, epochs=1, batch_builder=lim)
     assert abs(h.history["loss"][0] - float(np.mean(ref))) < 1e-5 * max(1.0, abs(np.mean(ref)))
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_data_parallel_step_on_one_gpu_with_a_stand_in_communicator(graphs):
+    """The data-parallel train step (unit-gradient BPTT, gradient bucket scaled by the rank's sample count, summed
+    allreduce with the count riding in the bucket's last element, optimiser dividing by the global count) run on ONE
+    GPU with a communicator that plays a second rank holding a batch 3x as large with the same mean gradient: the
+    trajectory must equal plain single-GPU training (the weighted mean of equal gradients is that gradient)."""
+    fov = _cuda()
+
+    class Twin:
+        rank, world = 0, 2
+
+        def allreduce_sum(self, flat):
+            assert float(flat[-1]) == 24.0                       # this rank's sample count rides in the last element
+            flat.mul_(4.0)                                       # + a peer with 3x the samples and the same mean gradient
+
+        def broadcast(self, flat, root=0):
+            pass
+
+    rng = np.random.default_rng(61)
+    enc = rng.uniform(-1, 1, (24, 10, 90)).astype(np.float32)
+    fut = np.tanh(enc[:, :, :6] * 0.5).astype(np.float32)
+    dec_in = np.concatenate([enc[:, -1:, :6], fut[:, :-1]], axis=1)
+    a = fov.fov_seq2seq(seed=3).compile("Adam", "mean_squared_error")
+    b = fov.fov_seq2seq(seed=3).compile("Adam", "mean_squared_error").distribute(Twin())
+    assert b.world_size == 2
+    if graphs:
+        a.enable_cuda_graphs()
+        b.enable_cuda_graphs()
+    la = [a.train_on_batch([enc, dec_in], fut) for _ in range(4)]
+    lb = [b.train_on_batch([enc, dec_in], fut) for _ in range(4)]
+    np.testing.assert_allclose(lb, la, rtol=2e-5)
+    assert la[-1] < la[0]
+    for x, y in zip(a.get_weights(), b.get_weights()):
+        np.testing.assert_allclose(x, y, atol=2e-5)
