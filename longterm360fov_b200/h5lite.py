@@ -17,6 +17,7 @@ The reader is pinned to a file libhdf5 wrote (scipy's ``testhdf5_7.4_GLNX86.mat`
 v0, v1 headers, layout v2 - tests/test_h5lite.py); the writer emits the same structures and is checked by reading
 its files back.  Host-side I/O only: nothing here touches the GPU.
 """
+import mmap
 import struct
 import zlib
 
@@ -370,11 +371,19 @@ class File(Group):
     """Read-only view of an HDF5 file (``h5lite.File(path)`` ~ ``h5py.File(path, 'r')``)."""
 
     def __init__(self, path_or_bytes):
+        self._mm = self._fh = None
         if isinstance(path_or_bytes, (bytes, bytearray, memoryview)):
             self.buf = memoryview(bytes(path_or_bytes))
         else:
-            with open(path_or_bytes, "rb") as fh:
-                self.buf = memoryview(fh.read())
+            # memory-mapped: the sample caches of the reference run to gigabytes; only the bytes a dataset read
+            # touches are paged in
+            self._fh = open(path_or_bytes, "rb")
+            try:
+                self._mm = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ)
+            except ValueError:
+                self._fh.close()
+                raise H5Error("not an HDF5 file (empty): %s" % path_or_bytes)
+            self.buf = memoryview(self._mm)
         buf = self.buf
         a = 0
         while True:                                                  # user block: 0, 512, 1024, ...
@@ -404,12 +413,26 @@ class File(Group):
         super().__init__(self, root, "/")
 
     def close(self):
-        pass
+        if self._mm is not None:
+            try:
+                self.buf.release()
+                self._mm.close()
+            except BufferError:                                      # a view of the mapping is still alive somewhere:
+                pass                                                 # the mapping goes with its last reference
+            self._fh.close()
+            self._mm = self._fh = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def __enter__(self):
         return self
 
     def __exit__(self, *a):
+        self.close()
         return False
 
     # -- helpers ---------------------------------------------------------------------------------------------------- #
