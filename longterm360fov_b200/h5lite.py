@@ -709,17 +709,19 @@ class Writer(_GroupWriter):
         if self._closed:
             return
         self._closed = True
-        self._out = bytearray(96)
         self._leaf_k = max(4, (self._max_group(self._node) + 1) // 2)
         self._int_k = 16
-        root_hdr, btree, heap = self._emit_group(self._node)
-        sb = SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, self._leaf_k, self._int_k, 0)
-        sb += struct.pack("<QQQQ", 0, UNDEF, len(self._out), UNDEF)
-        sb += struct.pack("<QQII", 0, root_hdr, 1, 0) + struct.pack("<QQ", btree, heap)
-        assert len(sb) == 96
-        self._out[:96] = sb
-        with open(self.path, "wb") as fh:
-            fh.write(self._out)
+        with open(self.path, "wb") as fh:                            # streamed: one dataset in memory at a time
+            self._fh, self._pos = fh, 96
+            fh.write(bytes(96))
+            root_hdr, btree, heap = self._emit_group(self._node)
+            sb = SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, self._leaf_k, self._int_k, 0)
+            sb += struct.pack("<QQQQ", 0, UNDEF, self._pos, UNDEF)
+            sb += struct.pack("<QQII", 0, root_hdr, 1, 0) + struct.pack("<QQ", btree, heap)
+            assert len(sb) == 96
+            fh.seek(0)
+            fh.write(sb)
+        self._fh = None
 
     # -- emitters ---------------------------------------------------------------------------------------------------- #
     def _max_group(self, g):
@@ -730,9 +732,12 @@ class Writer(_GroupWriter):
         return m
 
     def _alloc(self, blob):
-        self._out += bytes(-len(self._out) % 8)
-        addr = len(self._out)
-        self._out += blob
+        pad = -self._pos % 8
+        if pad:
+            self._fh.write(bytes(pad))
+        addr = self._pos + pad
+        self._fh.write(blob)
+        self._pos = addr + len(blob)
         return addr
 
     def _attr_msgs(self, node):
@@ -827,7 +832,7 @@ class Writer(_GroupWriter):
             root = self._emit_chunk_tree(recs, a.shape, chunk)
             lay = struct.pack("<BBBQ", 3, 2, a.ndim + 1, root) + b"".join(struct.pack("<I", c) for c in chunk + (esz,))
         else:
-            addr = self._alloc(a.tobytes()) if a.size else UNDEF
+            addr = self._alloc(a.reshape(-1).view(np.uint8).data if a.dtype.kind != "S" else a.tobytes()) if a.size else UNDEF
             lay = struct.pack("<BBQQ", 3, 1, addr, a.size * esz)
         msgs.append((0x08, 0, lay))
         return self._emit_header(msgs + self._attr_msgs(d))
@@ -847,7 +852,7 @@ class Writer(_GroupWriter):
             nodes = []
             groups = [items[i:i + 2 * k] for i in range(0, len(items), 2 * k)]
             addrs = []
-            base = len(self._out) + (-len(self._out) % 8)
+            base = self._pos + (-self._pos % 8)
             nsize = 24 + (2 * k + 1) * ksz + 2 * k * 8
             for gi in range(len(groups)):
                 addrs.append(base + gi * nsize)
