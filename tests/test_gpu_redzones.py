@@ -223,3 +223,51 @@ def test_red_zone_catches_a_real_overrun():
     _lib.check(lib.fov_mse_fwd_bwd(n + 1, ops.ptr(y_pred), ops.ptr(y_true), 1.0, ops.ptr(loss), ops.ptr(dy), st), "mse")
     torch.cuda.synchronize()
     assert gt.check() == [(1, "tail", n)]
+
+
+def _bench_cases():
+    rng = np.random.default_rng(78)
+    u = lambda *s: rng.uniform(-1, 1, s).astype(np.float32)
+
+    def m3_bench(fov):
+        from longterm360fov_b200 import data
+        w = kn.init_others_lstm_span_whole(seed=3, num_user=34)
+        m = fov.others_lstm_span_whole(num_user=34, weights=w).compile("Adam", ["mean_squared_error"] * 3)
+        x, y = data.make_m3_batch(40, 34, seed=17)
+        tile = lambda a: np.tile(a, (222,) + (1,) * (a.ndim - 1))                  # B = 8880, bench.py's per-GPU batch
+        return m, "bf16x2", [tile(a) for a in x], [tile(a) for a in y]
+
+    def m4_bench(fov):
+        from longterm360fov_b200.models import ConvLSTMSeq2Seq
+        w = kn.init_convlstm_seq2seq(seed=6, in_ch=30, filters=(32, 16, 8), kernel_size=5, head=(512, 1024, 30))
+        m = ConvLSTMSeq2Seq(w, "conv2d", max_decoder_seq_length=3).compile("RMSprop", "mean_squared_error")
+        B = 5                                                                      # 36 x 18 images, heads 512 / 1024 / 30
+        return m, "bf16", [np.abs(u(B, 10, 36, 18, 30)), np.abs(u(B, 1, 36, 18, 30))], [np.abs(u(B, 3, 36, 18, 30))]
+
+    def m2_bench(fov):
+        m = fov.fov_seq2seq_mu_var(teacher_forcing=False).compile("Adam", "mean_squared_error")
+        B = 37888                                                                  # config 3's training batch in bench.py
+        return m, "bf16x2", [u(B, 10, 6), u(B, 1, 6)], [u(B, 10, 6)]
+    return [("m3_b8880", m3_bench), ("m4_36x18_heads_512_1024", m4_bench), ("m2_b37888_ar", m2_bench)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,build", _bench_cases(), ids=[c[0] for c in _bench_cases()])
+def test_no_write_outside_any_buffer_at_bench_shapes(name, build, monkeypatch):
+    """The same red-zone check at the shapes bench.py times: config 2 at B = 8880 (bf16x2), config 5's full-size
+    images with the 512 / 1024 heads (bf16, the TMA-fed weight gradients), config 3's model at B = 37 888."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import longterm360fov_b200 as fov
+    from longterm360fov_b200 import ops
+    model, mode, x, y = build(fov)
+    model.set_compute(mode)
+    gt = GuardedTorch()
+    monkeypatch.setattr(ops, "torch", gt)
+    loss = model.train_on_batch(x, y)
+    out = model.predict_on_batch(x)
+    torch.cuda.synchronize()
+    assert np.isfinite(loss) and all(np.isfinite(np.asarray(o)).all() for o in (out if isinstance(out, list) else [out]))
+    assert len(gt.log) > 4
+    assert gt.check() == []
+    assert _gaps_clean(model)
