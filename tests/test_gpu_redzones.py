@@ -271,3 +271,38 @@ def test_no_write_outside_any_buffer_at_bench_shapes(name, build, monkeypatch):
     assert len(gt.log) > 4
     assert gt.check() == []
     assert _gaps_clean(model)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["bf16x2", "fp32"])
+@pytest.mark.parametrize("name,build", _cases(), ids=[c[0] for c in _cases()])
+def test_repeated_runs_agree(name, build, mode):
+    """Racecheck by repetition (compute-sanitizer is closed on this pool): the forward pass of every model family has
+    no atomics, so 8 repetitions on the same inputs must be BIT-identical - a shared-memory / TMEM / mbarrier race in
+    a persistent kernel shows up as run-to-run differences; the gradients (weight gradients are summed with
+    red.global.add, so only their rounding may differ) must agree to 1e-5 of their scale."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import longterm360fov_b200 as fov
+    model, x, y = build(fov)
+    model.set_compute(mode)
+    as_list = lambda o: o if isinstance(o, list) else [o]
+    first = [np.asarray(o).copy() for o in as_list(model.predict_on_batch(x))]
+    for rep in range(7):
+        again = as_list(model.predict_on_batch(x))
+        for a, b in zip(first, again):
+            assert np.array_equal(a, np.asarray(b)), (name, mode, rep)
+    xs, ys = model._to_dev(x), model._to_dev(y)
+    grads = []
+    for rep in range(4):
+        model.gflat.zero_()
+        from longterm360fov_b200 import ops
+        ops.set_math(mode)
+        model._loss(model._forward(xs, True), ys).backward()
+        ops.join_wgrad_stream()
+        torch.cuda.synchronize()
+        grads.append(model.gflat.clone())
+    scale = float(grads[0].abs().max())
+    assert scale > 0
+    for g in grads[1:]:
+        assert float((g - grads[0]).abs().max()) <= 1e-5 * scale, (name, mode)
