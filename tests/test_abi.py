@@ -153,3 +153,33 @@ def test_callbacks_host_logic():
     assert abs(m.optimizer.lr - 4e-5) < 1e-12 and m.stop_training is False
     e.on_epoch_end(8, {"val_loss": 0.95})
     assert m.stop_training is True
+
+
+def test_flags_shim_maps_the_reference_cfg_onto_builder_arguments():
+    """flags.cfg carries mycode/config.py's defaults of the flags the path reads; builder_kwargs() yields arguments
+    every builder's signature accepts (no GPU needed: signatures only)."""
+    import inspect
+    import longterm360fov_b200 as fov
+    from longterm360fov_b200 import flags
+    c = flags.reference_defaults()
+    assert (c.fps, c.running_length, c.predict_step, c.batch_size, c.data_chunk_stride) == (30, 10, 10, 32, 10)
+    assert (c.input_mean_var, c.predict_mean_var, c.sample_and_refeed, c.teacher_forcing, c.use_one_hot) == \
+        (False, False, True, False, False)
+    for script in flags.scripts():
+        name, kw = flags.builder_kwargs(script, c)
+        inspect.signature(getattr(fov, name)).bind_partial(**kw)
+    assert flags.builder_kwargs("FoV_seq2seq.py", c)[1]["num_encoder_tokens"] == 90
+    h = c.copy()
+    h.use_one_hot = True
+    assert flags.builder_kwargs("convlstm_seq2seq", h)[1]["use_one_hot"] is True and c.use_one_hot is False
+    t = c.copy()
+    t.predict_mean_var = True                                    # raw xyz in, mean/var out: the re-sampling graph
+    assert flags.builder_kwargs("convlstm_seq2seq", t)[1]["sample_and_refeed"] is True
+    t.input_mean_var = True
+    assert flags.builder_kwargs("convlstm_seq2seq", t)[1]["sample_and_refeed"] is False
+    assert flags.builder_kwargs("FoV_seq2seq_no_teac_forc", t)[1]["num_encoder_tokens"] == 6
+    import pytest
+    with pytest.raises(KeyError):
+        flags.builder_kwargs("lstm", c)
+    with pytest.raises(AttributeError):
+        c.no_such_flag

@@ -1101,3 +1101,29 @@ def test_data_parallel_step_on_one_gpu_with_a_stand_in_communicator(graphs):
     assert la[-1] < la[0]
     for x, y in zip(a.get_weights(), b.get_weights()):
         np.testing.assert_allclose(x, y, atol=2e-5)
+
+
+def test_flags_build_every_script():
+    """flags.build(script, cfg): every mapped reference script yields a model of the expected class; the heatmap
+    flags give the heatmap graph."""
+    fov = _cuda()
+    from longterm360fov_b200 import flags
+    c = flags.reference_defaults()
+    c.input_mean_var = c.predict_mean_var = True                  # the configuration the concat-state graph needs
+    want = {"FoV_seq2seq": fov.FovSeq2Seq, "FoV_seq2seq_mu_var": fov.FovSeq2Seq, "FoV_seq2seq_no_teac_forc": fov.FovSeq2Seq,
+            "others_LSTM_span_whole": fov.OthersLSTMSpanWhole, "convlstm_seq2seq": fov.ConvLSTMSeq2Seq,
+            "given_others_gt_mean_var_seq2seq": fov.GivenOthersSeq2Seq, "Fov_seq2seq_2layers": fov.StackedFovSeq2Seq,
+            "3layers": fov.StackedFovSeq2Seq}
+    assert sorted(want) == flags.scripts()
+    for script, cls in want.items():
+        over = {"num_user": 6} if script in ("others_LSTM_span_whole", "given_others_gt_mean_var_seq2seq") else {}
+        m = flags.build(script, c, **over)
+        assert isinstance(m, cls), script
+    m = flags.build("FoV_seq2seq_no_teac_forc", c)
+    rng = np.random.default_rng(3)
+    y = m.predict_on_batch([rng.uniform(-1, 1, (4, 10, 6)).astype(np.float32), rng.uniform(-1, 1, (4, 1, 6)).astype(np.float32)])
+    assert y.shape == (4, 10, 6)
+    h = flags.reference_defaults()
+    h.use_one_hot = True
+    hm = flags.build("convlstm_seq2seq", h, head=(8, 8, None))
+    assert hm.head_kind == "conv2d" and hm.dropout == 0.3
