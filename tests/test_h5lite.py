@@ -264,3 +264,71 @@ def test_model_save_with_optimizer_state(tmp_path):
     d = _FakeModel(4)
     d.load_weights(p2)
     np.testing.assert_array_equal(d.w[0], c.w[0])
+
+
+def test_round_trip_property():
+    """Property test (hypothesis): any tree of groups / datasets of the supported dtypes, any shapes incl. empty and
+    scalar, contiguous or chunked (+ shuffle / deflate), with attributes, reads back exactly."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    import tempfile
+
+    dtypes = st.sampled_from(["<f4", "<f8", "<f2", "<i8", "<i4", "<i2", "|i1", "|u1", "<u2", "<u4", ">f4", ">i4"])
+    shapes = st.lists(st.integers(0, 7), min_size=0, max_size=3).map(tuple)
+    names = st.text(alphabet="abcXYZ019_:.- ", min_size=1, max_size=12).filter(lambda s: s.strip("/. ") != "")
+
+    @st.composite
+    def arrays(draw):
+        dt = np.dtype(draw(dtypes))
+        shape = draw(shapes)
+        n = int(np.prod(shape)) if shape else 1
+        seed = draw(st.integers(0, 2 ** 16))
+        raw = np.random.default_rng(seed).integers(-100, 100, n)
+        a = raw.astype(dt.newbyteorder("=")).reshape(shape)
+        chunks = None
+        if shape and n and draw(st.booleans()):
+            chunks = tuple(draw(st.integers(1, max(1, s))) for s in shape)
+        return a, chunks, draw(st.booleans()), draw(st.booleans())
+
+    tree = st.dictionaries(names, st.one_of(arrays(), st.dictionaries(names, arrays(), max_size=3)), max_size=5)
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(tree, st.integers(0, 99))
+    def run(t, attr_seed):
+        with tempfile.TemporaryDirectory() as d:
+            p = os.path.join(d, "t.h5")
+            with h5.Writer(p) as w:
+                w.attrs["seed"] = attr_seed
+                w.attrs["names"] = np.array([k.encode() for k in t]) if t else np.zeros((0,), "S1")
+
+                def put(g, k, v):
+                    a, chunks, comp, shuf = v
+                    ds = g.create_dataset(k, data=a, chunks=chunks, compression="gzip" if (comp and chunks) else None,
+                                          shuffle=bool(shuf and chunks))
+                    ds.attrs["shape"] = np.array(a.shape, np.int64)
+                for k, v in t.items():
+                    if isinstance(v, dict):
+                        g = w.create_group(k)
+                        for k2, v2 in v.items():
+                            put(g, k2, v2)
+                    else:
+                        put(w, k, v)
+            with h5.File(p) as f:
+                assert f.attrs["seed"] == attr_seed
+                assert sorted(f.keys()) == sorted(t, key=lambda s: s.encode())
+                assert [s.decode() for s in np.atleast_1d(f.attrs["names"])] == list(t)
+
+                def check(node, v):
+                    a = v[0]
+                    got = np.array(node)
+                    assert got.shape == a.shape and got.dtype.newbyteorder("=") == a.dtype.newbyteorder("=")
+                    assert np.array_equal(got, a)
+                    assert tuple(np.atleast_1d(node.attrs["shape"])) == a.shape
+                for k, v in t.items():
+                    if isinstance(v, dict):
+                        assert sorted(f[k].keys()) == sorted(v, key=lambda s: s.encode())
+                        for k2, v2 in v.items():
+                            check(f[k][k2], v2)
+                    else:
+                        check(f[k], v)
+    run()
