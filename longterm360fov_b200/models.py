@@ -426,7 +426,8 @@ class Model:
 
     def train_step_device(self, xs, ys, targets_ready=None):
         """One optimiser step on device tensors; returns the loss as a device tensor
-        (no host sync).  DP: gradients are sum-allreduced and scaled by 1/world.
+        (no host sync).  DP: each rank's gradient bucket is scaled by its sample count, sum-allreduced with the count
+        riding in the last element, and the optimiser divides by the global count (unequal shards weight correctly).
         ``targets_ready``: optional CUDA event after which ``ys`` may be read (their H2D copy
         runs on a side stream while the forward pass computes)."""
         n_local = int(xs[0].shape[0])
