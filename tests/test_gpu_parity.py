@@ -1067,7 +1067,9 @@ def test_heatmap_batch_builder_on_device():
         while True:
             yield torch.from_numpy(raw).pin_memory()
     h = b.fit_generator(gen(), steps_per_epoch=2, epochs=1, batch_builder=lim)
-    assert abs(h.history["loss"][0] - float(np.mean(ref))) < 1e-5 * max(1.0, abs(np.mean(ref)))
+    # RMSprop's first step moves every element by ~lr / sqrt(0.1) in the direction of its gradient's sign, so an
+    # element whose gradient is summation-order noise may differ between the two runs: compare the losses loosely
+    assert abs(h.history["loss"][0] - float(np.mean(ref))) < 1e-3 * max(1.0, abs(np.mean(ref)))
 
 
 @pytest.mark.parametrize("graphs", [False, True])
