@@ -447,3 +447,41 @@ def test_heatmap_batches_per_video_structure():
             assert np.array_equal(tgt[u * n + i], heat[u, i * stride + 10:i * stride + 20])
     assert np.array_equal(dec[:, 0], enc[:, -1])
     assert np.array_equal(enc.sum(axis=(2, 3)), np.ones((U * n, 10, 30)))
+
+
+def test_conv_and_convlstm_against_scipy_correlate():
+    """A third, library-backed statement of the convolutions: Keras 'same' Conv2D = cross-correlation with TF's
+    low = floor(total / 2) padding, here through scipy.signal.correlate2d on explicitly padded planes,
+    incl. an even kernel and a dilated one; then one ConvLSTM2D step assembled from those planes."""
+    from scipy.signal import correlate2d
+    rng = np.random.default_rng(21)
+
+    def conv_ref(x, k, b, dil):
+        B, H, W, Cin = x.shape
+        kh, kw, _, Cout = k.shape
+        kd = np.zeros(((kh - 1) * dil[0] + 1, (kw - 1) * dil[1] + 1, Cin, Cout))
+        kd[::dil[0], ::dil[1]] = k                                            # dilation = zero-stuffed kernel
+        th, tw = kd.shape[0] - 1, kd.shape[1] - 1
+        xp = np.pad(x, ((0, 0), (th // 2, th - th // 2), (tw // 2, tw - tw // 2), (0, 0)))
+        y = np.zeros((B, H, W, Cout))
+        for n in range(B):
+            for co in range(Cout):
+                for ci in range(Cin):
+                    y[n, :, :, co] += correlate2d(xp[n, :, :, ci], kd[:, :, ci, co], mode="valid")
+        return y + b
+
+    for (H, W, kh, kw, dil) in [(6, 5, 3, 3, (1, 1)), (5, 7, 4, 2, (1, 1)), (7, 6, 3, 3, (2, 1)), (1, 9, 1, 5, (1, 1))]:
+        x = rng.standard_normal((2, H, W, 3)); k = rng.standard_normal((kh, kw, 3, 4)); b = rng.standard_normal(4)
+        np.testing.assert_allclose(kn.conv2d(x, k, b, None, dil), conv_ref(x, k, b, dil), atol=1e-12)
+    # one ConvLSTM2D step: z = x (*) K + b + h (*) R, gates i,f,c,o, hard sigmoid
+    H, W, Cin, F = 4, 6, 3, 2
+    x = rng.standard_normal((2, H, W, Cin)); h = rng.standard_normal((2, H, W, F)); c = rng.standard_normal((2, H, W, F))
+    K = rng.standard_normal((3, 3, Cin, 4 * F)); R = rng.standard_normal((3, 3, F, 4 * F)); b = rng.standard_normal(4 * F)
+    z = conv_ref(x, K, b, (2, 2)) + conv_ref(h, R, np.zeros(4 * F), (1, 1))      # the input kernel is dilated, R never
+    hs = lambda v: np.clip(0.2 * v + 0.5, 0, 1)
+    i, f, g, o = hs(z[..., :F]), hs(z[..., F:2 * F]), np.tanh(z[..., 2 * F:3 * F]), hs(z[..., 3 * F:])
+    c1 = f * c + i * g
+    h1 = o * np.tanh(c1)
+    got_h, got_c = kn.convlstm2d_step(x, h, c, K, R, b, dilation=(2, 2))
+    np.testing.assert_allclose(got_h, h1, atol=1e-12)
+    np.testing.assert_allclose(got_c, c1, atol=1e-12)
