@@ -992,3 +992,44 @@ def read_keras_optimizer(path):
         if og is not None:
             ws = [(n, np.array(og[n])) for n in _attr_list(og.attrs, "weight_names")]
         return cfg, ws
+
+
+# ------------------------------------------------------------------------------------------------------------------ #
+# inspection (``python -m longterm360fov_b200.h5lite checkpoint.h5`` ~ ``h5ls -r`` with attributes)
+# ------------------------------------------------------------------------------------------------------------------ #
+def describe(path):
+    """One line per group / dataset / attribute of the file, depth first: what a Keras checkpoint or a sample cache
+    holds, without h5py."""
+    lines = []
+
+    def attrs_of(obj, indent):
+        for k, v in obj.attrs.items():
+            a = np.asarray(v)
+            txt = repr(v.decode("utf8", "replace") if isinstance(v, bytes) else v)
+            if a.ndim:
+                txt = "%s%s" % (a.dtype, list(a.shape))
+            elif len(txt) > 60:
+                txt = txt[:57] + "..."
+            lines.append("%s@%s = %s" % (indent, k, txt))
+
+    def walk(g, indent):
+        attrs_of(g, indent)
+        for k in g.keys():
+            o = g[k]
+            if isinstance(o, Group):
+                lines.append("%s%s/" % (indent, k))
+                walk(o, indent + "  ")
+            else:
+                lines.append("%s%s  %s%s" % (indent, k, o.dtype, list(o.shape) if o.shape is not None else "null"))
+                attrs_of(o, indent + "  ")
+
+    with File(path) as f:
+        walk(f, "")
+    return lines
+
+
+if __name__ == "__main__":
+    import sys
+    for _p in sys.argv[1:]:
+        print(_p)
+        print("\n".join("  " + ln for ln in describe(_p)))

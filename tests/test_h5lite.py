@@ -332,3 +332,14 @@ def test_round_trip_property():
                     else:
                         check(f[k], v)
     run()
+
+
+def test_describe_lists_a_checkpoint(tmp_path):
+    p = str(tmp_path / "ck.h5")
+    a = _FakeModel(0)
+    a.save_weights(p)
+    lines = h5.describe(p)
+    assert "@layer_names = |S13[3]" in lines and "encoder/" in lines
+    assert any(ln.strip() == "kernel:0  float32[6, 256]" for ln in lines)
+    assert any("@keras_version = '2.2.4'" in ln for ln in lines)
+    assert h5.describe(GOLD) == ["testdouble  float64[9, 1]", "  @MATLAB_class = 'double'"]
