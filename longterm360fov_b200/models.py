@@ -241,7 +241,11 @@ class Model:
         model (one group per layer, weights in ``layer.weights`` order, TensorFlow-style ``:0`` names)."""
         layers = collections.OrderedDict()
         for k, a in self.get_weights_dict().items():
-            layers.setdefault(k.split("/", 1)[0], []).append((k + ":0", a))
+            layer = k.split("/", 1)[0]
+            for half in ("_fwd", "_bwd"):                 # Keras keeps both halves of a Bidirectional in ONE layer group
+                if layer.endswith(half):                  # (forward weights first, then backward)
+                    layer = layer[:-len(half)]
+            layers.setdefault(layer, []).append((k + ":0", a))
         return list(layers.items())
 
     def save_weights(self, path):

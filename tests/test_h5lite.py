@@ -343,3 +343,36 @@ def test_describe_lists_a_checkpoint(tmp_path):
     assert any(ln.strip() == "kernel:0  float32[6, 256]" for ln in lines)
     assert any("@keras_version = '2.2.4'" in ln for ln in lines)
     assert h5.describe(GOLD) == ["testdouble  float64[9, 1]", "  @MATLAB_class = 'double'"]
+
+
+def test_bidirectional_layers_are_one_keras_group(tmp_path):
+    """The Bi-LSTM others branch: Keras stores a Bidirectional wrapper as ONE layer with six weights (forward kernel,
+    recurrent kernel, bias, then backward); the model's two halves are saved and matched that way, by name for its
+    own files and by order for a Keras-named checkpoint."""
+    class Bi(_FakeModel):
+        weight_order = ["others_bilstm0_fwd/kernel", "others_bilstm0_fwd/recurrent_kernel", "others_bilstm0_fwd/bias",
+                        "others_bilstm0_bwd/kernel", "others_bilstm0_bwd/recurrent_kernel", "others_bilstm0_bwd/bias",
+                        "decoder_dense/kernel", "decoder_dense/bias"]
+        shapes = [(30, 128), (32, 128), (128,), (30, 128), (32, 128), (128,), (96, 6), (6,)]
+
+    a, b, c = Bi(0), Bi(1), Bi(2)
+    p = str(tmp_path / "bi.h5")
+    a.save_weights(p)
+    layers = h5.read_keras_weights(p)
+    assert [n for n, _ in layers] == ["others_bilstm0", "decoder_dense"] and len(layers[0][1]) == 6
+    b.load_weights(p)
+    for x, y in zip(a.w, b.w):
+        np.testing.assert_array_equal(x, y)
+    w = a.w
+    keras = [("bidirectional_1", [("bidirectional_1/forward_lstm_1/kernel:0", w[0]),
+                                  ("bidirectional_1/forward_lstm_1/recurrent_kernel:0", w[1]),
+                                  ("bidirectional_1/forward_lstm_1/bias:0", w[2]),
+                                  ("bidirectional_1/backward_lstm_1/kernel:0", w[3]),
+                                  ("bidirectional_1/backward_lstm_1/recurrent_kernel:0", w[4]),
+                                  ("bidirectional_1/backward_lstm_1/bias:0", w[5])]),
+             ("dense_1", [("dense_1/kernel:0", w[6]), ("dense_1/bias:0", w[7])])]
+    p2 = str(tmp_path / "keras_bi.h5")
+    h5.write_keras_weights(p2, keras)
+    c.load_weights(p2)
+    for x, y in zip(a.w, c.w):
+        np.testing.assert_array_equal(x, y)
